@@ -1,0 +1,550 @@
+"""CPU oracle: a restatement of the reference's hot path (johnveitch/cpnest).
+
+*** TEST INFRASTRUCTURE ONLY. ***  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.  Nothing under cpnest_b200/
+imports it and the product has no CPU fallback: it fails loudly when the CUDA library is
+missing.
+
+Pinning: the reference ships no golden vectors for this path, so
+this oracle is pinned against outputs of the reference itself: tests/golden/*.json, made
+by tests/golden/gen_golden.py from the unmodified reference built in oracle/_ref
+(tests/test_oracle_golden.py checks every function here against them at 1e-12 or
+bit-exactly).  Citations are `path:line` relative to the reference tree.
+
+Conventions: a point is a 1-D float64 numpy array; an ensemble is an (n, D) array.  Every
+random number is an explicit argument (the reference draws them from the unseeded stdlib
+`random`; fixtures record them), so each function is deterministic.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+LOG2 = math.log(2.0)
+
+# proposal ids, in the order of DefaultProposalCycle (cpnest/proposal.py:354-361)
+WALK, STRETCH, DE, EIGEN = 0, 1, 2, 3
+DEFAULT_WEIGHTS = (5, 5, 10, 10)
+
+
+# ----------------------------------------------------------------------------------------
+# LivePoint scalar semantics (cpnest/parameter.pyx:96-120)
+# ----------------------------------------------------------------------------------------
+def f32(s):
+    """`LivePoint.__mul__/__truediv__` declare the scalar operand as C `float`
+    (parameter.pyx:96,103,109,116): the Python float is rounded to fp32 and widened back
+    to fp64 before it multiplies the fp64 coordinates."""
+    return float(np.float32(s))
+
+
+def lp_mul(v, s, compat=True):
+    return (f32(s) if compat else float(s)) * np.asarray(v, dtype=np.float64)
+
+
+def lp_div(v, s, compat=True):
+    return np.asarray(v, dtype=np.float64) / (f32(s) if compat else float(s))
+
+
+# ----------------------------------------------------------------------------------------
+# Model contract (cpnest/model.py:20-33, 66-82)
+# ----------------------------------------------------------------------------------------
+def in_bounds(x, lo, hi):
+    """model.py:33 -- strict on both sides."""
+    x = np.asarray(x)
+    return bool(np.all((lo < x) & (x < hi)))
+
+
+def flat_log_prior(x, lo, hi):
+    """model.py:66-82"""
+    return 0.0 if in_bounds(x, lo, hi) else -np.inf
+
+
+class OracleModel:
+    """Restatement of one of the reference's test/example models: bounds + log_prior +
+    log_likelihood, as plain functions of a float64 vector.  `functor` is the name of the
+    device functor in cpnest_b200 that must agree with it."""
+
+    def __init__(self, functor, names, bounds, loglike, logprior=None, params=None):
+        self.functor = functor
+        self.names = list(names)
+        self.bounds = [list(map(float, b)) for b in bounds]
+        self.lo = np.array([b[0] for b in self.bounds])
+        self.hi = np.array([b[1] for b in self.bounds])
+        self._ll = loglike
+        self._lp = logprior
+        self.params = params or {}
+
+    @property
+    def D(self):
+        return len(self.names)
+
+    def in_bounds(self, x):
+        return in_bounds(x, self.lo, self.hi)
+
+    def log_prior(self, x):
+        if not self.in_bounds(x):
+            return -np.inf
+        return 0.0 if self._lp is None else float(self._lp(np.asarray(x, dtype=np.float64)))
+
+    def log_likelihood(self, x):
+        with np.errstate(all="ignore"):
+            return float(self._ll(np.asarray(x, dtype=np.float64)))
+
+
+def _gauss_iid(x):
+    # examples/test_50d.py:18-19 ; tests/test_2d.py:15-16 is the D=2 case of the same sum
+    return float(np.sum(-0.5 * x * x - 0.5 * math.log(2.0 * math.pi)))
+
+
+def _eggbox(x):
+    # examples/eggbox.py:19-23
+    t = 1.0
+    for v in x:
+        t *= math.cos(v / 2.0)
+    return (t + 2.0) ** 5.0
+
+
+def _rosenbrock(x):
+    # examples/rosenbrock.py:20-22
+    return float(-np.sum(100.0 * (x[1:] - x[:-1] ** 2.0) ** 2.0 + (1.0 - x[:-1]) ** 2.0))
+
+
+def _ring(x, radius=1.0, thickness=0.1):
+    # tests/test_ring.py:19-23
+    r = math.sqrt(x[0] ** 2 + x[1] ** 2)
+    return -0.5 * (radius - r) ** 2 / thickness ** 2
+
+
+def _gauss_mean_sigma_ll(x):
+    # tests/test_gaussian.py:15-16
+    return -0.5 * x[0] ** 2 / x[1] ** 2 - math.log(x[1]) - 0.5 * math.log(2.0 * math.pi)
+
+
+def _gauss_mean_sigma_lp(x):
+    # tests/test_gaussian.py:18-20
+    return -math.log(x[1]) - math.log(10) - math.log(0.95)
+
+
+def _norm_logpdf(x):
+    # tests/test_1d.py:20-21, tests/test_half_gaussian.py:24-25 (scipy.stats.norm.logpdf)
+    return -0.5 * x[0] * x[0] - 0.5 * math.log(2.0 * math.pi)
+
+
+def _ackley_std(x):
+    # examples/ackley.py:21-28 is NaN/-inf everywhere, so config 3
+    # uses the standard D-dimensional Ackley function, logL = -ackley(x).  No reference parity.
+    D = len(x)
+    return -(-20.0 * math.exp(-0.2 * math.sqrt(float(np.sum(x * x)) / D))
+             - math.exp(float(np.sum(np.cos(2.0 * math.pi * x))) / D) + 20.0 + math.e)
+
+
+def make_mixture(data):
+    data = np.asarray(data, dtype=np.float64)
+
+    def ll(x):
+        # examples/gaussianmixture.py:22-27
+        w = x[4]
+        l1 = np.log(w) - np.log(x[1]) - 0.5 * ((data - x[0]) / x[1]) ** 2
+        l2 = np.log(1.0 - w) - np.log(x[3]) - 0.5 * ((data - x[2]) / x[3]) ** 2
+        return np.logaddexp(l1, l2).sum()
+
+    def lp(x):
+        # examples/gaussianmixture.py:29-31
+        return -math.log(x[1]) - math.log(x[3])
+
+    return OracleModel("gaussian_mixture", ["mean1", "sigma1", "mean2", "sigma2", "weight"],
+                       [[-3, 3], [0.01, 1], [-3, 3], [0.01, 1], [0.0, 1.0]], ll, lp, params=dict(data=data))
+
+
+def make_correlated_gaussian(D, seed=1234, lo=-10.0, hi=10.0):
+    """SURVEY.md section 8d config 4 ('correlated' flavour): N(0, Sigma), Sigma = A A^T with a
+    fixed seed and condition number ~1e2; logZ stays -D log(hi-lo).  Not in the reference;
+    logL = -0.5 |L^-1 x|^2 - sum(log diag L) - D/2 log 2pi with L = chol(Sigma)."""
+    rs = np.random.RandomState(seed)
+    Q, _ = np.linalg.qr(rs.normal(size=(D, D)))
+    ev = np.exp(np.linspace(math.log(0.1), math.log(1.0), D)) ** 2  # sigma in [0.1, 1]
+    Sigma = (Q * ev) @ Q.T
+    Lc = np.linalg.cholesky(Sigma)
+    Linv = np.linalg.inv(Lc)
+    logdet = float(np.sum(np.log(np.diag(Lc))))
+
+    def ll(x):
+        y = Linv @ x
+        return -0.5 * float(y @ y) - logdet - 0.5 * D * math.log(2.0 * math.pi)
+
+    return OracleModel("gaussian_corr", [str(i) for i in range(D)], [[lo, hi]] * D, ll,
+                       params=dict(Linv=np.tril(Linv), logdet=logdet))
+
+
+def builtin_model(name, **kw):
+    """The reference's models by fixture name (tests/golden/models.json keys)."""
+    if name.startswith("gaussian") and name.endswith("d") and name[8:-1].isdigit():
+        D = int(name[8:-1])
+        if D == 1:
+            return OracleModel("gaussian_iid", ["x"], [[-10, 10]], _norm_logpdf)
+        names = ["x", "y"] if D == 2 else [str(i) for i in range(D)]
+        return OracleModel("gaussian_iid", names, [[-10, 10]] * D, _gauss_iid)
+    if name == "half_gaussian":
+        return OracleModel("gaussian_iid", ["x"], [[0, kw.get("xmax", 20)]], _norm_logpdf)
+    if name == "eggbox":
+        return OracleModel("eggbox", ["1", "2"], [[0, 10.0 * math.pi]] * 2, _eggbox)
+    if name.startswith("rosenbrock"):
+        D = int(name[10:-1])
+        return OracleModel("rosenbrock", ["x%d" % i for i in range(D)], [[-5, 5]] * D, _rosenbrock)
+    if name.startswith("ackley"):
+        D = int(name[6:-1])
+        return OracleModel("ackley", ["x%d" % i for i in range(D)], [[-5, 5]] * D, _ackley_std)
+    if name == "ring":
+        return OracleModel("ring", ["x", "y"], [[-2, 2]] * 2, _ring)
+    if name == "gaussian_mean_sigma":
+        return OracleModel("gaussian_mean_sigma", ["mean", "sigma"], [[-5, 5], [0.05, 1]],
+                           _gauss_mean_sigma_ll, _gauss_mean_sigma_lp)
+    if name == "gaussian_mixture":
+        return make_mixture(kw["data"])
+    raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------
+# Proposals (cpnest/proposal.py:209-342)
+# ----------------------------------------------------------------------------------------
+def ensemble_walk(old, ens, idx3, g3, compat=True):
+    """proposal.py:230-235.  idx3: the 3 distinct indices `sample` drew; g3: the 3 N(0,1)."""
+    s = [np.asarray(ens[i], dtype=np.float64) for i in idx3]
+    com = lp_div((s[0] + s[1]) + s[2], 3.0, compat)           # reduce(__add__) / float(Npoints)
+    out = np.array(old, dtype=np.float64)
+    for x, g in zip(s, g3):
+        out = out + lp_mul(x - com, g, compat)                 # out += (x - com) * gauss(0,1)
+    return out, 0.0
+
+
+def ensemble_stretch(old, ens, ia, u, compat=True):
+    """proposal.py:251-261.  u = uniform(-1,1); log_J uses the un-truncated x."""
+    a = np.asarray(ens[ia], dtype=np.float64)
+    x = u * math.log(2.0)
+    Z = math.exp(x)
+    out = a + lp_mul(np.asarray(old, dtype=np.float64) - a, Z, compat)
+    return out, len(out) * x
+
+
+def differential_evolution(old, ens, ia, ib, g, compat=True):
+    """proposal.py:284-287.  g = gauss(1.0, 1e-4) (the value actually drawn)."""
+    a = np.asarray(ens[ia], dtype=np.float64)
+    b = np.asarray(ens[ib], dtype=np.float64)
+    return np.asarray(old, dtype=np.float64) + lp_mul(b - a, g, compat), 0.0
+
+
+def ensemble_eigenvector(old, eigen_values, eigen_vectors, i, g):
+    """proposal.py:336-342 (full fp64: does not go through LivePoint.__mul__)."""
+    jumpsize = math.sqrt(math.fabs(eigen_values[i])) * g
+    out = np.array(old, dtype=np.float64)
+    for k in range(len(out)):
+        out[k] += jumpsize * eigen_vectors[k][i]
+    return out, 0.0
+
+
+def ensemble_covariance(ens):
+    """proposal.py:311-323: np.cov of the D x n array (unbiased); D == 1 uses np.var (ddof=0)
+    (proposal.py:314-318).  Returns (mean, covariance, eigen_values, eigen_vectors)."""
+    X = np.asarray(ens, dtype=np.float64)
+    n, D = X.shape
+    mean = X.mean(axis=0)
+    if D == 1:
+        var = np.atleast_1d(np.var(X[:, 0]))
+        return mean, np.atleast_2d(var), var, np.eye(1)
+    cov = np.cov(X.T)
+    w, v = np.linalg.eigh(cov)
+    return mean, cov, w, v
+
+
+def make_cycle(seed_state, weights=DEFAULT_WEIGHTS, cyclelength=100):
+    """proposal.py:71-75: np.random.choice(proposals, size, p=weights) on the legacy global
+    RandomState.  `seed_state` is a np.random.RandomState positioned where the reference's
+    global state is when ProposalCycle.__init__ runs (right after np.random.seed(seed) for
+    sampler 0)."""
+    w = np.asarray(weights, dtype=np.float64)
+    w = w / w.sum()
+    return seed_state.choice(len(w), size=cyclelength, p=w, replace=True).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------
+# MetropolisHastingsSampler.yield_sample (cpnest/sampler.py:322-358)
+# ----------------------------------------------------------------------------------------
+class TapeReader:
+    """Reads the event tape recorded by tests/golden/gen_golden.py."""
+
+    def __init__(self, events):
+        self.ev = list(events)
+        self.i = 0
+
+    def take(self, kind):
+        k, v = self.ev[self.i]
+        assert k == kind, "tape: expected %s got %s at %d" % (kind, k, self.i)
+        self.i += 1
+        return v
+
+    def exhausted(self):
+        return self.i == len(self.ev)
+
+
+def mh_chain(model, pool, pool_logL, pool_logP, cycle, cycle_idx, eigen_values, eigen_vectors,
+             tape, Nmcmc, maxmcmc, logLmin, compat=True, record=False):
+    """One `next(yield_sample(logLmin))` of the reference's MH sampler.
+
+    `pool*` are python lists mirroring the sampler's deque `evolution_points`: the chain
+    pops the OLDEST member (sampler.py:328), draws proposals from the remaining members
+    (the deque is the ensemble, proposal.py:230,253,284), and appends the result (:351).
+    The lists are modified in place.  Returns dict(out, logL, logP, steps, accepted,
+    cycle_idx, states)."""
+    tp = tape if isinstance(tape, TapeReader) else TapeReader(tape)
+    old = np.array(pool.pop(0), dtype=np.float64)
+    old_logL = pool_logL.pop(0)
+    pool_logP.pop(0)
+    logp_old = model.log_prior(old)                                     # :329
+    cur_logP = logp_old
+    ens = pool
+    D = len(old)
+    steps = accepted = 0
+    states = []
+    logLmax = -np.inf
+    while True:
+        steps += 1                                                       # :333
+        cycle_idx = (cycle_idx + 1) % len(cycle)                         # proposal.py:93 (pre-increment)
+        kind = int(cycle[cycle_idx])
+        if kind == WALK:
+            idx = tp.take("sample")
+            g = [tp.take("gauss") for _ in range(3)]
+            new, log_J = ensemble_walk(old, ens, idx, g, compat)
+        elif kind == STRETCH:
+            ia = tp.take("choice")
+            u = tp.take("uniform")
+            new, log_J = ensemble_stretch(old, ens, ia, u, compat)
+        elif kind == DE:
+            ia, ib = tp.take("sample")
+            g = tp.take("gauss")
+            new, log_J = differential_evolution(old, ens, ia, ib, g, compat)
+        else:
+            i = tp.take("randrange")
+            g = tp.take("gauss")
+            new, log_J = ensemble_eigenvector(old, eigen_values, eigen_vectors, i, g)
+        new_logP = model.log_prior(new)                                  # :335
+        u = tp.take("random")
+        with np.errstate(all="ignore"):
+            test = (new_logP - logp_old + log_J) > (math.log(u) if u > 0 else -np.inf)   # :337
+        if test:
+            new_logL = model.log_likelihood(new)                         # :338
+            if new_logL > logLmin:                                       # :339
+                logLmax = max(logLmax, new_logL)
+                old, old_logL, cur_logP = new, new_logL, new_logP
+                logp_old = new_logP
+                accepted += 1
+        if record:
+            states.append(old.copy())                                    # :345
+        if (steps >= Nmcmc and accepted > 0) or steps >= maxmcmc:        # :347
+            break
+    pool.append(old)
+    pool_logL.append(old_logL)
+    pool_logP.append(cur_logP)
+    return dict(out=old, logL=old_logL, logP=cur_logP, steps=steps, accepted=accepted,
+                cycle_idx=cycle_idx, states=states, logLmax=logLmax)
+
+
+# ----------------------------------------------------------------------------------------
+# Evidence integrator (cpnest/NestedSampling.py:88-144) and helpers (cpnest/nest2pos.py:17-42)
+# ----------------------------------------------------------------------------------------
+def logsubexp(x, y):
+    """nest2pos.py:17-31"""
+    return x + np.log1p(-np.exp(y - x))
+
+
+def log_integrate_log_trap(log_func, log_support):
+    """nest2pos.py:33-42"""
+    log_func = np.asarray(log_func, dtype=np.float64)
+    log_support = np.asarray(log_support, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        log_func_sum = np.logaddexp(log_func[:-1], log_func[1:]) - np.log(2)
+        log_dxs = logsubexp(log_support[:-1], log_support[1:])
+        return float(np.logaddexp.reduce(log_func_sum + log_dxs))
+
+
+class IntegralState:
+    """_NSintegralState (NestedSampling.py:88-144)."""
+
+    def __init__(self, nlive):
+        self.nlive = nlive
+        self.iteration = 0
+        self.logZ = -np.inf
+        self.logw = 0.0
+        self.info = 0.0
+        self.logLs = [-np.inf]
+        self.log_vols = [0.0]
+
+    def increment(self, logL, nlive=None, nreplace=1):
+        if nlive is None:
+            nlive = self.nlive
+        oldZ = self.logZ
+        logt = -nreplace / nlive                                         # :121
+        with np.errstate(all="ignore"):
+            Wt = self.logw + logL + logsubexp(0, logt)                   # :122
+            self.logZ = float(np.logaddexp(self.logZ, Wt))               # :123
+            if np.isfinite(oldZ) and np.isfinite(self.logZ) and np.isfinite(logL):   # :125
+                self.info = float(np.exp(Wt - self.logZ) * logL
+                                  + np.exp(oldZ - self.logZ) * (self.info + oldZ) - self.logZ)
+                if math.isnan(self.info):
+                    self.info = 0.0
+        self.logw += logt                                                # :131
+        self.iteration += 1
+        self.logLs.append(logL)
+        self.log_vols.append(self.logw)
+
+    def finalise(self):
+        """:136-144"""
+        self.logZ = log_integrate_log_trap(np.array(self.logLs), np.array(self.log_vols))
+        return self.logZ
+
+
+def compute_weights(data, Nlive):
+    """nest2pos.py:45-71"""
+    data = np.asarray(data, dtype=np.float64)
+    start_data = np.concatenate(([float("-inf")], data[:-Nlive]))
+    end_data = data[-Nlive:]
+    log_vols_start = np.cumsum(np.ones(len(start_data) + 1) * np.log1p(-1. / Nlive)) - np.log1p(-1. / Nlive)
+    log_vols_end = np.zeros(len(end_data))
+    log_vols_end[-1] = -np.inf
+    log_vols_end[0] = log_vols_start[-1] + np.log1p(-1.0 / Nlive)
+    for i in range(len(end_data) - 1):
+        log_vols_end[i + 1] = log_vols_end[i] + np.log1p(-1.0 / (Nlive - i))
+    log_likes = np.concatenate((start_data, end_data, [end_data[-1]]))
+    log_vols = np.concatenate((log_vols_start, log_vols_end))
+    log_ev = log_integrate_log_trap(log_likes, log_vols)
+    with np.errstate(all="ignore"):
+        log_dXs = logsubexp(log_vols[:-1], log_vols[1:])
+    log_wts = log_likes[1:-1] + log_dXs[:-1]
+    log_wts -= log_ev
+    return log_ev, log_wts
+
+
+def autocorrelation(x):
+    """nest2pos.py:175-187"""
+    x = np.asarray(x, dtype=np.float64)
+    m = x.mean()
+    v = np.var(x)
+    xp = x - m
+    cf = np.fft.fft(xp)
+    sf = cf.conjugate() * cf
+    return np.fft.ifft(sf).real / v / len(x)
+
+
+def acl(x, tolerance=0.01):
+    """nest2pos.py:189-199"""
+    T = 1
+    i = 0
+    acf = autocorrelation(x)
+    while i < len(acf) and acf[i] > tolerance:
+        T += 2 * acf[i]
+        i += 1
+    return T
+
+
+def estimate_nmcmc_on_the_fly(Nmcmc_exact, sub_acceptance, maxmcmc, poolsize, safety=5, tau=None):
+    """sampler.py:156-176.  Returns (Nmcmc_exact, Nmcmc)."""
+    if tau is None:
+        tau = poolsize / safety
+    if sub_acceptance == 0.0:
+        Nmcmc_exact = (1.0 + 1.0 / tau) * Nmcmc_exact
+    else:
+        Nmcmc_exact = (1.0 - 1.0 / tau) * Nmcmc_exact + (safety / tau) * (2.0 / sub_acceptance - 1.0)
+    Nmcmc_exact = float(min(Nmcmc_exact, maxmcmc))
+    return Nmcmc_exact, max(safety, int(Nmcmc_exact))
+
+
+# ----------------------------------------------------------------------------------------
+# NestedSampler.consume_sample (cpnest/NestedSampling.py:318-375) on a sorted logL list
+# ----------------------------------------------------------------------------------------
+class NSLoopOracle:
+    """The reference's batch step on the (sorted) live logL list.  `replacements` is the
+    list of accepted new logL values in the order the reference receives them (k reversed).
+    mode='reference': one integrator increment per batch, logt = -K/N at the K-th worst
+    (NestedSampling.py:324-326).  mode='sequential': per-point shrinkage -1/(N-i) over the
+    K sorted dead points, the rule the reference itself applies in its final sweep
+    (NestedSampling.py:474-476); this is cpnest_b200's default (SURVEY.md hard part 5)."""
+
+    def __init__(self, live_logL, mode="reference"):
+        self.N = len(live_logL)
+        self.keys = sorted(float(v) for v in live_logL)
+        self.state = IntegralState(self.N)
+        self.mode = mode
+        self.iteration = 0
+        self.insertion_indices = []
+        self.nested_logL = []
+        self.condition = np.inf
+
+    def batch(self, K, replacements, logLmax):
+        import bisect
+        logLmin = self.keys[K - 1]                                       # :374
+        if self.mode == "reference":
+            self.state.increment(logLmin, nreplace=K)                    # :326
+        else:
+            for i in range(K):
+                self.state.increment(self.keys[i], nlive=self.N - i)
+        self.nested_logL.extend(self.keys[:K])                           # :327
+        with np.errstate(all="ignore"):
+            self.condition = float(np.logaddexp(self.state.logZ, logLmax - self.iteration / float(self.N))
+                                   - self.state.logZ)                    # :332
+        assert len(replacements) == K
+        for j, k in enumerate(reversed(range(K))):
+            self.iteration += 1
+            new = float(replacements[j])
+            assert new > logLmin
+            index = bisect.bisect(self.keys, new)                        # KeyOrderedList.search :42-46
+            self.keys.insert(index, new)
+            self.insertion_indices.append((index - K) / (self.N - k - 1))   # :350
+        del self.keys[:K]                                                # :366
+        return logLmin
+
+    def survivor_ranks(self, K, replacements):
+        """cpnest_b200's insertion statistic: rank of each replacement among the N-K
+        survivors only (bisect-right), normalised by N-K.  Coincides with the reference's
+        (index - nreplace)/(Nlive - k - 1) when K == 1."""
+        import bisect
+        surv = self.keys[K:]
+        return [bisect.bisect(surv, float(v)) / (self.N - K) for v in replacements]
+
+    def finish(self):
+        """NestedSampling.py:472-480"""
+        for i, l in enumerate(self.keys):
+            self.state.increment(l, nlive=self.N - i)
+            self.nested_logL.append(l)
+        rect = self.state.logZ
+        return rect, self.state.info, self.state.finalise()
+
+
+# ----------------------------------------------------------------------------------------
+# Philox4x32-10 (Salmon et al. 2011, "Parallel random numbers: as easy as 1, 2, 3"; the
+# generator cpnest_b200's kernels use instead of the reference's unseeded MT19937) and the
+# integer -> real transforms of cpnest_b200/csrc/rng.cuh, for known-answer tests.
+# ----------------------------------------------------------------------------------------
+PHILOX_M0, PHILOX_M1 = 0xD2511F53, 0xCD9E8D57
+PHILOX_W0, PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(ctr, key):
+    c = [int(v) & 0xFFFFFFFF for v in ctr]
+    k = [int(v) & 0xFFFFFFFF for v in key]
+    for _ in range(10):
+        p0 = PHILOX_M0 * c[0]
+        p1 = PHILOX_M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF,
+             ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + PHILOX_W0) & 0xFFFFFFFF, (k[1] + PHILOX_W1) & 0xFFFFFFFF]
+    return c
+
+
+def u32_to_unit_open(r):
+    """(r + 0.5) * 2^-32 in fp64: uniform on (0,1), never 0 or 1."""
+    return (int(r) + 0.5) * (1.0 / 4294967296.0)
+
+
+def u32_to_index(r, n):
+    """mulhi(r, n): uniform index in [0, n)."""
+    return (int(r) * int(n)) >> 32
