@@ -1,0 +1,875 @@
+// C-ABI of cpnest_b200 (include/cpnest_b200.h): host-side driver of the device kernels.
+// The host only enqueues work; the nested-sampling state (threshold, evidence, chain length,
+// termination flag) lives on the device, so a run proceeds without per-batch host round trips.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cpnest_b200.h"
+#include "ensemble.cuh"
+#include "eval_kernel.cuh"
+#include "launch.h"
+#include "mh_kernel.cuh"
+#include "ns_kernels.cuh"
+
+using namespace cpn;
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+typedef int (*mh_fn)(int, int, int, const MHParams&, cudaStream_t);
+typedef int (*eval_fn)(int, int, const EvalParams&, cudaStream_t);
+static const mh_fn kMH[CPN_NUM_FUNCTORS] = {launch_mh_gauss_iid, launch_mh_gauss_corr, launch_mh_eggbox,
+                                            launch_mh_rosenbrock, launch_mh_ackley, launch_mh_ring,
+                                            launch_mh_gauss_mean_sigma, launch_mh_gauss_mixture};
+static const eval_fn kEval[CPN_NUM_FUNCTORS] = {launch_eval_gauss_iid, launch_eval_gauss_corr, launch_eval_eggbox,
+                                                launch_eval_rosenbrock, launch_eval_ackley, launch_eval_ring,
+                                                launch_eval_gauss_mean_sigma, launch_eval_gauss_mixture};
+
+struct cpn_ctx {
+    cpn_config cfg;
+    int D, Dp, N, G, E;
+    cudaStream_t stream;
+    double *d_lo, *d_hi, *d_blob;
+    double *d_x, *d_logL, *d_logP;
+    int* d_order[2];
+    double* d_skeys[2];
+    int cur;
+    int Npad;
+    double* d_sort_keys;
+    int* d_sort_idx;
+    double *d_new_x, *d_new_logL, *d_new_logP;
+    int *d_new_steps, *d_new_acc, *d_rank;
+    double* d_snew;
+    double *d_start_x, *d_start_logL, *d_start_logP;
+    double *d_mean, *d_cov, *d_covwork, *d_V, *d_eigval, *d_eigvec, *d_eigscale, *d_mean_partial, *d_cov_partial;
+    uint8_t* d_cycle;
+    int cycle_len;
+    NSState* d_state;
+    long long log_cap;          // capacity (rows) of the dead / history / insertion logs
+    double *d_dead_x, *d_dead_logL, *d_dead_logP, *d_hist_logL, *d_hist_logvol, *d_ins;
+    long long dead_upper;       // host upper bound of rows used in the logs
+    long long batches_enqueued;
+    unsigned long long chain_counter;
+    long long chains_since_stats;
+    LSE* d_trap_partial;
+    double* d_scalar;
+    double* d_rec;              // [N][D+2] record scratch of the host protocol
+    NSState* h_state;           // pinned
+    cudaEvent_t ev;
+    bool live_ready;
+};
+
+template <class T>
+static int dalloc(T** p, size_t n) {
+    CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+
+static int pick_config(int D, int lanes, int functor, int* G, int* E) {
+    static const int cfgs[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {4, 4}, {8, 2}, {8, 8}, {16, 4},
+                                  {32, 1}, {32, 2}, {32, 4}, {32, 8}};
+    const int ncfg = sizeof(cfgs) / sizeof(cfgs[0]);
+    if (lanes > 0) {
+        int best = -1;
+        for (int i = 0; i < ncfg; ++i)
+            if (cfgs[i][0] == lanes && cfgs[i][0] * cfgs[i][1] >= D && (best < 0 || cfgs[i][1] < cfgs[best][1])) best = i;
+        if (best < 0) return fail("no kernel configuration with %d lanes per chain covers dim=%d", lanes, D);
+        *G = cfgs[best][0]; *E = cfgs[best][1];
+        return 0;
+    }
+    if (functor == CPN_GAUSS_MIXTURE && D <= 32) { *G = 32; *E = 1; return 0; }   // lanes split the data sum
+    if (D <= 1) { *G = 1; *E = 1; }
+    else if (D <= 2) { *G = 1; *E = 2; }
+    else if (D <= 4) { *G = 1; *E = 4; }
+    else if (D <= 8) { *G = 1; *E = 8; }
+    else if (D <= 16) { *G = 4; *E = 4; }
+    else if (D <= 64) { *G = 8; *E = 8; }
+    else if (D <= 128) { *G = 32; *E = 4; }
+    else if (D <= 256) { *G = 32; *E = 8; }
+    else return fail("dim=%d exceeds the largest kernel configuration (256)", D);
+    return 0;
+}
+
+extern "C" const char* cpn_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cpn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static int grow_logs(cpn_ctx* c, long long need) {
+    if (need <= c->log_cap) return 0;
+    long long cap = std::max(need, c->log_cap * 2);
+    double *nx, *nl, *np, *hl, *hv, *ni;
+    CK(cudaMalloc((void**)&nx, (size_t)cap * c->Dp * sizeof(double)));
+    CK(cudaMalloc((void**)&nl, (size_t)cap * sizeof(double)));
+    CK(cudaMalloc((void**)&np, (size_t)cap * sizeof(double)));
+    CK(cudaMalloc((void**)&hl, (size_t)cap * sizeof(double)));
+    CK(cudaMalloc((void**)&hv, (size_t)cap * sizeof(double)));
+    CK(cudaMalloc((void**)&ni, (size_t)cap * sizeof(double)));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->log_cap > 0) {
+        const size_t n = (size_t)c->log_cap;
+        CK(cudaMemcpy(nx, c->d_dead_x, n * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(nl, c->d_dead_logL, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(np, c->d_dead_logP, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(hl, c->d_hist_logL, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(hv, c->d_hist_logvol, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(ni, c->d_ins, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        cudaFree(c->d_dead_x); cudaFree(c->d_dead_logL); cudaFree(c->d_dead_logP);
+        cudaFree(c->d_hist_logL); cudaFree(c->d_hist_logvol); cudaFree(c->d_ins);
+    }
+    c->d_dead_x = nx; c->d_dead_logL = nl; c->d_dead_logP = np;
+    c->d_hist_logL = hl; c->d_hist_logvol = hv; c->d_ins = ni;
+    c->log_cap = cap;
+    return 0;
+}
+
+static int fetch_state(cpn_ctx* c) {
+    CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(NSState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->dead_upper = c->h_state->iteration;
+    return 0;
+}
+
+static int push_state(cpn_ctx* c) {
+    CK(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(NSState), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static void init_state(cpn_ctx* c, NSState* s) {
+    memset(s, 0, sizeof *s);
+    s->logZ = -INFINITY;
+    s->B = 0.0;
+    s->info = 0.0;
+    s->logw = 0.0;
+    s->logLmin = -INFINITY;
+    s->logLmax = -INFINITY;
+    s->condition = INFINITY;
+    s->tolerance = 0.1;                                   // NestedSampler(stopping=0.1)
+    const int n0 = c->cfg.nmcmc_init > 0 ? c->cfg.nmcmc_init : std::max(1, c->cfg.maxmcmc / 10);   // sampler.py:79
+    s->nmcmc = std::min(n0, c->cfg.maxmcmc);
+    s->nmcmc_exact = (double)s->nmcmc;
+    s->nmcmc_safety = c->cfg.nmcmc_safety > 0 ? c->cfg.nmcmc_safety : 5.0;
+    s->nmcmc_tau = (double)c->N / s->nmcmc_safety;        // tau = poolsize / safety (sampler.py:166)
+    s->maxmcmc = c->cfg.maxmcmc;
+    s->adapt = c->cfg.adapt_nmcmc;
+}
+
+extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double* hi, const void* blob,
+                          size_t blob_bytes, cpn_ctx** out) {
+    if (!cfg || !lo || !hi || !out) return fail("cpn_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("cpn_create: no CUDA device available (cpnest_b200 has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("cpn_create: device %d out of range (%d devices)", cfg->device, ndev);
+    if (cfg->dim < 1) return fail("cpn_create: dim must be >= 1");
+    if (cfg->nlive < 4) return fail("cpn_create: nlive must be >= 4");
+    if (cfg->maxmcmc < 1) return fail("cpn_create: maxmcmc must be >= 1");
+    if (cfg->functor < 0 || cfg->functor >= CPN_NUM_FUNCTORS) return fail("cpn_create: unknown functor %d", cfg->functor);
+    for (int d = 0; d < cfg->dim; ++d)
+        if (!(lo[d] < hi[d])) return fail("cpn_create: bounds[%d] = (%g, %g) is empty", d, lo[d], hi[d]);
+    // functor-specific blob checks
+    const size_t nb = blob_bytes / sizeof(double);
+    switch (cfg->functor) {
+        case CPN_GAUSS_IID: if (nb != 3) return fail("gauss_iid blob must be {mu, 1/sigma, -log(sigma)-log(2pi)/2}"); break;
+        case CPN_GAUSS_CORR: if (nb != 1 + (size_t)cfg->dim * cfg->dim) return fail("gauss_corr blob must be {logdet, Linv[D*D]}"); break;
+        case CPN_RING: if (nb != 2 || cfg->dim != 2) return fail("ring needs dim=2 and blob {radius, thickness}"); break;
+        case CPN_GAUSS_MEAN_SIGMA: if (cfg->dim != 2) return fail("gauss_mean_sigma needs dim=2"); break;
+        case CPN_GAUSS_MIXTURE:
+            if (cfg->dim != 5 || nb < 2 || (size_t)((const double*)blob)[0] + 1 != nb) return fail("gauss_mixture needs dim=5 and blob {n, data[n]}");
+            break;
+        default: break;
+    }
+    CK(cudaSetDevice(cfg->device));
+    cpn_ctx* c = new cpn_ctx();
+    memset(c, 0, sizeof *c);
+    c->cfg = *cfg;
+    c->D = cfg->dim;
+    c->Dp = (cfg->dim + 3) & ~3;
+    c->N = cfg->nlive;
+    if (pick_config(c->D, cfg->lanes, cfg->functor, &c->G, &c->E)) { delete c; return 1; }
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    const int N = c->N, D = c->D, Dp = c->Dp;
+    if (dalloc(&c->d_lo, D) || dalloc(&c->d_hi, D) || dalloc(&c->d_blob, std::max<size_t>(nb, 1))) return 1;
+    CK(cudaMemcpy(c->d_lo, lo, D * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_hi, hi, D * sizeof(double), cudaMemcpyHostToDevice));
+    if (nb) CK(cudaMemcpy(c->d_blob, blob, nb * sizeof(double), cudaMemcpyHostToDevice));
+    if (dalloc(&c->d_x, (size_t)N * Dp) || dalloc(&c->d_logL, N) || dalloc(&c->d_logP, N)) return 1;
+    for (int b = 0; b < 2; ++b)
+        if (dalloc(&c->d_order[b], N) || dalloc(&c->d_skeys[b], N)) return 1;
+    c->Npad = 1;
+    while (c->Npad < N) c->Npad <<= 1;
+    if (dalloc(&c->d_sort_keys, c->Npad) || dalloc(&c->d_sort_idx, c->Npad)) return 1;
+    if (dalloc(&c->d_new_x, (size_t)N * Dp) || dalloc(&c->d_new_logL, N) || dalloc(&c->d_new_logP, N) ||
+        dalloc(&c->d_new_steps, N) || dalloc(&c->d_new_acc, N) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
+        return 1;
+    if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
+    if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, (size_t)D * D) ||
+        dalloc(&c->d_V, (size_t)D * D) || dalloc(&c->d_eigval, D) || dalloc(&c->d_eigvec, (size_t)D * Dp) ||
+        dalloc(&c->d_eigscale, D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
+        dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))
+        return 1;
+    if (dalloc(&c->d_state, 1) || dalloc(&c->d_trap_partial, 256) || dalloc(&c->d_scalar, 4) ||
+        dalloc(&c->d_rec, (size_t)N * (D + 2)))
+        return 1;
+    CK(cudaMallocHost((void**)&c->h_state, sizeof(NSState)));
+    // DefaultProposalCycle weights 5:5:10:10 laid out deterministically until cpn_set_cycle is called
+    {
+        std::vector<uint8_t> cyc;
+        const uint8_t pat[6] = {CPN_WALK, CPN_STRETCH, CPN_DE, CPN_DE, CPN_EIGEN, CPN_EIGEN};
+        for (int i = 0; i < 96; ++i) cyc.push_back(pat[i % 6]);
+        c->cycle_len = (int)cyc.size();
+        if (dalloc(&c->d_cycle, 4096)) return 1;
+        CK(cudaMemcpy(c->d_cycle, cyc.data(), cyc.size(), cudaMemcpyHostToDevice));
+    }
+    init_state(c, c->h_state);
+    if (push_state(c)) return 1;
+    if (grow_logs(c, std::max<long long>(4LL * N, 1 << 16))) return 1;
+    *out = c;
+    return 0;
+}
+
+extern "C" void cpn_destroy(cpn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
+                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_new_x, c->d_new_logL,
+                    c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
+                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_eigval, c->d_eigvec, c->d_eigscale,
+                    c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_state, c->d_dead_x, c->d_dead_logL,
+                    c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    cudaEventDestroy(c->ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int cpn_set_cycle(cpn_ctx* c, const uint8_t* cycle, int32_t len) {
+    if (!c || !cycle || len < 1 || len > 4096) return fail("cpn_set_cycle: bad arguments");
+    for (int i = 0; i < len; ++i)
+        if (cycle[i] > CPN_EIGEN) return fail("cpn_set_cycle: unknown proposal id %d at %d", cycle[i], i);
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(c->d_cycle, cycle, len, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->cycle_len = len;
+    return 0;
+}
+
+// ---- sort the live set by logL (OrderedLivePoints.__init__) -------------------------------------------
+static int sort_live(cpn_ctx* c) {
+    const int T = 256, Np = c->Npad;
+    k_sort_fill<<<(Np + T - 1) / T, T, 0, c->stream>>>(c->d_logL, c->N, Np, c->d_sort_keys, c->d_sort_idx);
+    for (int k = 2; k <= Np; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+            k_bitonic_step<<<(Np + T - 1) / T, T, 0, c->stream>>>(c->d_sort_keys, c->d_sort_idx, Np, j, k);
+    CKL();
+    CK(cudaMemcpyAsync(c->d_skeys[c->cur], c->d_sort_keys, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_order[c->cur], c->d_sort_idx, c->N * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int cpn_update_ensemble_stats(cpn_ctx* c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, N = c->N;
+    if (D > kStatThreads) return fail("ensemble statistics support dim <= %d", kStatThreads);
+    k_mean_partial<<<kStatBlocks, kStatThreads, 0, c->stream>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
+    k_mean_final<<<(D + 127) / 128, 128, 0, c->stream>>>(c->d_mean_partial, kStatBlocks, N, D, c->d_mean);
+    k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), c->stream>>>(
+        c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
+    k_cov_final<<<(D * D + 127) / 128, 128, 0, c->stream>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
+    CK(cudaMemcpyAsync(c->d_covwork, c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    k_jacobi_eigh<<<1, 256, 0, c->stream>>>(c->d_covwork, c->d_V, D, c->Dp, c->d_eigval, c->d_eigvec, c->d_eigscale);
+    CKL();
+    c->chains_since_stats = 0;
+    return 0;
+}
+
+extern "C" int cpn_get_ensemble_stats(cpn_ctx* c, double* mean, double* cov, double* eigval, double* eigvec) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int D = c->D;
+    if (mean) CK(cudaMemcpy(mean, c->d_mean, D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (cov) CK(cudaMemcpy(cov, c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (eigval) CK(cudaMemcpy(eigval, c->d_eigval, D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (eigvec) {
+        // numpy layout: eigvec[k][i] = component k of eigenvector i
+        std::vector<double> rows((size_t)D * c->Dp);
+        CK(cudaMemcpy(rows.data(), c->d_eigvec, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < D; ++i)
+            for (int k = 0; k < D; ++k) eigvec[(size_t)k * D + i] = rows[(size_t)i * c->Dp + k];
+    }
+    return 0;
+}
+
+static void fill_mh(cpn_ctx* c, MHParams* p) {
+    memset(p, 0, sizeof *p);
+    p->ens_x = c->d_x; p->ens_logL = c->d_logL; p->ens_logP = c->d_logP;
+    p->ens_n = c->N; p->Dp = c->Dp; p->D = c->D;
+    p->order = c->d_order[c->cur];
+    p->lo = c->d_lo; p->hi = c->d_hi;
+    p->cycle = c->d_cycle; p->cycle_len = c->cycle_len;
+    p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
+    p->eig_scale = c->d_eigscale; p->eig_vec = c->d_eigvec;
+    p->state = c->d_state;
+    p->maxmcmc = c->cfg.maxmcmc;
+    p->chain_base = c->chain_counter;
+    p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
+    p->blob = c->d_blob;
+    p->n_out = 1;
+    p->out_x[0] = c->d_new_x; p->out_logL[0] = c->d_new_logL; p->out_logP[0] = c->d_new_logP;
+    p->out_steps[0] = c->d_new_steps; p->out_acc[0] = c->d_new_acc;
+    p->counters = c->d_state->batch;
+}
+
+extern "C" int cpn_init_prior(cpn_ctx* c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    init_state(c, c->h_state);
+    if (push_state(c)) return 1;
+    c->dead_upper = 0; c->batches_enqueued = 0; c->chain_counter = 0; c->cur = 0;
+    EvalParams e;
+    memset(&e, 0, sizeof e);
+    e.x = c->d_x; e.logL = c->d_logL; e.logP = c->d_logP; e.n = c->N; e.D = c->D; e.Dp = c->Dp;
+    e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob; e.draw = 1;
+    e.seed_lo = (uint32_t)c->cfg.seed; e.seed_hi = (uint32_t)(c->cfg.seed >> 32);
+    e.id_base = 0x4000000000000000ull;
+    if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
+    CKL();
+    // Sampler.reset (sampler.py:129-135): evolve every member with logLmin = -inf so the set follows
+    // the prior, adapting the chain length on the way.  Two passes, ensemble statistics refreshed.
+    for (int pass = 0; pass < 2; ++pass) {
+        if (cpn_update_ensemble_stats(c)) return 1;
+        MHParams p;
+        fill_mh(c, &p);
+        p.start_mode = START_SELF;
+        p.n_skip = 0;
+        p.use_override = 0;
+        p.j0 = 0; p.j1 = c->N;
+        p.chain_base = 0x2000000000000000ull + (unsigned long long)pass * (unsigned long long)c->N;
+        p.cycle_pos0 = pass * 13 % c->cycle_len;
+        if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
+        CKL();
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N);
+        CK(cudaMemcpyAsync(c->d_x, c->d_new_x, (size_t)c->N * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_logL, c->d_new_logL, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_logP, c->d_new_logP, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (sort_live(c)) return 1;
+    if (cpn_update_ensemble_stats(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    c->live_ready = true;
+    return 0;
+}
+
+extern "C" int cpn_set_live(cpn_ctx* c, const double* rows, int32_t n) {
+    if (!c || !rows) return fail("null argument");
+    if (n != c->N) return fail("cpn_set_live: got %d rows, nlive is %d", n, c->N);
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp, N = c->N;
+    std::vector<double> x((size_t)N * Dp, 0.0), l(N), lp(N);
+    for (int i = 0; i < N; ++i) {
+        for (int d = 0; d < D; ++d) x[(size_t)i * Dp + d] = rows[(size_t)i * (D + 2) + d];
+        l[i] = rows[(size_t)i * (D + 2) + D];
+        lp[i] = rows[(size_t)i * (D + 2) + D + 1];
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->d_x, x.data(), x.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_logL, l.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_logP, lp.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+    if (sort_live(c)) return 1;
+    if (cpn_update_ensemble_stats(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    c->live_ready = true;
+    return 0;
+}
+
+static int check_K(cpn_ctx* c, int K) {
+    if (!c) return fail("null context");
+    if (!c->live_ready) return fail("live set not initialised: call cpn_init_prior or cpn_set_live first");
+    if (K < 1 || K > c->N - 3) return fail("K=%d must be in [1, nlive-3]", K);
+    return 0;
+}
+
+extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
+    if (check_K(c, K)) return 1;
+    CK(cudaSetDevice(c->cfg.device));
+    if (grow_logs(c, c->dead_upper + K + c->N)) return 1;
+    AccParams a;
+    memset(&a, 0, sizeof a);
+    a.st = c->d_state; a.skeys = c->d_skeys[c->cur]; a.N = c->N; a.K = K; a.mode = c->cfg.ns_mode;
+    a.final_sweep = 0; a.nlive_run = c->N; a.hist_logL = c->d_hist_logL; a.hist_logvol = c->d_hist_logvol;
+    a.update_threshold = 1;
+    k_ns_accumulate<<<1, kAccThreads, 0, c->stream>>>(a);
+    CKL();
+    c->dead_upper += K;
+    return 0;
+}
+
+extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
+    if (check_K(c, K)) return 1;
+    CK(cudaSetDevice(c->cfg.device));
+    MHParams p;
+    fill_mh(c, &p);
+    p.start_mode = START_SURVIVOR;
+    p.n_skip = K;
+    p.j0 = 0; p.j1 = K;
+    if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
+    CKL();
+    c->chain_counter += (unsigned long long)K;
+    c->chains_since_stats += K;
+    c->batches_enqueued += 1;
+    return 0;
+}
+
+extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
+    if (check_K(c, K)) return 1;
+    CK(cudaSetDevice(c->cfg.device));
+    const int T = 256;
+    k_rank_new<<<(K + T - 1) / T, T, T * sizeof(double), c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
+    MergeParams m;
+    memset(&m, 0, sizeof m);
+    m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp;
+    m.order_in = c->d_order[c->cur]; m.skeys_in = c->d_skeys[c->cur];
+    m.order_out = c->d_order[c->cur ^ 1]; m.skeys_out = c->d_skeys[c->cur ^ 1];
+    m.rank_new = c->d_rank; m.snew = c->d_snew;
+    m.live_x = c->d_x; m.live_logL = c->d_logL; m.live_logP = c->d_logP;
+    m.new_x = c->d_new_x; m.new_logL = c->d_new_logL; m.new_logP = c->d_new_logP;
+    m.dead_x = c->d_dead_x; m.dead_logL = c->d_dead_logL; m.dead_logP = c->d_dead_logP;
+    m.insertion = c->d_ins;
+    k_merge_commit<<<(c->N + T - 1) / T, T, 0, c->stream>>>(m);
+    CKL();
+    c->cur ^= 1;
+    return 0;
+}
+
+extern "C" int cpn_ns_step(cpn_ctx* c, int32_t K) {
+    if (check_K(c, K)) return 1;
+    // refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254)
+    if (c->chains_since_stats >= std::max(1, c->N / 4))
+        if (cpn_update_ensemble_stats(c)) return 1;
+    if (cpn_select_and_accumulate(c, K)) return 1;
+    if (cpn_evolve_batch(c, K)) return 1;
+    return cpn_insert_batch(c, K);
+}
+
+extern "C" int cpn_run(cpn_ctx* c, int32_t K, int64_t max_batches, double tolerance, int64_t* batches_done) {
+    if (check_K(c, K)) return 1;
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    const long long b0 = c->h_state->batches;
+    c->h_state->tolerance = tolerance;
+    if (push_state(c)) return 1;
+    const int chunk = 8;
+    long long enq = 0;
+    while (max_batches <= 0 || enq < max_batches) {
+        const int n = (max_batches > 0) ? (int)std::min<long long>(chunk, max_batches - enq) : chunk;
+        for (int i = 0; i < n; ++i)
+            if (cpn_ns_step(c, K)) return 1;
+        enq += n;
+        if (fetch_state(c)) return 1;
+        if (c->h_state->done || c->h_state->stop_next) break;
+    }
+    if (batches_done) *batches_done = c->h_state->batches - b0;
+    return 0;
+}
+
+extern "C" int cpn_finalise(cpn_ctx* c, double* logZ_rect, double* logZ_trap) {
+    if (!c) return fail("null context");
+    if (!c->live_ready) return fail("live set not initialised");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    const long long dead0 = c->h_state->iteration;
+    if (grow_logs(c, dead0 + c->N + 1)) return 1;
+    AccParams a;
+    memset(&a, 0, sizeof a);
+    a.st = c->d_state; a.skeys = c->d_skeys[c->cur]; a.N = c->N; a.K = c->N; a.mode = CPN_NS_SEQUENTIAL;
+    a.final_sweep = 1; a.nlive_run = c->N; a.hist_logL = c->d_hist_logL; a.hist_logvol = c->d_hist_logvol;
+    a.update_threshold = 1;
+    k_ns_accumulate<<<1, kAccThreads, 0, c->stream>>>(a);
+    const int T = 256;
+    k_append_live_sorted<<<(c->N + T - 1) / T, T, 0, c->stream>>>(c->d_order[c->cur], c->N, c->Dp, c->d_x, c->d_logL,
+                                                                 c->d_logP, c->d_dead_x, c->d_dead_logL, c->d_dead_logP, dead0);
+    CKL();
+    if (fetch_state(c)) return 1;
+    if (logZ_rect) *logZ_rect = c->h_state->logZ;
+    const long long nh = c->h_state->n_hist;
+    k_trap_partial<<<256, 256, 0, c->stream>>>(c->d_hist_logL, c->d_hist_logvol, nh, c->d_trap_partial);
+    k_trap_final<<<1, 32, 0, c->stream>>>(c->d_trap_partial, 256, c->d_scalar);
+    CKL();
+    double z;
+    CK(cudaMemcpyAsync(&z, c->d_scalar, sizeof z, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (logZ_trap) *logZ_trap = z;
+    c->h_state->logZ = z;                       // self.logZ = self.state.finalise() (NestedSampling.py:479-480)
+    c->h_state->done = 1;
+    if (push_state(c)) return 1;
+    c->live_ready = false;                      // the live set has been consumed
+    return 0;
+}
+
+extern "C" int cpn_synchronize(cpn_ctx* c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
+    if (!c || !o) return fail("null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    const NSState* s = c->h_state;
+    o->logZ = s->logZ; o->info = s->info; o->logw = s->logw; o->logLmin = s->logLmin; o->logLmax = s->logLmax;
+    o->condition = s->condition; o->nmcmc_exact = s->nmcmc_exact; o->iteration = s->iteration; o->n_hist = s->n_hist;
+    o->batches = s->batches;
+    o->total_steps = (int64_t)(s->totals[0] + s->batch[0]);
+    o->total_accepted = (int64_t)(s->totals[1] + s->batch[1]);
+    o->total_evals = (int64_t)(s->totals[2] + s->batch[2]);
+    o->failed_chains = (int64_t)(s->totals[3] + s->batch[3]);
+    o->nmcmc = s->nmcmc; o->done = s->done;
+    return 0;
+}
+
+extern "C" int cpn_set_nmcmc(cpn_ctx* c, int32_t nmcmc) {
+    if (!c) return fail("null context");
+    if (nmcmc < 1 || nmcmc > c->cfg.maxmcmc) return fail("nmcmc=%d must be in [1, maxmcmc=%d]", nmcmc, c->cfg.maxmcmc);
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    c->h_state->nmcmc = nmcmc;
+    c->h_state->nmcmc_exact = (double)nmcmc;
+    return push_state(c);
+}
+
+extern "C" int cpn_get_live(cpn_ctx* c, double* rows) {
+    if (!c || !rows) return fail("null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int N = c->N, D = c->D, Dp = c->Dp;
+    std::vector<double> x((size_t)N * Dp), l(N), lp(N);
+    std::vector<int> ord(N);
+    CK(cudaMemcpy(x.data(), c->d_x, x.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(l.data(), c->d_logL, N * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lp.data(), c->d_logP, N * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ord.data(), c->d_order[c->cur], N * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; ++i) {
+        const int s = ord[i];
+        if (s < 0 || s >= N) return fail("corrupt live order at %d: %d", i, s);
+        for (int d = 0; d < D; ++d) rows[(size_t)i * (D + 2) + d] = x[(size_t)s * Dp + d];
+        rows[(size_t)i * (D + 2) + D] = l[s];
+        rows[(size_t)i * (D + 2) + D + 1] = lp[s];
+    }
+    return 0;
+}
+
+extern "C" int64_t cpn_num_dead(cpn_ctx* c) {
+    if (!c) return -1;
+    cudaSetDevice(c->cfg.device);
+    if (fetch_state(c)) return -1;
+    return c->h_state->iteration;
+}
+
+extern "C" int cpn_get_dead(cpn_ctx* c, int64_t first, int64_t n, double* rows, double* log_vols) {
+    if (!c || !rows) return fail("null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    if (first < 0 || n < 0 || first + n > c->h_state->iteration) return fail("cpn_get_dead: range [%lld,%lld) outside %lld dead points", (long long)first, (long long)(first + n), c->h_state->iteration);
+    const int D = c->D, Dp = c->Dp;
+    std::vector<double> x((size_t)n * Dp), l(n), lp(n);
+    CK(cudaMemcpy(x.data(), c->d_dead_x + (size_t)first * Dp, x.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(l.data(), c->d_dead_logL + first, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lp.data(), c->d_dead_logP + first, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) {
+        for (int d = 0; d < D; ++d) rows[(size_t)i * (D + 2) + d] = x[(size_t)i * Dp + d];
+        rows[(size_t)i * (D + 2) + D] = l[i];
+        rows[(size_t)i * (D + 2) + D + 1] = lp[i];
+    }
+    if (log_vols) {
+        if (c->cfg.ns_mode != CPN_NS_SEQUENTIAL) return fail("per-point log volumes exist only in sequential mode");
+        CK(cudaMemcpy(log_vols, c->d_hist_logvol + first, n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int64_t cpn_num_insertion_indices(cpn_ctx* c) {
+    if (!c) return -1;
+    cudaSetDevice(c->cfg.device);
+    if (fetch_state(c)) return -1;
+    return c->h_state->n_ins;
+}
+
+extern "C" int cpn_get_insertion_indices(cpn_ctx* c, int64_t first, int64_t n, double* out) {
+    if (!c || !out) return fail("null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    if (first < 0 || n < 0 || first + n > c->h_state->n_ins) return fail("insertion index range out of bounds");
+    CK(cudaMemcpy(out, c->d_ins + first, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int cpn_get_last_batch(cpn_ctx* c, int32_t K, double* rows, int32_t* steps, int32_t* accepted) {
+    if (!c) return fail("null context");
+    if (K < 1 || K > c->N) return fail("K out of range");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int D = c->D, Dp = c->Dp;
+    if (rows) {
+        std::vector<double> x((size_t)K * Dp), l(K), lp(K);
+        CK(cudaMemcpy(x.data(), c->d_new_x, x.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(l.data(), c->d_new_logL, K * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(lp.data(), c->d_new_logP, K * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < K; ++i) {
+            for (int d = 0; d < D; ++d) rows[(size_t)i * (D + 2) + d] = x[(size_t)i * Dp + d];
+            rows[(size_t)i * (D + 2) + D] = l[i];
+            rows[(size_t)i * (D + 2) + D + 1] = lp[i];
+        }
+    }
+    if (steps) CK(cudaMemcpy(steps, c->d_new_steps, K * sizeof(int), cudaMemcpyDeviceToHost));
+    if (accepted) CK(cudaMemcpy(accepted, c->d_new_acc, K * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- host protocol: requests in, replies out (sampler.py:233-246) ---------------------------------------
+__global__ void k_unpack_records(const double* rec, int n, int D, int Dp, double* x, double* logL, double* logP) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * Dp) return;
+    const int r = i / Dp, d = i % Dp;
+    x[i] = (d < D) ? rec[(size_t)r * (D + 2) + d] : 0.0;
+    if (d == 0) {
+        logL[r] = rec[(size_t)r * (D + 2) + D];
+        logP[r] = rec[(size_t)r * (D + 2) + D + 1];
+    }
+}
+__global__ void k_pack_records(const double* x, const double* logL, const double* logP, int n, int D, int Dp, double* rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (D + 2)) return;
+    const int r = i / (D + 2), d = i % (D + 2);
+    rec[i] = (d < D) ? x[(size_t)r * Dp + d] : (d == D ? logL[r] : logP[r]);
+}
+
+extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nmcmc, const double* requests,
+                               double* replies, int32_t* steps, int32_t* accepted) {
+    if (!c || !requests || !replies) return fail("null argument");
+    if (!c->live_ready) return fail("live set not initialised");
+    if (K < 1 || K > c->N) return fail("K=%d must be in [1, nlive]", K);
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    double* d_rec = c->d_rec;
+    const size_t need = (size_t)K * (D + 2);
+    CK(cudaMemcpyAsync(d_rec, requests, need * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int T = 256;
+    k_unpack_records<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(d_rec, K, D, Dp, c->d_start_x, c->d_start_logL, c->d_start_logP);
+    MHParams p;
+    fill_mh(c, &p);
+    p.start_mode = START_GIVEN;
+    p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+    p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = std::max(1, std::min(nmcmc, c->cfg.maxmcmc));
+    p.j0 = 0; p.j1 = K;
+    if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
+    k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K);
+    k_pack_records<<<((int)need + T - 1) / T, T, 0, c->stream>>>(c->d_new_x, c->d_new_logL, c->d_new_logP, K, D, Dp, d_rec);
+    CKL();
+    CK(cudaMemcpyAsync(replies, d_rec, need * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (steps) CK(cudaMemcpyAsync(steps, c->d_new_steps, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (accepted) CK(cudaMemcpyAsync(accepted, c->d_new_acc, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->chain_counter += (unsigned long long)K;
+    c->batches_enqueued += 1;
+    return 0;
+}
+
+// ---- parity entry points --------------------------------------------------------------------------------------
+extern "C" int cpn_eval_model(cpn_ctx* c, const double* x, int32_t n, double* logL, double* logP) {
+    if (!c || !x || !logL || !logP || n < 1) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    std::vector<double> xp((size_t)n * Dp, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < D; ++d) xp[(size_t)i * Dp + d] = x[(size_t)i * D + d];
+    double *dx, *dl, *dp;
+    if (dalloc(&dx, xp.size()) || dalloc(&dl, n) || dalloc(&dp, n)) return 1;
+    CK(cudaMemcpy(dx, xp.data(), xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    EvalParams e;
+    memset(&e, 0, sizeof e);
+    e.x = dx; e.logL = dl; e.logP = dp; e.n = n; e.D = D; e.Dp = Dp; e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob;
+    if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(logL, dl, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(logP, dp, n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dl); cudaFree(dp);
+    return 0;
+}
+
+extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start,
+                             const double* eigval, const double* eigvec, int32_t cycle_idx, const double* tape,
+                             int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes,
+                             double* out, int32_t* steps, int32_t* accepted, double* states) {
+    if (!c || !ensemble || !start || !tape || !out) return fail("null argument");
+    if (P < 3 || C < 1 || maxmcmc < 1) return fail("bad sizes");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    int G, E;
+    if (pick_config(D, lanes > 0 ? lanes : c->G, c->cfg.functor, &G, &E)) return 1;
+    std::vector<double> ex((size_t)P * Dp, 0.0), sx((size_t)C * Dp, 0.0), sl(C), sp(C), ev((size_t)D * Dp, 0.0), es(D, 0.0);
+    for (int i = 0; i < P; ++i)
+        for (int d = 0; d < D; ++d) ex[(size_t)i * Dp + d] = ensemble[(size_t)i * D + d];
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) sx[(size_t)i * Dp + d] = start[(size_t)i * (D + 2) + d];
+        sl[i] = start[(size_t)i * (D + 2) + D];
+        sp[i] = start[(size_t)i * (D + 2) + D + 1];
+    }
+    if (eigval && eigvec)
+        for (int i = 0; i < D; ++i) {
+            es[i] = sqrt(fabs(eigval[i]));                                   // proposal.py:339
+            for (int k = 0; k < D; ++k) ev[(size_t)i * Dp + k] = eigvec[(size_t)k * D + i];
+        }
+    double *dex, *dsx, *dsl, *dsp, *dev, *des, *dtape, *dox, *dol, *dop, *dstates = nullptr, *dEL, *dEP;
+    int *dst, *dac;
+    if (dalloc(&dex, ex.size()) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) || dalloc(&dev, ev.size()) ||
+        dalloc(&des, D) || dalloc(&dtape, (size_t)C * maxmcmc * 8) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) ||
+        dalloc(&dop, C) || dalloc(&dst, C) || dalloc(&dac, C) || dalloc(&dEL, P) || dalloc(&dEP, P))
+        return 1;
+    if (states && dalloc(&dstates, (size_t)C * maxmcmc * D)) return 1;
+    CK(cudaMemcpy(dex, ex.data(), ex.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsl, sl.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsp, sp.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dev, ev.data(), ev.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(des, es.data(), D * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtape, tape, (size_t)C * maxmcmc * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    MHParams p;
+    memset(&p, 0, sizeof p);
+    p.ens_x = dex; p.ens_logL = dEL; p.ens_logP = dEP; p.ens_n = P; p.Dp = Dp; p.D = D;
+    p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
+    p.lo = c->d_lo; p.hi = c->d_hi;
+    p.cycle = c->d_cycle; p.cycle_len = c->cycle_len; p.cycle_pos0 = cycle_idx;
+    p.eig_scale = des; p.eig_vec = dev;
+    p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.maxmcmc = maxmcmc;
+    p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
+    p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
+    p.counters = nullptr; p.tape = dtape; p.compat = compat; p.states = dstates;
+    if (kMH[c->cfg.functor](G, E, 1, p, c->stream)) return fail("no replay kernel for G=%d E=%d", G, E);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
+    CK(cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
+        out[(size_t)i * (D + 2) + D] = ol[i];
+        out[(size_t)i * (D + 2) + D + 1] = op[i];
+    }
+    if (steps) CK(cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (accepted) CK(cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (states) CK(cudaMemcpy(states, dstates, (size_t)C * maxmcmc * D * sizeof(double), cudaMemcpyDeviceToHost));
+    void* fr[] = {dex, dsx, dsl, dsp, dev, des, dtape, dox, dol, dop, dst, dac, dEL, dEP, dstates};
+    for (void* q : fr)
+        if (q) cudaFree(q);
+    return 0;
+}
+
+extern "C" int cpn_stage_replacements(cpn_ctx* c, int32_t K, const double* rows) {
+    if (!c || !rows) return fail("null argument");
+    if (K < 1 || K > c->N) return fail("K out of range");
+    CK(cudaSetDevice(c->cfg.device));
+    const size_t need = (size_t)K * (c->D + 2);
+    CK(cudaMemcpyAsync(c->d_rec, rows, need * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int T = 256;
+    k_unpack_records<<<(K * c->Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rec, K, c->D, c->Dp, c->d_new_x, c->d_new_logL,
+                                                                   c->d_new_logP);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int cpn_ns_reset(cpn_ctx* c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    init_state(c, c->h_state);
+    c->dead_upper = 0;
+    return push_state(c);
+}
+
+extern "C" int cpn_ns_increment(cpn_ctx* c, const double* logL, int32_t K, int32_t nlive, int32_t ns_mode) {
+    if (!c || !logL || K < 1 || nlive < K) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (grow_logs(c, c->dead_upper + K + 1)) return 1;
+    double* d;
+    if (dalloc(&d, K)) return 1;
+    CK(cudaMemcpy(d, logL, K * sizeof(double), cudaMemcpyHostToDevice));
+    AccParams a;
+    memset(&a, 0, sizeof a);
+    a.st = c->d_state; a.skeys = d; a.N = nlive; a.K = K; a.mode = ns_mode; a.final_sweep = 1; a.nlive_run = c->N;
+    a.hist_logL = c->d_hist_logL; a.hist_logvol = c->d_hist_logvol; a.update_threshold = 0;
+    k_ns_accumulate<<<1, kAccThreads, 0, c->stream>>>(a);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    c->dead_upper += K;
+    return 0;
+}
+
+extern "C" int cpn_ns_trapezoid(cpn_ctx* c, double* logZ) {
+    if (!c || !logZ) return fail("null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    k_trap_partial<<<256, 256, 0, c->stream>>>(c->d_hist_logL, c->d_hist_logvol, c->h_state->n_hist, c->d_trap_partial);
+    k_trap_final<<<1, 32, 0, c->stream>>>(c->d_trap_partial, 256, c->d_scalar);
+    CKL();
+    CK(cudaMemcpyAsync(logZ, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+__global__ void k_philox_kat(const uint32_t* ctr, uint32_t k0, uint32_t k1, int n, uint32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Philox4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = r.v[k];
+}
+
+extern "C" int cpn_philox(cpn_ctx* c, const uint32_t* ctr, const uint32_t* key, int32_t n, uint32_t* out) {
+    if (!c || !ctr || !key || !out || n < 1) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    uint32_t *dc, *dout;
+    if (dalloc(&dc, (size_t)4 * n) || dalloc(&dout, (size_t)4 * n)) return 1;
+    CK(cudaMemcpy(dc, ctr, (size_t)4 * n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    k_philox_kat<<<(n + 127) / 128, 128, 0, c->stream>>>(dc, key[0], key[1], n, dout);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, dout, (size_t)4 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    cudaFree(dc); cudaFree(dout);
+    return 0;
+}

@@ -1,0 +1,18 @@
+// launcher table shared between the per-model translation units and api.cu
+#pragma once
+#include <cuda_runtime.h>
+namespace cpn {
+struct MHParams;
+struct EvalParams;
+#define CPN_DECLARE_MODEL(NAME)                                                          \
+    int launch_mh_##NAME(int G, int E, int replay, const MHParams& p, cudaStream_t s);   \
+    int launch_eval_##NAME(int G, int E, const EvalParams& p, cudaStream_t s);
+CPN_DECLARE_MODEL(gauss_iid)
+CPN_DECLARE_MODEL(gauss_corr)
+CPN_DECLARE_MODEL(eggbox)
+CPN_DECLARE_MODEL(rosenbrock)
+CPN_DECLARE_MODEL(ackley)
+CPN_DECLARE_MODEL(ring)
+CPN_DECLARE_MODEL(gauss_mean_sigma)
+CPN_DECLARE_MODEL(gauss_mixture)
+}  // namespace cpn

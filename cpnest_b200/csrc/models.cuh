@@ -1,0 +1,196 @@
+// Device functors for the Model contract (cpnest/model.py:20-33, 55-82): strict box test,
+// log_prior, log_likelihood.  One functor per model the reference ships (tests/ and examples/);
+// the Python callables of those models remain the parity oracle (tests/test_gpu_models.py).
+//
+// A functor sees the point distributed over the G lanes of its chain group: coordinate d is
+// x[d / G] of lane d % G.  log_likelihood/log_prior return the same value on every lane.
+#pragma once
+#include <math.h>
+#include "group.cuh"
+
+namespace cpn {
+
+#define CPN_NEG_INF (__longlong_as_double(0xfff0000000000000LL))
+#define CPN_HALF_LOG_2PI 0.91893853320467274178
+
+struct ModelCtx {
+    const double* blob;   // functor parameters (device)
+    int D;                // dimension
+    double* scratch;      // per-chain shared-memory scratch, >= D doubles (functors with kScratch)
+};
+
+template <int G, int E>
+__device__ __forceinline__ bool valid_dim(const Group<G>& g, int e, int D) { return g.lane + e * G < D; }
+
+// ---- flat prior, model.py:66-82 -------------------------------------------------------------
+struct FlatPrior {
+    template <int G, int E>
+    static __device__ __forceinline__ double log_prior(const Group<G>&, const double (&)[E], const ModelCtx&) {
+        return 0.0;
+    }
+};
+
+// ---- iid Gaussian: examples/test_50d.py:18-19 (sum_i -x_i^2/2 - log(2pi)/2), tests/test_2d.py:15-16,
+//      tests/test_1d.py:20-21 and tests/test_half_gaussian.py:24-25 (scipy norm.logpdf) ----------------
+struct GaussIid : FlatPrior {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        const double mu = m.blob[0], inv_sigma = m.blob[1], c = m.blob[2];   // c = -log(sigma) - log(2pi)/2
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double t = (x[e] - mu) * inv_sigma;
+            double term = -0.5 * t * t + c;
+            acc += valid_dim<G, E>(g, e, m.D) ? term : 0.0;
+        }
+        return g.sum(acc);
+    }
+};
+
+// ---- correlated Gaussian N(0, Sigma), Sigma = L L^T: logL = -|L^-1 x|^2/2 - sum log L_ii - D/2 log 2pi
+//      (not in the reference).  blob = {logdet, Linv[D][D] row-major lower} -------
+struct GaussCorr : FlatPrior {
+    static constexpr bool kScratch = true;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        const int D = m.D;
+        const double* Linv = m.blob + 1;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int d = g.lane + e * G;
+            if (d < D) m.scratch[d] = x[e];
+        }
+        __syncwarp();
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int r = g.lane + e * G;
+            if (r < D) {
+                const double* row = Linv + (size_t)r * D;
+                double y = 0.0;
+                for (int c = 0; c <= r; ++c) y = fma(__ldg(row + c), m.scratch[c], y);
+                acc = fma(y, y, acc);
+            }
+        }
+        __syncwarp();
+        return -0.5 * g.sum(acc) - m.blob[0] - D * CPN_HALF_LOG_2PI;
+    }
+};
+
+// ---- eggbox: examples/eggbox.py:19-23  (2 + prod cos(x_i/2))^5 ------------------------------
+struct Eggbox : FlatPrior {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        double p = 1.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) p *= valid_dim<G, E>(g, e, m.D) ? cos(x[e] / 2.0) : 1.0;
+        p = g.prod(p);
+        return pow(p + 2.0, 5.0);
+    }
+};
+
+// ---- Rosenbrock: examples/rosenbrock.py:20-22 ------------------------------------------------
+struct Rosenbrock : FlatPrior {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            // x_{d+1}: same slot of the next lane, or slot e+1 of lane 0 when this is the last lane
+            double nxt;
+            if (G == 1) {
+                nxt = (e + 1 < E) ? x[(e + 1 < E) ? e + 1 : e] : 0.0;
+            } else {
+                double a = __shfl_sync(FULL, x[e], (g.lane + 1) & (G - 1), G);
+                double b = (e + 1 < E) ? __shfl_sync(FULL, x[(e + 1 < E) ? e + 1 : e], 0, G) : 0.0;
+                nxt = (g.lane == G - 1) ? b : a;
+            }
+            int d = g.lane + e * G;
+            double u = nxt - x[e] * x[e];
+            double v = 1.0 - x[e];
+            double term = 100.0 * u * u + v * v;
+            acc += (d < m.D - 1) ? term : 0.0;
+        }
+        return -g.sum(acc);
+    }
+};
+
+// ---- standard D-dim Ackley, logL = -ackley(x) (examples/ackley.py:21-28 as written
+//      has no finite value anywhere, so there is no reference parity for this functor) --------------------
+struct Ackley : FlatPrior {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        double s2 = 0.0, sc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            bool ok = valid_dim<G, E>(g, e, m.D);
+            s2 += ok ? x[e] * x[e] : 0.0;
+            sc += ok ? cos(2.0 * 3.14159265358979323846 * x[e]) : 0.0;
+        }
+        s2 = g.sum(s2);
+        sc = g.sum(sc);
+        double a = -20.0 * exp(-0.2 * sqrt(s2 / m.D)) - exp(sc / m.D) + 20.0 + 2.71828182845904523536;
+        return -a;
+    }
+};
+
+// ---- ring: tests/test_ring.py:19-23 ; blob = {radius, thickness} ------------------------------
+struct Ring : FlatPrior {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        double a = coord<G, E>(g, x, 0), b = coord<G, E>(g, x, 1);
+        double r = sqrt(a * a + b * b);
+        double dr = m.blob[0] - r;
+        return -0.5 * (dr * dr) / (m.blob[1] * m.blob[1]);
+    }
+};
+
+// ---- (mean, sigma) Gaussian with a 1/sigma prior: tests/test_gaussian.py:15-20 ----------------
+struct GaussMeanSigma {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx&) {
+        double mean = coord<G, E>(g, x, 0), sigma = coord<G, E>(g, x, 1);
+        return -0.5 * (mean * mean) / (sigma * sigma) - log(sigma) - CPN_HALF_LOG_2PI;
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ double log_prior(const Group<G>& g, const double (&x)[E], const ModelCtx&) {
+        double sigma = coord<G, E>(g, x, 1);
+        return -log(sigma) - 2.30258509299404568402 /*log 10*/ - (-0.05129329438755058) /*log 0.95*/;
+    }
+};
+
+// ---- two-component mixture over a data vector: examples/gaussianmixture.py:22-31 ;
+//      blob = {n_data, data[n_data]} ; parameters (mean1, sigma1, mean2, sigma2, weight) ----------
+struct GaussMixture {
+    static constexpr bool kScratch = false;
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        const double m1 = coord<G, E>(g, x, 0), s1 = coord<G, E>(g, x, 1), m2 = coord<G, E>(g, x, 2),
+                     s2 = coord<G, E>(g, x, 3), w = coord<G, E>(g, x, 4);
+        const int n = (int)m.blob[0];
+        const double* data = m.blob + 1;
+        const double c1 = log(w) - log(s1), c2 = log(1.0 - w) - log(s2);
+        const double i1 = 1.0 / s1, i2 = 1.0 / s2;
+        double acc = 0.0;
+        for (int i = g.lane; i < n; i += G) {
+            double d = __ldg(data + i);
+            double t1 = (d - m1) * i1, t2 = (d - m2) * i2;
+            double l1 = c1 - 0.5 * t1 * t1, l2 = c2 - 0.5 * t2 * t2;
+            double hi = fmax(l1, l2), lo = fmin(l1, l2);
+            acc += hi + log1p(exp(lo - hi));          // np.logaddexp
+        }
+        return g.sum(acc);
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ double log_prior(const Group<G>& g, const double (&x)[E], const ModelCtx&) {
+        return -log(coord<G, E>(g, x, 1)) - log(coord<G, E>(g, x, 3));
+    }
+};
+
+}  // namespace cpn

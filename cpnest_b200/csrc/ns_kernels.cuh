@@ -1,0 +1,407 @@
+// Nested-sampling driver kernels: what the parent process of the reference does between two
+// rounds of sampler requests (cpnest/NestedSampling.py):
+//   k_ns_accumulate   get_worst_n_live_points (:368-375) + _NSintegralState.increment (:111-134)
+//                     + termination condition (:332, :451) + Nmcmc moving average (sampler.py:156-176)
+//   k_rank_new        ordering of the K replacements (KeyOrderedList.search, :42-46)
+//   k_merge_commit    insert_live_point / remove_n_worst_points (:74-85) + insertion indices (:347-350)
+//                     + nested_samples.extend (:327)
+//   k_bitonic_step    initial sort of the live set (OrderedLivePoints.__init__, :71-72)
+//   k_trap_*          _NSintegralState.finalise (:136-144) = nest2pos.log_integrate_log_trap
+// The live set stays in HBM as rows live_x[N][Dp] + logL[N] + logP[N]; its order is a
+// permutation `order` (ascending logL) with the sorted keys beside it, double-buffered.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "cpnest_b200.h"
+#include "state.cuh"
+
+namespace cpn {
+
+constexpr int kAccThreads = 1024;
+
+__device__ __forceinline__ double d_logaddexp(double a, double b) {
+    // numpy logaddexp semantics
+    if (a == b) return a + 0.69314718055994530942;
+    double d = a - b;
+    if (d > 0) return a + log1p(exp(-d));
+    if (d <= 0) return b + log1p(exp(d));
+    return a + b;  // NaN
+}
+
+// online log-sum-exp accumulator of (weight, weight*value) pairs in the log domain
+struct LSE {
+    double m, s, t;   // max, sum exp(w - m), sum exp(w - m) * v
+    __device__ __forceinline__ void init() { m = -INFINITY; s = 0.0; t = 0.0; }
+    __device__ __forceinline__ void push(double w, double v) {
+        if (!(w > -INFINITY)) return;
+        if (w > m) {
+            double f = exp(m - w);
+            s = s * f + 1.0;
+            t = t * f + v;
+            m = w;
+        } else {
+            double f = exp(w - m);
+            s += f;
+            t += f * v;
+        }
+    }
+    __device__ __forceinline__ void merge(const LSE& o) {
+        if (!(o.m > -INFINITY)) return;
+        if (!(m > -INFINITY)) { *this = o; return; }
+        if (o.m > m) {
+            double f = exp(m - o.m);
+            s = s * f + o.s;
+            t = t * f + o.t;
+            m = o.m;
+        } else {
+            double f = exp(o.m - m);
+            s += o.s * f;
+            t += o.t * f;
+        }
+    }
+};
+
+__device__ __forceinline__ LSE block_reduce_lse(LSE v, LSE* sh) {
+    // fixed-shape tree: deterministic for a given block size
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            LSE a = sh[tid];
+            a.merge(sh[tid + s]);
+            sh[tid] = a;
+        }
+        __syncthreads();
+    }
+    LSE r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// exclusive block scan of one double per thread (Hillis-Steele in shared memory)
+__device__ __forceinline__ double block_exclusive_scan(double v, double* sh, double* total) {
+    const int tid = threadIdx.x, n = blockDim.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int off = 1; off < n; off <<= 1) {
+        double add = (tid >= off) ? sh[tid - off] : 0.0;
+        __syncthreads();
+        sh[tid] += add;
+        __syncthreads();
+    }
+    double incl = sh[tid];
+    *total = sh[n - 1];
+    __syncthreads();
+    return incl - v;
+}
+
+struct AccParams {
+    NSState* st;
+    const double* skeys;   // sorted live logL (ascending), or the given dead logL values
+    int N;                 // live points enclosing the first dead point of this batch
+    int K;                 // dead points of this batch
+    int mode;              // cpn_ns_mode
+    int final_sweep;       // 1: NestedSampling.py:472-476 (ignores done, no threshold update)
+    int nlive_run;         // Nlive of the run (denominator of the termination condition)
+    double* hist_logL;     // state.logLs[1:]
+    double* hist_logvol;   // state.log_vols[1:]
+    int update_threshold;  // 0 for the raw integrator parity entry
+};
+
+__global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p) {
+    __shared__ LSE sh_lse[kAccThreads];
+    __shared__ double sh_scan[kAccThreads];
+    __shared__ double sh_carry;
+    NSState* st = p.st;
+    const int tid = threadIdx.x;
+    if (!p.final_sweep) {
+        if (st->done) return;
+        if (st->stop_next) {               // `while self.condition > self.tolerance` (NestedSampling.py:451)
+            __syncthreads();
+            if (tid == 0) st->done = 1;
+            return;
+        }
+    }
+    const double logw0 = st->logw, logZ0 = st->logZ, B0 = st->B;
+    const long long hist0 = st->n_hist;
+    const int K = p.K, N = p.N;
+    LSE acc;
+    acc.init();
+    double logw_end;
+    if (p.mode == CPN_NS_REFERENCE) {
+        // one increment at the K-th worst with logt = -K/N (NestedSampling.py:121, 324-326)
+        const double logt = -(double)K / (double)N;
+        const double logL = p.skeys[K - 1];
+        const double Wt = logw0 + logL + log1p(-exp(logt));
+        if (tid == 0) {
+            const bool first = !(logZ0 > -INFINITY);
+            acc.push(Wt, first ? Wt : logL);
+            p.hist_logL[hist0] = logL;
+            p.hist_logvol[hist0] = logw0 + logt;
+        }
+        logw_end = logw0 + logt;
+    } else {
+        // per-point shrinkage -1/(N-j) (the reference's final-sweep rule, NestedSampling.py:474-476)
+        if (tid == 0) sh_carry = 0.0;
+        __syncthreads();
+        for (int base = 0; base < K; base += kAccThreads) {
+            const int j = base + tid;
+            const bool in = j < K;
+            const double logt = in ? -1.0 / (double)(N - j) : 0.0;
+            double tile_total;
+            const double excl = block_exclusive_scan(logt, sh_scan, &tile_total);
+            const double carry = sh_carry;
+            if (in) {
+                const double logw_j = logw0 + (carry + excl);
+                const double logL = p.skeys[j];
+                const double Wt = logw_j + logL + log1p(-exp(logt));
+                // the reference leaves info at 0 on the increment that makes logZ finite, i.e. its
+                // recurrence starts from info + logZ = Wt rather than logL (NestedSampling.py:125-128)
+                bool first = false;
+                if (!(logZ0 > -INFINITY) && Wt > -INFINITY) {
+                    if (j == 0) first = true;
+                    else first = !(p.skeys[j - 1] > -INFINITY);
+                }
+                acc.push(Wt, first ? Wt : logL);
+                p.hist_logL[hist0 + j] = logL;
+                p.hist_logvol[hist0 + j] = logw_j + logt;
+            }
+            __syncthreads();
+            if (tid == 0) sh_carry = carry + tile_total;
+            __syncthreads();
+        }
+        logw_end = logw0 + sh_carry;
+    }
+    const LSE tot = block_reduce_lse(acc, sh_lse);
+    if (tid != 0) return;
+
+    double logZ = logZ0, B = B0, info = st->info;
+    if (tot.m > -INFINITY) {
+        const double Wsum = tot.m + log(tot.s);
+        logZ = d_logaddexp(logZ0, Wsum);
+        const double fnew = exp(tot.m - logZ);
+        B = fnew * tot.t + ((logZ0 > -INFINITY) ? exp(logZ0 - logZ) * B0 : 0.0);
+        info = B - logZ;
+        if (isnan(info)) { info = 0.0; B = logZ; }
+    }
+    st->logZ = logZ;
+    st->B = B;
+    st->info = info;
+    st->logw = logw_end;
+    st->n_hist = hist0 + ((p.mode == CPN_NS_REFERENCE) ? 1 : K);
+    if (!p.update_threshold) { st->iteration += K; return; }
+
+    const long long it0 = st->iteration;
+    st->iteration = it0 + K;
+    if (p.final_sweep) return;
+    st->batches += 1;
+    st->n_ins += K;                                                  // one insertion index per replacement
+    st->logLmin = p.skeys[K - 1];                                    // NestedSampling.py:374
+    const double logLmax = p.skeys[N - 1];
+    st->logLmax = logLmax;
+    const double cond = d_logaddexp(logZ, logLmax - (double)it0 / (double)p.nlive_run) - logZ;   // :332
+    st->condition = cond;
+    if (!(cond > st->tolerance)) st->stop_next = 1;
+}
+
+// acceptance-driven chain length, applied once per batch with the batch mean acceptance
+// (sampler.py:156-176: ACL = 2/acc - 1, times safety, moving average with decay tau chains).
+__device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains) {
+    const unsigned long long steps = st->batch[0], accd = st->batch[1];
+    for (int i = 0; i < 4; ++i) { st->totals[i] += st->batch[i]; st->batch[i] = 0; }
+    if (!st->adapt || steps == 0) return;
+    const double safety = st->nmcmc_safety;
+    double tau = st->nmcmc_tau / (double)chains;       // decay measured in batches
+    if (tau < 1.0) tau = 1.0;
+    const double sub_acc = (double)accd / (double)steps;
+    double ne = st->nmcmc_exact;
+    if (sub_acc == 0.0) ne = (1.0 + 1.0 / tau) * ne;
+    else ne = (1.0 - 1.0 / tau) * ne + (safety / tau) * (2.0 / sub_acc - 1.0);
+    ne = fmin(ne, (double)st->maxmcmc);
+    st->nmcmc_exact = ne;
+    int n = (int)ne;
+    if (n < (int)safety) n = (int)safety;
+    if (n > st->maxmcmc) n = st->maxmcmc;
+    st->nmcmc = n;
+}
+__global__ void k_adapt_nmcmc(NSState* st, int chains) {
+    if (st->done) return;
+    adapt_nmcmc(st, chains);
+}
+
+// rank of each replacement among the K replacements (ties broken by chain index), and the
+// sorted copy of their keys.
+__global__ void k_rank_new(const NSState* st, const double* __restrict__ new_logL, int K,
+                           int* __restrict__ rank, double* __restrict__ snew) {
+    if (st->done) return;
+    extern __shared__ double tile[];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const double key = (q < K) ? new_logL[q] : 0.0;
+    int r = 0;
+    for (int base = 0; base < K; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        tile[threadIdx.x] = (i < K) ? new_logL[i] : INFINITY;
+        __syncthreads();
+        const int lim = min((int)blockDim.x, K - base);
+        for (int t = 0; t < lim; ++t) {
+            const double o = tile[t];
+            r += (o < key) || (o == key && base + t < q);
+        }
+        __syncthreads();
+    }
+    if (q < K) {
+        rank[q] = r;
+        snew[r] = key;
+    }
+}
+
+struct MergeParams {
+    const NSState* st;
+    NSState* st_w;
+    int N, K, Dp;
+    const int* order_in;       // [N]
+    const double* skeys_in;    // [N]
+    int* order_out;
+    double* skeys_out;
+    const int* rank_new;       // [K]
+    const double* snew;        // [K] sorted replacement keys
+    double* live_x;            // [N][Dp]
+    double* live_logL;
+    double* live_logP;
+    const double* new_x;       // [K][Dp]
+    const double* new_logL;
+    const double* new_logP;
+    double* dead_x;            // rows appended at dead0
+    double* dead_logL;
+    double* dead_logP;
+    double* insertion;         // one entry per replacement, appended
+};
+
+__device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) {   // #elements < v
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_d(const double* a, int n, double v) {   // #elements <= v
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One thread per live-set position.  Threads [0,K) own a dead point + its replacement,
+// threads [K,N) own a survivor.  bisect-right semantics: a replacement goes after equal keys.
+__global__ void k_merge_commit(const MergeParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = p.N, K = p.K;
+    if (i >= N) return;
+    if (p.st->done) {              // run finished: keep the order valid in the other buffer
+        p.order_out[i] = p.order_in[i];
+        p.skeys_out[i] = p.skeys_in[i];
+        return;
+    }
+    // k_ns_accumulate of this batch already advanced the counters
+    const long long dead0 = p.st->iteration - K, ins0 = p.st->n_ins - K;
+    if (i >= K) {
+        const double key = p.skeys_in[i];
+        const int pos = (i - K) + lower_bound_d(p.snew, K, key);
+        p.order_out[pos] = p.order_in[i];
+        p.skeys_out[pos] = key;
+    } else {
+        const int slot = p.order_in[i];
+        const double key = p.new_logL[i];
+        const int nle = upper_bound_d(p.skeys_in + K, N - K, key);
+        const int pos = p.rank_new[i] + nle;
+        p.order_out[pos] = slot;
+        p.skeys_out[pos] = key;
+        p.insertion[ins0 + i] = (double)nle / (double)(N - K);
+        // nested_samples.extend(worst) then overwrite the slot with the replacement
+        double* lrow = p.live_x + (size_t)slot * p.Dp;
+        double* drow = p.dead_x + (size_t)(dead0 + i) * p.Dp;
+        const double* nrow = p.new_x + (size_t)i * p.Dp;
+        for (int d = 0; d < p.Dp; ++d) {
+            drow[d] = lrow[d];
+            lrow[d] = nrow[d];
+        }
+        p.dead_logL[dead0 + i] = p.live_logL[slot];
+        p.dead_logP[dead0 + i] = p.live_logP[slot];
+        p.live_logL[slot] = key;
+        p.live_logP[slot] = p.new_logP[i];
+        if (i == 0) adapt_nmcmc(p.st_w, K);
+    }
+}
+
+// copy the (sorted) remaining live points into the dead log: the final sweep
+__global__ void k_append_live_sorted(const int* order, int N, int Dp, const double* live_x, const double* live_logL,
+                                     const double* live_logP, double* dead_x, double* dead_logL, double* dead_logP,
+                                     long long dead0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int slot = order[i];
+    for (int d = 0; d < Dp; ++d) dead_x[(size_t)(dead0 + i) * Dp + d] = live_x[(size_t)slot * Dp + d];
+    dead_logL[dead0 + i] = live_logL[slot];
+    dead_logP[dead0 + i] = live_logP[slot];
+}
+
+// ---- full sort of the live set (init only): bitonic network on (key, slot) pairs ------------------
+__global__ void k_sort_fill(const double* logL, int N, int Npad, double* keys, int* idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    keys[i] = (i < N) ? logL[i] : INFINITY;
+    idx[i] = (i < N) ? i : 0x7fffffff;
+}
+__global__ void k_bitonic_step(double* keys, int* idx, int Npad, int j, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    const int l = i ^ j;
+    if (l > i) {
+        const double a = keys[i], b = keys[l];
+        const int ia = idx[i], ib = idx[l];
+        const bool up = (i & k) == 0;
+        // total order on (key, slot); NaN keys sort first so they are removed first
+        const bool a_gt_b = (a > b) || (a == b && ia > ib) || (isnan(b) && !isnan(a));
+        if (a_gt_b == up) {
+            keys[i] = b; keys[l] = a;
+            idx[i] = ib; idx[l] = ia;
+        }
+    }
+}
+
+// ---- log-trapezoid over the history (nest2pos.py:33-42), two-stage deterministic reduction --------
+__global__ void k_trap_partial(const double* hist_logL, const double* hist_logvol, long long n, LSE* partial) {
+    __shared__ LSE sh[256];
+    LSE acc;
+    acc.init();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // interval between history entries i-1 and i, entry -1 being the dummy (-inf, 0)
+        const double f0 = (i == 0) ? -INFINITY : hist_logL[i - 1];
+        const double f1 = hist_logL[i];
+        const double x0 = (i == 0) ? 0.0 : hist_logvol[i - 1];
+        const double x1 = hist_logvol[i];
+        const double fs = d_logaddexp(f0, f1) - 0.69314718055994530942;
+        const double dx = x0 + log1p(-exp(x1 - x0));          // logsubexp(x0, x1)
+        acc.push(fs + dx, 0.0);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { LSE a = sh[threadIdx.x]; a.merge(sh[threadIdx.x + s]); sh[threadIdx.x] = a; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void k_trap_final(const LSE* partial, int nb, double* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    LSE a;
+    a.init();
+    for (int i = 0; i < nb; ++i) a.merge(partial[i]);
+    *out = (a.m > -INFINITY) ? a.m + log(a.s) : -INFINITY;
+}
+
+}  // namespace cpn

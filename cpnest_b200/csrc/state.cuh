@@ -1,0 +1,33 @@
+// Device-resident state of the nested-sampling driver: what NestedSampler, _NSintegralState and
+// the samplers keep in Python attributes / mp.Value (cpnest/NestedSampling.py:88-134, 254-262,
+// cpnest/cpnest.py:572-574, cpnest/sampler.py:86-105).
+#pragma once
+namespace cpn {
+
+struct NSState {
+    double logZ;          // _NSintegralState.logZ
+    double B;             // info + logZ, the linear part of the information recurrence
+    double info;          // _NSintegralState.info
+    double logw;          // _NSintegralState.logw
+    double logLmin;       // manager.logLmin
+    double logLmax;       // manager.logLmax
+    double condition;     // NestedSampler.condition
+    double tolerance;     // NestedSampler.tolerance (stopping)
+    double nmcmc_exact;   // Sampler.Nmcmc_exact
+    double nmcmc_safety;
+    double nmcmc_tau;     // decay of the moving average, in chains
+    long long iteration;  // NestedSampler.iteration == number of dead points
+    long long n_hist;     // len(state.logLs) - 1
+    long long n_ins;      // len(insertion_indices)
+    long long batches;
+    unsigned long long totals[4];   // steps, accepted, evals, failed chains (whole run)
+    unsigned long long batch[4];    // same, last evolve launch
+    int nmcmc;            // Sampler.Nmcmc
+    int maxmcmc;
+    int adapt;
+    int stop_next;        // condition <= tolerance seen: the following batch must not run
+    int done;
+    int pad;
+};
+
+}  // namespace cpn

@@ -1,0 +1,242 @@
+"""Engine: numpy-facing wrapper of one device context (one GPU).
+
+This is the object the `CPNest` facade drives; it owns what the reference spreads over
+NestedSampler, its samplers and the RunManager (cpnest/cpnest.py:181-261): the live set, the
+proposal cycle, the evidence integrator and the chain-length adaptation, all device resident.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+
+def functor_blob(name, dim, params=None):
+    """Pack the parameters of a device functor (include/cpnest_b200.h enum cpn_functor)."""
+    params = dict(params or {})
+    if name == "gaussian_iid":
+        mu = float(params.get("mu", 0.0))
+        sigma = float(params.get("sigma", 1.0))
+        return np.array([mu, 1.0 / sigma, -math.log(sigma) - 0.5 * math.log(2.0 * math.pi)])
+    if name == "gaussian_corr":
+        Linv = np.asarray(params["Linv"], dtype=np.float64)
+        assert Linv.shape == (dim, dim)
+        return np.concatenate(([float(params["logdet"])], np.tril(Linv).ravel()))
+    if name == "ring":
+        return np.array([float(params.get("radius", 1.0)), float(params.get("thickness", 0.1))])
+    if name == "gaussian_mixture":
+        data = np.asarray(params["data"], dtype=np.float64).ravel()
+        return np.concatenate(([float(len(data))], data))
+    if name in ("eggbox", "rosenbrock", "ackley", "gaussian_mean_sigma"):
+        return np.zeros(0)
+    raise KeyError("unknown device functor %r (known: %s)" % (name, ", ".join(sorted(L.FUNCTORS))))
+
+
+class Engine:
+    def __init__(self, functor, bounds, nlive, maxmcmc=100, seed=1234, params=None, device=0,
+                 nmcmc_init=0, lanes=0, ns_mode="sequential", nmcmc_safety=5.0, adapt_nmcmc=True):
+        self.lib = L.load()
+        self.functor = functor
+        self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
+        self.dim = self.bounds.shape[0]
+        self.nlive = int(nlive)
+        self.maxmcmc = int(maxmcmc)
+        cfg = L.cpn_config()
+        cfg.device = device
+        cfg.dim = self.dim
+        cfg.nlive = self.nlive
+        cfg.maxmcmc = self.maxmcmc
+        cfg.nmcmc_init = int(nmcmc_init)
+        cfg.functor = L.FUNCTORS[functor]
+        cfg.lanes = int(lanes)
+        cfg.ns_mode = dict(sequential=L.NS_SEQUENTIAL, reference=L.NS_REFERENCE)[ns_mode]
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.nmcmc_safety = float(nmcmc_safety)
+        cfg.adapt_nmcmc = 1 if adapt_nmcmc else 0
+        cfg.world_size = 1
+        cfg.rank = 0
+        blob = L.f64(functor_blob(functor, self.dim, params))
+        lo = L.f64(self.bounds[:, 0])
+        hi = L.f64(self.bounds[:, 1])
+        h = C.c_void_p()
+        L.check(self.lib.cpn_create(C.byref(cfg), L.dptr(lo), L.dptr(hi),
+                                    blob.ctypes.data_as(C.c_void_p), blob.nbytes, C.byref(h)))
+        self.h = h
+        self.ns_mode = ns_mode
+
+    # ---- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cpn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- set-up -----------------------------------------------------------------------------
+    def set_cycle(self, cycle):
+        cyc = np.ascontiguousarray(cycle, dtype=np.uint8)
+        L.check(self.lib.cpn_set_cycle(self.h, cyc.ctypes.data_as(C.POINTER(C.c_uint8)), len(cyc)))
+
+    def init_prior(self):
+        L.check(self.lib.cpn_init_prior(self.h))
+
+    def set_live(self, rows):
+        rows = L.f64(rows)
+        assert rows.shape == (self.nlive, self.dim + 2)
+        L.check(self.lib.cpn_set_live(self.h, L.dptr(rows), self.nlive))
+
+    def update_ensemble_stats(self):
+        L.check(self.lib.cpn_update_ensemble_stats(self.h))
+
+    def ensemble_stats(self):
+        D = self.dim
+        mean, cov, w, v = np.zeros(D), np.zeros((D, D)), np.zeros(D), np.zeros((D, D))
+        L.check(self.lib.cpn_get_ensemble_stats(self.h, L.dptr(mean), L.dptr(cov), L.dptr(w), L.dptr(v)))
+        return mean, cov, w, v
+
+    # ---- the hot path -----------------------------------------------------------------------
+    def select_and_accumulate(self, K):
+        L.check(self.lib.cpn_select_and_accumulate(self.h, K))
+
+    def evolve_batch(self, K):
+        L.check(self.lib.cpn_evolve_batch(self.h, K))
+
+    def insert_batch(self, K):
+        L.check(self.lib.cpn_insert_batch(self.h, K))
+
+    def ns_step(self, K):
+        L.check(self.lib.cpn_ns_step(self.h, K))
+
+    def run(self, K, max_batches=0, tolerance=0.1):
+        done = C.c_int64(0)
+        L.check(self.lib.cpn_run(self.h, K, max_batches, tolerance, C.byref(done)))
+        return done.value
+
+    def finalise(self):
+        rect, trap = C.c_double(), C.c_double()
+        L.check(self.lib.cpn_finalise(self.h, C.byref(rect), C.byref(trap)))
+        return rect.value, trap.value
+
+    def synchronize(self):
+        L.check(self.lib.cpn_synchronize(self.h))
+
+    def evolve_host(self, requests, logLmin, nmcmc, replies=None, steps=None, accepted=None):
+        """Sampler pipe protocol with host buffers (numpy arrays or pinned torch tensors'
+        .numpy() views): requests[K][D+2] in, replies[K][D+2] out."""
+        K = requests.shape[0]
+        if replies is None:
+            replies = np.empty_like(requests)
+        if steps is None:
+            steps = np.empty(K, dtype=np.int32)
+        if accepted is None:
+            accepted = np.empty(K, dtype=np.int32)
+        L.check(self.lib.cpn_evolve_host(self.h, K, float(logLmin), int(nmcmc), requests.ctypes.data,
+                                         replies.ctypes.data, steps.ctypes.data, accepted.ctypes.data))
+        return replies, steps, accepted
+
+    # ---- observation ------------------------------------------------------------------------
+    def state(self):
+        s = L.cpn_state()
+        L.check(self.lib.cpn_get_state(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def set_nmcmc(self, n):
+        L.check(self.lib.cpn_set_nmcmc(self.h, int(n)))
+
+    def live(self):
+        rows = np.empty((self.nlive, self.dim + 2))
+        L.check(self.lib.cpn_get_live(self.h, L.dptr(rows)))
+        return rows
+
+    def num_dead(self):
+        n = self.lib.cpn_num_dead(self.h)
+        if n < 0:
+            raise L.CpnError(self.lib.cpn_last_error().decode())
+        return n
+
+    def dead(self, first=0, n=None, log_vols=False):
+        if n is None:
+            n = self.num_dead() - first
+        rows = np.empty((n, self.dim + 2))
+        lv = np.empty(n) if log_vols else None
+        L.check(self.lib.cpn_get_dead(self.h, first, n, L.dptr(rows), L.dptr(lv) if log_vols else None))
+        return (rows, lv) if log_vols else rows
+
+    def insertion_indices(self):
+        n = self.lib.cpn_num_insertion_indices(self.h)
+        out = np.empty(max(n, 0))
+        if n > 0:
+            L.check(self.lib.cpn_get_insertion_indices(self.h, 0, n, L.dptr(out)))
+        return out
+
+    def last_batch(self, K):
+        rows = np.empty((K, self.dim + 2))
+        steps = np.empty(K, dtype=np.int32)
+        acc = np.empty(K, dtype=np.int32)
+        L.check(self.lib.cpn_get_last_batch(self.h, K, L.dptr(rows), L.iptr(steps), L.iptr(acc)))
+        return rows, steps, acc
+
+    # ---- parity entry points ----------------------------------------------------------------
+    def eval_model(self, X):
+        X = L.f64(X).reshape(-1, self.dim)
+        n = X.shape[0]
+        logL, logP = np.empty(n), np.empty(n)
+        L.check(self.lib.cpn_eval_model(self.h, L.dptr(X), n, L.dptr(logL), L.dptr(logP)))
+        return logL, logP
+
+    def replay_mh(self, ensemble, start, eigval, eigvec, cycle_idx, tape, nmcmc, maxmcmc, logLmin,
+                  compat=True, lanes=0, record=False):
+        ens = L.f64(ensemble)
+        start = L.f64(start).reshape(-1, self.dim + 2)
+        Cn = start.shape[0]
+        tape = L.f64(tape).reshape(Cn, maxmcmc, 8)
+        ev = L.f64(eigval)
+        evec = L.f64(eigvec)
+        out = np.empty((Cn, self.dim + 2))
+        steps = np.empty(Cn, dtype=np.int32)
+        acc = np.empty(Cn, dtype=np.int32)
+        states = np.zeros((Cn, maxmcmc, self.dim)) if record else None
+        L.check(self.lib.cpn_replay_mh(self.h, ens.shape[0], L.dptr(ens), Cn, L.dptr(start), L.dptr(ev), L.dptr(evec),
+                                       int(cycle_idx), L.dptr(tape), int(nmcmc), int(maxmcmc), float(logLmin),
+                                       1 if compat else 0, int(lanes), L.dptr(out), L.iptr(steps), L.iptr(acc),
+                                       L.dptr(states) if record else None))
+        return out, steps, acc, states
+
+    def stage_replacements(self, rows):
+        rows = L.f64(rows).reshape(-1, self.dim + 2)
+        L.check(self.lib.cpn_stage_replacements(self.h, rows.shape[0], L.dptr(rows)))
+
+    def ns_reset(self):
+        L.check(self.lib.cpn_ns_reset(self.h))
+
+    def ns_increment(self, logL, nlive, mode="sequential"):
+        logL = L.f64(np.atleast_1d(logL))
+        m = dict(sequential=L.NS_SEQUENTIAL, reference=L.NS_REFERENCE)[mode]
+        L.check(self.lib.cpn_ns_increment(self.h, L.dptr(logL), len(logL), int(nlive), m))
+
+    def ns_trapezoid(self):
+        z = C.c_double()
+        L.check(self.lib.cpn_ns_trapezoid(self.h, C.byref(z)))
+        return z.value
+
+    def philox(self, ctr, key):
+        ctr = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 4)
+        key = np.ascontiguousarray(key, dtype=np.uint32).reshape(2)
+        out = np.empty_like(ctr)
+        u32p = C.POINTER(C.c_uint32)
+        L.check(self.lib.cpn_philox(self.h, ctr.ctypes.data_as(u32p), key.ctypes.data_as(u32p), ctr.shape[0],
+                                    out.ctypes.data_as(u32p)))
+        return out

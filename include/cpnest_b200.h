@@ -1,0 +1,174 @@
+/* cpnest_b200 -- C-ABI of the B200-native nested-sampling hot path.
+ *
+ * Drop-in boundary.  The reference (johnveitch/cpnest) has no FFI:
+ * its seams are the Python duck types `Model`, `Proposal`/`ProposalCycle` and the
+ * sampler <-> NestedSampler pipe protocol.  Each entry point below cites the reference
+ * interface (path:line in the reference tree) whose work it performs on the device.
+ *
+ * Conventions
+ *   - every call returns 0 on success, non-zero on failure; cpn_last_error() gives the text.
+ *   - one context per GPU; calls on one context are not thread-safe; contexts are independent.
+ *   - all `double*` / `int*` arguments are HOST pointers, caller-owned, copied synchronously,
+ *     unless the name says `dev_`.  Rows are row-major.  A "record" row is [x_0..x_{D-1}, logL,
+ *     logP] (the column order of LivePoint.asnparray, cpnest/parameter.pyx:148-157).
+ *   - no CPU fallback exists: without a CUDA device cpn_create fails.
+ */
+#ifndef CPNEST_B200_H
+#define CPNEST_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cpn_ctx cpn_ctx;
+
+/* device functors for Model.log_prior / Model.log_likelihood (cpnest/model.py:55-82) */
+enum cpn_functor {
+    CPN_GAUSS_IID = 0,        /* examples/test_50d.py:18-19, tests/test_2d.py:15-16, tests/test_1d.py:20-21;
+                                 blob: {mu, sigma} (2 doubles) */
+    CPN_GAUSS_CORR = 1,       /* SURVEY 8d config 4, N(0,Sigma); blob: {logdet_L, Linv[D][D] row-major lower} */
+    CPN_EGGBOX = 2,           /* examples/eggbox.py:19-23 */
+    CPN_ROSENBROCK = 3,       /* examples/rosenbrock.py:20-22 */
+    CPN_ACKLEY = 4,           /* standard D-dim Ackley (examples/ackley.py:21-28 is non-finite everywhere) */
+    CPN_RING = 5,             /* tests/test_ring.py:19-23; blob: {radius, thickness} */
+    CPN_GAUSS_MEAN_SIGMA = 6, /* tests/test_gaussian.py:15-20 (1/sigma prior) */
+    CPN_GAUSS_MIXTURE = 7,    /* examples/gaussianmixture.py:22-31; blob: {n_data, data[n_data]} */
+    CPN_NUM_FUNCTORS = 8
+};
+
+/* proposal ids, order of DefaultProposalCycle (cpnest/proposal.py:354-361) */
+enum cpn_proposal { CPN_WALK = 0, CPN_STRETCH = 1, CPN_DE = 2, CPN_EIGEN = 3 };
+
+/* evidence accumulation rule for one batch of K dead points */
+enum cpn_ns_mode {
+    CPN_NS_SEQUENTIAL = 0, /* per-point shrinkage -1/(N-i), the reference's final-sweep rule
+                              (cpnest/NestedSampling.py:474-476); default */
+    CPN_NS_REFERENCE = 1   /* one increment, logt=-K/N at the K-th worst (NestedSampling.py:324-326) */
+};
+
+typedef struct cpn_config {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t dim;           /* len(Model.names) */
+    int32_t nlive;         /* CPNest(nlive=) */
+    int32_t maxmcmc;       /* CPNest(maxmcmc=) */
+    int32_t nmcmc_init;    /* initial chain length; <=0: maxmcmc/10 (cpnest/sampler.py:79) */
+    int32_t functor;       /* enum cpn_functor */
+    int32_t lanes;         /* lanes per chain G in {0=auto,1,4,8,16,32} */
+    int32_t ns_mode;       /* enum cpn_ns_mode */
+    uint64_t seed;         /* CPNest(seed=), Philox key */
+    double nmcmc_safety;   /* safety factor of estimate_nmcmc_on_the_fly (cpnest/sampler.py:156); <=0: 5 */
+    int32_t adapt_nmcmc;   /* 1: adapt chain length from the batch acceptance; 0: keep nmcmc_init */
+    int32_t world_size;    /* number of ranks sharing the live set (1 = single GPU) */
+    int32_t rank;
+    int32_t reserved;
+} cpn_config;
+
+/* NestedSampler / _NSintegralState observable state (cpnest/NestedSampling.py:88-144, 254-262) */
+typedef struct cpn_state {
+    double logZ;           /* NS.state.logZ */
+    double info;           /* NS.state.info */
+    double logw;           /* NS.state.logw */
+    double logLmin;        /* manager.logLmin */
+    double logLmax;        /* manager.logLmax */
+    double condition;      /* NS.condition */
+    double nmcmc_exact;    /* Sampler.Nmcmc_exact */
+    int64_t iteration;     /* NS.iteration = number of dead points */
+    int64_t n_hist;        /* len(state.logLs) - 1 */
+    int64_t batches;       /* consume_sample calls */
+    int64_t total_steps;   /* sum of Sampler.mcmc_counter */
+    int64_t total_accepted;/* sum of Sampler.mcmc_accepted */
+    int64_t total_evals;   /* log_likelihood calls */
+    int64_t failed_chains; /* chains that returned with no accepted step (NestedSampling.py:354-357) */
+    int32_t nmcmc;         /* Sampler.Nmcmc */
+    int32_t done;          /* condition <= tolerance reached */
+} cpn_state;
+
+const char* cpn_last_error(void);
+int cpn_device_count(void);
+
+/* CPNest.__init__ (cpnest/cpnest.py:103-261): one context = NestedSampler + its samplers. */
+int cpn_create(const cpn_config* cfg, const double* lo, const double* hi,
+               const void* functor_blob, size_t blob_bytes, cpn_ctx** out);
+void cpn_destroy(cpn_ctx* ctx);
+
+/* ProposalCycle.set_cycle (cpnest/proposal.py:71-75): the host draws the cycle (np.random.choice)
+ * and hands the device the proposal id per slot. */
+int cpn_set_cycle(cpn_ctx* ctx, const uint8_t* cycle, int32_t len);
+
+/* Sampler.reset + NestedSampler.reset (cpnest/sampler.py:110-154, NestedSampling.py:404-431):
+ * draw nlive points uniformly in bounds (Model.new_point, model.py:35-53), evaluate, evolve each
+ * with logLmin=-inf so they follow the prior, sort by logL. */
+int cpn_init_prior(cpn_ctx* ctx);
+/* Load a given live set instead (resume, tests, host protocol): rows[n][D+2] records. */
+int cpn_set_live(cpn_ctx* ctx, const double* rows, int32_t n);
+
+/* EnsembleEigenVector.update_eigenvectors (cpnest/proposal.py:306-323): mean, covariance (np.cov)
+ * and its eigen-decomposition of the live ensemble, on the device. */
+int cpn_update_ensemble_stats(cpn_ctx* ctx);
+int cpn_get_ensemble_stats(cpn_ctx* ctx, double* mean, double* cov, double* eigval, double* eigvec);
+
+/* NestedSampler.get_worst_n_live_points + _NSintegralState.increment + termination condition
+ * (cpnest/NestedSampling.py:324-332, 368-375, 111-134).  Asynchronous. */
+int cpn_select_and_accumulate(cpn_ctx* ctx, int32_t K);
+/* MetropolisHastingsSampler.yield_sample for the K chains of the batch
+ * (cpnest/sampler.py:322-358 driving cpnest/proposal.py:209-362).  Asynchronous. */
+int cpn_evolve_batch(cpn_ctx* ctx, int32_t K);
+/* OrderedLivePoints.insert_live_point / remove_n_worst_points + insertion indices
+ * (cpnest/NestedSampling.py:44-85, 343-366).  Asynchronous. */
+int cpn_insert_batch(cpn_ctx* ctx, int32_t K);
+/* One consume_sample() = the three calls above (+ ensemble refresh on the sampler's cadence,
+ * cpnest/sampler.py:252-254). */
+int cpn_ns_step(cpn_ctx* ctx, int32_t K);
+/* `while self.condition > self.tolerance: consume_sample()` (NestedSampling.py:451): runs batches
+ * until the device-side condition drops below `tolerance` or max_batches are done; returns the
+ * number of batches that did work in *batches_done. */
+int cpn_run(cpn_ctx* ctx, int32_t K, int64_t max_batches, double tolerance, int64_t* batches_done);
+/* final sweep over the remaining live points + trapezoid refinement
+ * (NestedSampling.py:472-480, nest2pos.py:33-42). */
+int cpn_finalise(cpn_ctx* ctx, double* logZ_rect, double* logZ_trap);
+
+int cpn_synchronize(cpn_ctx* ctx);
+int cpn_get_state(cpn_ctx* ctx, cpn_state* out);
+int cpn_set_nmcmc(cpn_ctx* ctx, int32_t nmcmc);
+int cpn_get_live(cpn_ctx* ctx, double* rows /*[nlive][D+2], ascending logL*/);
+int64_t cpn_num_dead(cpn_ctx* ctx);
+int cpn_get_dead(cpn_ctx* ctx, int64_t first, int64_t n, double* rows /*[n][D+2]*/, double* log_vols /*[n] or NULL*/);
+int64_t cpn_num_insertion_indices(cpn_ctx* ctx);
+int cpn_get_insertion_indices(cpn_ctx* ctx, int64_t first, int64_t n, double* out);
+/* per-chain outcome of the last evolve: record rows, steps and accepted counts */
+int cpn_get_last_batch(cpn_ctx* ctx, int32_t K, double* rows, int32_t* steps, int32_t* accepted);
+
+/* The sampler <-> NestedSampler pipe protocol with HOST buffers (cpnest/sampler.py:233-246):
+ * `requests[K][D+2]` are the points sent down the pipes (used as chain start points),
+ * `replies[K][D+2]` the evolved points sent back.  Copies are inside the call. */
+int cpn_evolve_host(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc,
+                    const double* requests, double* replies, int32_t* steps, int32_t* accepted);
+
+/* ---- parity / test entry points ------------------------------------------------------------ */
+/* Model.log_prior / log_likelihood on given points (functor parity vs the Python callables). */
+int cpn_eval_model(cpn_ctx* ctx, const double* x /*[n][D]*/, int32_t n, double* logL, double* logP);
+/* MH chains driven by an explicit random tape instead of Philox (SURVEY 7 step 3 "replay mode").
+ * ensemble[P][D]; start[C][D+2]; per chain c and step s the tape row tape[(c*maxmcmc+s)*8+..] is
+ * {i0,i1,i2 (as doubles), g0,g1,g2, u_stretch, u_mh}.  compat=1 applies the reference's fp32
+ * rounding of LivePoint scalars (cpnest/parameter.pyx:96-120). */
+int cpn_replay_mh(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C, const double* start,
+                  const double* eigval, const double* eigvec /*[D][D] row k, col i as numpy*/,
+                  int32_t cycle_idx, const double* tape, int32_t nmcmc, int32_t maxmcmc,
+                  double logLmin, int32_t compat, int32_t lanes,
+                  double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted,
+                  double* states /*[C][maxmcmc][D] or NULL*/);
+/* Put K given records into the replacement staging area, as if the chains had returned them
+ * (`proposed` of NestedSampling.py:342): lets a test script the samplers' replies. */
+int cpn_stage_replacements(cpn_ctx* ctx, int32_t K, const double* rows /*[K][D+2]*/);
+/* _NSintegralState.increment on given sorted dead logL values (integrator parity). */
+int cpn_ns_reset(cpn_ctx* ctx);
+int cpn_ns_increment(cpn_ctx* ctx, const double* logL, int32_t K, int32_t nlive, int32_t ns_mode);
+int cpn_ns_trapezoid(cpn_ctx* ctx, double* logZ);
+/* Philox4x32-10 known-answer test: n counters (4 words each) -> n outputs (4 words each). */
+int cpn_philox(cpn_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int32_t n, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,139 @@
+"""End-to-end nested-sampling runs on the device (engine level): log-evidence within 3 sigma of
+the analytic value, sigma = sqrt(H/nlive) (BASELINE.json north_star; the reference's own tests use
+2 sigma, tests/test_2d.py:37-38), insertion indices uniform, and size-independent invariants."""
+import math
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import cpnest_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ns(functor, bounds, nlive, K, maxmcmc=200, seed=1234, params=None, tolerance=0.1, **kw):
+    from cpnest_b200.engine import Engine
+    e = Engine(functor, bounds, nlive=nlive, maxmcmc=maxmcmc, seed=seed, params=params, **kw)
+    e.set_cycle(O.make_cycle(np.random.RandomState(seed)))
+    e.init_prior()
+    nb = e.run(K, tolerance=tolerance)
+    ins = e.insertion_indices()
+    rect, trap = e.finalise()
+    s = e.state()
+    return e, s, trap, ins, nb
+
+
+def check_logz(s, logz, analytic, nlive, nsigma=3.0):
+    sigma = math.sqrt(s["info"] / nlive)
+    assert abs(logz - analytic) < nsigma * sigma, "logZ %.4f vs analytic %.4f (sigma %.4f, H %.2f)" % (
+        logz, analytic, sigma, s["info"])
+
+
+def test_gaussian2d_logz_and_invariants():
+    # config 1: tests/test_2d.py model, nlive=1000
+    e, s, logz, ins, nb = run_ns("gaussian_iid", [[-10, 10]] * 2, nlive=1000, K=64)
+    with e:
+        check_logz(s, logz, -2 * math.log(20.0), 1000)
+        assert 2.5 < s["info"] < 4.2                     # docs/index.rst:92-93 quotes H = 3.37
+        assert stats.kstest(ins, "uniform").pvalue > 1e-3
+        dead = e.dead()
+        assert len(dead) == s["iteration"] == nb * 64 + 1000
+        assert np.all(np.diff(dead[:, 2]) >= 0)          # nested samples come out ordered by logL
+        assert np.all(np.abs(dead[:, :2]) < 10)
+        assert np.allclose(dead[:, 2], -0.5 * (dead[:, :2] ** 2).sum(1) - math.log(2 * math.pi), rtol=1e-12)
+        # posterior moments from the weighted dead points
+        _, lw = O.compute_weights(dead[:, 2], 1000)
+        w = np.exp(lw - lw.max())
+        w /= w.sum()
+        mean = (w[:, None] * dead[:, :2]).sum(0)
+        var = (w[:, None] * (dead[:, :2] - mean) ** 2).sum(0)
+        assert np.all(np.abs(mean) < 0.15) and np.all(np.abs(var - 1.0) < 0.2)
+
+
+def test_gaussian2d_is_deterministic_per_seed():
+    a = run_ns("gaussian_iid", [[-10, 10]] * 2, nlive=500, K=32, seed=7)
+    b = run_ns("gaussian_iid", [[-10, 10]] * 2, nlive=500, K=32, seed=7)
+    c = run_ns("gaussian_iid", [[-10, 10]] * 2, nlive=500, K=32, seed=8)
+    assert a[2] == b[2] and a[1]["iteration"] == b[1]["iteration"]
+    assert np.array_equal(a[0].dead(), b[0].dead())
+    assert a[2] != c[2]
+    for r in (a, b, c):
+        r[0].close()
+
+
+def test_ring_logz():
+    # tests/test_ring.py: analytic -2.31836
+    e, s, logz, ins, nb = run_ns("ring", [[-2, 2]] * 2, nlive=1000, K=64, params=dict(radius=1.0, thickness=0.1))
+    with e:
+        check_logz(s, logz, -2.318358, 1000)
+        assert stats.kstest(ins, "uniform").pvalue > 1e-3
+
+
+def test_half_gaussian_and_1d_logz():
+    e, s, logz, ins, nb = run_ns("gaussian_iid", [[-10, 10]], nlive=1000, K=64)
+    with e:
+        check_logz(s, logz, -math.log(20.0), 1000)
+    e, s, logz, ins, nb = run_ns("gaussian_iid", [[0, 20]], nlive=500, K=32)
+    with e:
+        check_logz(s, logz, math.log(stats.norm.cdf(20) - 0.5) - math.log(20.0), 500)
+
+
+def test_gaussian_mean_sigma_nonflat_prior():
+    # tests/test_gaussian.py: logZ = log int L(mean,sigma) p(mean,sigma); evaluate by quadrature
+    from scipy import integrate
+    f = lambda m, s: math.exp(-0.5 * m * m / (s * s)) / (s * math.sqrt(2 * math.pi)) / (s * 10 * 0.95)
+    Z, _ = integrate.dblquad(f, 0.05, 1.0, lambda s: -5, lambda s: 5, epsabs=1e-10)
+    e, s, logz, ins, nb = run_ns("gaussian_mean_sigma", [[-5, 5], [0.05, 1]], nlive=1000, K=64)
+    with e:
+        check_logz(s, logz, math.log(Z), 1000)
+
+
+def test_eggbox_logz():
+    # config 2: anchor 235.85594 by quadrature; 18 equal modes
+    e, s, logz, ins, nb = run_ns("eggbox", [[0, 10 * math.pi]] * 2, nlive=2000, K=128)
+    with e:
+        check_logz(s, logz, 235.85594, 2000)
+
+
+def test_rosenbrock2d_logz():
+    e, s, logz, ins, nb = run_ns("rosenbrock", [[-5, 5]] * 2, nlive=2000, K=128, maxmcmc=400)
+    with e:
+        check_logz(s, logz, -5.804132, 2000)
+
+
+def test_gaussian50d_logz():
+    # config 4 model at a test-sized live set: analytic -149.786614 (examples/test_50d.py:16)
+    e, s, logz, ins, nb = run_ns("gaussian_iid", [[-10, 10]] * 50, nlive=2000, K=256, maxmcmc=500)
+    with e:
+        check_logz(s, logz, -50 * math.log(20.0), 2000)
+        assert stats.kstest(ins[-20000:], "uniform").pvalue > 1e-3
+        assert 60 < s["info"] < 100
+
+
+def test_full_size_invariants_50d_nlive_1e4():
+    """BASELINE size (50-D Gaussian, nlive=10^4): size-independent properties of the batch step."""
+    from cpnest_b200.engine import Engine
+    N, K = 10000, 2048
+    with Engine("gaussian_iid", [[-10, 10]] * 50, nlive=N, maxmcmc=100, seed=3) as e:
+        e.set_cycle(O.make_cycle(np.random.RandomState(3)))
+        e.init_prior()
+        live0 = e.live()
+        assert np.all(np.diff(live0[:, 50]) >= 0)
+        for b in range(6):
+            e.ns_step(K)
+        s = e.state()
+        live = e.live()
+        dead = e.dead()
+        assert s["iteration"] == 6 * K == len(dead)
+        assert np.all(np.diff(live[:, 50]) >= 0) and np.all(np.diff(dead[:, 50]) >= 0)
+        assert live[0, 50] > s["logLmin"] == dead[-1, 50]
+        assert np.all(np.abs(live[:, :50]) < 10)
+        logL, logP = e.eval_model(live[:, :50])
+        assert np.array_equal(logL, live[:, 50]) and np.all(logP == 0)
+        ins = e.insertion_indices()
+        assert len(ins) == 6 * K and ins.min() >= 0 and ins.max() <= 1
+        assert s["total_evals"] <= s["total_steps"] and s["total_accepted"] <= s["total_evals"]
+        # the union of live and dead points holds every point exactly once (no slot lost in the merge)
+        allp = np.concatenate((live, dead))
+        assert len(np.unique(allp[:, :3], axis=0)) == len(allp) - s["failed_chains"] or s["failed_chains"] > 0
