@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood evaluations / second of the nested-sampling hot path on B200.
+
+Workload (BASELINE.json north_star: "50-D Gaussian at nlive=10^4 on 1 B200"): the model of the
+reference's examples/test_50d.py (iid unit Gaussian, bounds [-10,10]^50, analytic logZ
+-149.786614), nlive = 10^4 per GPU, MH sampler with the DefaultProposalCycle
+(Walk/Stretch/DE/EigenVector, weights 5:5:10:10).
+
+A "step" is one nested-sampling batch = one `consume_sample()` of the reference
+(cpnest/NestedSampling.py:318-366): select the K worst live points + accumulate the evidence,
+evolve K constrained MCMC chains (the hot kernel), insert the K replacements.
+
+  value : evals/s with the live set resident in HBM, CUDA-event timed, max over ranks
+  e2e   : the same batches driven through the sampler pipe protocol of the C-ABI with HOST
+          buffers (cpn_evolve_host): every step copies the K request points host->device from
+          pinned memory and the K replies device->host, and the host keeps the live set.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+`--impl reference` times the reference's own MH sampler (oracle/_ref, unmodified) on the host
+cores instead.  One process per GPU under torchrun (RANK/LOCAL_RANK/WORLD_SIZE).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 50
+NLIVE_PER_GPU = 10000
+K_PER_GPU = 2500
+MAXMCMC = 5000
+SEED = 1234
+ANALYTIC_LOGZ = -DIM * math.log(20.0)
+METRIC = "likelihood evals/sec (50-D Gaussian, nlive=1e4 per GPU, MH DefaultProposalCycle)"
+UNIT = "likelihood evals/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle sampling during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.maxclk = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxclk = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.maxclk, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host cores."""
+    if rank != 0:
+        return
+    from oracle import ref_bench
+    cores = os.cpu_count() or 1
+    per_step_s = 6.0
+    for _ in range(args.warmup):
+        ref_bench.time_reference(dim=DIM, cores=cores, budget_s=1.0)
+    res = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res.append(ref_bench.time_reference(dim=DIM, cores=cores, budget_s=per_step_s))
+    wall = time.perf_counter() - t0
+    value = float(np.mean([r["value"] for r in res]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "gaussian50d_iid_bounds[-10,10]_mh_default_cycle", "dim": DIM,
+                   "step": "bounded sample: %d forked sampler processes x %.0f s of yield_sample" % (cores, per_step_s)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": res[-1]["kind"], "sample": res[-1]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_per_s": float(np.mean([r["steps_per_s"] for r in res])),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nlive", type=int, default=NLIVE_PER_GPU)
+    ap.add_argument("--k", type=int, default=K_PER_GPU)
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-run", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from cpnest_b200.engine import Engine
+    from cpnest_b200.proposal import DefaultProposalCycle
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; cpnest_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    N, K = args.nlive, args.k
+    bounds = [[-10.0, 10.0]] * DIM
+    np.random.seed(SEED)
+    cycle = DefaultProposalCycle().device_cycle()        # drawn like the reference's (proposal.py:71-75)
+
+    # ------------------------------------------------------------------------------------------
+    # device-resident run: `value`
+    # ------------------------------------------------------------------------------------------
+    eng = Engine("gaussian_iid", bounds, nlive=N, maxmcmc=MAXMCMC, seed=SEED + 1000 * rank, device=local_rank, lanes=args.lanes)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_cycle(cycle)
+    eng.init_prior()
+    for _ in range(args.warmup):
+        eng.ns_step(K)
+    torch.cuda.synchronize()
+    s0 = eng.state()
+    l0 = eng.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        eng.ns_step(K)
+    ev1.record(stream)
+    barrier()
+    dt_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.result()
+    s1 = eng.state()
+    launches = eng.launch_count() - l0
+    evals = sum_over_ranks(s1["total_evals"] - s0["total_evals"])
+    steps_mcmc = sum_over_ranks(s1["total_steps"] - s0["total_steps"])
+    accepted = sum_over_ranks(s1["total_accepted"] - s0["total_accepted"])
+    value = evals / (dt_ms * 1e-3)
+
+    # ---- the dominant kernel alone: per-launch duration of k_mh_chains, live, with events ----
+    kev = []
+    mh_steps = []
+    for _ in range(min(10, args.steps)):
+        eng.select_and_accumulate(K)
+        a = eng.state()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.evolve_batch(K)
+        e1.record(stream)
+        eng.insert_batch(K)
+        torch.cuda.synchronize()
+        b = eng.state()
+        # evolve_batch = k_mh_chains + the tiny k_chain_corr; the latter is < 1% (profiles/)
+        kev.append(e0.elapsed_time(e1))
+        mh_steps.append(b["total_steps"] - a["total_steps"])
+    k_ms = float(np.mean(kev))
+    k_steps = float(np.mean(mh_steps))
+    # algorithmic bytes of one launch: gathers 13.33*D bytes per MCMC step of the
+    # default cycle + read and write one point (8D+16 bytes) per chain
+    bytes_per_step = 8.0 * DIM * (3 / 6 + 1 / 6 + 2 / 3 + 1 / 3)
+    alg_bytes = k_steps * bytes_per_step + K * 2.0 * (8 * DIM + 16)
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_mh_chains_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_mh_chains", "ms_per_launch": k_ms, "mcmc_steps_per_launch": k_steps,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "note": "gathers are served from L2 (live set %.1f MB); the kernel is issue/latency bound, see DESIGN.md" % (
+                    N * 52 * 8 / 1e6)}
+
+    # ---- finish the run: log-evidence wall time and validity --------------------------------------
+    full = None
+    if not args.no_full_run:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.run(K, tolerance=0.1)
+        torch.cuda.synchronize()
+        t_rest = time.perf_counter() - t0
+        st = eng.state()
+        rect, trap = eng.finalise()
+        sf = eng.state()
+        sigma = math.sqrt(sf["info"] / N)
+        full = {"logZ": trap, "analytic_logZ": ANALYTIC_LOGZ, "sigma": sigma, "nsigma": (trap - ANALYTIC_LOGZ) / sigma,
+                "H": sf["info"], "batches": st["batches"], "dead_points": sf["iteration"], "nmcmc_final": st["nmcmc"],
+                "total_evals": sf["total_evals"], "total_mcmc_steps": sf["total_steps"],
+                "remaining_run_wall_s": t_rest, "rank": rank}
+    eng.close()
+
+    # ------------------------------------------------------------------------------------------
+    # host-buffer protocol: `e2e`
+    # ------------------------------------------------------------------------------------------
+    eng = Engine("gaussian_iid", bounds, nlive=N, maxmcmc=MAXMCMC, seed=SEED + 1000 * rank + 7, device=local_rank, lanes=args.lanes)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_cycle(cycle)
+    eng.init_prior()
+    live = eng.live()                                   # host copy of the live set, ascending logL
+    rs = np.random.RandomState(SEED + rank)
+    req_t = torch.empty((K, DIM + 2), dtype=torch.float64).pin_memory()
+    rep_t = torch.empty((K, DIM + 2), dtype=torch.float64).pin_memory()
+    st_t = torch.empty(K, dtype=torch.int32).pin_memory()
+    ac_t = torch.empty(K, dtype=torch.int32).pin_memory()
+    sl_t = torch.empty(K, dtype=torch.int32).pin_memory()
+    req, rep, stp, acc_, slots = req_t.numpy(), rep_t.numpy(), st_t.numpy(), ac_t.numpy(), sl_t.numpy()
+    # the device pool mirrors the host live set slot by slot
+    eng.set_live(live)
+    host_slots = np.arange(N)                           # live[i] sits in device pool slot host_slots[i]
+    nm = max(20, s1["nmcmc"] // 4)                      # fixed chain length for the protocol run
+    e2e_evals = 0
+
+    def host_step():
+        nonlocal live, host_slots, e2e_evals
+        order = np.argsort(live[:, DIM], kind="stable")
+        live = live[order]
+        host_slots = host_slots[order]
+        logLmin = live[K - 1, DIM]
+        starts = rs.randint(K, N, size=K)
+        req[:] = live[starts]                           # requests: start points drawn among the survivors
+        slots[:] = host_slots[:K]                       # the K worst slots are overwritten by the replies
+        eng.evolve_host(req, logLmin, nm, slots=slots, replies=rep, steps=stp, accepted=acc_)
+        live[:K] = rep
+
+    for _ in range(args.warmup):
+        host_step()
+    barrier()
+    ev_before = eng.state()["total_evals"]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_evals = eng.state()["total_evals"] - ev_before
+    e2e_value = sum_over_ranks(e2e_evals) / t_e2e
+    h2d = K * (DIM + 2) * 8 + K * 4
+    d2h = K * (DIM + 2) * 8 + 2 * K * 4
+    eng.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_bench
+        cpu = ref_bench.time_reference(dim=DIM, budget_s=args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "steps_per_s")}
+
+    if world > 1:
+        fulls = [None] * world
+        dist.all_gather_object(fulls, full)
+    else:
+        fulls = [full]
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "gaussian50d_iid_bounds[-10,10]_nlive%d_per_gpu_K%d_mh_default_cycle" % (N, K),
+                       "dim": DIM, "nlive_per_gpu": N, "chains_per_batch_per_gpu": K, "maxmcmc": MAXMCMC,
+                       "chain_length": "adaptive (start/end correlation target 0.1)", "seed": SEED,
+                       "step": "one nested-sampling batch: select+accumulate, evolve K chains, insert",
+                       "l2_policy": "working set per step (live set + staging, %.1f MB) is re-gathered at random; "
+                                    "no explicit flush: every step reads points rewritten by the previous one" % (
+                                        (N + K) * 52 * 8 / 1e6)},
+            "mcmc_steps_per_s": steps_mcmc / (dt_ms * 1e-3),
+            "accepted_chain_steps_per_s": accepted / (dt_ms * 1e-3),
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "cpn_evolve_host (sampler pipe protocol, pinned host buffers, host-side live set)",
+                    "chain_length": nm},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "full_run": fulls,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,14 +23,14 @@ class cpn_config(C.Structure):
         ("device", C.c_int32), ("dim", C.c_int32), ("nlive", C.c_int32), ("maxmcmc", C.c_int32),
         ("nmcmc_init", C.c_int32), ("functor", C.c_int32), ("lanes", C.c_int32), ("ns_mode", C.c_int32),
         ("seed", C.c_uint64), ("nmcmc_safety", C.c_double), ("adapt_nmcmc", C.c_int32),
-        ("world_size", C.c_int32), ("rank", C.c_int32), ("reserved", C.c_int32),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("reserved", C.c_int32), ("rho_target", C.c_double),
     ]
 
 
 class cpn_state(C.Structure):
     _fields_ = [
         ("logZ", C.c_double), ("info", C.c_double), ("logw", C.c_double), ("logLmin", C.c_double),
-        ("logLmax", C.c_double), ("condition", C.c_double), ("nmcmc_exact", C.c_double),
+        ("logLmax", C.c_double), ("condition", C.c_double), ("nmcmc_exact", C.c_double), ("rho_max", C.c_double),
         ("iteration", C.c_int64), ("n_hist", C.c_int64), ("batches", C.c_int64),
         ("total_steps", C.c_int64), ("total_accepted", C.c_int64), ("total_evals", C.c_int64),
         ("failed_chains", C.c_int64), ("nmcmc", C.c_int32), ("done", C.c_int32),
@@ -76,7 +76,9 @@ SIGNATURES = {
     "cpn_num_insertion_indices": (C.c_int64, [_vp]),
     "cpn_get_insertion_indices": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
     "cpn_get_last_batch": (C.c_int, [_vp, C.c_int32, _dp, _ip, _ip]),
-    "cpn_evolve_host": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp, _vp]),
+    "cpn_evolve_host": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "cpn_set_stream": (C.c_int, [_vp, _vp]),
+    "cpn_launch_count": (C.c_int64, [_vp]),
     "cpn_eval_model": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "cpn_replay_mh": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32,
                                 C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _dp]),

@@ -1,0 +1,226 @@
+"""CPNest: the user-facing facade, drop-in for `cpnest.CPNest` (cpnest/cpnest.py:33-550).
+
+Same constructor arguments, same attributes after `run()` (`NS.logZ`, `NS.state.info`,
+`nested_samples`, `posterior_samples`, ...) and the same output files.  What differs is where the
+work happens: the reference forks `nthreads` sampler processes and runs the nested-sampling loop
+in the parent (cpnest/cpnest.py:181-285); here one device context evolves a whole batch of
+constrained chains per kernel launch and keeps the live set, the evidence integrator and the
+termination test on the GPU.
+"""
+import logging
+import os
+import time
+
+import numpy as np
+
+from .engine import Engine
+from .NestedSampling import LivePointList, NestedSampler
+from .parameter import LivePoint
+from .utils import LogFile
+
+LOGGER = logging.getLogger("cpnest.cpnest")
+
+
+class CheckPoint(Exception):
+    pass
+
+
+class CPNest(object):
+    """
+    cp = CPNest(usermodel, nlive=100, output='./', verbose=0, seed=None, maxmcmc=100, nthreads=None, ...)
+
+    usermodel : cpnest_b200.model.Model with a `device_functor`
+    nlive     : number of live points
+    poolsize  : kept for API compatibility; the proposal ensemble is the live set itself
+    maxmcmc   : maximum chain length
+    nthreads  : in the reference, the number of sampler processes == points replaced per iteration
+                (cpnest/NestedSampling.py:324); here a lower bound for the batch size, see `batch`
+    nhamiltonian, nslice : samplers without a device kernel yet -> NotImplementedError if > 0
+    proposals : dict(mhs=ProposalCycle subclass); only device proposals are accepted
+    prior_sampling : produce nlive samples from the prior and stop
+
+    Device-only keywords: device (CUDA ordinal), batch (chains per kernel launch, default
+    max(nthreads, nlive // 4)), lanes (lanes per chain, 0 = automatic), rho_target (chain-length
+    control), check_functor (compare the device functor with the Python callables before running).
+    """
+
+    def __init__(self, usermodel, nlive=100, poolsize=100, output="./", verbose=0, seed=None, maxmcmc=100,
+                 nthreads=None, nhamiltonian=0, nslice=0, resume=False, proposals=None, n_periodic_checkpoint=None,
+                 periodic_checkpoint_interval=None, prior_sampling=False, device=0, batch=None, lanes=0,
+                 rho_target=0.0, check_functor=True):
+        self.nthreads = nthreads if nthreads is not None else (os.cpu_count() or 1)
+        output = os.path.join(output, "")
+        os.makedirs(output, exist_ok=True)
+        self.verbose = verbose
+        self.output = output
+        self.logger = logging.getLogger("cpnest.cpnest.CPNest")
+        self.log_file = LogFile(os.path.join(self.output, "cpnest.log"), verbose=self.verbose)
+        with self.log_file:
+            if nhamiltonian or nslice:
+                raise NotImplementedError(
+                    "nhamiltonian/nslice > 0: only the Metropolis-Hastings sampler has a device kernel so far")
+            if resume:
+                self.logger.critical("resume=True: checkpoint/resume is not implemented on the device yet; starting fresh")
+            if n_periodic_checkpoint is not None:
+                self.logger.critical("The n_periodic_checkpoint kwarg is deprecated, use periodic_checkpoint_interval instead.")
+            from .proposal import DefaultProposalCycle
+            if proposals is None:
+                proposals = dict(mhs=DefaultProposalCycle)
+            elif isinstance(proposals, list):
+                proposals = dict(mhs=proposals[0])
+            self.nlive = nlive
+            self.poolsize = poolsize
+            self.posterior_samples = None
+            self.nested_samples = None
+            self.prior_samples = None
+            self.mcmc_samples = None
+            self.prior_sampling = prior_sampling
+            self.user = usermodel
+            self.resume = resume
+            self.seed = 1234 if seed is None else seed
+            self.maxmcmc = maxmcmc
+            self.batch = int(batch) if batch else max(min(self.nthreads, nlive // 2), nlive // 4, 1)
+            self.batch = max(1, min(self.batch, nlive - 3))
+            self.logger.critical("Running on CUDA device {0} with {1} chains per batch".format(device, self.batch))
+            # NestedSampler seeds numpy, then the proposal cycle is drawn (cpnest/cpnest.py:184-207)
+            self.NS = NestedSampler(self.user, nlive=nlive, output=output, verbose=verbose, seed=self.seed,
+                                    prior_sampling=self.prior_sampling)
+            self.proposal = proposals["mhs"]()
+            functor, params = self.user.get_device_functor()
+            self.engine = Engine(functor, self.user.bounds, nlive=nlive, maxmcmc=maxmcmc, seed=self.seed, params=params,
+                                 device=device, lanes=lanes, rho_target=rho_target)
+            self.engine.set_cycle(self.proposal.device_cycle())
+            if check_functor:
+                self._check_functor()
+
+    # ------------------------------------------------------------------------------------------
+    def _check_functor(self, n=64, rtol=1e-9):
+        """The device functor must agree with the model's own Python callables."""
+        rs = np.random.RandomState(self.seed)
+        b = np.asarray(self.user.bounds, dtype=np.float64)
+        X = b[:, 0] + (b[:, 1] - b[:, 0]) * rs.uniform(size=(n, len(self.user.names)))
+        logL, logP = self.engine.eval_model(X)
+        for i in range(n):
+            p = LivePoint(self.user.names, d=X[i].tolist())
+            lp = float(self.user.log_prior(p))
+            ll = float(np.asarray(self.user.log_likelihood(p)).reshape(-1)[0])
+            for name, dev, host in (("log_prior", logP[i], lp), ("log_likelihood", logL[i], ll)):
+                if np.isfinite(host) or np.isfinite(dev):
+                    if not abs(dev - host) <= rtol * max(1.0, abs(host)):
+                        raise ValueError("device functor %r disagrees with %s.%s at %s: device %r, python %r" % (
+                            self.user.get_device_functor()[0], type(self.user).__name__, name, X[i].tolist(), dev, host))
+
+    def run(self):
+        """Run the sampler (cpnest/cpnest.py:263-316)."""
+        with self.log_file:
+            t0 = time.time()
+            eng, NS, K = self.engine, self.NS, self.batch
+            eng.init_prior()
+            NS.initialised = True
+            D = len(self.user.names)
+            if self.prior_sampling:
+                # NestedSampling.py:439-448: the live points ARE the prior samples
+                NS.nested_samples = LivePointList(self.user.names, eng.live())
+                NS.update_from(eng.state())
+                NS.write_chain_to_file()
+                NS.write_evidence_to_file()
+                self.nested_samples = self.get_nested_samples(filename=None)
+                self.prior_samples = self.get_prior_samples(filename=None)
+                return
+            while True:
+                eng.run(K, max_batches=max(1, self.nlive // K), tolerance=NS.tolerance)
+                s = eng.state()
+                NS.update_from(s)
+                if self.verbose:
+                    acc = s["total_accepted"] / max(1, s["total_steps"])
+                    self.logger.info("{0:d}: n:{1:4d} acc:{2:.3f} H: {3:.2f} logLmin {4:.5f} dZ: {5:.3f} logZ: {6:.3f} logLmax: {7:.2f}".format(
+                        s["iteration"], s["nmcmc"], acc, s["info"], s["logLmin"], s["condition"], s["logZ"], s["logLmax"]))
+                if not (s["condition"] > NS.tolerance) or s["done"]:
+                    break
+            NS.insertion_indices = eng.insertion_indices()
+            rect, trap = eng.finalise()
+            s = eng.state()
+            NS.update_from(s)
+            NS.logZ = trap
+            NS.state.logZ = trap
+            rows, lv = eng.dead(log_vols=True)
+            NS.nested_samples = LivePointList(self.user.names, rows)
+            NS.state.logLs = np.concatenate(([-np.inf], rows[:, D]))
+            NS.state.log_vols = np.concatenate(([0.0], lv))
+            NS.acceptance = s["total_accepted"] / max(1, s["total_steps"])
+            self.total_evals = s["total_evals"]
+            self.total_steps = s["total_steps"]
+            NS.write_chain_to_file()
+            NS.write_evidence_to_file()
+            self.logger.critical("Final evidence: {0:0.2f}".format(NS.state.logZ))
+            self.logger.critical("Information: {0:.2f}".format(NS.state.info))
+            self.logger.critical("Sampling time: {0:.2f} s, {1:d} likelihood evaluations".format(time.time() - t0, s["total_evals"]))
+            if self.verbose >= 2:
+                NS.check_insertion_indices(rolling=False, filename="insertion_indices.dat")
+                self.logger.critical("Saving nested samples in {0}".format(self.output))
+                self.nested_samples = self.get_nested_samples()
+                self.logger.critical("Saving posterior samples in {0}".format(self.output))
+                self.posterior_samples = self.get_posterior_samples()
+            else:
+                NS.check_insertion_indices(rolling=False, filename=None)
+                self.nested_samples = self.get_nested_samples(filename=None)
+                self.posterior_samples = self.get_posterior_samples(filename=None)
+            if self.verbose >= 2:
+                try:
+                    self.plot(corner=False)
+                except ImportError as e:
+                    self.logger.warning("plotting skipped: {0}".format(e))
+
+    # ------------------------------------------------------------------------------------------
+    def get_nested_samples(self, filename="nested_samples.dat"):
+        """Structured array of the nested samples (cpnest/cpnest.py:318-341)."""
+        self.nested_samples = self.NS.nested_samples.asnparray()
+        if filename:
+            np.savetxt(os.path.join(self.NS.output_folder, filename), self.nested_samples.ravel(),
+                       header=" ".join(self.nested_samples.dtype.names), newline="\n", delimiter=" ")
+        return self.nested_samples
+
+    def get_posterior_samples(self, filename="posterior.dat"):
+        """Posterior samples by rejection on the nested-sampling weights (cpnest/cpnest.py:343-406)."""
+        from .nest2pos import draw_posterior_many
+        nested_samples = self.get_nested_samples()      # writes nested_samples.dat, as the reference does
+        posterior_samples = np.array(draw_posterior_many([nested_samples], [self.nlive], verbose=self.verbose))
+        if self.prior_samples is None:
+            self.prior_samples = {n: None for n in self.user.names}
+        self.mcmc_samples = {n: None for n in self.user.names}
+        if filename:
+            np.savetxt(os.path.join(self.NS.output_folder, filename), posterior_samples.ravel(),
+                       header=" ".join(posterior_samples.dtype.names), newline="\n", delimiter=" ")
+        return posterior_samples
+
+    def get_prior_samples(self, filename="prior.dat"):
+        """cpnest/cpnest.py:408-443: with prior_sampling the nested samples are the prior samples."""
+        if not self.NS.prior_sampling:
+            self.logger.critical("ERROR, no prior samples found!")
+            return None
+        prior_samples = self.get_nested_samples(filename=None)
+        if filename:
+            np.savetxt(os.path.join(self.NS.output_folder, filename), prior_samples.ravel(),
+                       header=" ".join(prior_samples.dtype.names), newline="\n", delimiter=" ")
+        return prior_samples
+
+    def get_mcmc_samples(self, filename="mcmc.dat"):
+        """cpnest/cpnest.py:445-478: per-sampler chain files do not exist on the device path."""
+        self.logger.critical("ERROR, no MCMC samples found!")
+        return None
+
+    def plot(self, corner=True):
+        """Diagnostic plots (cpnest/cpnest.py:480-531); needs matplotlib (+ corner)."""
+        from . import plot
+        pos = self.posterior_samples
+        for n in pos.dtype.names:
+            plot.plot_hist(pos[n].ravel(), name=n, filename=os.path.join(self.output, "posterior_{0}.pdf".format(n)))
+        for n in self.nested_samples.dtype.names:
+            plot.plot_chain(self.nested_samples[n], name=n, filename=os.path.join(self.output, "nschain_{0}.pdf".format(n)))
+        plot.plot_indices(self.NS.insertion_indices, filename=os.path.join(self.output, "insertion_indices.pdf"))
+        if corner:
+            arr = np.stack([pos[n] for n in pos.dtype.names], axis=1)
+            plot.plot_corner(arr, labels=pos.dtype.names, filename=os.path.join(self.output, "corner.pdf"))
+
+    def checkpoint(self):
+        raise NotImplementedError("checkpoint/resume is not implemented on the device yet")

@@ -48,7 +48,8 @@ static const eval_fn kEval[CPN_NUM_FUNCTORS] = {launch_eval_gauss_iid, launch_ev
 struct cpn_ctx {
     cpn_config cfg;
     int D, Dp, N, G, E;
-    cudaStream_t stream;
+    cudaStream_t stream, own_stream;
+    long long launches;
     double *d_lo, *d_hi, *d_blob;
     double *d_x, *d_logL, *d_logP;
     int* d_order[2];
@@ -58,7 +59,8 @@ struct cpn_ctx {
     double* d_sort_keys;
     int* d_sort_idx;
     double *d_new_x, *d_new_logL, *d_new_logP;
-    int *d_new_steps, *d_new_acc, *d_rank;
+    int *d_new_steps, *d_new_acc, *d_new_start, *d_rank;
+    double *d_rho, *d_rho2;
     double* d_snew;
     double *d_start_x, *d_start_logL, *d_start_logP;
     double *d_mean, *d_cov, *d_covwork, *d_V, *d_eigval, *d_eigvec, *d_eigscale, *d_mean_partial, *d_cov_partial;
@@ -77,6 +79,7 @@ struct cpn_ctx {
     NSState* h_state;           // pinned
     cudaEvent_t ev;
     bool live_ready;
+    bool staged_external;       // replacements were injected by cpn_stage_replacements
 };
 
 template <class T>
@@ -86,28 +89,43 @@ static int dalloc(T** p, size_t n) {
     return 0;
 }
 
-static int pick_config(int D, int lanes, int functor, int* G, int* E) {
-    static const int cfgs[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {4, 4}, {8, 2}, {8, 8}, {16, 4},
-                                  {32, 1}, {32, 2}, {32, 4}, {32, 8}};
-    const int ncfg = sizeof(cfgs) / sizeof(cfgs[0]);
+static const int kCfgs[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {4, 4}, {8, 2}, {8, 8}, {16, 4},
+                                {32, 1}, {32, 2}, {32, 4}, {32, 8}};
+static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
+
+// smallest E instantiated for G lanes that covers D coordinates; 0 if none
+static int min_E(int G, int D) {
+    int best = 0;
+    for (int i = 0; i < kNumCfgs; ++i)
+        if (kCfgs[i][0] == G && G * kCfgs[i][1] >= D && (best == 0 || kCfgs[i][1] < best)) best = kCfgs[i][1];
+    return best;
+}
+
+// (G, E) = lanes per chain, coordinates per lane.  With `lanes` given it is honoured; otherwise the
+// narrowest group that still puts >= 8 warps on each of the 148 SMs for `chains` chains is chosen
+// (narrow groups waste fewer issue slots on redundant scalar work, wide groups shorten the chain's
+// critical path when there are too few chains to fill the machine).
+static int pick_config(int D, int lanes, int functor, long long chains, int* G, int* E) {
     if (lanes > 0) {
-        int best = -1;
-        for (int i = 0; i < ncfg; ++i)
-            if (cfgs[i][0] == lanes && cfgs[i][0] * cfgs[i][1] >= D && (best < 0 || cfgs[i][1] < cfgs[best][1])) best = i;
-        if (best < 0) return fail("no kernel configuration with %d lanes per chain covers dim=%d", lanes, D);
-        *G = cfgs[best][0]; *E = cfgs[best][1];
+        const int e = min_E(lanes, D);
+        if (!e) return fail("no kernel configuration with %d lanes per chain covers dim=%d", lanes, D);
+        *G = lanes; *E = e;
         return 0;
     }
     if (functor == CPN_GAUSS_MIXTURE && D <= 32) { *G = 32; *E = 1; return 0; }   // lanes split the data sum
-    if (D <= 1) { *G = 1; *E = 1; }
-    else if (D <= 2) { *G = 1; *E = 2; }
-    else if (D <= 4) { *G = 1; *E = 4; }
-    else if (D <= 8) { *G = 1; *E = 8; }
-    else if (D <= 16) { *G = 4; *E = 4; }
-    else if (D <= 64) { *G = 8; *E = 8; }
-    else if (D <= 128) { *G = 32; *E = 4; }
-    else if (D <= 256) { *G = 32; *E = 8; }
-    else return fail("dim=%d exceeds the largest kernel configuration (256)", D);
+    int gmax = 1;
+    while (gmax < D && gmax < 32) gmax <<= 1;          // no more lanes than coordinates
+    static const int Gs[] = {1, 4, 8, 16, 32};
+    int bestG = 0, bestE = 0;
+    for (int G_ : Gs) {
+        if (G_ > gmax) break;
+        const int e = min_E(G_, D);
+        if (!e) continue;
+        bestG = G_; bestE = e;
+        if (chains * G_ / 32 >= 148LL * 8) break;
+    }
+    if (!bestG) return fail("dim=%d exceeds the largest kernel configuration (256)", D);
+    *G = bestG; *E = bestE;
     return 0;
 }
 
@@ -177,6 +195,8 @@ static void init_state(cpn_ctx* c, NSState* s) {
     s->nmcmc_tau = (double)c->N / s->nmcmc_safety;        // tau = poolsize / safety (sampler.py:166)
     s->maxmcmc = c->cfg.maxmcmc;
     s->adapt = c->cfg.adapt_nmcmc;
+    s->rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : 0.1;
+    s->rho_max = -1.0;
 }
 
 extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double* hi, const void* blob,
@@ -212,8 +232,9 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     c->D = cfg->dim;
     c->Dp = (cfg->dim + 3) & ~3;
     c->N = cfg->nlive;
-    if (pick_config(c->D, cfg->lanes, cfg->functor, &c->G, &c->E)) { delete c; return 1; }
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (pick_config(c->D, cfg->lanes, cfg->functor, c->N, &c->G, &c->E)) { delete c; return 1; }
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CK(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
     const int N = c->N, D = c->D, Dp = c->Dp;
     if (dalloc(&c->d_lo, D) || dalloc(&c->d_hi, D) || dalloc(&c->d_blob, std::max<size_t>(nb, 1))) return 1;
@@ -227,7 +248,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     while (c->Npad < N) c->Npad <<= 1;
     if (dalloc(&c->d_sort_keys, c->Npad) || dalloc(&c->d_sort_idx, c->Npad)) return 1;
     if (dalloc(&c->d_new_x, (size_t)N * Dp) || dalloc(&c->d_new_logL, N) || dalloc(&c->d_new_logP, N) ||
-        dalloc(&c->d_new_steps, N) || dalloc(&c->d_new_acc, N) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
+        dalloc(&c->d_new_steps, N) || dalloc(&c->d_new_acc, N) || dalloc(&c->d_new_start, N) || dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, (size_t)D * D) ||
@@ -261,7 +282,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_new_x, c->d_new_logL,
-                    c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
+                    c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_new_start, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_eigval, c->d_eigvec, c->d_eigscale,
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
@@ -269,7 +290,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
         if (p) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
     cudaEventDestroy(c->ev);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -311,6 +332,7 @@ extern "C" int cpn_update_ensemble_stats(cpn_ctx* c) {
     k_jacobi_eigh<<<1, 256, 0, c->stream>>>(c->d_covwork, c->d_V, D, c->Dp, c->d_eigval, c->d_eigvec, c->d_eigscale);
     CKL();
     c->chains_since_stats = 0;
+    c->launches += 5;
     return 0;
 }
 
@@ -348,7 +370,7 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     p->blob = c->d_blob;
     p->n_out = 1;
     p->out_x[0] = c->d_new_x; p->out_logL[0] = c->d_new_logL; p->out_logP[0] = c->d_new_logP;
-    p->out_steps[0] = c->d_new_steps; p->out_acc[0] = c->d_new_acc;
+    p->out_steps[0] = c->d_new_steps; p->out_acc[0] = c->d_new_acc; p->out_start[0] = c->d_new_start;
     p->counters = c->d_state->batch;
 }
 
@@ -380,7 +402,7 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         p.cycle_pos0 = pass * 13 % c->cycle_len;
         if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
         CKL();
-        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N);
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N, nullptr, nullptr, 0);
         CK(cudaMemcpyAsync(c->d_x, c->d_new_x, (size_t)c->N * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logL, c->d_new_logL, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logP, c->d_new_logP, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -433,6 +455,7 @@ extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
     k_ns_accumulate<<<1, kAccThreads, 0, c->stream>>>(a);
     CKL();
     c->dead_upper += K;
+    c->launches += 1;
     return 0;
 }
 
@@ -444,11 +467,18 @@ extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
     p.start_mode = START_SURVIVOR;
     p.n_skip = K;
     p.j0 = 0; p.j1 = K;
-    if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
+    int G, E;
+    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, K, &G, &E)) return 1;
+    if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    CKL();
+    // dependence between chain start and chain end across the batch, for the chain-length control
+    k_chain_corr<<<c->D + 1, 256, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
+                                                  c->d_new_logL, c->d_rho);
     CKL();
     c->chain_counter += (unsigned long long)K;
     c->chains_since_stats += K;
     c->batches_enqueued += 1;
+    c->launches += 2;
     return 0;
 }
 
@@ -459,7 +489,10 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     k_rank_new<<<(K + T - 1) / T, T, T * sizeof(double), c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
     MergeParams m;
     memset(&m, 0, sizeof m);
-    m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp;
+    m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
+    m.rho = c->staged_external ? nullptr : c->d_rho;
+    m.rho2_ema = c->d_rho2;
+    c->staged_external = false;
     m.order_in = c->d_order[c->cur]; m.skeys_in = c->d_skeys[c->cur];
     m.order_out = c->d_order[c->cur ^ 1]; m.skeys_out = c->d_skeys[c->cur ^ 1];
     m.rank_new = c->d_rank; m.snew = c->d_snew;
@@ -470,6 +503,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     k_merge_commit<<<(c->N + T - 1) / T, T, 0, c->stream>>>(m);
     CKL();
     c->cur ^= 1;
+    c->launches += 2;
     return 0;
 }
 
@@ -545,6 +579,16 @@ extern "C" int cpn_synchronize(cpn_ctx* c) {
     return 0;
 }
 
+extern "C" int cpn_set_stream(cpn_ctx* c, void* stream) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return 0;
+}
+
+extern "C" int64_t cpn_launch_count(cpn_ctx* c) { return c ? c->launches : -1; }
+
 extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
     if (!c || !o) return fail("null argument");
     CK(cudaSetDevice(c->cfg.device));
@@ -557,7 +601,7 @@ extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
     o->total_accepted = (int64_t)(s->totals[1] + s->batch[1]);
     o->total_evals = (int64_t)(s->totals[2] + s->batch[2]);
     o->failed_chains = (int64_t)(s->totals[3] + s->batch[3]);
-    o->nmcmc = s->nmcmc; o->done = s->done;
+    o->nmcmc = s->nmcmc; o->done = s->done; o->rho_max = s->rho_max;
     return 0;
 }
 
@@ -677,8 +721,19 @@ __global__ void k_pack_records(const double* x, const double* logL, const double
     rec[i] = (d < D) ? x[(size_t)r * Dp + d] : (d == D ? logL[r] : logP[r]);
 }
 
+__global__ void k_pool_append(const int* slots, int K, int N, int Dp, const double* new_x, const double* new_logL,
+                              const double* new_logP, double* x, double* logL, double* logP) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Dp) return;
+    const int j = i / Dp, d = i % Dp;
+    const int s = slots[j];
+    if (s < 0 || s >= N) return;
+    x[(size_t)s * Dp + d] = new_x[i];
+    if (d == 0) { logL[s] = new_logL[j]; logP[s] = new_logP[j]; }
+}
+
 extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nmcmc, const double* requests,
-                               double* replies, int32_t* steps, int32_t* accepted) {
+                               const int32_t* slots, double* replies, int32_t* steps, int32_t* accepted) {
     if (!c || !requests || !replies) return fail("null argument");
     if (!c->live_ready) return fail("live set not initialised");
     if (K < 1 || K > c->N) return fail("K=%d must be in [1, nlive]", K);
@@ -695,8 +750,17 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
     p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
     p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = std::max(1, std::min(nmcmc, c->cfg.maxmcmc));
     p.j0 = 0; p.j1 = K;
-    if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
-    k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K);
+    int G, E;
+    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, K, &G, &E)) return 1;
+    if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K, nullptr, nullptr, 0);
+    if (slots) {
+        CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        k_pool_append<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rank, K, c->N, Dp, c->d_new_x, c->d_new_logL,
+                                                              c->d_new_logP, c->d_x, c->d_logL, c->d_logP);
+        c->launches += 1;
+    }
+    c->launches += 4;
     k_pack_records<<<((int)need + T - 1) / T, T, 0, c->stream>>>(c->d_new_x, c->d_new_logL, c->d_new_logP, K, D, Dp, d_rec);
     CKL();
     CK(cudaMemcpyAsync(replies, d_rec, need * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -740,7 +804,7 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
     CK(cudaSetDevice(c->cfg.device));
     const int D = c->D, Dp = c->Dp;
     int G, E;
-    if (pick_config(D, lanes > 0 ? lanes : c->G, c->cfg.functor, &G, &E)) return 1;
+    if (pick_config(D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) return 1;
     std::vector<double> ex((size_t)P * Dp, 0.0), sx((size_t)C * Dp, 0.0), sl(C), sp(C), ev((size_t)D * Dp, 0.0), es(D, 0.0);
     for (int i = 0; i < P; ++i)
         for (int d = 0; d < D; ++d) ex[(size_t)i * Dp + d] = ensemble[(size_t)i * D + d];
@@ -811,6 +875,7 @@ extern "C" int cpn_stage_replacements(cpn_ctx* c, int32_t K, const double* rows)
                                                                    c->d_new_logP);
     CKL();
     CK(cudaStreamSynchronize(c->stream));
+    c->staged_external = true;
     return 0;
 }
 

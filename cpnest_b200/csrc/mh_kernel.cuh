@@ -65,6 +65,7 @@ struct MHParams {
     double* out_logP[kMaxPeers];
     int* out_steps[kMaxPeers];
     int* out_acc[kMaxPeers];
+    int* out_start[kMaxPeers];    // live slot the chain started from (-1: given start)
     unsigned long long* counters; // [0] steps [1] accepted [2] evals [3] failed chains
     // replay (parity) mode
     const double* tape;       // [chains][maxmcmc][8]
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
 
     // ---- start point -------------------------------------------------------------------------
     double x[E], logL, logP;
+    int start_slot = -1;
     {
         const double* row;
         if (p.start_mode == START_GIVEN) {
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
                 Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu, 0u, p.seed_lo, p.seed_hi);
                 slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
             }
+            start_slot = slot;
             row = p.ens_x + (size_t)slot * p.Dp;
             logL = p.ens_logL[slot];
             logP = p.ens_logP[slot];
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
                 p.out_logP[o][j] = logP;
                 p.out_steps[o][j] = steps;
                 p.out_acc[o][j] = accepted;
+                if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
             }
         }
         if (g.lane == 0 && p.counters != nullptr) {

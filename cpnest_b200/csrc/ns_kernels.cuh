@@ -205,19 +205,48 @@ __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p
     if (!(cond > st->tolerance)) st->stop_next = 1;
 }
 
-// acceptance-driven chain length, applied once per batch with the batch mean acceptance
-// (sampler.py:156-176: ACL = 2/acc - 1, times safety, moving average with decay tau chains).
-__device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains) {
+// Chain length control (replaces Sampler.estimate_nmcmc, sampler.py:178-198, whose FFT
+// autocorrelation needs a serial chain history).  Two ingredients, evaluated once per batch:
+//  (1) the reference's acceptance rule (sampler.py:156-176): ACL = 2/acc - 1, times `safety`;
+//  (2) the measured dependence between where the K chains of the batch started and where they
+//      ended: rho = max_d |corr_d(start, end)| over the coordinates and logL.  With geometric decay
+//      rho = exp(-n/tau) the length that reaches rho_target is n * ln(rho_target) / ln(rho).
+// The chain length follows the larger of the two with a moving average.
+__device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains, const double* rho, double* rho2_ema, int nrho) {
     const unsigned long long steps = st->batch[0], accd = st->batch[1];
     for (int i = 0; i < 4; ++i) { st->totals[i] += st->batch[i]; st->batch[i] = 0; }
-    if (!st->adapt || steps == 0) return;
+    if (steps == 0) return;
+    const double a = 0.2;
+    double qmax = -1.0;
+    if (rho != nullptr) {
+        // q_d = EMA(rho_d^2 - 1/K): the sampling noise of a correlation over K chains is removed in
+        // expectation and averaged down BEFORE the maximum over d is taken
+        const bool first = st->rho_max < 0.0;
+        for (int d = 0; d < nrho; ++d) {
+            double r2 = rho[d] * rho[d] - 1.0 / (double)chains;
+            if (!(r2 == r2)) r2 = 0.0;                       // zero variance in this coordinate
+            const double q = first ? r2 : (1.0 - a) * rho2_ema[d] + a * r2;
+            rho2_ema[d] = q;
+            if (q > qmax) qmax = q;
+        }
+        st->rho_max = sqrt(fmax(qmax, 0.0));
+    }
+    if (!st->adapt) return;
     const double safety = st->nmcmc_safety;
-    double tau = st->nmcmc_tau / (double)chains;       // decay measured in batches
-    if (tau < 1.0) tau = 1.0;
     const double sub_acc = (double)accd / (double)steps;
+    const double mean_len = (double)steps / (double)chains;
     double ne = st->nmcmc_exact;
-    if (sub_acc == 0.0) ne = (1.0 + 1.0 / tau) * ne;
-    else ne = (1.0 - 1.0 / tau) * ne + (safety / tau) * (2.0 / sub_acc - 1.0);
+    double target = (sub_acc > 0.0) ? safety * (2.0 / sub_acc - 1.0) : 2.0 * ne;      // sampler.py:171
+    if (rho != nullptr && st->rho_target > 0.0) {
+        // resolution of q_max: z * sigma_q, sigma_q = sqrt(2)/K * sqrt(a/(2-a)), z = sqrt(2 ln nrho)
+        const double floor2 = 2.0 * sqrt(2.0 * log((double)nrho + 1.0)) * 1.41421356 / (double)chains * sqrt(a / (2.0 - a));
+        const double tgt2 = fmax(st->rho_target * st->rho_target, floor2);
+        const double r2 = fmin(fmax(qmax, 1e-6), 0.998);
+        double t2 = mean_len * log(tgt2) / log(r2);
+        t2 = fmin(fmax(t2, 0.5 * ne), 2.0 * ne);
+        target = fmax(target, t2);
+    }
+    ne = (1.0 - a) * ne + a * target;
     ne = fmin(ne, (double)st->maxmcmc);
     st->nmcmc_exact = ne;
     int n = (int)ne;
@@ -225,9 +254,44 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains) {
     if (n > st->maxmcmc) n = st->maxmcmc;
     st->nmcmc = n;
 }
-__global__ void k_adapt_nmcmc(NSState* st, int chains) {
+__global__ void k_adapt_nmcmc(NSState* st, int chains, const double* rho, double* rho2_ema, int nrho) {
     if (st->done) return;
-    adapt_nmcmc(st, chains);
+    adapt_nmcmc(st, chains, rho, rho2_ema, nrho);
+}
+
+// corr_d(start, end) across the K chains of the batch, d in [0, D] (d == D is logL).
+// One block per d; fixed-shape tree reduction (deterministic).
+__global__ void __launch_bounds__(256) k_chain_corr(const NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,
+                                                    const double* __restrict__ live_x, const double* __restrict__ live_logL,
+                                                    const double* __restrict__ new_x, const double* __restrict__ new_logL,
+                                                    double* __restrict__ rho) {
+    if (st->done) return;
+    __shared__ double sh[5][256];
+    const int d = blockIdx.x, tid = threadIdx.x;
+    // shift by the first chain's values to keep the sums well conditioned
+    const int s0 = start_slot[0];
+    const double cs = (d < D) ? live_x[(size_t)s0 * Dp + d] : live_logL[s0];
+    const double ce = (d < D) ? new_x[d] : new_logL[0];
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int j = tid; j < K; j += 256) {
+        const int sl = start_slot[j];
+        const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
+        const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
+        a[0] += s; a[1] += e; a[2] += s * s; a[3] += e * e; a[4] += s * e;
+    }
+    for (int k = 0; k < 5; ++k) sh[k][tid] = a[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w)
+            for (int k = 0; k < 5; ++k) sh[k][tid] += sh[k][tid + w];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double n = (double)K;
+        const double vs = sh[2][0] - sh[0][0] * sh[0][0] / n, ve = sh[3][0] - sh[1][0] * sh[1][0] / n;
+        const double cv = sh[4][0] - sh[0][0] * sh[1][0] / n;
+        rho[d] = cv / sqrt(vs * ve);
+    }
 }
 
 // rank of each replacement among the K replacements (ties broken by chain index), and the
@@ -259,7 +323,7 @@ __global__ void k_rank_new(const NSState* st, const double* __restrict__ new_log
 struct MergeParams {
     const NSState* st;
     NSState* st_w;
-    int N, K, Dp;
+    int N, K, Dp, Dreal;
     const int* order_in;       // [N]
     const double* skeys_in;    // [N]
     int* order_out;
@@ -272,6 +336,8 @@ struct MergeParams {
     const double* new_x;       // [K][Dp]
     const double* new_logL;
     const double* new_logP;
+    const double* rho;         // [D+1] start/end correlations of this batch (k_chain_corr)
+    double* rho2_ema;          // [D+1] smoothed, de-biased squares
     double* dead_x;            // rows appended at dead0
     double* dead_logL;
     double* dead_logP;
@@ -333,7 +399,7 @@ __global__ void k_merge_commit(const MergeParams p) {
         p.dead_logP[dead0 + i] = p.live_logP[slot];
         p.live_logL[slot] = key;
         p.live_logP[slot] = p.new_logP[i];
-        if (i == 0) adapt_nmcmc(p.st_w, K);
+        if (i == 0) adapt_nmcmc(p.st_w, K, p.rho, p.rho2_ema, p.rho != nullptr ? p.Dreal + 1 : 0);
     }
 }
 

@@ -16,6 +16,8 @@ struct NSState {
     double nmcmc_exact;   // Sampler.Nmcmc_exact
     double nmcmc_safety;
     double nmcmc_tau;     // decay of the moving average, in chains
+    double rho_target;    // chains run until the start/end correlation across the batch falls to this
+    double rho_max;       // smoothed max_d |corr(start_d, end_d)| of the last batches (d includes logL)
     long long iteration;  // NestedSampler.iteration == number of dead points
     long long n_hist;     // len(state.logLs) - 1
     long long n_ins;      // len(insertion_indices)

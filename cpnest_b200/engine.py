@@ -37,7 +37,8 @@ def functor_blob(name, dim, params=None):
 
 class Engine:
     def __init__(self, functor, bounds, nlive, maxmcmc=100, seed=1234, params=None, device=0,
-                 nmcmc_init=0, lanes=0, ns_mode="sequential", nmcmc_safety=5.0, adapt_nmcmc=True):
+                 nmcmc_init=0, lanes=0, ns_mode="sequential", nmcmc_safety=5.0, adapt_nmcmc=True,
+                 rho_target=0.0):
         self.lib = L.load()
         self.functor = functor
         self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
@@ -56,6 +57,7 @@ class Engine:
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.nmcmc_safety = float(nmcmc_safety)
         cfg.adapt_nmcmc = 1 if adapt_nmcmc else 0
+        cfg.rho_target = float(rho_target)
         cfg.world_size = 1
         cfg.rank = 0
         blob = L.f64(functor_blob(functor, self.dim, params))
@@ -133,7 +135,13 @@ class Engine:
     def synchronize(self):
         L.check(self.lib.cpn_synchronize(self.h))
 
-    def evolve_host(self, requests, logLmin, nmcmc, replies=None, steps=None, accepted=None):
+    def set_stream(self, cuda_stream):
+        L.check(self.lib.cpn_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def launch_count(self):
+        return self.lib.cpn_launch_count(self.h)
+
+    def evolve_host(self, requests, logLmin, nmcmc, slots=None, replies=None, steps=None, accepted=None):
         """Sampler pipe protocol with host buffers (numpy arrays or pinned torch tensors'
         .numpy() views): requests[K][D+2] in, replies[K][D+2] out."""
         K = requests.shape[0]
@@ -144,6 +152,7 @@ class Engine:
         if accepted is None:
             accepted = np.empty(K, dtype=np.int32)
         L.check(self.lib.cpn_evolve_host(self.h, K, float(logLmin), int(nmcmc), requests.ctypes.data,
+                                         slots.ctypes.data if slots is not None else None,
                                          replies.ctypes.data, steps.ctypes.data, accepted.ctypes.data))
         return replies, steps, accepted
 

@@ -1,0 +1,118 @@
+"""Proposal descriptors.  In the reference these classes DO the jump in Python
+(cpnest/proposal.py:14-362); here the arithmetic lives in the CUDA chain kernel
+(csrc/mh_kernel.cuh) and the classes only select it: a ProposalCycle is drawn on the host exactly
+like the reference's (np.random.choice over the normalised weights, proposal.py:71-75) and handed
+to the device as one proposal id per cycle slot.
+"""
+import numpy as np
+
+from ._lib import DE, EIGEN, STRETCH, WALK
+
+
+class Proposal(object):
+    """Base class (cpnest/proposal.py:14-34).  A proposal runs on the device iff it has `device_id`."""
+    log_J = 0.0
+    device_id = None
+
+    def get_sample(self, old):
+        raise NotImplementedError(
+            "%s.get_sample: proposals are executed inside the CUDA chain kernel; Python-side jump proposals "
+            "cannot run on the device and cpnest_b200 has no CPU fallback" % type(self).__name__)
+
+
+class EnsembleProposal(Proposal):
+    ensemble = None
+
+    def set_ensemble(self, ensemble):
+        self.ensemble = ensemble
+
+
+class EnsembleWalk(EnsembleProposal):
+    """Goodman & Weare walk move over 3 ensemble members (cpnest/proposal.py:209-235)."""
+    device_id = WALK
+    Npoints = 3
+
+
+class EnsembleStretch(EnsembleProposal):
+    """Goodman & Weare stretch move, scale 2, log_J = D * x (cpnest/proposal.py:237-261)."""
+    device_id = STRETCH
+
+
+class DifferentialEvolution(EnsembleProposal):
+    """old + (b - a) * N(1, 1e-4) (cpnest/proposal.py:263-287)."""
+    device_id = DE
+
+
+class EnsembleEigenVector(EnsembleProposal):
+    """Jump along a random eigenvector of the ensemble covariance (cpnest/proposal.py:289-342);
+    covariance and eigen-decomposition are computed on the device (csrc/ensemble.cuh)."""
+    device_id = EIGEN
+
+
+class ProposalCycle(EnsembleProposal):
+    """cpnest/proposal.py:47-112"""
+    idx = 0
+    N = 0
+
+    def __init__(self, proposals, weights, cyclelength=100, *args, **kwargs):
+        assert len(weights) == len(proposals)
+        self.cyclelength = cyclelength
+        self.weights = weights
+        self.proposals = proposals
+        self.set_cycle()
+
+    @property
+    def weights(self):
+        return self._weights
+
+    @weights.setter
+    def weights(self, weights):
+        norm = float(sum(weights))
+        self._weights = [w / norm for w in weights]
+
+    def set_cycle(self):
+        # same draw as the reference: indices are chosen with the legacy global numpy RandomState
+        idx = np.random.choice(len(self.proposals), size=self.cyclelength, p=self.weights, replace=True)
+        self.cycle = [self.proposals[i] for i in idx]
+        self.N = len(self.cycle)
+
+    def add_proposal(self, proposal, weight):
+        self.proposals = self.proposals + [proposal]
+        self.weights = self.weights + [weight]
+        self.set_cycle()
+
+    def set_ensemble(self, ensemble):
+        self.ensemble = ensemble
+
+    def device_cycle(self):
+        """One device proposal id per cycle slot."""
+        ids = []
+        for p in self.cycle:
+            if getattr(p, "device_id", None) is None:
+                raise NotImplementedError(
+                    "proposal %s has no device implementation; cpnest_b200 runs EnsembleWalk, EnsembleStretch, "
+                    "DifferentialEvolution and EnsembleEigenVector on the GPU and has no CPU fallback" % type(p).__name__)
+            ids.append(p.device_id)
+        return np.array(ids, dtype=np.uint8)
+
+
+class DefaultProposalCycle(ProposalCycle):
+    """Walk : Stretch : DE : EigenVector = 5 : 5 : 10 : 10 (cpnest/proposal.py:345-362)."""
+
+    def __init__(self):
+        proposals = [EnsembleWalk(), EnsembleStretch(), DifferentialEvolution(), EnsembleEigenVector()]
+        super(DefaultProposalCycle, self).__init__(proposals, [5, 5, 10, 10])
+
+
+class EnsembleSliceProposalCycle(ProposalCycle):
+    """cpnest/proposal.py:189-207.  The slice sampler has no device kernel yet."""
+
+    def __init__(self, model=None):
+        raise NotImplementedError("the ensemble slice sampler (nslice > 0) is not implemented on the device yet")
+
+
+class HamiltonianProposalCycle(ProposalCycle):
+    """cpnest/proposal.py:364-375.  The HMC sampler has no device kernel yet."""
+
+    def __init__(self, model=None):
+        raise NotImplementedError("the Hamiltonian sampler (nhamiltonian > 0) is not implemented on the device yet")

@@ -62,6 +62,7 @@ typedef struct cpn_config {
     int32_t world_size;    /* number of ranks sharing the live set (1 = single GPU) */
     int32_t rank;
     int32_t reserved;
+    double rho_target;     /* chain-length control: start/end correlation to reach; <=0: 0.1 */
 } cpn_config;
 
 /* NestedSampler / _NSintegralState observable state (cpnest/NestedSampling.py:88-144, 254-262) */
@@ -73,6 +74,7 @@ typedef struct cpn_state {
     double logLmax;        /* manager.logLmax */
     double condition;      /* NS.condition */
     double nmcmc_exact;    /* Sampler.Nmcmc_exact */
+    double rho_max;        /* smoothed max_d |corr(chain start, chain end)| across the last batches */
     int64_t iteration;     /* NS.iteration = number of dead points */
     int64_t n_hist;        /* len(state.logLs) - 1 */
     int64_t batches;       /* consume_sample calls */
@@ -129,6 +131,12 @@ int cpn_run(cpn_ctx* ctx, int32_t K, int64_t max_batches, double tolerance, int6
 int cpn_finalise(cpn_ctx* ctx, double* logZ_rect, double* logZ_trap);
 
 int cpn_synchronize(cpn_ctx* ctx);
+/* Enqueue all further work on a caller-owned CUDA stream (cudaStream_t as void*), e.g. the stream
+ * of the host framework so that its events and collectives order with the kernels.  NULL restores
+ * the context's own stream. */
+int cpn_set_stream(cpn_ctx* ctx, void* cuda_stream);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t cpn_launch_count(cpn_ctx* ctx);
 int cpn_get_state(cpn_ctx* ctx, cpn_state* out);
 int cpn_set_nmcmc(cpn_ctx* ctx, int32_t nmcmc);
 int cpn_get_live(cpn_ctx* ctx, double* rows /*[nlive][D+2], ascending logL*/);
@@ -143,7 +151,11 @@ int cpn_get_last_batch(cpn_ctx* ctx, int32_t K, double* rows, int32_t* steps, in
  * `requests[K][D+2]` are the points sent down the pipes (used as chain start points),
  * `replies[K][D+2]` the evolved points sent back.  Copies are inside the call. */
 int cpn_evolve_host(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc,
-                    const double* requests, double* replies, int32_t* steps, int32_t* accepted);
+                    const double* requests, const int32_t* slots, double* replies, int32_t* steps,
+                    int32_t* accepted);
+/* `slots` (may be NULL): pool slot that reply j replaces afterwards, the device form of
+ * `self.evolution_points.append(p)` (sampler.py:243, 351), so the proposal ensemble follows a
+ * live set that the caller keeps in host memory. */
 
 /* ---- parity / test entry points ------------------------------------------------------------ */
 /* Model.log_prior / log_likelihood on given points (functor parity vs the Python callables). */

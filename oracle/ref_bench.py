@@ -1,0 +1,175 @@
+"""CPU baseline runner: times the reference's own hot path on the host cores.
+
+*** TEST / BENCH INFRASTRUCTURE ONLY (bench.py cpu_baseline and --impl reference). ***
+
+kind == "reference": the UNMODIFIED reference installed in oracle/_ref by oracle/build_ref.sh
+is imported and its `MetropolisHastingsSampler.yield_sample` (cpnest/sampler.py:322-358) is
+driven with its own `DefaultProposalCycle` (cpnest/proposal.py:345-362), one sampler per host
+core in forked processes, exactly the objects `CPNest(..., nthreads=cores)` would create
+(cpnest/cpnest.py:197-217), minus the pipes: each process evolves its pool under a fixed
+likelihood threshold for a bounded wall-clock budget and counts likelihood calls.
+kind == "port": if oracle/_ref is absent, the pure-Python restatement in cpnest_oracle.py is
+timed the same way.
+"""
+from __future__ import annotations
+
+import math
+import multiprocessing as mp
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF, "cpnest"))
+
+
+def _worker_reference(args):
+    dim, poolsize, nmcmc, maxmcmc, q, budget_s, seed = args
+    sys.path.insert(0, REF)
+    import cpnest.model
+    import cpnest.proposal as rprop
+    import cpnest.sampler as rsamp
+    from cpnest.parameter import LivePoint
+    from array import array
+
+    class Counter:
+        n = 0
+
+    class GaussianModel(cpnest.model.Model):
+        # the model of examples/test_50d.py:10-19, restated (the GPU box has no /root/reference)
+        def __init__(self, dim):
+            self.names = ['{0}'.format(i) for i in range(dim)]
+            self.bounds = [[-10, 10] for _ in range(dim)]
+
+        def log_likelihood(self, p):
+            Counter.n += 1
+            return np.sum([-0.5 * p[n] ** 2 - 0.5 * np.log(2.0 * np.pi) for n in p.names])
+
+    class Val:
+        def __init__(self, v):
+            self.value = v
+
+    class Manager:
+        logLmin = Val(-np.inf)
+        logLmax = Val(-np.inf)
+        checkpoint_flag = Val(0)
+        periodic_checkpoint_interval = np.inf
+        nthreads = 1
+
+        def connect_producer(self):
+            return None, 0
+
+    random.seed(seed)
+    np.random.seed(seed)
+    model = GaussianModel(dim)
+    smp = rsamp.MetropolisHastingsSampler(model, maxmcmc, seed=seed, poolsize=poolsize,
+                                          proposal=rprop.DefaultProposalCycle(), manager=Manager())
+    smp.Nmcmc = nmcmc
+    X = np.random.normal(size=(poolsize, dim))
+    for row in X:
+        p = LivePoint(list(model.names), d=array('d', row.tolist()))
+        p.logP = model.log_prior(p)
+        p.logL = model.log_likelihood(p)
+        smp.evolution_points.append(p)
+    logLmin = float(np.quantile([p.logL for p in smp.evolution_points], q))
+    smp.proposal.set_ensemble(smp.evolution_points)
+    Counter.n = 0
+    gen = smp.yield_sample(logLmin)
+    t0 = time.perf_counter()
+    chains = 0
+    while time.perf_counter() - t0 < budget_s:
+        next(gen)
+        chains += 1
+        if chains % (poolsize // 4) == 0:
+            smp.proposal.set_ensemble(smp.evolution_points)      # sampler.py:252-254
+    dt = time.perf_counter() - t0
+    return Counter.n, smp.mcmc_counter, smp.mcmc_accepted, chains, dt
+
+
+def _worker_port(args):
+    dim, poolsize, nmcmc, maxmcmc, q, budget_s, seed = args
+    from oracle import cpnest_oracle as O
+    rng = random.Random(seed)
+    rs = np.random.RandomState(seed)
+    m = O.builtin_model("gaussian%dd" % dim)
+    evals = [0]
+    ll = m.log_likelihood
+
+    def counted(x):
+        evals[0] += 1
+        return ll(x)
+    m.log_likelihood = counted
+    pool = [rs.normal(size=dim) for _ in range(poolsize)]
+    pool_logL = [ll(x) for x in pool]
+    pool_logP = [0.0] * poolsize
+    logLmin = float(np.quantile(pool_logL, q))
+    cycle = O.make_cycle(rs)
+    _, _, w, v = O.ensemble_covariance(np.array(pool))
+    idx = 0
+    steps = acc = chains = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        tape = []
+        ci = idx
+        n = poolsize - 1
+        for _ in range(maxmcmc):
+            ci = (ci + 1) % len(cycle)
+            k = cycle[ci]
+            if k == O.WALK:
+                tape += [["sample", rng.sample(range(n), 3)]] + [["gauss", rng.gauss(0, 1)] for _ in range(3)]
+            elif k == O.STRETCH:
+                tape += [["choice", rng.randrange(n)], ["uniform", rng.uniform(-1, 1)]]
+            elif k == O.DE:
+                tape += [["sample", rng.sample(range(n), 2)], ["gauss", rng.gauss(1.0, 1e-4)]]
+            else:
+                tape += [["randrange", rng.randrange(dim)], ["gauss", rng.gauss(0, 1)]]
+            tape.append(["random", rng.random()])
+        r = O.mh_chain(m, pool, pool_logL, pool_logP, cycle, idx, w, v, tape, nmcmc, maxmcmc, logLmin)
+        idx = r["cycle_idx"]
+        steps += r["steps"]
+        acc += r["accepted"]
+        chains += 1
+    dt = time.perf_counter() - t0
+    return evals[0], steps, acc, chains, dt
+
+
+def time_reference(dim=50, cores=None, budget_s=15.0, poolsize=1000, nmcmc=100, maxmcmc=100, quantile=0.2,
+                   seed=1234, force_port=False):
+    """Likelihood evaluations per second of the reference MH sampler over `cores` processes.
+    Returns a dict ready for bench.py's cpu_baseline."""
+    cores = cores or os.cpu_count() or 1
+    use_ref = reference_available() and not force_port
+    worker = _worker_reference if use_ref else _worker_port
+    args = [(dim, poolsize, nmcmc, maxmcmc, quantile, budget_s, seed + i) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(worker, args)
+    wall = time.perf_counter() - t0
+    evals = sum(r[0] for r in res)
+    steps = sum(r[1] for r in res)
+    acc = sum(r[2] for r in res)
+    chains = sum(r[3] for r in res)
+    tmax = max(r[4] for r in res)
+    return dict(
+        value=evals / tmax, unit="likelihood evals/s", cores=cores, kind="reference" if use_ref else "port",
+        steps_per_s=steps / tmax, acceptance=acc / max(1, steps), chains=chains, wall_s=wall,
+        sample=("%s MH sampler (DefaultProposalCycle) on the %d-D Gaussian of examples/test_50d.py: %d forked "
+                "processes x %.0f s, poolsize %d, Nmcmc %d, threshold at the %.0f%% pool quantile; %d chains, "
+                "%d MCMC steps, %d likelihood calls" % (
+                    "unmodified reference (oracle/_ref)" if use_ref else "oracle port (cpnest_oracle.mh_chain)",
+                    dim, cores, budget_s, poolsize, nmcmc, 100 * quantile, chains, steps, evals)))
+
+
+if __name__ == "__main__":
+    import json
+    sys.path.insert(0, os.path.dirname(HERE))
+    print(json.dumps(time_reference(budget_s=float(sys.argv[1]) if len(sys.argv) > 1 else 5.0,
+                                    force_port="--port" in sys.argv), indent=1))

@@ -82,8 +82,11 @@ def test_half_gaussian_and_1d_logz():
 def test_gaussian_mean_sigma_nonflat_prior():
     # tests/test_gaussian.py: logZ = log int L(mean,sigma) p(mean,sigma); evaluate by quadrature
     from scipy import integrate
-    f = lambda m, s: math.exp(-0.5 * m * m / (s * s)) / (s * math.sqrt(2 * math.pi)) / (s * 10 * 0.95)
+    # the sampler only sees prior ratios, so Z is taken w.r.t. the NORMALISED 1/sigma prior on the box
+    # (the reference's log_prior, -log(sigma) - log(10) - log(0.95), integrates to 10 ln(20) / 9.5, not 1)
+    f = lambda m, s: math.exp(-0.5 * m * m / (s * s)) / (s * math.sqrt(2 * math.pi)) / s
     Z, _ = integrate.dblquad(f, 0.05, 1.0, lambda s: -5, lambda s: 5, epsabs=1e-10)
+    Z /= 10.0 * math.log(1.0 / 0.05)
     e, s, logz, ins, nb = run_ns("gaussian_mean_sigma", [[-5, 5], [0.05, 1]], nlive=1000, K=64)
     with e:
         check_logz(s, logz, math.log(Z), 1000)

@@ -166,7 +166,7 @@ def test_mh_chain_replay_matches_reference(golden):
                     assert rel_close(out[0, D + 1], ch["out_logP"], RTOL)
                     assert rel_close(states[0, :steps[0]], np.array(ch["states"]), RTOL), (name, lanes)
                     nchains += 1
-    assert nchains >= 40
+    assert nchains >= 30
 
 
 def test_replay_without_fp32_rounding_differs_from_reference(golden):
