@@ -160,7 +160,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch's events/collectives and the engine's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
 
     def barrier():
         if world > 1:

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -328,8 +329,14 @@ extern "C" int cpn_update_ensemble_stats(cpn_ctx* c) {
     k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), c->stream>>>(
         c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
     k_cov_final<<<(D * D + 127) / 128, 128, 0, c->stream>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
-    CK(cudaMemcpyAsync(c->d_covwork, c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    k_jacobi_eigh<<<1, 256, 0, c->stream>>>(c->d_covwork, c->d_V, D, c->Dp, c->d_eigval, c->d_eigvec, c->d_eigscale);
+    {
+        const size_t sm = 2 * (size_t)D * D * sizeof(double);
+        const int use_smem = sm <= 160 * 1024;
+        if (use_smem && sm > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_jacobi_eigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_jacobi_eigh<<<1, 256, use_smem ? sm : 0, c->stream>>>(c->d_cov, c->d_covwork, c->d_V, use_smem, D, c->Dp,
+                                                               c->d_eigval, c->d_eigvec, c->d_eigscale);
+    }
     CKL();
     c->chains_since_stats = 0;
     c->launches += 5;
@@ -389,8 +396,14 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
     if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
     CKL();
     // Sampler.reset (sampler.py:129-135): evolve every member with logLmin = -inf so the set follows
-    // the prior, adapting the chain length on the way.  Two passes, ensemble statistics refreshed.
-    for (int pass = 0; pass < 2; ++pass) {
+    // the prior, adapting the chain length on the way.  Passes are repeated until the product of the
+    // per-pass start/end correlations shows that the members have forgotten their uniform draw
+    // (at least 2, at most 24 passes).
+    // Functors with the flat prior of Model.log_prior (model.py:66-82) need no burn-in: the uniform
+    // draw IS a draw from the prior.
+    const bool flat = !(c->cfg.functor == CPN_GAUSS_MEAN_SIGMA || c->cfg.functor == CPN_GAUSS_MIXTURE);
+    double memory = 1.0;
+    for (int pass = 0; pass < (flat ? 0 : 24); ++pass) {
         if (cpn_update_ensemble_stats(c)) return 1;
         MHParams p;
         fill_mh(c, &p);
@@ -400,13 +413,30 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         p.j0 = 0; p.j1 = c->N;
         p.chain_base = 0x2000000000000000ull + (unsigned long long)pass * (unsigned long long)c->N;
         p.cycle_pos0 = pass * 13 % c->cycle_len;
-        if (kMH[c->cfg.functor](c->G, c->E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", c->G, c->E);
+        int G, E;
+        if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, c->N, &G, &E)) return 1;
+        if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
         CKL();
-        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N, nullptr, nullptr, 0);
+        k_chain_corr<<<c->D + 1, 256, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
+                                                      c->d_new_x, c->d_new_logL, c->d_rho);
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N, c->d_rho, c->d_rho2, c->D);   // coordinates only: logL is unconstrained here
         CK(cudaMemcpyAsync(c->d_x, c->d_new_x, (size_t)c->N * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logL, c->d_new_logL, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logP, c->d_new_logP, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        c->launches += 3;
+        std::vector<double> rho(c->D);
+        CK(cudaMemcpyAsync(rho.data(), c->d_rho, c->D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        double r = 0.0;
+        for (double v : rho)
+            if (v == v) r = std::max(r, std::fabs(v));
+        memory *= std::min(1.0, r + 2.0 / std::sqrt((double)c->N));
+        if (pass >= 1 && memory < 0.05) break;
     }
+    // the burn-in statistics must not leak into the run's controller
+    if (fetch_state(c)) return 1;
+    c->h_state->rho_max = -1.0;
+    if (push_state(c)) return 1;
     if (sort_live(c)) return 1;
     if (cpn_update_ensemble_stats(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));

@@ -92,21 +92,29 @@ __global__ void k_cov_final(const double* __restrict__ partial, int nb, int n, i
 }
 
 // Cyclic Jacobi, round-robin ordering: n/2 disjoint rotations per round, n-1 rounds per sweep.
-// A (D x D, row-major) is destroyed; on exit eigval ascending (np.linalg.eigh order),
+// The input matrix Ain (D x D, row-major) is copied into the working matrix A, which together with
+// the accumulated rotations V lives in shared memory when 2*D*D doubles fit (D <= 100), otherwise in
+// the global scratch buffers.  On exit eigval is ascending (np.linalg.eigh order),
 // eig_vec[i][0..D) = i-th eigenvector (a ROW here), eig_scale[i] = sqrt|eigval[i]| (proposal.py:339).
-__global__ void __launch_bounds__(256) k_jacobi_eigh(double* A, double* V, int D, int Dp,
-                                                     double* __restrict__ eigval, double* __restrict__ eig_vec,
-                                                     double* __restrict__ eig_scale) {
+__global__ void __launch_bounds__(256) k_jacobi_eigh(const double* __restrict__ Ain, double* Aglob, double* Vglob,
+                                                     int use_smem, int D, int Dp, double* __restrict__ eigval,
+                                                     double* __restrict__ eig_vec, double* __restrict__ eig_scale) {
+    extern __shared__ double jsm[];
     __shared__ double cs[128], sn[128];
     __shared__ int pp[128], qq[128];
     __shared__ double red[256];
     __shared__ int converged;
     const int tid = threadIdx.x, nt = blockDim.x;
+    double* A = use_smem ? jsm : Aglob;
+    double* V = use_smem ? jsm + D * D : Vglob;
     const int n = (D + 1) & ~1;            // even number of players; index D (if any) is a bye
     const int half = n / 2;
-    for (int i = tid; i < D * D; i += nt) V[i] = ((i / D) == (i % D)) ? 1.0 : 0.0;
+    for (int i = tid; i < D * D; i += nt) {
+        A[i] = Ain[i];
+        V[i] = ((i / D) == (i % D)) ? 1.0 : 0.0;
+    }
     __syncthreads();
-    for (int sweep = 0; sweep < 40; ++sweep) {
+    for (int sweep = 0; sweep < 30; ++sweep) {
         // convergence: off-diagonal Frobenius norm against the diagonal
         double off = 0.0, dia = 0.0;
         for (int i = tid; i < D * D; i += nt) {
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(256) k_jacobi_eigh(double* A, double* V, int D
         __syncthreads();
         for (int s = nt >> 1; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
         dia = red[0];
-        if (tid == 0) converged = (off <= 1e-30 * dia) || (D == 1);
+        if (tid == 0) converged = (off <= 1e-25 * dia) || (D == 1);
         __syncthreads();
         if (converged) break;
         for (int r = 0; r < n - 1; ++r) {

@@ -91,6 +91,92 @@ __device__ __forceinline__ void load_row(const Group<G>& g, const double* row, i
     }
 }
 
+// What one MCMC step consumes: the proposal kind, the ensemble members it draws and its random
+// numbers.  Everything here is independent of the chain's current point, so the draw (and the
+// gather it implies) of step t+1 is issued while step t is still being evaluated.
+struct Draw {
+    int kind;
+    uint32_t i0, i1, i2;
+    double g0, g1, g2, us, umh;
+};
+
+// Philox blocks of G consecutive steps are computed once, one step per lane, and handed out by
+// shuffle: the stream is the same as if every lane computed block (chain, step, k) itself.
+template <int G>
+struct RngFeed {
+    uint32_t a[4], b[4];
+    __device__ __forceinline__ void refill(int step0, int lane, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1) {
+        const Philox4 p = philox4x32_10(cid_lo, cid_hi, (uint32_t)(step0 + lane), 0u, k0, k1);
+        const Philox4 q = philox4x32_10(cid_lo, cid_hi, (uint32_t)(step0 + lane), 1u, k0, k1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] = p.v[k]; b[k] = q.v[k]; }
+    }
+    __device__ __forceinline__ void get(int src_lane, uint32_t (&ra)[4], uint32_t (&rb)[4]) const {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ra[k] = (G == 1) ? a[k] : __shfl_sync(FULL, a[k], src_lane, G);
+            rb[k] = (G == 1) ? b[k] : __shfl_sync(FULL, b[k], src_lane, G);
+        }
+    }
+};
+
+__device__ __forceinline__ Draw make_draw(int kind, const uint32_t (&r)[4], const uint32_t (&q)[4], uint32_t ens_n, uint32_t D) {
+    Draw d;
+    d.kind = kind;
+    d.umh = u32_to_unit_open(r[3]);
+    d.i0 = d.i1 = d.i2 = 0;
+    d.g0 = d.g1 = d.g2 = d.us = 0.0;
+    if (kind == CPN_WALK) {
+        // three distinct members, `sample(list(ensemble), 3)` proposal.py:230
+        d.i0 = u32_to_index(r[0], ens_n);
+        d.i1 = u32_to_index(r[1], ens_n - 1);
+        d.i1 += (d.i1 >= d.i0);
+        d.i2 = u32_to_index(r[2], ens_n - 2);
+        const uint32_t lo2 = min(d.i0, d.i1), hi2 = max(d.i0, d.i1);
+        d.i2 += (d.i2 >= lo2);
+        d.i2 += (d.i2 >= hi2);
+        double g3;
+        box_muller(q[0], q[1], d.g0, d.g1);
+        box_muller(q[2], q[3], d.g2, g3);
+    } else if (kind == CPN_STRETCH) {
+        d.i0 = u32_to_index(r[0], ens_n);                    // random.choice, proposal.py:253
+        d.us = 2.0 * u32_to_unit_open(r[1]) - 1.0;           // uniform(-1,1), proposal.py:255
+    } else if (kind == CPN_DE) {
+        d.i0 = u32_to_index(r[0], ens_n);                    // sample(...,2), proposal.py:284
+        d.i1 = u32_to_index(r[1], ens_n - 1);
+        d.i1 += (d.i1 >= d.i0);
+        double gd, unused;
+        box_muller(r[2] << 16, r[2] & 0xffff0000u, gd, unused);
+        d.g0 = 1.0 + 1e-4 * gd;                              // gauss(1.0, sigma), proposal.py:285-286
+    } else {
+        d.i0 = u32_to_index(r[0], D);                        // randrange(D), proposal.py:338
+        double unused;
+        box_muller(r[1], r[2], d.g0, unused);
+    }
+    return d;
+}
+
+__device__ __forceinline__ Draw tape_draw(int kind, const double* t, int compat) {
+    Draw d;
+    d.kind = kind;
+    d.i0 = (uint32_t)t[0]; d.i1 = (uint32_t)t[1]; d.i2 = (uint32_t)t[2];
+    d.g0 = t[3]; d.g1 = t[4]; d.g2 = t[5]; d.us = t[6]; d.umh = t[7];
+    if (compat && kind != CPN_EIGEN) {   // EnsembleEigenVector is full fp64 (proposal.py:339-341)
+        d.g0 = (double)(float)d.g0; d.g1 = (double)(float)d.g1; d.g2 = (double)(float)d.g2;
+    }
+    return d;
+}
+
+// the (up to three) rows a draw gathers: ensemble members, or one eigenvector
+template <int G, int E>
+__device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, const Draw& d, double (&r0)[E],
+                                            double (&r1)[E], double (&r2)[E]) {
+    const double* base0 = (d.kind == CPN_EIGEN) ? p.eig_vec : p.ens_x;
+    load_row<G, E>(g, base0 + (size_t)d.i0 * p.Dp, p.D, r0);
+    if (d.kind == CPN_WALK || d.kind == CPN_DE) load_row<G, E>(g, p.ens_x + (size_t)d.i1 * p.Dp, p.D, r1);
+    if (d.kind == CPN_WALK) load_row<G, E>(g, p.ens_x + (size_t)d.i2 * p.Dp, p.D, r2);
+}
+
 template <int G, int E, class Model, bool REPLAY>
 __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
     using A = Arith<REPLAY>;
@@ -142,6 +228,14 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
         }
         load_row<G, E>(g, row, D, x);
     }
+    // the box, held in registers; coordinates beyond D get (-inf, +inf) so the test needs no branch
+    double blo[E], bhi[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = g.lane + e * G;
+        blo[e] = (d < D) ? __ldg(p.lo + d) : CPN_NEG_INF;
+        bhi[e] = (d < D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
+    }
 
     int steps = 0, accepted = 0, evals = 0;
     bool active = true;
@@ -149,117 +243,80 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
     const double* tape = REPLAY ? p.tape + (size_t)c * maxmcmc * 8 : nullptr;
     const uint32_t ens_n = (uint32_t)p.ens_n;
 
-    for (int it = 0; it < maxmcmc; ++it) {
-        if (!__any_sync(FULL, active)) break;
+    // ---- software pipeline: draw + gather of step `it+1` overlap the evaluation of step `it` -----------
+    RngFeed<G> feed;
+    Draw cur;
+    double r0[E], r1[E], r2[E];
+    auto next_draw = [&](int it) -> Draw {
         cpos = (cpos + 1 == p.cycle_len) ? 0 : cpos + 1;          // pre-increment, proposal.py:93
         const int kind = p.cycle[cpos];
+        if (REPLAY) return tape_draw(kind, tape + (size_t)min(it, maxmcmc - 1) * 8, p.compat);
+        if ((it & (G - 1)) == 0) feed.refill(it, g.lane, cid_lo, cid_hi, p.seed_lo, p.seed_hi);
+        uint32_t ra[4], rb[4];
+        feed.get(it & (G - 1), ra, rb);
+        return make_draw(kind, ra, rb, ens_n, (uint32_t)D);
+    };
+    cur = next_draw(0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) r1[e] = r2[e] = 0.0;
+    gather_rows<G, E>(g, p, cur, r0, r1, r2);
 
-        // ---- random inputs of this step --------------------------------------------------------
-        uint32_t i0, i1, i2;
-        double g0, g1, g2, us, umh;
-        if (REPLAY) {
-            const double* t = tape + (size_t)it * 8;
-            i0 = (uint32_t)t[0]; i1 = (uint32_t)t[1]; i2 = (uint32_t)t[2];
-            g0 = t[3]; g1 = t[4]; g2 = t[5]; us = t[6]; umh = t[7];
-            if (p.compat && kind != CPN_EIGEN) {   // EnsembleEigenVector is full fp64 (proposal.py:339-341)
-                g0 = (double)(float)g0; g1 = (double)(float)g1; g2 = (double)(float)g2;
-            }
-        } else {
-            const Philox4 r = philox4x32_10(cid_lo, cid_hi, (uint32_t)it, 0u, p.seed_lo, p.seed_hi);
-            umh = u32_to_unit_open(r.v[3]);
-            i0 = i1 = i2 = 0;
-            g0 = g1 = g2 = us = 0.0;
-            if (kind == CPN_WALK) {
-                // three distinct members, `sample(list(ensemble), 3)` proposal.py:230
-                i0 = u32_to_index(r.v[0], ens_n);
-                i1 = u32_to_index(r.v[1], ens_n - 1);
-                i1 += (i1 >= i0);
-                i2 = u32_to_index(r.v[2], ens_n - 2);
-                const uint32_t lo2 = min(i0, i1), hi2 = max(i0, i1);
-                i2 += (i2 >= lo2);
-                i2 += (i2 >= hi2);
-                const Philox4 q = philox4x32_10(cid_lo, cid_hi, (uint32_t)it, 1u, p.seed_lo, p.seed_hi);
-                double g3;
-                box_muller(q.v[0], q.v[1], g0, g1);
-                box_muller(q.v[2], q.v[3], g2, g3);
-            } else if (kind == CPN_STRETCH) {
-                i0 = u32_to_index(r.v[0], ens_n);                    // random.choice, proposal.py:253
-                us = 2.0 * u32_to_unit_open(r.v[1]) - 1.0;           // uniform(-1,1), proposal.py:255
-            } else if (kind == CPN_DE) {
-                i0 = u32_to_index(r.v[0], ens_n);                    // sample(...,2), proposal.py:284
-                i1 = u32_to_index(r.v[1], ens_n - 1);
-                i1 += (i1 >= i0);
-                double gd, unused;
-                box_muller(r.v[2] << 16, r.v[2] & 0xffff0000u, gd, unused);
-                g0 = 1.0 + 1e-4 * gd;                                // gauss(1.0, sigma), proposal.py:285-286
-            } else {
-                i0 = u32_to_index(r.v[0], (uint32_t)D);              // randrange(D), proposal.py:338
-                double unused;
-                box_muller(r.v[1], r.v[2], g0, unused);
-            }
-        }
+    for (int it = 0; it < maxmcmc; ++it) {
+        if (!__any_sync(FULL, active)) break;
+        const Draw nxt = next_draw(it + 1);
+        double n0[E], n1[E], n2[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) n1[e] = n2[e] = 0.0;
+        gather_rows<G, E>(g, p, nxt, n0, n1, n2);
 
         // ---- proposal ------------------------------------------------------------------------------
+        const int kind = cur.kind;
         double xn[E];
         double log_J = 0.0;
         if (kind == CPN_WALK) {
-            double s0[E], s1[E], s2[E];
-            load_row<G, E>(g, p.ens_x + (size_t)i0 * p.Dp, D, s0);
-            load_row<G, E>(g, p.ens_x + (size_t)i1 * p.Dp, D, s1);
-            load_row<G, E>(g, p.ens_x + (size_t)i2 * p.Dp, D, s2);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 if (REPLAY) {
-                    const double com = __ddiv_rn(__dadd_rn(__dadd_rn(s0[e], s1[e]), s2[e]), 3.0);
+                    const double com = __ddiv_rn(__dadd_rn(__dadd_rn(r0[e], r1[e]), r2[e]), 3.0);
                     double o = x[e];
-                    o = __dadd_rn(o, __dmul_rn(g0, __dsub_rn(s0[e], com)));
-                    o = __dadd_rn(o, __dmul_rn(g1, __dsub_rn(s1[e], com)));
-                    o = __dadd_rn(o, __dmul_rn(g2, __dsub_rn(s2[e], com)));
+                    o = __dadd_rn(o, __dmul_rn(cur.g0, __dsub_rn(r0[e], com)));
+                    o = __dadd_rn(o, __dmul_rn(cur.g1, __dsub_rn(r1[e], com)));
+                    o = __dadd_rn(o, __dmul_rn(cur.g2, __dsub_rn(r2[e], com)));
                     xn[e] = o;
                 } else {
-                    const double com = (s0[e] + s1[e] + s2[e]) * (1.0 / 3.0);
-                    xn[e] = x[e] + g0 * (s0[e] - com) + g1 * (s1[e] - com) + g2 * (s2[e] - com);
+                    const double com = (r0[e] + r1[e] + r2[e]) * (1.0 / 3.0);
+                    xn[e] = x[e] + cur.g0 * (r0[e] - com) + cur.g1 * (r1[e] - com) + cur.g2 * (r2[e] - com);
                 }
             }
         } else if (kind == CPN_STRETCH) {
-            double a[E];
-            load_row<G, E>(g, p.ens_x + (size_t)i0 * p.Dp, D, a);
-            const double xs = A::mul(us, 0.69314718055994530942);     // uniform(-1,1)*log(scale)
+            const double xs = A::mul(cur.us, 0.69314718055994530942);     // uniform(-1,1)*log(scale)
             double Z = exp(xs);
             if (REPLAY && p.compat) Z = (double)(float)Z;
-            log_J = A::mul((double)D, xs);                            // proposal.py:260 (un-rounded x)
+            log_J = A::mul((double)D, xs);                                // proposal.py:260 (un-rounded x)
 #pragma unroll
-            for (int e = 0; e < E; ++e) xn[e] = A::add(a[e], A::mul(Z, A::sub(x[e], a[e])));
+            for (int e = 0; e < E; ++e) xn[e] = A::add(r0[e], A::mul(Z, A::sub(x[e], r0[e])));
         } else if (kind == CPN_DE) {
-            double a[E], b[E];
-            load_row<G, E>(g, p.ens_x + (size_t)i0 * p.Dp, D, a);
-            load_row<G, E>(g, p.ens_x + (size_t)i1 * p.Dp, D, b);
 #pragma unroll
-            for (int e = 0; e < E; ++e) xn[e] = A::add(x[e], A::mul(g0, A::sub(b[e], a[e])));
+            for (int e = 0; e < E; ++e) xn[e] = A::add(x[e], A::mul(cur.g0, A::sub(r1[e], r0[e])));
         } else {
-            double v[E];
-            load_row<G, E>(g, p.eig_vec + (size_t)i0 * p.Dp, D, v);
-            const double jump = A::mul(__ldg(p.eig_scale + i0), g0);   // sqrt|lambda_i| * gauss(0,1)
+            const double jump = A::mul(__ldg(p.eig_scale + cur.i0), cur.g0);   // sqrt|lambda_i| * gauss(0,1)
 #pragma unroll
-            for (int e = 0; e < E; ++e) xn[e] = A::add(x[e], A::mul(jump, v[e]));
+            for (int e = 0; e < E; ++e) xn[e] = A::add(x[e], A::mul(jump, r0[e]));
         }
 
         // ---- box test, prior MH test, likelihood, hard constraint -------------------------------------
         bool inb = true;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int d = g.lane + e * G;
-            if (d < D) inb = inb && (__ldg(p.lo + d) < xn[e]) && (xn[e] < __ldg(p.hi + d));   // strict, model.py:33
-        }
+        for (int e = 0; e < E; ++e) inb = inb & (blo[e] < xn[e]) & (xn[e] < bhi[e]);    // strict, model.py:33
         inb = g.all(inb);
         double logP_new = Model::template log_prior<G, E>(g, xn, m);
         logP_new = inb ? logP_new : CPN_NEG_INF;
         const double delta = A::add(A::sub(logP_new, logP), log_J);   // sampler.py:337
         bool pass;
         if (REPLAY) {
-            pass = delta > ((umh > 0.0) ? log(umh) : CPN_NEG_INF);
+            pass = delta > ((cur.umh > 0.0) ? log(cur.umh) : CPN_NEG_INF);
         } else {
-            pass = (delta >= 0.0) || (delta > log(umh));                // log(u) < 0 always
+            pass = (delta >= 0.0) || (delta > log(cur.umh));            // log(u) < 0 always
         }
         pass = pass && active;
         if (__any_sync(FULL, pass)) {
@@ -285,6 +342,9 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
             }
             if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
         }
+        cur = nxt;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { r0[e] = n0[e]; r1[e] = n1[e]; r2[e] = n2[e]; }
     }
 
     // ---- hand the evolved point back (`producer_pipe.send`, sampler.py:246) ------------------

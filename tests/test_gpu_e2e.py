@@ -107,7 +107,7 @@ def test_rosenbrock2d_logz():
 
 def test_gaussian50d_logz():
     # config 4 model at a test-sized live set: analytic -149.786614 (examples/test_50d.py:16)
-    e, s, logz, ins, nb = run_ns("gaussian_iid", [[-10, 10]] * 50, nlive=2000, K=256, maxmcmc=500)
+    e, s, logz, ins, nb = run_ns("gaussian_iid", [[-10, 10]] * 50, nlive=2000, K=256, maxmcmc=5000)
     with e:
         check_logz(s, logz, -50 * math.log(20.0), 2000)
         assert stats.kstest(ins[-20000:], "uniform").pvalue > 1e-3
@@ -133,7 +133,7 @@ def test_full_size_invariants_50d_nlive_1e4():
         assert live[0, 50] > s["logLmin"] == dead[-1, 50]
         assert np.all(np.abs(live[:, :50]) < 10)
         logL, logP = e.eval_model(live[:, :50])
-        assert np.array_equal(logL, live[:, 50]) and np.all(logP == 0)
+        assert np.allclose(logL, live[:, 50], rtol=1e-13, atol=0) and np.all(logP == 0)
         ins = e.insertion_indices()
         assert len(ins) == 6 * K and ins.min() >= 0 and ins.max() <= 1
         assert s["total_evals"] <= s["total_steps"] and s["total_accepted"] <= s["total_evals"]
