@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -64,7 +65,14 @@ struct cpn_ctx {
     double *d_rho, *d_rho2;
     double* d_snew;
     double *d_start_x, *d_start_logL, *d_start_logP;
-    double *d_mean, *d_cov, *d_covwork, *d_V, *d_eigval, *d_eigvec, *d_eigscale, *d_mean_partial, *d_cov_partial;
+    double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
+    // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
+    // side stream concurrently with the chain kernel, writes the other one
+    double *d_eigval[2], *d_eigvec[2], *d_eigscale[2];
+    int eig_cur;
+    bool eig_pending, wait_cov;
+    cudaStream_t side;
+    cudaEvent_t ev_main, ev_cov, ev_eig;
     uint8_t* d_cycle;
     int cycle_len;
     NSState* d_state;
@@ -74,9 +82,11 @@ struct cpn_ctx {
     long long batches_enqueued;
     unsigned long long chain_counter;
     long long chains_since_stats;
+    long long eig_calls;
     LSE* d_trap_partial;
     double* d_scalar;
     double* d_rec;              // [N][D+2] record scratch of the host protocol
+    int* d_sweeps;
     NSState* h_state;           // pinned
     cudaEvent_t ev;
     bool live_ready;
@@ -87,6 +97,9 @@ template <class T>
 static int dalloc(T** p, size_t n) {
     CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
     CK(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    // the memset runs on the legacy default stream, the kernels on non-blocking streams: without this
+    // the zeroing could land after a kernel has written the buffer
+    CK(cudaStreamSynchronize(0));
     return 0;
 }
 
@@ -237,6 +250,10 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_cov, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_eig, cudaEventDisableTiming));
     const int N = c->N, D = c->D, Dp = c->Dp;
     if (dalloc(&c->d_lo, D) || dalloc(&c->d_hi, D) || dalloc(&c->d_blob, std::max<size_t>(nb, 1))) return 1;
     CK(cudaMemcpy(c->d_lo, lo, D * sizeof(double), cudaMemcpyHostToDevice));
@@ -252,13 +269,14 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         dalloc(&c->d_new_steps, N) || dalloc(&c->d_new_acc, N) || dalloc(&c->d_new_start, N) || dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
-    if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, (size_t)D * D) ||
-        dalloc(&c->d_V, (size_t)D * D) || dalloc(&c->d_eigval, D) || dalloc(&c->d_eigvec, (size_t)D * Dp) ||
-        dalloc(&c->d_eigscale, D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
+    if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
+        dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
+        dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigvec[0], (size_t)D * Dp) || dalloc(&c->d_eigscale[0], D) ||
+        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp) || dalloc(&c->d_eigscale[1], D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
         dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))
         return 1;
     if (dalloc(&c->d_state, 1) || dalloc(&c->d_trap_partial, 256) || dalloc(&c->d_scalar, 4) ||
-        dalloc(&c->d_rec, (size_t)N * (D + 2)))
+        dalloc(&c->d_rec, (size_t)N * (D + 2)) || dalloc(&c->d_sweeps, 1))
         return 1;
     CK(cudaMallocHost((void**)&c->h_state, sizeof(NSState)));
     // DefaultProposalCycle weights 5:5:10:10 laid out deterministically until cpn_set_cycle is called
@@ -281,16 +299,19 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->side);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_new_x, c->d_new_logL,
                     c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_new_start, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
-                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_eigval, c->d_eigvec, c->d_eigscale,
+                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
     cudaEventDestroy(c->ev);
+    cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_cov); cudaEventDestroy(c->ev_eig);
+    cudaStreamDestroy(c->side);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -319,42 +340,77 @@ static int sort_live(cpn_ctx* c) {
     return 0;
 }
 
+// mean, covariance, eigen-decomposition of the live ensemble into eigen buffer `buf`, on stream `st`
+static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events) {
+    const int D = c->D, N = c->N;
+    if (D > kStatThreads) return fail("ensemble statistics support dim <= %d", kStatThreads);
+    k_mean_partial<<<kStatBlocks, kStatThreads, 0, st>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
+    k_mean_final<<<(D + 127) / 128, 128, 0, st>>>(c->d_mean_partial, kStatBlocks, N, D, c->d_mean);
+    k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), st>>>(
+        c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
+    k_cov_final<<<(D * D + 127) / 128, 128, 0, st>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
+    if (record_events) CK(cudaEventRecord(c->ev_cov, st));     // the live rows have been read
+    const size_t sm = 4 * (size_t)D * (D | 1) * sizeof(double);
+    const int use_smem = sm <= 200 * 1024;
+    if (use_smem && sm > 40 * 1024)
+        CK(cudaFuncSetAttribute(k_jacobi_eigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    c->eig_calls += 1;
+    k_jacobi_eigh<<<1, kJacobiThreads, use_smem ? sm : 0, st>>>(c->d_cov, c->d_covwork, use_smem, D, c->Dp, c->d_eigval[buf],
+                                                               c->d_eigvec[buf], c->d_eigscale[buf], c->d_sweeps);
+    CKL();
+    if (record_events) CK(cudaEventRecord(c->ev_eig, st));
+    c->chains_since_stats = 0;
+    c->launches += 5;
+    return 0;
+}
+
+// a refresh started on the side stream during the previous batch becomes current
+static int adopt_pending_stats(cpn_ctx* c) {
+    if (!c->eig_pending) return 0;
+    CK(cudaStreamWaitEvent(c->stream, c->ev_eig, 0));
+    c->eig_cur ^= 1;
+    c->eig_pending = false;
+    return 0;
+}
+
 extern "C" int cpn_update_ensemble_stats(cpn_ctx* c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));
-    const int D = c->D, N = c->N;
-    if (D > kStatThreads) return fail("ensemble statistics support dim <= %d", kStatThreads);
-    k_mean_partial<<<kStatBlocks, kStatThreads, 0, c->stream>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
-    k_mean_final<<<(D + 127) / 128, 128, 0, c->stream>>>(c->d_mean_partial, kStatBlocks, N, D, c->d_mean);
-    k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), c->stream>>>(
-        c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
-    k_cov_final<<<(D * D + 127) / 128, 128, 0, c->stream>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
-    {
-        const size_t sm = 2 * (size_t)D * D * sizeof(double);
-        const int use_smem = sm <= 160 * 1024;
-        if (use_smem && sm > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_jacobi_eigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_jacobi_eigh<<<1, 256, use_smem ? sm : 0, c->stream>>>(c->d_cov, c->d_covwork, c->d_V, use_smem, D, c->Dp,
-                                                               c->d_eigval, c->d_eigvec, c->d_eigscale);
-    }
-    CKL();
-    c->chains_since_stats = 0;
-    c->launches += 5;
+    if (adopt_pending_stats(c)) return 1;
+    if (launch_stats(c, c->stream, c->eig_cur ^ 1, false)) return 1;
+    c->eig_cur ^= 1;
+    return 0;
+}
+
+// refresh on the side stream: reads the live set as it is now (after everything already enqueued on
+// the main stream), overlaps with the chain kernel of the coming batch, is adopted by the batch after
+static int start_async_stats(cpn_ctx* c) {
+    CK(cudaEventRecord(c->ev_main, c->stream));
+    CK(cudaStreamWaitEvent(c->side, c->ev_main, 0));
+    if (launch_stats(c, c->side, c->eig_cur ^ 1, true)) return 1;
+    c->eig_pending = true;
+    c->wait_cov = true;
     return 0;
 }
 
 extern "C" int cpn_get_ensemble_stats(cpn_ctx* c, double* mean, double* cov, double* eigval, double* eigvec) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));
+    if (adopt_pending_stats(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     const int D = c->D;
+    if (getenv("CPN_DEBUG")) {
+        int sw = -1;
+        CK(cudaMemcpy(&sw, c->d_sweeps, sizeof(int), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[cpn] jacobi sweeps of the last refresh: %d (refresh #%lld)\n", sw, c->eig_calls);
+    }
     if (mean) CK(cudaMemcpy(mean, c->d_mean, D * sizeof(double), cudaMemcpyDeviceToHost));
     if (cov) CK(cudaMemcpy(cov, c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost));
-    if (eigval) CK(cudaMemcpy(eigval, c->d_eigval, D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (eigval) CK(cudaMemcpy(eigval, c->d_eigval[c->eig_cur], D * sizeof(double), cudaMemcpyDeviceToHost));
     if (eigvec) {
         // numpy layout: eigvec[k][i] = component k of eigenvector i
         std::vector<double> rows((size_t)D * c->Dp);
-        CK(cudaMemcpy(rows.data(), c->d_eigvec, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rows.data(), c->d_eigvec[c->eig_cur], rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int i = 0; i < D; ++i)
             for (int k = 0; k < D; ++k) eigvec[(size_t)k * D + i] = rows[(size_t)i * c->Dp + k];
     }
@@ -369,7 +425,7 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     p->lo = c->d_lo; p->hi = c->d_hi;
     p->cycle = c->d_cycle; p->cycle_len = c->cycle_len;
     p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
-    p->eig_scale = c->d_eigscale; p->eig_vec = c->d_eigvec;
+    p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
     p->state = c->d_state;
     p->maxmcmc = c->cfg.maxmcmc;
     p->chain_base = c->chain_counter;
@@ -386,7 +442,7 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
     CK(cudaSetDevice(c->cfg.device));
     init_state(c, c->h_state);
     if (push_state(c)) return 1;
-    c->dead_upper = 0; c->batches_enqueued = 0; c->chain_counter = 0; c->cur = 0;
+    c->dead_upper = 0; c->batches_enqueued = 0; c->chain_counter = 0; c->cur = 0; c->eig_calls = 0;
     EvalParams e;
     memset(&e, 0, sizeof e);
     e.x = c->d_x; e.logL = c->d_logL; e.logP = c->d_logP; e.n = c->N; e.D = c->D; e.Dp = c->Dp;
@@ -530,6 +586,10 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     m.new_x = c->d_new_x; m.new_logL = c->d_new_logL; m.new_logP = c->d_new_logP;
     m.dead_x = c->d_dead_x; m.dead_logL = c->d_dead_logL; m.dead_logP = c->d_dead_logP;
     m.insertion = c->d_ins;
+    if (c->wait_cov) {     // an asynchronous refresh must have read the live rows before they are overwritten
+        CK(cudaStreamWaitEvent(c->stream, c->ev_cov, 0));
+        c->wait_cov = false;
+    }
     k_merge_commit<<<(c->N + T - 1) / T, T, 0, c->stream>>>(m);
     CKL();
     c->cur ^= 1;
@@ -539,9 +599,12 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
 
 extern "C" int cpn_ns_step(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
-    // refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254)
+    CK(cudaSetDevice(c->cfg.device));
+    if (adopt_pending_stats(c)) return 1;
+    // refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254); the refresh runs
+    // beside this batch's chains and serves the next batch
     if (c->chains_since_stats >= std::max(1, c->N / 4))
-        if (cpn_update_ensemble_stats(c)) return 1;
+        if (start_async_stats(c)) return 1;
     if (cpn_select_and_accumulate(c, K)) return 1;
     if (cpn_evolve_batch(c, K)) return 1;
     return cpn_insert_batch(c, K);

@@ -91,34 +91,46 @@ __global__ void k_cov_final(const double* __restrict__ partial, int nb, int n, i
     cov[ent] = s / (double)((D == 1) ? n : n - 1);
 }
 
-// Cyclic Jacobi, round-robin ordering: n/2 disjoint rotations per round, n-1 rounds per sweep.
-// The input matrix Ain (D x D, row-major) is copied into the working matrix A, which together with
-// the accumulated rotations V lives in shared memory when 2*D*D doubles fit (D <= 100), otherwise in
-// the global scratch buffers.  On exit eigval is ascending (np.linalg.eigh order),
+// Cyclic two-sided Jacobi with round-robin (parallel) ordering: n/2 disjoint rotations per round,
+// n-1 rounds per sweep, one block of kJacobiThreads threads.
+// A round applies all of its rotations at once: with J the product of the round's disjoint plane
+// rotations, A' = J^T A J is computed element-wise from the OLD matrix (every entry needs the four
+// entries at the crossing of its row pair and its column pair) into a second buffer, so a round costs
+// two block barriers.  A, A', V, V' live in shared memory with an odd leading dimension when they fit
+// (D <= 80), otherwise in global scratch.  On exit eigval is ascending (np.linalg.eigh order),
 // eig_vec[i][0..D) = i-th eigenvector (a ROW here), eig_scale[i] = sqrt|eigval[i]| (proposal.py:339).
-__global__ void __launch_bounds__(256) k_jacobi_eigh(const double* __restrict__ Ain, double* Aglob, double* Vglob,
-                                                     int use_smem, int D, int Dp, double* __restrict__ eigval,
-                                                     double* __restrict__ eig_vec, double* __restrict__ eig_scale) {
+constexpr int kJacobiThreads = 1024;
+
+__global__ void __launch_bounds__(kJacobiThreads) k_jacobi_eigh(const double* __restrict__ C, double* scratch, int use_smem,
+                                                                int D, int Dp, double* __restrict__ eigval,
+                                                                double* __restrict__ eig_vec, double* __restrict__ eig_scale,
+                                                                int* __restrict__ sweeps_out) {
     extern __shared__ double jsm[];
-    __shared__ double cs[128], sn[128];
-    __shared__ int pp[128], qq[128];
-    __shared__ double red[256];
+    __shared__ double alpha[256], beta[256];     // row/column i becomes alpha_i * (i) + beta_i * (partner_i)
+    __shared__ int partner[256];
+    __shared__ double red[kJacobiThreads];
     __shared__ int converged;
     const int tid = threadIdx.x, nt = blockDim.x;
-    double* A = use_smem ? jsm : Aglob;
-    double* V = use_smem ? jsm + D * D : Vglob;
+    const int LD = D | 1;
+    double* base = use_smem ? jsm : scratch;
+    double* A = base;
+    double* A2 = base + (size_t)D * LD;
+    double* V = base + 2 * (size_t)D * LD;
+    double* V2 = base + 3 * (size_t)D * LD;
     const int n = (D + 1) & ~1;            // even number of players; index D (if any) is a bye
     const int half = n / 2;
     for (int i = tid; i < D * D; i += nt) {
-        A[i] = Ain[i];
-        V[i] = ((i / D) == (i % D)) ? 1.0 : 0.0;
+        const int r = i / D, c = i % D;
+        A[r * LD + c] = C[i];
+        V[r * LD + c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
-    for (int sweep = 0; sweep < 30; ++sweep) {
+    int sweep = 0;
+    for (; sweep < 30; ++sweep) {
         // convergence: off-diagonal Frobenius norm against the diagonal
         double off = 0.0, dia = 0.0;
         for (int i = tid; i < D * D; i += nt) {
-            const double a = A[i];
+            const double a = A[(i / D) * LD + (i % D)];
             if ((i / D) == (i % D)) dia += a * a; else off += a * a;
         }
         red[tid] = off;
@@ -135,64 +147,52 @@ __global__ void __launch_bounds__(256) k_jacobi_eigh(const double* __restrict__ 
         if (converged) break;
         for (int r = 0; r < n - 1; ++r) {
             if (tid < half) {
-                int i = (r + tid) % (n - 1);
-                int j = (tid == 0) ? n - 1 : (r + n - 1 - tid) % (n - 1);
-                int p = min(i, j), q = max(i, j);
+                const int i = (r + tid) % (n - 1);
+                const int j = (tid == 0) ? n - 1 : (r + n - 1 - tid) % (n - 1);
+                const int p = min(i, j), q = max(i, j);
                 double c = 1.0, s = 0.0;
                 if (q < D) {
-                    const double apq = A[p * D + q];
+                    const double apq = A[p * LD + q];
                     if (apq != 0.0) {
-                        const double theta = (A[q * D + q] - A[p * D + p]) / (2.0 * apq);
+                        const double theta = (A[q * LD + q] - A[p * LD + p]) / (2.0 * apq);
                         const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
                         c = 1.0 / sqrt(t * t + 1.0);
                         s = t * c;
                     }
-                } else {
-                    p = -1;
-                }
-                pp[tid] = p; qq[tid] = q; cs[tid] = c; sn[tid] = s;
-            }
-            __syncthreads();
-            // rows: A <- J^T A
-            for (int w = tid; w < half * D; w += nt) {
-                const int k = w / D, m = w % D;
-                const int p = pp[k], q = qq[k];
-                if (p >= 0) {
-                    const double c = cs[k], s = sn[k];
-                    const double ap = A[p * D + m], aq = A[q * D + m];
-                    A[p * D + m] = c * ap - s * aq;
-                    A[q * D + m] = s * ap + c * aq;
+                    // J = [[c, s], [-s, c]] on (p, q): row'_p = c row_p - s row_q ; row'_q = c row_q + s row_p
+                    alpha[p] = c; beta[p] = -s; partner[p] = q;
+                    alpha[q] = c; beta[q] = s;  partner[q] = p;
+                } else if (p < D) {
+                    alpha[p] = 1.0; beta[p] = 0.0; partner[p] = p;       // paired with the bye
                 }
             }
             __syncthreads();
-            // columns: A <- A J, V <- V J
-            for (int w = tid; w < half * D; w += nt) {
-                const int k = w / D, m = w % D;
-                const int p = pp[k], q = qq[k];
-                if (p >= 0) {
-                    const double c = cs[k], s = sn[k];
-                    const double ap = A[m * D + p], aq = A[m * D + q];
-                    A[m * D + p] = c * ap - s * aq;
-                    A[m * D + q] = s * ap + c * aq;
-                    const double vp = V[m * D + p], vq = V[m * D + q];
-                    V[m * D + p] = c * vp - s * vq;
-                    V[m * D + q] = s * vp + c * vq;
-                }
+            for (int w = tid; w < D * D; w += nt) {
+                const int i = w / D, j = w % D;
+                const int pi = partner[i], pj = partner[j];
+                const double ai = alpha[i], bi = beta[i], aj = alpha[j], bj = beta[j];
+                const double t0 = ai * A[i * LD + j] + bi * A[pi * LD + j];
+                const double t1 = ai * A[i * LD + pj] + bi * A[pi * LD + pj];
+                A2[i * LD + j] = aj * t0 + bj * t1;
+                V2[i * LD + j] = aj * V[i * LD + j] + bj * V[i * LD + pj];
             }
             __syncthreads();
+            double* t = A; A = A2; A2 = t;
+            t = V; V = V2; V2 = t;
         }
     }
+    if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep;
     // ascending order by counting, ties by index
     for (int i = tid; i < D; i += nt) {
-        const double li = A[i * D + i];
+        const double li = A[i * LD + i];
         int rank = 0;
         for (int j = 0; j < D; ++j) {
-            const double lj = A[j * D + j];
+            const double lj = A[j * LD + j];
             rank += (lj < li) || (lj == li && j < i);
         }
         eigval[rank] = li;
         eig_scale[rank] = sqrt(fabs(li));
-        for (int k = 0; k < Dp; ++k) eig_vec[(size_t)rank * Dp + k] = (k < D) ? V[k * D + i] : 0.0;
+        for (int k = 0; k < Dp; ++k) eig_vec[(size_t)rank * Dp + k] = (k < D) ? V[k * LD + i] : 0.0;
     }
 }
 

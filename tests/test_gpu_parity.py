@@ -260,6 +260,16 @@ def test_ensemble_covariance_and_eigen(golden):
         assert rel_close(cov, np.cov(X.T), 1e-11, 1e-12)
         assert rel_close(w, np.linalg.eigvalsh(np.cov(X.T)), 1e-9, 1e-10)
         assert np.max(np.abs(v.T @ v - np.eye(50))) < 1e-12
+        # warm-started refreshes (previous eigenvectors as the starting basis) on drifting ensembles
+        for k in range(20):
+            X = X * (1.0 + 0.05 * rs.normal(size=(1, 50))) + 0.1 * rs.normal(size=X.shape)
+            e.set_live(np.concatenate((X, np.arange(4000.0)[:, None], np.zeros((4000, 1))), axis=1))
+            mean, cov, w, v = e.ensemble_stats()
+            ref = np.cov(X.T)
+            assert rel_close(cov, ref, 1e-11, 1e-12)
+            assert rel_close(w, np.linalg.eigvalsh(ref), 1e-9, 1e-10), k
+            assert np.max(np.abs(v.T @ v - np.eye(50))) < 1e-11
+            assert np.max(np.abs(ref @ v - v * w)) < 1e-10 * np.max(np.abs(w))
 
 
 def test_ns_batch_loop_matches_reference(golden):
