@@ -71,6 +71,7 @@ struct cpn_ctx {
     double *d_eigval[2], *d_eigvec[2], *d_eigscale[2];
     int eig_cur;
     bool eig_pending, wait_cov;
+    int eig_pending_age;        // batches started since the pending refresh was launched
     cudaStream_t side;
     cudaEvent_t ev_main, ev_cov, ev_eig;
     uint8_t* d_cycle;
@@ -355,7 +356,9 @@ static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events
     if (use_smem && sm > 40 * 1024)
         CK(cudaFuncSetAttribute(k_jacobi_eigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     c->eig_calls += 1;
-    k_jacobi_eigh<<<1, kJacobiThreads, use_smem ? sm : 0, st>>>(c->d_cov, c->d_covwork, use_smem, D, c->Dp, c->d_eigval[buf],
+    // beside a running chain kernel only a small block finds room on an SM (registers); alone, use them all
+    const int jt = record_events ? 256 : kJacobiThreads;
+    k_jacobi_eigh<<<1, jt, use_smem ? sm : 0, st>>>(c->d_cov, c->d_covwork, use_smem, D, c->Dp, c->d_eigval[buf],
                                                                c->d_eigvec[buf], c->d_eigscale[buf], c->d_sweeps);
     CKL();
     if (record_events) CK(cudaEventRecord(c->ev_eig, st));
@@ -389,6 +392,7 @@ static int start_async_stats(cpn_ctx* c) {
     CK(cudaStreamWaitEvent(c->side, c->ev_main, 0));
     if (launch_stats(c, c->side, c->eig_cur ^ 1, true)) return 1;
     c->eig_pending = true;
+    c->eig_pending_age = 0;
     c->wait_cov = true;
     return 0;
 }
@@ -600,10 +604,13 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
 extern "C" int cpn_ns_step(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
     CK(cudaSetDevice(c->cfg.device));
-    if (adopt_pending_stats(c)) return 1;
-    // refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254); the refresh runs
-    // beside this batch's chains and serves the next batch
-    if (c->chains_since_stats >= std::max(1, c->N / 4))
+    // Refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254).  The refresh runs
+    // on the side stream beside the chain kernels of two batches and is adopted by the batch after those
+    // (fixed latency, so the schedule - and with it every result - is deterministic); one refresh is in
+    // flight at a time, which makes the cadence max(2 batches, nlive/4 chains).
+    if (c->eig_pending && ++c->eig_pending_age >= 2)
+        if (adopt_pending_stats(c)) return 1;
+    if (!c->eig_pending && c->chains_since_stats >= std::max(1, c->N / 4))
         if (start_async_stats(c)) return 1;
     if (cpn_select_and_accumulate(c, K)) return 1;
     if (cpn_evolve_batch(c, K)) return 1;
