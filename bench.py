@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.2)      # the recipe samples every 200 ms; NVML queries are not free
 
     def result(self):
         self.stop_flag = True

@@ -291,7 +291,15 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     }
     init_state(c, c->h_state);
     if (push_state(c)) return 1;
-    if (grow_logs(c, std::max<long long>(4LL * N, 1 << 16))) return 1;
+    // Dead-point log: a run produces about nlive * (H + a few sqrt(H)) dead points; HBM is plentiful
+    // (180 GB), re-allocation mid-run is not free (allocation + copy + implicit synchronisation), so
+    // reserve 128 * nlive rows up front (bounded by 8 GB) and double beyond that.
+    {
+        long long rows = 128LL * N;
+        const long long cap_rows = (8LL << 30) / ((long long)Dp * 8 + 40);
+        rows = std::max<long long>(std::min(rows, cap_rows), 4LL * N);
+        if (grow_logs(c, rows)) return 1;
+    }
     *out = c;
     return 0;
 }
