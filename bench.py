@@ -130,12 +130,14 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nlive", type=int, default=NLIVE_PER_GPU)
     ap.add_argument("--k", type=int, default=K_PER_GPU)
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--comm", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU exchange of the replacements: fused into the chain kernel over peer memory, or NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-run", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -184,7 +186,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    N, K = args.nlive, args.k
+    # weak scaling: nlive and chains per batch grow with the number of GPUs; every rank holds a replica
+    # of the live set and evolves its slice of the chains (cpnest_b200/sharded.py)
+    N, K = args.nlive * world, args.k * world
     bounds = [[-10.0, 10.0]] * DIM
     np.random.seed(SEED)
     cycle = DefaultProposalCycle().device_cycle()        # drawn like the reference's (proposal.py:71-75)
@@ -192,12 +196,18 @@ def main():
     # ------------------------------------------------------------------------------------------
     # device-resident run: `value`
     # ------------------------------------------------------------------------------------------
-    eng = Engine("gaussian_iid", bounds, nlive=N, maxmcmc=MAXMCMC, seed=SEED + 1000 * rank, device=local_rank, lanes=args.lanes)
+    eng = Engine("gaussian_iid", bounds, nlive=N, maxmcmc=MAXMCMC, seed=SEED, device=local_rank, lanes=args.lanes,
+                 rank=rank, world_size=world)
     eng.set_stream(stream.cuda_stream)
     eng.set_cycle(cycle)
-    eng.init_prior()
+    eng.init_prior()                                     # same seed everywhere: identical replicas, no broadcast
+    if world > 1:
+        from cpnest_b200.sharded import ShardedEngine
+        drv = ShardedEngine(eng, comm=args.comm)
+    else:
+        drv = eng
     for _ in range(args.warmup):
-        eng.ns_step(K)
+        drv.ns_step(K)
     torch.cuda.synchronize()
     s0 = eng.state()
     l0 = eng.launch_count()
@@ -207,16 +217,17 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
-        eng.ns_step(K)
+        drv.ns_step(K)
     ev1.record(stream)
     barrier()
     dt_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clk = clocks.result()
     s1 = eng.state()
     launches = eng.launch_count() - l0
-    evals = sum_over_ranks(s1["total_evals"] - s0["total_evals"])
-    steps_mcmc = sum_over_ranks(s1["total_steps"] - s0["total_steps"])
-    accepted = sum_over_ranks(s1["total_accepted"] - s0["total_accepted"])
+    # the counters are sums over the gathered per-chain outcomes: already global on every rank
+    evals = s1["total_evals"] - s0["total_evals"]
+    steps_mcmc = s1["total_steps"] - s0["total_steps"]
+    accepted = s1["total_accepted"] - s0["total_accepted"]
     value = evals / (dt_ms * 1e-3)
 
     # ---- the dominant kernel alone: per-launch duration of k_mh_chains, live, with events ----
@@ -227,20 +238,21 @@ def main():
         a = eng.state()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        eng.evolve_batch(K)
+        eng.evolve_batch(K)                 # exactly one launch of k_mh_chains (this rank's chains)
         e1.record(stream)
+        if world > 1:
+            drv.exchange(K)
         eng.insert_batch(K)
         torch.cuda.synchronize()
         b = eng.state()
-        # evolve_batch = k_mh_chains + the tiny k_chain_corr; the latter is < 1% (profiles/)
         kev.append(e0.elapsed_time(e1))
-        mh_steps.append(b["total_steps"] - a["total_steps"])
+        mh_steps.append((b["total_steps"] - a["total_steps"]) / world)
     k_ms = float(np.mean(kev))
     k_steps = float(np.mean(mh_steps))
     # algorithmic bytes of one launch: gathers 13.33*D bytes per MCMC step of the
     # default cycle + read and write one point (8D+16 bytes) per chain
     bytes_per_step = 8.0 * DIM * (3 / 6 + 1 / 6 + 2 / 3 + 1 / 3)
-    alg_bytes = k_steps * bytes_per_step + K * 2.0 * (8 * DIM + 16)
+    alg_bytes = k_steps * bytes_per_step + (K / world) * 2.0 * (8 * DIM + 16)
     peak, peak_src = peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -261,7 +273,7 @@ def main():
     if not args.no_full_run:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng.run(K, tolerance=0.1)
+        drv.run(K, tolerance=0.1)
         torch.cuda.synchronize()
         t_rest = time.perf_counter() - t0
         st = eng.state()
@@ -272,11 +284,14 @@ def main():
                 "H": sf["info"], "batches": st["batches"], "dead_points": sf["iteration"], "nmcmc_final": st["nmcmc"],
                 "total_evals": sf["total_evals"], "total_mcmc_steps": sf["total_steps"],
                 "remaining_run_wall_s": t_rest, "rank": rank}
+    if world > 1:
+        drv.close()
     eng.close()
 
     # ------------------------------------------------------------------------------------------
-    # host-buffer protocol: `e2e`
+    # host-buffer protocol: `e2e` (every rank serves its own K requests per step from its own host)
     # ------------------------------------------------------------------------------------------
+    N, K = args.nlive, args.k
     eng = Engine("gaussian_iid", bounds, nlive=N, maxmcmc=MAXMCMC, seed=SEED + 1000 * rank + 7, device=local_rank, lanes=args.lanes)
     eng.set_stream(stream.cuda_stream)
     eng.set_cycle(cycle)
@@ -292,7 +307,7 @@ def main():
     # the device pool mirrors the host live set slot by slot
     eng.set_live(live)
     host_slots = np.arange(N)                           # live[i] sits in device pool slot host_slots[i]
-    nm = max(20, s1["nmcmc"] // 4)                      # fixed chain length for the protocol run
+    nm = max(20, s1["nmcmc"])                           # the chain length the device-resident run settled on
     e2e_evals = 0
 
     def host_step():
@@ -339,6 +354,7 @@ def main():
             "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "gaussian50d_iid_bounds[-10,10]_nlive%d_per_gpu_K%d_mh_default_cycle" % (N, K),
+                       "multi_gpu": ("chains sharded over %d ranks, live set (nlive=%d) replicated, exchange=%s" % (world, N * world, args.comm)) if world > 1 else "single GPU",
                        "dim": DIM, "nlive_per_gpu": N, "chains_per_batch_per_gpu": K, "maxmcmc": MAXMCMC,
                        "chain_length": "adaptive (start/end correlation target 0.1)", "seed": SEED,
                        "step": "one nested-sampling batch: select+accumulate, evolve K chains, insert",

@@ -64,12 +64,19 @@ SIGNATURES = {
     "cpn_select_and_accumulate": (C.c_int, [_vp, C.c_int32]),
     "cpn_evolve_batch": (C.c_int, [_vp, C.c_int32]),
     "cpn_insert_batch": (C.c_int, [_vp, C.c_int32]),
+    "cpn_staging_bytes": (C.c_int64, [_vp]),
+    "cpn_set_staging": (C.c_int, [_vp, _P(_vp), C.c_int32]),
+    "cpn_shard_record_doubles": (C.c_int64, [_vp]),
+    "cpn_shard_range": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, _ip]),
+    "cpn_pack_shard": (C.c_int, [_vp, C.c_int32, _vp]),
+    "cpn_unpack_shards": (C.c_int, [_vp, C.c_int32, _vp]),
     "cpn_ns_step": (C.c_int, [_vp, C.c_int32]),
     "cpn_run": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_double, _P(C.c_int64)]),
     "cpn_finalise": (C.c_int, [_vp, _dp, _dp]),
     "cpn_synchronize": (C.c_int, [_vp]),
     "cpn_get_state": (C.c_int, [_vp, _P(cpn_state)]),
     "cpn_set_nmcmc": (C.c_int, [_vp, C.c_int32]),
+    "cpn_set_tolerance": (C.c_int, [_vp, C.c_double]),
     "cpn_get_live": (C.c_int, [_vp, _dp]),
     "cpn_num_dead": (C.c_int64, [_vp]),
     "cpn_get_dead": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp, _dp]),

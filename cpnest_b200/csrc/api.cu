@@ -60,8 +60,14 @@ struct cpn_ctx {
     int Npad;
     double* d_sort_keys;
     int* d_sort_idx;
+    // replacement staging: one block [x N*Dp | logL N | logP N | steps N | acc N | start N | evals N],
+    // private by default, or a caller-provided (symmetric, peer-mapped) block for multi-GPU runs
+    void* d_stage_own;
+    void* stage_peer[kMaxPeers];
+    int n_peers;                // 0: private staging; else == world_size, stage_peer[rank] is the local block
+    int rank, world;
     double *d_new_x, *d_new_logL, *d_new_logP;
-    int *d_new_steps, *d_new_acc, *d_new_start, *d_rank;
+    int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_rank;
     double *d_rho, *d_rho2;
     double* d_snew;
     double *d_start_x, *d_start_logL, *d_start_logP;
@@ -214,6 +220,49 @@ static void init_state(cpn_ctx* c, NSState* s) {
     s->rho_max = -1.0;
 }
 
+static size_t stage_off(int N, int Dp, int which) {
+    // byte offsets of the arrays inside a staging block for N chains
+    size_t o = 0;
+    const size_t sizes[7] = {(size_t)N * Dp * 8, (size_t)N * 8, (size_t)N * 8, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4};
+    for (int i = 0; i < which; ++i) o += (sizes[i] + 255) & ~(size_t)255;
+    return o;
+}
+static size_t stage_bytes(int N, int Dp) { return stage_off(N, Dp, 7); }
+static void bind_staging(cpn_ctx* c, void* base) {
+    char* b = (char*)base;
+    c->d_new_x = (double*)(b + stage_off(c->N, c->Dp, 0));
+    c->d_new_logL = (double*)(b + stage_off(c->N, c->Dp, 1));
+    c->d_new_logP = (double*)(b + stage_off(c->N, c->Dp, 2));
+    c->d_new_steps = (int*)(b + stage_off(c->N, c->Dp, 3));
+    c->d_new_acc = (int*)(b + stage_off(c->N, c->Dp, 4));
+    c->d_new_start = (int*)(b + stage_off(c->N, c->Dp, 5));
+    c->d_new_evals = (int*)(b + stage_off(c->N, c->Dp, 6));
+}
+
+extern "C" int64_t cpn_staging_bytes(cpn_ctx* c) { return c ? (int64_t)stage_bytes(c->N, c->Dp) : -1; }
+
+// Multi-GPU: `peers[r]` is the address, valid on THIS device, of rank r's staging block (peer-mapped
+// symmetric memory; peers[rank] is the local block).  From then on every chain writes its outcome
+// into all blocks, i.e. the exchange of the replacements is done by the chain kernel itself.
+extern "C" int cpn_set_staging(cpn_ctx* c, void* const* peers, int32_t npeers) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (!peers || npeers == 0) {
+        c->n_peers = 0;
+        bind_staging(c, c->d_stage_own);
+        return 0;
+    }
+    if (npeers != c->world) return fail("cpn_set_staging: %d peer blocks given, world size is %d", npeers, c->world);
+    for (int r = 0; r < npeers; ++r) {
+        if (!peers[r]) return fail("cpn_set_staging: null block for rank %d", r);
+        c->stage_peer[r] = peers[r];
+    }
+    c->n_peers = npeers;
+    bind_staging(c, peers[c->rank]);
+    return 0;
+}
+
 extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double* hi, const void* blob,
                           size_t blob_bytes, cpn_ctx** out) {
     if (!cfg || !lo || !hi || !out) return fail("cpn_create: null argument");
@@ -266,8 +315,16 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     c->Npad = 1;
     while (c->Npad < N) c->Npad <<= 1;
     if (dalloc(&c->d_sort_keys, c->Npad) || dalloc(&c->d_sort_idx, c->Npad)) return 1;
-    if (dalloc(&c->d_new_x, (size_t)N * Dp) || dalloc(&c->d_new_logL, N) || dalloc(&c->d_new_logP, N) ||
-        dalloc(&c->d_new_steps, N) || dalloc(&c->d_new_acc, N) || dalloc(&c->d_new_start, N) || dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
+    {
+        char* blk;
+        if (dalloc(&blk, (size_t)stage_bytes(N, Dp))) return 1;
+        c->d_stage_own = blk;
+        bind_staging(c, blk);
+    }
+    c->rank = std::max(0, cfg->rank);
+    c->world = std::max(1, cfg->world_size);
+    if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
+    if (dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
@@ -310,8 +367,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->side);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
-                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_new_x, c->d_new_logL,
-                    c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_new_start, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
+                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
@@ -443,10 +499,20 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     p->chain_base = c->chain_counter;
     p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
     p->blob = c->d_blob;
-    p->n_out = 1;
-    p->out_x[0] = c->d_new_x; p->out_logL[0] = c->d_new_logL; p->out_logP[0] = c->d_new_logP;
-    p->out_steps[0] = c->d_new_steps; p->out_acc[0] = c->d_new_acc; p->out_start[0] = c->d_new_start;
-    p->counters = c->d_state->batch;
+    const int nout = c->n_peers > 0 ? c->n_peers : 1;
+    p->n_out = nout;
+    for (int o = 0; o < nout; ++o) {
+        // slot 0 is always the local block, the other ranks follow
+        const int r = (o == 0) ? c->rank : (o <= c->rank ? o - 1 : o);
+        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] : (char*)c->d_stage_own;
+        p->out_x[o] = (double*)(b + stage_off(c->N, c->Dp, 0));
+        p->out_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 1));
+        p->out_logP[o] = (double*)(b + stage_off(c->N, c->Dp, 2));
+        p->out_steps[o] = (int*)(b + stage_off(c->N, c->Dp, 3));
+        p->out_acc[o] = (int*)(b + stage_off(c->N, c->Dp, 4));
+        p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
+        p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
+    }
 }
 
 extern "C" int cpn_init_prior(cpn_ctx* c) {
@@ -485,8 +551,9 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, c->N, &G, &E)) return 1;
         if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
         CKL();
-        k_chain_corr<<<c->D + 1, 256, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
-                                                      c->d_new_x, c->d_new_logL, c->d_rho);
+        k_chain_corr<<<c->D + 2, 256, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
+                                                      c->d_new_x, c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc,
+                                                      c->d_new_evals);
         k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N, c->d_rho, c->d_rho2, c->D);   // coordinates only: logL is unconstrained here
         CK(cudaMemcpyAsync(c->d_x, c->d_new_x, (size_t)c->N * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logL, c->d_new_logL, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -564,19 +631,80 @@ extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
     fill_mh(c, &p);
     p.start_mode = START_SURVIVOR;
     p.n_skip = K;
-    p.j0 = 0; p.j1 = K;
+    // this rank's slice of the K chains of the batch (all of them on a single GPU)
+    p.j0 = (int)((long long)K * c->rank / c->world);
+    p.j1 = (int)((long long)K * (c->rank + 1) / c->world);
     int G, E;
-    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, K, &G, &E)) return 1;
+    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, p.j1 - p.j0, &G, &E)) return 1;
     if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
-    CKL();
-    // dependence between chain start and chain end across the batch, for the chain-length control
-    k_chain_corr<<<c->D + 1, 256, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
-                                                  c->d_new_logL, c->d_rho);
     CKL();
     c->chain_counter += (unsigned long long)K;
     c->chains_since_stats += K;
     c->batches_enqueued += 1;
-    c->launches += 2;
+    c->launches += 1;
+    return 0;
+}
+
+// NCCL path of a multi-GPU run: this rank's slice of the staging arrays as one contiguous record
+// block [chains][Dp + 4] doubles {x.., logL, logP, (steps, acc), (start, evals)}, and back.
+__global__ void k_pack_shard(int j0, int n, int Dp, const double* x, const double* logL, const double* logP, const int* steps,
+                             const int* acc, const int* start, const int* evals, double* rec) {
+    const int S = Dp + 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * S) return;
+    const int r = i / S, d = i % S, j = j0 + r;
+    double v;
+    if (d < Dp) v = x[(size_t)j * Dp + d];
+    else if (d == Dp) v = logL[j];
+    else if (d == Dp + 1) v = logP[j];
+    else if (d == Dp + 2) v = __hiloint2double(acc[j], steps[j]);
+    else v = __hiloint2double(evals[j], start[j]);
+    rec[i] = v;
+}
+__global__ void k_unpack_shards(int K, int Dp, const double* rec, double* x, double* logL, double* logP, int* steps, int* acc,
+                                int* start, int* evals) {
+    const int S = Dp + 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * S) return;
+    const int j = i / S, d = i % S;
+    const double v = rec[i];
+    if (d < Dp) x[(size_t)j * Dp + d] = v;
+    else if (d == Dp) logL[j] = v;
+    else if (d == Dp + 1) logP[j] = v;
+    else if (d == Dp + 2) { steps[j] = __double2loint(v); acc[j] = __double2hiint(v); }
+    else { start[j] = __double2loint(v); evals[j] = __double2hiint(v); }
+}
+
+extern "C" int64_t cpn_shard_record_doubles(cpn_ctx* c) { return c ? c->Dp + 4 : -1; }
+
+extern "C" int cpn_shard_range(cpn_ctx* c, int32_t K, int32_t rank, int32_t* j0, int32_t* j1) {
+    if (!c || !j0 || !j1 || rank < 0 || rank >= c->world) return fail("bad argument");
+    *j0 = (int)((long long)K * rank / c->world);
+    *j1 = (int)((long long)K * (rank + 1) / c->world);
+    return 0;
+}
+
+extern "C" int cpn_pack_shard(cpn_ctx* c, int32_t K, void* dev_send) {
+    if (check_K(c, K) || !dev_send) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    const int j0 = (int)((long long)K * c->rank / c->world), j1 = (int)((long long)K * (c->rank + 1) / c->world);
+    const int n = j1 - j0, S = c->Dp + 4, T = 256;
+    if (n > 0)
+        k_pack_shard<<<(n * S + T - 1) / T, T, 0, c->stream>>>(j0, n, c->Dp, c->d_new_x, c->d_new_logL, c->d_new_logP, c->d_new_steps,
+                                                            c->d_new_acc, c->d_new_start, c->d_new_evals, (double*)dev_send);
+    CKL();
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int cpn_unpack_shards(cpn_ctx* c, int32_t K, const void* dev_recv) {
+    if (check_K(c, K) || !dev_recv) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    const int S = c->Dp + 4, T = 256;
+    k_unpack_shards<<<(K * S + T - 1) / T, T, 0, c->stream>>>(K, c->Dp, (const double*)dev_recv, c->d_new_x, c->d_new_logL,
+                                                           c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_new_start, c->d_new_evals);
+    CKL();
+    c->launches += 1;
     return 0;
 }
 
@@ -584,6 +712,13 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
     CK(cudaSetDevice(c->cfg.device));
     const int T = 256;
+    if (!c->staged_external) {
+        // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
+        // control, and the batch counters
+        k_chain_corr<<<c->D + 2, 256, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
+                                                      c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc, c->d_new_evals);
+        c->launches += 1;
+    }
     k_rank_new<<<(K + T - 1) / T, T, T * sizeof(double), c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
     MergeParams m;
     memset(&m, 0, sizeof m);
@@ -723,6 +858,14 @@ extern "C" int cpn_set_nmcmc(cpn_ctx* c, int32_t nmcmc) {
     return push_state(c);
 }
 
+extern "C" int cpn_set_tolerance(cpn_ctx* c, double tolerance) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    c->h_state->tolerance = tolerance;
+    return push_state(c);
+}
+
 extern "C" int cpn_get_live(cpn_ctx* c, double* rows) {
     if (!c || !rows) return fail("null argument");
     CK(cudaSetDevice(c->cfg.device));
@@ -858,9 +1001,11 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
     p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
     p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = std::max(1, std::min(nmcmc, c->cfg.maxmcmc));
     p.j0 = 0; p.j1 = K;
+    p.n_out = 1;                                   // the host protocol is served by one GPU
     int G, E;
     if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, K, &G, &E)) return 1;
     if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    k_batch_counters<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_steps, c->d_new_acc, c->d_new_evals);
     k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K, nullptr, nullptr, 0);
     if (slots) {
         CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -868,7 +1013,7 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
                                                               c->d_new_logP, c->d_x, c->d_logL, c->d_logP);
         c->launches += 1;
     }
-    c->launches += 4;
+    c->launches += 5;
     k_pack_records<<<((int)need + T - 1) / T, T, 0, c->stream>>>(c->d_new_x, c->d_new_logL, c->d_new_logP, K, D, Dp, d_rec);
     CKL();
     CK(cudaMemcpyAsync(replies, d_rec, need * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -950,7 +1095,7 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
     p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.maxmcmc = maxmcmc;
     p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
     p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
-    p.counters = nullptr; p.tape = dtape; p.compat = compat; p.states = dstates;
+    p.tape = dtape; p.compat = compat; p.states = dstates;
     if (kMH[c->cfg.functor](G, E, 1, p, c->stream)) return fail("no replay kernel for G=%d E=%d", G, E);
     CKL();
     CK(cudaStreamSynchronize(c->stream));

@@ -66,7 +66,7 @@ struct MHParams {
     int* out_steps[kMaxPeers];
     int* out_acc[kMaxPeers];
     int* out_start[kMaxPeers];    // live slot the chain started from (-1: given start)
-    unsigned long long* counters; // [0] steps [1] accepted [2] evals [3] failed chains
+    int* out_evals[kMaxPeers];    // likelihood evaluations of the chain
     // replay (parity) mode
     const double* tape;       // [chains][maxmcmc][8]
     int compat;               // fp32 rounding of LivePoint scalars (cpnest/parameter.pyx:96-120)
@@ -362,13 +362,8 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
                 p.out_steps[o][j] = steps;
                 p.out_acc[o][j] = accepted;
                 if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
+                if (p.out_evals[o] != nullptr) p.out_evals[o][j] = evals;
             }
-        }
-        if (g.lane == 0 && p.counters != nullptr) {
-            atomicAdd(p.counters + 0, (unsigned long long)steps);
-            atomicAdd(p.counters + 1, (unsigned long long)accepted);
-            atomicAdd(p.counters + 2, (unsigned long long)evals);
-            if (accepted == 0) atomicAdd(p.counters + 3, 1ull);
         }
     }
 }

@@ -259,13 +259,44 @@ __global__ void k_adapt_nmcmc(NSState* st, int chains, const double* rho, double
     adapt_nmcmc(st, chains, rho, rho2_ema, nrho);
 }
 
+// Sums of the per-chain outcome arrays of a launch -> st->batch[] = {steps, accepted, evals, failed
+// chains}.  Integer sums: the result does not depend on the order, nor on how the chains were split
+// over GPUs.
+__device__ __forceinline__ void block_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals) {
+    __shared__ unsigned long long shc[4][256];
+    const int tid = threadIdx.x;
+    unsigned long long a[4] = {0, 0, 0, 0};
+    for (int j = tid; j < K; j += 256) {
+        a[0] += (unsigned long long)steps[j];
+        a[1] += (unsigned long long)acc[j];
+        a[2] += (unsigned long long)(evals != nullptr ? evals[j] : 0);
+        a[3] += (acc[j] == 0) ? 1ull : 0ull;
+    }
+    for (int k = 0; k < 4; ++k) shc[k][tid] = a[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w)
+            for (int k = 0; k < 4; ++k) shc[k][tid] += shc[k][tid + w];
+        __syncthreads();
+    }
+    if (tid == 0)
+        for (int k = 0; k < 4; ++k) st->batch[k] = shc[k][0];
+}
+__global__ void __launch_bounds__(256) k_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals) {
+    block_batch_counters(st, K, steps, acc, evals);
+}
+
 // corr_d(start, end) across the K chains of the batch, d in [0, D] (d == D is logL).
-// One block per d; fixed-shape tree reduction (deterministic).
-__global__ void __launch_bounds__(256) k_chain_corr(const NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,
+// One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
+__global__ void __launch_bounds__(256) k_chain_corr(NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,
                                                     const double* __restrict__ live_x, const double* __restrict__ live_logL,
                                                     const double* __restrict__ new_x, const double* __restrict__ new_logL,
-                                                    double* __restrict__ rho) {
+                                                    double* __restrict__ rho, const int* steps, const int* acc, const int* evals) {
     if (st->done) return;
+    if (blockIdx.x == D + 1) {
+        block_batch_counters(st, K, steps, acc, evals);
+        return;
+    }
     __shared__ double sh[5][256];
     const int d = blockIdx.x, tid = threadIdx.x;
     // shift by the first chain's values to keep the sums well conditioned

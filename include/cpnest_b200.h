@@ -119,6 +119,20 @@ int cpn_evolve_batch(cpn_ctx* ctx, int32_t K);
 /* OrderedLivePoints.insert_live_point / remove_n_worst_points + insertion indices
  * (cpnest/NestedSampling.py:44-85, 343-366).  Asynchronous. */
 int cpn_insert_batch(cpn_ctx* ctx, int32_t K);
+/* ---- multi-GPU (one process per GPU; every rank holds a replica of the live set and evolves its
+ * slice [K*rank/world, K*(rank+1)/world) of the K chains of a batch).  The exchange step between
+ * cpn_evolve_batch and cpn_insert_batch is either
+ *   fused : cpn_set_staging() with peer-mapped staging blocks - the chain kernel itself stores every
+ *           finished chain into all ranks' blocks over NVLink; the caller only needs a barrier; or
+ *   NCCL  : cpn_pack_shard() -> all-gather of [chains][cpn_shard_record_doubles()] doubles ->
+ *           cpn_unpack_shards().
+ * This replaces the per-sampler pipes of the reference (cpnest/cpnest.py:553-584). */
+int64_t cpn_staging_bytes(cpn_ctx* ctx);
+int cpn_set_staging(cpn_ctx* ctx, void* const* peer_blocks /*device addresses, [world]*/, int32_t npeers);
+int64_t cpn_shard_record_doubles(cpn_ctx* ctx);
+int cpn_shard_range(cpn_ctx* ctx, int32_t K, int32_t rank, int32_t* j0, int32_t* j1);
+int cpn_pack_shard(cpn_ctx* ctx, int32_t K, void* dev_send);
+int cpn_unpack_shards(cpn_ctx* ctx, int32_t K, const void* dev_recv);
 /* One consume_sample() = the three calls above (+ ensemble refresh on the sampler's cadence,
  * cpnest/sampler.py:252-254). */
 int cpn_ns_step(cpn_ctx* ctx, int32_t K);
@@ -139,6 +153,8 @@ int cpn_set_stream(cpn_ctx* ctx, void* cuda_stream);
 int64_t cpn_launch_count(cpn_ctx* ctx);
 int cpn_get_state(cpn_ctx* ctx, cpn_state* out);
 int cpn_set_nmcmc(cpn_ctx* ctx, int32_t nmcmc);
+/* NestedSampler(stopping=) (cpnest/NestedSampling.py:229,250) */
+int cpn_set_tolerance(cpn_ctx* ctx, double tolerance);
 int cpn_get_live(cpn_ctx* ctx, double* rows /*[nlive][D+2], ascending logL*/);
 int64_t cpn_num_dead(cpn_ctx* ctx);
 int cpn_get_dead(cpn_ctx* ctx, int64_t first, int64_t n, double* rows /*[n][D+2]*/, double* log_vols /*[n] or NULL*/);

@@ -1,0 +1,74 @@
+"""Host-side logic of the multi-GPU path, on CPU with the gloo backend (world_size 2):
+the chain slices cover a batch exactly once, and the record layout used for the NCCL all-gather
+(csrc/api.cu k_pack_shard / k_unpack_shards: [chains][Dp+4] doubles {x.., logL, logP, (steps,acc),
+(start,evals)}) round-trips through all_gather_into_tensor."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cpnest_b200.sharded import shard_range
+
+
+def test_shard_ranges_partition_the_batch():
+    for world in (1, 2, 3, 4, 8):
+        for K in (1, 7, 8, 2500, 2501, 20000):
+            edges = [shard_range(K, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == K
+            for (a0, a1), (b0, b1) in zip(edges[:-1], edges[1:]):
+                assert a1 == b0 and a0 <= a1
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def pack(j0, j1, Dp, x, logL, logP, steps, acc, start, evals):
+    n = j1 - j0
+    rec = np.zeros((n, Dp + 4))
+    rec[:, :Dp] = x[j0:j1]
+    rec[:, Dp] = logL[j0:j1]
+    rec[:, Dp + 1] = logP[j0:j1]
+    ints = np.zeros((n, 4), dtype=np.int32)
+    ints[:, 0], ints[:, 1], ints[:, 2], ints[:, 3] = steps[j0:j1], acc[j0:j1], start[j0:j1], evals[j0:j1]
+    rec[:, Dp + 2:] = ints.view(np.float64)       # (lo, hi) int pairs share a double slot
+    return rec
+
+
+def unpack(rec, Dp):
+    ints = np.ascontiguousarray(rec[:, Dp + 2:]).view(np.int32)
+    return rec[:, :Dp], rec[:, Dp], rec[:, Dp + 1], ints[:, 0], ints[:, 1], ints[:, 2], ints[:, 3]
+
+
+def _worker(rank, world, port, K, Dp, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(0)                   # every rank knows the full truth
+    x = rs.normal(size=(K, Dp)); logL = rs.normal(size=K); logP = rs.normal(size=K)
+    steps = rs.randint(1, 5000, K).astype(np.int32); acc = rs.randint(0, 2000, K).astype(np.int32)
+    start = rs.randint(0, 10 ** 6, K).astype(np.int32); evals = rs.randint(0, 5000, K).astype(np.int32)
+    j0, j1 = shard_range(K, rank, world)
+    # a rank only has ITS slice; poison the rest to prove the gather fills it
+    mine = pack(j0, j1, Dp, x, logL, logP, steps, acc, start, evals)
+    recv = torch.full((K * (Dp + 4),), float("nan"), dtype=torch.float64)
+    send = recv[j0 * (Dp + 4):j1 * (Dp + 4)]
+    send.copy_(torch.from_numpy(mine.ravel()))
+    dist.all_gather_into_tensor(recv, send.clone())
+    got = unpack(recv.numpy().reshape(K, Dp + 4), Dp)
+    ok = all(np.array_equal(a, b) for a, b in zip(got, (x, logL, logP, steps, acc, start, evals)))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_record_layout_roundtrips_through_gloo_allgather():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, 64, 52, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}
