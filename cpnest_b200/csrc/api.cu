@@ -65,6 +65,7 @@ struct cpn_ctx {
     void* d_stage_own;
     void* stage_peer[kMaxPeers];
     int n_peers;                // 0: private staging; else == world_size, stage_peer[rank] is the local block
+    int stage_half;             // which half of the peer-mapped blocks the current batch uses
     int rank, world;
     double *d_new_x, *d_new_logL, *d_new_logP;
     int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_rank;
@@ -239,7 +240,9 @@ static void bind_staging(cpn_ctx* c, void* base) {
     c->d_new_evals = (int*)(b + stage_off(c->N, c->Dp, 6));
 }
 
-extern "C" int64_t cpn_staging_bytes(cpn_ctx* c) { return c ? (int64_t)stage_bytes(c->N, c->Dp) : -1; }
+// two halves: batch b uses half b & 1, so that a fast rank's chains of batch b+1 never store into a
+// block that a slow rank is still reading for batch b (one barrier per batch is then enough)
+extern "C" int64_t cpn_staging_bytes(cpn_ctx* c) { return c ? 2 * (int64_t)stage_bytes(c->N, c->Dp) : -1; }
 
 // Multi-GPU: `peers[r]` is the address, valid on THIS device, of rank r's staging block (peer-mapped
 // symmetric memory; peers[rank] is the local block).  From then on every chain writes its outcome
@@ -259,6 +262,7 @@ extern "C" int cpn_set_staging(cpn_ctx* c, void* const* peers, int32_t npeers) {
         c->stage_peer[r] = peers[r];
     }
     c->n_peers = npeers;
+    c->stage_half = 0;
     bind_staging(c, peers[c->rank]);
     return 0;
 }
@@ -504,7 +508,8 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     for (int o = 0; o < nout; ++o) {
         // slot 0 is always the local block, the other ranks follow
         const int r = (o == 0) ? c->rank : (o <= c->rank ? o - 1 : o);
-        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] : (char*)c->d_stage_own;
+        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp)
+                                   : (char*)c->d_stage_own;
         p->out_x[o] = (double*)(b + stage_off(c->N, c->Dp, 0));
         p->out_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 1));
         p->out_logP[o] = (double*)(b + stage_off(c->N, c->Dp, 2));
@@ -611,6 +616,15 @@ static int check_K(cpn_ctx* c, int K) {
 extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
     CK(cudaSetDevice(c->cfg.device));
+    // Refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254).  The refresh runs
+    // on the side stream beside the chain kernels of two batches and is adopted by the batch after those
+    // (fixed latency, so the schedule - and with it every result - is deterministic); one refresh is in
+    // flight at a time, which makes the cadence max(2 batches, nlive/4 chains).
+    if (c->eig_pending && ++c->eig_pending_age >= 2)
+        if (adopt_pending_stats(c)) return 1;
+    if (!c->eig_pending && c->chains_since_stats >= std::max(1, c->N / 4))
+        if (start_async_stats(c)) return 1;
+
     if (grow_logs(c, c->dead_upper + K + c->N)) return 1;
     AccParams a;
     memset(&a, 0, sizeof a);
@@ -627,6 +641,10 @@ extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
 extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
     CK(cudaSetDevice(c->cfg.device));
+    if (c->n_peers > 0) {                       // next half of the peer-mapped staging blocks
+        c->stage_half ^= 1;
+        bind_staging(c, (char*)c->stage_peer[c->rank] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp));
+    }
     MHParams p;
     fill_mh(c, &p);
     p.start_mode = START_SURVIVOR;
@@ -746,15 +764,6 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
 
 extern "C" int cpn_ns_step(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
-    CK(cudaSetDevice(c->cfg.device));
-    // Refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254).  The refresh runs
-    // on the side stream beside the chain kernels of two batches and is adopted by the batch after those
-    // (fixed latency, so the schedule - and with it every result - is deterministic); one refresh is in
-    // flight at a time, which makes the cadence max(2 batches, nlive/4 chains).
-    if (c->eig_pending && ++c->eig_pending_age >= 2)
-        if (adopt_pending_stats(c)) return 1;
-    if (!c->eig_pending && c->chains_since_stats >= std::max(1, c->N / 4))
-        if (start_async_stats(c)) return 1;
     if (cpn_select_and_accumulate(c, K)) return 1;
     if (cpn_evolve_batch(c, K)) return 1;
     return cpn_insert_batch(c, K);

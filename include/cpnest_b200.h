@@ -127,7 +127,7 @@ int cpn_insert_batch(cpn_ctx* ctx, int32_t K);
  *   NCCL  : cpn_pack_shard() -> all-gather of [chains][cpn_shard_record_doubles()] doubles ->
  *           cpn_unpack_shards().
  * This replaces the per-sampler pipes of the reference (cpnest/cpnest.py:553-584). */
-int64_t cpn_staging_bytes(cpn_ctx* ctx);
+int64_t cpn_staging_bytes(cpn_ctx* ctx);   /* size of one peer block (two halves, alternating per batch) */
 int cpn_set_staging(cpn_ctx* ctx, void* const* peer_blocks /*device addresses, [world]*/, int32_t npeers);
 int64_t cpn_shard_record_doubles(cpn_ctx* ctx);
 int cpn_shard_range(cpn_ctx* ctx, int32_t K, int32_t rank, int32_t* j0, int32_t* j1);

@@ -63,4 +63,5 @@ def test_sharded_run_equals_single_gpu(comm):
     s.close()
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, comm, out), nprocs=2, join=True)
-    assert out[0] == out[1] == ref
+    assert out[0] == out[1], (out[0], out[1])
+    assert out[0] == ref, (out[0], ref)
