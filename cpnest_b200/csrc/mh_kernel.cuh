@@ -73,15 +73,6 @@ struct MHParams {
     double* states;           // [chains][maxmcmc][D] or null
 };
 
-template <bool EXACT>
-struct Arith {
-    // EXACT: one IEEE operation per reference operation (no FMA contraction), so a replay
-    // reproduces the reference's fp64 numbers bit for bit.
-    static __device__ __forceinline__ double add(double a, double b) { return EXACT ? __dadd_rn(a, b) : a + b; }
-    static __device__ __forceinline__ double sub(double a, double b) { return EXACT ? __dsub_rn(a, b) : a - b; }
-    static __device__ __forceinline__ double mul(double a, double b) { return EXACT ? __dmul_rn(a, b) : a * b; }
-};
-
 template <int G, int E>
 __device__ __forceinline__ void load_row(const Group<G>& g, const double* row, int D, double (&v)[E]) {
 #pragma unroll
@@ -91,95 +82,140 @@ __device__ __forceinline__ void load_row(const Group<G>& g, const double* row, i
     }
 }
 
-// What one MCMC step consumes: the proposal kind, the ensemble members it draws and its random
-// numbers.  Everything here is independent of the chain's current point, so the draw (and the
-// gather it implies) of step t+1 is issued while step t is still being evaluated.
-struct Draw {
+// ---- what one MCMC step consumes besides the chain's current point ---------------------------------
+// Nothing of it depends on the chain state, so the inputs (and the gather they imply) of step t+1 are
+// produced while step t is still being evaluated.
+//
+// Production form.  All four proposals of the DefaultProposalCycle are instances of
+//     new = cx * old + c0 * r0 + c1 * r1 + c2 * r2          (r_j: gathered ensemble rows / eigen-direction)
+//   EnsembleWalk          old + sum_j g_j (s_j - com), com = (s0+s1+s2)/3  ->  cx = 1, c_j = g_j - mean(g)   proposal.py:230-234
+//   EnsembleStretch       a + Z (old - a)                                  ->  cx = Z, c0 = 1 - Z            proposal.py:253-260
+//   DifferentialEvolution old + g (b - a), g ~ N(1, 1e-4)                  ->  cx = 1, c0 = -g, c1 = g       proposal.py:284-286
+//   EnsembleEigenVector   old + sqrt|lambda_i| N(0,1) v_i                  ->  cx = 1, c0 = jump, r0 = v_i   proposal.py:336-342
+// so a step is straight-line code whatever the proposal kind: the compiler can interleave the draw and the
+// gather of the following step with the dependent chain proposal -> box test -> likelihood reduction ->
+// accept of this one.  `thr` = log(u) - log_J: the prior MH test (sampler.py:337) reads dlogP > thr.
+struct StepIn {
     int kind;
     uint32_t i0, i1, i2;
-    double g0, g1, g2, us, umh;
+    double cx, c0, c1, c2;
+    double thr;
 };
 
-// Philox blocks of G consecutive steps are computed once, one step per lane, and handed out by
-// shuffle: the stream is the same as if every lane computed block (chain, step, k) itself.
+// The inputs of G consecutive steps are computed once, one step per lane (Philox blocks (chain, step, 0/1),
+// Box-Muller, log(u), exp), packed into 8 words and handed out by shuffle step after step: a step costs
+// 8 shuffles instead of a redundant RNG evaluation on every lane, and the stream is a pure function of
+// (seed, chain, step) - independent of G and of the grid.
 template <int G>
-struct RngFeed {
-    uint32_t a[4], b[4];
-    __device__ __forceinline__ void refill(int step0, int lane, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1) {
-        const Philox4 p = philox4x32_10(cid_lo, cid_hi, (uint32_t)(step0 + lane), 0u, k0, k1);
-        const Philox4 q = philox4x32_10(cid_lo, cid_hi, (uint32_t)(step0 + lane), 1u, k0, k1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { a[k] = p.v[k]; b[k] = q.v[k]; }
-    }
-    __device__ __forceinline__ void get(int src_lane, uint32_t (&ra)[4], uint32_t (&rb)[4]) const {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ra[k] = (G == 1) ? a[k] : __shfl_sync(FULL, a[k], src_lane, G);
-            rb[k] = (G == 1) ? b[k] : __shfl_sync(FULL, b[k], src_lane, G);
+struct DrawFeed {
+    uint32_t w[8];   // i0, i1, i2, c0, c1, c2 (fp32 bits), thr (fp64 bits)
+    __device__ __forceinline__ void refill(int kind, uint32_t step, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1,
+                                           uint32_t ens_n, uint32_t D, const double* eig_scale) {
+        const Philox4 r = philox4x32_10(cid_lo, cid_hi, step, 0u, k0, k1);
+        double thr = log(u32_to_unit_open(r.v[3]));
+        uint32_t i0 = u32_to_index(r.v[0], ens_n), i1, i2;
+        float c0, c1 = 0.0f, c2 = 0.0f;
+        if (kind == CPN_WALK) {
+            // three distinct members, `sample(list(ensemble), 3)` proposal.py:230
+            i1 = u32_to_index(r.v[1], ens_n - 1);
+            i1 += (i1 >= i0);
+            i2 = u32_to_index(r.v[2], ens_n - 2);
+            const uint32_t lo2 = min(i0, i1), hi2 = max(i0, i1);
+            i2 += (i2 >= lo2);
+            i2 += (i2 >= hi2);
+            const Philox4 q = philox4x32_10(cid_lo, cid_hi, step, 1u, k0, k1);
+            float g0, g1, g2, g3;
+            box_muller_f(q.v[0], q.v[1], g0, g1);
+            box_muller_f(q.v[2], q.v[3], g2, g3);
+            const float gbar = (g0 + g1 + g2) * (1.0f / 3.0f);
+            c0 = g0 - gbar; c1 = g1 - gbar; c2 = g2 - gbar;
+        } else if (kind == CPN_STRETCH) {
+            i1 = i2 = i0;                                                          // random.choice, proposal.py:253
+            const double xs = (2.0 * u32_to_unit_open(r.v[1]) - 1.0) * 0.69314718055994530942;   // uniform(-1,1)*log(2)
+            c0 = (float)(1.0 - exp(xs));                                           // Z = exp(x), proposal.py:256-258
+            thr -= (double)D * log(1.0 - (double)c0);                              // log_J = D log Z of the Z applied, :260
+        } else if (kind == CPN_DE) {
+            i1 = u32_to_index(r.v[1], ens_n - 1);                                  // sample(...,2), proposal.py:284
+            i1 += (i1 >= i0);
+            i2 = i1;
+            float gd, unused;
+            box_muller_f(r.v[2] << 16, r.v[2] & 0xffff0000u, gd, unused);
+            c1 = fmaf(1e-4f, gd, 1.0f);                                            // gauss(1.0, 1e-4), proposal.py:285-286
+            c0 = -c1;
+        } else {
+            i0 = u32_to_index(r.v[0], D);                                          // randrange(D), proposal.py:338
+            i1 = i2 = i0;
+            float g, unused;
+            box_muller_f(r.v[1], r.v[2], g, unused);
+            c0 = (float)(__ldg(eig_scale + i0) * (double)g);                       // sqrt|lambda_i| * gauss(0,1), :339
         }
+        w[0] = i0; w[1] = i1; w[2] = i2;
+        w[3] = __float_as_uint(c0); w[4] = __float_as_uint(c1); w[5] = __float_as_uint(c2);
+        w[6] = (uint32_t)__double2loint(thr);
+        w[7] = (uint32_t)__double2hiint(thr);
+    }
+    __device__ __forceinline__ StepIn get(int kind, int src_lane) const {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (G == 1) ? w[k] : __shfl_sync(FULL, w[k], src_lane, G);
+        StepIn s;
+        s.kind = kind;
+        s.i0 = v[0]; s.i1 = v[1]; s.i2 = v[2];
+        s.c0 = (double)__uint_as_float(v[3]); s.c1 = (double)__uint_as_float(v[4]); s.c2 = (double)__uint_as_float(v[5]);
+        s.cx = (kind == CPN_STRETCH) ? 1.0 - s.c0 : 1.0;
+        s.thr = __hiloint2double((int)v[7], (int)v[6]);
+        return s;
     }
 };
 
-__device__ __forceinline__ Draw make_draw(int kind, const uint32_t (&r)[4], const uint32_t (&q)[4], uint32_t ens_n, uint32_t D) {
-    Draw d;
-    d.kind = kind;
-    d.umh = u32_to_unit_open(r[3]);
-    d.i0 = d.i1 = d.i2 = 0;
-    d.g0 = d.g1 = d.g2 = d.us = 0.0;
-    if (kind == CPN_WALK) {
-        // three distinct members, `sample(list(ensemble), 3)` proposal.py:230
-        d.i0 = u32_to_index(r[0], ens_n);
-        d.i1 = u32_to_index(r[1], ens_n - 1);
-        d.i1 += (d.i1 >= d.i0);
-        d.i2 = u32_to_index(r[2], ens_n - 2);
-        const uint32_t lo2 = min(d.i0, d.i1), hi2 = max(d.i0, d.i1);
-        d.i2 += (d.i2 >= lo2);
-        d.i2 += (d.i2 >= hi2);
-        double g3;
-        box_muller(q[0], q[1], d.g0, d.g1);
-        box_muller(q[2], q[3], d.g2, g3);
-    } else if (kind == CPN_STRETCH) {
-        d.i0 = u32_to_index(r[0], ens_n);                    // random.choice, proposal.py:253
-        d.us = 2.0 * u32_to_unit_open(r[1]) - 1.0;           // uniform(-1,1), proposal.py:255
-    } else if (kind == CPN_DE) {
-        d.i0 = u32_to_index(r[0], ens_n);                    // sample(...,2), proposal.py:284
-        d.i1 = u32_to_index(r[1], ens_n - 1);
-        d.i1 += (d.i1 >= d.i0);
-        double gd, unused;
-        box_muller(r[2] << 16, r[2] & 0xffff0000u, gd, unused);
-        d.g0 = 1.0 + 1e-4 * gd;                              // gauss(1.0, sigma), proposal.py:285-286
-    } else {
-        d.i0 = u32_to_index(r[0], D);                        // randrange(D), proposal.py:338
-        double unused;
-        box_muller(r[1], r[2], d.g0, unused);
-    }
-    return d;
-}
-
-__device__ __forceinline__ Draw tape_draw(int kind, const double* t, int compat) {
-    Draw d;
-    d.kind = kind;
-    d.i0 = (uint32_t)t[0]; d.i1 = (uint32_t)t[1]; d.i2 = (uint32_t)t[2];
-    d.g0 = t[3]; d.g1 = t[4]; d.g2 = t[5]; d.us = t[6]; d.umh = t[7];
-    if (compat && kind != CPN_EIGEN) {   // EnsembleEigenVector is full fp64 (proposal.py:339-341)
-        d.g0 = (double)(float)d.g0; d.g1 = (double)(float)d.g1; d.g2 = (double)(float)d.g2;
-    }
-    return d;
-}
-
-// the (up to three) rows a draw gathers: ensemble members, or one eigenvector
+// the three rows a production step gathers (kinds that need fewer re-read row i0: an L1 hit)
 template <int G, int E>
-__device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, const Draw& d, double (&r0)[E],
+__device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, const StepIn& s, double (&r0)[E],
                                             double (&r1)[E], double (&r2)[E]) {
-    const double* base0 = (d.kind == CPN_EIGEN) ? p.eig_vec : p.ens_x;
-    load_row<G, E>(g, base0 + (size_t)d.i0 * p.Dp, p.D, r0);
-    if (d.kind == CPN_WALK || d.kind == CPN_DE) load_row<G, E>(g, p.ens_x + (size_t)d.i1 * p.Dp, p.D, r1);
-    if (d.kind == CPN_WALK) load_row<G, E>(g, p.ens_x + (size_t)d.i2 * p.Dp, p.D, r2);
+    const bool eig = s.kind == CPN_EIGEN;
+    const double* base = eig ? p.eig_vec : p.ens_x;
+    load_row<G, E>(g, base + (size_t)s.i0 * p.Dp, p.D, r0);
+    const bool two = (s.kind == CPN_WALK) | (s.kind == CPN_DE), three = s.kind == CPN_WALK;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = g.lane + e * G;
+        if (two && d < p.D) r1[e] = __ldg(p.ens_x + (size_t)s.i1 * p.Dp + d);
+        if (three && d < p.D) r2[e] = __ldg(p.ens_x + (size_t)s.i2 * p.Dp + d);
+    }
+}
+
+// ---- replay (parity) form: the reference's own random numbers from the tape, one IEEE operation per
+// reference operation ---------------------------------------------------------------------------------
+struct TapeIn {
+    int kind;
+    uint32_t i0, i1, i2;
+    double a0, a1, a2;     // WALK: the 3 Gaussians; STRETCH: a0 = Z; DE: a0 = factor; EIGEN: a0 = N(0,1)
+    double log_J;          // proposal.py:260 (STRETCH), else 0
+    double logu;           // log of the uniform of the prior MH test, sampler.py:337
+};
+
+__device__ __forceinline__ TapeIn tape_step(int kind, const double* t, int compat, int D) {
+    TapeIn s;
+    s.kind = kind;
+    s.i0 = (uint32_t)t[0]; s.i1 = (uint32_t)t[1]; s.i2 = (uint32_t)t[2];
+    s.a0 = t[3]; s.a1 = t[4]; s.a2 = t[5];
+    s.log_J = 0.0;
+    if (compat && kind != CPN_EIGEN) {   // EnsembleEigenVector is full fp64 (proposal.py:339-341)
+        s.a0 = (double)(float)s.a0; s.a1 = (double)(float)s.a1; s.a2 = (double)(float)s.a2;
+    }
+    if (kind == CPN_STRETCH) {
+        const double xs = __dmul_rn(t[6], 0.69314718055994530942);     // uniform(-1,1)*log(scale), proposal.py:255-256
+        double Z = exp(xs);
+        if (compat) Z = (double)(float)Z;
+        s.a0 = Z;
+        s.log_J = __dmul_rn((double)D, xs);                              // proposal.py:260 (un-rounded x)
+    }
+    s.logu = (t[7] > 0.0) ? log(t[7]) : CPN_NEG_INF;
+    return s;
 }
 
 template <int G, int E, class Model, bool REPLAY>
 __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
-    using A = Arith<REPLAY>;
     if (!REPLAY && p.state != nullptr && p.state->done) return;
     const Group<G> g;
     const int cpb = kMHThreads / G;
@@ -239,112 +275,134 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
 
     int steps = 0, accepted = 0, evals = 0;
     bool active = true;
-    int cpos = p.cycle_pos0;
-    const double* tape = REPLAY ? p.tape + (size_t)c * maxmcmc * 8 : nullptr;
-    const uint32_t ens_n = (uint32_t)p.ens_n;
+    const int clen = p.cycle_len;
+    // position in the proposal cycle of the next step to be drawn (pre-increment, proposal.py:93)
+    int npos = (p.cycle_pos0 + 1) % clen;
 
-    // ---- software pipeline: draw + gather of step `it+1` overlap the evaluation of step `it` -----------
-    RngFeed<G> feed;
-    Draw cur;
-    double r0[E], r1[E], r2[E];
-    auto next_draw = [&](int it) -> Draw {
-        cpos = (cpos + 1 == p.cycle_len) ? 0 : cpos + 1;          // pre-increment, proposal.py:93
-        const int kind = p.cycle[cpos];
-        if (REPLAY) return tape_draw(kind, tape + (size_t)min(it, maxmcmc - 1) * 8, p.compat);
-        if ((it & (G - 1)) == 0) feed.refill(it, g.lane, cid_lo, cid_hi, p.seed_lo, p.seed_hi);
-        uint32_t ra[4], rb[4];
-        feed.get(it & (G - 1), ra, rb);
-        return make_draw(kind, ra, rb, ens_n, (uint32_t)D);
-    };
-    cur = next_draw(0);
+    if constexpr (REPLAY) {
+        // ================================ parity mode =================================================
+        const double* tape = p.tape + (size_t)c * maxmcmc * 8;
+        for (int it = 0; it < maxmcmc; ++it) {
+            if (!__any_sync(FULL, active)) break;
+            const int kind = p.cycle[npos];
+            npos = (npos + 1 == clen) ? 0 : npos + 1;
+            const TapeIn s = tape_step(kind, tape + (size_t)it * 8, p.compat, D);
+            double r0[E], r1[E], r2[E], xn[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) r1[e] = r2[e] = 0.0;
-    gather_rows<G, E>(g, p, cur, r0, r1, r2);
-
-    for (int it = 0; it < maxmcmc; ++it) {
-        if (!__any_sync(FULL, active)) break;
-        const Draw nxt = next_draw(it + 1);
-        double n0[E], n1[E], n2[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) n1[e] = n2[e] = 0.0;
-        gather_rows<G, E>(g, p, nxt, n0, n1, n2);
-
-        // ---- proposal ------------------------------------------------------------------------------
-        const int kind = cur.kind;
-        double xn[E];
-        double log_J = 0.0;
-        if (kind == CPN_WALK) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if (REPLAY) {
-                    const double com = __ddiv_rn(__dadd_rn(__dadd_rn(r0[e], r1[e]), r2[e]), 3.0);
-                    double o = x[e];
-                    o = __dadd_rn(o, __dmul_rn(cur.g0, __dsub_rn(r0[e], com)));
-                    o = __dadd_rn(o, __dmul_rn(cur.g1, __dsub_rn(r1[e], com)));
-                    o = __dadd_rn(o, __dmul_rn(cur.g2, __dsub_rn(r2[e], com)));
-                    xn[e] = o;
-                } else {
-                    const double com = (r0[e] + r1[e] + r2[e]) * (1.0 / 3.0);
-                    xn[e] = x[e] + cur.g0 * (r0[e] - com) + cur.g1 * (r1[e] - com) + cur.g2 * (r2[e] - com);
-                }
-            }
-        } else if (kind == CPN_STRETCH) {
-            const double xs = A::mul(cur.us, 0.69314718055994530942);     // uniform(-1,1)*log(scale)
-            double Z = exp(xs);
-            if (REPLAY && p.compat) Z = (double)(float)Z;
-            log_J = A::mul((double)D, xs);                                // proposal.py:260 (un-rounded x)
-#pragma unroll
-            for (int e = 0; e < E; ++e) xn[e] = A::add(r0[e], A::mul(Z, A::sub(x[e], r0[e])));
-        } else if (kind == CPN_DE) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) xn[e] = A::add(x[e], A::mul(cur.g0, A::sub(r1[e], r0[e])));
-        } else {
-            const double jump = A::mul(__ldg(p.eig_scale + cur.i0), cur.g0);   // sqrt|lambda_i| * gauss(0,1)
-#pragma unroll
-            for (int e = 0; e < E; ++e) xn[e] = A::add(x[e], A::mul(jump, r0[e]));
-        }
-
-        // ---- box test, prior MH test, likelihood, hard constraint -------------------------------------
-        bool inb = true;
-#pragma unroll
-        for (int e = 0; e < E; ++e) inb = inb & (blo[e] < xn[e]) & (xn[e] < bhi[e]);    // strict, model.py:33
-        inb = g.all(inb);
-        double logP_new = Model::template log_prior<G, E>(g, xn, m);
-        logP_new = inb ? logP_new : CPN_NEG_INF;
-        const double delta = A::add(A::sub(logP_new, logP), log_J);   // sampler.py:337
-        bool pass;
-        if (REPLAY) {
-            pass = delta > ((cur.umh > 0.0) ? log(cur.umh) : CPN_NEG_INF);
-        } else {
-            pass = (delta >= 0.0) || (delta > log(cur.umh));            // log(u) < 0 always
-        }
-        pass = pass && active;
-        if (__any_sync(FULL, pass)) {
-            const double logL_new = Model::template log_likelihood<G, E>(g, xn, m);   // sampler.py:338
-            evals += pass ? 1 : 0;
-            if (pass && logL_new > logLmin) {                           // sampler.py:339
-#pragma unroll
-                for (int e = 0; e < E; ++e) x[e] = xn[e];
-                logL = logL_new;
-                logP = logP_new;
-                ++accepted;
-            }
-        }
-        if (active) {
-            ++steps;
-            if (REPLAY && p.states != nullptr && valid) {
-                double* srow = p.states + ((size_t)c * maxmcmc + it) * D;
+            for (int e = 0; e < E; ++e) r1[e] = r2[e] = 0.0;
+            load_row<G, E>(g, (kind == CPN_EIGEN ? p.eig_vec : p.ens_x) + (size_t)s.i0 * p.Dp, D, r0);
+            if (kind == CPN_WALK || kind == CPN_DE) load_row<G, E>(g, p.ens_x + (size_t)s.i1 * p.Dp, D, r1);
+            if (kind == CPN_WALK) load_row<G, E>(g, p.ens_x + (size_t)s.i2 * p.Dp, D, r2);
+            if (kind == CPN_WALK) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    const int d = g.lane + e * G;
-                    if (d < D) srow[d] = x[e];
+                    const double com = __ddiv_rn(__dadd_rn(__dadd_rn(r0[e], r1[e]), r2[e]), 3.0);
+                    double o = x[e];
+                    o = __dadd_rn(o, __dmul_rn(s.a0, __dsub_rn(r0[e], com)));
+                    o = __dadd_rn(o, __dmul_rn(s.a1, __dsub_rn(r1[e], com)));
+                    o = __dadd_rn(o, __dmul_rn(s.a2, __dsub_rn(r2[e], com)));
+                    xn[e] = o;
+                }
+            } else if (kind == CPN_STRETCH) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = __dadd_rn(r0[e], __dmul_rn(s.a0, __dsub_rn(x[e], r0[e])));
+            } else if (kind == CPN_DE) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = __dadd_rn(x[e], __dmul_rn(s.a0, __dsub_rn(r1[e], r0[e])));
+            } else {
+                const double jump = __dmul_rn(__ldg(p.eig_scale + s.i0), s.a0);   // sqrt|lambda_i| * gauss(0,1)
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = __dadd_rn(x[e], __dmul_rn(jump, r0[e]));
+            }
+            bool inb = true;
+#pragma unroll
+            for (int e = 0; e < E; ++e) inb = inb & (blo[e] < xn[e]) & (xn[e] < bhi[e]);    // strict, model.py:33
+            inb = g.all(inb);
+            double logP_new = Model::template log_prior<G, E>(g, xn, m);
+            logP_new = inb ? logP_new : CPN_NEG_INF;
+            const double delta = __dadd_rn(__dsub_rn(logP_new, logP), s.log_J);   // sampler.py:337
+            const bool pass = (delta > s.logu) && active;
+            if (__any_sync(FULL, pass)) {
+                const double logL_new = Model::template log_likelihood<G, E>(g, xn, m);   // sampler.py:338
+                evals += pass ? 1 : 0;
+                if (pass && logL_new > logLmin) {                           // sampler.py:339
+#pragma unroll
+                    for (int e = 0; e < E; ++e) x[e] = xn[e];
+                    logL = logL_new;
+                    logP = logP_new;
+                    ++accepted;
                 }
             }
-            if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
-        }
-        cur = nxt;
+            if (active) {
+                ++steps;
+                if (p.states != nullptr && valid) {
+                    double* srow = p.states + ((size_t)c * maxmcmc + it) * D;
 #pragma unroll
-        for (int e = 0; e < E; ++e) { r0[e] = n0[e]; r1[e] = n1[e]; r2[e] = n2[e]; }
+                    for (int e = 0; e < E; ++e) {
+                        const int d = g.lane + e * G;
+                        if (d < D) srow[d] = x[e];
+                    }
+                }
+                if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
+            }
+        }
+    } else {
+        // ================================ production ==================================================
+        const uint32_t ens_n = (uint32_t)p.ens_n;
+        DrawFeed<G> feed;
+        auto next_in = [&](int it) -> StepIn {
+            const int kind = p.cycle[npos];
+            if ((it & (G - 1)) == 0) {                                   // this lane prepares step it + lane
+                const int lpos = (npos + g.lane) % clen;
+                feed.refill(p.cycle[lpos], (uint32_t)(it + g.lane), cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D,
+                            p.eig_scale);
+            }
+            npos = (npos + 1 == clen) ? 0 : npos + 1;
+            return feed.get(kind, it & (G - 1));
+        };
+        // One MCMC step on (s, r0..r2); meanwhile the inputs of the following step are drawn and gathered into
+        // (ns, n0..n2).  The caller alternates two such sets, so nothing is copied between steps.
+        auto mcmc_step = [&](int it, const StepIn& s, const double (&r0)[E], const double (&r1)[E], const double (&r2)[E],
+                             StepIn& ns, double (&n0)[E], double (&n1)[E], double (&n2)[E]) {
+            ns = next_in(it + 1);
+            gather_rows<G, E>(g, p, ns, n0, n1, n2);
+            double xn[E];
+            bool inb = true;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                xn[e] = fma(s.c2, r2[e], fma(s.c1, r1[e], fma(s.c0, r0[e], s.cx * x[e])));
+                inb = inb & (blo[e] < xn[e]) & (xn[e] < bhi[e]);            // strict, model.py:33
+            }
+            inb = g.all(inb);
+            double logP_new = Model::template log_prior<G, E>(g, xn, m);
+            logP_new = inb ? logP_new : CPN_NEG_INF;
+            const bool pass = (logP_new - logP > s.thr) && active;          // sampler.py:337
+            if (Model::kCheap || __any_sync(FULL, pass)) {
+                const double logL_new = Model::template log_likelihood<G, E>(g, xn, m);   // sampler.py:338
+                evals += pass ? 1 : 0;
+                const bool acc = pass && logL_new > logLmin;                // sampler.py:339
+#pragma unroll
+                for (int e = 0; e < E; ++e) x[e] = acc ? xn[e] : x[e];
+                logL = acc ? logL_new : logL;
+                logP = acc ? logP_new : logP;
+                accepted += acc ? 1 : 0;
+            }
+            steps += active ? 1 : 0;
+            if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
+        };
+
+        StepIn sa, sb;
+        double a0[E], a1[E], a2[E], b0[E], b1[E], b2[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) a0[e] = a1[e] = a2[e] = b0[e] = b1[e] = b2[e] = 0.0;
+        sa = next_in(0);
+        gather_rows<G, E>(g, p, sa, a0, a1, a2);
+        for (int it = 0; it < maxmcmc; it += 2) {
+            mcmc_step(it, sa, a0, a1, a2, sb, b0, b1, b2);
+            if (!__any_sync(FULL, active)) break;
+            mcmc_step(it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
+            if (!__any_sync(FULL, active)) break;
+        }
     }
 
     // ---- hand the evolved point back (`producer_pipe.send`, sampler.py:246) ------------------

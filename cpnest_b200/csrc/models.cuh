@@ -34,6 +34,7 @@ struct FlatPrior {
 //      tests/test_1d.py:20-21 and tests/test_half_gaussian.py:24-25 (scipy norm.logpdf) ----------------
 struct GaussIid : FlatPrior {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;    // evaluated every step: cheaper than asking whether any chain needs it
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         const double mu = m.blob[0], inv_sigma = m.blob[1], c = m.blob[2];   // c = -log(sigma) - log(2pi)/2
@@ -52,6 +53,7 @@ struct GaussIid : FlatPrior {
 //      (not in the reference).  blob = {logdet, Linv[D][D] row-major lower} -------
 struct GaussCorr : FlatPrior {
     static constexpr bool kScratch = true;
+    static constexpr bool kCheap = false;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         const int D = m.D;
@@ -81,6 +83,7 @@ struct GaussCorr : FlatPrior {
 // ---- eggbox: examples/eggbox.py:19-23  (2 + prod cos(x_i/2))^5 ------------------------------
 struct Eggbox : FlatPrior {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         double p = 1.0;
@@ -94,6 +97,7 @@ struct Eggbox : FlatPrior {
 // ---- Rosenbrock: examples/rosenbrock.py:20-22 ------------------------------------------------
 struct Rosenbrock : FlatPrior {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         double acc = 0.0;
@@ -122,6 +126,7 @@ struct Rosenbrock : FlatPrior {
 //      has no finite value anywhere, so there is no reference parity for this functor) --------------------
 struct Ackley : FlatPrior {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         double s2 = 0.0, sc = 0.0;
@@ -141,6 +146,7 @@ struct Ackley : FlatPrior {
 // ---- ring: tests/test_ring.py:19-23 ; blob = {radius, thickness} ------------------------------
 struct Ring : FlatPrior {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         double a = coord<G, E>(g, x, 0), b = coord<G, E>(g, x, 1);
@@ -153,6 +159,7 @@ struct Ring : FlatPrior {
 // ---- (mean, sigma) Gaussian with a 1/sigma prior: tests/test_gaussian.py:15-20 ----------------
 struct GaussMeanSigma {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx&) {
         double mean = coord<G, E>(g, x, 0), sigma = coord<G, E>(g, x, 1);
@@ -169,6 +176,7 @@ struct GaussMeanSigma {
 //      blob = {n_data, data[n_data]} ; parameters (mean1, sigma1, mean2, sigma2, weight) ----------
 struct GaussMixture {
     static constexpr bool kScratch = false;
+    static constexpr bool kCheap = false;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         const double m1 = coord<G, E>(g, x, 0), s1 = coord<G, E>(g, x, 1), m2 = coord<G, E>(g, x, 2),

@@ -44,16 +44,22 @@ __host__ __device__ __forceinline__ uint32_t u32_to_index(uint32_t r, uint32_t n
 }
 
 #ifdef __CUDACC__
-// two N(0,1) from two u32 (Box-Muller, fp32 special-function units, widened to fp64).  The
-// proposal only needs a symmetric unit-variance draw; 24-bit resolution is ample.
-__device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, double& g0, double& g1) {
+// two N(0,1) from two u32 (Box-Muller, fp32 special-function units).  The proposals only need
+// symmetric unit-variance draws; 24-bit resolution is ample.
+__device__ __forceinline__ void box_muller_f(uint32_t r0, uint32_t r1, float& g0, float& g1) {
     float u1 = ((float)(r0 >> 8) + 0.5f) * (1.0f / 16777216.0f);           // (0,1)
     float th = ((float)(r1 >> 8) + 0.5f) * (2.0f / 16777216.0f) - 1.0f;    // (-1,1) -> angle pi*th
     float rad = sqrtf(-2.0f * __logf(u1));
     float s, c;
     __sincosf(3.14159265358979f * th, &s, &c);
-    g0 = (double)(rad * c);
-    g1 = (double)(rad * s);
+    g0 = rad * c;
+    g1 = rad * s;
+}
+__device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, double& g0, double& g1) {
+    float a, b;
+    box_muller_f(r0, r1, a, b);
+    g0 = (double)a;
+    g1 = (double)b;
 }
 #endif
 
