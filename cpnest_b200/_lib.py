@@ -23,7 +23,7 @@ class cpn_config(C.Structure):
         ("device", C.c_int32), ("dim", C.c_int32), ("nlive", C.c_int32), ("maxmcmc", C.c_int32),
         ("nmcmc_init", C.c_int32), ("functor", C.c_int32), ("lanes", C.c_int32), ("ns_mode", C.c_int32),
         ("seed", C.c_uint64), ("nmcmc_safety", C.c_double), ("adapt_nmcmc", C.c_int32),
-        ("world_size", C.c_int32), ("rank", C.c_int32), ("reserved", C.c_int32), ("rho_target", C.c_double),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("sampler", C.c_int32), ("rho_target", C.c_double),
     ]
 
 
@@ -34,6 +34,7 @@ class cpn_state(C.Structure):
         ("iteration", C.c_int64), ("n_hist", C.c_int64), ("batches", C.c_int64),
         ("total_steps", C.c_int64), ("total_accepted", C.c_int64), ("total_evals", C.c_int64),
         ("failed_chains", C.c_int64), ("nmcmc", C.c_int32), ("done", C.c_int32),
+        ("slice_mu", C.c_double), ("hmc_dt", C.c_double),
     ]
 
     def as_dict(self):
@@ -44,6 +45,8 @@ FUNCTORS = dict(gaussian_iid=0, gaussian_corr=1, eggbox=2, rosenbrock=3, ackley=
                 gaussian_mean_sigma=6, gaussian_mixture=7)
 WALK, STRETCH, DE, EIGEN = 0, 1, 2, 3
 NS_SEQUENTIAL, NS_REFERENCE = 0, 1
+SAMPLERS = dict(mh=0, slice=1, hmc=2)
+SLICE_DIFF, SLICE_GAUSS, SLICE_CORR = 0, 1, 2
 
 _P = C.POINTER
 _dp = _P(C.c_double)
@@ -57,6 +60,8 @@ SIGNATURES = {
     "cpn_create": (C.c_int, [_P(cpn_config), _dp, _dp, _vp, C.c_size_t, _P(_vp)]),
     "cpn_destroy": (None, [_vp]),
     "cpn_set_cycle": (C.c_int, [_vp, _P(C.c_uint8), C.c_int32]),
+    "cpn_set_slice_cycle": (C.c_int, [_vp, _P(C.c_uint8), C.c_int32]),
+    "cpn_set_slice_mu": (C.c_int, [_vp, C.c_double]),
     "cpn_init_prior": (C.c_int, [_vp]),
     "cpn_set_live": (C.c_int, [_vp, _dp, C.c_int32]),
     "cpn_update_ensemble_stats": (C.c_int, [_vp]),
@@ -89,6 +94,9 @@ SIGNATURES = {
     "cpn_eval_model": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "cpn_replay_mh": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32,
                                 C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _dp]),
+    "cpn_replay_slice": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, C.c_int32, _dp, _P(C.c_int64), C.c_double,
+                                   C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _ip, _dp]),
+    "cpn_slice_directions": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, _dp]),
     "cpn_stage_replacements": (C.c_int, [_vp, C.c_int32, _dp]),
     "cpn_ns_reset": (C.c_int, [_vp]),
     "cpn_ns_increment": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, C.c_int32]),

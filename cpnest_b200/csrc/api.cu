@@ -18,6 +18,7 @@
 #include "launch.h"
 #include "mh_kernel.cuh"
 #include "ns_kernels.cuh"
+#include "slice_kernel.cuh"
 
 using namespace cpn;
 
@@ -40,6 +41,10 @@ static int fail(const char* fmt, ...) {
 
 typedef int (*mh_fn)(int, int, int, const MHParams&, cudaStream_t);
 typedef int (*eval_fn)(int, int, const EvalParams&, cudaStream_t);
+typedef int (*slice_fn)(int, int, int, const SliceParams&, cudaStream_t);
+static const slice_fn kSlice[CPN_NUM_FUNCTORS] = {launch_slice_gauss_iid, launch_slice_gauss_corr, launch_slice_eggbox,
+                                                  launch_slice_rosenbrock, launch_slice_ackley, launch_slice_ring,
+                                                  launch_slice_gauss_mean_sigma, launch_slice_gauss_mixture};
 static const mh_fn kMH[CPN_NUM_FUNCTORS] = {launch_mh_gauss_iid, launch_mh_gauss_corr, launch_mh_eggbox,
                                             launch_mh_rosenbrock, launch_mh_ackley, launch_mh_ring,
                                             launch_mh_gauss_mean_sigma, launch_mh_gauss_mixture};
@@ -68,14 +73,14 @@ struct cpn_ctx {
     int stage_half;             // which half of the peer-mapped blocks the current batch uses
     int rank, world;
     double *d_new_x, *d_new_logL, *d_new_logP;
-    int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_rank;
+    int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_new_ne, *d_new_nc, *d_rank;
     double *d_rho, *d_rho2;
     double* d_snew;
     double *d_start_x, *d_start_logL, *d_start_logP;
     double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
     // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
     // side stream concurrently with the chain kernel, writes the other one
-    double *d_eigval[2], *d_eigvec[2], *d_eigscale[2];
+    double *d_eigval[2], *d_eigvec[2], *d_eigscale[2], *d_eigmean[2];
     int eig_cur;
     bool eig_pending, wait_cov;
     int eig_pending_age;        // batches started since the pending refresh was launched
@@ -83,6 +88,8 @@ struct cpn_ctx {
     cudaEvent_t ev_main, ev_cov, ev_eig;
     uint8_t* d_cycle;
     int cycle_len;
+    uint8_t* d_slice_cycle;     // EnsembleSliceProposalCycle
+    int slice_cycle_len;
     NSState* d_state;
     long long log_cap;          // capacity (rows) of the dead / history / insertion logs
     double *d_dead_x, *d_dead_logL, *d_dead_logP, *d_hist_logL, *d_hist_logvol, *d_ins;
@@ -219,16 +226,19 @@ static void init_state(cpn_ctx* c, NSState* s) {
     s->adapt = c->cfg.adapt_nmcmc;
     s->rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : 0.1;
     s->rho_max = -1.0;
+    s->slice_mu = 1.0;                                    // SliceSampler.reset (sampler.py:422)
+    s->hmc_dt = 0.0;
 }
 
 static size_t stage_off(int N, int Dp, int which) {
     // byte offsets of the arrays inside a staging block for N chains
     size_t o = 0;
-    const size_t sizes[7] = {(size_t)N * Dp * 8, (size_t)N * 8, (size_t)N * 8, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4};
+    const size_t sizes[9] = {(size_t)N * Dp * 8, (size_t)N * 8, (size_t)N * 8, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4,
+                             (size_t)N * 4, (size_t)N * 4};
     for (int i = 0; i < which; ++i) o += (sizes[i] + 255) & ~(size_t)255;
     return o;
 }
-static size_t stage_bytes(int N, int Dp) { return stage_off(N, Dp, 7); }
+static size_t stage_bytes(int N, int Dp) { return stage_off(N, Dp, 9); }
 static void bind_staging(cpn_ctx* c, void* base) {
     char* b = (char*)base;
     c->d_new_x = (double*)(b + stage_off(c->N, c->Dp, 0));
@@ -238,6 +248,8 @@ static void bind_staging(cpn_ctx* c, void* base) {
     c->d_new_acc = (int*)(b + stage_off(c->N, c->Dp, 4));
     c->d_new_start = (int*)(b + stage_off(c->N, c->Dp, 5));
     c->d_new_evals = (int*)(b + stage_off(c->N, c->Dp, 6));
+    c->d_new_ne = (int*)(b + stage_off(c->N, c->Dp, 7));
+    c->d_new_nc = (int*)(b + stage_off(c->N, c->Dp, 8));
 }
 
 // two halves: batch b uses half b & 1, so that a fast rank's chains of batch b+1 never store into a
@@ -279,6 +291,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     if (cfg->nlive < 4) return fail("cpn_create: nlive must be >= 4");
     if (cfg->maxmcmc < 1) return fail("cpn_create: maxmcmc must be >= 1");
     if (cfg->functor < 0 || cfg->functor >= CPN_NUM_FUNCTORS) return fail("cpn_create: unknown functor %d", cfg->functor);
+    if (cfg->sampler < CPN_SAMPLER_MH || cfg->sampler > CPN_SAMPLER_HMC) return fail("cpn_create: unknown sampler %d", cfg->sampler);
     for (int d = 0; d < cfg->dim; ++d)
         if (!(lo[d] < hi[d])) return fail("cpn_create: bounds[%d] = (%g, %g) is empty", d, lo[d], hi[d]);
     // functor-specific blob checks
@@ -334,7 +347,8 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
         dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigvec[0], (size_t)D * Dp) || dalloc(&c->d_eigscale[0], D) ||
-        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp) || dalloc(&c->d_eigscale[1], D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
+        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp) || dalloc(&c->d_eigscale[1], D) ||
+        dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
         dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))
         return 1;
     if (dalloc(&c->d_state, 1) || dalloc(&c->d_trap_partial, 256) || dalloc(&c->d_scalar, 4) ||
@@ -349,6 +363,15 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         c->cycle_len = (int)cyc.size();
         if (dalloc(&c->d_cycle, 4096)) return 1;
         CK(cudaMemcpy(c->d_cycle, cyc.data(), cyc.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        // EnsembleSliceProposalCycle: equal weights (proposal.py:195), laid out deterministically until
+        // cpn_set_slice_cycle is called
+        std::vector<uint8_t> cyc;
+        for (int i = 0; i < 99; ++i) cyc.push_back((uint8_t)(i % 3));
+        c->slice_cycle_len = (int)cyc.size();
+        if (dalloc(&c->d_slice_cycle, 4096)) return 1;
+        CK(cudaMemcpy(c->d_slice_cycle, cyc.data(), cyc.size(), cudaMemcpyHostToDevice));
     }
     init_state(c, c->h_state);
     if (push_state(c)) return 1;
@@ -373,7 +396,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
-                    c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_state, c->d_dead_x, c->d_dead_logL,
+                    c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -396,6 +419,26 @@ extern "C" int cpn_set_cycle(cpn_ctx* c, const uint8_t* cycle, int32_t len) {
     return 0;
 }
 
+extern "C" int cpn_set_slice_cycle(cpn_ctx* c, const uint8_t* cycle, int32_t len) {
+    if (!c || !cycle || len < 1 || len > 4096) return fail("cpn_set_slice_cycle: bad arguments");
+    for (int i = 0; i < len; ++i)
+        if (cycle[i] > CPN_SLICE_CORR) return fail("cpn_set_slice_cycle: unknown direction id %d at %d", cycle[i], i);
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(c->d_slice_cycle, cycle, len, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->slice_cycle_len = len;
+    return 0;
+}
+
+extern "C" int cpn_set_slice_mu(cpn_ctx* c, double mu) {
+    if (!c) return fail("null context");
+    if (!(mu > 0.0)) return fail("cpn_set_slice_mu: mu must be > 0");
+    CK(cudaSetDevice(c->cfg.device));
+    if (fetch_state(c)) return 1;
+    c->h_state->slice_mu = mu;
+    return push_state(c);
+}
+
 // ---- sort the live set by logL (OrderedLivePoints.__init__) -------------------------------------------
 static int sort_live(cpn_ctx* c) {
     const int T = 256, Np = c->Npad;
@@ -415,6 +458,7 @@ static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events
     if (D > kStatThreads) return fail("ensemble statistics support dim <= %d", kStatThreads);
     k_mean_partial<<<kStatBlocks, kStatThreads, 0, st>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
     k_mean_final<<<(D + 127) / 128, 128, 0, st>>>(c->d_mean_partial, kStatBlocks, N, D, c->d_mean);
+    CK(cudaMemcpyAsync(c->d_eigmean[buf], c->d_mean, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
     k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), st>>>(
         c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
     k_cov_final<<<(D * D + 127) / 128, 128, 0, st>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
@@ -518,6 +562,69 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
         p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
         p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
     }
+}
+
+static void fill_slice(cpn_ctx* c, SliceParams* p) {
+    memset(p, 0, sizeof *p);
+    p->ens_x = c->d_x; p->ens_logL = c->d_logL; p->ens_logP = c->d_logP;
+    p->ens_n = c->N; p->Dp = c->Dp; p->D = c->D;
+    p->order = c->d_order[c->cur];
+    p->lo = c->d_lo; p->hi = c->d_hi;
+    p->cycle = c->d_slice_cycle; p->cycle_len = c->slice_cycle_len;
+    p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->slice_cycle_len);
+    p->mean = c->d_eigmean[c->eig_cur]; p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
+    p->state = c->d_state;
+    p->maxmcmc = c->cfg.maxmcmc;
+    p->chain_base = c->chain_counter;
+    p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
+    p->blob = c->d_blob;
+    const int nout = c->n_peers > 0 ? c->n_peers : 1;
+    p->n_out = nout;
+    for (int o = 0; o < nout; ++o) {
+        const int r = (o == 0) ? c->rank : (o <= c->rank ? o - 1 : o);
+        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp)
+                                   : (char*)c->d_stage_own;
+        p->out_x[o] = (double*)(b + stage_off(c->N, c->Dp, 0));
+        p->out_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 1));
+        p->out_logP[o] = (double*)(b + stage_off(c->N, c->Dp, 2));
+        p->out_steps[o] = (int*)(b + stage_off(c->N, c->Dp, 3));
+        p->out_acc[o] = (int*)(b + stage_off(c->N, c->Dp, 4));
+        p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
+        p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
+        p->out_ne[o] = (int*)(b + stage_off(c->N, c->Dp, 7));
+        p->out_nc[o] = (int*)(b + stage_off(c->N, c->Dp, 8));
+    }
+}
+
+// chains [j0, j1) of a batch with the context's sampler; START_SURVIVOR unless start rows are given
+static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int n_skip, bool use_override, double logLmin,
+                         int nmcmc, int n_out_override) {
+    int G, E;
+    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, j1 - j0, &G, &E)) return 1;
+    if (c->cfg.sampler == CPN_SAMPLER_SLICE) {
+        SliceParams p;
+        fill_slice(c, &p);
+        p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
+        p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+        if (use_override) {
+            if (fetch_state(c)) return 1;
+            p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.mu_override = c->h_state->slice_mu;
+        }
+        if (n_out_override > 0) p.n_out = n_out_override;
+        if (kSlice[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no slice kernel for G=%d E=%d", G, E);
+    } else if (c->cfg.sampler == CPN_SAMPLER_MH) {
+        MHParams p;
+        fill_mh(c, &p);
+        p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
+        p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+        if (use_override) { p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; }
+        if (n_out_override > 0) p.n_out = n_out_override;
+        if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    } else {
+        return fail("sampler %d is not available on the device yet", c->cfg.sampler);
+    }
+    CKL();
+    return 0;
 }
 
 extern "C" int cpn_init_prior(cpn_ctx* c) {
@@ -645,17 +752,9 @@ extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
         c->stage_half ^= 1;
         bind_staging(c, (char*)c->stage_peer[c->rank] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp));
     }
-    MHParams p;
-    fill_mh(c, &p);
-    p.start_mode = START_SURVIVOR;
-    p.n_skip = K;
     // this rank's slice of the K chains of the batch (all of them on a single GPU)
-    p.j0 = (int)((long long)K * c->rank / c->world);
-    p.j1 = (int)((long long)K * (c->rank + 1) / c->world);
-    int G, E;
-    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, p.j1 - p.j0, &G, &E)) return 1;
-    if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
-    CKL();
+    const int j0 = (int)((long long)K * c->rank / c->world), j1 = (int)((long long)K * (c->rank + 1) / c->world);
+    if (launch_chains(c, K, j0, j1, START_SURVIVOR, K, false, 0.0, 0, 0)) return 1;
     c->chain_counter += (unsigned long long)K;
     c->chains_since_stats += K;
     c->batches_enqueued += 1;
@@ -664,10 +763,10 @@ extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
 }
 
 // NCCL path of a multi-GPU run: this rank's slice of the staging arrays as one contiguous record
-// block [chains][Dp + 4] doubles {x.., logL, logP, (steps, acc), (start, evals)}, and back.
+// block [chains][Dp + 5] doubles {x.., logL, logP, (steps, acc), (start, evals), (ne, nc)}, and back.
 __global__ void k_pack_shard(int j0, int n, int Dp, const double* x, const double* logL, const double* logP, const int* steps,
-                             const int* acc, const int* start, const int* evals, double* rec) {
-    const int S = Dp + 4;
+                             const int* acc, const int* start, const int* evals, const int* ne, const int* nc, double* rec) {
+    const int S = Dp + 5;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * S) return;
     const int r = i / S, d = i % S, j = j0 + r;
@@ -676,12 +775,13 @@ __global__ void k_pack_shard(int j0, int n, int Dp, const double* x, const doubl
     else if (d == Dp) v = logL[j];
     else if (d == Dp + 1) v = logP[j];
     else if (d == Dp + 2) v = __hiloint2double(acc[j], steps[j]);
-    else v = __hiloint2double(evals[j], start[j]);
+    else if (d == Dp + 3) v = __hiloint2double(evals[j], start[j]);
+    else v = __hiloint2double(nc[j], ne[j]);
     rec[i] = v;
 }
 __global__ void k_unpack_shards(int K, int Dp, const double* rec, double* x, double* logL, double* logP, int* steps, int* acc,
-                                int* start, int* evals) {
-    const int S = Dp + 4;
+                                int* start, int* evals, int* ne, int* nc) {
+    const int S = Dp + 5;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * S) return;
     const int j = i / S, d = i % S;
@@ -690,10 +790,11 @@ __global__ void k_unpack_shards(int K, int Dp, const double* rec, double* x, dou
     else if (d == Dp) logL[j] = v;
     else if (d == Dp + 1) logP[j] = v;
     else if (d == Dp + 2) { steps[j] = __double2loint(v); acc[j] = __double2hiint(v); }
-    else { start[j] = __double2loint(v); evals[j] = __double2hiint(v); }
+    else if (d == Dp + 3) { start[j] = __double2loint(v); evals[j] = __double2hiint(v); }
+    else { ne[j] = __double2loint(v); nc[j] = __double2hiint(v); }
 }
 
-extern "C" int64_t cpn_shard_record_doubles(cpn_ctx* c) { return c ? c->Dp + 4 : -1; }
+extern "C" int64_t cpn_shard_record_doubles(cpn_ctx* c) { return c ? c->Dp + 5 : -1; }
 
 extern "C" int cpn_shard_range(cpn_ctx* c, int32_t K, int32_t rank, int32_t* j0, int32_t* j1) {
     if (!c || !j0 || !j1 || rank < 0 || rank >= c->world) return fail("bad argument");
@@ -706,10 +807,11 @@ extern "C" int cpn_pack_shard(cpn_ctx* c, int32_t K, void* dev_send) {
     if (check_K(c, K) || !dev_send) return fail("bad argument");
     CK(cudaSetDevice(c->cfg.device));
     const int j0 = (int)((long long)K * c->rank / c->world), j1 = (int)((long long)K * (c->rank + 1) / c->world);
-    const int n = j1 - j0, S = c->Dp + 4, T = 256;
+    const int n = j1 - j0, S = c->Dp + 5, T = 256;
     if (n > 0)
         k_pack_shard<<<(n * S + T - 1) / T, T, 0, c->stream>>>(j0, n, c->Dp, c->d_new_x, c->d_new_logL, c->d_new_logP, c->d_new_steps,
-                                                            c->d_new_acc, c->d_new_start, c->d_new_evals, (double*)dev_send);
+                                                            c->d_new_acc, c->d_new_start, c->d_new_evals, c->d_new_ne, c->d_new_nc,
+                                                            (double*)dev_send);
     CKL();
     c->launches += 1;
     return 0;
@@ -718,9 +820,10 @@ extern "C" int cpn_pack_shard(cpn_ctx* c, int32_t K, void* dev_send) {
 extern "C" int cpn_unpack_shards(cpn_ctx* c, int32_t K, const void* dev_recv) {
     if (check_K(c, K) || !dev_recv) return fail("bad argument");
     CK(cudaSetDevice(c->cfg.device));
-    const int S = c->Dp + 4, T = 256;
+    const int S = c->Dp + 5, T = 256;
     k_unpack_shards<<<(K * S + T - 1) / T, T, 0, c->stream>>>(K, c->Dp, (const double*)dev_recv, c->d_new_x, c->d_new_logL,
-                                                           c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_new_start, c->d_new_evals);
+                                                           c->d_new_logP, c->d_new_steps, c->d_new_acc, c->d_new_start, c->d_new_evals,
+                                                           c->d_new_ne, c->d_new_nc);
     CKL();
     c->launches += 1;
     return 0;
@@ -736,6 +839,10 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         k_chain_corr<<<c->D + 2, 256, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
                                                       c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc, c->d_new_evals);
         c->launches += 1;
+        if (c->cfg.sampler == CPN_SAMPLER_SLICE) {
+            k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_ne, c->d_new_nc);
+            c->launches += 1;
+        }
     }
     k_rank_new<<<(K + T - 1) / T, T, T * sizeof(double), c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
     MergeParams m;
@@ -854,6 +961,7 @@ extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
     o->total_evals = (int64_t)(s->totals[2] + s->batch[2]);
     o->failed_chains = (int64_t)(s->totals[3] + s->batch[3]);
     o->nmcmc = s->nmcmc; o->done = s->done; o->rho_max = s->rho_max;
+    o->slice_mu = s->slice_mu; o->hmc_dt = s->hmc_dt;
     return 0;
 }
 
@@ -1004,18 +1112,11 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
     CK(cudaMemcpyAsync(d_rec, requests, need * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int T = 256;
     k_unpack_records<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(d_rec, K, D, Dp, c->d_start_x, c->d_start_logL, c->d_start_logP);
-    MHParams p;
-    fill_mh(c, &p);
-    p.start_mode = START_GIVEN;
-    p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
-    p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = std::max(1, std::min(nmcmc, c->cfg.maxmcmc));
-    p.j0 = 0; p.j1 = K;
-    p.n_out = 1;                                   // the host protocol is served by one GPU
-    int G, E;
-    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, K, &G, &E)) return 1;
-    if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    // the host protocol is served by one GPU (n_out = 1)
+    if (launch_chains(c, K, 0, K, START_GIVEN, 0, true, logLmin, std::max(1, std::min(nmcmc, c->cfg.maxmcmc)), 1)) return 1;
     k_batch_counters<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_steps, c->d_new_acc, c->d_new_evals);
     k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K, nullptr, nullptr, 0);
+    if (c->cfg.sampler == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_ne, c->d_new_nc);
     if (slots) {
         CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         k_pool_append<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rank, K, c->N, Dp, c->d_new_x, c->d_new_logL,
@@ -1123,6 +1224,108 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
     void* fr[] = {dex, dsx, dsl, dsp, dev, des, dtape, dox, dol, dop, dst, dac, dEL, dEP, dstates};
     for (void* q : fr)
         if (q) cudaFree(q);
+    return 0;
+}
+
+static int slice_scratch_launch(cpn_ctx* c, SliceParams& p, int replay, int lanes, int C) {
+    int G, E;
+    if (pick_config(c->D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) return 1;
+    if (kSlice[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no slice kernel for G=%d E=%d", G, E);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int cpn_replay_slice(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start,
+                                int32_t cycle_idx, const double* tape, const int64_t* tape_off, double mu, int32_t nmcmc,
+                                int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes, double* out, int32_t* steps,
+                                int32_t* accepted, int32_t* evals, double* last) {
+    if (!c || !ensemble || !start || !tape || !tape_off || !out) return fail("null argument");
+    if (P < 2 || C < 1 || maxmcmc < 1) return fail("bad sizes");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    std::vector<double> ex((size_t)P * Dp, 0.0), sx((size_t)C * Dp, 0.0), sl(C), sp(C);
+    for (int i = 0; i < P; ++i)
+        for (int d = 0; d < D; ++d) ex[(size_t)i * Dp + d] = ensemble[(size_t)i * D + d];
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) sx[(size_t)i * Dp + d] = start[(size_t)i * (D + 2) + d];
+        sl[i] = start[(size_t)i * (D + 2) + D];
+        sp[i] = start[(size_t)i * (D + 2) + D + 1];
+    }
+    const size_t ntape = (size_t)tape_off[C];
+    double *dex, *dsx, *dsl, *dsp, *dtape, *dox, *dol, *dop, *dlast, *dEL, *dEP;
+    long long* doff;
+    int *dst, *dac, *dev;
+    if (dalloc(&dex, ex.size()) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) || dalloc(&dtape, ntape + 8) ||
+        dalloc(&doff, C + 1) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) || dalloc(&dst, C) ||
+        dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dlast, (size_t)C * 4) || dalloc(&dEL, P) || dalloc(&dEP, P))
+        return 1;
+    CK(cudaMemcpy(dex, ex.data(), ex.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsl, sl.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsp, sp.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtape, tape, ntape * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(doff, tape_off, (C + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    SliceParams p;
+    memset(&p, 0, sizeof p);
+    p.ens_x = dex; p.ens_logL = dEL; p.ens_logP = dEP; p.ens_n = P; p.Dp = Dp; p.D = D;
+    p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
+    p.lo = c->d_lo; p.hi = c->d_hi;
+    p.cycle = c->d_slice_cycle; p.cycle_len = c->slice_cycle_len; p.cycle_pos0 = cycle_idx;
+    p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.mu_override = mu;
+    p.maxmcmc = maxmcmc; p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
+    p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
+    p.out_evals[0] = dev;
+    p.tape = dtape; p.tape_off = doff; p.compat = compat; p.last = dlast;
+    if (slice_scratch_launch(c, p, 1, lanes, C)) return 1;
+    std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
+    CK(cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
+        out[(size_t)i * (D + 2) + D] = ol[i];
+        out[(size_t)i * (D + 2) + D + 1] = op[i];
+    }
+    if (steps) CK(cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (accepted) CK(cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (evals) CK(cudaMemcpy(evals, dev, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (last) CK(cudaMemcpy(last, dlast, (size_t)C * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    void* fr[] = {dex, dsx, dsl, dsp, dtape, doff, dox, dol, dop, dst, dac, dev, dlast, dEL, dEP};
+    for (void* q : fr)
+        if (q) cudaFree(q);
+    return 0;
+}
+
+extern "C" int cpn_slice_directions(cpn_ctx* c, int32_t direction, int32_t C, double mu, double* out) {
+    if (!c || !out) return fail("null argument");
+    if (!c->live_ready) return fail("live set not initialised");
+    if (direction < CPN_SLICE_DIFF || direction > CPN_SLICE_CORR || C < 1 || C > c->N) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    if (adopt_pending_stats(c)) return 1;
+    uint8_t* dcyc;
+    double* ddir;
+    char* scratch;
+    if (dalloc(&dcyc, 4) || dalloc(&ddir, (size_t)C * c->D) || dalloc(&scratch, stage_bytes(c->N, c->Dp))) return 1;
+    CK(cudaMemset(dcyc, direction, 4));
+    CK(cudaStreamSynchronize(0));
+    SliceParams p;
+    fill_slice(c, &p);
+    p.cycle = dcyc; p.cycle_len = 4; p.cycle_pos0 = 0;
+    p.start_mode = START_SELF; p.j0 = 0; p.j1 = C;
+    p.use_override = 1; p.logLmin_override = -INFINITY; p.nmcmc_override = 0; p.mu_override = mu;
+    p.maxmcmc = 1;
+    p.n_out = 1;
+    p.out_x[0] = (double*)(scratch + stage_off(c->N, c->Dp, 0));
+    p.out_logL[0] = (double*)(scratch + stage_off(c->N, c->Dp, 1));
+    p.out_logP[0] = (double*)(scratch + stage_off(c->N, c->Dp, 2));
+    p.out_steps[0] = (int*)(scratch + stage_off(c->N, c->Dp, 3));
+    p.out_acc[0] = (int*)(scratch + stage_off(c->N, c->Dp, 4));
+    p.out_start[0] = nullptr; p.out_evals[0] = nullptr; p.out_ne[0] = nullptr; p.out_nc[0] = nullptr;
+    p.dir_out = ddir;
+    if (slice_scratch_launch(c, p, 0, 0, C)) return 1;
+    CK(cudaMemcpy(out, ddir, (size_t)C * c->D * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dcyc); cudaFree(ddir); cudaFree(scratch);
     return 0;
 }
 

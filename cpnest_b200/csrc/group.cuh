@@ -24,6 +24,16 @@ struct Group {
         for (int m = G >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m, G);
         return v;
     }
+    __device__ __forceinline__ double max(double v) const {
+#pragma unroll
+        for (int m = G >> 1; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, m, G));
+        return v;
+    }
+    __device__ __forceinline__ double min(double v) const {
+#pragma unroll
+        for (int m = G >> 1; m > 0; m >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, m, G));
+        return v;
+    }
     __device__ __forceinline__ double prod(double v) const {
 #pragma unroll
         for (int m = G >> 1; m > 0; m >>= 1) v *= __shfl_xor_sync(FULL, v, m, G);

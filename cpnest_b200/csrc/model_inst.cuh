@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include "eval_kernel.cuh"
 #include "mh_kernel.cuh"
+#include "slice_kernel.cuh"
 #include "launch.h"
 
 #define CPN_CONFIGS(X) X(1, 1) X(1, 2) X(1, 4) X(1, 8) X(4, 4) X(8, 2) X(8, 8) X(16, 4) X(32, 1) X(32, 2) X(32, 4) X(32, 8)
@@ -22,6 +23,24 @@ static int launch_mh_model(int G, int E, int replay, const MHParams& p, cudaStre
         const size_t sm = Model::kScratch ? (size_t)cpb * p.Dp * sizeof(double) : 0;                  \
         if (replay) k_mh_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                   \
         else k_mh_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                         \
+        return 0;                                                                                     \
+    }
+    CPN_CONFIGS(CPN_CASE)
+#undef CPN_CASE
+    return -1;
+}
+
+template <class Model>
+static int launch_slice_model(int G, int E, int replay, const SliceParams& p, cudaStream_t s) {
+    const int nchains = p.j1 - p.j0;
+    if (nchains <= 0) return 0;
+#define CPN_CASE(GG, EE)                                                                              \
+    if (G == GG && E == EE) {                                                                         \
+        const int cpb = kMHThreads / GG;                                                              \
+        const int nb = (nchains + cpb - 1) / cpb;                                                     \
+        const size_t sm = Model::kScratch ? (size_t)cpb * p.Dp * sizeof(double) : 0;                  \
+        if (replay) k_slice_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                \
+        else k_slice_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                      \
         return 0;                                                                                     \
     }
     CPN_CONFIGS(CPN_CASE)
@@ -54,5 +73,8 @@ static int launch_eval_model(int G, int E, const EvalParams& p, cudaStream_t s) 
     }                                                                                                 \
     int launch_eval_##NAME(int G, int E, const EvalParams& p, cudaStream_t s) {                       \
         return launch_eval_model<MODEL>(G, E, p, s);                                                  \
+    }                                                                                                 \
+    int launch_slice_##NAME(int G, int E, int replay, const SliceParams& p, cudaStream_t s) {         \
+        return launch_slice_model<MODEL>(G, E, replay, p, s);                                         \
     }                                                                                                 \
     }

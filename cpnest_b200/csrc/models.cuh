@@ -24,6 +24,7 @@ __device__ __forceinline__ bool valid_dim(const Group<G>& g, int e, int D) { ret
 
 // ---- flat prior, model.py:66-82 -------------------------------------------------------------
 struct FlatPrior {
+    static constexpr bool kFlatPrior = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_prior(const Group<G>&, const double (&)[E], const ModelCtx&) {
         return 0.0;
@@ -158,6 +159,7 @@ struct Ring : FlatPrior {
 
 // ---- (mean, sigma) Gaussian with a 1/sigma prior: tests/test_gaussian.py:15-20 ----------------
 struct GaussMeanSigma {
+    static constexpr bool kFlatPrior = false;
     static constexpr bool kScratch = false;
     static constexpr bool kCheap = true;
     template <int G, int E>
@@ -175,6 +177,7 @@ struct GaussMeanSigma {
 // ---- two-component mixture over a data vector: examples/gaussianmixture.py:22-31 ;
 //      blob = {n_data, data[n_data]} ; parameters (mean1, sigma1, mean2, sigma2, weight) ----------
 struct GaussMixture {
+    static constexpr bool kFlatPrior = false;
     static constexpr bool kScratch = false;
     static constexpr bool kCheap = false;
     template <int G, int E>

@@ -286,6 +286,29 @@ __global__ void __launch_bounds__(256) k_batch_counters(NSState* st, int K, cons
     block_batch_counters(st, K, steps, acc, evals);
 }
 
+// SliceSampler.adapt_length_scale (sampler.py:429-437): mu *= 2 Ne / (Ne + Nc).  The reference applies it per
+// chain with the counts of that chain's last slice, during its first 10*poolsize slices; here the counts of
+// ALL slices of the batch are pooled (integer sums: independent of order and of the split over GPUs), which
+// makes the estimate of the expansion/contraction balance precise enough to keep following the shrinking
+// constrained region for the whole run.
+__global__ void __launch_bounds__(256) k_adapt_slice_mu(NSState* st, int K, const int* ne, const int* nc) {
+    if (st->done) return;
+    __shared__ unsigned long long sh[2][256];
+    const int tid = threadIdx.x;
+    unsigned long long a = 0, b = 0;
+    for (int j = tid; j < K; j += 256) { a += (unsigned long long)ne[j]; b += (unsigned long long)nc[j]; }
+    sh[0][tid] = a; sh[1][tid] = b;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) { sh[0][tid] += sh[0][tid + w]; sh[1][tid] += sh[1][tid + w]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double Ne = fmax(1.0, (double)sh[0][0]), Nc = fmax(1.0, (double)sh[1][0]);
+        st->slice_mu *= 2.0 * (Ne / (Ne + Nc));
+    }
+}
+
 // corr_d(start, end) across the K chains of the batch, d in [0, D] (d == D is logL).
 // One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
 __global__ void __launch_bounds__(256) k_chain_corr(NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,

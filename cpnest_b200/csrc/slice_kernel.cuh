@@ -1,0 +1,378 @@
+// Ensemble slice sampling of the likelihood-constrained prior: the device form of
+//   SliceSampler.yield_sample                       cpnest/sampler.py:465-569
+//   SliceSampler.reset_boundaries / increase_*      cpnest/sampler.py:439-463
+//   EnsembleSliceProposalCycle.get_direction        cpnest/proposal.py:199-207
+//   EnsembleSliceDifferential / Gaussian / CorrelatedGaussian   cpnest/proposal.py:121-187
+// One launch evolves all chains of a nested-sampling batch, same lane layout as the MH kernel
+// (a chain = G lanes, E coordinates per lane).  Per slice: a direction through the current point,
+// stepping out in unit steps of the slice coordinate while the point stays in the box (and above the
+// prior slice level), then shrinkage towards the current point until a point with log_prior above
+// the slice level AND logL > logLmin is found.
+#pragma once
+#include <stdint.h>
+#include "group.cuh"
+#include "mh_kernel.cuh"
+#include "models.cuh"
+#include "rng.cuh"
+#include "state.cuh"
+#include "cpnest_b200.h"
+
+namespace cpn {
+
+struct SliceParams {
+    // ensemble = the live set, read-only during the launch
+    const double* ens_x;      // [ens_n][Dp]
+    const double* ens_logL;
+    const double* ens_logP;
+    int ens_n, Dp, D;
+    int start_mode;           // StartMode of mh_kernel.cuh
+    const int* order;
+    int n_skip;
+    const double* start_x;
+    const double* start_logL;
+    const double* start_logP;
+    const double* lo;
+    const double* hi;
+    // direction cycle (cpn_slice_direction per slot) and the ensemble statistics behind the
+    // correlated-Gaussian direction: N(mean, cov) = mean + sum_i z_i sqrt|lambda_i| v_i
+    const uint8_t* cycle;
+    int cycle_len, cycle_pos0;
+    const double* mean;       // [D]
+    const double* eig_scale;  // [D]
+    const double* eig_vec;    // [D][Dp]
+    // chain control
+    const NSState* state;
+    int use_override;
+    double logLmin_override;
+    int nmcmc_override;
+    double mu_override;       // slice length scale (SliceSampler.mu)
+    int maxmcmc;              // also max_steps_out and max_slices (sampler.py:424-425)
+    int j0, j1;
+    unsigned long long chain_base;
+    uint32_t seed_lo, seed_hi;
+    const double* blob;
+    // outputs, replicated to every peer's staging area
+    int n_out;
+    double* out_x[kMaxPeers];
+    double* out_logL[kMaxPeers];
+    double* out_logP[kMaxPeers];
+    int* out_steps[kMaxPeers];    // slices
+    int* out_acc[kMaxPeers];      // accepted slices
+    int* out_start[kMaxPeers];
+    int* out_evals[kMaxPeers];
+    int* out_ne[kMaxPeers];       // expansions, summed over the chain's slices
+    int* out_nc[kMaxPeers];       // contractions, summed over the chain's slices
+    // replay (parity) mode: per chain a flat tape  { uL, direction data, Exp(1), uJ, X'_1, X'_2, ... } per slice,
+    // direction data = {i0, i1} (differential) or the D-vector numpy returned (Gaussian kinds)
+    const double* tape;
+    const long long* tape_off;    // [chains + 1]
+    int compat;
+    double* last;                 // [chains][4] = {Ne, Nc, L, R} of the chain's last slice, or null
+    double* dir_out;              // [chains][D] direction of the chain's first slice, or null (tests)
+};
+
+template <int G, int E, class Model, bool REPLAY>
+__global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p) {
+    if (!REPLAY && p.state != nullptr && p.state->done) return;
+    const Group<G> g;
+    const int cpb = kMHThreads / G;
+    const int nchains = p.j1 - p.j0;
+    int c = blockIdx.x * cpb + (int)threadIdx.x / G;
+    if ((c & ~(32 / G - 1)) >= nchains) return;
+    const bool valid = c < nchains;
+    if (!valid) c = nchains - 1;
+    const int j = p.j0 + c;
+
+    extern __shared__ double smem[];
+    ModelCtx m;
+    m.blob = p.blob;
+    m.D = p.D;
+    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * p.Dp : nullptr;
+
+    const int D = p.D;
+    const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;
+    const int nmcmc = p.use_override ? p.nmcmc_override : p.state->nmcmc;
+    const double mu = p.use_override ? p.mu_override : p.state->slice_mu;
+    const int maxmcmc = p.maxmcmc;
+    const unsigned long long chain_id = p.chain_base + (unsigned long long)j;
+    const uint32_t cid_lo = (uint32_t)chain_id, cid_hi = (uint32_t)(chain_id >> 32);
+
+    // ---- start point: a member with logL > logLmin (sampler.py:471-478) ---------------------------
+    double x[E], logL, logP;
+    int start_slot = -1;
+    {
+        const double* row;
+        if (p.start_mode == START_GIVEN) {
+            row = p.start_x + (size_t)c * p.Dp;
+            logL = p.start_logL[c];
+            logP = p.start_logP[c];
+        } else {
+            int slot;
+            if (p.start_mode == START_SELF) {
+                slot = j;
+            } else {
+                Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu, 0u, p.seed_lo, p.seed_hi);
+                slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
+            }
+            start_slot = slot;
+            row = p.ens_x + (size_t)slot * p.Dp;
+            logL = p.ens_logL[slot];
+            logP = p.ens_logP[slot];
+        }
+        load_row<G, E>(g, row, D, x);
+    }
+    double blo[E], bhi[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = g.lane + e * G;
+        blo[e] = (d < D) ? __ldg(p.lo + d) : CPN_NEG_INF;
+        bhi[e] = (d < D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
+    }
+
+    int steps = 0, accepted = 0, evals = 0, ne_sum = 0, nc_sum = 0;
+    double Ne = 0.0, Nc = 0.0, L = 0.0, R = 0.0;
+    bool active = true;
+    const int clen = p.cycle_len;
+    int pos = p.cycle_pos0;
+    const double* tp = REPLAY ? p.tape + p.tape_off[c] : nullptr;
+    const uint32_t ens_n = (uint32_t)p.ens_n;
+    const double mu_diff = (REPLAY && p.compat) ? (double)(float)mu : mu;   // LivePoint * float, parameter.pyx:96
+
+    // point on the slice: direction * t + old (LivePoint.__mul__ then __add__; t rounded to fp32 in the reference)
+    auto along = [&](const double (&dir)[E], double t, double (&out)[E]) {
+        const double ts = (REPLAY && p.compat) ? (double)(float)t : t;
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = REPLAY ? __dadd_rn(__dmul_rn(dir[e], ts), x[e]) : fma(dir[e], ts, x[e]);
+    };
+    auto in_box = [&](const double (&v)[E]) -> bool {
+        bool inb = true;
+#pragma unroll
+        for (int e = 0; e < E; ++e) inb = inb & (blo[e] < v[e]) & (v[e] < bhi[e]);      // strict, model.py:33
+        return g.all(inb);
+    };
+
+    for (int s = 0;; ++s) {
+        if (!__any_sync(FULL, active)) break;
+        pos = (pos + 1 == clen) ? 0 : pos + 1;                       // pre-increment, proposal.py:203
+        const int kind = p.cycle[pos];
+
+        // ---- draws of this slice + direction ----------------------------------------------------------
+        double uL, eexp, uJ;
+        double dir[E];
+        if (REPLAY) {
+            uL = active ? tp[0] : 0.5;
+            const double* q = tp + 1;
+            if (kind == CPN_SLICE_DIFF) {
+                const uint32_t i0 = active ? (uint32_t)q[0] : 0u, i1 = active ? (uint32_t)q[1] : 1u;
+                double ra[E], rb[E];
+                load_row<G, E>(g, p.ens_x + (size_t)i0 * p.Dp, D, ra);
+                load_row<G, E>(g, p.ens_x + (size_t)i1 * p.Dp, D, rb);
+#pragma unroll
+                for (int e = 0; e < E; ++e) dir[e] = __dmul_rn(__dsub_rn(ra[e], rb[e]), mu_diff);   // proposal.py:131-133
+                q += 2;
+            } else {
+                double z[E], n2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int d = g.lane + e * G;
+                    z[e] = (active && d < D) ? q[d] : 0.0;
+                    n2 += z[e] * z[e];
+                }
+                if (kind == CPN_SLICE_GAUSS) {
+                    const double nrm = sqrt(g.sum(n2));               // np.linalg.norm, proposal.py:185
+#pragma unroll
+                    for (int e = 0; e < E; ++e) dir[e] = __dmul_rn(__ddiv_rn(z[e], nrm), mu);    // :186-187
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) dir[e] = __dmul_rn(mu, z[e]);                     // :172
+                }
+                q += D;
+            }
+            eexp = active ? q[0] : 1.0;
+            uJ = active ? q[1] : 0.5;
+            if (active) tp = q + 2;
+        } else {
+            const Philox4 r = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 0u, p.seed_lo, p.seed_hi);
+            uL = u32_to_unit_open(r.v[0]);                           // np.random.uniform(0,1), sampler.py:444
+            uJ = u32_to_unit_open(r.v[1]);                           // :491
+            eexp = -log(u32_to_unit_open(r.v[2]));                   // np.random.exponential(), :490
+            if (kind == CPN_SLICE_DIFF) {
+                const Philox4 r2 = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 1u, p.seed_lo, p.seed_hi);
+                const uint32_t i0 = u32_to_index(r.v[3], ens_n);     // sample(list(ensemble), 2), proposal.py:131
+                uint32_t i1 = u32_to_index(r2.v[0], ens_n - 1);
+                i1 += (i1 >= i0);
+                double ra[E], rb[E];
+                load_row<G, E>(g, p.ens_x + (size_t)i0 * p.Dp, D, ra);
+                load_row<G, E>(g, p.ens_x + (size_t)i1 * p.Dp, D, rb);
+#pragma unroll
+                for (int e = 0; e < E; ++e) dir[e] = (ra[e] - rb[e]) * mu;
+            } else {
+                // one N(0,1) per coordinate: block (chain, slice, 0x80000000 | d)
+                double z[E], n2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int d = g.lane + e * G;
+                    const Philox4 rz = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 0x80000000u | (uint32_t)d, p.seed_lo, p.seed_hi);
+                    double g0, g1;
+                    box_muller(rz.v[0], rz.v[1], g0, g1);
+                    z[e] = (d < D) ? g0 : 0.0;
+                    n2 += z[e] * z[e];
+                }
+                if (kind == CPN_SLICE_GAUSS) {
+                    const double sc = mu / sqrt(g.sum(n2));           // unit vector * mu, proposal.py:184-187
+#pragma unroll
+                    for (int e = 0; e < E; ++e) dir[e] = z[e] * sc;
+                } else {
+                    // mu * N(mean, cov) (the mean is not subtracted, proposal.py:172)
+                    double acc[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int d = g.lane + e * G;
+                        acc[e] = (d < D) ? __ldg(p.mean + d) : 0.0;
+                    }
+                    for (int i = 0; i < D; ++i) {
+                        const double zi = coord<G, E>(g, z, i) * __ldg(p.eig_scale + i);
+                        const double* vrow = p.eig_vec + (size_t)i * p.Dp;
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            const int d = g.lane + e * G;
+                            acc[e] = fma(zi, (d < D) ? __ldg(vrow + d) : 0.0, acc[e]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; ++e) dir[e] = mu * acc[e];
+                }
+            }
+        }
+        if (p.dir_out != nullptr && s == 0 && valid) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < D) p.dir_out[(size_t)c * D + d] = dir[e];
+            }
+        }
+
+        // ---- initial interval and stepping out (sampler.py:439-447, 489-524) ----------------------------
+        L = -uL;
+        R = L + 1.0;
+        Ne = 0.0;
+        Nc = 0.0;
+        const double Yp = logP - eexp;                               // :490
+        int J = (int)floor((double)maxmcmc * uJ);                    // :491
+        int K = (maxmcmc - 1) - J;                                   // :492
+        if (!REPLAY && Model::kFlatPrior) {
+            // Under the flat prior of Model.log_prior (model.py:66-82) stepping out only ends at the box or
+            // when its budget is spent: the number of unit steps follows from the interval of the slice
+            // coordinate that lies inside the box.
+            double tlo = CPN_NEG_INF, thi = -CPN_NEG_INF;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double a = (blo[e] - x[e]) / dir[e], b = (bhi[e] - x[e]) / dir[e];
+                const bool use = dir[e] != 0.0 && (blo[e] > CPN_NEG_INF);
+                tlo = use ? fmax(tlo, fmin(a, b)) : tlo;
+                thi = use ? fmin(thi, fmax(a, b)) : thi;
+            }
+            tlo = g.max(tlo);
+            thi = g.min(thi);
+            const double kl = fmin((double)J, fmax(0.0, ceil(L - tlo)));
+            const double kr = fmin((double)K, fmax(0.0, ceil(thi - R)));
+            L -= kl;
+            R += kr;
+            Ne = kl + kr;
+        } else {
+            bool go = active && J > 0;
+            while (__any_sync(FULL, go)) {                           // :495-508
+                double xt[E];
+                along(dir, L, xt);
+                const bool inb = in_box(xt);
+                const double lp = Model::template log_prior<G, E>(g, xt, m);
+                const bool grow = go && inb && !(Yp > lp);
+                L = grow ? L - 1.0 : L;
+                Ne = grow ? Ne + 1.0 : Ne;
+                J = grow ? J - 1 : J;
+                go = grow && J > 0;
+            }
+            go = active && K > 0;
+            while (__any_sync(FULL, go)) {                           // :512-524
+                double xt[E];
+                along(dir, R, xt);
+                const bool inb = in_box(xt);
+                const double lp = Model::template log_prior<G, E>(g, xt, m);
+                const bool grow = go && inb && !(Yp > lp);
+                R = grow ? R + 1.0 : R;
+                Ne = grow ? Ne + 1.0 : Ne;
+                K = grow ? K - 1 : K;
+                go = grow && K > 0;
+            }
+        }
+
+        // ---- shrinkage (sampler.py:529-551) ---------------------------------------------------------------
+        bool searching = active;
+        for (int sl = 0; sl < maxmcmc; ++sl) {
+            if (!__any_sync(FULL, searching)) break;
+            double Xp;
+            if (REPLAY) {
+                Xp = searching ? tp[0] : 0.0;                        // the value np.random.uniform(L, R) returned
+                if (searching) ++tp;
+            } else {
+                const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 0x40000000u | (uint32_t)(sl >> 2), p.seed_lo, p.seed_hi);
+                const uint32_t w = (sl & 2) ? ((sl & 1) ? ru.v[3] : ru.v[2]) : ((sl & 1) ? ru.v[1] : ru.v[0]);
+                Xp = fma(R - L, u32_to_unit_open(w), L);
+            }
+            double xn[E];
+            along(dir, Xp, xn);
+            const bool inb = in_box(xn);
+            double logP_new = Model::template log_prior<G, E>(g, xn, m);
+            logP_new = inb ? logP_new : CPN_NEG_INF;
+            const bool pass = searching && (logP_new > Yp);          // :535
+            bool acc = false;
+            if (Model::kCheap || __any_sync(FULL, pass)) {
+                const double logL_new = Model::template log_likelihood<G, E>(g, xn, m);   // :537
+                evals += pass ? 1 : 0;
+                acc = pass && (logL_new > logLmin);                  // :538
+#pragma unroll
+                for (int e = 0; e < E; ++e) x[e] = acc ? xn[e] : x[e];
+                logL = acc ? logL_new : logL;
+                logP = acc ? logP_new : logP;
+                accepted += acc ? 1 : 0;
+            }
+            const bool shrink = searching && !acc;
+            if (shrink && Xp < 0.0) { L = Xp; Nc += 1.0; }           // :545-550
+            else if (shrink && Xp > 0.0) { R = Xp; Nc += 1.0; }
+            searching = shrink;
+        }
+        if (active) {
+            ++steps;
+            ne_sum += (int)Ne;
+            nc_sum += (int)Nc;
+            if ((steps > nmcmc && accepted > 0) || steps > maxmcmc) active = false;   // :553-557
+        }
+    }
+
+    if (valid) {
+        for (int o = 0; o < p.n_out; ++o) {
+            double* row = p.out_x[o] + (size_t)j * p.Dp;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < p.Dp) row[d] = (d < D) ? x[e] : 0.0;
+            }
+            if (g.lane == 0) {
+                p.out_logL[o][j] = logL;
+                p.out_logP[o][j] = logP;
+                p.out_steps[o][j] = steps;
+                p.out_acc[o][j] = accepted;
+                if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
+                if (p.out_evals[o] != nullptr) p.out_evals[o][j] = evals;
+                if (p.out_ne[o] != nullptr) p.out_ne[o][j] = ne_sum;
+                if (p.out_nc[o] != nullptr) p.out_nc[o][j] = nc_sum;
+            }
+        }
+        if (p.last != nullptr && g.lane == 0) {
+            double* q = p.last + (size_t)c * 4;
+            q[0] = Ne; q[1] = Nc; q[2] = L; q[3] = R;
+        }
+    }
+}
+
+}  // namespace cpn

@@ -18,6 +18,8 @@ struct NSState {
     double nmcmc_tau;     // decay of the moving average, in chains
     double rho_target;    // chains run until the start/end correlation across the batch falls to this
     double rho_max;       // smoothed max_d |corr(start_d, end_d)| of the last batches (d includes logL)
+    double slice_mu;      // SliceSampler.mu: length scale of the slice directions (sampler.py:422, 429-437)
+    double hmc_dt;        // HamiltonianProposal.dt: leapfrog time step (proposal.py:393, 539-552)
     long long iteration;  // NestedSampler.iteration == number of dead points
     long long n_hist;     // len(state.logLs) - 1
     long long n_ins;      // len(insertion_indices)

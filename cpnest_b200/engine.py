@@ -38,7 +38,7 @@ def functor_blob(name, dim, params=None):
 class Engine:
     def __init__(self, functor, bounds, nlive, maxmcmc=100, seed=1234, params=None, device=0,
                  nmcmc_init=0, lanes=0, ns_mode="sequential", nmcmc_safety=5.0, adapt_nmcmc=True,
-                 rho_target=0.0, rank=0, world_size=1):
+                 rho_target=0.0, rank=0, world_size=1, sampler="mh"):
         self.lib = L.load()
         self.functor = functor
         self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
@@ -60,6 +60,10 @@ class Engine:
         cfg.rho_target = float(rho_target)
         cfg.world_size = int(world_size)
         cfg.rank = int(rank)
+        if sampler not in L.SAMPLERS:
+            raise ValueError("unknown sampler %r (known: %s)" % (sampler, ", ".join(L.SAMPLERS)))
+        cfg.sampler = L.SAMPLERS[sampler]
+        self.sampler = sampler
         blob = L.f64(functor_blob(functor, self.dim, params))
         lo = L.f64(self.bounds[:, 0])
         hi = L.f64(self.bounds[:, 1])
@@ -91,6 +95,13 @@ class Engine:
     def set_cycle(self, cycle):
         cyc = np.ascontiguousarray(cycle, dtype=np.uint8)
         L.check(self.lib.cpn_set_cycle(self.h, cyc.ctypes.data_as(C.POINTER(C.c_uint8)), len(cyc)))
+
+    def set_slice_cycle(self, cycle):
+        cyc = np.ascontiguousarray(cycle, dtype=np.uint8)
+        L.check(self.lib.cpn_set_slice_cycle(self.h, cyc.ctypes.data_as(C.POINTER(C.c_uint8)), len(cyc)))
+
+    def set_slice_mu(self, mu):
+        L.check(self.lib.cpn_set_slice_mu(self.h, float(mu)))
 
     def init_prior(self):
         L.check(self.lib.cpn_init_prior(self.h))
@@ -223,6 +234,32 @@ class Engine:
                                        1 if compat else 0, int(lanes), L.dptr(out), L.iptr(steps), L.iptr(acc),
                                        L.dptr(states) if record else None))
         return out, steps, acc, states
+
+    def replay_slice(self, ensemble, start, cycle_idx, tapes, mu, nmcmc, maxmcmc, logLmin, compat=True, lanes=0):
+        """Slice chains from explicit random tapes (one flat float sequence per chain, see
+        include/cpnest_b200.h cpn_replay_slice).  Returns (out, steps, accepted, evals, last)."""
+        ens = L.f64(ensemble)
+        start = L.f64(start).reshape(-1, self.dim + 2)
+        Cn = start.shape[0]
+        assert len(tapes) == Cn
+        off = np.zeros(Cn + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(t) for t in tapes])
+        tape = L.f64(np.concatenate([np.asarray(t, dtype=np.float64) for t in tapes]))
+        out = np.empty((Cn, self.dim + 2))
+        steps = np.empty(Cn, dtype=np.int32)
+        acc = np.empty(Cn, dtype=np.int32)
+        evals = np.empty(Cn, dtype=np.int32)
+        last = np.empty((Cn, 4))
+        L.check(self.lib.cpn_replay_slice(self.h, ens.shape[0], L.dptr(ens), Cn, L.dptr(start), int(cycle_idx), L.dptr(tape),
+                                          off.ctypes.data_as(C.POINTER(C.c_int64)), float(mu), int(nmcmc), int(maxmcmc),
+                                          float(logLmin), 1 if compat else 0, int(lanes), L.dptr(out), L.iptr(steps),
+                                          L.iptr(acc), L.iptr(evals), L.dptr(last)))
+        return out, steps, acc, evals, last
+
+    def slice_directions(self, direction, n, mu=1.0):
+        out = np.empty((n, self.dim))
+        L.check(self.lib.cpn_slice_directions(self.h, int(direction), int(n), float(mu), L.dptr(out)))
+        return out
 
     def stage_replacements(self, rows):
         rows = L.f64(rows).reshape(-1, self.dim + 2)

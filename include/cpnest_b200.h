@@ -40,6 +40,16 @@ enum cpn_functor {
 /* proposal ids, order of DefaultProposalCycle (cpnest/proposal.py:354-361) */
 enum cpn_proposal { CPN_WALK = 0, CPN_STRETCH = 1, CPN_DE = 2, CPN_EIGEN = 3 };
 
+/* sampler choice: CPNest(nthreads - nslice - nhamiltonian, nslice, nhamiltonian) (cpnest/cpnest.py:197-261) */
+enum cpn_sampler {
+    CPN_SAMPLER_MH = 0,    /* MetropolisHastingsSampler + DefaultProposalCycle (cpnest/sampler.py:316-358) */
+    CPN_SAMPLER_SLICE = 1, /* SliceSampler + EnsembleSliceProposalCycle (cpnest/sampler.py:414-569) */
+    CPN_SAMPLER_HMC = 2    /* HamiltonianMonteCarloSampler + ConstrainedLeapFrog (cpnest/sampler.py:360-412) */
+};
+
+/* slice direction ids, order of EnsembleSliceProposalCycle (cpnest/proposal.py:196) */
+enum cpn_slice_direction { CPN_SLICE_DIFF = 0, CPN_SLICE_GAUSS = 1, CPN_SLICE_CORR = 2 };
+
 /* evidence accumulation rule for one batch of K dead points */
 enum cpn_ns_mode {
     CPN_NS_SEQUENTIAL = 0, /* per-point shrinkage -1/(N-i), the reference's final-sweep rule
@@ -61,7 +71,7 @@ typedef struct cpn_config {
     int32_t adapt_nmcmc;   /* 1: adapt chain length from the batch acceptance; 0: keep nmcmc_init */
     int32_t world_size;    /* number of ranks sharing the live set (1 = single GPU) */
     int32_t rank;
-    int32_t reserved;
+    int32_t sampler;       /* enum cpn_sampler */
     double rho_target;     /* chain-length control: start/end correlation to reach; <=0: 0.1 */
 } cpn_config;
 
@@ -84,6 +94,8 @@ typedef struct cpn_state {
     int64_t failed_chains; /* chains that returned with no accepted step (NestedSampling.py:354-357) */
     int32_t nmcmc;         /* Sampler.Nmcmc */
     int32_t done;          /* condition <= tolerance reached */
+    double slice_mu;       /* SliceSampler.mu */
+    double hmc_dt;         /* HamiltonianProposal.dt */
 } cpn_state;
 
 const char* cpn_last_error(void);
@@ -97,6 +109,10 @@ void cpn_destroy(cpn_ctx* ctx);
 /* ProposalCycle.set_cycle (cpnest/proposal.py:71-75): the host draws the cycle (np.random.choice)
  * and hands the device the proposal id per slot. */
 int cpn_set_cycle(cpn_ctx* ctx, const uint8_t* cycle, int32_t len);
+/* EnsembleSliceProposalCycle (cpnest/proposal.py:189-207): direction id (enum cpn_slice_direction) per slot. */
+int cpn_set_slice_cycle(cpn_ctx* ctx, const uint8_t* cycle, int32_t len);
+/* SliceSampler.mu (cpnest/sampler.py:422): initial / current length scale of the slice directions. */
+int cpn_set_slice_mu(cpn_ctx* ctx, double mu);
 
 /* Sampler.reset + NestedSampler.reset (cpnest/sampler.py:110-154, NestedSampling.py:404-431):
  * draw nlive points uniformly in bounds (Model.new_point, model.py:35-53), evaluate, evolve each
@@ -186,6 +202,21 @@ int cpn_replay_mh(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C, co
                   double logLmin, int32_t compat, int32_t lanes,
                   double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted,
                   double* states /*[C][maxmcmc][D] or NULL*/);
+/* Slice chains driven by an explicit random tape (SliceSampler.yield_sample, cpnest/sampler.py:465-569).
+ * Per chain c the doubles tape[tape_off[c] .. tape_off[c+1]) hold, slice after slice,
+ *   { u of reset_boundaries, direction data, Exp(1) draw, u of J, X'_1, X'_2, ... }
+ * with direction data = {i0, i1} (EnsembleSliceDifferential: the two `sample`d members) or the D-vector numpy
+ * returned (np.random.normal for EnsembleSliceGaussian, multivariate_normal for ...CorrelatedGaussian), and X'_k
+ * the values np.random.uniform(L, R) returned.  cycle_idx indexes the slice cycle.  last[C][4] = {Ne, Nc, L, R}
+ * of each chain's last slice. */
+int cpn_replay_slice(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C, const double* start,
+                     int32_t cycle_idx, const double* tape, const int64_t* tape_off, double mu,
+                     int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes,
+                     double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted, int32_t* evals,
+                     double* last /*[C][4]*/);
+/* Directions of the production slice kernel for chains [0, C) of the next batch's first slice, all of kind
+ * `direction` (test entry: distribution of the three direction proposals, cpnest/proposal.py:121-187). */
+int cpn_slice_directions(cpn_ctx* ctx, int32_t direction, int32_t C, double mu, double* out /*[C][D]*/);
 /* Put K given records into the replacement staging area, as if the chains had returned them
  * (`proposed` of NestedSampling.py:342): lets a test script the samplers' replies. */
 int cpn_stage_replacements(cpn_ctx* ctx, int32_t K, const double* rows /*[K][D+2]*/);

@@ -350,6 +350,111 @@ def mh_chain(model, pool, pool_logL, pool_logP, cycle, cycle_idx, eigen_values, 
 
 
 # ----------------------------------------------------------------------------------------
+# SliceSampler.yield_sample (cpnest/sampler.py:414-569) with the direction proposals of
+# EnsembleSliceProposalCycle (cpnest/proposal.py:114-207)
+# ----------------------------------------------------------------------------------------
+SLICE_DIFF, SLICE_GAUSS, SLICE_CORR = 0, 1, 2      # order of EnsembleSliceProposalCycle (proposal.py:196)
+
+
+def slice_direction(kind, ens, mu, tp, compat=True):
+    """proposal.py:126-133 (differential: `reduce(__sub__, sample(ens, 2)) * mu`, a LivePoint times a
+    scalar, i.e. mu rounded to fp32), :180-187 (unit Gaussian direction, numpy: full fp64) and
+    :167-173 (`mu * multivariate_normal(mean, cov)`; the mean is NOT subtracted).  For the two
+    numpy kinds the tape holds the vector numpy returned (np.random.normal / multivariate_normal)."""
+    if kind == SLICE_DIFF:
+        ia, ib = tp.take("sample")
+        d = np.asarray(ens[ia], dtype=np.float64) - np.asarray(ens[ib], dtype=np.float64)
+        return lp_mul(d, mu, compat)
+    if kind == SLICE_GAUSS:
+        z = np.array(tp.take("np_normal"), dtype=np.float64)
+        z = z / np.linalg.norm(z)
+        return z * mu
+    z = np.array(tp.take("np_mvn"), dtype=np.float64)
+    return mu * z
+
+
+def slice_chain(model, pool, pool_logL, pool_logP, cycle, cycle_idx, mu, tape, Nmcmc, maxmcmc, logLmin,
+                compat=True, mcmc_counter=0, tuning_steps=None):
+    """One `next(yield_sample(logLmin))` of the reference's SliceSampler.  `pool*` mirror the
+    deque `evolution_points` and are modified in place.  Returns dict(out, logL, logP, steps,
+    accepted, cycle_idx, mu, Ne, Nc, L, R, evals)."""
+    tp = tape if isinstance(tape, TapeReader) else TapeReader(tape)
+    P = len(pool)
+    max_steps_out = max_slices = maxmcmc                                  # sampler.py:424-425
+    # :471-478 first pool member above the threshold (at most poolsize pops; the last popped one is
+    # kept even if it fails, exactly as the reference does)
+    j = 0
+    while j < P:
+        old = np.array(pool.pop(0), dtype=np.float64)
+        old_logL = pool_logL.pop(0)
+        old_logP = pool_logP.pop(0)
+        if old_logL > logLmin:
+            break
+        pool.append(old); pool_logL.append(old_logL); pool_logP.append(old_logP)
+        j += 1
+    ens = pool
+    sub_counter = sub_accepted = evals = 0
+    Ne = Nc = 0.0
+    L = R = 0.0
+    while True:
+        L = -tp.take("np_uniform")                                        # reset_boundaries :444-447
+        R = L + 1.0
+        Ne = Nc = 0.0
+        sub_counter += 1
+        cycle_idx = (cycle_idx + 1) % len(cycle)                          # proposal.py:203
+        direction = slice_direction(int(cycle[cycle_idx]), ens, mu, tp, compat)
+        Y = logLmin
+        Yp = old_logP - tp.take("np_exponential")                         # :490
+        J = math.floor(max_steps_out * tp.take("np_uniform"))             # :491
+        K = (max_steps_out - 1) - J
+        while J > 0:                                                      # :495-508
+            left = lp_mul(direction, L, compat) + old
+            if model.in_bounds(left):
+                if Yp > model.log_prior(left):
+                    break
+                L -= 1.0; Ne += 1; J -= 1
+            else:
+                break
+        while K > 0:                                                      # :512-524
+            right = lp_mul(direction, R, compat) + old
+            if model.in_bounds(right):
+                if Yp > model.log_prior(right):
+                    break
+                R += 1.0; Ne += 1; K -= 1
+            else:
+                break
+        sl = 0
+        while sl < max_slices:                                            # :529-551
+            Xp = tp.take("np_uniform")                                    # np.random.uniform(L, R): value drawn
+            new = lp_mul(direction, Xp, compat) + old
+            new_logP = model.log_prior(new)
+            if new_logP > Yp:
+                new_logL = model.log_likelihood(new)
+                evals += 1
+                if new_logL > Y:
+                    old, old_logL, old_logP = new, new_logL, new_logP
+                    sub_accepted += 1
+                    break
+            if Xp < 0.0:
+                L = Xp; Nc += 1
+            elif Xp > 0.0:
+                R = Xp; Nc += 1
+            sl += 1
+        if sub_counter > Nmcmc and sub_accepted > 0:                      # :553-554
+            break
+        if sub_counter > maxmcmc:                                         # :556-557
+            break
+    pool.append(old); pool_logL.append(old_logL); pool_logP.append(old_logP)
+    mcmc_counter += sub_counter
+    if tuning_steps is None:
+        tuning_steps = 10 * (P)                                           # :426
+    if mcmc_counter < tuning_steps:                                       # :566-567, adapt_length_scale :429-437
+        mu = mu * (2 * (max(1, Ne) / (max(1, Ne) + max(1, Nc))))
+    return dict(out=old, logL=old_logL, logP=old_logP, steps=sub_counter, accepted=sub_accepted,
+                cycle_idx=cycle_idx, mu=mu, Ne=Ne, Nc=Nc, L=L, R=R, evals=evals, mcmc_counter=mcmc_counter)
+
+
+# ----------------------------------------------------------------------------------------
 # Evidence integrator (cpnest/NestedSampling.py:88-144) and helpers (cpnest/nest2pos.py:17-42)
 # ----------------------------------------------------------------------------------------
 def logsubexp(x, y):

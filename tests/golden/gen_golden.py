@@ -414,6 +414,125 @@ def gen_mh_chain():
 
 
 # --------------------------------------------------------------------------------------
+# H. SliceSampler.yield_sample traces (cpnest/sampler.py:414-569, cpnest/proposal.py:114-207)
+# --------------------------------------------------------------------------------------
+class _NpRandomTape:
+    """Stands in for `np.random` inside cpnest.sampler / cpnest.proposal: draws from a private
+    RandomState and records every value the reference receives."""
+
+    def __init__(self, tape, seed):
+        self.tape = tape
+        self.rs = np.random.RandomState(seed)
+
+    def uniform(self, low=0.0, high=1.0, size=None):
+        v = self.rs.uniform(low, high, size)
+        self.tape.events.append(["np_uniform", float(v)])
+        return v
+
+    def exponential(self, scale=1.0, size=None):
+        v = self.rs.exponential(scale, size)
+        self.tape.events.append(["np_exponential", float(v)])
+        return v
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        v = self.rs.normal(loc, scale, size)
+        self.tape.events.append(["np_normal", np.atleast_1d(v).tolist()])
+        return v
+
+    def multivariate_normal(self, mean, cov):
+        v = self.rs.multivariate_normal(mean, cov)
+        self.tape.events.append(["np_mvn", np.atleast_1d(v).tolist()])
+        return v
+
+    def __getattr__(self, name):          # choice(), seed(), ... : not on the recorded path
+        return getattr(np.random, name)
+
+
+class _NpShim:
+    """`np` as seen by the reference module: numpy, except for `.random`."""
+
+    def __init__(self, rnd):
+        self.random = rnd
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+def gen_slice_chain():
+    models = reference_models()
+    out = []
+    letter = {rprop.EnsembleSliceDifferential: 0, rprop.EnsembleSliceGaussian: 1,
+              rprop.EnsembleSliceCorrelatedGaussian: 2}
+    specs = [
+        # (model, poolsize, Nmcmc, maxmcmc, nchains, logLmin quantile, scale of pool, mu)
+        ("gaussian2d", 16, 4, 30, 4, 0.3, 3.0, 1.0),
+        ("gaussian_mean_sigma", 20, 3, 24, 4, 0.3, None, 0.4),     # non-flat prior: stepping out stops on Yp
+        ("gaussian10d", 32, 5, 40, 3, 0.2, 1.5, 0.7),
+        ("rosenbrock2d", 24, 4, 30, 3, 0.4, 1.0, 1.5),
+        ("ring", 24, 4, 30, 3, 0.5, None, 0.5),
+        ("gaussian50d", 96, 3, 20, 2, 0.05, 1.2, 2.0),
+        ("gaussian2d", 16, 2, 4, 4, 0.97, 3.0, 1.0),               # nearly impossible constraint: max_slices exits
+    ]
+    real_np_samp, real_np_prop = rsamp.np, rprop.np
+    for si, (mname, P, Nmcmc, maxmcmc, nchains, q, scale, mu) in enumerate(specs):
+        model = models[mname]
+        D = len(model.names)
+        rs = np.random.RandomState(300 + si)
+        lo = np.array([b[0] for b in model.bounds], dtype=float)
+        hi = np.array([b[1] for b in model.bounds], dtype=float)
+        if scale is None:
+            X = lo + (hi - lo) * rs.uniform(size=(P, D))
+        else:
+            X = np.clip(rs.normal(size=(P, D)) * scale, lo + 1e-3, hi - 1e-3)
+        pts = make_points(model.names, X)
+        for p in pts:
+            p.logP = float(model.log_prior(p))
+            p.logL = float(np.asarray(model.log_likelihood(p)).reshape(-1)[0])
+        logLs = np.array([p.logL for p in pts])
+        logLmin = float(np.quantile(logLs, q))
+        np.random.seed(4321 + si)
+        cycle = rprop.EnsembleSliceProposalCycle()
+        tape = Tape(7000 + si)
+        install_tape(tape)
+        rnd = _NpRandomTape(tape, 9000 + si)
+        rsamp.np = _NpShim(rnd)
+        rprop.np = _NpShim(rnd)
+        try:
+            mgr = _FakeManager()
+            smp = rsamp.SliceSampler(model, maxmcmc, seed=1, poolsize=P, proposal=cycle, manager=mgr)
+            # what SliceSampler.reset sets (sampler.py:423-427), without its prior draw / burn-in
+            smp.mu = mu
+            smp.max_steps_out = smp.maxmcmc
+            smp.max_slices = smp.maxmcmc
+            smp.tuning_steps = 10 * P
+            smp.Nmcmc = Nmcmc
+            for p in pts:
+                smp.evolution_points.append(p)
+            cycle.set_ensemble(smp.evolution_points)
+            corr = [p for p in cycle.proposals if isinstance(p, rprop.EnsembleSliceCorrelatedGaussian)][0]
+            case = dict(model=mname, D=D, P=P, Nmcmc=Nmcmc, maxmcmc=maxmcmc, logLmin=logLmin, mu0=mu,
+                        pool=X.tolist(), pool_logL=logLs.tolist(), pool_logP=[p.logP for p in pts],
+                        cycle=[letter[type(p)] for p in cycle.cycle],
+                        mean=np.atleast_1d(corr.mean).tolist(), covariance=np.atleast_2d(corr.covariance).tolist(),
+                        chains=[])
+            gen = smp.yield_sample(logLmin)
+            for c in range(nchains):
+                tape.events = []
+                idx0 = cycle.idx
+                mu_before = smp.mu
+                steps, outp = next(gen)
+                case["chains"].append(dict(cycle_idx_before=idx0, mu_before=fl(mu_before), mu_after=fl(smp.mu),
+                                           tape=tape.events, steps=steps, out=list(outp.values),
+                                           out_logL=fl(outp.logL), out_logP=fl(outp.logP),
+                                           sub_acceptance=fl(smp.sub_acceptance), Ne=fl(smp.Ne), Nc=fl(smp.Nc),
+                                           L=fl(smp.L), R=fl(smp.R), logLmax=fl(mgr.logLmax.value)))
+        finally:
+            rsamp.np, rprop.np = real_np_samp, real_np_prop
+        out.append(case)
+    dump("slice_chain.json", out)
+
+
+# --------------------------------------------------------------------------------------
 # G. NestedSampler.consume_sample / final sweep with scripted samplers
 #    (cpnest/NestedSampling.py:318-375, 433-493)
 # --------------------------------------------------------------------------------------
@@ -499,6 +618,6 @@ def gen_ns_loop(tmpdir="/tmp/cpnest_golden_ns"):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["integrator", "nest2pos", "proposals", "cycle", "models", "mh_chain", "ns_loop"]
+    which = sys.argv[1:] or ["integrator", "nest2pos", "proposals", "cycle", "models", "mh_chain", "slice_chain", "ns_loop"]
     for w in which:
         globals()["gen_" + w]()

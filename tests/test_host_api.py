@@ -25,9 +25,9 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_abi_struct_sizes_match_header():
     import ctypes
     from cpnest_b200 import _lib
-    # cpn_config: 8 int32 + uint64 + double + 4 int32 + double ; cpn_state: 8 doubles + 7 int64 + 2 int32
+    # cpn_config: 8 int32 + uint64 + double + 4 int32 + double ; cpn_state: 8 doubles + 7 int64 + 2 int32 + 2 doubles
     assert ctypes.sizeof(_lib.cpn_config) == 8 * 4 + 8 + 8 + 4 * 4 + 8
-    assert ctypes.sizeof(_lib.cpn_state) == 8 * 8 + 7 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.cpn_state) == 8 * 8 + 7 * 8 + 2 * 4 + 2 * 8
 
 
 def test_no_cpu_fallback_fails_loudly():

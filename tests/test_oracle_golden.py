@@ -162,6 +162,35 @@ def test_mh_chain_golden(golden):
     assert nchains >= 20
 
 
+def test_slice_chain_golden(golden):
+    """SliceSampler.yield_sample (sampler.py:465-569): chain outcome, interval, expansion/contraction
+    counts and the adapted length scale, bit for bit, from the reference's recorded random numbers."""
+    mg = golden("models.json")
+    nchains = 0
+    for case in golden("slice_chain.json"):
+        m = _model_for(case["model"], mg[case["model"]])
+        pool = [np.array(p) for p in case["pool"]]
+        pool_logL = list(case["pool_logL"])
+        pool_logP = list(case["pool_logP"])
+        idx, mu, counter = 0, case["mu0"], 0
+        for ch in case["chains"]:
+            assert idx == ch["cycle_idx_before"] and mu == ch["mu_before"]
+            tp = O.TapeReader(ch["tape"])
+            r = O.slice_chain(m, pool, pool_logL, pool_logP, case["cycle"], idx, mu, tp, case["Nmcmc"],
+                              case["maxmcmc"], case["logLmin"], mcmc_counter=counter, tuning_steps=10 * case["P"])
+            assert tp.exhausted()
+            idx, mu, counter = r["cycle_idx"], r["mu"], r["mcmc_counter"]
+            assert r["steps"] == ch["steps"]
+            assert r["accepted"] == round(ch["sub_acceptance"] * ch["steps"])
+            assert (r["Ne"], r["Nc"], r["L"], r["R"]) == (ch["Ne"], ch["Nc"], ch["L"], ch["R"]), case["model"]
+            assert close(r["out"], ch["out"], 1e-15), case["model"]      # direction norm: numpy dot vs nrm2
+            assert close(r["logL"], ch["out_logL"], 1e-13)
+            assert close(r["logP"], ch["out_logP"], 1e-13)
+            assert r["mu"] == ch["mu_after"]
+            nchains += 1
+    assert nchains >= 20
+
+
 def test_ns_loop_golden(golden):
     for case in golden("ns_loop.json"):
         ns = O.NSLoopOracle(case["L0"], mode="reference")
