@@ -35,8 +35,12 @@ class CPNest(object):
     maxmcmc   : maximum chain length
     nthreads  : in the reference, the number of sampler processes == points replaced per iteration
                 (cpnest/NestedSampling.py:324); here a lower bound for the batch size, see `batch`
-    nhamiltonian, nslice : samplers without a device kernel yet -> NotImplementedError if > 0
-    proposals : dict(mhs=ProposalCycle subclass); only device proposals are accepted
+    nslice    : number of slice samplers.  The reference mixes sampler kinds across its processes; one device
+                context runs ONE kind per run: nslice == nthreads (as in the reference's own tests and examples,
+                tests/test_2d_slice.py:30, examples/test_50d.py:37) selects the slice kernel, a mixed
+                population raises NotImplementedError
+    nhamiltonian : no device kernel yet -> NotImplementedError if > 0
+    proposals : dict(mhs=ProposalCycle subclass, sli=EnsembleSliceProposalCycle subclass); device proposals only
     prior_sampling : produce nlive samples from the prior and stop
 
     Device-only keywords: device (CUDA ordinal), batch (chains per kernel launch, default
@@ -56,18 +60,27 @@ class CPNest(object):
         self.logger = logging.getLogger("cpnest.cpnest.CPNest")
         self.log_file = LogFile(os.path.join(self.output, "cpnest.log"), verbose=self.verbose)
         with self.log_file:
-            if nhamiltonian or nslice:
+            n_mh = self.nthreads - nhamiltonian - nslice
+            kinds = [k for k, n in (("mh", n_mh), ("slice", nslice), ("hmc", nhamiltonian)) if n > 0]
+            if len(kinds) != 1:
                 raise NotImplementedError(
-                    "nhamiltonian/nslice > 0: only the Metropolis-Hastings sampler has a device kernel so far")
+                    "nthreads={0}, nslice={1}, nhamiltonian={2}: one device context runs a single sampler kind; "
+                    "use nslice == nthreads (or nhamiltonian == nthreads) for a pure population".format(
+                        self.nthreads, nslice, nhamiltonian))
+            self.sampler_kind = kinds[0]
+            if self.sampler_kind == "hmc":
+                raise NotImplementedError("nhamiltonian > 0: the Hamiltonian sampler has no device kernel yet")
             if resume:
                 self.logger.critical("resume=True: checkpoint/resume is not implemented on the device yet; starting fresh")
             if n_periodic_checkpoint is not None:
                 self.logger.critical("The n_periodic_checkpoint kwarg is deprecated, use periodic_checkpoint_interval instead.")
-            from .proposal import DefaultProposalCycle
+            from .proposal import DefaultProposalCycle, EnsembleSliceProposalCycle
+            defaults = dict(mhs=DefaultProposalCycle, sli=EnsembleSliceProposalCycle)     # cpnest/cpnest.py:155-158
             if proposals is None:
-                proposals = dict(mhs=DefaultProposalCycle)
+                proposals = defaults
             elif isinstance(proposals, list):
                 proposals = dict(mhs=proposals[0])
+            proposals = dict(defaults, **proposals)
             self.nlive = nlive
             self.poolsize = poolsize
             self.posterior_samples = None
@@ -85,11 +98,15 @@ class CPNest(object):
             # NestedSampler seeds numpy, then the proposal cycle is drawn (cpnest/cpnest.py:184-207)
             self.NS = NestedSampler(self.user, nlive=nlive, output=output, verbose=verbose, seed=self.seed,
                                     prior_sampling=self.prior_sampling)
-            self.proposal = proposals["mhs"]()
             functor, params = self.user.get_device_functor()
             self.engine = Engine(functor, self.user.bounds, nlive=nlive, maxmcmc=maxmcmc, seed=self.seed, params=params,
-                                 device=device, lanes=lanes, rho_target=rho_target)
-            self.engine.set_cycle(self.proposal.device_cycle())
+                                 device=device, lanes=lanes, rho_target=rho_target, sampler=self.sampler_kind)
+            if self.sampler_kind == "slice":
+                self.proposal = proposals["sli"](model=self.user)        # cpnest/cpnest.py:252
+                self.engine.set_slice_cycle(self.proposal.device_cycle())
+            else:
+                self.proposal = proposals["mhs"]()                       # cpnest/cpnest.py:207
+                self.engine.set_cycle(self.proposal.device_cycle())
             if check_functor:
                 self._check_functor()
 

@@ -6,7 +6,7 @@ to the device as one proposal id per cycle slot.
 """
 import numpy as np
 
-from ._lib import DE, EIGEN, STRETCH, WALK
+from ._lib import DE, EIGEN, SLICE_CORR, SLICE_DIFF, SLICE_GAUSS, STRETCH, WALK
 
 
 class Proposal(object):
@@ -104,11 +104,47 @@ class DefaultProposalCycle(ProposalCycle):
         super(DefaultProposalCycle, self).__init__(proposals, [5, 5, 10, 10])
 
 
+class EnsembleSlice(EnsembleProposal):
+    """Direction proposals of the ensemble slice sampler (cpnest/proposal.py:114-119); the directions are
+    drawn inside the CUDA slice kernel (csrc/slice_kernel.cuh)."""
+    log_J = 0.0
+
+    def get_direction(self, mu=1.0):
+        raise NotImplementedError("%s.get_direction: slice directions are drawn inside the CUDA slice kernel" % type(self).__name__)
+
+
+class EnsembleSliceDifferential(EnsembleSlice):
+    """Difference of two ensemble members times mu (cpnest/proposal.py:121-133)."""
+    device_id = SLICE_DIFF
+
+
+class EnsembleSliceGaussian(EnsembleSlice):
+    """Isotropic unit direction times mu (cpnest/proposal.py:175-187)."""
+    device_id = SLICE_GAUSS
+
+
+class EnsembleSliceCorrelatedGaussian(EnsembleSlice):
+    """mu * N(mean, cov) of the ensemble (cpnest/proposal.py:135-173)."""
+    device_id = SLICE_CORR
+
+
 class EnsembleSliceProposalCycle(ProposalCycle):
-    """cpnest/proposal.py:189-207.  The slice sampler has no device kernel yet."""
+    """Differential : Gaussian : CorrelatedGaussian = 1 : 1 : 1 (cpnest/proposal.py:189-207)."""
 
     def __init__(self, model=None):
-        raise NotImplementedError("the ensemble slice sampler (nslice > 0) is not implemented on the device yet")
+        proposals = [EnsembleSliceDifferential(), EnsembleSliceGaussian(), EnsembleSliceCorrelatedGaussian()]
+        super(EnsembleSliceProposalCycle, self).__init__(proposals, [1, 1, 1])
+
+    def get_direction(self, mu=1.0, **kwargs):
+        raise NotImplementedError("slice directions are drawn inside the CUDA slice kernel")
+
+    def device_cycle(self):
+        ids = []
+        for p in self.cycle:
+            if not isinstance(p, EnsembleSlice) or getattr(p, "device_id", None) is None:
+                raise NotImplementedError("slice direction %s has no device implementation" % type(p).__name__)
+            ids.append(p.device_id)
+        return np.array(ids, dtype=np.uint8)
 
 
 class HamiltonianProposalCycle(ProposalCycle):

@@ -100,5 +100,24 @@ def test_functor_mismatch_and_unsupported_samplers_fail_loudly(tmp_path):
             return 2.0 * M.GaussianModel.log_likelihood(self, p)
     with pytest.raises(ValueError, match="disagrees"):
         cpnest.CPNest(Wrong(2), output=str(tmp_path), nlive=100)
-    with pytest.raises(NotImplementedError):
-        cpnest.CPNest(M.GaussianModel(2), output=str(tmp_path), nlive=100, nslice=1)
+    with pytest.raises(NotImplementedError, match="single sampler kind"):
+        cpnest.CPNest(M.GaussianModel(2), output=str(tmp_path), nlive=100, nthreads=4, nslice=1)   # mixed population
+
+
+def test_2d_slice_like_reference_test(tmp_path):
+    # tests/test_2d_slice.py:30: CPNest(model, verbose=2, nthreads=1, nslice=1, nlive=1000, maxmcmc=5000, poolsize=1000)
+    import cpnest_b200.models as M
+    model = M.GaussianModel(2)
+    work = _run(model, tmp_path, verbose=1, nthreads=1, nslice=1, nlive=1000, maxmcmc=5000, poolsize=1000)
+    assert work.sampler_kind == "slice"
+    assert np.abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * np.sqrt(work.NS.state.info / work.NS.Nlive)
+    pos = work.posterior_samples
+    assert abs(pos["x"].mean()) < 0.2 and abs(pos["x"].std() - 1.0) < 0.2
+
+
+def test_ring_slice_like_reference_test(tmp_path):
+    # tests/test_ring_slice.py:31: nthreads=4, nslice=4, nlive=1000, maxmcmc=1000
+    import cpnest_b200.models as M
+    model = M.RingModel()
+    work = _run(model, tmp_path, verbose=0, nthreads=4, nslice=4, nlive=1000, maxmcmc=1000, poolsize=1000)
+    assert np.abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * np.sqrt(work.NS.state.info / work.NS.Nlive)
