@@ -224,7 +224,9 @@ static void init_state(cpn_ctx* c, NSState* s) {
     s->nmcmc_tau = (double)c->N / s->nmcmc_safety;        // tau = poolsize / safety (sampler.py:166)
     s->maxmcmc = c->cfg.maxmcmc;
     s->adapt = c->cfg.adapt_nmcmc;
-    s->rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : 0.1;
+    // measured on the 50-D Gaussian (nlive 1e4, 8 seeds each): MH chains are unbiased at 0.1; slice chains show
+    // +1.0 sigma (+0.09 nats) mean deviation of logZ at 0.1 and none at 0.05
+    s->rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : (c->cfg.sampler == CPN_SAMPLER_SLICE ? 0.05 : 0.1);
     s->rho_max = -1.0;
     s->slice_mu = 1.0;                                    // SliceSampler.reset (sampler.py:422)
     s->hmc_dt = 0.0;

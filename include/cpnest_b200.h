@@ -72,7 +72,7 @@ typedef struct cpn_config {
     int32_t world_size;    /* number of ranks sharing the live set (1 = single GPU) */
     int32_t rank;
     int32_t sampler;       /* enum cpn_sampler */
-    double rho_target;     /* chain-length control: start/end correlation to reach; <=0: 0.1 */
+    double rho_target;     /* chain-length control: start/end correlation to reach; <=0: 0.1 (MH), 0.05 (slice) */
 } cpn_config;
 
 /* NestedSampler / _NSintegralState observable state (cpnest/NestedSampling.py:88-144, 254-262) */

@@ -455,6 +455,107 @@ def slice_chain(model, pool, pool_logL, pool_logP, cycle, cycle_idx, mu, tape, N
 
 
 # ----------------------------------------------------------------------------------------
+# HamiltonianMonteCarloSampler.yield_sample (cpnest/sampler.py:360-402) driving
+# ConstrainedLeapFrog (cpnest/proposal.py:377-844)
+# ----------------------------------------------------------------------------------------
+def hmc_set_integration_parameters(bounds):
+    """proposal.py:524-536 -> (base_L, base_dt)"""
+    ranges = [b[1] - b[0] for b in bounds]
+    d = len(bounds)
+    l, h = np.min(ranges), np.max(ranges)
+    base_L = 10 + int((h / l) * d ** (1. / 4.))
+    base_dt = (1.0 / base_L) * l / h
+    return base_L, base_dt
+
+
+def hmc_kinetic_energy(p, C, logdet):
+    """proposal.py:562-575: 0.5 p.C.p - logdet(M) - d/2 log 2pi, C = ensemble covariance = inverse mass matrix"""
+    return 0.5 * np.dot(p, np.dot(C, p)) - logdet - 0.5 * len(p) * np.log(2.0 * np.pi)
+
+
+def hmc_trajectory(model, grad_V, q0, p0, C, inverse_mass, logdet, dt, L, logLmin, tp):
+    """ConstrainedLeapFrog.evolve_trajectory + sample_trajectory (proposal.py:793-844).  `grad_V(x)` is
+    Model.force (the gradient of the potential -log_prior); the unit normals used at reflections off
+    the likelihood boundary are taken from the tape (the reference estimates them with per-dimension
+    spline fits over the ensemble, proposal.py:417-486).  Returns (q, p, logL, logP) of the picked point."""
+    lo, hi = model.lo, model.hi
+    D = len(q0)
+    traj = [(np.array(q0), np.array(p0), None, None)]
+
+    def position(p, q):                                                   # :729-741
+        for j in range(D):
+            q[j] += dt * p[j] * inverse_mass[j]
+            while q[j] < lo[j] or q[j] > hi[j]:
+                if q[j] > hi[j]:
+                    q[j] = hi[j] - (q[j] - hi[j])
+                    p[j] *= -1
+                if q[j] < lo[j]:
+                    q[j] = lo[j] + (lo[j] - q[j])
+                    p[j] *= -1
+
+    def momentum(p, q):                                                   # :760-773
+        dV = grad_V(q)
+        logP = model.log_prior(q)                                         # check_constraint :790-791
+        logL = model.log_likelihood(q)
+        if logL - logLmin > 0:
+            p += -dt * dV
+        else:
+            normal = np.array(tp.take("normal"))
+            p += -2.0 * np.dot(p, normal) * normal
+        return logL, logP
+
+    for sign in (1.0, -1.0):
+        p = sign * np.array(p0, dtype=np.float64)
+        q = np.array(q0, dtype=np.float64)
+        p += -0.5 * dt * grad_V(q)                                        # half step :757-759
+        for _ in range(L):
+            position(p, q)
+            logL, logP = momentum(p, q)
+            traj.append((q.copy(), p.copy(), logL, logP))
+    # (the closing half step of :829 changes p only; the last point is excluded from the draw below)
+    with np.errstate(all="ignore"):
+        logw = np.array([-(hmc_kinetic_energy(pp, C, logdet) - model.log_prior(qq)) for qq, pp, _, _ in traj[1:-1]])
+        m = np.max(logw)
+        norm = m + np.log(np.sum(np.exp(logw - m)))                       # scipy logsumexp
+        prob = np.exp(logw - norm)
+    u = tp.take("choice_u")
+    cdf = np.cumsum(prob)
+    cdf /= cdf[-1]
+    idx = 1 + int(cdf.searchsorted(u, side="right"))                      # np.random.choice(range(1, n-1), p=prob)
+    assert idx == tp.take("choice_idx")
+    return traj[idx]
+
+
+def hmc_chain(model, grad_V, start, start_logL, start_logP, C, inverse_mass, logdet, dt, L, logLmin, tape,
+              max_trajectories=10**9):
+    """One `next(yield_sample(logLmin))` of the reference's HMC sampler: trajectories from `start` until
+    one is accepted (sampler.py:375-385).  Returns dict(out, logL, logP, steps, log_J, evals)."""
+    tp = tape if isinstance(tape, TapeReader) else TapeReader(tape)
+    q0 = np.array(start, dtype=np.float64)
+    steps = 0
+    while True:
+        steps += 1
+        p0 = np.array(tp.take("p0"), dtype=np.float64)
+        E0 = hmc_kinetic_energy(p0, C, logdet) - model.log_prior(q0)      # hamiltonian(p0, q0) :621
+        q, p, logL, logP = hmc_trajectory(model, grad_V, q0, p0, C, inverse_mass, logdet, dt, L, logLmin, tp)
+        E1 = hmc_kinetic_energy(p, C, logdet) - model.log_prior(q)        # :625
+        with np.errstate(all="ignore"):
+            log_J = min(0.0, E0 - E1)                                     # :626
+        u = tp.take("random")
+        if log_J > (math.log(u) if u > 0 else -np.inf):                   # sampler.py:380
+            if logL > logLmin:                                            # :382
+                return dict(out=q, logL=logL, logP=logP, steps=steps, log_J=log_J, evals=2 * L * steps)
+        if steps >= max_trajectories:
+            return dict(out=q0, logL=start_logL, logP=start_logP, steps=steps, log_J=log_J, evals=2 * L * steps)
+
+
+def hmc_update_time_step(scale, acceptance, base_dt, target=0.5, adaptation=0.001):
+    """proposal.py:539-550 -> (scale, dt)"""
+    scale = float(np.exp(np.log(scale) + adaptation * (acceptance - target)))
+    return scale, base_dt * scale
+
+
+# ----------------------------------------------------------------------------------------
 # Evidence integrator (cpnest/NestedSampling.py:88-144) and helpers (cpnest/nest2pos.py:17-42)
 # ----------------------------------------------------------------------------------------
 def logsubexp(x, y):

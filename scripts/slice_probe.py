@@ -9,8 +9,10 @@ N = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 2500
 sampler = sys.argv[5] if len(sys.argv) > 5 else "slice"
 lanes = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+seed = int(sys.argv[7]) if len(sys.argv) > 7 else 1234
+rho = float(sys.argv[8]) if len(sys.argv) > 8 else 0.0
 b = 10.0 if which == "gaussian_iid" else 5.0
-e = Engine(which, [[-b, b]] * D, nlive=N, maxmcmc=5000, seed=1234, sampler=sampler, lanes=lanes)
+e = Engine(which, [[-b, b]] * D, nlive=N, maxmcmc=5000, seed=seed, sampler=sampler, lanes=lanes, rho_target=rho)
 e.init_prior()
 e.synchronize()
 t0 = time.time()

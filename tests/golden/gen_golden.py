@@ -533,6 +533,129 @@ def gen_slice_chain():
 
 
 # --------------------------------------------------------------------------------------
+# I. HamiltonianMonteCarloSampler.yield_sample + ConstrainedLeapFrog traces
+#    (cpnest/sampler.py:360-402, cpnest/proposal.py:377-844)
+# --------------------------------------------------------------------------------------
+class _NpRandomTapeHMC(_NpRandomTape):
+    def choice(self, a, size=None, replace=True, p=None):
+        """np.random.choice(range, p=p) as the legacy RandomState does it (one uniform, searchsorted on the
+        normalised cumulative sum); the uniform is recorded so that the selection can be replayed."""
+        if p is None or size is not None:
+            return np.random.choice(a, size=size, replace=replace, p=p)
+        a = list(a)
+        u = self.rs.random_sample()
+        cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+        cdf /= cdf[-1]
+        k = int(cdf.searchsorted(u, side="right"))
+        self.tape.events.append(["choice_u", float(u)])
+        self.tape.events.append(["choice_idx", int(a[k])])
+        return a[k]
+
+    def randint(self, low, high=None, size=None):
+        v = self.rs.randint(low, high, size)
+        self.tape.events.append(["randint", int(v)])
+        return v
+
+
+class _RecordingMomenta:
+    def __init__(self, dist, tape, rs):
+        self.dist, self.tape, self.rs = dist, tape, rs
+
+    def rvs(self):
+        v = np.atleast_1d(self.dist.rvs(random_state=self.rs))
+        self.tape.events.append(["p0", v.tolist()])
+        return v
+
+
+def gen_hmc_chain():
+    models = reference_models()
+
+    class MeanSigmaWithForce(type(models["gaussian_mean_sigma"])):
+        # tests/test_gaussian.py defines no force; the analytic gradient of the potential -log_prior = log(sigma) + const
+        def force(self, p):
+            f = np.zeros(1, dtype={"names": p.names, "formats": ["f8" for _ in p.names]})
+            f["sigma"] = 1.0 / p["sigma"]
+            return f
+
+    t2h = _load_module(os.path.join(REFROOT, "tests/test_2d_hmc.py"), "ref_test_2d_hmc")
+    models = dict(models, gaussian2d=t2h.GaussianModel(), gaussian_mean_sigma=MeanSigmaWithForce())
+    out = []
+    specs = [
+        # (model, poolsize, Nmcmc, nchains, logLmin quantile, scale of pool)
+        ("gaussian2d", 64, 3, 4, 0.3, 3.0),
+        ("gaussian_mean_sigma", 64, 3, 4, 0.3, None),
+        ("gaussian10d", 96, 2, 3, 0.2, 1.5),
+        ("rosenbrock2d", 64, 3, 3, 0.4, 1.0),
+        ("gaussian2d", 64, 2, 3, 0.9, 3.0),          # tight constraint: many reflections, rejected trajectories
+    ]
+    real_np_samp, real_np_prop = rsamp.np, rprop.np
+    for si, (mname, P, Nmcmc, nchains, q, scale) in enumerate(specs):
+        model = models[mname]
+        D = len(model.names)
+        rs = np.random.RandomState(500 + si)
+        lo = np.array([b[0] for b in model.bounds], dtype=float)
+        hi = np.array([b[1] for b in model.bounds], dtype=float)
+        if scale is None:
+            X = lo + (hi - lo) * rs.uniform(size=(P, D))
+        else:
+            X = np.clip(rs.normal(size=(P, D)) * scale, lo + 1e-3, hi - 1e-3)
+        pts = make_points(model.names, X)
+        for p in pts:
+            p.logP = float(model.log_prior(p))
+            p.logL = float(np.asarray(model.log_likelihood(p)).reshape(-1)[0])
+        logLs = np.array([p.logL for p in pts])
+        logLmin = float(np.quantile(logLs, q))
+        # the chains start from pool members above the threshold (the reference pops the right end of the deque)
+        order = np.argsort(logLs)
+        pts = [pts[i] for i in order]
+        X, logLs = X[order], logLs[order]
+        np.random.seed(2468 + si)
+        cycle = rprop.HamiltonianProposalCycle(model=model)
+        prop = cycle.proposals[0]
+        tape = Tape(11000 + si)
+        install_tape(tape)
+        rnd = _NpRandomTapeHMC(tape, 12000 + si)
+        rsamp.np = _NpShim(rnd)
+        rprop.np = _NpShim(rnd)
+        try:
+            mgr = _FakeManager()
+            smp = rsamp.HamiltonianMonteCarloSampler(model, 100, seed=1, poolsize=P, proposal=cycle, manager=mgr)
+            smp.Nmcmc = Nmcmc
+            for p in pts:
+                smp.evolution_points.append(p)
+            cycle.set_ensemble(smp.evolution_points)
+            prop.momenta_distribution = _RecordingMomenta(prop.momenta_distribution, tape, rnd.rs)
+            real_normal = prop.unit_normal
+
+            def rec_normal(qq, _f=real_normal):
+                n = _f(qq)
+                tape.events.append(["normal", np.asarray(n, dtype=float).tolist()])
+                return n
+            prop.unit_normal = rec_normal
+            case = dict(model=mname, D=D, P=P, Nmcmc=Nmcmc, logLmin=logLmin,
+                        pool=X.tolist(), pool_logL=logLs.tolist(), pool_logP=[p.logP for p in pts],
+                        covariance=np.atleast_2d(prop.covariance).tolist(),
+                        inverse_mass=np.atleast_1d(prop.inverse_mass).tolist(),
+                        logdeterminant=fl(prop.logdeterminant), base_dt=fl(prop.base_dt), base_L=int(prop.base_L),
+                        chains=[])
+            gen = smp.yield_sample(logLmin)
+            for c in range(nchains):
+                tape.events = []
+                dt0, L0, scale0 = fl(prop.dt), int(prop.L), fl(prop.scale)
+                start = smp.evolution_points[-1]
+                steps, outp = next(gen)
+                case["chains"].append(dict(dt=dt0, L=L0, scale=scale0, start=list(start.values), start_logL=fl(start.logL),
+                                           start_logP=fl(start.logP), tape=tape.events, steps=steps,
+                                           out=list(outp.values), out_logL=fl(outp.logL), out_logP=fl(outp.logP),
+                                           log_J=fl(prop.log_J), acceptance=fl(smp.acceptance),
+                                           dt_after=fl(prop.dt), L_after=int(prop.L), scale_after=fl(prop.scale)))
+        finally:
+            rsamp.np, rprop.np = real_np_samp, real_np_prop
+        out.append(case)
+    dump("hmc_chain.json", out)
+
+
+# --------------------------------------------------------------------------------------
 # G. NestedSampler.consume_sample / final sweep with scripted samplers
 #    (cpnest/NestedSampling.py:318-375, 433-493)
 # --------------------------------------------------------------------------------------
@@ -618,6 +741,6 @@ def gen_ns_loop(tmpdir="/tmp/cpnest_golden_ns"):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["integrator", "nest2pos", "proposals", "cycle", "models", "mh_chain", "slice_chain", "ns_loop"]
+    which = sys.argv[1:] or ["integrator", "nest2pos", "proposals", "cycle", "models", "mh_chain", "slice_chain", "hmc_chain", "ns_loop"]
     for w in which:
         globals()["gen_" + w]()

@@ -191,6 +191,44 @@ def test_slice_chain_golden(golden):
     assert nchains >= 20
 
 
+def _grad_V(name):
+    """Model.force of the fixture models: the gradient of the potential -log_prior."""
+    if name == "gaussian_mean_sigma":
+        return lambda x: np.array([0.0, 1.0 / x[1]])
+    return lambda x: np.zeros(len(x))
+
+
+def test_hmc_chain_golden(golden):
+    """HamiltonianMonteCarloSampler.yield_sample + ConstrainedLeapFrog (sampler.py:365-402, proposal.py:793-844)
+    from the reference's recorded momenta, reflection normals and uniforms."""
+    mg = golden("models.json")
+    nchains = 0
+    for case in golden("hmc_chain.json"):
+        m = _model_for(case["model"], mg[case["model"]])
+        assert O.hmc_set_integration_parameters(m.bounds) == (case["base_L"], case["base_dt"])
+        C = np.array(case["covariance"])
+        cov = O.ensemble_covariance(np.array(case["pool"]))[1]
+        assert close(C, cov, 1e-13, 1e-15)
+        assert close(-np.linalg.slogdet(C)[1], case["logdeterminant"], 1e-11)
+        accepted = counter = 0
+        for ch in case["chains"]:
+            tp = O.TapeReader(ch["tape"])
+            r = O.hmc_chain(m, _grad_V(case["model"]), ch["start"], ch["start_logL"], ch["start_logP"], C,
+                            np.array(case["inverse_mass"]), case["logdeterminant"], ch["dt"], ch["L"], case["logLmin"], tp)
+            assert r["steps"] == ch["steps"], case["model"]
+            assert close(r["out"], ch["out"], 1e-12), case["model"]
+            assert close(r["logL"], ch["out_logL"], 1e-12) and close(r["logP"], ch["out_logP"], 1e-12)
+            assert close(r["log_J"], ch["log_J"], 1e-9, 1e-12)
+            accepted += 1
+            counter += r["steps"]
+            assert close(accepted / counter, ch["acceptance"], 1e-15)
+            scale, dt = O.hmc_update_time_step(ch["scale"], ch["acceptance"], case["base_dt"])
+            assert close(scale, ch["scale_after"], 1e-15) and close(dt, ch["dt_after"], 1e-15)
+            assert tp.take("randint") + case["base_L"] == ch["L_after"] and tp.exhausted()
+            nchains += 1
+    assert nchains >= 17
+
+
 def test_ns_loop_golden(golden):
     for case in golden("ns_loop.json"):
         ns = O.NSLoopOracle(case["L0"], mode="reference")
