@@ -92,10 +92,13 @@ SIGNATURES = {
     "cpn_set_stream": (C.c_int, [_vp, _vp]),
     "cpn_launch_count": (C.c_int64, [_vp]),
     "cpn_eval_model": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
+    "cpn_eval_gradients": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "cpn_replay_mh": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32,
                                 C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _dp]),
     "cpn_replay_slice": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, C.c_int32, _dp, _P(C.c_int64), C.c_double,
                                    C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _ip, _dp]),
+    "cpn_replay_hmc": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.c_double, _dp, _P(C.c_int64), C.c_double, C.c_int32, C.c_int32,
+                                 C.c_double, C.c_int32, _dp, _ip, _ip, _ip, _dp]),
     "cpn_slice_directions": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, _dp]),
     "cpn_stage_replacements": (C.c_int, [_vp, C.c_int32, _dp]),
     "cpn_ns_reset": (C.c_int, [_vp]),

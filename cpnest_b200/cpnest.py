@@ -39,8 +39,10 @@ class CPNest(object):
                 context runs ONE kind per run: nslice == nthreads (as in the reference's own tests and examples,
                 tests/test_2d_slice.py:30, examples/test_50d.py:37) selects the slice kernel, a mixed
                 population raises NotImplementedError
-    nhamiltonian : no device kernel yet -> NotImplementedError if > 0
-    proposals : dict(mhs=ProposalCycle subclass, sli=EnsembleSliceProposalCycle subclass); device proposals only
+    nhamiltonian : number of HMC samplers; nhamiltonian == nthreads selects the constrained-leapfrog kernel
+                (tests/test_2d_hmc.py:30).  The reflection normal is the functor's analytic gradient
+    proposals : dict(mhs=ProposalCycle subclass, sli=EnsembleSliceProposalCycle subclass, hmc=HamiltonianProposalCycle
+                subclass); device proposals only
     prior_sampling : produce nlive samples from the prior and stop
 
     Device-only keywords: device (CUDA ordinal), batch (chains per kernel launch, default
@@ -68,14 +70,12 @@ class CPNest(object):
                     "use nslice == nthreads (or nhamiltonian == nthreads) for a pure population".format(
                         self.nthreads, nslice, nhamiltonian))
             self.sampler_kind = kinds[0]
-            if self.sampler_kind == "hmc":
-                raise NotImplementedError("nhamiltonian > 0: the Hamiltonian sampler has no device kernel yet")
             if resume:
                 self.logger.critical("resume=True: checkpoint/resume is not implemented on the device yet; starting fresh")
             if n_periodic_checkpoint is not None:
                 self.logger.critical("The n_periodic_checkpoint kwarg is deprecated, use periodic_checkpoint_interval instead.")
-            from .proposal import DefaultProposalCycle, EnsembleSliceProposalCycle
-            defaults = dict(mhs=DefaultProposalCycle, sli=EnsembleSliceProposalCycle)     # cpnest/cpnest.py:155-158
+            from .proposal import DefaultProposalCycle, EnsembleSliceProposalCycle, HamiltonianProposalCycle
+            defaults = dict(mhs=DefaultProposalCycle, sli=EnsembleSliceProposalCycle, hmc=HamiltonianProposalCycle)   # cpnest/cpnest.py:155-158
             if proposals is None:
                 proposals = defaults
             elif isinstance(proposals, list):
@@ -104,6 +104,12 @@ class CPNest(object):
             if self.sampler_kind == "slice":
                 self.proposal = proposals["sli"](model=self.user)        # cpnest/cpnest.py:252
                 self.engine.set_slice_cycle(self.proposal.device_cycle())
+            elif self.sampler_kind == "hmc":
+                self.proposal = proposals["hmc"](model=self.user)        # cpnest/cpnest.py:231
+                self.proposal.device_cycle()
+                if functor in ("gaussian_mean_sigma", "gaussian_mixture"):
+                    self.logger.warning("HMC with a non-flat prior inherits the reference's trajectory-draw + energy-test rule, "
+                                        "which is not exactly reversible when the potential varies (DESIGN.md); prefer MH or slice")
             else:
                 self.proposal = proposals["mhs"]()                       # cpnest/cpnest.py:207
                 self.engine.set_cycle(self.proposal.device_cycle())

@@ -18,6 +18,7 @@
 #include "launch.h"
 #include "mh_kernel.cuh"
 #include "ns_kernels.cuh"
+#include "hmc_kernel.cuh"
 #include "slice_kernel.cuh"
 
 using namespace cpn;
@@ -42,6 +43,10 @@ static int fail(const char* fmt, ...) {
 typedef int (*mh_fn)(int, int, int, const MHParams&, cudaStream_t);
 typedef int (*eval_fn)(int, int, const EvalParams&, cudaStream_t);
 typedef int (*slice_fn)(int, int, int, const SliceParams&, cudaStream_t);
+typedef int (*hmc_fn)(int, int, int, const HMCParams&, cudaStream_t);
+static const hmc_fn kHMC[CPN_NUM_FUNCTORS] = {launch_hmc_gauss_iid, launch_hmc_gauss_corr, launch_hmc_eggbox,
+                                              launch_hmc_rosenbrock, launch_hmc_ackley, launch_hmc_ring,
+                                              launch_hmc_gauss_mean_sigma, launch_hmc_gauss_mixture};
 static const slice_fn kSlice[CPN_NUM_FUNCTORS] = {launch_slice_gauss_iid, launch_slice_gauss_corr, launch_slice_eggbox,
                                                   launch_slice_rosenbrock, launch_slice_ackley, launch_slice_ring,
                                                   launch_slice_gauss_mean_sigma, launch_slice_gauss_mixture};
@@ -80,7 +85,9 @@ struct cpn_ctx {
     double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
     // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
     // side stream concurrently with the chain kernel, writes the other one
-    double *d_eigval[2], *d_eigvec[2], *d_eigscale[2], *d_eigmean[2];
+    double *d_eigval[2], *d_eigvec[2], *d_eigscale[2], *d_eigmean[2], *d_covbuf[2];
+    int hmc_base_L;             // HamiltonianProposal.set_integration_parameters (proposal.py:524-536)
+    double hmc_base_dt;
     int eig_cur;
     bool eig_pending, wait_cov;
     int eig_pending_age;        // batches started since the pending refresh was launched
@@ -229,7 +236,8 @@ static void init_state(cpn_ctx* c, NSState* s) {
     s->rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : (c->cfg.sampler == CPN_SAMPLER_SLICE ? 0.05 : 0.1);
     s->rho_max = -1.0;
     s->slice_mu = 1.0;                                    // SliceSampler.reset (sampler.py:422)
-    s->hmc_dt = 0.0;
+    s->hmc_dt = c->hmc_base_dt;                           // dt = base_dt * scale, scale = 1 (proposal.py:395-396, 550)
+    s->sampler = c->cfg.sampler;
 }
 
 static size_t stage_off(int N, int Dp, int which) {
@@ -350,7 +358,8 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
         dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigvec[0], (size_t)D * Dp) || dalloc(&c->d_eigscale[0], D) ||
         dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp) || dalloc(&c->d_eigscale[1], D) ||
-        dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
+        dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) ||
+        dalloc(&c->d_covbuf[0], (size_t)D * D) || dalloc(&c->d_covbuf[1], (size_t)D * D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
         dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))
         return 1;
     if (dalloc(&c->d_state, 1) || dalloc(&c->d_trap_partial, 256) || dalloc(&c->d_scalar, 4) ||
@@ -375,6 +384,13 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         if (dalloc(&c->d_slice_cycle, 4096)) return 1;
         CK(cudaMemcpy(c->d_slice_cycle, cyc.data(), cyc.size(), cudaMemcpyHostToDevice));
     }
+    {
+        // base_L = 10 + int((h/l) d^(1/4)), base_dt = (1/base_L) l/h with l, h the shortest and longest prior range
+        double l = INFINITY, h = 0.0;
+        for (int d = 0; d < D; ++d) { l = std::min(l, hi[d] - lo[d]); h = std::max(h, hi[d] - lo[d]); }
+        c->hmc_base_L = 10 + (int)((h / l) * std::pow((double)D, 0.25));
+        c->hmc_base_dt = (1.0 / c->hmc_base_L) * l / h;
+    }
     init_state(c, c->h_state);
     if (push_state(c)) return 1;
     // Dead-point log: a run produces about nlive * (H + a few sqrt(H)) dead points; HBM is plentiful
@@ -398,7 +414,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
-                    c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_state, c->d_dead_x, c->d_dead_logL,
+                    c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -464,6 +480,7 @@ static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events
     k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), st>>>(
         c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
     k_cov_final<<<(D * D + 127) / 128, 128, 0, st>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
+    CK(cudaMemcpyAsync(c->d_covbuf[buf], c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (record_events) CK(cudaEventRecord(c->ev_cov, st));     // the live rows have been read
     const size_t sm = 4 * (size_t)D * (D | 1) * sizeof(double);
     const int use_smem = sm <= 200 * 1024;
@@ -598,6 +615,35 @@ static void fill_slice(cpn_ctx* c, SliceParams* p) {
     }
 }
 
+static void fill_hmc(cpn_ctx* c, HMCParams* p) {
+    memset(p, 0, sizeof *p);
+    p->ens_x = c->d_x; p->ens_logL = c->d_logL; p->ens_logP = c->d_logP;
+    p->ens_n = c->N; p->Dp = c->Dp; p->D = c->D;
+    p->order = c->d_order[c->cur];
+    p->lo = c->d_lo; p->hi = c->d_hi;
+    p->cov = c->d_covbuf[c->eig_cur]; p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
+    p->state = c->d_state;
+    p->base_L = c->hmc_base_L;
+    p->max_traj = c->cfg.maxmcmc;
+    p->chain_base = c->chain_counter;
+    p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
+    p->blob = c->d_blob;
+    const int nout = c->n_peers > 0 ? c->n_peers : 1;
+    p->n_out = nout;
+    for (int o = 0; o < nout; ++o) {
+        const int r = (o == 0) ? c->rank : (o <= c->rank ? o - 1 : o);
+        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp)
+                                   : (char*)c->d_stage_own;
+        p->out_x[o] = (double*)(b + stage_off(c->N, c->Dp, 0));
+        p->out_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 1));
+        p->out_logP[o] = (double*)(b + stage_off(c->N, c->Dp, 2));
+        p->out_steps[o] = (int*)(b + stage_off(c->N, c->Dp, 3));
+        p->out_acc[o] = (int*)(b + stage_off(c->N, c->Dp, 4));
+        p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
+        p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
+    }
+}
+
 // chains [j0, j1) of a batch with the context's sampler; START_SURVIVOR unless start rows are given
 static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int n_skip, bool use_override, double logLmin,
                          int nmcmc, int n_out_override) {
@@ -623,7 +669,16 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
         if (n_out_override > 0) p.n_out = n_out_override;
         if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
     } else {
-        return fail("sampler %d is not available on the device yet", c->cfg.sampler);
+        HMCParams p;
+        fill_hmc(c, &p);
+        p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
+        p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+        if (use_override) {
+            if (fetch_state(c)) return 1;
+            p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.dt_override = c->h_state->hmc_dt;
+        }
+        if (n_out_override > 0) p.n_out = n_out_override;
+        if (kHMC[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no HMC kernel for G=%d E=%d", G, E);
     }
     CKL();
     return 0;
@@ -843,6 +898,9 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         c->launches += 1;
         if (c->cfg.sampler == CPN_SAMPLER_SLICE) {
             k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_ne, c->d_new_nc);
+            c->launches += 1;
+        } else if (c->cfg.sampler == CPN_SAMPLER_HMC) {
+            k_adapt_hmc_dt<<<1, 1, 0, c->stream>>>(c->d_state);
             c->launches += 1;
         }
     }
@@ -1160,6 +1218,35 @@ extern "C" int cpn_eval_model(cpn_ctx* c, const double* x, int32_t n, double* lo
     return 0;
 }
 
+extern "C" int cpn_eval_gradients(cpn_ctx* c, const double* x, int32_t n, double* grad_logL, double* grad_V) {
+    if (!c || !x || !grad_logL || !grad_V || n < 1) return fail("bad argument");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    std::vector<double> xp((size_t)n * Dp, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < D; ++d) xp[(size_t)i * Dp + d] = x[(size_t)i * D + d];
+    double *dx, *dl, *dp, *dgl, *dgv;
+    if (dalloc(&dx, xp.size()) || dalloc(&dl, n) || dalloc(&dp, n) || dalloc(&dgl, xp.size()) || dalloc(&dgv, xp.size())) return 1;
+    CK(cudaMemcpy(dx, xp.data(), xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    EvalParams e;
+    memset(&e, 0, sizeof e);
+    e.x = dx; e.logL = dl; e.logP = dp; e.n = n; e.D = D; e.Dp = Dp; e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob;
+    e.grad_logL = dgl; e.grad_V = dgv;
+    if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<double> a(xp.size()), b(xp.size());
+    CK(cudaMemcpy(a.data(), dgl, a.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), dgv, b.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < D; ++d) {
+            grad_logL[(size_t)i * D + d] = a[(size_t)i * Dp + d];
+            grad_V[(size_t)i * D + d] = b[(size_t)i * Dp + d];
+        }
+    cudaFree(dx); cudaFree(dl); cudaFree(dp); cudaFree(dgl); cudaFree(dgv);
+    return 0;
+}
+
 extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start,
                              const double* eigval, const double* eigvec, int32_t cycle_idx, const double* tape,
                              int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes,
@@ -1294,6 +1381,71 @@ extern "C" int cpn_replay_slice(cpn_ctx* c, int32_t P, const double* ensemble, i
     if (evals) CK(cudaMemcpy(evals, dev, C * sizeof(int), cudaMemcpyDeviceToHost));
     if (last) CK(cudaMemcpy(last, dlast, (size_t)C * 4 * sizeof(double), cudaMemcpyDeviceToHost));
     void* fr[] = {dex, dsx, dsl, dsp, dtape, doff, dox, dol, dop, dst, dac, dev, dlast, dEL, dEP};
+    for (void* q : fr)
+        if (q) cudaFree(q);
+    return 0;
+}
+
+extern "C" int cpn_replay_hmc(cpn_ctx* c, int32_t C, const double* start, const double* cov, double logdet,
+                              const double* tape, const int64_t* tape_off, double dt, int32_t L, int32_t max_traj,
+                              double logLmin, int32_t lanes, double* out, int32_t* steps, int32_t* accepted, int32_t* evals,
+                              double* log_J) {
+    if (!c || !start || !cov || !tape || !tape_off || !out) return fail("null argument");
+    if (C < 1 || L < 1 || max_traj < 1) return fail("bad sizes");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    std::vector<double> sx((size_t)C * Dp, 0.0), sl(C), sp(C);
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) sx[(size_t)i * Dp + d] = start[(size_t)i * (D + 2) + d];
+        sl[i] = start[(size_t)i * (D + 2) + D];
+        sp[i] = start[(size_t)i * (D + 2) + D + 1];
+    }
+    const size_t ntape = (size_t)tape_off[C];
+    const size_t ntraj = (size_t)C * (2 * L + 1) * (Dp + 3);
+    double *dsx, *dsl, *dsp, *dcov, *dtape, *dtraj, *dox, *dol, *dop, *dlj;
+    long long* doff;
+    int *dst, *dac, *dev;
+    if (dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) || dalloc(&dcov, (size_t)D * D) || dalloc(&dtape, ntape + 8) ||
+        dalloc(&doff, C + 1) || dalloc(&dtraj, ntraj) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) ||
+        dalloc(&dst, C) || dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dlj, C))
+        return 1;
+    CK(cudaMemcpy(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsl, sl.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsp, sp.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dcov, cov, (size_t)D * D * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtape, tape, ntape * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(doff, tape_off, (C + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    HMCParams p;
+    memset(&p, 0, sizeof p);
+    p.ens_n = 0; p.Dp = Dp; p.D = D;
+    p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
+    p.lo = c->d_lo; p.hi = c->d_hi;
+    p.cov = dcov; p.logdet = logdet;
+    p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.dt_override = dt; p.L_override = L;
+    p.nmcmc_override = 1;
+    p.max_traj = max_traj; p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
+    p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
+    p.out_evals[0] = dev;
+    p.tape = dtape; p.tape_off = doff; p.traj = dtraj; p.logJ_out = dlj;
+    int G, E;
+    if (pick_config(D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) return 1;
+    if (kHMC[c->cfg.functor](G, E, 1, p, c->stream)) return fail("no HMC kernel for G=%d E=%d", G, E);
+    CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
+    CK(cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
+        out[(size_t)i * (D + 2) + D] = ol[i];
+        out[(size_t)i * (D + 2) + D + 1] = op[i];
+    }
+    if (steps) CK(cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (accepted) CK(cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (evals) CK(cudaMemcpy(evals, dev, C * sizeof(int), cudaMemcpyDeviceToHost));
+    if (log_J) CK(cudaMemcpy(log_J, dlj, C * sizeof(double), cudaMemcpyDeviceToHost));
+    void* fr[] = {dsx, dsl, dsp, dcov, dtape, doff, dtraj, dox, dol, dop, dst, dac, dev, dlj};
     for (void* q : fr)
         if (q) cudaFree(q);
     return 0;

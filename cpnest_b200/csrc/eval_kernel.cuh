@@ -17,6 +17,8 @@ struct EvalParams {
     const double* hi;
     const double* blob;
     int draw;          // 1: draw uniformly in the box until log_prior is finite (model.py:44-52)
+    double* grad_logL; // [n][Dp] or null: gradient of log_likelihood (reflection normal of the HMC kernel)
+    double* grad_V;    // [n][Dp] or null: Model.force, gradient of the potential -log_prior
     uint32_t seed_lo, seed_hi;
     unsigned long long id_base;
 };
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_points(const EvalParams p
     ModelCtx m;
     m.blob = p.blob;
     m.D = p.D;
-    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * p.Dp : nullptr;
+    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
     const int D = p.D;
     double x[E];
     double logP = CPN_NEG_INF;
@@ -84,6 +86,18 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_points(const EvalParams p
         logP = inb ? lp : CPN_NEG_INF;
     }
     const double logL = Model::template log_likelihood<G, E>(g, x, m);
+    if (p.grad_logL != nullptr) {
+        double gl[E], gv[E];
+        Model::template grad_log_likelihood<G, E>(g, x, m, gl);
+        Model::template grad_potential<G, E>(g, x, m, gv);
+        if (valid) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < D) { p.grad_logL[(size_t)c * p.Dp + d] = gl[e]; p.grad_V[(size_t)c * p.Dp + d] = gv[e]; }
+            }
+        }
+    }
     if (valid) {
         if (p.draw) {
 #pragma unroll

@@ -1,0 +1,397 @@
+// Constrained Hamiltonian Monte Carlo: the device form of
+//   HamiltonianMonteCarloSampler.yield_sample      cpnest/sampler.py:365-402
+//   LeapFrog.get_sample (energies, log_J)          cpnest/proposal.py:605-627
+//   ConstrainedLeapFrog.evolve_trajectory          cpnest/proposal.py:793-835
+//     .evolve_trajectory_one_step_position         cpnest/proposal.py:714-741  (bound reflection)
+//     .evolve_trajectory_one_step_momentum         cpnest/proposal.py:743-773  (reflection off logL = logLmin)
+//     .sample_trajectory                           cpnest/proposal.py:837-844  (point drawn with weight exp(-H))
+//   HamiltonianProposal.kinetic_energy / update_mass   cpnest/proposal.py:510-522, 562-575
+// A chain is owned by G lanes, E coordinates per lane (same layout as the MH kernel).  Momenta are drawn from
+// N(0, M), M = (ensemble covariance)^-1, through the eigen-decomposition the ensemble statistics already
+// provide: p0 = sum_i z_i |lambda_i|^-1/2 v_i.  The kinetic energy 0.5 p.C.p (D^2 work) is only re-evaluated
+// after the momentum changed (bound reflection, likelihood reflection, non-zero force).
+//
+// Chain length.  The reference returns after ONE accepted trajectory whose length follows the estimated
+// autocorrelation length, L = base_L + randint(Nmcmc, 5 Nmcmc) (sampler.py:375, proposal.py:553-559), and
+// relies on its noisy spline normals to break the regularity of the reflections.  With exact normals the
+// reflected motion inside a convex (e.g. spherical) constraint is an integrable billiard: a single trajectory,
+// however long, keeps its impact parameter, so the new point stays correlated with its start (measured:
+// start/end correlation 0.58 whatever L, logZ of the 10-D Gaussian +4 sigma).  The production kernel therefore
+// runs Nmcmc trajectories per chain, each with a fresh momentum and L = base_L + randint(10, 50) leapfrog
+// steps per direction, and stops with the MH rule (steps >= Nmcmc and accepted > 0, or steps >= maxmcmc,
+// sampler.py:347); Nmcmc is set by the same start/end-correlation controller as for the other samplers.
+// Replay reproduces the reference's rule (stop at the first accepted trajectory, L given).
+//
+// Production: the trajectory point is drawn in one pass by weighted reservoir sampling (same distribution as
+// the reference's multinomial draw over the stored trajectory, no trajectory storage); the reflection normal is
+// the analytic gradient of the functor's log_likelihood (the reference estimates it with per-dimension spline
+// fits over the ensemble, proposal.py:417-486).
+// Replay: momenta, reflection normals and uniforms come from a tape recorded from the reference; the
+// trajectory is stored and the point picked from the normalised cumulative weights as np.random.choice does.
+#pragma once
+#include <stdint.h>
+#include "group.cuh"
+#include "mh_kernel.cuh"
+#include "models.cuh"
+#include "rng.cuh"
+#include "state.cuh"
+#include "cpnest_b200.h"
+
+namespace cpn {
+
+struct HMCParams {
+    const double* ens_x;
+    const double* ens_logL;
+    const double* ens_logP;
+    int ens_n, Dp, D;
+    int start_mode;
+    const int* order;
+    int n_skip;
+    const double* start_x;
+    const double* start_logL;
+    const double* start_logP;
+    const double* lo;
+    const double* hi;
+    // ensemble statistics
+    const double* cov;        // [D][D] ensemble covariance = inverse mass matrix (proposal.py:516)
+    const double* eig_scale;  // [D] sqrt|lambda_i|
+    const double* eig_vec;    // [D][Dp]
+    double logdet;            // log det of the mass matrix (proposal.py:520); replay only (it cancels in every difference)
+    // chain control
+    const NSState* state;
+    int use_override;
+    double logLmin_override;
+    int nmcmc_override;       // trajectories per chain (1 in replay: the reference stops at the first accepted one)
+    double dt_override;
+    int L_override;           // > 0: trajectory length given (replay)
+    int base_L;
+    int max_traj;             // trajectories per chain at most (the reference loops until one is accepted)
+    int j0, j1;
+    unsigned long long chain_base;
+    uint32_t seed_lo, seed_hi;
+    const double* blob;
+    int n_out;
+    double* out_x[kMaxPeers];
+    double* out_logL[kMaxPeers];
+    double* out_logP[kMaxPeers];
+    int* out_steps[kMaxPeers];    // trajectories
+    int* out_acc[kMaxPeers];      // accepted trajectories (0 or 1)
+    int* out_start[kMaxPeers];
+    int* out_evals[kMaxPeers];
+    // replay: per chain a flat tape, per trajectory { p0[D], normal[D] per reflection in order, u of the draw, u of the test }
+    const double* tape;
+    const long long* tape_off;
+    double* traj;             // replay scratch [chains][2L+1][Dp + 3] = {q.., logL, logP, H}
+    double* logJ_out;         // [chains] log_J of the last trajectory, or null
+};
+
+template <int G, int E, class Model, bool REPLAY>
+__global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
+    if (!REPLAY && p.state != nullptr && p.state->done) return;
+    const Group<G> g;
+    const int cpb = kMHThreads / G;
+    const int nchains = p.j1 - p.j0;
+    int c = blockIdx.x * cpb + (int)threadIdx.x / G;
+    if ((c & ~(32 / G - 1)) >= nchains) return;
+    const bool valid = c < nchains;
+    if (!valid) c = nchains - 1;
+    const int j = p.j0 + c;
+
+    extern __shared__ double smem[];
+    ModelCtx m;
+    m.blob = p.blob;
+    m.D = p.D;
+    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
+
+    const int D = p.D;
+    const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;
+    const int nmcmc = p.use_override ? p.nmcmc_override : p.state->nmcmc;
+    const double dt = p.use_override ? p.dt_override : p.state->hmc_dt;
+    const unsigned long long chain_id = p.chain_base + (unsigned long long)j;
+    const uint32_t cid_lo = (uint32_t)chain_id, cid_hi = (uint32_t)(chain_id >> 32);
+
+    // ---- start point -------------------------------------------------------------------------
+    double q0[E], logL0, logP0;
+    int start_slot = -1;
+    {
+        const double* row;
+        if (p.start_mode == START_GIVEN) {
+            row = p.start_x + (size_t)c * p.Dp;
+            logL0 = p.start_logL[c];
+            logP0 = p.start_logP[c];
+        } else {
+            int slot;
+            if (p.start_mode == START_SELF) {
+                slot = j;
+            } else {
+                Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu, 0u, p.seed_lo, p.seed_hi);
+                slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
+            }
+            start_slot = slot;
+            row = p.ens_x + (size_t)slot * p.Dp;
+            logL0 = p.ens_logL[slot];
+            logP0 = p.ens_logP[slot];
+        }
+        load_row<G, E>(g, row, D, q0);
+    }
+    double blo[E], bhi[E], imass[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = g.lane + e * G;
+        blo[e] = (d < D) ? __ldg(p.lo + d) : CPN_NEG_INF;
+        bhi[e] = (d < D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
+        imass[e] = (d < D) ? __ldg(p.cov + (size_t)d * D + d) : 0.0;      // inverse_mass = diag(covariance), :519
+    }
+    const int Lmax = p.L_override > 0 ? p.L_override : p.base_L + 50;
+
+    // 0.5 p.C.p (+ the constants of proposal.py:575 in replay, where they enter exp(logw - norm) rounding)
+    const double tconst = REPLAY ? (-p.logdet - 0.5 * (double)D * 1.8378770664093454836) : 0.0;
+    auto kinetic = [&](const double (&pp)[E]) -> double {
+        double w[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) w[e] = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double pk = coord<G, E>(g, pp, k);
+            const double* crow = p.cov + (size_t)k * D;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                w[e] = fma((d < D) ? __ldg(crow + d) : 0.0, pk, w[e]);
+            }
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc = fma(pp[e], w[e], acc);
+        return 0.5 * g.sum(acc) + tconst;
+    };
+
+    // replay: one IEEE operation per reference (numpy) operation, no FMA contraction
+    auto mul = [](double a, double b) -> double { return REPLAY ? __dmul_rn(a, b) : a * b; };
+    auto add = [](double a, double b) -> double { return REPLAY ? __dadd_rn(a, b) : a + b; };
+
+    int steps = 0, accepted = 0, evals = 0;
+    bool active = true;
+    double x[E], logL = logL0, logP = logP0, last_logJ = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = q0[e];
+    const double* tp = REPLAY ? p.tape + p.tape_off[c] : nullptr;
+    const int npts = 2 * Lmax + 1;
+    double* traj = REPLAY ? p.traj + (size_t)c * npts * (p.Dp + 3) : nullptr;
+
+    for (int attempt = 0; attempt < p.max_traj; ++attempt) {
+        if (!__any_sync(FULL, active)) break;
+        // trajectory length: given (replay), else base_L + randint(10, 50) (cf. proposal.py:553-559); the leapfrog
+        // loops hold warp-wide shuffles, so the chains sharing a warp use the length drawn by the first of them
+        int L = p.L_override;
+        if (L <= 0) {
+            const Philox4 r = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 2u, p.seed_lo, p.seed_hi);
+            L = p.base_L + 10 + (int)u32_to_index(r.v[0], 40u);
+            L = __shfl_sync(FULL, L, 0);
+        }
+        // ---- momentum draw: np.atleast_1d(momenta_distribution.rvs()), proposal.py:620 ------------------
+        double p0[E];
+        if (REPLAY) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                p0[e] = (active && d < D) ? tp[d] : 0.0;
+            }
+            if (active) tp += D;
+        } else {
+            double z[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                const Philox4 rz = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 0x80000000u | (uint32_t)d, p.seed_lo, p.seed_hi);
+                double g0, g1;
+                box_muller(rz.v[0], rz.v[1], g0, g1);
+                const double sc = __ldg(p.eig_scale + min(d, D - 1));
+                z[e] = (d < D && sc > 0.0) ? g0 / sc : 0.0;                            // z_i |lambda_i|^-1/2
+                p0[e] = 0.0;
+            }
+            for (int i = 0; i < D; ++i) {
+                const double zi = coord<G, E>(g, z, i);
+                const double* vrow = p.eig_vec + (size_t)i * p.Dp;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int d = g.lane + e * G;
+                    p0[e] = fma(zi, (d < D) ? __ldg(vrow + d) : 0.0, p0[e]);
+                }
+            }
+        }
+        const double E0 = kinetic(p0) - logP;                           // hamiltonian(p0, q0), :621
+
+        // ---- the two half trajectories + the weighted draw ----------------------------------------------
+        double logW = CPN_NEG_INF;                                      // production: running log sum of weights
+        double qc[E], logLc = CPN_NEG_INF, logPc = CPN_NEG_INF, Hc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) qc[e] = x[e];
+        int point = 0;                                                  // index in the reference's trajectory list
+        for (int dirn = 0; dirn < 2; ++dirn) {
+            double pm[E], q[E], gv[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) { pm[e] = dirn == 0 ? p0[e] : -p0[e]; q[e] = x[e]; }
+            Model::template grad_potential<G, E>(g, q, m, gv);
+#pragma unroll
+            for (int e = 0; e < E; ++e) pm[e] = add(pm[e], mul(mul(-0.5, dt), gv[e]));     // half step, :757-759
+            double T = 0.0;
+            bool dirty = true;
+            for (int i = 0; i < L; ++i) {
+                ++point;
+                // position step with reflection off the prior bounds, :729-741
+                bool flipped = false;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    q[e] = add(q[e], mul(mul(dt, pm[e]), imass[e]));
+                    for (int guard = 0; guard < 64 && (q[e] < blo[e] || q[e] > bhi[e]); ++guard) {
+                        if (q[e] > bhi[e]) { q[e] = bhi[e] - (q[e] - bhi[e]); pm[e] *= -1.0; flipped = true; }
+                        if (q[e] < blo[e]) { q[e] = blo[e] + (blo[e] - q[e]); pm[e] *= -1.0; flipped = true; }
+                    }
+                }
+                // momentum step, :760-773
+                bool inb = true;
+#pragma unroll
+                for (int e = 0; e < E; ++e) inb = inb & (blo[e] < q[e]) & (q[e] < bhi[e]);
+                inb = g.all(inb);
+                double lp = Model::template log_prior<G, E>(g, q, m);
+                lp = inb ? lp : CPN_NEG_INF;                            // q.logP = -V(q), :790
+                const double ll = Model::template log_likelihood<G, E>(g, q, m);   // :791
+                evals += active ? 1 : 0;
+                Model::template grad_potential<G, E>(g, q, m, gv);
+                const bool inside = ll - logLmin > 0.0;
+                double nrm[E];
+                if (REPLAY) {
+                    const bool refl = active && !inside;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int d = g.lane + e * G;
+                        nrm[e] = (refl && d < D) ? tp[d] : 0.0;
+                    }
+                    if (refl) tp += D;
+                } else {
+                    Model::template grad_log_likelihood<G, E>(g, q, m, nrm);
+                    double n2 = 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        nrm[e] = (g.lane + e * G < D) ? nrm[e] : 0.0;
+                        n2 = fma(nrm[e], nrm[e], n2);
+                    }
+                    n2 = g.sum(n2);
+                    const double inv = (n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) nrm[e] *= inv;           // unit_normal, :469-486
+                }
+                double pn = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) pn = fma(pm[e], nrm[e], pn);
+                pn = g.sum(pn);
+#pragma unroll
+                for (int e = 0; e < E; ++e) pm[e] = add(pm[e], inside ? mul(-dt, gv[e]) : mul(mul(-2.0, pn), nrm[e]));
+                dirty = dirty || !inside || !Model::kFlatPrior;
+                if (g.all(!flipped) == false) dirty = true;
+                if (__any_sync(FULL, dirty)) {
+                    const double Tn = kinetic(pm);
+                    T = dirty ? Tn : T;
+                    dirty = false;
+                }
+                const double H = T - lp;                                 // hamiltonian(p, q) = T(p) + V(q)
+                const bool last = (dirn == 1 && i == L - 1);             // trajectory[1:-1], :841
+                if (REPLAY) {
+                    if (valid && active) {
+                        double* row = traj + (size_t)point * (p.Dp + 3);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            const int d = g.lane + e * G;
+                            if (d < D) row[d] = q[e];
+                        }
+                        if (g.lane == 0) { row[p.Dp] = ll; row[p.Dp + 1] = lp; row[p.Dp + 2] = H; }
+                    }
+                } else if (!last) {
+                    // weighted reservoir: keep this point with probability w / (sum of weights so far)
+                    const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 0x40000000u | (uint32_t)(point >> 2), p.seed_lo, p.seed_hi);
+                    const int k = point & 3;
+                    const uint32_t wv = (k & 2) ? ((k & 1) ? ru.v[3] : ru.v[2]) : ((k & 1) ? ru.v[1] : ru.v[0]);
+                    const double lw = -H;
+                    const double hi2 = fmax(logW, lw), lo2 = fmin(logW, lw);
+                    const double logWn = (hi2 > CPN_NEG_INF) ? hi2 + log1p(exp(lo2 - hi2)) : CPN_NEG_INF;
+                    const bool take = (lw > CPN_NEG_INF) && (log(u32_to_unit_open(wv)) < lw - logWn);
+                    logW = logWn;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) qc[e] = take ? q[e] : qc[e];
+                    logLc = take ? ll : logLc;
+                    logPc = take ? lp : logPc;
+                    Hc = take ? H : Hc;
+                }
+            }
+        }
+        double u_acc;
+        if (REPLAY) {
+            // np.random.choice(range(1, n-1), p = exp(logw - logsumexp(logw))), :840-843: one uniform, searchsorted
+            // on the normalised cumulative sum
+            __syncwarp();
+            const double u = active ? tp[0] : 0.5;
+            u_acc = active ? tp[1] : 0.5;
+            if (active) tp += 2;
+            const int n = 2 * L - 1;                                     // points 1 .. 2L-1
+            double mx = CPN_NEG_INF;
+            for (int k = 1; k <= n; ++k) mx = fmax(mx, -traj[(size_t)k * (p.Dp + 3) + p.Dp + 2]);
+            double ssum = 0.0;
+            for (int k = 1; k <= n; ++k) ssum += exp(-traj[(size_t)k * (p.Dp + 3) + p.Dp + 2] - mx);
+            const double norm = mx + log(ssum);
+            double tot = 0.0;
+            for (int k = 1; k <= n; ++k) tot += exp(-traj[(size_t)k * (p.Dp + 3) + p.Dp + 2] - norm);
+            double cum = 0.0;
+            int idx = n;
+            for (int k = 1; k <= n; ++k) {
+                cum += exp(-traj[(size_t)k * (p.Dp + 3) + p.Dp + 2] - norm);
+                if (u < cum / tot) { idx = k; break; }                    // searchsorted(u, side='right')
+            }
+            const double* row = traj + (size_t)idx * (p.Dp + 3);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                qc[e] = (d < D) ? row[d] : 0.0;
+            }
+            logLc = row[p.Dp]; logPc = row[p.Dp + 1]; Hc = row[p.Dp + 2];
+            __syncwarp();
+        } else {
+            const Philox4 ra = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 1u, p.seed_lo, p.seed_hi);
+            u_acc = u32_to_unit_open(ra.v[0]);
+        }
+        const double log_J = fmin(0.0, E0 - Hc);                         // :626
+        const bool acc = active && (log_J > log(u_acc)) && (logLc > logLmin);   // sampler.py:380-382
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = acc ? qc[e] : x[e];
+        logL = acc ? logLc : logL;
+        logP = acc ? logPc : logP;
+        if (active) {
+            ++steps;
+            last_logJ = log_J;
+            accepted += acc ? 1 : 0;
+            // replay (nmcmc = 1): `while sub_accepted == 0`, sampler.py:375; production: the rule of sampler.py:347
+            if ((steps >= nmcmc && accepted > 0) || steps >= p.max_traj) active = false;
+        }
+    }
+
+    if (valid) {
+        for (int o = 0; o < p.n_out; ++o) {
+            double* row = p.out_x[o] + (size_t)j * p.Dp;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < p.Dp) row[d] = (d < D) ? x[e] : 0.0;
+            }
+            if (g.lane == 0) {
+                p.out_logL[o][j] = logL;
+                p.out_logP[o][j] = logP;
+                p.out_steps[o][j] = steps;
+                p.out_acc[o][j] = accepted;
+                if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
+                if (p.out_evals[o] != nullptr) p.out_evals[o][j] = evals;
+            }
+        }
+        if (p.logJ_out != nullptr && g.lane == 0) p.logJ_out[c] = last_logJ;
+    }
+}
+
+}  // namespace cpn

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
     ModelCtx m;
     m.blob = p.blob;
     m.D = p.D;
-    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * p.Dp : nullptr;
+    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
 
     const int D = p.D;
     const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;

@@ -6,6 +6,7 @@
 #include "eval_kernel.cuh"
 #include "mh_kernel.cuh"
 #include "slice_kernel.cuh"
+#include "hmc_kernel.cuh"
 #include "launch.h"
 
 #define CPN_CONFIGS(X) X(1, 1) X(1, 2) X(1, 4) X(1, 8) X(4, 4) X(8, 2) X(8, 8) X(16, 4) X(32, 1) X(32, 2) X(32, 4) X(32, 8)
@@ -20,7 +21,7 @@ static int launch_mh_model(int G, int E, int replay, const MHParams& p, cudaStre
     if (G == GG && E == EE) {                                                                         \
         const int cpb = kMHThreads / GG;                                                              \
         const int nb = (nchains + cpb - 1) / cpb;                                                     \
-        const size_t sm = Model::kScratch ? (size_t)cpb * p.Dp * sizeof(double) : 0;                  \
+        const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;                  \
         if (replay) k_mh_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                   \
         else k_mh_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                         \
         return 0;                                                                                     \
@@ -38,9 +39,27 @@ static int launch_slice_model(int G, int E, int replay, const SliceParams& p, cu
     if (G == GG && E == EE) {                                                                         \
         const int cpb = kMHThreads / GG;                                                              \
         const int nb = (nchains + cpb - 1) / cpb;                                                     \
-        const size_t sm = Model::kScratch ? (size_t)cpb * p.Dp * sizeof(double) : 0;                  \
+        const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;                  \
         if (replay) k_slice_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                \
         else k_slice_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                      \
+        return 0;                                                                                     \
+    }
+    CPN_CONFIGS(CPN_CASE)
+#undef CPN_CASE
+    return -1;
+}
+
+template <class Model>
+static int launch_hmc_model(int G, int E, int replay, const HMCParams& p, cudaStream_t s) {
+    const int nchains = p.j1 - p.j0;
+    if (nchains <= 0) return 0;
+#define CPN_CASE(GG, EE)                                                                              \
+    if (G == GG && E == EE) {                                                                         \
+        const int cpb = kMHThreads / GG;                                                              \
+        const int nb = (nchains + cpb - 1) / cpb;                                                     \
+        const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;  \
+        if (replay) k_hmc_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                  \
+        else k_hmc_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                        \
         return 0;                                                                                     \
     }
     CPN_CONFIGS(CPN_CASE)
@@ -55,7 +74,7 @@ static int launch_eval_model(int G, int E, const EvalParams& p, cudaStream_t s) 
     if (G == GG && E == EE) {                                                                         \
         const int cpb = kEvalThreads / GG;                                                            \
         const int nb = (p.n + cpb - 1) / cpb;                                                         \
-        const size_t sm = Model::kScratch ? (size_t)cpb * p.Dp * sizeof(double) : 0;                  \
+        const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;                  \
         k_eval_points<GG, EE, Model><<<nb, kEvalThreads, sm, s>>>(p);                                 \
         return 0;                                                                                     \
     }
@@ -76,5 +95,8 @@ static int launch_eval_model(int G, int E, const EvalParams& p, cudaStream_t s) 
     }                                                                                                 \
     int launch_slice_##NAME(int G, int E, int replay, const SliceParams& p, cudaStream_t s) {         \
         return launch_slice_model<MODEL>(G, E, replay, p, s);                                         \
+    }                                                                                                 \
+    int launch_hmc_##NAME(int G, int E, int replay, const HMCParams& p, cudaStream_t s) {             \
+        return launch_hmc_model<MODEL>(G, E, replay, p, s);                                           \
     }                                                                                                 \
     }

@@ -13,10 +13,12 @@ namespace cpn {
 #define CPN_NEG_INF (__longlong_as_double(0xfff0000000000000LL))
 #define CPN_HALF_LOG_2PI 0.91893853320467274178
 
+constexpr int kScratchRows = 2;   // shared-memory scratch per chain of functors with kScratch: kScratchRows * Dp doubles
+
 struct ModelCtx {
     const double* blob;   // functor parameters (device)
     int D;                // dimension
-    double* scratch;      // per-chain shared-memory scratch, >= D doubles (functors with kScratch)
+    double* scratch;      // per-chain shared-memory scratch, kScratchRows * Dp doubles (functors with kScratch)
 };
 
 template <int G, int E>
@@ -29,7 +31,18 @@ struct FlatPrior {
     static __device__ __forceinline__ double log_prior(const Group<G>&, const double (&)[E], const ModelCtx&) {
         return 0.0;
     }
+    // Model.force (model.py:97-106): gradient of the potential -log_prior; zero for the flat prior, as in every
+    // model the reference ships (tests/test_2d_hmc.py:22-24, examples/test_50d.py:25-28, examples/rosenbrock.py:24-26)
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_potential(const Group<G>&, const double (&)[E], const ModelCtx&, double (&gv)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) gv[e] = 0.0;
+    }
 };
+
+// Gradients of log_likelihood (one component per coordinate, laid out like the point) give the normal of the
+// iso-likelihood surface the constrained leapfrog reflects off; the reference estimates that normal from
+// per-dimension spline fits over the ensemble (proposal.py:417-486), the device functors provide it analytically.
 
 // ---- iid Gaussian: examples/test_50d.py:18-19 (sum_i -x_i^2/2 - log(2pi)/2), tests/test_2d.py:15-16,
 //      tests/test_1d.py:20-21 and tests/test_half_gaussian.py:24-25 (scipy norm.logpdf) ----------------
@@ -47,6 +60,12 @@ struct GaussIid : FlatPrior {
             acc += valid_dim<G, E>(g, e, m.D) ? term : 0.0;
         }
         return g.sum(acc);
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>&, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        const double mu = m.blob[0], inv_sigma = m.blob[1];
+#pragma unroll
+        for (int e = 0; e < E; ++e) gr[e] = -(x[e] - mu) * inv_sigma * inv_sigma;
     }
 };
 
@@ -79,6 +98,39 @@ struct GaussCorr : FlatPrior {
         __syncwarp();
         return -0.5 * g.sum(acc) - m.blob[0] - D * CPN_HALF_LOG_2PI;
     }
+    // grad = -Linv^T (Linv x); scratch holds x in [0, D) and y = Linv x in [Dp, Dp + D)
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        const int D = m.D, Dp = (D + 3) & ~3;
+        const double* Linv = m.blob + 1;
+        double* y = m.scratch + Dp;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int d = g.lane + e * G;
+            if (d < D) m.scratch[d] = x[e];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int r = g.lane + e * G;
+            if (r < D) {
+                const double* row = Linv + (size_t)r * D;
+                double v = 0.0;
+                for (int c = 0; c <= r; ++c) v = fma(__ldg(row + c), m.scratch[c], v);
+                y[r] = v;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int c = g.lane + e * G;
+            double v = 0.0;
+            if (c < D)
+                for (int r = c; r < D; ++r) v = fma(__ldg(Linv + (size_t)r * D + c), y[r], v);
+            gr[e] = -v;
+        }
+        __syncwarp();
+    }
 };
 
 // ---- eggbox: examples/eggbox.py:19-23  (2 + prod cos(x_i/2))^5 ------------------------------
@@ -92,6 +144,23 @@ struct Eggbox : FlatPrior {
         for (int e = 0; e < E; ++e) p *= valid_dim<G, E>(g, e, m.D) ? cos(x[e] / 2.0) : 1.0;
         p = g.prod(p);
         return pow(p + 2.0, 5.0);
+    }
+    // d/dx_i (2 + P)^5 = 5 (2 + P)^4 * (-1/2) sin(x_i/2) prod_{j != i} cos(x_j/2)
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        double cs[E], p = 1.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            cs[e] = valid_dim<G, E>(g, e, m.D) ? cos(x[e] / 2.0) : 1.0;
+            p *= cs[e];
+        }
+        p = g.prod(p);
+        const double f = 5.0 * (p + 2.0) * (p + 2.0) * (p + 2.0) * (p + 2.0);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double others = (cs[e] != 0.0) ? p / cs[e] : 0.0;
+            gr[e] = valid_dim<G, E>(g, e, m.D) ? f * (-0.5 * sin(x[e] / 2.0)) * others : 0.0;
+        }
     }
 };
 
@@ -121,6 +190,29 @@ struct Rosenbrock : FlatPrior {
         }
         return -g.sum(acc);
     }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double nxt, prv;
+            if (G == 1) {
+                nxt = (e + 1 < E) ? x[(e + 1 < E) ? e + 1 : e] : 0.0;
+                prv = (e > 0) ? x[(e > 0) ? e - 1 : 0] : 0.0;
+            } else {
+                const double a = __shfl_sync(FULL, x[e], (g.lane + 1) & (G - 1), G);
+                const double b = (e + 1 < E) ? __shfl_sync(FULL, x[(e + 1 < E) ? e + 1 : e], 0, G) : 0.0;
+                nxt = (g.lane == G - 1) ? b : a;
+                const double c = __shfl_sync(FULL, x[e], (g.lane + G - 1) & (G - 1), G);
+                const double dd = (e > 0) ? __shfl_sync(FULL, x[(e > 0) ? e - 1 : 0], G - 1, G) : 0.0;
+                prv = (g.lane == 0) ? dd : c;
+            }
+            const int d = g.lane + e * G;
+            double v = 0.0;
+            if (d < m.D - 1) v += -400.0 * x[e] * (nxt - x[e] * x[e]) - 2.0 * (1.0 - x[e]);
+            if (d > 0 && d < m.D) v += 200.0 * (x[e] - prv * prv);
+            gr[e] = -v;
+        }
+    }
 };
 
 // ---- standard D-dim Ackley, logL = -ackley(x) (examples/ackley.py:21-28 as written
@@ -142,6 +234,23 @@ struct Ackley : FlatPrior {
         double a = -20.0 * exp(-0.2 * sqrt(s2 / m.D)) - exp(sc / m.D) + 20.0 + 2.71828182845904523536;
         return -a;
     }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        const double twopi = 2.0 * 3.14159265358979323846;
+        double s2 = 0.0, sc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            bool ok = valid_dim<G, E>(g, e, m.D);
+            s2 += ok ? x[e] * x[e] : 0.0;
+            sc += ok ? cos(twopi * x[e]) : 0.0;
+        }
+        s2 = g.sum(s2);
+        sc = g.sum(sc);
+        const double r = sqrt(s2 / m.D);
+        const double t1 = (r > 0.0) ? 4.0 * exp(-0.2 * r) / (m.D * r) : 0.0, t2 = twopi / m.D * exp(sc / m.D);
+#pragma unroll
+        for (int e = 0; e < E; ++e) gr[e] = valid_dim<G, E>(g, e, m.D) ? -(t1 * x[e] + t2 * sin(twopi * x[e])) : 0.0;
+    }
 };
 
 // ---- ring: tests/test_ring.py:19-23 ; blob = {radius, thickness} ------------------------------
@@ -154,6 +263,14 @@ struct Ring : FlatPrior {
         double r = sqrt(a * a + b * b);
         double dr = m.blob[0] - r;
         return -0.5 * (dr * dr) / (m.blob[1] * m.blob[1]);
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        const double a = coord<G, E>(g, x, 0), b = coord<G, E>(g, x, 1);
+        const double r = sqrt(a * a + b * b);
+        const double f = (r > 0.0) ? (m.blob[0] - r) / (m.blob[1] * m.blob[1]) / r : 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) gr[e] = (g.lane + e * G < 2) ? f * x[e] : 0.0;
     }
 };
 
@@ -171,6 +288,23 @@ struct GaussMeanSigma {
     static __device__ __forceinline__ double log_prior(const Group<G>& g, const double (&x)[E], const ModelCtx&) {
         double sigma = coord<G, E>(g, x, 1);
         return -log(sigma) - 2.30258509299404568402 /*log 10*/ - (-0.05129329438755058) /*log 0.95*/;
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx&, double (&gr)[E]) {
+        const double mean = coord<G, E>(g, x, 0), sigma = coord<G, E>(g, x, 1);
+        const double v[2] = {-mean / (sigma * sigma), mean * mean / (sigma * sigma * sigma) - 1.0 / sigma};
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int d = g.lane + e * G;
+            gr[e] = (d == 0) ? v[0] : (d == 1 ? v[1] : 0.0);
+        }
+    }
+    // potential = -log_prior = log(sigma) + const
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_potential(const Group<G>& g, const double (&x)[E], const ModelCtx&, double (&gv)[E]) {
+        const double sigma = coord<G, E>(g, x, 1);
+#pragma unroll
+        for (int e = 0; e < E; ++e) gv[e] = (g.lane + e * G == 1) ? 1.0 / sigma : 0.0;
     }
 };
 
@@ -201,6 +335,50 @@ struct GaussMixture {
     template <int G, int E>
     static __device__ __forceinline__ double log_prior(const Group<G>& g, const double (&x)[E], const ModelCtx&) {
         return -log(coord<G, E>(g, x, 1)) - log(coord<G, E>(g, x, 3));
+    }
+    // responsibilities r_k = exp(l_k - logaddexp(l1, l2)):
+    //   d/dmean_k = sum r_k (d - mean_k)/sigma_k^2 ; d/dsigma_k = sum r_k ((d - mean_k)^2/sigma_k^3 - 1/sigma_k) ;
+    //   d/dw = sum r_1 / w - r_2 / (1 - w)
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        const double m1 = coord<G, E>(g, x, 0), s1 = coord<G, E>(g, x, 1), m2 = coord<G, E>(g, x, 2),
+                     s2 = coord<G, E>(g, x, 3), w = coord<G, E>(g, x, 4);
+        const int n = (int)m.blob[0];
+        const double* data = m.blob + 1;
+        const double c1 = log(w) - log(s1), c2 = log(1.0 - w) - log(s2);
+        const double i1 = 1.0 / s1, i2 = 1.0 / s2;
+        double a[5] = {0, 0, 0, 0, 0};
+        for (int i = g.lane; i < n; i += G) {
+            const double d = __ldg(data + i);
+            const double t1 = (d - m1) * i1, t2 = (d - m2) * i2;
+            const double l1 = c1 - 0.5 * t1 * t1, l2 = c2 - 0.5 * t2 * t2;
+            const double hi = fmax(l1, l2), lae = hi + log1p(exp(fmin(l1, l2) - hi));
+            const double r1 = exp(l1 - lae), r2 = exp(l2 - lae);
+            a[0] += r1 * t1 * i1;
+            a[1] += r1 * (t1 * t1 - 1.0) * i1;
+            a[2] += r2 * t2 * i2;
+            a[3] += r2 * (t2 * t2 - 1.0) * i2;
+            a[4] += r1 / w - r2 / (1.0 - w);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a[k] = g.sum(a[k]);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int d = g.lane + e * G;
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v = (d == k) ? a[k] : v;
+            gr[e] = v;
+        }
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_potential(const Group<G>& g, const double (&x)[E], const ModelCtx&, double (&gv)[E]) {
+        const double s1 = coord<G, E>(g, x, 1), s2 = coord<G, E>(g, x, 3);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int d = g.lane + e * G;
+            gv[e] = (d == 1) ? 1.0 / s1 : (d == 3 ? 1.0 / s2 : 0.0);
+        }
     }
 };
 

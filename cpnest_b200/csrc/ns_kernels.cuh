@@ -309,6 +309,18 @@ __global__ void __launch_bounds__(256) k_adapt_slice_mu(NSState* st, int K, cons
     }
 }
 
+// HamiltonianProposal.update_time_step (proposal.py:539-550): log(scale) += ADAPTATIONSIZE * (acceptance - TARGET),
+// TARGET = 0.5.  The reference applies it once per returned chain with ADAPTATIONSIZE = 0.001 and its running
+// acceptance; here once per batch with the batch's trajectory acceptance (accepted / attempted trajectories) and a
+// gain of 0.05.  Must run after k_chain_corr (batch counters) and before k_merge_commit (which folds them).
+__global__ void k_adapt_hmc_dt(NSState* st) {
+    if (st->done) return;
+    const unsigned long long traj = st->batch[0], accd = st->batch[1];
+    if (traj == 0) return;
+    const double acc = (double)accd / (double)traj;
+    st->hmc_dt *= exp(0.05 * (acc - 0.5));
+}
+
 // corr_d(start, end) across the K chains of the batch, d in [0, D] (d == D is logL).
 // One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
 __global__ void __launch_bounds__(256) k_chain_corr(NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,

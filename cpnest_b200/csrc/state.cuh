@@ -31,7 +31,7 @@ struct NSState {
     int adapt;
     int stop_next;        // condition <= tolerance seen: the following batch must not run
     int done;
-    int pad;
+    int sampler;          // cpn_sampler of the context (the chain-length controller reads it)
 };
 
 }  // namespace cpn

@@ -12,6 +12,7 @@ import math
 import numpy as np
 
 from . import _lib as L
+from . import _lib as L_
 
 
 def functor_blob(name, dim, params=None):
@@ -217,6 +218,13 @@ class Engine:
         L.check(self.lib.cpn_eval_model(self.h, L.dptr(X), n, L.dptr(logL), L.dptr(logP)))
         return logL, logP
 
+    def eval_gradients(self, X):
+        X = L.f64(X).reshape(-1, self.dim)
+        n = X.shape[0]
+        gl, gv = np.empty((n, self.dim)), np.empty((n, self.dim))
+        L.check(self.lib.cpn_eval_gradients(self.h, L.dptr(X), n, L.dptr(gl), L.dptr(gv)))
+        return gl, gv
+
     def replay_mh(self, ensemble, start, eigval, eigvec, cycle_idx, tape, nmcmc, maxmcmc, logLmin,
                   compat=True, lanes=0, record=False):
         ens = L.f64(ensemble)
@@ -255,6 +263,27 @@ class Engine:
                                           float(logLmin), 1 if compat else 0, int(lanes), L.dptr(out), L.iptr(steps),
                                           L.iptr(acc), L.iptr(evals), L.dptr(last)))
         return out, steps, acc, evals, last
+
+    def replay_hmc(self, start, cov, logdet, tapes, dt, L, logLmin, max_traj=1000, lanes=0):
+        """HMC chains from explicit tapes (include/cpnest_b200.h cpn_replay_hmc).
+        Returns (out, steps, accepted, evals, log_J)."""
+        start = L_.f64(start).reshape(-1, self.dim + 2)
+        Cn = start.shape[0]
+        assert len(tapes) == Cn
+        off = np.zeros(Cn + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(t) for t in tapes])
+        tape = L_.f64(np.concatenate([np.asarray(t, dtype=np.float64) for t in tapes]))
+        cov = L_.f64(cov).reshape(self.dim, self.dim)
+        out = np.empty((Cn, self.dim + 2))
+        steps = np.empty(Cn, dtype=np.int32)
+        acc = np.empty(Cn, dtype=np.int32)
+        evals = np.empty(Cn, dtype=np.int32)
+        logJ = np.empty(Cn)
+        L_.check(self.lib.cpn_replay_hmc(self.h, Cn, L_.dptr(start), L_.dptr(cov), float(logdet), L_.dptr(tape),
+                                         off.ctypes.data_as(C.POINTER(C.c_int64)), float(dt), int(L), int(max_traj),
+                                         float(logLmin), int(lanes), L_.dptr(out), L_.iptr(steps), L_.iptr(acc),
+                                         L_.iptr(evals), L_.dptr(logJ)))
+        return out, steps, acc, evals, logJ
 
     def slice_directions(self, direction, n, mu=1.0):
         out = np.empty((n, self.dim))

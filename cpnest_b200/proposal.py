@@ -147,8 +147,34 @@ class EnsembleSliceProposalCycle(ProposalCycle):
         return np.array(ids, dtype=np.uint8)
 
 
+class HamiltonianProposal(EnsembleEigenVector):
+    """Base of the Hamiltonian proposals (cpnest/proposal.py:377-588): mass matrix = inverse ensemble covariance,
+    dt / L adaptation.  Runs inside the CUDA HMC kernel (csrc/hmc_kernel.cuh)."""
+    device_id = None
+    TARGET = 0.500
+
+    def __init__(self, model=None, **kwargs):
+        self.model = model
+
+
+class LeapFrog(HamiltonianProposal):
+    """Unconstrained leapfrog (cpnest/proposal.py:590-673); on the device it is the constrained kernel at logLmin = -inf."""
+    hmc_device = True
+
+
+class ConstrainedLeapFrog(LeapFrog):
+    """Leapfrog with reflection off the logL = logLmin surface (cpnest/proposal.py:675-844)."""
+    hmc_device = True
+
+
 class HamiltonianProposalCycle(ProposalCycle):
-    """cpnest/proposal.py:364-375.  The HMC sampler has no device kernel yet."""
+    """One ConstrainedLeapFrog (cpnest/proposal.py:364-375)."""
 
     def __init__(self, model=None):
-        raise NotImplementedError("the Hamiltonian sampler (nhamiltonian > 0) is not implemented on the device yet")
+        super(HamiltonianProposalCycle, self).__init__([ConstrainedLeapFrog(model=model)], [1])
+
+    def device_cycle(self):
+        for p in self.cycle:
+            if not getattr(p, "hmc_device", False):
+                raise NotImplementedError("Hamiltonian proposal %s has no device implementation" % type(p).__name__)
+        return np.zeros(len(self.cycle), dtype=np.uint8)

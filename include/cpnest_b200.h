@@ -192,6 +192,10 @@ int cpn_evolve_host(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc,
 /* ---- parity / test entry points ------------------------------------------------------------ */
 /* Model.log_prior / log_likelihood on given points (functor parity vs the Python callables). */
 int cpn_eval_model(cpn_ctx* ctx, const double* x /*[n][D]*/, int32_t n, double* logL, double* logP);
+/* Gradient functors on given points: d log_likelihood / dx (the reflection normal of the constrained leapfrog,
+ * cpnest/proposal.py:469-486, 766-772) and Model.force = d(-log_prior)/dx (cpnest/model.py:97-106). */
+int cpn_eval_gradients(cpn_ctx* ctx, const double* x /*[n][D]*/, int32_t n, double* grad_logL /*[n][D]*/,
+                       double* grad_V /*[n][D]*/);
 /* MH chains driven by an explicit random tape instead of Philox (SURVEY 7 step 3 "replay mode").
  * ensemble[P][D]; start[C][D+2]; per chain c and step s the tape row tape[(c*maxmcmc+s)*8+..] is
  * {i0,i1,i2 (as doubles), g0,g1,g2, u_stretch, u_mh}.  compat=1 applies the reference's fp32
@@ -214,6 +218,15 @@ int cpn_replay_slice(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C,
                      int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes,
                      double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted, int32_t* evals,
                      double* last /*[C][4]*/);
+/* HMC chains driven by an explicit tape (HamiltonianMonteCarloSampler.yield_sample, cpnest/sampler.py:365-402, with
+ * ConstrainedLeapFrog, cpnest/proposal.py:793-844).  Per chain c the doubles tape[tape_off[c] .. tape_off[c+1]) hold,
+ * trajectory after trajectory, { p0[D] (momenta_distribution.rvs()), normal[D] for every reflection off the likelihood
+ * boundary in the order they occur (unit_normal), u of np.random.choice in sample_trajectory, u of the acceptance test }.
+ * cov[D][D] is the ensemble covariance (= inverse mass matrix), logdet = log det of the mass matrix. */
+int cpn_replay_hmc(cpn_ctx* ctx, int32_t C, const double* start /*[C][D+2]*/, const double* cov, double logdet,
+                   const double* tape, const int64_t* tape_off, double dt, int32_t L, int32_t max_traj,
+                   double logLmin, int32_t lanes, double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted,
+                   int32_t* evals, double* log_J /*[C]*/);
 /* Directions of the production slice kernel for chains [0, C) of the next batch's first slice, all of kind
  * `direction` (test entry: distribution of the three direction proposals, cpnest/proposal.py:121-187). */
 int cpn_slice_directions(cpn_ctx* ctx, int32_t direction, int32_t C, double mu, double* out /*[C][D]*/);

@@ -115,6 +115,15 @@ def test_2d_slice_like_reference_test(tmp_path):
     assert abs(pos["x"].mean()) < 0.2 and abs(pos["x"].std() - 1.0) < 0.2
 
 
+def test_2d_hmc_like_reference_test(tmp_path):
+    # tests/test_2d_hmc.py:30: CPNest(model, verbose=1, nthreads=1, nlive=1000, maxmcmc=5000, poolsize=1000, nhamiltonian=1)
+    import cpnest_b200.models as M
+    model = M.GaussianModel(2)
+    work = _run(model, tmp_path, verbose=1, nthreads=1, nhamiltonian=1, nlive=1000, maxmcmc=5000, poolsize=1000)
+    assert work.sampler_kind == "hmc"
+    assert np.abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * np.sqrt(work.NS.state.info / work.NS.Nlive)
+
+
 def test_ring_slice_like_reference_test(tmp_path):
     # tests/test_ring_slice.py:31: nthreads=4, nslice=4, nlive=1000, maxmcmc=1000
     import cpnest_b200.models as M
