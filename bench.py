@@ -36,12 +36,22 @@ sys.path.insert(0, ROOT)
 
 DIM = 50
 NLIVE_PER_GPU = 10000
-K_PER_GPU = 2500
+K_PER_GPU = 4704          # 147 SMs x 16 resident warps x 2 chains per warp: one wave of the chain kernel, with room
+                          # left on one SM for the ensemble-statistics kernels that run beside it on the side stream
 MAXMCMC = 5000
 SEED = 1234
 ANALYTIC_LOGZ = -DIM * math.log(20.0)
 METRIC = "likelihood evals/sec (50-D Gaussian, nlive=1e4 per GPU, MH DefaultProposalCycle)"
 UNIT = "likelihood evals/s"
+
+
+def fp64_peak():
+    """Measured DFMA peak of this pool's B200 (scripts/fp_peak.cu -> profiles/fp_peaks.json); MEASURED_PEAKS.json has
+    no FP64 figure."""
+    p = os.path.join(ROOT, "profiles", "fp_peaks.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["fp64_fma_tflops"]), "measured (profiles/fp_peaks.json, scripts/fp_peak.cu)"
+    return 34.0, "fallback (earlier measurement on this pool)"
 
 
 def peaks():
@@ -130,8 +140,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nlive", type=int, default=NLIVE_PER_GPU)
     ap.add_argument("--k", type=int, default=K_PER_GPU)
@@ -206,33 +216,69 @@ def main():
         drv = ShardedEngine(eng, comm=args.comm)
     else:
         drv = eng
-    for _ in range(args.warmup):
-        drv.ns_step(K)
+    # A run has about nlive * (H + 3 sqrt(H)) / K batches (H = 79 nats): ~190 at the default sizes.  Steps beyond the end
+    # of a run would be no-ops, so the state is polled every CHECK steps and a finished run is followed by a fresh one
+    # (new seed); the re-initialisation (prior draw + sort, a few ms) stays inside the timed region.
+    CHECK = 16
+    runs = [0]
+
+    carried = dict(total_evals=0, total_steps=0, total_accepted=0)
+
+    def fresh_run():
+        st = eng.state()
+        for k in carried:
+            carried[k] += st[k]                   # cpn_init_prior resets the run's counters
+        runs[0] += 1
+        eng.set_seed(SEED + 7919 * runs[0])
+        eng.init_prior()
+
+    def totals():
+        st = eng.state()
+        return {k: carried[k] + st[k] for k in carried}, st
+
+    def do_steps(n):
+        done = 0
+        while done < n:
+            m = min(CHECK, n - done)
+            for _ in range(m):
+                drv.ns_step(K)
+            done += m
+            st = eng.state()
+            if st["done"] or not (st["condition"] > 0.1):
+                fresh_run()
+
+    do_steps(args.warmup)
     torch.cuda.synchronize()
-    s0 = eng.state()
+    s0, _ = totals()
+    r0 = runs[0]
     l0 = eng.launch_count()
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
-        drv.ns_step(K)
+    do_steps(args.steps)
     ev1.record(stream)
     barrier()
     dt_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clk = clocks.result()
-    s1 = eng.state()
+    t1, s1 = totals()
     launches = eng.launch_count() - l0
-    # the counters are sums over the gathered per-chain outcomes: already global on every rank
-    evals = s1["total_evals"] - s0["total_evals"]
-    steps_mcmc = s1["total_steps"] - s0["total_steps"]
-    accepted = s1["total_accepted"] - s0["total_accepted"]
+    # the counters are sums over the gathered per-chain outcomes: already global on every rank; they are cumulative
+    # over the runs of this context
+    evals = t1["total_evals"] - s0["total_evals"]
+    steps_mcmc = t1["total_steps"] - s0["total_steps"]
+    accepted = t1["total_accepted"] - s0["total_accepted"]
     value = evals / (dt_ms * 1e-3)
+    restarts = runs[0] - r0
+    if s1["done"] or not (s1["condition"] > 0.1) or s1["batches"] < 12:
+        fresh_run()
+        do_steps(30)
 
     # ---- the dominant kernel alone: per-launch duration of k_mh_chains, live, with events ----
     kev = []
     mh_steps = []
+    mh_evals = []
     for _ in range(min(10, args.steps)):
         eng.select_and_accumulate(K)
         a = eng.state()
@@ -247,6 +293,7 @@ def main():
         b = eng.state()
         kev.append(e0.elapsed_time(e1))
         mh_steps.append((b["total_steps"] - a["total_steps"]) / world)
+        mh_evals.append((b["total_evals"] - a["total_evals"]) / world)
     k_ms = float(np.mean(kev))
     k_steps = float(np.mean(mh_steps))
     # algorithmic bytes of one launch: gathers 13.33*D bytes per MCMC step of the
@@ -262,10 +309,19 @@ def main():
             traffic = json.load(open(tp)).get("k_mh_chains_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # algorithmic FP64 work of the same launch: 6.17*D flops per proposal + box test, 3*D per
+    # likelihood evaluation of the iid Gaussian
+    k_evals = float(np.mean(mh_evals))
+    alg_flops = k_steps * 6.17 * DIM + k_evals * 3.0 * DIM
+    f64_peak, f64_src = fp64_peak()
+    f64_achieved = alg_flops / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_mh_chains", "ms_per_launch": k_ms, "mcmc_steps_per_launch": k_steps,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "gathers are served from L2 (live set %.1f MB); the kernel is issue/latency bound, see DESIGN.md" % (
+                "fp64": {"achieved": f64_achieved, "peak": f64_peak, "unit": "TFLOP/s", "frac": f64_achieved / f64_peak,
+                         "algorithmic_flops_per_launch": alg_flops, "evals_per_launch": k_evals, "peak_source": f64_src},
+                "note": "gathers are served from L2 (live set %.1f MB, DRAM traffic per launch = `traffic`); the kernel is "
+                        "bound by dependent-instruction latency at the occupancy K chains allow, see DESIGN.md" % (
                     N * 52 * 8 / 1e6)}
 
     # ---- finish the run: log-evidence wall time and validity --------------------------------------
@@ -361,6 +417,7 @@ def main():
                        "l2_policy": "working set per step (live set + staging, %.1f MB) is re-gathered at random; "
                                     "no explicit flush: every step reads points rewritten by the previous one" % (
                                         (N + K) * 52 * 8 / 1e6)},
+            "runs_restarted_in_timed_region": restarts,
             "mcmc_steps_per_s": steps_mcmc / (dt_ms * 1e-3),
             "accepted_chain_steps_per_s": accepted / (dt_ms * 1e-3),
             "clocks": clk,

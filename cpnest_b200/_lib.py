@@ -62,6 +62,7 @@ SIGNATURES = {
     "cpn_set_cycle": (C.c_int, [_vp, _P(C.c_uint8), C.c_int32]),
     "cpn_set_slice_cycle": (C.c_int, [_vp, _P(C.c_uint8), C.c_int32]),
     "cpn_set_slice_mu": (C.c_int, [_vp, C.c_double]),
+    "cpn_set_seed": (C.c_int, [_vp, C.c_uint64]),
     "cpn_init_prior": (C.c_int, [_vp]),
     "cpn_set_live": (C.c_int, [_vp, _dp, C.c_int32]),
     "cpn_update_ensemble_stats": (C.c_int, [_vp]),

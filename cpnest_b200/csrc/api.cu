@@ -448,6 +448,12 @@ extern "C" int cpn_set_slice_cycle(cpn_ctx* c, const uint8_t* cycle, int32_t len
     return 0;
 }
 
+extern "C" int cpn_set_seed(cpn_ctx* c, uint64_t seed) {
+    if (!c) return fail("null context");
+    c->cfg.seed = seed;
+    return 0;
+}
+
 extern "C" int cpn_set_slice_mu(cpn_ctx* c, double mu) {
     if (!c) return fail("null context");
     if (!(mu > 0.0)) return fail("cpn_set_slice_mu: mu must be > 0");
@@ -783,10 +789,14 @@ extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
     // Refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254).  The refresh runs
     // on the side stream beside the chain kernels of two batches and is adopted by the batch after those
     // (fixed latency, so the schedule - and with it every result - is deterministic); one refresh is in
-    // flight at a time, which makes the cadence max(2 batches, nlive/4 chains).
+    // flight at a time.
     if (c->eig_pending && ++c->eig_pending_age >= 2)
         if (adopt_pending_stats(c)) return 1;
-    if (!c->eig_pending && c->chains_since_stats >= std::max(1, c->N / 4))
+    // Beyond nlive/4 chains the cadence follows what the statistics are used for: replacing K of N points shrinks
+    // each axis of the ensemble by exp(-K/(N D)), so the jump scales sqrt|lambda_i| drift by 5% only after
+    // 0.05 N D chains (5 batches at N = 1e4, D = 50, K = 4.7e3; nlive/4 again for D <= 5).
+    const long long cadence = std::max<long long>(std::max(1, c->N / 4), (long long)(0.05 * (double)c->N * (double)c->D));
+    if (!c->eig_pending && c->chains_since_stats >= cadence)
         if (start_async_stats(c)) return 1;
 
     if (grow_logs(c, c->dead_upper + K + c->N)) return 1;

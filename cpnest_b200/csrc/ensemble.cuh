@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kJacobiThreads) k_jacobi_eigh(const double* __
         __syncthreads();
         for (int s = nt >> 1; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
         dia = red[0];
-        if (tid == 0) converged = (off <= 1e-25 * dia) || (D == 1);
+        if (tid == 0) converged = (off <= 1e-24 * dia) || (D == 1);     // |off|_F <= 1e-12 |diag|_F
         __syncthreads();
         if (converged) break;
         for (int r = 0; r < n - 1; ++r) {

@@ -168,19 +168,22 @@ struct DrawFeed {
     }
 };
 
-// the three rows a production step gathers (kinds that need fewer re-read row i0: an L1 hit)
+// the three rows a production step gathers (kinds that need fewer re-read row i0: an L1 hit).  Slots beyond D
+// are never loaded: the buffers are zeroed once and stay zero, so no select follows the loads.
 template <int G, int E>
 __device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, const StepIn& s, double (&r0)[E],
                                             double (&r1)[E], double (&r2)[E]) {
     const bool eig = s.kind == CPN_EIGEN;
-    const double* base = eig ? p.eig_vec : p.ens_x;
-    load_row<G, E>(g, base + (size_t)s.i0 * p.Dp, p.D, r0);
+    const double* b0 = (eig ? p.eig_vec : p.ens_x) + (size_t)s.i0 * p.Dp + g.lane;
+    const double* b1 = p.ens_x + (size_t)s.i1 * p.Dp + g.lane;
+    const double* b2 = p.ens_x + (size_t)s.i2 * p.Dp + g.lane;
     const bool two = (s.kind == CPN_WALK) | (s.kind == CPN_DE), three = s.kind == CPN_WALK;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const int d = g.lane + e * G;
-        if (two && d < p.D) r1[e] = __ldg(p.ens_x + (size_t)s.i1 * p.Dp + d);
-        if (three && d < p.D) r2[e] = __ldg(p.ens_x + (size_t)s.i2 * p.Dp + d);
+        const bool in = g.lane + e * G < p.D;
+        if (in) r0[e] = __ldg(b0 + e * G);
+        if (two && in) r1[e] = __ldg(b1 + e * G);
+        if (three && in) r2[e] = __ldg(b2 + e * G);
     }
 }
 
@@ -215,7 +218,9 @@ __device__ __forceinline__ TapeIn tape_step(int kind, const double* t, int compa
 }
 
 template <int G, int E, class Model, bool REPLAY>
-__global__ void __launch_bounds__(kMHThreads) k_mh_chains(const MHParams p) {
+// E <= 4: 128 registers, 4 blocks = 16 warps per SM, one wave for up to 4736 chains of 16 lanes (one latency-bound
+// wave: time per launch is flat in the number of chains up to there)
+__global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(const MHParams p) {
     if (!REPLAY && p.state != nullptr && p.state->done) return;
     const Group<G> g;
     const int cpb = kMHThreads / G;

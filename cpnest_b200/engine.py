@@ -104,6 +104,9 @@ class Engine:
     def set_slice_mu(self, mu):
         L.check(self.lib.cpn_set_slice_mu(self.h, float(mu)))
 
+    def set_seed(self, seed):
+        L.check(self.lib.cpn_set_seed(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+
     def init_prior(self):
         L.check(self.lib.cpn_init_prior(self.h))
 

@@ -114,6 +114,8 @@ int cpn_set_slice_cycle(cpn_ctx* ctx, const uint8_t* cycle, int32_t len);
 /* SliceSampler.mu (cpnest/sampler.py:422): initial / current length scale of the slice directions. */
 int cpn_set_slice_mu(cpn_ctx* ctx, double mu);
 
+/* CPNest(seed=): Philox key of everything drawn from now on (takes effect with the next cpn_init_prior). */
+int cpn_set_seed(cpn_ctx* ctx, uint64_t seed);
 /* Sampler.reset + NestedSampler.reset (cpnest/sampler.py:110-154, NestedSampling.py:404-431):
  * draw nlive points uniformly in bounds (Model.new_point, model.py:35-53), evaluate, evolve each
  * with logLmin=-inf so they follow the prior, sort by logL. */
