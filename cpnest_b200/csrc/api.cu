@@ -914,7 +914,12 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
             c->launches += 1;
         }
     }
-    k_rank_new<<<(K + T - 1) / T, T, T * sizeof(double), c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
+    CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
+    {
+        const int nt = (K + kRankTile - 1) / kRankTile;
+        k_rank_count<<<dim3(nt, nt), kRankTile, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank);
+        k_rank_scatter<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
+    }
     MergeParams m;
     memset(&m, 0, sizeof m);
     m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
@@ -932,10 +937,10 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         CK(cudaStreamWaitEvent(c->stream, c->ev_cov, 0));
         c->wait_cov = false;
     }
-    k_merge_commit<<<(c->N + T - 1) / T, T, 0, c->stream>>>(m);
+    k_merge_commit<<<(c->N + K * c->Dp + T - 1) / T, T, 0, c->stream>>>(m);
     CKL();
     c->cur ^= 1;
-    c->launches += 2;
+    c->launches += 3;
     return 0;
 }
 

@@ -2,7 +2,7 @@
 // rounds of sampler requests (cpnest/NestedSampling.py):
 //   k_ns_accumulate   get_worst_n_live_points (:368-375) + _NSintegralState.increment (:111-134)
 //                     + termination condition (:332, :451) + Nmcmc moving average (sampler.py:156-176)
-//   k_rank_new        ordering of the K replacements (KeyOrderedList.search, :42-46)
+//   k_rank_count/scatter  ordering of the K replacements (KeyOrderedList.search, :42-46)
 //   k_merge_commit    insert_live_point / remove_n_worst_points (:74-85) + insertion indices (:347-350)
 //                     + nested_samples.extend (:327)
 //   k_bitonic_step    initial sort of the live set (OrderedLivePoints.__init__, :71-72)
@@ -360,30 +360,35 @@ __global__ void __launch_bounds__(256) k_chain_corr(NSState* st, int K, int D, i
     }
 }
 
-// rank of each replacement among the K replacements (ties broken by chain index), and the
-// sorted copy of their keys.
-__global__ void k_rank_new(const NSState* st, const double* __restrict__ new_logL, int K,
-                           int* __restrict__ rank, double* __restrict__ snew) {
+// rank of each replacement among the K replacements (ties broken by chain index), and the sorted copy of
+// their keys.  Counting over a 2-D grid: block (bx, by) compares its 256 replacements with the by-th tile of
+// 256 keys and adds its partial counts (integer atomics: order-independent); k_rank_scatter then places the keys.
+constexpr int kRankTile = 256;
+__global__ void __launch_bounds__(kRankTile) k_rank_count(const NSState* st, const double* __restrict__ new_logL, int K,
+                                                          int* __restrict__ rank) {
     if (st->done) return;
-    extern __shared__ double tile[];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const double key = (q < K) ? new_logL[q] : 0.0;
+    __shared__ double tile[kRankTile];
+    const int q = blockIdx.x * kRankTile + threadIdx.x;
+    const int base = blockIdx.y * kRankTile;
+    const int i = base + threadIdx.x;
+    tile[threadIdx.x] = (i < K) ? new_logL[i] : INFINITY;
+    __syncthreads();
+    if (q >= K) return;
+    const double key = new_logL[q];
+    const int lim = min(kRankTile, K - base);
     int r = 0;
-    for (int base = 0; base < K; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        tile[threadIdx.x] = (i < K) ? new_logL[i] : INFINITY;
-        __syncthreads();
-        const int lim = min((int)blockDim.x, K - base);
-        for (int t = 0; t < lim; ++t) {
-            const double o = tile[t];
-            r += (o < key) || (o == key && base + t < q);
-        }
-        __syncthreads();
+#pragma unroll 8
+    for (int t = 0; t < lim; ++t) {
+        const double o = tile[t];
+        r += (o < key) || (o == key && base + t < q);
     }
-    if (q < K) {
-        rank[q] = r;
-        snew[r] = key;
-    }
+    if (r) atomicAdd(rank + q, r);
+}
+__global__ void k_rank_scatter(const NSState* st, const double* __restrict__ new_logL, int K, const int* __restrict__ rank,
+                               double* __restrict__ snew) {
+    if (st->done) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < K) snew[rank[q]] = new_logL[q];
 }
 
 struct MergeParams {
@@ -429,17 +434,30 @@ __device__ __forceinline__ int upper_bound_d(const double* a, int n, double v) {
 
 // One thread per live-set position.  Threads [0,K) own a dead point + its replacement,
 // threads [K,N) own a survivor.  bisect-right semantics: a replacement goes after equal keys.
+// The rows themselves (nested_samples.extend(worst), then the slot is overwritten by the replacement) are moved
+// by the threads beyond N, one coordinate each, so that consecutive threads touch consecutive doubles.
 __global__ void k_merge_commit(const MergeParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = p.N, K = p.K;
-    if (i >= N) return;
     if (p.st->done) {              // run finished: keep the order valid in the other buffer
-        p.order_out[i] = p.order_in[i];
-        p.skeys_out[i] = p.skeys_in[i];
+        if (i < N) {
+            p.order_out[i] = p.order_in[i];
+            p.skeys_out[i] = p.skeys_in[i];
+        }
         return;
     }
     // k_ns_accumulate of this batch already advanced the counters
     const long long dead0 = p.st->iteration - K, ins0 = p.st->n_ins - K;
+    if (i >= N) {
+        const int w = i - N;
+        if (w >= K * p.Dp) return;
+        const int r = w / p.Dp, d = w % p.Dp;
+        const int slot = p.order_in[r];
+        double* l = p.live_x + (size_t)slot * p.Dp + d;
+        p.dead_x[(size_t)(dead0 + r) * p.Dp + d] = *l;
+        *l = p.new_x[w];
+        return;
+    }
     if (i >= K) {
         const double key = p.skeys_in[i];
         const int pos = (i - K) + lower_bound_d(p.snew, K, key);
@@ -453,14 +471,6 @@ __global__ void k_merge_commit(const MergeParams p) {
         p.order_out[pos] = slot;
         p.skeys_out[pos] = key;
         p.insertion[ins0 + i] = (double)nle / (double)(N - K);
-        // nested_samples.extend(worst) then overwrite the slot with the replacement
-        double* lrow = p.live_x + (size_t)slot * p.Dp;
-        double* drow = p.dead_x + (size_t)(dead0 + i) * p.Dp;
-        const double* nrow = p.new_x + (size_t)i * p.Dp;
-        for (int d = 0; d < p.Dp; ++d) {
-            drow[d] = lrow[d];
-            lrow[d] = nrow[d];
-        }
         p.dead_logL[dead0 + i] = p.live_logL[slot];
         p.dead_logP[dead0 + i] = p.live_logP[slot];
         p.live_logL[slot] = key;
