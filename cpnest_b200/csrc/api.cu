@@ -336,7 +336,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     CK(cudaMemcpy(c->d_lo, lo, D * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_hi, hi, D * sizeof(double), cudaMemcpyHostToDevice));
     if (nb) CK(cudaMemcpy(c->d_blob, blob, nb * sizeof(double), cudaMemcpyHostToDevice));
-    if (dalloc(&c->d_x, (size_t)N * Dp) || dalloc(&c->d_logL, N) || dalloc(&c->d_logP, N)) return 1;
+    if (dalloc(&c->d_x, (size_t)N * Dp + kRowSlack) || dalloc(&c->d_logL, N) || dalloc(&c->d_logP, N)) return 1;
     for (int b = 0; b < 2; ++b)
         if (dalloc(&c->d_order[b], N) || dalloc(&c->d_skeys[b], N)) return 1;
     c->Npad = 1;
@@ -356,8 +356,8 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
-        dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigvec[0], (size_t)D * Dp) || dalloc(&c->d_eigscale[0], D) ||
-        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp) || dalloc(&c->d_eigscale[1], D) ||
+        dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigvec[0], (size_t)D * Dp + kRowSlack) || dalloc(&c->d_eigscale[0], D) ||
+        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp + kRowSlack) || dalloc(&c->d_eigscale[1], D) ||
         dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) ||
         dalloc(&c->d_covbuf[0], (size_t)D * D) || dalloc(&c->d_covbuf[1], (size_t)D * D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
         dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))

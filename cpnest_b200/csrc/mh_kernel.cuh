@@ -21,6 +21,7 @@ namespace cpn {
 
 constexpr int kMHThreads = 128;
 constexpr int kMaxPeers = 8;
+constexpr int kRowSlack = 256;    // doubles of slack behind row arrays the chain kernels gather from (see gather_rows)
 
 enum StartMode { START_SURVIVOR = 0, START_SELF = 1, START_GIVEN = 2 };
 
@@ -168,22 +169,23 @@ struct DrawFeed {
     }
 };
 
-// the three rows a production step gathers (kinds that need fewer re-read row i0: an L1 hit).  Slots beyond D
-// are never loaded: the buffers are zeroed once and stay zero, so no select follows the loads.
+// the three rows a production step gathers (kinds that need fewer re-read row i0: an L1 hit).  Straight-line:
+// every slot is loaded, also the slots beyond D of the last lanes, which then read the head of the following row
+// (the arrays carry kRowSlack doubles of slack at their end).  Those values are finite and never used: the box
+// test (+-inf bounds), the functors (valid_dim masks) and the final store ignore slots beyond D.
 template <int G, int E>
 __device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, const StepIn& s, double (&r0)[E],
                                             double (&r1)[E], double (&r2)[E]) {
     const bool eig = s.kind == CPN_EIGEN;
-    const double* b0 = (eig ? p.eig_vec : p.ens_x) + (size_t)s.i0 * p.Dp + g.lane;
-    const double* b1 = p.ens_x + (size_t)s.i1 * p.Dp + g.lane;
-    const double* b2 = p.ens_x + (size_t)s.i2 * p.Dp + g.lane;
-    const bool two = (s.kind == CPN_WALK) | (s.kind == CPN_DE), three = s.kind == CPN_WALK;
+    const unsigned Dp = (unsigned)p.Dp, lane = (unsigned)g.lane;
+    const double* b0 = (eig ? p.eig_vec : p.ens_x) + (s.i0 * Dp + lane);
+    const double* b1 = p.ens_x + (s.i1 * Dp + lane);
+    const double* b2 = p.ens_x + (s.i2 * Dp + lane);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const bool in = g.lane + e * G < p.D;
-        if (in) r0[e] = __ldg(b0 + e * G);
-        if (two && in) r1[e] = __ldg(b1 + e * G);
-        if (three && in) r2[e] = __ldg(b2 + e * G);
+        r0[e] = __ldg(b0 + e * G);
+        r1[e] = __ldg(b1 + e * G);
+        r2[e] = __ldg(b2 + e * G);
     }
 }
 
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
     m.blob = p.blob;
     m.D = p.D;
     m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
+    Model::prepare(m);
 
     const int D = p.D;
     const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;

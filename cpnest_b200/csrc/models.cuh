@@ -19,13 +19,18 @@ struct ModelCtx {
     const double* blob;   // functor parameters (device)
     int D;                // dimension
     double* scratch;      // per-chain shared-memory scratch, kScratchRows * Dp doubles (functors with kScratch)
+    double par[4];        // functor parameters kept in registers by Model::prepare (read once per chain, not per step)
+};
+
+struct ModelBase {
+    static __device__ __forceinline__ void prepare(ModelCtx&) {}
 };
 
 template <int G, int E>
 __device__ __forceinline__ bool valid_dim(const Group<G>& g, int e, int D) { return g.lane + e * G < D; }
 
 // ---- flat prior, model.py:66-82 -------------------------------------------------------------
-struct FlatPrior {
+struct FlatPrior : ModelBase {
     static constexpr bool kFlatPrior = true;
     template <int G, int E>
     static __device__ __forceinline__ double log_prior(const Group<G>&, const double (&)[E], const ModelCtx&) {
@@ -49,9 +54,12 @@ struct FlatPrior {
 struct GaussIid : FlatPrior {
     static constexpr bool kScratch = false;
     static constexpr bool kCheap = true;    // evaluated every step: cheaper than asking whether any chain needs it
+    static __device__ __forceinline__ void prepare(ModelCtx& m) {
+        m.par[0] = m.blob[0]; m.par[1] = m.blob[1]; m.par[2] = m.blob[2];
+    }
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
-        const double mu = m.blob[0], inv_sigma = m.blob[1], c = m.blob[2];   // c = -log(sigma) - log(2pi)/2
+        const double mu = m.par[0], inv_sigma = m.par[1], c = m.par[2];   // c = -log(sigma) - log(2pi)/2
         double acc = 0.0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -63,7 +71,7 @@ struct GaussIid : FlatPrior {
     }
     template <int G, int E>
     static __device__ __forceinline__ void grad_log_likelihood(const Group<G>&, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
-        const double mu = m.blob[0], inv_sigma = m.blob[1];
+        const double mu = m.par[0], inv_sigma = m.par[1];
 #pragma unroll
         for (int e = 0; e < E; ++e) gr[e] = -(x[e] - mu) * inv_sigma * inv_sigma;
     }
@@ -275,7 +283,7 @@ struct Ring : FlatPrior {
 };
 
 // ---- (mean, sigma) Gaussian with a 1/sigma prior: tests/test_gaussian.py:15-20 ----------------
-struct GaussMeanSigma {
+struct GaussMeanSigma : ModelBase {
     static constexpr bool kFlatPrior = false;
     static constexpr bool kScratch = false;
     static constexpr bool kCheap = true;
@@ -310,7 +318,7 @@ struct GaussMeanSigma {
 
 // ---- two-component mixture over a data vector: examples/gaussianmixture.py:22-31 ;
 //      blob = {n_data, data[n_data]} ; parameters (mean1, sigma1, mean2, sigma2, weight) ----------
-struct GaussMixture {
+struct GaussMixture : ModelBase {
     static constexpr bool kFlatPrior = false;
     static constexpr bool kScratch = false;
     static constexpr bool kCheap = false;
