@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_points(const EvalParams p
     m.D = p.D;
     m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
     Model::prepare(m);
+    set_valid_mask<G, E>(g, m);
     const int D = p.D;
     double x[E];
     double logP = CPN_NEG_INF;

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
     m.D = p.D;
     m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
     Model::prepare(m);
+    set_valid_mask<G, E>(g, m);
 
     const int D = p.D;
     const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;

@@ -6,6 +6,7 @@
 // x[d / G] of lane d % G.  log_likelihood/log_prior return the same value on every lane.
 #pragma once
 #include <math.h>
+#include <stdint.h>
 #include "group.cuh"
 
 namespace cpn {
@@ -20,7 +21,18 @@ struct ModelCtx {
     int D;                // dimension
     double* scratch;      // per-chain shared-memory scratch, kScratchRows * Dp doubles (functors with kScratch)
     double par[4];        // functor parameters kept in registers by Model::prepare (read once per chain, not per step)
+    uint32_t vmsk[8];     // per slot e: all ones if coordinate lane + e*G exists (< D), else 0 (set by set_valid_mask)
 };
+
+template <int G, int E>
+__device__ __forceinline__ void set_valid_mask(const Group<G>& g, ModelCtx& m) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) m.vmsk[e] = (g.lane + e * G < m.D) ? 0xffffffffu : 0u;
+}
+// v if slot e holds a coordinate, else +0.0: two bit-ANDs with a register mask
+__device__ __forceinline__ double masked(const ModelCtx& m, int e, double v) {
+    return __hiloint2double(__double2hiint(v) & (int)m.vmsk[e], __double2loint(v) & (int)m.vmsk[e]);
+}
 
 struct ModelBase {
     static __device__ __forceinline__ void prepare(ModelCtx&) {}
@@ -64,8 +76,7 @@ struct GaussIid : FlatPrior {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             double t = (x[e] - mu) * inv_sigma;
-            double term = -0.5 * t * t + c;
-            acc += valid_dim<G, E>(g, e, m.D) ? term : 0.0;
+            acc += masked(m, e, fma(-0.5 * t, t, c));
         }
         return g.sum(acc);
     }
@@ -233,9 +244,8 @@ struct Ackley : FlatPrior {
         double s2 = 0.0, sc = 0.0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            bool ok = valid_dim<G, E>(g, e, m.D);
-            s2 += ok ? x[e] * x[e] : 0.0;
-            sc += ok ? cos(2.0 * 3.14159265358979323846 * x[e]) : 0.0;
+            s2 += masked(m, e, x[e] * x[e]);
+            sc += masked(m, e, cos(2.0 * 3.14159265358979323846 * x[e]));
         }
         s2 = g.sum(s2);
         sc = g.sum(sc);

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
     m.D = p.D;
     m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
     Model::prepare(m);
+    set_valid_mask<G, E>(g, m);
 
     const int D = p.D;
     const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;

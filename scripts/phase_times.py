@@ -6,10 +6,11 @@ sys.path.insert(0, ".")
 from cpnest_b200.engine import Engine
 from cpnest_b200.proposal import DefaultProposalCycle
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 4704
+lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 N = 10000
 np.random.seed(1234)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-e = Engine("gaussian_iid", [[-10, 10]] * 50, nlive=N, maxmcmc=5000, seed=1234)
+e = Engine("gaussian_iid", [[-10, 10]] * 50, nlive=N, maxmcmc=5000, seed=1234, lanes=lanes)
 e.set_stream(stream.cuda_stream)
 e.set_cycle(DefaultProposalCycle().device_cycle())
 e.init_prior()
@@ -26,5 +27,5 @@ for i in range(n):
 torch.cuda.synchronize()
 t = np.array([[ev[i][k].elapsed_time(ev[i][k + 1]) for k in range(3)] for i in range(n)])
 tot = ev[0][0].elapsed_time(ev[n - 1][3]) / n
-print("K=%d mean ms: select %.3f evolve %.3f insert %.3f | sum %.3f, wall/step %.3f" % (K, *t.mean(0), t.mean(0).sum(), tot))
+print("lanes=%d " % lanes + "K=%d mean ms: select %.3f evolve %.3f insert %.3f | sum %.3f, wall/step %.3f" % (K, *t.mean(0), t.mean(0).sum(), tot))
 print("per-step evolve:", np.round(t[:12, 1], 3), "select:", np.round(t[:12, 0], 3), "insert:", np.round(t[:12, 2], 3))

@@ -7,7 +7,7 @@ from cpnest_b200.engine import Engine
 from cpnest_b200.proposal import DefaultProposalCycle
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-K = int(sys.argv[2]) if len(sys.argv) > 2 else 2500
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 4704
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 lanes = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 np.random.seed(1234)
