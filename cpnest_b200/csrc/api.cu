@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <string>
@@ -81,6 +83,9 @@ struct cpn_ctx {
     int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_new_ne, *d_new_nc, *d_rank;
     double *d_rho, *d_rho2;
     double* d_snew;
+    int *d_iota, *d_sorted_idx;     // large batches: the replacements are ranked with a stable radix sort (cub)
+    void* d_cub_tmp;
+    size_t cub_tmp_bytes;
     double *d_start_x, *d_start_logL, *d_start_logP;
     double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
     // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
@@ -353,6 +358,18 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
     if (dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
+    {
+        std::vector<int> iota(N);
+        for (int i = 0; i < N; ++i) iota[i] = i;
+        if (dalloc(&c->d_iota, N) || dalloc(&c->d_sorted_idx, N)) return 1;
+        CK(cudaMemcpy(c->d_iota, iota.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+        c->cub_tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, c->cub_tmp_bytes, (const double*)nullptr, (double*)nullptr, (const int*)nullptr,
+                                           (int*)nullptr, N));
+        char* tmp;
+        if (dalloc(&tmp, c->cub_tmp_bytes + 256)) return 1;
+        c->d_cub_tmp = tmp;
+    }
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
@@ -412,7 +429,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->side);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
-                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_start_x, c->d_start_logL,
+                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_iota, c->d_sorted_idx, c->d_cub_tmp, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
@@ -726,7 +743,7 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, c->N, &G, &E)) return 1;
         if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
         CKL();
-        k_chain_corr<<<c->D + 2, 256, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
+        k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
                                                       c->d_new_x, c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc,
                                                       c->d_new_evals);
         k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N, c->d_rho, c->d_rho2, c->D);   // coordinates only: logL is unconstrained here
@@ -787,10 +804,10 @@ extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
     CK(cudaSetDevice(c->cfg.device));
     // Refresh cadence of the reference: every poolsize//4 chains (sampler.py:252-254).  The refresh runs
-    // on the side stream beside the chain kernels of two batches and is adopted by the batch after those
+    // on the side stream beside the chain kernels of three batches and is adopted by the batch after those
     // (fixed latency, so the schedule - and with it every result - is deterministic); one refresh is in
     // flight at a time.
-    if (c->eig_pending && ++c->eig_pending_age >= 2)
+    if (c->eig_pending && ++c->eig_pending_age >= 3)
         if (adopt_pending_stats(c)) return 1;
     // Beyond nlive/4 chains the cadence follows what the statistics are used for: replacing K of N points shrinks
     // each axis of the ensemble by exp(-K/(N D)), so the jump scales sqrt|lambda_i| drift by 5% only after
@@ -903,7 +920,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     if (!c->staged_external) {
         // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
         // control, and the batch counters
-        k_chain_corr<<<c->D + 2, 256, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
+        k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
                                                       c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc, c->d_new_evals);
         c->launches += 1;
         if (c->cfg.sampler == CPN_SAMPLER_SLICE) {
@@ -914,11 +931,18 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
             c->launches += 1;
         }
     }
-    CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
-    {
+    if (K <= 20000) {
+        // K^2 comparisons over a 2-D grid: fewer, shorter launches than a sort at this size
+        CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
         const int nt = (K + kRankTile - 1) / kRankTile;
         k_rank_count<<<dim3(nt, nt), kRankTile, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank);
         k_rank_scatter<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
+    } else {
+        // stable LSD radix sort of (logL, chain index): equal keys keep the chain order, the same rank as the counting rule
+        size_t bytes = c->cub_tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, (const double*)c->d_new_logL, c->d_snew, (const int*)c->d_iota,
+                                           c->d_sorted_idx, K, 0, 64, c->stream));
+        k_rank_from_sorted<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_sorted_idx, K, c->d_rank);
     }
     MergeParams m;
     memset(&m, 0, sizeof m);
@@ -1189,7 +1213,7 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
     k_unpack_records<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(d_rec, K, D, Dp, c->d_start_x, c->d_start_logL, c->d_start_logP);
     // the host protocol is served by one GPU (n_out = 1)
     if (launch_chains(c, K, 0, K, START_GIVEN, 0, true, logLmin, std::max(1, std::min(nmcmc, c->cfg.maxmcmc)), 1)) return 1;
-    k_batch_counters<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_steps, c->d_new_acc, c->d_new_evals);
+    k_batch_counters<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, K, c->d_new_steps, c->d_new_acc, c->d_new_evals);
     k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K, nullptr, nullptr, 0);
     if (c->cfg.sampler == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_ne, c->d_new_nc);
     if (slots) {

@@ -112,7 +112,6 @@ struct AccParams {
 __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p) {
     __shared__ LSE sh_lse[kAccThreads];
     __shared__ double sh_scan[kAccThreads];
-    __shared__ double sh_carry;
     NSState* st = p.st;
     const int tid = threadIdx.x;
     if (!p.final_sweep) {
@@ -142,36 +141,33 @@ __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p
         }
         logw_end = logw0 + logt;
     } else {
-        // per-point shrinkage -1/(N-j) (the reference's final-sweep rule, NestedSampling.py:474-476)
-        if (tid == 0) sh_carry = 0.0;
-        __syncthreads();
-        for (int base = 0; base < K; base += kAccThreads) {
-            const int j = base + tid;
-            const bool in = j < K;
-            const double logt = in ? -1.0 / (double)(N - j) : 0.0;
-            double tile_total;
-            const double excl = block_exclusive_scan(logt, sh_scan, &tile_total);
-            const double carry = sh_carry;
-            if (in) {
-                const double logw_j = logw0 + (carry + excl);
-                const double logL = p.skeys[j];
-                const double Wt = logw_j + logL + log1p(-exp(logt));
-                // the reference leaves info at 0 on the increment that makes logZ finite, i.e. its
-                // recurrence starts from info + logZ = Wt rather than logL (NestedSampling.py:125-128)
-                bool first = false;
-                if (!(logZ0 > -INFINITY) && Wt > -INFINITY) {
-                    if (j == 0) first = true;
-                    else first = !(p.skeys[j - 1] > -INFINITY);
-                }
-                acc.push(Wt, first ? Wt : logL);
-                p.hist_logL[hist0 + j] = logL;
-                p.hist_logvol[hist0 + j] = logw_j + logt;
+        // per-point shrinkage -1/(N-j) (the reference's final-sweep rule, NestedSampling.py:474-476).  Thread t owns
+        // the consecutive points [t*C, (t+1)*C): a serial prefix inside the chunk, one block scan over the chunk totals
+        const int C = (K + kAccThreads - 1) / kAccThreads;
+        const int j0 = min(tid * C, K), j1 = min(j0 + C, K);
+        double mine = 0.0;
+        for (int j = j0; j < j1; ++j) mine += -1.0 / (double)(N - j);
+        double total;
+        const double before = block_exclusive_scan(mine, sh_scan, &total);
+        double run = before;
+        for (int j = j0; j < j1; ++j) {
+            const double logt = -1.0 / (double)(N - j);
+            const double logw_j = logw0 + run;
+            const double logL = p.skeys[j];
+            const double Wt = logw_j + logL + log1p(-exp(logt));
+            // the reference leaves info at 0 on the increment that makes logZ finite, i.e. its
+            // recurrence starts from info + logZ = Wt rather than logL (NestedSampling.py:125-128)
+            bool first = false;
+            if (!(logZ0 > -INFINITY) && Wt > -INFINITY) {
+                if (j == 0) first = true;
+                else first = !(p.skeys[j - 1] > -INFINITY);
             }
-            __syncthreads();
-            if (tid == 0) sh_carry = carry + tile_total;
-            __syncthreads();
+            acc.push(Wt, first ? Wt : logL);
+            p.hist_logL[hist0 + j] = logL;
+            p.hist_logvol[hist0 + j] = logw_j + logt;
+            run += logt;
         }
-        logw_end = logw0 + sh_carry;
+        logw_end = logw0 + total;
     }
     const LSE tot = block_reduce_lse(acc, sh_lse);
     if (tid != 0) return;
@@ -262,11 +258,12 @@ __global__ void k_adapt_nmcmc(NSState* st, int chains, const double* rho, double
 // Sums of the per-chain outcome arrays of a launch -> st->batch[] = {steps, accepted, evals, failed
 // chains}.  Integer sums: the result does not depend on the order, nor on how the chains were split
 // over GPUs.
-__device__ __forceinline__ void block_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals) {
-    __shared__ unsigned long long shc[4][256];
+constexpr int kCorrThreads = 1024;    // block size of k_chain_corr / k_batch_counters (fixed: the reduction shape must not vary)
+__device__ __forceinline__ void block_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals,
+                                                     unsigned long long (*shc)[kCorrThreads]) {
     const int tid = threadIdx.x;
     unsigned long long a[4] = {0, 0, 0, 0};
-    for (int j = tid; j < K; j += 256) {
+    for (int j = tid; j < K; j += kCorrThreads) {
         a[0] += (unsigned long long)steps[j];
         a[1] += (unsigned long long)acc[j];
         a[2] += (unsigned long long)(evals != nullptr ? evals[j] : 0);
@@ -274,7 +271,7 @@ __device__ __forceinline__ void block_batch_counters(NSState* st, int K, const i
     }
     for (int k = 0; k < 4; ++k) shc[k][tid] = a[k];
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
+    for (int w = kCorrThreads / 2; w > 0; w >>= 1) {
         if (tid < w)
             for (int k = 0; k < 4; ++k) shc[k][tid] += shc[k][tid + w];
         __syncthreads();
@@ -282,8 +279,9 @@ __device__ __forceinline__ void block_batch_counters(NSState* st, int K, const i
     if (tid == 0)
         for (int k = 0; k < 4; ++k) st->batch[k] = shc[k][0];
 }
-__global__ void __launch_bounds__(256) k_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals) {
-    block_batch_counters(st, K, steps, acc, evals);
+__global__ void __launch_bounds__(kCorrThreads) k_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals) {
+    __shared__ unsigned long long shc[4][kCorrThreads];
+    block_batch_counters(st, K, steps, acc, evals, shc);
 }
 
 // SliceSampler.adapt_length_scale (sampler.py:429-437): mu *= 2 Ne / (Ne + Nc).  The reference applies it per
@@ -323,23 +321,23 @@ __global__ void k_adapt_hmc_dt(NSState* st) {
 
 // corr_d(start, end) across the K chains of the batch, d in [0, D] (d == D is logL).
 // One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
-__global__ void __launch_bounds__(256) k_chain_corr(NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,
+__global__ void __launch_bounds__(kCorrThreads) k_chain_corr(NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,
                                                     const double* __restrict__ live_x, const double* __restrict__ live_logL,
                                                     const double* __restrict__ new_x, const double* __restrict__ new_logL,
                                                     double* __restrict__ rho, const int* steps, const int* acc, const int* evals) {
     if (st->done) return;
+    __shared__ double sh[5][kCorrThreads];
     if (blockIdx.x == D + 1) {
-        block_batch_counters(st, K, steps, acc, evals);
+        block_batch_counters(st, K, steps, acc, evals, reinterpret_cast<unsigned long long (*)[kCorrThreads]>(&sh[0][0]));
         return;
     }
-    __shared__ double sh[5][256];
     const int d = blockIdx.x, tid = threadIdx.x;
     // shift by the first chain's values to keep the sums well conditioned
     const int s0 = start_slot[0];
     const double cs = (d < D) ? live_x[(size_t)s0 * Dp + d] : live_logL[s0];
     const double ce = (d < D) ? new_x[d] : new_logL[0];
     double a[5] = {0, 0, 0, 0, 0};
-    for (int j = tid; j < K; j += 256) {
+    for (int j = tid; j < K; j += kCorrThreads) {
         const int sl = start_slot[j];
         const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
         const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
@@ -347,7 +345,7 @@ __global__ void __launch_bounds__(256) k_chain_corr(NSState* st, int K, int D, i
     }
     for (int k = 0; k < 5; ++k) sh[k][tid] = a[k];
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
+    for (int w = kCorrThreads / 2; w > 0; w >>= 1) {
         if (tid < w)
             for (int k = 0; k < 5; ++k) sh[k][tid] += sh[k][tid + w];
         __syncthreads();
@@ -389,6 +387,12 @@ __global__ void k_rank_scatter(const NSState* st, const double* __restrict__ new
     if (st->done) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < K) snew[rank[q]] = new_logL[q];
+}
+
+// rank[chain] = position of the chain's key in the sorted order (large batches, after the radix sort)
+__global__ void k_rank_from_sorted(const int* __restrict__ sorted_idx, int K, int* __restrict__ rank) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < K) rank[sorted_idx[r]] = r;
 }
 
 struct MergeParams {

@@ -7,17 +7,18 @@ from cpnest_b200.engine import Engine
 from cpnest_b200.proposal import DefaultProposalCycle
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 4704
 lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-N = 10000
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
 np.random.seed(1234)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 e = Engine("gaussian_iid", [[-10, 10]] * 50, nlive=N, maxmcmc=5000, seed=1234, lanes=lanes)
 e.set_stream(stream.cuda_stream)
 e.set_cycle(DefaultProposalCycle().device_cycle())
 e.init_prior()
-for _ in range(60):
+warm = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+for _ in range(warm):
     e.ns_step(K)
 torch.cuda.synchronize()
-n = 60
+n = int(sys.argv[5]) if len(sys.argv) > 5 else 60
 ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n)]
 for i in range(n):
     ev[i][0].record(stream); e.select_and_accumulate(K)
