@@ -362,21 +362,23 @@ def main():
     req, rep, stp, acc_, slots = req_t.numpy(), rep_t.numpy(), st_t.numpy(), ac_t.numpy(), sl_t.numpy()
     # the device pool mirrors the host live set slot by slot
     eng.set_live(live)
-    host_slots = np.arange(N)                           # live[i] sits in device pool slot host_slots[i]
     nm = max(20, s1["nmcmc"])                           # the chain length the device-resident run settled on
     e2e_evals = 0
 
     def host_step():
-        nonlocal live, host_slots, e2e_evals
-        order = np.argsort(live[:, DIM], kind="stable")
-        live = live[order]
-        host_slots = host_slots[order]
-        logLmin = live[K - 1, DIM]
-        starts = rs.randint(K, N, size=K)
-        req[:] = live[starts]                           # requests: start points drawn among the survivors
-        slots[:] = host_slots[:K]                       # the K worst slots are overwritten by the replies
+        # the caller's side of the protocol, as NestedSampler.consume_sample does it (NestedSampling.py:318-366): pick the
+        # K worst live points and the threshold, send K requests, put the K replies in their place.  The live set stays
+        # where it is (row i <-> device pool slot i); a partial selection replaces the reference's sorted list.
+        nonlocal e2e_evals
+        logL = live[:, DIM]
+        part = np.argpartition(logL, K - 1)
+        worst, surv = part[:K], part[K:]
+        logLmin = logL[worst].max()
+        starts = surv[rs.randint(0, N - K, size=K)]
+        np.take(live, starts, axis=0, out=req)          # requests: start points drawn among the survivors
+        slots[:] = worst                                # the K worst slots are overwritten by the replies
         eng.evolve_host(req, logLmin, nm, slots=slots, replies=rep, steps=stp, accepted=acc_)
-        live[:K] = rep
+        live[worst] = rep
 
     for _ in range(args.warmup):
         host_step()
