@@ -42,7 +42,7 @@ class cpn_state(C.Structure):
 
 
 FUNCTORS = dict(gaussian_iid=0, gaussian_corr=1, eggbox=2, rosenbrock=3, ackley=4, ring=5,
-                gaussian_mean_sigma=6, gaussian_mixture=7)
+                gaussian_mean_sigma=6, gaussian_mixture=7, user=8)
 WALK, STRETCH, DE, EIGEN = 0, 1, 2, 3
 NS_SEQUENTIAL, NS_REFERENCE = 0, 1
 SAMPLERS = dict(mh=0, slice=1, hmc=2)
@@ -62,6 +62,7 @@ SIGNATURES = {
     "cpn_set_cycle": (C.c_int, [_vp, _P(C.c_uint8), C.c_int32]),
     "cpn_set_slice_cycle": (C.c_int, [_vp, _P(C.c_uint8), C.c_int32]),
     "cpn_set_slice_mu": (C.c_int, [_vp, C.c_double]),
+    "cpn_set_user_functor": (C.c_int, [_vp, C.c_char_p, _P(C.c_char_p), C.c_int32]),
     "cpn_set_seed": (C.c_int, [_vp, C.c_uint64]),
     "cpn_init_prior": (C.c_int, [_vp]),
     "cpn_set_live": (C.c_int, [_vp, _dp, C.c_int32]),

@@ -62,7 +62,7 @@ def build(force=False, jobs=None, verbose=True):
         print("cpnest_b200.build: compiling %d translation units for sm_100a with %d jobs" % (len(srcs), jobs), flush=True)
     with cf.ThreadPoolExecutor(jobs) as ex:
         objs = list(ex.map(_compile, srcs))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

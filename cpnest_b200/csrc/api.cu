@@ -10,6 +10,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "launch.h"
 #include "mh_kernel.cuh"
 #include "ns_kernels.cuh"
+#include "rtc.h"
 #include "hmc_kernel.cuh"
 #include "slice_kernel.cuh"
 
@@ -48,16 +50,16 @@ typedef int (*slice_fn)(int, int, int, const SliceParams&, cudaStream_t);
 typedef int (*hmc_fn)(int, int, int, const HMCParams&, cudaStream_t);
 static const hmc_fn kHMC[CPN_NUM_FUNCTORS] = {launch_hmc_gauss_iid, launch_hmc_gauss_corr, launch_hmc_eggbox,
                                               launch_hmc_rosenbrock, launch_hmc_ackley, launch_hmc_ring,
-                                              launch_hmc_gauss_mean_sigma, launch_hmc_gauss_mixture};
+                                              launch_hmc_gauss_mean_sigma, launch_hmc_gauss_mixture, nullptr};
 static const slice_fn kSlice[CPN_NUM_FUNCTORS] = {launch_slice_gauss_iid, launch_slice_gauss_corr, launch_slice_eggbox,
                                                   launch_slice_rosenbrock, launch_slice_ackley, launch_slice_ring,
-                                                  launch_slice_gauss_mean_sigma, launch_slice_gauss_mixture};
+                                                  launch_slice_gauss_mean_sigma, launch_slice_gauss_mixture, nullptr};
 static const mh_fn kMH[CPN_NUM_FUNCTORS] = {launch_mh_gauss_iid, launch_mh_gauss_corr, launch_mh_eggbox,
                                             launch_mh_rosenbrock, launch_mh_ackley, launch_mh_ring,
-                                            launch_mh_gauss_mean_sigma, launch_mh_gauss_mixture};
+                                            launch_mh_gauss_mean_sigma, launch_mh_gauss_mixture, nullptr};
 static const eval_fn kEval[CPN_NUM_FUNCTORS] = {launch_eval_gauss_iid, launch_eval_gauss_corr, launch_eval_eggbox,
                                                 launch_eval_rosenbrock, launch_eval_ackley, launch_eval_ring,
-                                                launch_eval_gauss_mean_sigma, launch_eval_gauss_mixture};
+                                                launch_eval_gauss_mean_sigma, launch_eval_gauss_mixture, nullptr};
 
 struct cpn_ctx {
     cpn_config cfg;
@@ -116,6 +118,8 @@ struct cpn_ctx {
     int* d_sweeps;
     NSState* h_state;           // pinned
     cudaEvent_t ev;
+    RtcModule* rtc;             // kernels compiled at run time around a user-written functor (CPN_USER)
+    bool user_flat_prior;
     bool live_ready;
     bool staged_external;       // replacements were injected by cpn_stage_replacements
 };
@@ -167,6 +171,46 @@ static int pick_config(int D, int lanes, int functor, long long chains, int* G, 
     }
     if (!bestG) return fail("dim=%d exceeds the largest kernel configuration (256)", D);
     *G = bestG; *E = bestE;
+    return 0;
+}
+
+// ---- kernel dispatch: built-in functors through the launcher tables, CPN_USER through the NVRTC module -----------
+static int user_launch(cpn_ctx* c, const char* kind, int G, int E, const void* params, int n, int Dp, int threads) {
+    if (n <= 0) return 0;
+    const int cpb = threads / G;
+    const int nb = (n + cpb - 1) / cpb;
+    const size_t sm = (size_t)cpb * kScratchRows * Dp * sizeof(double);
+    char err[4096];
+    if (rtc_launch(c->rtc, kind, G, E, params, nb, threads, sm, c->stream, err, sizeof err)) return fail("%s", err);
+    return 0;
+}
+static int run_eval(cpn_ctx* c, int G, int E, const EvalParams& p) {
+    if (c->cfg.functor == CPN_USER) return user_launch(c, "eval", G, E, &p, p.n, p.Dp, kEvalThreads);
+    if (kEval[c->cfg.functor](G, E, p, c->stream)) return fail("no eval kernel for G=%d E=%d", G, E);
+    return 0;
+}
+static int run_mh(cpn_ctx* c, int G, int E, int replay, const MHParams& p) {
+    if (c->cfg.functor == CPN_USER) {
+        if (replay) return fail("replay entry points are not available for a user functor");
+        return user_launch(c, "mh", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
+    }
+    if (kMH[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    return 0;
+}
+static int run_slice(cpn_ctx* c, int G, int E, int replay, const SliceParams& p) {
+    if (c->cfg.functor == CPN_USER) {
+        if (replay) return fail("replay entry points are not available for a user functor");
+        return user_launch(c, "slice", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
+    }
+    if (kSlice[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no slice kernel for G=%d E=%d", G, E);
+    return 0;
+}
+static int run_hmc(cpn_ctx* c, int G, int E, int replay, const HMCParams& p) {
+    if (c->cfg.functor == CPN_USER) {
+        if (replay) return fail("replay entry points are not available for a user functor");
+        return user_launch(c, "hmc", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
+    }
+    if (kHMC[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no HMC kernel for G=%d E=%d", G, E);
     return 0;
 }
 
@@ -435,6 +479,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (c->rtc) rtc_destroy(c->rtc);
     if (c->h_state) cudaFreeHost(c->h_state);
     cudaEventDestroy(c->ev);
     cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_cov); cudaEventDestroy(c->ev_eig);
@@ -462,6 +507,45 @@ extern "C" int cpn_set_slice_cycle(cpn_ctx* c, const uint8_t* cycle, int32_t len
     CK(cudaMemcpyAsync(c->d_slice_cycle, cycle, len, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->slice_cycle_len = len;
+    return 0;
+}
+
+// Model.log_likelihood / log_prior written by the user in CUDA C++ (csrc/user_model.cuh states the contract): the chain
+// kernels are instantiated around it with NVRTC for sm_100a, for every lane configuration this context can pick.
+extern "C" int cpn_set_user_functor(cpn_ctx* c, const char* source, const char* const* include_dirs, int32_t n_dirs) {
+    if (!c || !source) return fail("null argument");
+    if (c->cfg.functor != CPN_USER) return fail("cpn_set_user_functor: the context was not created with functor CPN_USER");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaFree(0));                                  // make sure the primary context is current for the driver API
+    std::vector<std::array<int, 2>> cfgs;
+    static const int Gs[] = {1, 4, 8, 16, 32};
+    int gmax = 1;
+    while (gmax < c->D && gmax < 32) gmax <<= 1;
+    if (c->cfg.lanes > 0) {
+        const int e = min_E(c->cfg.lanes, c->D);
+        if (!e) return fail("no kernel configuration with %d lanes per chain covers dim=%d", c->cfg.lanes, c->D);
+        cfgs.push_back({c->cfg.lanes, e});
+    } else {
+        for (int G_ : Gs) {
+            if (G_ > gmax) break;
+            const int e = min_E(G_, c->D);
+            if (e) cfgs.push_back({G_, e});
+        }
+    }
+    bool have = false;
+    for (auto& g : cfgs) have = have || (g[0] == c->G && g[1] == c->E);
+    if (!have) cfgs.push_back({c->G, c->E});
+    int kinds = 1 | 2;                                // eval + MH (the prior burn-in of Sampler.reset runs MH chains)
+    if (c->cfg.sampler == CPN_SAMPLER_SLICE) kinds |= 4;
+    if (c->cfg.sampler == CPN_SAMPLER_HMC) kinds |= 8;
+    std::vector<int> flat;
+    for (auto& g : cfgs) { flat.push_back(g[0]); flat.push_back(g[1]); }
+    char err[8192];
+    err[0] = 0;
+    if (c->rtc) { rtc_destroy(c->rtc); c->rtc = nullptr; }
+    c->rtc = rtc_compile(source, include_dirs, n_dirs, (const int(*)[2])flat.data(), (int)cfgs.size(), kinds, err, sizeof err);
+    if (!c->rtc) return fail("%s", err);
+    c->user_flat_prior = strstr(source, "CPN_USER_HAS_PRIOR") == nullptr;
     return 0;
 }
 
@@ -682,7 +766,7 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
             p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.mu_override = c->h_state->slice_mu;
         }
         if (n_out_override > 0) p.n_out = n_out_override;
-        if (kSlice[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no slice kernel for G=%d E=%d", G, E);
+        if (run_slice(c, G, E, 0, p)) return 1;
     } else if (c->cfg.sampler == CPN_SAMPLER_MH) {
         MHParams p;
         fill_mh(c, &p);
@@ -690,7 +774,7 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
         p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
         if (use_override) { p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; }
         if (n_out_override > 0) p.n_out = n_out_override;
-        if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+        if (run_mh(c, G, E, 0, p)) return 1;
     } else {
         HMCParams p;
         fill_hmc(c, &p);
@@ -701,7 +785,7 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
             p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.dt_override = c->h_state->hmc_dt;
         }
         if (n_out_override > 0) p.n_out = n_out_override;
-        if (kHMC[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no HMC kernel for G=%d E=%d", G, E);
+        if (run_hmc(c, G, E, 0, p)) return 1;
     }
     CKL();
     return 0;
@@ -719,7 +803,7 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
     e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob; e.draw = 1;
     e.seed_lo = (uint32_t)c->cfg.seed; e.seed_hi = (uint32_t)(c->cfg.seed >> 32);
     e.id_base = 0x4000000000000000ull;
-    if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
+    if (run_eval(c, c->G, c->E, e)) return 1;
     CKL();
     // Sampler.reset (sampler.py:129-135): evolve every member with logLmin = -inf so the set follows
     // the prior, adapting the chain length on the way.  Passes are repeated until the product of the
@@ -727,7 +811,8 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
     // (at least 2, at most 24 passes).
     // Functors with the flat prior of Model.log_prior (model.py:66-82) need no burn-in: the uniform
     // draw IS a draw from the prior.
-    const bool flat = !(c->cfg.functor == CPN_GAUSS_MEAN_SIGMA || c->cfg.functor == CPN_GAUSS_MIXTURE);
+    const bool flat = (c->cfg.functor == CPN_USER) ? c->user_flat_prior
+                                                   : !(c->cfg.functor == CPN_GAUSS_MEAN_SIGMA || c->cfg.functor == CPN_GAUSS_MIXTURE);
     double memory = 1.0;
     for (int pass = 0; pass < (flat ? 0 : 24); ++pass) {
         if (cpn_update_ensemble_stats(c)) return 1;
@@ -741,7 +826,7 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         p.cycle_pos0 = pass * 13 % c->cycle_len;
         int G, E;
         if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, c->N, &G, &E)) return 1;
-        if (kMH[c->cfg.functor](G, E, 0, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+        if (run_mh(c, G, E, 0, p)) return 1;
         CKL();
         k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
                                                       c->d_new_x, c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc,
@@ -1248,7 +1333,7 @@ extern "C" int cpn_eval_model(cpn_ctx* c, const double* x, int32_t n, double* lo
     EvalParams e;
     memset(&e, 0, sizeof e);
     e.x = dx; e.logL = dl; e.logP = dp; e.n = n; e.D = D; e.Dp = Dp; e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob;
-    if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
+    if (run_eval(c, c->G, c->E, e)) return 1;
     CKL();
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(logL, dl, n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1271,7 +1356,7 @@ extern "C" int cpn_eval_gradients(cpn_ctx* c, const double* x, int32_t n, double
     memset(&e, 0, sizeof e);
     e.x = dx; e.logL = dl; e.logP = dp; e.n = n; e.D = D; e.Dp = Dp; e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob;
     e.grad_logL = dgl; e.grad_V = dgv;
-    if (kEval[c->cfg.functor](c->G, c->E, e, c->stream)) return fail("no eval kernel for G=%d E=%d", c->G, c->E);
+    if (run_eval(c, c->G, c->E, e)) return 1;
     CKL();
     CK(cudaStreamSynchronize(c->stream));
     std::vector<double> a(xp.size()), b(xp.size());
@@ -1334,7 +1419,7 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
     p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
     p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
     p.tape = dtape; p.compat = compat; p.states = dstates;
-    if (kMH[c->cfg.functor](G, E, 1, p, c->stream)) return fail("no replay kernel for G=%d E=%d", G, E);
+    if (run_mh(c, G, E, 1, p)) return 1;
     CKL();
     CK(cudaStreamSynchronize(c->stream));
     std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
@@ -1358,7 +1443,7 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
 static int slice_scratch_launch(cpn_ctx* c, SliceParams& p, int replay, int lanes, int C) {
     int G, E;
     if (pick_config(c->D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) return 1;
-    if (kSlice[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no slice kernel for G=%d E=%d", G, E);
+    if (run_slice(c, G, E, replay, p)) return 1;
     CKL();
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1468,7 +1553,7 @@ extern "C" int cpn_replay_hmc(cpn_ctx* c, int32_t C, const double* start, const 
     p.tape = dtape; p.tape_off = doff; p.traj = dtraj; p.logJ_out = dlj;
     int G, E;
     if (pick_config(D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) return 1;
-    if (kHMC[c->cfg.functor](G, E, 1, p, c->stream)) return fail("no HMC kernel for G=%d E=%d", G, E);
+    if (run_hmc(c, G, E, 1, p)) return 1;
     CKL();
     CK(cudaStreamSynchronize(c->stream));
     std::vector<double> ox((size_t)C * Dp), ol(C), op(C);

@@ -2,6 +2,7 @@
 // used by the live-set initialisation (Sampler.reset, cpnest/sampler.py:116-126) and by the
 // functor parity entry point.
 #pragma once
+#include "sysinc.cuh"
 #include "group.cuh"
 #include "models.cuh"
 #include "rng.cuh"

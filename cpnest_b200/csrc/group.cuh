@@ -2,7 +2,7 @@
 // E coordinates, coordinate d lives in lane d % G, slot d / G (so a point row in HBM is read
 // with consecutive lanes on consecutive doubles).  All shuffles are issued by the full warp.
 #pragma once
-#include <stdint.h>
+#include "sysinc.cuh"
 
 namespace cpn {
 

@@ -29,7 +29,7 @@
 // Replay: momenta, reflection normals and uniforms come from a tape recorded from the reference; the
 // trajectory is stored and the point picked from the normalised cumulative weights as np.random.choice does.
 #pragma once
-#include <stdint.h>
+#include "sysinc.cuh"
 #include "group.cuh"
 #include "mh_kernel.cuh"
 #include "models.cuh"

@@ -10,7 +10,7 @@
 // the prior MH test, the likelihood functor and the hard constraint logL > logLmin all run in
 // this kernel; nothing goes back to the host between steps.
 #pragma once
-#include <stdint.h>
+#include "sysinc.cuh"
 #include "group.cuh"
 #include "models.cuh"
 #include "rng.cuh"

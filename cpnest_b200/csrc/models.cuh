@@ -5,8 +5,7 @@
 // A functor sees the point distributed over the G lanes of its chain group: coordinate d is
 // x[d / G] of lane d % G.  log_likelihood/log_prior return the same value on every lane.
 #pragma once
-#include <math.h>
-#include <stdint.h>
+#include "sysinc.cuh"
 #include "group.cuh"
 
 namespace cpn {

@@ -3,7 +3,7 @@
 // cpnest/sampler.py:9).  counter = (chain id lo, chain id hi, step, block), key = run seed:
 // a chain's random stream does not depend on the grid shape or on which GPU evolves it.
 #pragma once
-#include <stdint.h>
+#include "sysinc.cuh"
 
 namespace cpn {
 

@@ -9,7 +9,7 @@
 // prior slice level), then shrinkage towards the current point until a point with log_prior above
 // the slice level AND logL > logLmin is found.
 #pragma once
-#include <stdint.h>
+#include "sysinc.cuh"
 #include "group.cuh"
 #include "mh_kernel.cuh"
 #include "models.cuh"

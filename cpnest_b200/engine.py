@@ -33,6 +33,8 @@ def functor_blob(name, dim, params=None):
         return np.concatenate(([float(len(data))], data))
     if name in ("eggbox", "rosenbrock", "ackley", "gaussian_mean_sigma"):
         return np.zeros(0)
+    if name == "user":
+        return np.asarray(params.get("params", []), dtype=np.float64).ravel()
     raise KeyError("unknown device functor %r (known: %s)" % (name, ", ".join(sorted(L.FUNCTORS))))
 
 
@@ -73,6 +75,13 @@ class Engine:
                                     blob.ctypes.data_as(C.c_void_p), blob.nbytes, C.byref(h)))
         self.h = h
         self.ns_mode = ns_mode
+        if functor == "user":
+            src = (params or {}).get("source")
+            if not src:
+                self.close()
+                raise ValueError("functor 'user' needs params['source']: CUDA C++ defining cpn_user_log_likelihood "
+                                 "(contract in cpnest_b200/csrc/user_model.cuh)")
+            self.set_user_functor(src)
 
     # ---- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -103,6 +112,18 @@ class Engine:
 
     def set_slice_mu(self, mu):
         L.check(self.lib.cpn_set_slice_mu(self.h, float(mu)))
+
+    def set_user_functor(self, source):
+        """Compile a user-written CUDA functor (NVRTC, sm_100a) into this context's chain kernels."""
+        import os
+        here = os.path.dirname(os.path.abspath(__file__))
+        dirs = [os.path.join(here, "csrc"), os.path.join(os.path.dirname(here), "include")]
+        arr = (C.c_char_p * len(dirs))(*[d.encode() for d in dirs])
+        try:
+            L.check(self.lib.cpn_set_user_functor(self.h, source.encode(), arr, len(dirs)))
+        except Exception:
+            self.close()
+            raise
 
     def set_seed(self, seed):
         L.check(self.lib.cpn_set_seed(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF))

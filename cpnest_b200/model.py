@@ -9,6 +9,17 @@ names the device functor that evaluates it on the GPU:
         device_functor = ('gaussian_iid', {'mu': 0.0, 'sigma': 1.0})
         def log_likelihood(self, p): ...      # kept: it is the parity oracle of the functor
 
+or carries its own functor as CUDA C++ source, compiled at run time with NVRTC into the same kernels:
+
+    class MyModel(cpnest_b200.model.Model):
+        names = ['a', 'b']; bounds = [[-5, 5], [-5, 5]]
+        device_source = '''
+        __device__ double cpn_user_log_likelihood(const double* x, int D, const double* params) {
+            return -0.5 * (x[0] * x[0] + x[1] * x[1]) / (params[0] * params[0]);
+        }'''
+        device_params = [2.0]
+        def log_likelihood(self, p): return -0.5 * (p['a']**2 + p['b']**2) / 4.0
+
 `CPNest` checks the functor against the Python callables on random prior points before a run.
 """
 from array import array
@@ -24,6 +35,8 @@ class Model(object):
     names = []     # parameter names, e.g. ['p1', 'p2']
     bounds = []    # prior box, e.g. [(min1, max1), (min2, max2)]
     device_functor = None   # (functor name, parameter dict), see cpnest_b200.engine.functor_blob
+    device_source = None    # or: CUDA C++ source of the model's own functor (contract: csrc/user_model.cuh)
+    device_params = ()      # doubles handed to the user functor as `params`
 
     def in_bounds(self, param):
         """Strict box test (cpnest/model.py:33)."""
@@ -74,12 +87,16 @@ class Model(object):
         f = self.device_functor
         if callable(f):
             f = f()
+        if f is None and self.device_source:
+            # the model's own log_likelihood / log_prior written in CUDA C++, compiled at run time (NVRTC)
+            return "user", dict(source=self.device_source, params=list(self.device_params))
         if f is None:
             raise NotImplementedError(
                 "%s has no device functor. cpnest_b200 evaluates log_prior/log_likelihood inside its CUDA kernels "
                 "and has no CPU fallback: set `device_functor = (name, params)` to one of the built-in functors "
                 "(gaussian_iid, gaussian_corr, eggbox, rosenbrock, ackley, ring, gaussian_mean_sigma, "
-                "gaussian_mixture) -- see cpnest_b200/models.py for ready-made models." % type(self).__name__)
+                "gaussian_mixture; ready-made models in cpnest_b200/models.py), or set `device_source` to CUDA C++ "
+                "defining cpn_user_log_likelihood (contract in cpnest_b200/csrc/user_model.cuh)." % type(self).__name__)
         if isinstance(f, str):
             f = (f, {})
         return f[0], dict(f[1] or {})

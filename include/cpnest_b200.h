@@ -15,8 +15,10 @@
  */
 #ifndef CPNEST_B200_H
 #define CPNEST_B200_H
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
 #include <stdint.h>
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -34,7 +36,9 @@ enum cpn_functor {
     CPN_RING = 5,             /* tests/test_ring.py:19-23; blob: {radius, thickness} */
     CPN_GAUSS_MEAN_SIGMA = 6, /* tests/test_gaussian.py:15-20 (1/sigma prior) */
     CPN_GAUSS_MIXTURE = 7,    /* examples/gaussianmixture.py:22-31; blob: {n_data, data[n_data]} */
-    CPN_NUM_FUNCTORS = 8
+    CPN_USER = 8,             /* user-written CUDA functor, compiled at run time: cpn_set_user_functor (any subclass of
+                                 cpnest.model.Model with its own log_likelihood / log_prior, cpnest/model.py:55-82); blob: free */
+    CPN_NUM_FUNCTORS = 9
 };
 
 /* proposal ids, order of DefaultProposalCycle (cpnest/proposal.py:354-361) */
@@ -114,6 +118,13 @@ int cpn_set_slice_cycle(cpn_ctx* ctx, const uint8_t* cycle, int32_t len);
 /* SliceSampler.mu (cpnest/sampler.py:422): initial / current length scale of the slice directions. */
 int cpn_set_slice_mu(cpn_ctx* ctx, double mu);
 
+/* Device form of a user's Model subclass (cpnest/model.py:55-82): `source` is CUDA C++ defining the __device__
+ * function `cpn_user_log_likelihood` (x, D, params) -> double and optionally, announced with
+ * #define CPN_USER_HAS_PRIOR / CPN_USER_HAS_GRADIENT, `cpn_user_log_prior` and `cpn_user_grad_log_likelihood`
+ * (exact prototypes: cpnest_b200/csrc/user_model.cuh).  Compiled with NVRTC for sm_100a into the same chain kernels
+ * as the built-in functors; include_dirs must contain cpnest_b200/csrc and include/.  The context must have been
+ * created with functor CPN_USER. */
+int cpn_set_user_functor(cpn_ctx* ctx, const char* source, const char* const* include_dirs, int32_t n_dirs);
 /* CPNest(seed=): Philox key of everything drawn from now on (takes effect with the next cpn_init_prior). */
 int cpn_set_seed(cpn_ctx* ctx, uint64_t seed);
 /* Sampler.reset + NestedSampler.reset (cpnest/sampler.py:110-154, NestedSampling.py:404-431):
