@@ -80,6 +80,9 @@ SIGNATURES = {
     "cpn_ns_step": (C.c_int, [_vp, C.c_int32]),
     "cpn_run": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_double, _P(C.c_int64)]),
     "cpn_finalise": (C.c_int, [_vp, _dp, _dp]),
+    "cpn_checkpoint_bytes": (C.c_int64, [_vp]),
+    "cpn_save_checkpoint": (C.c_int, [_vp, _vp, C.c_int64]),
+    "cpn_load_checkpoint": (C.c_int, [_vp, _vp, C.c_int64]),
     "cpn_synchronize": (C.c_int, [_vp]),
     "cpn_get_state": (C.c_int, [_vp, _P(cpn_state)]),
     "cpn_set_nmcmc": (C.c_int, [_vp, C.c_int32]),

@@ -9,6 +9,9 @@ termination test on the GPU.
 """
 import logging
 import os
+import pickle
+import signal
+import sys
 import time
 
 import numpy as np
@@ -23,6 +26,11 @@ LOGGER = logging.getLogger("cpnest.cpnest")
 
 class CheckPoint(Exception):
     pass
+
+
+def sighandler(signal, frame):
+    # cpnest/cpnest.py:27-30: the handlers installed with resume=True raise, run() checkpoints and exits with 130
+    raise CheckPoint()
 
 
 class CPNest(object):
@@ -70,8 +78,6 @@ class CPNest(object):
                     "use nslice == nthreads (or nhamiltonian == nthreads) for a pure population".format(
                         self.nthreads, nslice, nhamiltonian))
             self.sampler_kind = kinds[0]
-            if resume:
-                self.logger.critical("resume=True: checkpoint/resume is not implemented on the device yet; starting fresh")
             if n_periodic_checkpoint is not None:
                 self.logger.critical("The n_periodic_checkpoint kwarg is deprecated, use periodic_checkpoint_interval instead.")
             from .proposal import DefaultProposalCycle, EnsembleSliceProposalCycle, HamiltonianProposalCycle
@@ -90,6 +96,11 @@ class CPNest(object):
             self.prior_sampling = prior_sampling
             self.user = usermodel
             self.resume = resume
+            # the reference pickles NestedSampler and every sampler (nested_sampler_resume.pkl, sampler_{i}.pkl,
+            # cpnest/cpnest.py:176-179, 221-222); the device run is ONE state blob, kept under the NestedSampler's file name
+            self.resume_file = os.path.join(output, "nested_sampler_resume.pkl")
+            self.periodic_checkpoint_interval = (np.inf if periodic_checkpoint_interval is None
+                                                 else float(periodic_checkpoint_interval))
             self.seed = 1234 if seed is None else seed
             self.maxmcmc = maxmcmc
             self.batch = int(batch) if batch else max(min(self.nthreads, nlive // 2), nlive // 4, 1)
@@ -138,8 +149,15 @@ class CPNest(object):
         with self.log_file:
             t0 = time.time()
             eng, NS, K = self.engine, self.NS, self.batch
-            eng.init_prior()
+            if self.resume and os.path.exists(self.resume_file):
+                self._resume()                                  # cpnest/cpnest.py:181-183
+            else:
+                eng.init_prior()
             NS.initialised = True
+            if self.resume:                                     # cpnest/cpnest.py:271-277
+                for sig in (signal.SIGTERM, signal.SIGALRM, signal.SIGQUIT, signal.SIGINT, signal.SIGUSR1, signal.SIGUSR2):
+                    signal.signal(sig, sighandler)
+            last_checkpoint = time.time()
             D = len(self.user.names)
             if self.prior_sampling:
                 # NestedSampling.py:439-448: the live points ARE the prior samples
@@ -151,8 +169,15 @@ class CPNest(object):
                 self.prior_samples = self.get_prior_samples(filename=None)
                 return
             while True:
-                eng.run(K, max_batches=max(1, self.nlive // K), tolerance=NS.tolerance)
-                s = eng.state()
+                try:
+                    eng.run(K, max_batches=max(1, self.nlive // K), tolerance=NS.tolerance)
+                    s = eng.state()
+                except CheckPoint:                              # cpnest/cpnest.py:286-288
+                    self.checkpoint()
+                    sys.exit(130)
+                if time.time() - last_checkpoint > self.periodic_checkpoint_interval:      # NestedSampling.py:453-455
+                    self.checkpoint()
+                    last_checkpoint = time.time()
                 NS.update_from(s)
                 if self.verbose:
                     acc = s["total_accepted"] / max(1, s["total_steps"])
@@ -246,4 +271,22 @@ class CPNest(object):
             plot.plot_corner(arr, labels=pos.dtype.names, filename=os.path.join(self.output, "corner.pdf"))
 
     def checkpoint(self):
-        raise NotImplementedError("checkpoint/resume is not implemented on the device yet")
+        """Write the run state to the resume file (cpnest/cpnest.py:548-550, NestedSampling.py:495-501)."""
+        self.logger.critical("Checkpointing nested sampling")
+        rec = dict(blob=self.engine.save_checkpoint(), names=list(self.user.names), nlive=self.nlive, seed=self.seed,
+                   batch=self.batch, sampler=self.sampler_kind, maxmcmc=self.maxmcmc)
+        tmp = self.resume_file + ".tmp"
+        with open(tmp, "wb") as f:
+            pickle.dump(rec, f)
+        os.replace(tmp, self.resume_file)
+
+    def _resume(self):
+        with open(self.resume_file, "rb") as f:
+            rec = pickle.load(f)
+        for k, mine in (("names", list(self.user.names)), ("nlive", self.nlive), ("batch", self.batch),
+                        ("sampler", self.sampler_kind), ("maxmcmc", self.maxmcmc)):
+            if rec[k] != mine:
+                raise ValueError("resume file %s belongs to a different run: %s = %r, this run has %r" % (
+                    self.resume_file, k, rec[k], mine))
+        self.engine.load_checkpoint(rec["blob"])
+        self.logger.critical("Resuming NestedSampler from " + self.resume_file)

@@ -1115,6 +1115,123 @@ extern "C" int cpn_finalise(cpn_ctx* c, double* logZ_rect, double* logZ_trap) {
     return 0;
 }
 
+// ---- checkpoint / resume (NestedSampler.checkpoint / resume + Sampler.checkpoint / resume,
+// cpnest/NestedSampling.py:495-537, cpnest/sampler.py:275-314): the device state is a handful of flat arrays and
+// counters; it is written into / read from one caller-owned host blob.  A resumed run continues bit-identically.
+namespace {
+struct CkptHeader {
+    char magic[8];                 // "CPNB200\0"
+    int32_t version, dim, nlive, functor, sampler, ns_mode, maxmcmc, cycle_len, slice_cycle_len, cur, eig_cur, eig_pending,
+        eig_pending_age, live_ready;
+    uint64_t seed;
+    long long dead_upper, batches_enqueued, chains_since_stats, eig_calls, n_dead, n_hist, n_ins;
+    unsigned long long chain_counter;
+    NSState state;
+};
+struct CkptSection { void* dev; size_t bytes; };
+
+static std::vector<CkptSection> ckpt_sections(cpn_ctx* c, long long n_dead, long long n_hist, long long n_ins) {
+    const size_t N = c->N, D = c->D, Dp = c->Dp;
+    std::vector<CkptSection> v = {
+        {c->d_x, N * Dp * 8}, {c->d_logL, N * 8}, {c->d_logP, N * 8},
+        {c->d_order[c->cur], N * 4}, {c->d_skeys[c->cur], N * 8},
+        {c->d_dead_x, (size_t)n_dead * Dp * 8}, {c->d_dead_logL, (size_t)n_dead * 8}, {c->d_dead_logP, (size_t)n_dead * 8},
+        {c->d_hist_logL, (size_t)n_hist * 8}, {c->d_hist_logvol, (size_t)n_hist * 8}, {c->d_ins, (size_t)n_ins * 8},
+        {c->d_rho2, (D + 1) * 8}, {c->d_cycle, (size_t)c->cycle_len}, {c->d_slice_cycle, (size_t)c->slice_cycle_len},
+        {c->d_mean, D * 8}, {c->d_cov, D * D * 8}};
+    for (int b = 0; b < 2; ++b) {
+        v.push_back({c->d_eigval[b], D * 8});
+        v.push_back({c->d_eigvec[b], D * Dp * 8});
+        v.push_back({c->d_eigscale[b], D * 8});
+        v.push_back({c->d_eigmean[b], D * 8});
+        v.push_back({c->d_covbuf[b], D * D * 8});
+    }
+    return v;
+}
+}  // namespace
+
+// finish what is in flight (a statistics refresh on the side stream) so that the arrays are final
+static int ckpt_quiesce(cpn_ctx* c) {
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->side));
+    c->wait_cov = false;
+    return fetch_state(c);
+}
+
+extern "C" int64_t cpn_checkpoint_bytes(cpn_ctx* c) {
+    if (!c) return -1;
+    if (ckpt_quiesce(c)) return -1;
+    const NSState* s = c->h_state;
+    size_t tot = sizeof(CkptHeader);
+    for (auto& sec : ckpt_sections(c, s->iteration, s->n_hist, s->n_ins)) tot += (sec.bytes + 7) & ~(size_t)7;
+    return (int64_t)tot;
+}
+
+extern "C" int cpn_save_checkpoint(cpn_ctx* c, void* blob, int64_t bytes) {
+    if (!c || !blob) return fail("null argument");
+    if (ckpt_quiesce(c)) return 1;
+    const NSState* s = c->h_state;
+    CkptHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "CPNB200", 8);
+    h.version = 1; h.dim = c->D; h.nlive = c->N; h.functor = c->cfg.functor; h.sampler = c->cfg.sampler; h.ns_mode = c->cfg.ns_mode;
+    h.maxmcmc = c->cfg.maxmcmc; h.cycle_len = c->cycle_len; h.slice_cycle_len = c->slice_cycle_len; h.cur = c->cur;
+    h.eig_cur = c->eig_cur; h.eig_pending = c->eig_pending ? 1 : 0; h.eig_pending_age = c->eig_pending_age;
+    h.live_ready = c->live_ready ? 1 : 0; h.seed = c->cfg.seed; h.dead_upper = c->dead_upper; h.batches_enqueued = c->batches_enqueued;
+    h.chains_since_stats = c->chains_since_stats; h.eig_calls = c->eig_calls; h.n_dead = s->iteration; h.n_hist = s->n_hist;
+    h.n_ins = s->n_ins; h.chain_counter = c->chain_counter; h.state = *s;
+    auto secs = ckpt_sections(c, h.n_dead, h.n_hist, h.n_ins);
+    size_t tot = sizeof h;
+    for (auto& sec : secs) tot += (sec.bytes + 7) & ~(size_t)7;
+    if ((size_t)bytes < tot) return fail("cpn_save_checkpoint: blob of %lld bytes, %zu needed", (long long)bytes, tot);
+    char* p = (char*)blob;
+    memcpy(p, &h, sizeof h);
+    p += sizeof h;
+    for (auto& sec : secs) {
+        if (sec.bytes) CK(cudaMemcpy(p, sec.dev, sec.bytes, cudaMemcpyDeviceToHost));
+        p += (sec.bytes + 7) & ~(size_t)7;
+    }
+    return 0;
+}
+
+extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) {
+    if (!c || !blob) return fail("null argument");
+    if ((size_t)bytes < sizeof(CkptHeader)) return fail("cpn_load_checkpoint: blob too small");
+    CkptHeader h;
+    memcpy(&h, blob, sizeof h);
+    if (memcmp(h.magic, "CPNB200", 8) != 0 || h.version != 1) return fail("cpn_load_checkpoint: not a cpnest_b200 checkpoint (version 1)");
+    if (h.dim != c->D || h.nlive != c->N || h.functor != c->cfg.functor || h.sampler != c->cfg.sampler || h.ns_mode != c->cfg.ns_mode ||
+        h.maxmcmc != c->cfg.maxmcmc)
+        return fail("cpn_load_checkpoint: checkpoint of a different run (dim %d nlive %d functor %d sampler %d maxmcmc %d)", h.dim,
+                    h.nlive, h.functor, h.sampler, h.maxmcmc);
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->side));
+    if (grow_logs(c, std::max(h.n_dead, std::max(h.n_hist, h.n_ins)) + 2LL * c->N)) return 1;
+    c->cycle_len = h.cycle_len; c->slice_cycle_len = h.slice_cycle_len; c->cur = h.cur; c->eig_cur = h.eig_cur;
+    c->eig_pending = h.eig_pending != 0; c->eig_pending_age = h.eig_pending_age; c->wait_cov = false;
+    c->live_ready = h.live_ready != 0; c->cfg.seed = h.seed; c->dead_upper = h.dead_upper; c->batches_enqueued = h.batches_enqueued;
+    c->chains_since_stats = h.chains_since_stats; c->eig_calls = h.eig_calls; c->chain_counter = h.chain_counter;
+    c->staged_external = false;
+    auto secs = ckpt_sections(c, h.n_dead, h.n_hist, h.n_ins);
+    size_t tot = sizeof h;
+    for (auto& sec : secs) tot += (sec.bytes + 7) & ~(size_t)7;
+    if ((size_t)bytes < tot) return fail("cpn_load_checkpoint: truncated blob (%lld of %zu bytes)", (long long)bytes, tot);
+    const char* p = (const char*)blob + sizeof h;
+    for (auto& sec : secs) {
+        if (sec.bytes) CK(cudaMemcpy(sec.dev, p, sec.bytes, cudaMemcpyHostToDevice));
+        p += (sec.bytes + 7) & ~(size_t)7;
+    }
+    *c->h_state = h.state;
+    if (push_state(c)) return 1;
+    if (c->eig_pending) {
+        // the refresh that was in flight had finished before the state was saved: make its event "already happened"
+        CK(cudaEventRecord(c->ev_eig, c->stream));
+    }
+    return 0;
+}
+
 extern "C" int cpn_synchronize(cpn_ctx* c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));

@@ -168,6 +168,19 @@ class Engine:
         L.check(self.lib.cpn_finalise(self.h, C.byref(rect), C.byref(trap)))
         return rect.value, trap.value
 
+    def save_checkpoint(self):
+        """The run state as bytes (cpn_save_checkpoint)."""
+        n = self.lib.cpn_checkpoint_bytes(self.h)
+        if n < 0:
+            raise L.CpnError(self.lib.cpn_last_error().decode())
+        buf = np.empty(n, dtype=np.uint8)
+        L.check(self.lib.cpn_save_checkpoint(self.h, buf.ctypes.data_as(C.c_void_p), n))
+        return buf.tobytes()
+
+    def load_checkpoint(self, blob):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        L.check(self.lib.cpn_load_checkpoint(self.h, buf.ctypes.data_as(C.c_void_p), len(buf)))
+
     def synchronize(self):
         L.check(self.lib.cpn_synchronize(self.h))
 

@@ -173,6 +173,14 @@ int cpn_run(cpn_ctx* ctx, int32_t K, int64_t max_batches, double tolerance, int6
  * (NestedSampling.py:472-480, nest2pos.py:33-42). */
 int cpn_finalise(cpn_ctx* ctx, double* logZ_rect, double* logZ_trap);
 
+/* NestedSampler.checkpoint / resume + Sampler.checkpoint / resume (cpnest/NestedSampling.py:495-537,
+ * cpnest/sampler.py:275-314): the whole run state (live set, order, dead-point log, integrator history, insertion
+ * indices, ensemble statistics, controllers, RNG counters) as one host blob.  The context that loads it must have
+ * been created with the same dim / nlive / functor / sampler / maxmcmc; the run then continues bit-identically. */
+int64_t cpn_checkpoint_bytes(cpn_ctx* ctx);
+int cpn_save_checkpoint(cpn_ctx* ctx, void* blob, int64_t bytes);
+int cpn_load_checkpoint(cpn_ctx* ctx, const void* blob, int64_t bytes);
+
 int cpn_synchronize(cpn_ctx* ctx);
 /* Enqueue all further work on a caller-owned CUDA stream (cudaStream_t as void*), e.g. the stream
  * of the host framework so that its events and collectives order with the kernels.  NULL restores

@@ -140,3 +140,42 @@ def test_full_size_invariants_50d_nlive_1e4():
         # the union of live and dead points holds every point exactly once (no slot lost in the merge)
         allp = np.concatenate((live, dead))
         assert len(np.unique(allp[:, :3], axis=0)) == len(allp) - s["failed_chains"] or s["failed_chains"] > 0
+
+
+def test_checkpoint_resume_continues_bit_identically():
+    """NestedSampler.checkpoint / resume (cpnest/NestedSampling.py:495-537): a run restored from its state blob in a NEW
+    context continues exactly like the uninterrupted one (also across a pending ensemble-statistics refresh)."""
+    import hashlib
+    from cpnest_b200.engine import Engine
+
+    def make(sampler):
+        e = Engine("gaussian_iid", [[-10, 10]] * 6, nlive=1000, maxmcmc=100, seed=11, sampler=sampler)
+        if sampler == "mh":
+            e.set_cycle(O.make_cycle(np.random.RandomState(11)))
+        return e
+
+    def digest(e):
+        s = e.state()
+        return (hashlib.sha1(e.dead().tobytes() + e.live().tobytes() + e.insertion_indices().tobytes()).hexdigest(),
+                s["logZ"], s["info"], s["nmcmc"], s["total_evals"], s["slice_mu"], s["hmc_dt"])
+
+    for sampler in ("mh", "slice", "hmc"):
+        for cut in (7, 8, 9, 10):                       # the refresh cadence makes some of these cuts fall mid-refresh
+            a = make(sampler)
+            a.init_prior()
+            for _ in range(cut):
+                a.ns_step(250)
+            blob = a.save_checkpoint()
+            for _ in range(9):
+                a.ns_step(250)
+            ref = digest(a)
+            a.close()
+            b = make(sampler)
+            b.load_checkpoint(blob)
+            for _ in range(9):
+                b.ns_step(250)
+            assert digest(b) == ref, (sampler, cut)
+            b.close()
+    with pytest.raises(Exception, match="different run"):
+        c = Engine("gaussian_iid", [[-10, 10]] * 6, nlive=500, maxmcmc=100, seed=11)
+        c.load_checkpoint(blob)

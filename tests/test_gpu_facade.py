@@ -130,3 +130,35 @@ def test_ring_slice_like_reference_test(tmp_path):
     model = M.RingModel()
     work = _run(model, tmp_path, verbose=0, nthreads=4, nslice=4, nlive=1000, maxmcmc=1000, poolsize=1000)
     assert np.abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * np.sqrt(work.NS.state.info / work.NS.Nlive)
+
+
+def test_resume_after_interrupt_gives_the_uninterrupted_result(tmp_path):
+    """CPNest(resume=True) (cpnest/cpnest.py:271-288): a signal during the run checkpoints and exits with 130; a second
+    CPNest in the same output directory picks the run up and finishes it with the result of an uninterrupted run."""
+    import signal
+    import cpnest_b200 as cpnest
+    import cpnest_b200.models as M
+    kw = dict(verbose=0, nthreads=4, nlive=1000, maxmcmc=200, seed=77)
+    ref = _run(M.GaussianModel(2), tmp_path / "ref", **kw)
+    out = tmp_path / "run"
+    work = cpnest.CPNest(M.GaussianModel(2), output=str(out), resume=True, **kw)
+    calls = [0]
+    real_run = work.engine.run
+
+    def interrupted_run(*a, **k):
+        calls[0] += 1
+        r = real_run(*a, **k)
+        if calls[0] == 3:
+            signal.raise_signal(signal.SIGUSR1)
+        return r
+    work.engine.run = interrupted_run
+    with pytest.raises(SystemExit) as ex:
+        work.run()
+    assert ex.value.code == 130 and os.path.exists(os.path.join(str(out), "nested_sampler_resume.pkl"))
+    work.engine.close()
+    again = cpnest.CPNest(M.GaussianModel(2), output=str(out), resume=True, **kw)
+    again.run()
+    assert again.NS.logZ == ref.NS.logZ and again.NS.iteration == ref.NS.iteration
+    assert np.array_equal(again.nested_samples["x"], ref.nested_samples["x"])
+    for sig in (signal.SIGTERM, signal.SIGALRM, signal.SIGQUIT, signal.SIGINT, signal.SIGUSR1, signal.SIGUSR2):
+        signal.signal(sig, signal.SIG_DFL)
