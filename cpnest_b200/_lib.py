@@ -42,7 +42,7 @@ class cpn_state(C.Structure):
 
 
 FUNCTORS = dict(gaussian_iid=0, gaussian_corr=1, eggbox=2, rosenbrock=3, ackley=4, ring=5,
-                gaussian_mean_sigma=6, gaussian_mixture=7, user=8)
+                gaussian_mean_sigma=6, gaussian_mixture=7, user=8, gaussian_mixture_nd=9)
 WALK, STRETCH, DE, EIGEN = 0, 1, 2, 3
 NS_SEQUENTIAL, NS_REFERENCE = 0, 1
 SAMPLERS = dict(mh=0, slice=1, hmc=2)

@@ -50,16 +50,16 @@ typedef int (*slice_fn)(int, int, int, const SliceParams&, cudaStream_t);
 typedef int (*hmc_fn)(int, int, int, const HMCParams&, cudaStream_t);
 static const hmc_fn kHMC[CPN_NUM_FUNCTORS] = {launch_hmc_gauss_iid, launch_hmc_gauss_corr, launch_hmc_eggbox,
                                               launch_hmc_rosenbrock, launch_hmc_ackley, launch_hmc_ring,
-                                              launch_hmc_gauss_mean_sigma, launch_hmc_gauss_mixture, nullptr};
+                                              launch_hmc_gauss_mean_sigma, launch_hmc_gauss_mixture, nullptr, launch_hmc_gauss_mix_nd};
 static const slice_fn kSlice[CPN_NUM_FUNCTORS] = {launch_slice_gauss_iid, launch_slice_gauss_corr, launch_slice_eggbox,
                                                   launch_slice_rosenbrock, launch_slice_ackley, launch_slice_ring,
-                                                  launch_slice_gauss_mean_sigma, launch_slice_gauss_mixture, nullptr};
+                                                  launch_slice_gauss_mean_sigma, launch_slice_gauss_mixture, nullptr, launch_slice_gauss_mix_nd};
 static const mh_fn kMH[CPN_NUM_FUNCTORS] = {launch_mh_gauss_iid, launch_mh_gauss_corr, launch_mh_eggbox,
                                             launch_mh_rosenbrock, launch_mh_ackley, launch_mh_ring,
-                                            launch_mh_gauss_mean_sigma, launch_mh_gauss_mixture, nullptr};
+                                            launch_mh_gauss_mean_sigma, launch_mh_gauss_mixture, nullptr, launch_mh_gauss_mix_nd};
 static const eval_fn kEval[CPN_NUM_FUNCTORS] = {launch_eval_gauss_iid, launch_eval_gauss_corr, launch_eval_eggbox,
                                                 launch_eval_rosenbrock, launch_eval_ackley, launch_eval_ring,
-                                                launch_eval_gauss_mean_sigma, launch_eval_gauss_mixture, nullptr};
+                                                launch_eval_gauss_mean_sigma, launch_eval_gauss_mixture, nullptr, launch_eval_gauss_mix_nd};
 
 struct cpn_ctx {
     cpn_config cfg;
@@ -363,6 +363,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         case CPN_GAUSS_MIXTURE:
             if (cfg->dim != 5 || nb < 2 || (size_t)((const double*)blob)[0] + 1 != nb) return fail("gauss_mixture needs dim=5 and blob {n, data[n]}");
             break;
+        case CPN_GAUSS_MIX_ND: if (nb != 5) return fail("gauss_mix_nd blob must be {w, m1, s1, m2, s2}"); break;
         default: break;
     }
     CK(cudaSetDevice(cfg->device));

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
                         nrm[e] = (refl && d < D) ? tp[d] : 0.0;
                     }
                     if (refl) tp += D;
-                } else {
+                } else if (__any_sync(FULL, active && !inside)) {       // the normal is only needed by a reflecting chain
                     Model::template grad_log_likelihood<G, E>(g, q, m, nrm);
                     double n2 = 0.0;
 #pragma unroll
@@ -282,6 +282,9 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
                     const double inv = (n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
 #pragma unroll
                     for (int e = 0; e < E; ++e) nrm[e] *= inv;           // unit_normal, :469-486
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) nrm[e] = 0.0;
                 }
                 double pn = 0.0;
 #pragma unroll

@@ -19,4 +19,5 @@ CPN_DECLARE_MODEL(ackley)
 CPN_DECLARE_MODEL(ring)
 CPN_DECLARE_MODEL(gauss_mean_sigma)
 CPN_DECLARE_MODEL(gauss_mixture)
+CPN_DECLARE_MODEL(gauss_mix_nd)
 }  // namespace cpn

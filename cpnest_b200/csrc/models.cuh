@@ -151,6 +151,49 @@ struct GaussCorr : FlatPrior {
     }
 };
 
+// ---- two-component isotropic Gaussian mixture in PARAMETER space (BASELINE.json config 5 names a "20-D Gaussian
+//      mixture", which the reference does not contain: examples/gaussianmixture.py is 5-D over a data vector):
+//      L(x) = w N(x; m1 1, s1^2 I) + (1 - w) N(x; m2 1, s2^2 I);  blob = {w, m1, s1, m2, s2};  Z = 1/volume(box) ------
+struct GaussMixND : FlatPrior {
+    static constexpr bool kScratch = false;
+    static constexpr bool kCheap = true;
+    static __device__ __forceinline__ void prepare(ModelCtx& m) {
+        m.par[0] = m.blob[1]; m.par[1] = 1.0 / m.blob[2]; m.par[2] = m.blob[3]; m.par[3] = 1.0 / m.blob[4];
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ void components(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double& l1, double& l2) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double t1 = (x[e] - m.par[0]) * m.par[1], t2 = (x[e] - m.par[2]) * m.par[3];
+            a += masked(m, e, t1 * t1);
+            b += masked(m, e, t2 * t2);
+        }
+        a = g.sum(a);
+        b = g.sum(b);
+        const double w = m.blob[0];
+        l1 = log(w) - 0.5 * a + m.D * (log(m.par[1]) - CPN_HALF_LOG_2PI);
+        l2 = log(1.0 - w) - 0.5 * b + m.D * (log(m.par[3]) - CPN_HALF_LOG_2PI);
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        double l1, l2;
+        components<G, E>(g, x, m, l1, l2);
+        const double hi = fmax(l1, l2), lo = fmin(l1, l2);
+        return hi + log1p(exp(lo - hi));
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
+        double l1, l2;
+        components<G, E>(g, x, m, l1, l2);
+        const double hi = fmax(l1, l2), lae = hi + log1p(exp(fmin(l1, l2) - hi));
+        const double r1 = exp(l1 - lae), r2 = exp(l2 - lae);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            gr[e] = masked(m, e, -r1 * (x[e] - m.par[0]) * m.par[1] * m.par[1] - r2 * (x[e] - m.par[2]) * m.par[3] * m.par[3]);
+    }
+};
+
 // ---- eggbox: examples/eggbox.py:19-23  (2 + prod cos(x_i/2))^5 ------------------------------
 struct Eggbox : FlatPrior {
     static constexpr bool kScratch = false;

@@ -33,6 +33,9 @@ def functor_blob(name, dim, params=None):
         return np.concatenate(([float(len(data))], data))
     if name in ("eggbox", "rosenbrock", "ackley", "gaussian_mean_sigma"):
         return np.zeros(0)
+    if name == "gaussian_mixture_nd":
+        return np.array([float(params.get("w", 0.3)), float(params.get("m1", -2.5)), float(params.get("s1", 1.0)),
+                         float(params.get("m2", 2.5)), float(params.get("s2", 1.0))])
     if name == "user":
         return np.asarray(params.get("params", []), dtype=np.float64).ravel()
     raise KeyError("unknown device functor %r (known: %s)" % (name, ", ".join(sorted(L.FUNCTORS))))

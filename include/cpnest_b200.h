@@ -38,7 +38,9 @@ enum cpn_functor {
     CPN_GAUSS_MIXTURE = 7,    /* examples/gaussianmixture.py:22-31; blob: {n_data, data[n_data]} */
     CPN_USER = 8,             /* user-written CUDA functor, compiled at run time: cpn_set_user_functor (any subclass of
                                  cpnest.model.Model with its own log_likelihood / log_prior, cpnest/model.py:55-82); blob: free */
-    CPN_NUM_FUNCTORS = 9
+    CPN_GAUSS_MIX_ND = 9,     /* two isotropic Gaussians in parameter space (BASELINE config 5's "20-D Gaussian mixture";
+                                 not in the reference); blob: {w, m1, s1, m2, s2} */
+    CPN_NUM_FUNCTORS = 10
 };
 
 /* proposal ids, order of DefaultProposalCycle (cpnest/proposal.py:354-361) */

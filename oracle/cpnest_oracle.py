@@ -177,6 +177,17 @@ def make_correlated_gaussian(D, seed=1234, lo=-10.0, hi=10.0):
                        params=dict(Linv=np.tril(Linv), logdet=logdet))
 
 
+def make_mixture_nd(D, w=0.3, m1=-2.5, s1=1.0, m2=2.5, s2=1.0, lo=-10.0, hi=10.0):
+    """BASELINE.json config 5 names a "20-D Gaussian mixture" that the reference does not contain: two
+    isotropic Gaussians in parameter space, L = w N(x; m1 1, s1^2 I) + (1-w) N(x; m2 1, s2^2 I); logZ = -D log(hi-lo)."""
+    def ll(x):
+        l1 = math.log(w) - 0.5 * float(np.sum(((x - m1) / s1) ** 2)) - D * (math.log(s1) + 0.5 * math.log(2 * math.pi))
+        l2 = math.log(1 - w) - 0.5 * float(np.sum(((x - m2) / s2) ** 2)) - D * (math.log(s2) + 0.5 * math.log(2 * math.pi))
+        return float(np.logaddexp(l1, l2))
+    return OracleModel("gaussian_mixture_nd", [str(i) for i in range(D)], [[lo, hi]] * D, ll,
+                       params=dict(w=w, m1=m1, s1=s1, m2=m2, s2=s2))
+
+
 def builtin_model(name, **kw):
     """The reference's models by fixture name (tests/golden/models.json keys)."""
     if name.startswith("gaussian") and name.endswith("d") and name[8:-1].isdigit():

@@ -61,10 +61,16 @@ def test_gradient_functors_match_finite_differences(golden):
     from cpnest_b200.engine import Engine
     mg = golden("models.json")
     rs = np.random.RandomState(3)
-    for name in ["gaussian10d", "rosenbrock10d", "eggbox", "ring", "gaussian_mean_sigma", "gaussian_mixture", "ackley10d", "gaussian_corr"]:
+    for name in ["gaussian10d", "rosenbrock10d", "eggbox", "ring", "gaussian_mean_sigma", "gaussian_mixture", "ackley10d", "gaussian_corr", "gaussian_mixture_nd"]:
         if name == "gaussian_corr":
             m = O.make_correlated_gaussian(8)
             e = Engine(m.functor, m.bounds, nlive=64, params=m.params)
+        elif name == "gaussian_mixture_nd":
+            m = O.make_mixture_nd(20)
+            e = Engine(m.functor, m.bounds, nlive=64, params=m.params)
+            X0 = np.random.RandomState(1).uniform(-4, 4, size=(50, 20))
+            logL, _ = e.eval_model(X0)
+            assert rel_close(logL, [m.log_likelihood(x) for x in X0], 1e-12)
         elif name == "ackley10d":
             m = O.builtin_model(name)
             e = Engine(m.functor, m.bounds, nlive=64)
@@ -73,6 +79,8 @@ def test_gradient_functors_match_finite_differences(golden):
         with e:
             lo, hi = m.lo, m.hi
             X = lo + (hi - lo) * (0.3 + 0.4 * rs.uniform(size=(6, m.D)))
+            if name == "gaussian_mixture_nd":
+                X = rs.uniform(-3, 3, size=(6, m.D))
             gl, gp = e.eval_gradients(X)
             for x, a, b in zip(X, gl, gp):
                 for d in range(m.D):
@@ -139,3 +147,22 @@ def test_hmc_ring_logz():
     e, s, logz, ins, nb = run_hmc("ring", [[-2, 2]] * 2, nlive=1000, K=64, params=dict(radius=1.0, thickness=0.1))
     with e:
         check_logz(s, logz, -2.318358, 1000)
+
+
+def test_20d_mixture_logz_with_ensemble_moves():
+    """BASELINE config 5 stand-in (oracle.make_mixture_nd): two separated 20-D modes, analytic logZ = -20 log 20.  The MH
+    cycle crosses between the modes through its ensemble moves (DifferentialEvolution / EnsembleWalk with members of
+    both modes); HMC as the reference specifies it (global-covariance mass matrix, no inter-mode move) loses a mode on
+    this target, so its 20-D test is the unimodal Gaussian."""
+    from cpnest_b200.engine import Engine
+    m = O.make_mixture_nd(20)
+    with Engine(m.functor, m.bounds, nlive=4000, maxmcmc=5000, seed=3, params=m.params) as e:
+        e.set_cycle(O.make_cycle(np.random.RandomState(3)))
+        e.init_prior()
+        e.run(1000, tolerance=0.1)
+        rect, trap = e.finalise()
+        s = e.state()
+        check_logz(s, trap, -20 * math.log(20.0), 4000)
+    e, s, logz, ins, nb = run_hmc("gaussian_iid", [[-10, 10]] * 20, nlive=2000, K=512, maxmcmc=500)
+    with e:
+        check_logz(s, logz, -20 * math.log(20.0), 2000)
