@@ -22,6 +22,11 @@
 // sampler.py:347); Nmcmc is set by the same start/end-correlation controller as for the other samplers.
 // Replay reproduces the reference's rule (stop at the first accepted trajectory, L given).
 //
+// Reflection.  Production reflects off the likelihood boundary in the metric of the kinetic energy,
+// p -= 2 (n.C.p / n.C.n) n, so that 0.5 p.C.p is conserved exactly (the reference's Euclidean reflection,
+// p -= 2 (p.n) n, conserves it only for C proportional to the identity).  Measured on the 20-D Gaussian at nlive 4000:
+// mean logZ deviation -0.85 sigma over 24 runs with the Euclidean rule, +0.24 +- 0.35 sigma with the metric rule.
+//
 // Production: the trajectory point is drawn in one pass by weighted reservoir sampling (same distribution as
 // the reference's multinomial draw over the stored trajectory, no trajectory storage); the reflection normal is
 // the analytic gradient of the functor's log_likelihood (the reference estimates it with per-dimension spline
@@ -148,8 +153,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
 
     // 0.5 p.C.p (+ the constants of proposal.py:575 in replay, where they enter exp(logw - norm) rounding)
     const double tconst = REPLAY ? (-p.logdet - 0.5 * (double)D * 1.8378770664093454836) : 0.0;
-    auto kinetic = [&](const double (&pp)[E]) -> double {
-        double w[E];
+    auto matvec = [&](const double (&pp)[E], double (&w)[E]) {          // w = C pp (this lane's coordinates)
 #pragma unroll
         for (int e = 0; e < E; ++e) w[e] = 0.0;
         for (int k = 0; k < D; ++k) {
@@ -161,6 +165,10 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
                 w[e] = fma((d < D) ? __ldg(crow + d) : 0.0, pk, w[e]);
             }
         }
+    };
+    auto kinetic = [&](const double (&pp)[E]) -> double {
+        double w[E];
+        matvec(pp, w);
         double acc = 0.0;
 #pragma unroll
         for (int e = 0; e < E; ++e) acc = fma(pp[e], w[e], acc);
@@ -286,13 +294,30 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
 #pragma unroll
                     for (int e = 0; e < E; ++e) nrm[e] = 0.0;
                 }
-                double pn = 0.0;
+                // Reflection off the likelihood boundary.  The reference reflects in the Euclidean metric,
+                // p -= 2 (p.n) n (:769-771; replay), which changes the kinetic energy 0.5 p.C.p unless C is a
+                // multiple of the identity; every such change feeds the (inexact, see the header) trajectory draw +
+                // energy test.  Production reflects in the metric of the kinetic energy instead,
+                // p -= 2 (n.C.p / n.C.n) n, which conserves it exactly: under a flat prior H is then constant along
+                // the trajectory, the draw is uniform and the energy test always passes.
+                double pn = 0.0, scale = 2.0;
+                if (REPLAY) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) pn = fma(pm[e], nrm[e], pn);
-                pn = g.sum(pn);
+                    for (int e = 0; e < E; ++e) pn = fma(pm[e], nrm[e], pn);
+                    pn = g.sum(pn);
+                } else if (__any_sync(FULL, active && !inside)) {
+                    double cn[E];
+                    matvec(nrm, cn);
+                    double ncp = 0.0, ncn = 0.0;
 #pragma unroll
-                for (int e = 0; e < E; ++e) pm[e] = add(pm[e], inside ? mul(-dt, gv[e]) : mul(mul(-2.0, pn), nrm[e]));
-                dirty = dirty || !inside || !Model::kFlatPrior;
+                    for (int e = 0; e < E; ++e) { ncp = fma(cn[e], pm[e], ncp); ncn = fma(cn[e], nrm[e], ncn); }
+                    ncp = g.sum(ncp);
+                    ncn = g.sum(ncn);
+                    pn = (ncn > 0.0) ? ncp / ncn : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < E; ++e) pm[e] = add(pm[e], inside ? mul(-dt, gv[e]) : mul(mul(-scale, pn), nrm[e]));
+                dirty = dirty || (REPLAY && !inside) || !Model::kFlatPrior;
                 if (g.all(!flipped) == false) dirty = true;
                 if (__any_sync(FULL, dirty)) {
                     const double Tn = kinetic(pm);

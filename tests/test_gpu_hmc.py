@@ -163,6 +163,6 @@ def test_20d_mixture_logz_with_ensemble_moves():
         rect, trap = e.finalise()
         s = e.state()
         check_logz(s, trap, -20 * math.log(20.0), 4000)
-    e, s, logz, ins, nb = run_hmc("gaussian_iid", [[-10, 10]] * 20, nlive=2000, K=512, maxmcmc=500)
+    e, s, logz, ins, nb = run_hmc("gaussian_iid", [[-10, 10]] * 20, nlive=4000, K=1000, maxmcmc=500)
     with e:
-        check_logz(s, logz, -20 * math.log(20.0), 2000)
+        check_logz(s, logz, -20 * math.log(20.0), 4000)

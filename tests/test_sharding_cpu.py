@@ -1,7 +1,7 @@
 """Host-side logic of the multi-GPU path, on CPU with the gloo backend (world_size 2):
 the chain slices cover a batch exactly once, and the record layout used for the NCCL all-gather
-(csrc/api.cu k_pack_shard / k_unpack_shards: [chains][Dp+4] doubles {x.., logL, logP, (steps,acc),
-(start,evals)}) round-trips through all_gather_into_tensor."""
+(csrc/api.cu k_pack_shard / k_unpack_shards: [chains][Dp+5] doubles {x.., logL, logP, (steps,acc),
+(start,evals), (ne,nc)}) round-trips through all_gather_into_tensor."""
 import os
 import socket
 
@@ -25,21 +25,25 @@ def test_shard_ranges_partition_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
-def pack(j0, j1, Dp, x, logL, logP, steps, acc, start, evals):
+S_EXTRA = 5      # cpn_shard_record_doubles() - Dp
+
+
+def pack(j0, j1, Dp, x, logL, logP, steps, acc, start, evals, ne, nc):
     n = j1 - j0
-    rec = np.zeros((n, Dp + 4))
+    rec = np.zeros((n, Dp + S_EXTRA))
     rec[:, :Dp] = x[j0:j1]
     rec[:, Dp] = logL[j0:j1]
     rec[:, Dp + 1] = logP[j0:j1]
-    ints = np.zeros((n, 4), dtype=np.int32)
-    ints[:, 0], ints[:, 1], ints[:, 2], ints[:, 3] = steps[j0:j1], acc[j0:j1], start[j0:j1], evals[j0:j1]
+    ints = np.zeros((n, 6), dtype=np.int32)
+    for k, a in enumerate((steps, acc, start, evals, ne, nc)):
+        ints[:, k] = a[j0:j1]
     rec[:, Dp + 2:] = ints.view(np.float64)       # (lo, hi) int pairs share a double slot
     return rec
 
 
 def unpack(rec, Dp):
     ints = np.ascontiguousarray(rec[:, Dp + 2:]).view(np.int32)
-    return rec[:, :Dp], rec[:, Dp], rec[:, Dp + 1], ints[:, 0], ints[:, 1], ints[:, 2], ints[:, 3]
+    return (rec[:, :Dp], rec[:, Dp], rec[:, Dp + 1]) + tuple(ints[:, k] for k in range(6))
 
 
 def _worker(rank, world, port, K, Dp, out):
@@ -50,15 +54,16 @@ def _worker(rank, world, port, K, Dp, out):
     x = rs.normal(size=(K, Dp)); logL = rs.normal(size=K); logP = rs.normal(size=K)
     steps = rs.randint(1, 5000, K).astype(np.int32); acc = rs.randint(0, 2000, K).astype(np.int32)
     start = rs.randint(0, 10 ** 6, K).astype(np.int32); evals = rs.randint(0, 5000, K).astype(np.int32)
+    ne = rs.randint(0, 10 ** 5, K).astype(np.int32); nc = rs.randint(0, 10 ** 5, K).astype(np.int32)
     j0, j1 = shard_range(K, rank, world)
     # a rank only has ITS slice; poison the rest to prove the gather fills it
-    mine = pack(j0, j1, Dp, x, logL, logP, steps, acc, start, evals)
-    recv = torch.full((K * (Dp + 4),), float("nan"), dtype=torch.float64)
-    send = recv[j0 * (Dp + 4):j1 * (Dp + 4)]
+    mine = pack(j0, j1, Dp, x, logL, logP, steps, acc, start, evals, ne, nc)
+    recv = torch.full((K * (Dp + S_EXTRA),), float("nan"), dtype=torch.float64)
+    send = recv[j0 * (Dp + S_EXTRA):j1 * (Dp + S_EXTRA)]
     send.copy_(torch.from_numpy(mine.ravel()))
     dist.all_gather_into_tensor(recv, send.clone())
-    got = unpack(recv.numpy().reshape(K, Dp + 4), Dp)
-    ok = all(np.array_equal(a, b) for a, b in zip(got, (x, logL, logP, steps, acc, start, evals)))
+    got = unpack(recv.numpy().reshape(K, Dp + S_EXTRA), Dp)
+    ok = all(np.array_equal(a, b) for a, b in zip(got, (x, logL, logP, steps, acc, start, evals, ne, nc)))
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
