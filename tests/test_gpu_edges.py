@@ -1,0 +1,62 @@
+"""Edge cases of the batch step through the C-ABI: smallest and ragged sizes, one dimension, more dimensions than a
+warp has lanes, a single chain per batch (the reference's nthreads=1), chains that cannot move, bad arguments."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(functor, D, nlive, K, sampler, maxmcmc=50, nbatches=6, bound=10.0, **kw):
+    from cpnest_b200.engine import Engine
+    e = Engine(functor, [[-bound, bound]] * D, nlive=nlive, maxmcmc=maxmcmc, seed=5, sampler=sampler, **kw)
+    e.init_prior()
+    for _ in range(nbatches):
+        e.ns_step(K)
+    s = e.state()
+    live, dead = e.live(), e.dead()
+    assert s["iteration"] == nbatches * K == len(dead)
+    assert np.all(np.diff(live[:, D]) >= 0) and np.all(np.diff(dead[:, D]) >= 0)
+    assert live[0, D] > dead[-1, D] or s["failed_chains"] > 0
+    assert np.all(np.abs(live[:, :D]) < bound) and np.all(np.isfinite(live))
+    logL, _ = e.eval_model(live[:, :D])
+    assert np.allclose(logL, live[:, D], rtol=1e-12, atol=1e-12)
+    e.close()
+    return s
+
+
+@pytest.mark.parametrize("sampler", ["mh", "slice", "hmc"])
+def test_sizes_and_dimensions(sampler):
+    _run("gaussian_iid", 1, 8, 1, sampler)                 # one dimension, one chain per batch, tiny live set
+    _run("gaussian_iid", 3, 37, 5, sampler)                # ragged: nothing divides anything
+    _run("gaussian_iid", 2, 64, 61, sampler)               # K = nlive - 3, the largest batch allowed
+    _run("gaussian_iid", 33, 200, 50, sampler)             # one more dimension than a warp has lanes
+    _run("gaussian_iid", 100, 400, 100, sampler, nbatches=3)
+    _run("rosenbrock", 7, 100, 25, sampler, bound=5.0)     # neighbour shuffles across an odd dimension
+
+
+def test_chains_that_cannot_move_return_their_start():
+    """maxmcmc = 1 with a sharp constraint: most chains fail; the batch step must stay consistent (the reference
+    resends such points, NestedSampling.py:354-357; here they return a copy of their start point and are counted)."""
+    s = _run("gaussian_iid", 20, 200, 50, "mh", maxmcmc=1, nbatches=10)
+    assert s["failed_chains"] > 0 and s["total_steps"] == 10 * 50
+
+
+def test_bad_arguments_fail_loudly():
+    from cpnest_b200.engine import Engine
+    from cpnest_b200._lib import CpnError
+    with pytest.raises(CpnError, match="nlive must be >= 4"):
+        Engine("gaussian_iid", [[-1, 1]], nlive=3)
+    with pytest.raises(CpnError, match="is empty"):
+        Engine("gaussian_iid", [[1, 1]], nlive=16)
+    with pytest.raises(CpnError, match="ring needs dim=2"):
+        Engine("ring", [[-2, 2]] * 3, nlive=16, params=dict(radius=1.0, thickness=0.1))
+    with Engine("gaussian_iid", [[-1, 1]] * 2, nlive=16) as e:
+        with pytest.raises(CpnError, match="live set not initialised"):
+            e.ns_step(4)
+        e.init_prior()
+        with pytest.raises(CpnError, match=r"must be in \[1, nlive-3\]"):
+            e.ns_step(14)
+        with pytest.raises(CpnError, match="must be in"):
+            e.set_nmcmc(10 ** 6)
