@@ -660,15 +660,12 @@ extern "C" int cpn_get_ensemble_stats(cpn_ctx* c, double* mean, double* cov, dou
     return 0;
 }
 
-static void fill_mh(cpn_ctx* c, MHParams* p) {
-    memset(p, 0, sizeof *p);
+// what every chain kernel needs: the ensemble, the box, the chain control and the staging outputs
+static void fill_common(cpn_ctx* c, ChainParams* p) {
     p->ens_x = c->d_x; p->ens_logL = c->d_logL; p->ens_logP = c->d_logP;
     p->ens_n = c->N; p->Dp = c->Dp; p->D = c->D;
     p->order = c->d_order[c->cur];
     p->lo = c->d_lo; p->hi = c->d_hi;
-    p->cycle = c->d_cycle; p->cycle_len = c->cycle_len;
-    p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
-    p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
     p->state = c->d_state;
     p->maxmcmc = c->cfg.maxmcmc;
     p->chain_base = c->chain_counter;
@@ -688,68 +685,33 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
         p->out_acc[o] = (int*)(b + stage_off(c->N, c->Dp, 4));
         p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
         p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
-    }
-}
-
-static void fill_slice(cpn_ctx* c, SliceParams* p) {
-    memset(p, 0, sizeof *p);
-    p->ens_x = c->d_x; p->ens_logL = c->d_logL; p->ens_logP = c->d_logP;
-    p->ens_n = c->N; p->Dp = c->Dp; p->D = c->D;
-    p->order = c->d_order[c->cur];
-    p->lo = c->d_lo; p->hi = c->d_hi;
-    p->cycle = c->d_slice_cycle; p->cycle_len = c->slice_cycle_len;
-    p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->slice_cycle_len);
-    p->mean = c->d_eigmean[c->eig_cur]; p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
-    p->state = c->d_state;
-    p->maxmcmc = c->cfg.maxmcmc;
-    p->chain_base = c->chain_counter;
-    p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
-    p->blob = c->d_blob;
-    const int nout = c->n_peers > 0 ? c->n_peers : 1;
-    p->n_out = nout;
-    for (int o = 0; o < nout; ++o) {
-        const int r = (o == 0) ? c->rank : (o <= c->rank ? o - 1 : o);
-        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp)
-                                   : (char*)c->d_stage_own;
-        p->out_x[o] = (double*)(b + stage_off(c->N, c->Dp, 0));
-        p->out_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 1));
-        p->out_logP[o] = (double*)(b + stage_off(c->N, c->Dp, 2));
-        p->out_steps[o] = (int*)(b + stage_off(c->N, c->Dp, 3));
-        p->out_acc[o] = (int*)(b + stage_off(c->N, c->Dp, 4));
-        p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
-        p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
         p->out_ne[o] = (int*)(b + stage_off(c->N, c->Dp, 7));
         p->out_nc[o] = (int*)(b + stage_off(c->N, c->Dp, 8));
     }
 }
 
+static void fill_mh(cpn_ctx* c, MHParams* p) {
+    memset(p, 0, sizeof *p);
+    fill_common(c, p);
+    p->cycle = c->d_cycle; p->cycle_len = c->cycle_len;
+    p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
+    p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
+}
+
+static void fill_slice(cpn_ctx* c, SliceParams* p) {
+    memset(p, 0, sizeof *p);
+    fill_common(c, p);
+    p->cycle = c->d_slice_cycle; p->cycle_len = c->slice_cycle_len;
+    p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->slice_cycle_len);
+    p->mean = c->d_eigmean[c->eig_cur]; p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
+}
+
 static void fill_hmc(cpn_ctx* c, HMCParams* p) {
     memset(p, 0, sizeof *p);
-    p->ens_x = c->d_x; p->ens_logL = c->d_logL; p->ens_logP = c->d_logP;
-    p->ens_n = c->N; p->Dp = c->Dp; p->D = c->D;
-    p->order = c->d_order[c->cur];
-    p->lo = c->d_lo; p->hi = c->d_hi;
+    fill_common(c, p);
     p->cov = c->d_covbuf[c->eig_cur]; p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
-    p->state = c->d_state;
     p->base_L = c->hmc_base_L;
     p->max_traj = c->cfg.maxmcmc;
-    p->chain_base = c->chain_counter;
-    p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
-    p->blob = c->d_blob;
-    const int nout = c->n_peers > 0 ? c->n_peers : 1;
-    p->n_out = nout;
-    for (int o = 0; o < nout; ++o) {
-        const int r = (o == 0) ? c->rank : (o <= c->rank ? o - 1 : o);
-        char* b = (c->n_peers > 0) ? (char*)c->stage_peer[r] + (size_t)c->stage_half * stage_bytes(c->N, c->Dp)
-                                   : (char*)c->d_stage_own;
-        p->out_x[o] = (double*)(b + stage_off(c->N, c->Dp, 0));
-        p->out_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 1));
-        p->out_logP[o] = (double*)(b + stage_off(c->N, c->Dp, 2));
-        p->out_steps[o] = (int*)(b + stage_off(c->N, c->Dp, 3));
-        p->out_acc[o] = (int*)(b + stage_off(c->N, c->Dp, 4));
-        p->out_start[o] = (int*)(b + stage_off(c->N, c->Dp, 5));
-        p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
-    }
 }
 
 // chains [j0, j1) of a batch with the context's sampler; START_SURVIVOR unless start rows are given

@@ -34,55 +34,20 @@
 // Replay: momenta, reflection normals and uniforms come from a tape recorded from the reference; the
 // trajectory is stored and the point picked from the normalised cumulative weights as np.random.choice does.
 #pragma once
-#include "sysinc.cuh"
-#include "group.cuh"
-#include "mh_kernel.cuh"
-#include "models.cuh"
-#include "rng.cuh"
-#include "state.cuh"
-#include "cpnest_b200.h"
+#include "chain_common.cuh"
 
 namespace cpn {
 
-struct HMCParams {
-    const double* ens_x;
-    const double* ens_logL;
-    const double* ens_logP;
-    int ens_n, Dp, D;
-    int start_mode;
-    const int* order;
-    int n_skip;
-    const double* start_x;
-    const double* start_logL;
-    const double* start_logP;
-    const double* lo;
-    const double* hi;
+struct HMCParams : ChainParams {        // nmcmc = trajectories per chain (1 in replay: the reference stops at the first accepted one)
     // ensemble statistics
     const double* cov;        // [D][D] ensemble covariance = inverse mass matrix (proposal.py:516)
     const double* eig_scale;  // [D] sqrt|lambda_i|
     const double* eig_vec;    // [D][Dp]
     double logdet;            // log det of the mass matrix (proposal.py:520); replay only (it cancels in every difference)
-    // chain control
-    const NSState* state;
-    int use_override;
-    double logLmin_override;
-    int nmcmc_override;       // trajectories per chain (1 in replay: the reference stops at the first accepted one)
     double dt_override;
     int L_override;           // > 0: trajectory length given (replay)
     int base_L;
     int max_traj;             // trajectories per chain at most (the reference loops until one is accepted)
-    int j0, j1;
-    unsigned long long chain_base;
-    uint32_t seed_lo, seed_hi;
-    const double* blob;
-    int n_out;
-    double* out_x[kMaxPeers];
-    double* out_logL[kMaxPeers];
-    double* out_logP[kMaxPeers];
-    int* out_steps[kMaxPeers];    // trajectories
-    int* out_acc[kMaxPeers];      // accepted trajectories (0 or 1)
-    int* out_start[kMaxPeers];
-    int* out_evals[kMaxPeers];
     // replay: per chain a flat tape, per trajectory { p0[D], normal[D] per reflection in order, u of the draw, u of the test }
     const double* tape;
     const long long* tape_off;
@@ -92,61 +57,25 @@ struct HMCParams {
 
 template <int G, int E, class Model, bool REPLAY>
 __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
-    if (!REPLAY && p.state != nullptr && p.state->done) return;
-    const Group<G> g;
-    const int cpb = kMHThreads / G;
-    const int nchains = p.j1 - p.j0;
-    int c = blockIdx.x * cpb + (int)threadIdx.x / G;
-    if ((c & ~(32 / G - 1)) >= nchains) return;
-    const bool valid = c < nchains;
-    if (!valid) c = nchains - 1;
-    const int j = p.j0 + c;
-
     extern __shared__ double smem[];
-    ModelCtx m;
-    m.blob = p.blob;
-    m.D = p.D;
-    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
-    Model::prepare(m);
-    set_valid_mask<G, E>(g, m);
-
-    const int D = p.D;
-    const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;
-    const int nmcmc = p.use_override ? p.nmcmc_override : p.state->nmcmc;
+    Chain<G, E, Model> ch;
+    if (!ch.begin(p, smem, REPLAY)) return;
+    const Group<G>& g = ch.g;
+    const ModelCtx& m = ch.m;
+    const int c = ch.c, D = p.D, nmcmc = ch.nmcmc;
+    const bool valid = ch.valid;
+    const double logLmin = ch.logLmin;
     const double dt = p.use_override ? p.dt_override : p.state->hmc_dt;
-    const unsigned long long chain_id = p.chain_base + (unsigned long long)j;
-    const uint32_t cid_lo = (uint32_t)chain_id, cid_hi = (uint32_t)(chain_id >> 32);
-
-    // ---- start point -------------------------------------------------------------------------
-    double q0[E], logL0, logP0;
-    int start_slot = -1;
-    {
-        const double* row;
-        if (p.start_mode == START_GIVEN) {
-            row = p.start_x + (size_t)c * p.Dp;
-            logL0 = p.start_logL[c];
-            logP0 = p.start_logP[c];
-        } else {
-            int slot;
-            if (p.start_mode == START_SELF) {
-                slot = j;
-            } else {
-                Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu, 0u, p.seed_lo, p.seed_hi);
-                slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
-            }
-            start_slot = slot;
-            row = p.ens_x + (size_t)slot * p.Dp;
-            logL0 = p.ens_logL[slot];
-            logP0 = p.ens_logP[slot];
-        }
-        load_row<G, E>(g, row, D, q0);
-    }
-    double blo[E], bhi[E], imass[E];
+    const uint32_t cid_lo = ch.cid_lo, cid_hi = ch.cid_hi;
+    double (&x)[E] = ch.x;
+    double (&blo)[E] = ch.blo;
+    double (&bhi)[E] = ch.bhi;
+    double& logL = ch.logL;
+    double& logP = ch.logP;
+    double imass[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int d = g.lane + e * G;
-        blo[e] = (d < D) ? __ldg(p.lo + d) : CPN_NEG_INF;
-        bhi[e] = (d < D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
         imass[e] = (d < D) ? __ldg(p.cov + (size_t)d * D + d) : 0.0;      // inverse_mass = diag(covariance), :519
     }
     const int Lmax = p.L_override > 0 ? p.L_override : p.base_L + 50;
@@ -181,9 +110,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
 
     int steps = 0, accepted = 0, evals = 0;
     bool active = true;
-    double x[E], logL = logL0, logP = logP0, last_logJ = 0.0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) x[e] = q0[e];
+    double last_logJ = 0.0;
     const double* tp = REPLAY ? p.tape + p.tape_off[c] : nullptr;
     const int npts = 2 * Lmax + 1;
     double* traj = REPLAY ? p.traj + (size_t)c * npts * (p.Dp + 3) : nullptr;
@@ -403,23 +330,8 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
         }
     }
 
+    ch.finish(p, steps, accepted, evals, 0, 0);
     if (valid) {
-        for (int o = 0; o < p.n_out; ++o) {
-            double* row = p.out_x[o] + (size_t)j * p.Dp;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int d = g.lane + e * G;
-                if (d < p.Dp) row[d] = (d < D) ? x[e] : 0.0;
-            }
-            if (g.lane == 0) {
-                p.out_logL[o][j] = logL;
-                p.out_logP[o][j] = logP;
-                p.out_steps[o][j] = steps;
-                p.out_acc[o][j] = accepted;
-                if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
-                if (p.out_evals[o] != nullptr) p.out_evals[o][j] = evals;
-            }
-        }
         if (p.logJ_out != nullptr && g.lane == 0) p.logJ_out[c] = last_logJ;
     }
 }

@@ -10,78 +10,22 @@
 // the prior MH test, the likelihood functor and the hard constraint logL > logLmin all run in
 // this kernel; nothing goes back to the host between steps.
 #pragma once
-#include "sysinc.cuh"
-#include "group.cuh"
-#include "models.cuh"
-#include "rng.cuh"
-#include "state.cuh"
-#include "cpnest_b200.h"
+#include "chain_common.cuh"
 
 namespace cpn {
 
-constexpr int kMHThreads = 128;
-constexpr int kMaxPeers = 8;
-constexpr int kRowSlack = 256;    // doubles of slack behind row arrays the chain kernels gather from (see gather_rows)
-
-enum StartMode { START_SURVIVOR = 0, START_SELF = 1, START_GIVEN = 2 };
-
-struct MHParams {
-    // ensemble = the live set, read-only during the launch
-    const double* ens_x;      // [ens_n][Dp]
-    const double* ens_logL;   // [ens_n]
-    const double* ens_logP;   // [ens_n]
-    int ens_n;
-    int Dp;
-    int D;
-    // chain start
-    int start_mode;
-    const int* order;         // live slots sorted by ascending logL; survivors are order[n_skip..ens_n)
-    int n_skip;
-    const double* start_x;    // START_GIVEN: [chains][Dp]
-    const double* start_logL;
-    const double* start_logP;
-    // box
-    const double* lo;
-    const double* hi;
+struct MHParams : ChainParams {
     // proposal cycle + eigen directions
     const uint8_t* cycle;
     int cycle_len;
     int cycle_pos0;
     const double* eig_scale;  // [D]     sqrt|lambda_i|
     const double* eig_vec;    // [D][Dp] row i = eigenvector i
-    // chain control
-    const NSState* state;     // logLmin / nmcmc / done live on the device
-    int use_override;
-    double logLmin_override;
-    int nmcmc_override;
-    int maxmcmc;
-    int j0, j1;               // chains [j0, j1) of the batch are evolved by this launch
-    unsigned long long chain_base;
-    uint32_t seed_lo, seed_hi;
-    const double* blob;
-    // outputs, replicated to every peer's staging area (n_out == 1 on a single GPU)
-    int n_out;
-    double* out_x[kMaxPeers];     // [K][Dp]
-    double* out_logL[kMaxPeers];
-    double* out_logP[kMaxPeers];
-    int* out_steps[kMaxPeers];
-    int* out_acc[kMaxPeers];
-    int* out_start[kMaxPeers];    // live slot the chain started from (-1: given start)
-    int* out_evals[kMaxPeers];    // likelihood evaluations of the chain
     // replay (parity) mode
     const double* tape;       // [chains][maxmcmc][8]
     int compat;               // fp32 rounding of LivePoint scalars (cpnest/parameter.pyx:96-120)
     double* states;           // [chains][maxmcmc][D] or null
 };
-
-template <int G, int E>
-__device__ __forceinline__ void load_row(const Group<G>& g, const double* row, int D, double (&v)[E]) {
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        int d = g.lane + e * G;
-        v[e] = (d < D) ? __ldg(row + d) : 0.0;
-    }
-}
 
 // ---- what one MCMC step consumes besides the chain's current point ---------------------------------
 // Nothing of it depends on the chain state, so the inputs (and the gather they imply) of step t+1 are
@@ -223,64 +167,20 @@ template <int G, int E, class Model, bool REPLAY>
 // E <= 4: 128 registers, 4 blocks = 16 warps per SM, one wave for up to 4736 chains of 16 lanes (one latency-bound
 // wave: time per launch is flat in the number of chains up to there)
 __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(const MHParams p) {
-    if (!REPLAY && p.state != nullptr && p.state->done) return;
-    const Group<G> g;
-    const int cpb = kMHThreads / G;
-    const int nchains = p.j1 - p.j0;
-    int c = blockIdx.x * cpb + (int)threadIdx.x / G;      // chain of this launch
-    if ((c & ~(32 / G - 1)) >= nchains) return;            // whole warp beyond the batch
-    const bool valid = c < nchains;
-    if (!valid) c = nchains - 1;                           // shadow a real chain, discard results
-    const int j = p.j0 + c;                                // chain of the batch
-
     extern __shared__ double smem[];
-    ModelCtx m;
-    m.blob = p.blob;
-    m.D = p.D;
-    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
-    Model::prepare(m);
-    set_valid_mask<G, E>(g, m);
-
-    const int D = p.D;
-    const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;
-    const int nmcmc = p.use_override ? p.nmcmc_override : p.state->nmcmc;
-    const int maxmcmc = p.maxmcmc;
-    const unsigned long long chain_id = p.chain_base + (unsigned long long)j;
-    const uint32_t cid_lo = (uint32_t)chain_id, cid_hi = (uint32_t)(chain_id >> 32);
-
-    // ---- start point -------------------------------------------------------------------------
-    double x[E], logL, logP;
-    int start_slot = -1;
-    {
-        const double* row;
-        if (p.start_mode == START_GIVEN) {
-            row = p.start_x + (size_t)c * p.Dp;
-            logL = p.start_logL[c];
-            logP = p.start_logP[c];
-        } else {
-            int slot;
-            if (p.start_mode == START_SELF) {
-                slot = j;
-            } else {
-                // a uniformly drawn survivor: every survivor satisfies logL > logLmin
-                Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu, 0u, p.seed_lo, p.seed_hi);
-                slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
-            }
-            start_slot = slot;
-            row = p.ens_x + (size_t)slot * p.Dp;
-            logL = p.ens_logL[slot];
-            logP = p.ens_logP[slot];
-        }
-        load_row<G, E>(g, row, D, x);
-    }
-    // the box, held in registers; coordinates beyond D get (-inf, +inf) so the test needs no branch
-    double blo[E], bhi[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int d = g.lane + e * G;
-        blo[e] = (d < D) ? __ldg(p.lo + d) : CPN_NEG_INF;
-        bhi[e] = (d < D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
-    }
+    Chain<G, E, Model> ch;
+    if (!ch.begin(p, smem, REPLAY)) return;
+    const Group<G>& g = ch.g;
+    const ModelCtx& m = ch.m;
+    const int c = ch.c, D = p.D, nmcmc = ch.nmcmc, maxmcmc = p.maxmcmc;
+    const bool valid = ch.valid;
+    const double logLmin = ch.logLmin;
+    const uint32_t cid_lo = ch.cid_lo, cid_hi = ch.cid_hi;
+    double (&x)[E] = ch.x;
+    double (&blo)[E] = ch.blo;
+    double (&bhi)[E] = ch.bhi;
+    double& logL = ch.logL;
+    double& logP = ch.logP;
 
     int steps = 0, accepted = 0, evals = 0;
     bool active = true;
@@ -414,25 +314,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         }
     }
 
-    // ---- hand the evolved point back (`producer_pipe.send`, sampler.py:246) ------------------
-    if (valid) {
-        for (int o = 0; o < p.n_out; ++o) {
-            double* row = p.out_x[o] + (size_t)j * p.Dp;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int d = g.lane + e * G;
-                if (d < p.Dp) row[d] = (d < D) ? x[e] : 0.0;
-            }
-            if (g.lane == 0) {
-                p.out_logL[o][j] = logL;
-                p.out_logP[o][j] = logP;
-                p.out_steps[o][j] = steps;
-                p.out_acc[o][j] = accepted;
-                if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
-                if (p.out_evals[o] != nullptr) p.out_evals[o][j] = evals;
-            }
-        }
-    }
+    ch.finish(p, steps, accepted, evals, 0, 0);
 }
 
 }  // namespace cpn

@@ -9,30 +9,11 @@
 // prior slice level), then shrinkage towards the current point until a point with log_prior above
 // the slice level AND logL > logLmin is found.
 #pragma once
-#include "sysinc.cuh"
-#include "group.cuh"
-#include "mh_kernel.cuh"
-#include "models.cuh"
-#include "rng.cuh"
-#include "state.cuh"
-#include "cpnest_b200.h"
+#include "chain_common.cuh"
 
 namespace cpn {
 
-struct SliceParams {
-    // ensemble = the live set, read-only during the launch
-    const double* ens_x;      // [ens_n][Dp]
-    const double* ens_logL;
-    const double* ens_logP;
-    int ens_n, Dp, D;
-    int start_mode;           // StartMode of mh_kernel.cuh
-    const int* order;
-    int n_skip;
-    const double* start_x;
-    const double* start_logL;
-    const double* start_logP;
-    const double* lo;
-    const double* hi;
+struct SliceParams : ChainParams {      // maxmcmc is also max_steps_out and max_slices (sampler.py:424-425)
     // direction cycle (cpn_slice_direction per slot) and the ensemble statistics behind the
     // correlated-Gaussian direction: N(mean, cov) = mean + sum_i z_i sqrt|lambda_i| v_i
     const uint8_t* cycle;
@@ -40,28 +21,7 @@ struct SliceParams {
     const double* mean;       // [D]
     const double* eig_scale;  // [D]
     const double* eig_vec;    // [D][Dp]
-    // chain control
-    const NSState* state;
-    int use_override;
-    double logLmin_override;
-    int nmcmc_override;
     double mu_override;       // slice length scale (SliceSampler.mu)
-    int maxmcmc;              // also max_steps_out and max_slices (sampler.py:424-425)
-    int j0, j1;
-    unsigned long long chain_base;
-    uint32_t seed_lo, seed_hi;
-    const double* blob;
-    // outputs, replicated to every peer's staging area
-    int n_out;
-    double* out_x[kMaxPeers];
-    double* out_logL[kMaxPeers];
-    double* out_logP[kMaxPeers];
-    int* out_steps[kMaxPeers];    // slices
-    int* out_acc[kMaxPeers];      // accepted slices
-    int* out_start[kMaxPeers];
-    int* out_evals[kMaxPeers];
-    int* out_ne[kMaxPeers];       // expansions, summed over the chain's slices
-    int* out_nc[kMaxPeers];       // contractions, summed over the chain's slices
     // replay (parity) mode: per chain a flat tape  { uL, direction data, Exp(1), uJ, X'_1, X'_2, ... } per slice,
     // direction data = {i0, i1} (differential) or the D-vector numpy returned (Gaussian kinds)
     const double* tape;
@@ -73,63 +33,21 @@ struct SliceParams {
 
 template <int G, int E, class Model, bool REPLAY>
 __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p) {
-    if (!REPLAY && p.state != nullptr && p.state->done) return;
-    const Group<G> g;
-    const int cpb = kMHThreads / G;
-    const int nchains = p.j1 - p.j0;
-    int c = blockIdx.x * cpb + (int)threadIdx.x / G;
-    if ((c & ~(32 / G - 1)) >= nchains) return;
-    const bool valid = c < nchains;
-    if (!valid) c = nchains - 1;
-    const int j = p.j0 + c;
-
     extern __shared__ double smem[];
-    ModelCtx m;
-    m.blob = p.blob;
-    m.D = p.D;
-    m.scratch = Model::kScratch ? smem + ((int)threadIdx.x / G) * kScratchRows * p.Dp : nullptr;
-    Model::prepare(m);
-    set_valid_mask<G, E>(g, m);
-
-    const int D = p.D;
-    const double logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;
-    const int nmcmc = p.use_override ? p.nmcmc_override : p.state->nmcmc;
+    Chain<G, E, Model> ch;
+    if (!ch.begin(p, smem, REPLAY)) return;
+    const Group<G>& g = ch.g;
+    const ModelCtx& m = ch.m;
+    const int c = ch.c, D = p.D, nmcmc = ch.nmcmc, maxmcmc = p.maxmcmc;
+    const bool valid = ch.valid;
+    const double logLmin = ch.logLmin;
     const double mu = p.use_override ? p.mu_override : p.state->slice_mu;
-    const int maxmcmc = p.maxmcmc;
-    const unsigned long long chain_id = p.chain_base + (unsigned long long)j;
-    const uint32_t cid_lo = (uint32_t)chain_id, cid_hi = (uint32_t)(chain_id >> 32);
-
-    // ---- start point: a member with logL > logLmin (sampler.py:471-478) ---------------------------
-    double x[E], logL, logP;
-    int start_slot = -1;
-    {
-        const double* row;
-        if (p.start_mode == START_GIVEN) {
-            row = p.start_x + (size_t)c * p.Dp;
-            logL = p.start_logL[c];
-            logP = p.start_logP[c];
-        } else {
-            int slot;
-            if (p.start_mode == START_SELF) {
-                slot = j;
-            } else {
-                Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu, 0u, p.seed_lo, p.seed_hi);
-                slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
-            }
-            start_slot = slot;
-            row = p.ens_x + (size_t)slot * p.Dp;
-            logL = p.ens_logL[slot];
-            logP = p.ens_logP[slot];
-        }
-        load_row<G, E>(g, row, D, x);
-    }
-    double blo[E], bhi[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int d = g.lane + e * G;
-        blo[e] = (d < D) ? __ldg(p.lo + d) : CPN_NEG_INF;
-        bhi[e] = (d < D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
-    }
+    const uint32_t cid_lo = ch.cid_lo, cid_hi = ch.cid_hi;
+    double (&x)[E] = ch.x;
+    double (&blo)[E] = ch.blo;
+    double (&bhi)[E] = ch.bhi;
+    double& logL = ch.logL;
+    double& logP = ch.logP;
 
     int steps = 0, accepted = 0, evals = 0, ne_sum = 0, nc_sum = 0;
     double Ne = 0.0, Nc = 0.0, L = 0.0, R = 0.0;
@@ -146,12 +64,7 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
 #pragma unroll
         for (int e = 0; e < E; ++e) out[e] = REPLAY ? __dadd_rn(__dmul_rn(dir[e], ts), x[e]) : fma(dir[e], ts, x[e]);
     };
-    auto in_box = [&](const double (&v)[E]) -> bool {
-        bool inb = true;
-#pragma unroll
-        for (int e = 0; e < E; ++e) inb = inb & (blo[e] < v[e]) & (v[e] < bhi[e]);      // strict, model.py:33
-        return g.all(inb);
-    };
+    auto in_box = [&](const double (&v)[E]) -> bool { return ch.in_box(v); };
 
     for (int s = 0;; ++s) {
         if (!__any_sync(FULL, active)) break;
@@ -351,25 +264,8 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
         }
     }
 
+    ch.finish(p, steps, accepted, evals, ne_sum, nc_sum);
     if (valid) {
-        for (int o = 0; o < p.n_out; ++o) {
-            double* row = p.out_x[o] + (size_t)j * p.Dp;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int d = g.lane + e * G;
-                if (d < p.Dp) row[d] = (d < D) ? x[e] : 0.0;
-            }
-            if (g.lane == 0) {
-                p.out_logL[o][j] = logL;
-                p.out_logP[o][j] = logP;
-                p.out_steps[o][j] = steps;
-                p.out_acc[o][j] = accepted;
-                if (p.out_start[o] != nullptr) p.out_start[o][j] = start_slot;
-                if (p.out_evals[o] != nullptr) p.out_evals[o][j] = evals;
-                if (p.out_ne[o] != nullptr) p.out_ne[o][j] = ne_sum;
-                if (p.out_nc[o] != nullptr) p.out_nc[o][j] = nc_sum;
-            }
-        }
         if (p.last != nullptr && g.lane == 0) {
             double* q = p.last + (size_t)c * 4;
             q[0] = Ne; q[1] = Nc; q[2] = L; q[3] = R;

@@ -29,4 +29,4 @@ torch.cuda.synchronize()
 t = np.array([[ev[i][k].elapsed_time(ev[i][k + 1]) for k in range(3)] for i in range(n)])
 tot = ev[0][0].elapsed_time(ev[n - 1][3]) / n
 print("lanes=%d " % lanes + "K=%d mean ms: select %.3f evolve %.3f insert %.3f | sum %.3f, wall/step %.3f" % (K, *t.mean(0), t.mean(0).sum(), tot))
-print("per-step evolve:", np.round(t[:12, 1], 3), "select:", np.round(t[:12, 0], 3), "insert:", np.round(t[:12, 2], 3))
+pass
