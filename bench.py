@@ -375,7 +375,7 @@ def main():
         worst, surv = part[:K], part[K:]
         logLmin = logL[worst].max()
         starts = surv[rs.randint(0, N - K, size=K)]
-        np.take(live, starts, axis=0, out=req)          # requests: start points drawn among the survivors
+        np.take(live, starts, axis=0, out=req, mode="clip")   # requests: start points drawn among the survivors (unbuffered)
         slots[:] = worst                                # the K worst slots are overwritten by the replies
         eng.evolve_host(req, logLmin, nm, slots=slots, replies=rep, steps=stp, accepted=acc_)
         live[worst] = rep
