@@ -7,8 +7,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -85,9 +83,7 @@ struct cpn_ctx {
     int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_new_ne, *d_new_nc, *d_rank;
     double *d_rho, *d_rho2;
     double* d_snew;
-    int *d_iota, *d_sorted_idx;     // large batches: the replacements are ranked with a stable radix sort (cub)
-    void* d_cub_tmp;
-    size_t cub_tmp_bytes;
+    double* d_seg_sorted;           // large batches: the replacements sorted inside segments of kRankSeg keys
     double *d_start_x, *d_start_logL, *d_start_logP;
     double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
     // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
@@ -123,6 +119,15 @@ struct cpn_ctx {
     bool live_ready;
     bool staged_external;       // replacements were injected by cpn_stage_replacements
 };
+
+// Host -> device copy that has LANDED when it returns.  cudaMemcpy from pageable memory may return once the data is
+// staged, before the DMA into device memory has completed; that DMA is ordered in the legacy default stream, but the
+// kernels of this library run on non-blocking streams, which the default stream does not order with.
+static cudaError_t h2d_sync(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(0);
+}
 
 template <class T>
 static int dalloc(T** p, size_t n) {
@@ -383,9 +388,9 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     CK(cudaEventCreateWithFlags(&c->ev_eig, cudaEventDisableTiming));
     const int N = c->N, D = c->D, Dp = c->Dp;
     if (dalloc(&c->d_lo, D) || dalloc(&c->d_hi, D) || dalloc(&c->d_blob, std::max<size_t>(nb, 1))) return 1;
-    CK(cudaMemcpy(c->d_lo, lo, D * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_hi, hi, D * sizeof(double), cudaMemcpyHostToDevice));
-    if (nb) CK(cudaMemcpy(c->d_blob, blob, nb * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d_sync(c->d_lo, lo, D * sizeof(double)));
+    CK(h2d_sync(c->d_hi, hi, D * sizeof(double)));
+    if (nb) CK(h2d_sync(c->d_blob, blob, nb * sizeof(double)));
     if (dalloc(&c->d_x, (size_t)N * Dp + kRowSlack) || dalloc(&c->d_logL, N) || dalloc(&c->d_logP, N)) return 1;
     for (int b = 0; b < 2; ++b)
         if (dalloc(&c->d_order[b], N) || dalloc(&c->d_skeys[b], N)) return 1;
@@ -403,18 +408,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
     if (dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
-    {
-        std::vector<int> iota(N);
-        for (int i = 0; i < N; ++i) iota[i] = i;
-        if (dalloc(&c->d_iota, N) || dalloc(&c->d_sorted_idx, N)) return 1;
-        CK(cudaMemcpy(c->d_iota, iota.data(), N * sizeof(int), cudaMemcpyHostToDevice));
-        c->cub_tmp_bytes = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, c->cub_tmp_bytes, (const double*)nullptr, (double*)nullptr, (const int*)nullptr,
-                                           (int*)nullptr, N));
-        char* tmp;
-        if (dalloc(&tmp, c->cub_tmp_bytes + 256)) return 1;
-        c->d_cub_tmp = tmp;
-    }
+    if (dalloc(&c->d_seg_sorted, (size_t)((N + kRankSeg - 1) / kRankSeg) * kRankSeg)) return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
@@ -435,7 +429,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         for (int i = 0; i < 96; ++i) cyc.push_back(pat[i % 6]);
         c->cycle_len = (int)cyc.size();
         if (dalloc(&c->d_cycle, 4096)) return 1;
-        CK(cudaMemcpy(c->d_cycle, cyc.data(), cyc.size(), cudaMemcpyHostToDevice));
+        CK(h2d_sync(c->d_cycle, cyc.data(), cyc.size()));
     }
     {
         // EnsembleSliceProposalCycle: equal weights (proposal.py:195), laid out deterministically until
@@ -444,7 +438,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         for (int i = 0; i < 99; ++i) cyc.push_back((uint8_t)(i % 3));
         c->slice_cycle_len = (int)cyc.size();
         if (dalloc(&c->d_slice_cycle, 4096)) return 1;
-        CK(cudaMemcpy(c->d_slice_cycle, cyc.data(), cyc.size(), cudaMemcpyHostToDevice));
+        CK(h2d_sync(c->d_slice_cycle, cyc.data(), cyc.size()));
     }
     {
         // base_L = 10 + int((h/l) d^(1/4)), base_dt = (1/base_L) l/h with l, h the shortest and longest prior range
@@ -474,7 +468,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->side);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
-                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_iota, c->d_sorted_idx, c->d_cub_tmp, c->d_start_x, c->d_start_logL,
+                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_seg_sorted, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
@@ -831,9 +825,9 @@ extern "C" int cpn_set_live(cpn_ctx* c, const double* rows, int32_t n) {
         lp[i] = rows[(size_t)i * (D + 2) + D + 1];
     }
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(c->d_x, x.data(), x.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_logL, l.data(), N * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_logP, lp.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d_sync(c->d_x, x.data(), x.size() * sizeof(double)));
+    CK(h2d_sync(c->d_logL, l.data(), N * sizeof(double)));
+    CK(h2d_sync(c->d_logP, lp.data(), N * sizeof(double)));
     if (sort_live(c)) return 1;
     if (cpn_update_ensemble_stats(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
@@ -979,18 +973,20 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
             c->launches += 1;
         }
     }
-    if (K <= 20000) {
-        // K^2 comparisons over a 2-D grid: fewer, shorter launches than a sort at this size
-        CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
+    if (K <= 2 * kRankSeg) {
+        // K^2 comparisons over a 2-D grid
         const int nt = (K + kRankTile - 1) / kRankTile;
         k_rank_count<<<dim3(nt, nt), kRankTile, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank);
         k_rank_scatter<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
+        c->launches += 2;
     } else {
-        // stable LSD radix sort of (logL, chain index): equal keys keep the chain order, the same rank as the counting rule
-        size_t bytes = c->cub_tmp_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, (const double*)c->d_new_logL, c->d_snew, (const int*)c->d_iota,
-                                           c->d_sorted_idx, K, 0, 64, c->stream));
-        k_rank_from_sorted<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_sorted_idx, K, c->d_rank);
+        // segments of kRankSeg keys ranked by counting, then merged by binary search
+        const int nt = kRankSeg / kRankTile, nseg = (K + kRankSeg - 1) / kRankSeg;
+        k_rank_count_seg<<<dim3(nt, nt, nseg), kRankTile, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank);
+        k_rank_seg_sorted<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_seg_sorted);
+        k_rank_merge_seg<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_seg_sorted, c->d_rank, c->d_snew);
+        c->launches += 3;
     }
     MergeParams m;
     memset(&m, 0, sizeof m);
@@ -1012,7 +1008,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     k_merge_commit<<<(c->N + K * c->Dp + T - 1) / T, T, 0, c->stream>>>(m);
     CKL();
     c->cur ^= 1;
-    c->launches += 3;
+    c->launches += 1;
     return 0;
 }
 
@@ -1183,7 +1179,7 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
     if ((size_t)bytes < tot) return fail("cpn_load_checkpoint: truncated blob (%lld of %zu bytes)", (long long)bytes, tot);
     const char* p = (const char*)blob + sizeof h;
     for (auto& sec : secs) {
-        if (sec.bytes) CK(cudaMemcpy(sec.dev, p, sec.bytes, cudaMemcpyHostToDevice));
+        if (sec.bytes) CK(h2d_sync(sec.dev, p, sec.bytes));
         p += (sec.bytes + 7) & ~(size_t)7;
     }
     *c->h_state = h.state;
@@ -1409,7 +1405,7 @@ extern "C" int cpn_eval_model(cpn_ctx* c, const double* x, int32_t n, double* lo
         for (int d = 0; d < D; ++d) xp[(size_t)i * Dp + d] = x[(size_t)i * D + d];
     double *dx, *dl, *dp;
     if (dalloc(&dx, xp.size()) || dalloc(&dl, n) || dalloc(&dp, n)) return 1;
-    CK(cudaMemcpy(dx, xp.data(), xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d_sync(dx, xp.data(), xp.size() * sizeof(double)));
     EvalParams e;
     memset(&e, 0, sizeof e);
     e.x = dx; e.logL = dl; e.logP = dp; e.n = n; e.D = D; e.Dp = Dp; e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob;
@@ -1431,7 +1427,7 @@ extern "C" int cpn_eval_gradients(cpn_ctx* c, const double* x, int32_t n, double
         for (int d = 0; d < D; ++d) xp[(size_t)i * Dp + d] = x[(size_t)i * D + d];
     double *dx, *dl, *dp, *dgl, *dgv;
     if (dalloc(&dx, xp.size()) || dalloc(&dl, n) || dalloc(&dp, n) || dalloc(&dgl, xp.size()) || dalloc(&dgv, xp.size())) return 1;
-    CK(cudaMemcpy(dx, xp.data(), xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d_sync(dx, xp.data(), xp.size() * sizeof(double)));
     EvalParams e;
     memset(&e, 0, sizeof e);
     e.x = dx; e.logL = dl; e.logP = dp; e.n = n; e.D = D; e.Dp = Dp; e.lo = c->d_lo; e.hi = c->d_hi; e.blob = c->d_blob;
@@ -1481,13 +1477,13 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
         dalloc(&dop, C) || dalloc(&dst, C) || dalloc(&dac, C) || dalloc(&dEL, P) || dalloc(&dEP, P))
         return 1;
     if (states && dalloc(&dstates, (size_t)C * maxmcmc * D)) return 1;
-    CK(cudaMemcpy(dex, ex.data(), ex.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsl, sl.data(), C * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsp, sp.data(), C * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dev, ev.data(), ev.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(des, es.data(), D * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dtape, tape, (size_t)C * maxmcmc * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d_sync(dex, ex.data(), ex.size() * sizeof(double)));
+    CK(h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)));
+    CK(h2d_sync(dsl, sl.data(), C * sizeof(double)));
+    CK(h2d_sync(dsp, sp.data(), C * sizeof(double)));
+    CK(h2d_sync(dev, ev.data(), ev.size() * sizeof(double)));
+    CK(h2d_sync(des, es.data(), D * sizeof(double)));
+    CK(h2d_sync(dtape, tape, (size_t)C * maxmcmc * 8 * sizeof(double)));
     MHParams p;
     memset(&p, 0, sizeof p);
     p.ens_x = dex; p.ens_logL = dEL; p.ens_logP = dEP; p.ens_n = P; p.Dp = Dp; p.D = D;
@@ -1553,12 +1549,12 @@ extern "C" int cpn_replay_slice(cpn_ctx* c, int32_t P, const double* ensemble, i
         dalloc(&doff, C + 1) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) || dalloc(&dst, C) ||
         dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dlast, (size_t)C * 4) || dalloc(&dEL, P) || dalloc(&dEP, P))
         return 1;
-    CK(cudaMemcpy(dex, ex.data(), ex.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsl, sl.data(), C * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsp, sp.data(), C * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dtape, tape, ntape * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(doff, tape_off, (C + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(h2d_sync(dex, ex.data(), ex.size() * sizeof(double)));
+    CK(h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)));
+    CK(h2d_sync(dsl, sl.data(), C * sizeof(double)));
+    CK(h2d_sync(dsp, sp.data(), C * sizeof(double)));
+    CK(h2d_sync(dtape, tape, ntape * sizeof(double)));
+    CK(h2d_sync(doff, tape_off, (C + 1) * sizeof(long long)));
     SliceParams p;
     memset(&p, 0, sizeof p);
     p.ens_x = dex; p.ens_logL = dEL; p.ens_logP = dEP; p.ens_n = P; p.Dp = Dp; p.D = D;
@@ -1613,12 +1609,12 @@ extern "C" int cpn_replay_hmc(cpn_ctx* c, int32_t C, const double* start, const 
         dalloc(&doff, C + 1) || dalloc(&dtraj, ntraj) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) ||
         dalloc(&dst, C) || dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dlj, C))
         return 1;
-    CK(cudaMemcpy(dsx, sx.data(), sx.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsl, sl.data(), C * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsp, sp.data(), C * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dcov, cov, (size_t)D * D * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dtape, tape, ntape * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(doff, tape_off, (C + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)));
+    CK(h2d_sync(dsl, sl.data(), C * sizeof(double)));
+    CK(h2d_sync(dsp, sp.data(), C * sizeof(double)));
+    CK(h2d_sync(dcov, cov, (size_t)D * D * sizeof(double)));
+    CK(h2d_sync(dtape, tape, ntape * sizeof(double)));
+    CK(h2d_sync(doff, tape_off, (C + 1) * sizeof(long long)));
     HMCParams p;
     memset(&p, 0, sizeof p);
     p.ens_n = 0; p.Dp = Dp; p.D = D;
@@ -1716,7 +1712,7 @@ extern "C" int cpn_ns_increment(cpn_ctx* c, const double* logL, int32_t K, int32
     if (grow_logs(c, c->dead_upper + K + 1)) return 1;
     double* d;
     if (dalloc(&d, K)) return 1;
-    CK(cudaMemcpy(d, logL, K * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d_sync(d, logL, K * sizeof(double)));
     AccParams a;
     memset(&a, 0, sizeof a);
     a.st = c->d_state; a.skeys = d; a.N = nlive; a.K = K; a.mode = ns_mode; a.final_sweep = 1; a.nlive_run = c->N;
@@ -1753,7 +1749,7 @@ extern "C" int cpn_philox(cpn_ctx* c, const uint32_t* ctr, const uint32_t* key, 
     CK(cudaSetDevice(c->cfg.device));
     uint32_t *dc, *dout;
     if (dalloc(&dc, (size_t)4 * n) || dalloc(&dout, (size_t)4 * n)) return 1;
-    CK(cudaMemcpy(dc, ctr, (size_t)4 * n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(h2d_sync(dc, ctr, (size_t)4 * n * sizeof(uint32_t)));
     k_philox_kat<<<(n + 127) / 128, 128, 0, c->stream>>>(dc, key[0], key[1], n, dout);
     CKL();
     CK(cudaStreamSynchronize(c->stream));

