@@ -96,6 +96,9 @@ struct cpn_ctx {
     int eig_pending_age;        // batches started since the pending refresh was launched
     cudaStream_t side;
     cudaEvent_t ev_main, ev_cov, ev_eig;
+    cudaStream_t acc_stream;    // evidence accumulation of a batch, beside its chain kernel
+    cudaEvent_t ev_thr, ev_acc;
+    bool acc_pending;           // an accumulation is in flight that the main stream has not waited for yet
     uint8_t* d_cycle;
     int cycle_len;
     uint8_t* d_slice_cycle;     // EnsembleSliceProposalCycle
@@ -255,7 +258,17 @@ static int grow_logs(cpn_ctx* c, long long need) {
     return 0;
 }
 
+// everything that reads what k_ns_accumulate writes (counters, evidence, stop flag) first joins its stream
+static int join_acc(cpn_ctx* c) {
+    if (c->acc_pending) {
+        CK(cudaStreamWaitEvent(c->stream, c->ev_acc, 0));
+        c->acc_pending = false;
+    }
+    return 0;
+}
+
 static int fetch_state(cpn_ctx* c) {
+    if (join_acc(c)) return 1;
     CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(NSState), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->dead_upper = c->h_state->iteration;
@@ -263,6 +276,7 @@ static int fetch_state(cpn_ctx* c) {
 }
 
 static int push_state(cpn_ctx* c) {
+    if (join_acc(c)) return 1;
     CK(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(NSState), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -386,6 +400,9 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_cov, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_eig, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->acc_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_thr, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_acc, cudaEventDisableTiming));
     const int N = c->N, D = c->D, Dp = c->Dp;
     if (dalloc(&c->d_lo, D) || dalloc(&c->d_hi, D) || dalloc(&c->d_blob, std::max<size_t>(nb, 1))) return 1;
     CK(h2d_sync(c->d_lo, lo, D * sizeof(double)));
@@ -467,6 +484,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->side);
+    cudaStreamSynchronize(c->acc_stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_seg_sorted, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
@@ -479,6 +497,8 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaEventDestroy(c->ev);
     cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_cov); cudaEventDestroy(c->ev_eig);
     cudaStreamDestroy(c->side);
+    cudaStreamDestroy(c->acc_stream);
+    cudaEventDestroy(c->ev_thr); cudaEventDestroy(c->ev_acc);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -864,10 +884,16 @@ extern "C" int cpn_select_and_accumulate(cpn_ctx* c, int32_t K) {
     a.st = c->d_state; a.skeys = c->d_skeys[c->cur]; a.N = c->N; a.K = K; a.mode = c->cfg.ns_mode;
     a.final_sweep = 0; a.nlive_run = c->N; a.hist_logL = c->d_hist_logL; a.hist_logvol = c->d_hist_logvol;
     a.update_threshold = 1;
-    k_ns_accumulate<<<1, kAccThreads, 0, c->stream>>>(a);
+    if (join_acc(c)) return 1;
+    k_ns_threshold<<<1, 1, 0, c->stream>>>(c->d_state, c->d_skeys[c->cur], c->N, K);
+    CK(cudaEventRecord(c->ev_thr, c->stream));
+    CK(cudaStreamWaitEvent(c->acc_stream, c->ev_thr, 0));
+    k_ns_accumulate<<<1, kAccThreads, 0, c->acc_stream>>>(a);
     CKL();
+    CK(cudaEventRecord(c->ev_acc, c->acc_stream));
+    c->acc_pending = true;
     c->dead_upper += K;
-    c->launches += 1;
+    c->launches += 2;
     return 0;
 }
 
@@ -959,6 +985,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     if (check_K(c, K)) return 1;
     CK(cudaSetDevice(c->cfg.device));
     const int T = 256;
+    if (join_acc(c)) return 1;                 // the merge appends at the counters the accumulation has advanced
     if (!c->staged_external) {
         // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
         // control, and the batch counters
@@ -1112,6 +1139,7 @@ static std::vector<CkptSection> ckpt_sections(cpn_ctx* c, long long n_dead, long
 // finish what is in flight (a statistics refresh on the side stream) so that the arrays are final
 static int ckpt_quiesce(cpn_ctx* c) {
     CK(cudaSetDevice(c->cfg.device));
+    if (join_acc(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->side));
     c->wait_cov = false;
@@ -1194,6 +1222,7 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
 extern "C" int cpn_synchronize(cpn_ctx* c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));
+    if (join_acc(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1201,6 +1230,7 @@ extern "C" int cpn_synchronize(cpn_ctx* c) {
 extern "C" int cpn_set_stream(cpn_ctx* c, void* stream) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));
+    if (join_acc(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     c->stream = stream ? (cudaStream_t)stream : c->own_stream;
     return 0;

@@ -109,19 +109,23 @@ struct AccParams {
     int update_threshold;  // 0 for the raw integrator parity entry
 };
 
+// What the chains of a batch need from the selection: whether the run goes on (`while self.condition > self.tolerance`,
+// NestedSampling.py:451: a condition <= tolerance seen by the previous batch ends the run), the threshold = K-th worst
+// logL (:374) and logLmax.  One thread; the evidence accumulation of the same batch (k_ns_accumulate) then runs on its
+// own stream beside the chain kernel, which does not depend on it.
+__global__ void k_ns_threshold(NSState* st, const double* __restrict__ skeys, int N, int K) {
+    if (st->done) return;
+    if (st->stop_next) { st->done = 1; return; }
+    st->logLmin = skeys[K - 1];
+    st->logLmax = skeys[N - 1];
+}
+
 __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p) {
     __shared__ LSE sh_lse[kAccThreads];
     __shared__ double sh_scan[kAccThreads];
     NSState* st = p.st;
     const int tid = threadIdx.x;
-    if (!p.final_sweep) {
-        if (st->done) return;
-        if (st->stop_next) {               // `while self.condition > self.tolerance` (NestedSampling.py:451)
-            __syncthreads();
-            if (tid == 0) st->done = 1;
-            return;
-        }
-    }
+    if (!p.final_sweep && st->done) return;     // k_ns_threshold of this batch has turned stop_next into done
     const double logw0 = st->logw, logZ0 = st->logZ, B0 = st->B;
     const long long hist0 = st->n_hist;
     const int K = p.K, N = p.N;
@@ -193,9 +197,7 @@ __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p
     if (p.final_sweep) return;
     st->batches += 1;
     st->n_ins += K;                                                  // one insertion index per replacement
-    st->logLmin = p.skeys[K - 1];                                    // NestedSampling.py:374
     const double logLmax = p.skeys[N - 1];
-    st->logLmax = logLmax;
     const double cond = d_logaddexp(logZ, logLmax - (double)it0 / (double)p.nlive_run) - logZ;   // :332
     st->condition = cond;
     if (!(cond > st->tolerance)) st->stop_next = 1;
