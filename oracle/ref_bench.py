@@ -80,17 +80,78 @@ def _worker_reference(args):
         smp.evolution_points.append(p)
     logLmin = float(np.quantile([p.logL for p in smp.evolution_points], q))
     smp.proposal.set_ensemble(smp.evolution_points)
-    Counter.n = 0
     gen = smp.yield_sample(logLmin)
-    t0 = time.perf_counter()
-    chains = 0
-    while time.perf_counter() - t0 < budget_s:
-        next(gen)
-        chains += 1
-        if chains % (poolsize // 4) == 0:
-            smp.proposal.set_ensemble(smp.evolution_points)      # sampler.py:252-254
-    dt = time.perf_counter() - t0
-    return Counter.n, smp.mcmc_counter, smp.mcmc_accepted, chains, dt
+    state = dict(chains=0)
+
+    def run(budget):
+        """evolve the pool for `budget` seconds; (likelihood calls, MCMC steps, accepted, chains, seconds) of this leg"""
+        n0, s0, a0, c0 = Counter.n, smp.mcmc_counter, smp.mcmc_accepted, state["chains"]
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < budget:
+            next(gen)
+            state["chains"] += 1
+            if state["chains"] % (poolsize // 4) == 0:
+                smp.proposal.set_ensemble(smp.evolution_points)      # sampler.py:252-254
+        dt = time.perf_counter() - t0
+        return Counter.n - n0, smp.mcmc_counter - s0, smp.mcmc_accepted - a0, state["chains"] - c0, dt
+
+    if budget_s is None:
+        return run                      # persistent worker: the caller drives the legs
+    return run(budget_s)
+
+
+def _persistent_worker(conn, args):
+    run = _worker_reference(args)
+    conn.send("ready")
+    while True:
+        budget = conn.recv()
+        if budget is None:
+            break
+        conn.send(run(budget))
+
+
+class ReferencePool(object):
+    """`cores` forked processes, each holding one reference MH sampler with its pool; `leg(budget_s)` lets all of them
+    evolve for budget_s seconds and returns the summed counts.  Set-up (fork, pool of 1000 points) is paid once."""
+
+    def __init__(self, dim=50, cores=None, poolsize=1000, nmcmc=100, maxmcmc=100, quantile=0.2, seed=1234):
+        if not reference_available():
+            raise RuntimeError("oracle/_ref is absent")
+        self.cores = cores or os.cpu_count() or 1
+        self.desc = (dim, poolsize, nmcmc, quantile)
+        ctx = mp.get_context("fork")
+        self.procs, self.conns = [], []
+        for i in range(self.cores):
+            a, b = ctx.Pipe()
+            pr = ctx.Process(target=_persistent_worker, args=(b, (dim, poolsize, nmcmc, maxmcmc, quantile, None, seed + i)), daemon=True)
+            pr.start()
+            self.procs.append(pr)
+            self.conns.append(a)
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    def leg(self, budget_s):
+        for c in self.conns:
+            c.send(float(budget_s))
+        res = [c.recv() for c in self.conns]
+        tmax = max(r[4] for r in res)
+        evals, steps, acc, chains = (sum(r[k] for r in res) for k in range(4))
+        dim, poolsize, nmcmc, quantile = self.desc
+        return dict(value=evals / tmax, unit="likelihood evals/s", cores=self.cores, kind="reference", steps_per_s=steps / tmax,
+                    acceptance=acc / max(1, steps), chains=chains, wall_s=tmax,
+                    sample=("unmodified reference (oracle/_ref) MH sampler (DefaultProposalCycle) on the %d-D Gaussian of "
+                            "examples/test_50d.py: %d forked processes x %.1f s, poolsize %d, Nmcmc %d, threshold at the %.0f%% "
+                            "pool quantile; %d chains, %d MCMC steps, %d likelihood calls" % (
+                                dim, self.cores, budget_s, poolsize, nmcmc, 100 * quantile, chains, steps, evals)))
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for pr in self.procs:
+            pr.join(timeout=5)
 
 
 def _worker_port(args):
