@@ -24,6 +24,7 @@ class cpn_config(C.Structure):
         ("nmcmc_init", C.c_int32), ("functor", C.c_int32), ("lanes", C.c_int32), ("ns_mode", C.c_int32),
         ("seed", C.c_uint64), ("nmcmc_safety", C.c_double), ("adapt_nmcmc", C.c_int32),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("sampler", C.c_int32), ("rho_target", C.c_double),
+        ("mix", C.c_int32 * 3), ("reserved_", C.c_int32),
     ]
 
 
@@ -35,10 +36,15 @@ class cpn_state(C.Structure):
         ("total_steps", C.c_int64), ("total_accepted", C.c_int64), ("total_evals", C.c_int64),
         ("failed_chains", C.c_int64), ("nmcmc", C.c_int32), ("done", C.c_int32),
         ("slice_mu", C.c_double), ("hmc_dt", C.c_double),
+        ("rho_kind", C.c_double * 3), ("nmcmc_kind", C.c_int32 * 3), ("chains_kind", C.c_int32 * 3),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {}
+        for n, _ in self._fields_:
+            v = getattr(self, n)
+            d[n] = list(v) if hasattr(v, "__len__") else v
+        return d
 
 
 FUNCTORS = dict(gaussian_iid=0, gaussian_corr=1, eggbox=2, rosenbrock=3, ackley=4, ring=5,

@@ -43,11 +43,12 @@ class CPNest(object):
     maxmcmc   : maximum chain length
     nthreads  : in the reference, the number of sampler processes == points replaced per iteration
                 (cpnest/NestedSampling.py:324); here a lower bound for the batch size, see `batch`
-    nslice    : number of slice samplers.  The reference mixes sampler kinds across its processes; one device
-                context runs ONE kind per run: nslice == nthreads (as in the reference's own tests and examples,
-                tests/test_2d_slice.py:30, examples/test_50d.py:37) selects the slice kernel, a mixed
-                population raises NotImplementedError
-    nhamiltonian : number of HMC samplers; nhamiltonian == nthreads selects the constrained-leapfrog kernel
+    nslice    : number of slice samplers.  nslice == nthreads (as in the reference's own tests and examples,
+                tests/test_2d_slice.py:30, examples/test_50d.py:37) runs the slice kernel alone.  A mixed population
+                (the reference spreads the kinds over its processes, cpnest/cpnest.py:197-261) splits the chains of every
+                batch in the proportions (nthreads - nslice - nhamiltonian) : nslice : nhamiltonian; each kind keeps its
+                own chain-length controller and the kinds' kernels run side by side
+    nhamiltonian : number of HMC samplers; nhamiltonian == nthreads runs the constrained-leapfrog kernel alone
                 (tests/test_2d_hmc.py:30).  The reflection normal is the functor's analytic gradient
     proposals : dict(mhs=ProposalCycle subclass, sli=EnsembleSliceProposalCycle subclass, hmc=HamiltonianProposalCycle
                 subclass); device proposals only
@@ -71,13 +72,14 @@ class CPNest(object):
         self.log_file = LogFile(os.path.join(self.output, "cpnest.log"), verbose=self.verbose)
         with self.log_file:
             n_mh = self.nthreads - nhamiltonian - nslice
-            kinds = [k for k, n in (("mh", n_mh), ("slice", nslice), ("hmc", nhamiltonian)) if n > 0]
-            if len(kinds) != 1:
-                raise NotImplementedError(
-                    "nthreads={0}, nslice={1}, nhamiltonian={2}: one device context runs a single sampler kind; "
-                    "use nslice == nthreads (or nhamiltonian == nthreads) for a pure population".format(
-                        self.nthreads, nslice, nhamiltonian))
-            self.sampler_kind = kinds[0]
+            if n_mh < 0 or nslice < 0 or nhamiltonian < 0:
+                raise ValueError("nthreads={0} < nslice={1} + nhamiltonian={2}".format(self.nthreads, nslice, nhamiltonian))
+            self.population = dict(mh=n_mh, slice=nslice, hmc=nhamiltonian)
+            kinds = [k for k in ("mh", "slice", "hmc") if self.population[k] > 0]
+            if not kinds:
+                raise ValueError("no sampler requested: nthreads={0}".format(self.nthreads))
+            self.sampler_kind = kinds[0] if len(kinds) == 1 else "+".join(kinds)
+            primary = kinds[0]
             if n_periodic_checkpoint is not None:
                 self.logger.critical("The n_periodic_checkpoint kwarg is deprecated, use periodic_checkpoint_interval instead.")
             from .proposal import DefaultProposalCycle, EnsembleSliceProposalCycle, HamiltonianProposalCycle
@@ -104,26 +106,31 @@ class CPNest(object):
             self.seed = 1234 if seed is None else seed
             self.maxmcmc = maxmcmc
             self.batch = int(batch) if batch else max(min(self.nthreads, nlive // 2), nlive // 4, 1)
-            self.batch = max(1, min(self.batch, nlive - 3))
+            self.batch = max(len(kinds), min(self.batch, nlive - 3))
             self.logger.critical("Running on CUDA device {0} with {1} chains per batch".format(device, self.batch))
             # NestedSampler seeds numpy, then the proposal cycle is drawn (cpnest/cpnest.py:184-207)
             self.NS = NestedSampler(self.user, nlive=nlive, output=output, verbose=verbose, seed=self.seed,
                                     prior_sampling=self.prior_sampling)
             functor, params = self.user.get_device_functor()
             self.engine = Engine(functor, self.user.bounds, nlive=nlive, maxmcmc=maxmcmc, seed=self.seed, params=params,
-                                 device=device, lanes=lanes, rho_target=rho_target, sampler=self.sampler_kind)
-            if self.sampler_kind == "slice":
-                self.proposal = proposals["sli"](model=self.user)        # cpnest/cpnest.py:252
-                self.engine.set_slice_cycle(self.proposal.device_cycle())
-            elif self.sampler_kind == "hmc":
-                self.proposal = proposals["hmc"](model=self.user)        # cpnest/cpnest.py:231
-                self.proposal.device_cycle()
+                                 device=device, lanes=lanes, rho_target=rho_target, sampler=primary,
+                                 mix=self.population if len(kinds) > 1 else None)
+            # one proposal object per sampler kind present, in the reference's order of construction
+            # (cpnest/cpnest.py:197-261: MH samplers, then HMC, then slice); self.proposal is the first kind's
+            self.proposals = {}
+            if "mh" in kinds:
+                self.proposals["mh"] = proposals["mhs"]()                       # cpnest/cpnest.py:207
+                self.engine.set_cycle(self.proposals["mh"].device_cycle())
+            if "hmc" in kinds:
+                self.proposals["hmc"] = proposals["hmc"](model=self.user)       # cpnest/cpnest.py:231
+                self.proposals["hmc"].device_cycle()
                 if functor in ("gaussian_mean_sigma", "gaussian_mixture"):
                     self.logger.warning("HMC with a non-flat prior inherits the reference's trajectory-draw + energy-test rule, "
                                         "which is not exactly reversible when the potential varies (DESIGN.md); prefer MH or slice")
-            else:
-                self.proposal = proposals["mhs"]()                       # cpnest/cpnest.py:207
-                self.engine.set_cycle(self.proposal.device_cycle())
+            if "slice" in kinds:
+                self.proposals["slice"] = proposals["sli"](model=self.user)     # cpnest/cpnest.py:252
+                self.engine.set_slice_cycle(self.proposals["slice"].device_cycle())
+            self.proposal = self.proposals[primary]
             if check_functor:
                 self._check_functor()
 

@@ -121,7 +121,51 @@ struct cpn_ctx {
     bool user_flat_prior;
     bool live_ready;
     bool staged_external;       // replacements were injected by cpn_stage_replacements
+    // sampler population: relative numbers of MH / slice / HMC chains in a batch (cpn_config.mix; a pure population
+    // has one non-zero entry).  `primary` is the kind whose controller cpn_get_state reports.
+    int mix[kNumKinds];
+    int primary;
+    bool mixed;
+    cudaStream_t kind_stream[kNumKinds];   // the kinds' chain kernels of a batch run side by side
+    cudaEvent_t ev_fork, ev_kind[kNumKinds];
+    cudaStream_t chain_stream;  // stream of the chain launch in progress (null: c->stream)
+    int last_kb[kNumKinds + 1]; // chain ranges of the kinds in the last evolved batch
 };
+static inline cudaStream_t chain_stream(cpn_ctx* c) { return c->chain_stream ? c->chain_stream : c->stream; }
+
+// The K chains of a batch by sampler kind: kind s owns [kb[s], kb[s+1]).  Largest-remainder split of K in the
+// proportions c->mix, at least one chain for every kind present (the reference gives every sampler process one
+// of the nthreads worst points per iteration, cpnest/NestedSampling.py:324-342).
+static int kind_ranges(cpn_ctx* c, int K, int* kb) {
+    long long W = 0;
+    int active = 0;
+    for (int s = 0; s < kNumKinds; ++s) { W += c->mix[s]; active += c->mix[s] > 0; }
+    if (K < active) return fail("K=%d chains cannot hold %d sampler kinds", K, active);
+    int n[kNumKinds];
+    long long rem[kNumKinds];
+    int used = 0;
+    for (int s = 0; s < kNumKinds; ++s) {
+        const long long q = (long long)K * c->mix[s];
+        n[s] = (int)(q / W);
+        rem[s] = q % W;
+        if (c->mix[s] > 0 && n[s] == 0) { n[s] = 1; rem[s] = 0; }
+        used += n[s];
+    }
+    while (used < K) {          // hand out what the floors left, largest remainder first (ties: lower kind)
+        int best = -1;
+        for (int s = 0; s < kNumKinds; ++s)
+            if (c->mix[s] > 0 && (best < 0 || rem[s] > rem[best])) best = s;
+        n[best] += 1; rem[best] -= W; used += 1;
+    }
+    while (used > K) {          // the minimum of one chain per kind overshot: take from the largest
+        int best = 0;
+        for (int s = 1; s < kNumKinds; ++s) if (n[s] > n[best]) best = s;
+        n[best] -= 1; used -= 1;
+    }
+    kb[0] = 0;
+    for (int s = 0; s < kNumKinds; ++s) kb[s + 1] = kb[s] + n[s];
+    return 0;
+}
 
 // Host -> device copy that has LANDED when it returns.  cudaMemcpy from pageable memory may return once the data is
 // staged, before the DMA into device memory has completed; that DMA is ordered in the legacy default stream, but the
@@ -189,7 +233,7 @@ static int user_launch(cpn_ctx* c, const char* kind, int G, int E, const void* p
     const int nb = (n + cpb - 1) / cpb;
     const size_t sm = (size_t)cpb * kScratchRows * Dp * sizeof(double);
     char err[4096];
-    if (rtc_launch(c->rtc, kind, G, E, params, nb, threads, sm, c->stream, err, sizeof err)) return fail("%s", err);
+    if (rtc_launch(c->rtc, kind, G, E, params, nb, threads, sm, chain_stream(c), err, sizeof err)) return fail("%s", err);
     return 0;
 }
 static int run_eval(cpn_ctx* c, int G, int E, const EvalParams& p) {
@@ -202,7 +246,7 @@ static int run_mh(cpn_ctx* c, int G, int E, int replay, const MHParams& p) {
         if (replay) return fail("replay entry points are not available for a user functor");
         return user_launch(c, "mh", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
     }
-    if (kMH[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no MH kernel for G=%d E=%d", G, E);
+    if (kMH[c->cfg.functor](G, E, replay, p, chain_stream(c))) return fail("no MH kernel for G=%d E=%d", G, E);
     return 0;
 }
 static int run_slice(cpn_ctx* c, int G, int E, int replay, const SliceParams& p) {
@@ -210,7 +254,7 @@ static int run_slice(cpn_ctx* c, int G, int E, int replay, const SliceParams& p)
         if (replay) return fail("replay entry points are not available for a user functor");
         return user_launch(c, "slice", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
     }
-    if (kSlice[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no slice kernel for G=%d E=%d", G, E);
+    if (kSlice[c->cfg.functor](G, E, replay, p, chain_stream(c))) return fail("no slice kernel for G=%d E=%d", G, E);
     return 0;
 }
 static int run_hmc(cpn_ctx* c, int G, int E, int replay, const HMCParams& p) {
@@ -218,7 +262,7 @@ static int run_hmc(cpn_ctx* c, int G, int E, int replay, const HMCParams& p) {
         if (replay) return fail("replay entry points are not available for a user functor");
         return user_launch(c, "hmc", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
     }
-    if (kHMC[c->cfg.functor](G, E, replay, p, c->stream)) return fail("no HMC kernel for G=%d E=%d", G, E);
+    if (kHMC[c->cfg.functor](G, E, replay, p, chain_stream(c))) return fail("no HMC kernel for G=%d E=%d", G, E);
     return 0;
 }
 
@@ -293,19 +337,21 @@ static void init_state(cpn_ctx* c, NSState* s) {
     s->condition = INFINITY;
     s->tolerance = 0.1;                                   // NestedSampler(stopping=0.1)
     const int n0 = c->cfg.nmcmc_init > 0 ? c->cfg.nmcmc_init : std::max(1, c->cfg.maxmcmc / 10);   // sampler.py:79
-    s->nmcmc = std::min(n0, c->cfg.maxmcmc);
-    s->nmcmc_exact = (double)s->nmcmc;
+    for (int k = 0; k < kNumKinds; ++k) {
+        s->ctl[k].nmcmc = std::min(n0, c->cfg.maxmcmc);
+        s->ctl[k].nmcmc_exact = (double)s->ctl[k].nmcmc;
+        // measured on the 50-D Gaussian (nlive 1e4, 8 seeds each): MH chains are unbiased at 0.1; slice chains show
+        // +1.0 sigma (+0.09 nats) mean deviation of logZ at 0.1 and none at 0.05
+        s->ctl[k].rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : (k == CPN_SAMPLER_SLICE ? 0.05 : 0.1);
+        s->ctl[k].rho_max = -1.0;
+    }
     s->nmcmc_safety = c->cfg.nmcmc_safety > 0 ? c->cfg.nmcmc_safety : 5.0;
     s->nmcmc_tau = (double)c->N / s->nmcmc_safety;        // tau = poolsize / safety (sampler.py:166)
     s->maxmcmc = c->cfg.maxmcmc;
     s->adapt = c->cfg.adapt_nmcmc;
-    // measured on the 50-D Gaussian (nlive 1e4, 8 seeds each): MH chains are unbiased at 0.1; slice chains show
-    // +1.0 sigma (+0.09 nats) mean deviation of logZ at 0.1 and none at 0.05
-    s->rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : (c->cfg.sampler == CPN_SAMPLER_SLICE ? 0.05 : 0.1);
-    s->rho_max = -1.0;
     s->slice_mu = 1.0;                                    // SliceSampler.reset (sampler.py:422)
     s->hmc_dt = c->hmc_base_dt;                           // dt = base_dt * scale, scale = 1 (proposal.py:395-396, 550)
-    s->sampler = c->cfg.sampler;
+    s->sampler = c->primary;
 }
 
 static size_t stage_off(int N, int Dp, int which) {
@@ -370,6 +416,8 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     if (cfg->maxmcmc < 1) return fail("cpn_create: maxmcmc must be >= 1");
     if (cfg->functor < 0 || cfg->functor >= CPN_NUM_FUNCTORS) return fail("cpn_create: unknown functor %d", cfg->functor);
     if (cfg->sampler < CPN_SAMPLER_MH || cfg->sampler > CPN_SAMPLER_HMC) return fail("cpn_create: unknown sampler %d", cfg->sampler);
+    for (int k = 0; k < kNumKinds; ++k)
+        if (cfg->mix[k] < 0) return fail("cpn_create: mix[%d] = %d must be >= 0", k, cfg->mix[k]);
     for (int d = 0; d < cfg->dim; ++d)
         if (!(lo[d] < hi[d])) return fail("cpn_create: bounds[%d] = (%g, %g) is empty", d, lo[d], hi[d]);
     // functor-specific blob checks
@@ -392,6 +440,16 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     c->D = cfg->dim;
     c->Dp = (cfg->dim + 3) & ~3;
     c->N = cfg->nlive;
+    {
+        int active = 0;
+        for (int k = 0; k < kNumKinds; ++k) { c->mix[k] = cfg->mix[k]; active += cfg->mix[k] > 0; }
+        if (active == 0) { c->mix[cfg->sampler] = 1; active = 1; }
+        c->mixed = active > 1;
+        c->primary = cfg->sampler;
+        if (c->mix[c->primary] == 0)
+            for (int k = kNumKinds - 1; k >= 0; --k) if (c->mix[k] > 0) c->primary = k;
+        c->cfg.sampler = c->primary;
+    }
     if (pick_config(c->D, cfg->lanes, cfg->functor, c->N, &c->G, &c->E)) { delete c; return 1; }
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
@@ -403,6 +461,13 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     CK(cudaStreamCreateWithFlags(&c->acc_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_thr, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_acc, cudaEventDisableTiming));
+    if (c->mixed) {
+        CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        for (int k = 0; k < kNumKinds; ++k) {
+            CK(cudaStreamCreateWithFlags(&c->kind_stream[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->ev_kind[k], cudaEventDisableTiming));
+        }
+    }
     const int N = c->N, D = c->D, Dp = c->Dp;
     if (dalloc(&c->d_lo, D) || dalloc(&c->d_hi, D) || dalloc(&c->d_blob, std::max<size_t>(nb, 1))) return 1;
     CK(h2d_sync(c->d_lo, lo, D * sizeof(double)));
@@ -423,7 +488,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     c->rank = std::max(0, cfg->rank);
     c->world = std::max(1, cfg->world_size);
     if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
-    if (dalloc(&c->d_rho, D + 1) || dalloc(&c->d_rho2, D + 1) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
+    if (dalloc(&c->d_rho, kNumKinds * (D + 1)) || dalloc(&c->d_rho2, kNumKinds * (D + 1)) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
     if (dalloc(&c->d_seg_sorted, (size_t)((N + kRankSeg - 1) / kRankSeg) * kRankSeg)) return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
@@ -499,6 +564,10 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaStreamDestroy(c->side);
     cudaStreamDestroy(c->acc_stream);
     cudaEventDestroy(c->ev_thr); cudaEventDestroy(c->ev_acc);
+    if (c->mixed) {
+        cudaEventDestroy(c->ev_fork);
+        for (int k = 0; k < kNumKinds; ++k) { cudaStreamSynchronize(c->kind_stream[k]); cudaStreamDestroy(c->kind_stream[k]); cudaEventDestroy(c->ev_kind[k]); }
+    }
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -551,8 +620,8 @@ extern "C" int cpn_set_user_functor(cpn_ctx* c, const char* source, const char* 
     for (auto& g : cfgs) have = have || (g[0] == c->G && g[1] == c->E);
     if (!have) cfgs.push_back({c->G, c->E});
     int kinds = 1 | 2;                                // eval + MH (the prior burn-in of Sampler.reset runs MH chains)
-    if (c->cfg.sampler == CPN_SAMPLER_SLICE) kinds |= 4;
-    if (c->cfg.sampler == CPN_SAMPLER_HMC) kinds |= 8;
+    if (c->mix[CPN_SAMPLER_SLICE] > 0) kinds |= 4;
+    if (c->mix[CPN_SAMPLER_HMC] > 0) kinds |= 8;
     std::vector<int> flat;
     for (auto& g : cfgs) { flat.push_back(g[0]); flat.push_back(g[1]); }
     char err[8192];
@@ -681,6 +750,7 @@ static void fill_common(cpn_ctx* c, ChainParams* p) {
     p->order = c->d_order[c->cur];
     p->lo = c->d_lo; p->hi = c->d_hi;
     p->state = c->d_state;
+    p->kind = c->primary;
     p->maxmcmc = c->cfg.maxmcmc;
     p->chain_base = c->chain_counter;
     p->seed_lo = (uint32_t)c->cfg.seed; p->seed_hi = (uint32_t)(c->cfg.seed >> 32);
@@ -728,35 +798,43 @@ static void fill_hmc(cpn_ctx* c, HMCParams* p) {
     p->max_traj = c->cfg.maxmcmc;
 }
 
-// chains [j0, j1) of a batch with the context's sampler; START_SURVIVOR unless start rows are given
-static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int n_skip, bool use_override, double logLmin,
-                         int nmcmc, int n_out_override) {
+// chains [j0, j1) of a batch with sampler `kind`; START_SURVIVOR unless start rows are given (START_GIVEN: row c of the
+// start arrays belongs to chain start_row0 + c of the launch)
+static int launch_chains_kind(cpn_ctx* c, int kind, int j0, int j1, int start_mode, int n_skip, bool use_override,
+                              double logLmin, int nmcmc, int n_out_override, int start_row0) {
     int G, E;
+    if (j1 <= j0) return 0;
     if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, j1 - j0, &G, &E)) return 1;
-    if (c->cfg.sampler == CPN_SAMPLER_SLICE) {
+    const double* sx = c->d_start_x + (size_t)start_row0 * c->Dp;
+    const double* sl = c->d_start_logL + start_row0;
+    const double* sp = c->d_start_logP + start_row0;
+    if (kind == CPN_SAMPLER_SLICE) {
         SliceParams p;
         fill_slice(c, &p);
+        p.kind = kind;
         p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
-        p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+        p.start_x = sx; p.start_logL = sl; p.start_logP = sp;
         if (use_override) {
             if (fetch_state(c)) return 1;
             p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.mu_override = c->h_state->slice_mu;
         }
         if (n_out_override > 0) p.n_out = n_out_override;
         if (run_slice(c, G, E, 0, p)) return 1;
-    } else if (c->cfg.sampler == CPN_SAMPLER_MH) {
+    } else if (kind == CPN_SAMPLER_MH) {
         MHParams p;
         fill_mh(c, &p);
+        p.kind = kind;
         p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
-        p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+        p.start_x = sx; p.start_logL = sl; p.start_logP = sp;
         if (use_override) { p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; }
         if (n_out_override > 0) p.n_out = n_out_override;
         if (run_mh(c, G, E, 0, p)) return 1;
     } else {
         HMCParams p;
         fill_hmc(c, &p);
+        p.kind = kind;
         p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
-        p.start_x = c->d_start_x; p.start_logL = c->d_start_logL; p.start_logP = c->d_start_logP;
+        p.start_x = sx; p.start_logL = sl; p.start_logP = sp;
         if (use_override) {
             if (fetch_state(c)) return 1;
             p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.dt_override = c->h_state->hmc_dt;
@@ -765,7 +843,33 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
         if (run_hmc(c, G, E, 0, p)) return 1;
     }
     CKL();
+    c->launches += 1;
     return 0;
+}
+
+// chains [j0, j1) of the K chains of a batch, each with the sampler kind that owns it (kind_ranges).  A mixed
+// population forks onto one stream per kind so that the kinds' kernels share the GPU, and joins the main stream.
+static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int n_skip, bool use_override, double logLmin,
+                         int nmcmc, int n_out_override) {
+    int kb[kNumKinds + 1];
+    if (kind_ranges(c, K, kb)) return 1;
+    for (int k = 0; k <= kNumKinds; ++k) c->last_kb[k] = kb[k];
+    if (!c->mixed)
+        return launch_chains_kind(c, c->primary, j0, j1, start_mode, n_skip, use_override, logLmin, nmcmc, n_out_override, 0);
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    int rc = 0;
+    for (int k = 0; k < kNumKinds && !rc; ++k) {
+        const int a = std::max(j0, kb[k]), b = std::min(j1, kb[k + 1]);
+        if (b <= a) continue;
+        CK(cudaStreamWaitEvent(c->kind_stream[k], c->ev_fork, 0));
+        c->chain_stream = c->kind_stream[k];
+        rc = launch_chains_kind(c, k, a, b, start_mode, n_skip, use_override, logLmin, nmcmc, n_out_override, a - j0);
+        c->chain_stream = nullptr;
+        if (rc) break;
+        CK(cudaEventRecord(c->ev_kind[k], c->kind_stream[k]));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_kind[k], 0));
+    }
+    return rc;
 }
 
 extern "C" int cpn_init_prior(cpn_ctx* c) {
@@ -805,10 +909,11 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, c->N, &G, &E)) return 1;
         if (run_mh(c, G, E, 0, p)) return 1;
         CKL();
-        k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, c->N, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
-                                                      c->d_new_x, c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc,
+        // the burn-in chains (always MH) run under the primary kind's controller
+        k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, c->primary, 0, c->N, c->D, c->Dp, c->d_new_start, c->d_x,
+                                                      c->d_logL, c->d_new_x, c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc,
                                                       c->d_new_evals);
-        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->N, c->d_rho, c->d_rho2, c->D);   // coordinates only: logL is unconstrained here
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->primary, c->N, c->d_rho, c->d_rho2, c->D);   // coordinates only: logL is unconstrained here
         CK(cudaMemcpyAsync(c->d_x, c->d_new_x, (size_t)c->N * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logL, c->d_new_logL, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logP, c->d_new_logP, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -824,7 +929,11 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
     }
     // the burn-in statistics must not leak into the run's controller
     if (fetch_state(c)) return 1;
-    c->h_state->rho_max = -1.0;
+    for (int k = 0; k < kNumKinds; ++k) {
+        c->h_state->ctl[k].rho_max = -1.0;
+        c->h_state->ctl[k].nmcmc = c->h_state->ctl[c->primary].nmcmc;             // every kind starts from the burn-in's length
+        c->h_state->ctl[k].nmcmc_exact = c->h_state->ctl[c->primary].nmcmc_exact;
+    }
     if (push_state(c)) return 1;
     if (sort_live(c)) return 1;
     if (cpn_update_ensemble_stats(c)) return 1;
@@ -910,7 +1019,6 @@ extern "C" int cpn_evolve_batch(cpn_ctx* c, int32_t K) {
     c->chain_counter += (unsigned long long)K;
     c->chains_since_stats += K;
     c->batches_enqueued += 1;
-    c->launches += 1;
     return 0;
 }
 
@@ -986,18 +1094,24 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     CK(cudaSetDevice(c->cfg.device));
     const int T = 256;
     if (join_acc(c)) return 1;                 // the merge appends at the counters the accumulation has advanced
+    int kb[kNumKinds + 1];
+    if (kind_ranges(c, K, kb)) return 1;
     if (!c->staged_external) {
         // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
         // control, and the batch counters
-        k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, K, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL, c->d_new_x,
-                                                      c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc, c->d_new_evals);
-        c->launches += 1;
-        if (c->cfg.sampler == CPN_SAMPLER_SLICE) {
-            k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_ne, c->d_new_nc);
+        for (int k = 0; k < kNumKinds; ++k) {
+            if (kb[k + 1] <= kb[k]) continue;
+            k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, k, kb[k], kb[k + 1], c->D, c->Dp, c->d_new_start, c->d_x,
+                                                          c->d_logL, c->d_new_x, c->d_new_logL, c->d_rho + k * (c->D + 1),
+                                                          c->d_new_steps, c->d_new_acc, c->d_new_evals);
             c->launches += 1;
-        } else if (c->cfg.sampler == CPN_SAMPLER_HMC) {
-            k_adapt_hmc_dt<<<1, 1, 0, c->stream>>>(c->d_state);
-            c->launches += 1;
+            if (k == CPN_SAMPLER_SLICE) {
+                k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, kb[k], kb[k + 1], c->d_new_ne, c->d_new_nc);
+                c->launches += 1;
+            } else if (k == CPN_SAMPLER_HMC) {
+                k_adapt_hmc_dt<<<1, 1, 0, c->stream>>>(c->d_state);
+                c->launches += 1;
+            }
         }
     }
     CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
@@ -1020,6 +1134,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
     m.rho = c->staged_external ? nullptr : c->d_rho;
     m.rho2_ema = c->d_rho2;
+    for (int k = 0; k < kNumKinds; ++k) m.kind_n[k] = kb[k + 1] - kb[k];
     c->staged_external = false;
     m.order_in = c->d_order[c->cur]; m.skeys_in = c->d_skeys[c->cur];
     m.order_out = c->d_order[c->cur ^ 1]; m.skeys_out = c->d_skeys[c->cur ^ 1];
@@ -1108,7 +1223,7 @@ namespace {
 struct CkptHeader {
     char magic[8];                 // "CPNB200\0"
     int32_t version, dim, nlive, functor, sampler, ns_mode, maxmcmc, cycle_len, slice_cycle_len, cur, eig_cur, eig_pending,
-        eig_pending_age, live_ready;
+        eig_pending_age, live_ready, mix[kNumKinds];
     uint64_t seed;
     long long dead_upper, batches_enqueued, chains_since_stats, eig_calls, n_dead, n_hist, n_ins;
     unsigned long long chain_counter;
@@ -1123,7 +1238,7 @@ static std::vector<CkptSection> ckpt_sections(cpn_ctx* c, long long n_dead, long
         {c->d_order[c->cur], N * 4}, {c->d_skeys[c->cur], N * 8},
         {c->d_dead_x, (size_t)n_dead * Dp * 8}, {c->d_dead_logL, (size_t)n_dead * 8}, {c->d_dead_logP, (size_t)n_dead * 8},
         {c->d_hist_logL, (size_t)n_hist * 8}, {c->d_hist_logvol, (size_t)n_hist * 8}, {c->d_ins, (size_t)n_ins * 8},
-        {c->d_rho2, (D + 1) * 8}, {c->d_cycle, (size_t)c->cycle_len}, {c->d_slice_cycle, (size_t)c->slice_cycle_len},
+        {c->d_rho2, kNumKinds * (D + 1) * 8}, {c->d_cycle, (size_t)c->cycle_len}, {c->d_slice_cycle, (size_t)c->slice_cycle_len},
         {c->d_mean, D * 8}, {c->d_cov, D * D * 8}};
     for (int b = 0; b < 2; ++b) {
         v.push_back({c->d_eigval[b], D * 8});
@@ -1162,9 +1277,10 @@ extern "C" int cpn_save_checkpoint(cpn_ctx* c, void* blob, int64_t bytes) {
     CkptHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, "CPNB200", 8);
-    h.version = 1; h.dim = c->D; h.nlive = c->N; h.functor = c->cfg.functor; h.sampler = c->cfg.sampler; h.ns_mode = c->cfg.ns_mode;
+    h.version = 2; h.dim = c->D; h.nlive = c->N; h.functor = c->cfg.functor; h.sampler = c->cfg.sampler; h.ns_mode = c->cfg.ns_mode;
     h.maxmcmc = c->cfg.maxmcmc; h.cycle_len = c->cycle_len; h.slice_cycle_len = c->slice_cycle_len; h.cur = c->cur;
     h.eig_cur = c->eig_cur; h.eig_pending = c->eig_pending ? 1 : 0; h.eig_pending_age = c->eig_pending_age;
+    for (int k = 0; k < kNumKinds; ++k) h.mix[k] = c->mix[k];
     h.live_ready = c->live_ready ? 1 : 0; h.seed = c->cfg.seed; h.dead_upper = c->dead_upper; h.batches_enqueued = c->batches_enqueued;
     h.chains_since_stats = c->chains_since_stats; h.eig_calls = c->eig_calls; h.n_dead = s->iteration; h.n_hist = s->n_hist;
     h.n_ins = s->n_ins; h.chain_counter = c->chain_counter; h.state = *s;
@@ -1187,9 +1303,9 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
     if ((size_t)bytes < sizeof(CkptHeader)) return fail("cpn_load_checkpoint: blob too small");
     CkptHeader h;
     memcpy(&h, blob, sizeof h);
-    if (memcmp(h.magic, "CPNB200", 8) != 0 || h.version != 1) return fail("cpn_load_checkpoint: not a cpnest_b200 checkpoint (version 1)");
+    if (memcmp(h.magic, "CPNB200", 8) != 0 || h.version != 2) return fail("cpn_load_checkpoint: not a cpnest_b200 checkpoint (version 2)");
     if (h.dim != c->D || h.nlive != c->N || h.functor != c->cfg.functor || h.sampler != c->cfg.sampler || h.ns_mode != c->cfg.ns_mode ||
-        h.maxmcmc != c->cfg.maxmcmc)
+        h.maxmcmc != c->cfg.maxmcmc || h.mix[0] != c->mix[0] || h.mix[1] != c->mix[1] || h.mix[2] != c->mix[2])
         return fail("cpn_load_checkpoint: checkpoint of a different run (dim %d nlive %d functor %d sampler %d maxmcmc %d)", h.dim,
                     h.nlive, h.functor, h.sampler, h.maxmcmc);
     CK(cudaSetDevice(c->cfg.device));
@@ -1244,13 +1360,21 @@ extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
     if (fetch_state(c)) return 1;
     const NSState* s = c->h_state;
     o->logZ = s->logZ; o->info = s->info; o->logw = s->logw; o->logLmin = s->logLmin; o->logLmax = s->logLmax;
-    o->condition = s->condition; o->nmcmc_exact = s->nmcmc_exact; o->iteration = s->iteration; o->n_hist = s->n_hist;
+    const KindCtl& pk = s->ctl[c->primary];
+    o->condition = s->condition; o->nmcmc_exact = pk.nmcmc_exact; o->iteration = s->iteration; o->n_hist = s->n_hist;
     o->batches = s->batches;
-    o->total_steps = (int64_t)(s->totals[0] + s->batch[0]);
-    o->total_accepted = (int64_t)(s->totals[1] + s->batch[1]);
-    o->total_evals = (int64_t)(s->totals[2] + s->batch[2]);
-    o->failed_chains = (int64_t)(s->totals[3] + s->batch[3]);
-    o->nmcmc = s->nmcmc; o->done = s->done; o->rho_max = s->rho_max;
+    unsigned long long t[4];
+    for (int i = 0; i < 4; ++i) {
+        t[i] = s->totals[i];
+        for (int k = 0; k < kNumKinds; ++k) t[i] += s->ctl[k].batch[i];
+    }
+    o->total_steps = (int64_t)t[0]; o->total_accepted = (int64_t)t[1]; o->total_evals = (int64_t)t[2]; o->failed_chains = (int64_t)t[3];
+    o->nmcmc = pk.nmcmc; o->done = s->done; o->rho_max = pk.rho_max;
+    for (int k = 0; k < kNumKinds; ++k) {
+        o->rho_kind[k] = s->ctl[k].rho_max;
+        o->nmcmc_kind[k] = s->ctl[k].nmcmc;
+        o->chains_kind[k] = c->last_kb[k + 1] - c->last_kb[k];
+    }
     o->slice_mu = s->slice_mu; o->hmc_dt = s->hmc_dt;
     return 0;
 }
@@ -1260,8 +1384,10 @@ extern "C" int cpn_set_nmcmc(cpn_ctx* c, int32_t nmcmc) {
     if (nmcmc < 1 || nmcmc > c->cfg.maxmcmc) return fail("nmcmc=%d must be in [1, maxmcmc=%d]", nmcmc, c->cfg.maxmcmc);
     CK(cudaSetDevice(c->cfg.device));
     if (fetch_state(c)) return 1;
-    c->h_state->nmcmc = nmcmc;
-    c->h_state->nmcmc_exact = (double)nmcmc;
+    for (int k = 0; k < kNumKinds; ++k) {
+        c->h_state->ctl[k].nmcmc = nmcmc;
+        c->h_state->ctl[k].nmcmc_exact = (double)nmcmc;
+    }
     return push_state(c);
 }
 
@@ -1404,16 +1530,21 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
     k_unpack_records<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(d_rec, K, D, Dp, c->d_start_x, c->d_start_logL, c->d_start_logP);
     // the host protocol is served by one GPU (n_out = 1)
     if (launch_chains(c, K, 0, K, START_GIVEN, 0, true, logLmin, std::max(1, std::min(nmcmc, c->cfg.maxmcmc)), 1)) return 1;
-    k_batch_counters<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, K, c->d_new_steps, c->d_new_acc, c->d_new_evals);
-    k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, K, nullptr, nullptr, 0);
-    if (c->cfg.sampler == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, K, c->d_new_ne, c->d_new_nc);
+    for (int k = 0; k < kNumKinds; ++k) {
+        const int a = c->last_kb[k], b = c->last_kb[k + 1];
+        if (b <= a) continue;
+        k_batch_counters<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, k, a, b, c->d_new_steps, c->d_new_acc, c->d_new_evals);
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, k, b - a, nullptr, nullptr, 0);
+        if (k == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, a, b, c->d_new_ne, c->d_new_nc);
+        c->launches += 2 + (k == CPN_SAMPLER_SLICE);
+    }
     if (slots) {
         CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         k_pool_append<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rank, K, c->N, Dp, c->d_new_x, c->d_new_logL,
                                                               c->d_new_logP, c->d_x, c->d_logL, c->d_logP);
         c->launches += 1;
     }
-    c->launches += 5;
+    c->launches += 2;
     k_pack_records<<<((int)need + T - 1) / T, T, 0, c->stream>>>(c->d_new_x, c->d_new_logL, c->d_new_logP, K, D, Dp, d_rec);
     CKL();
     CK(cudaMemcpyAsync(replies, d_rec, need * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -38,6 +38,7 @@ struct ChainParams {
     const double* hi;
     // chain control
     const NSState* state;     // logLmin / nmcmc / done live on the device
+    int kind;                 // cpn_sampler whose controller (state->ctl[kind]) gives the chain length
     int use_override;
     double logLmin_override;
     int nmcmc_override;
@@ -99,7 +100,7 @@ struct Chain {
         Model::prepare(m);
         set_valid_mask<G, E>(g, m);
         logLmin = p.use_override ? p.logLmin_override : p.state->logLmin;
-        nmcmc = p.use_override ? p.nmcmc_override : p.state->nmcmc;
+        nmcmc = p.use_override ? p.nmcmc_override : p.state->ctl[p.kind].nmcmc;
         const unsigned long long chain_id = p.chain_base + (unsigned long long)j;
         cid_lo = (uint32_t)chain_id;
         cid_hi = (uint32_t)(chain_id >> 32);

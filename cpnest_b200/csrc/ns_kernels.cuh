@@ -210,16 +210,18 @@ __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p
 //      ended: rho = max_d |corr_d(start, end)| over the coordinates and logL.  With geometric decay
 //      rho = exp(-n/tau) the length that reaches rho_target is n * ln(rho_target) / ln(rho).
 // The chain length follows the larger of the two with a moving average.
-__device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains, const double* rho, double* rho2_ema, int nrho) {
-    const unsigned long long steps = st->batch[0], accd = st->batch[1];
-    for (int i = 0; i < 4; ++i) { st->totals[i] += st->batch[i]; st->batch[i] = 0; }
-    if (steps == 0) return;
+// One controller per sampler kind (KindCtl): `chains` chains of kind `kind` returned in this batch.
+__device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, const double* rho, double* rho2_ema, int nrho) {
+    KindCtl& k = st->ctl[kind];
+    const unsigned long long steps = k.batch[0], accd = k.batch[1];
+    for (int i = 0; i < 4; ++i) { st->totals[i] += k.batch[i]; k.batch[i] = 0; }
+    if (steps == 0 || chains <= 0) return;
     const double a = 0.2;
     double qmax = -1.0;
     if (rho != nullptr) {
         // q_d = EMA(rho_d^2 - 1/K): the sampling noise of a correlation over K chains is removed in
         // expectation and averaged down BEFORE the maximum over d is taken
-        const bool first = st->rho_max < 0.0;
+        const bool first = k.rho_max < 0.0;
         for (int d = 0; d < nrho; ++d) {
             double r2 = rho[d] * rho[d] - 1.0 / (double)chains;
             if (!(r2 == r2)) r2 = 0.0;                       // zero variance in this coordinate
@@ -227,18 +229,18 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains, const doubl
             rho2_ema[d] = q;
             if (q > qmax) qmax = q;
         }
-        st->rho_max = sqrt(fmax(qmax, 0.0));
+        k.rho_max = sqrt(fmax(qmax, 0.0));
     }
     if (!st->adapt) return;
     const double safety = st->nmcmc_safety;
     const double sub_acc = (double)accd / (double)steps;
     const double mean_len = (double)steps / (double)chains;
-    double ne = st->nmcmc_exact;
+    double ne = k.nmcmc_exact;
     double target = (sub_acc > 0.0) ? safety * (2.0 / sub_acc - 1.0) : 2.0 * ne;      // sampler.py:171
-    if (rho != nullptr && st->rho_target > 0.0) {
+    if (rho != nullptr && k.rho_target > 0.0) {
         // resolution of q_max: z * sigma_q, sigma_q = sqrt(2)/K * sqrt(a/(2-a)), z = sqrt(2 ln nrho)
         const double floor2 = 2.0 * sqrt(2.0 * log((double)nrho + 1.0)) * 1.41421356 / (double)chains * sqrt(a / (2.0 - a));
-        const double tgt2 = fmax(st->rho_target * st->rho_target, floor2);
+        const double tgt2 = fmax(k.rho_target * k.rho_target, floor2);
         const double r2 = fmin(fmax(qmax, 1e-6), 0.998);
         double t2 = mean_len * log(tgt2) / log(r2);
         t2 = fmin(fmax(t2, 0.5 * ne), 2.0 * ne);
@@ -246,26 +248,26 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int chains, const doubl
     }
     ne = (1.0 - a) * ne + a * target;
     ne = fmin(ne, (double)st->maxmcmc);
-    st->nmcmc_exact = ne;
+    k.nmcmc_exact = ne;
     int n = (int)ne;
     if (n < (int)safety) n = (int)safety;
     if (n > st->maxmcmc) n = st->maxmcmc;
-    st->nmcmc = n;
+    k.nmcmc = n;
 }
-__global__ void k_adapt_nmcmc(NSState* st, int chains, const double* rho, double* rho2_ema, int nrho) {
+__global__ void k_adapt_nmcmc(NSState* st, int kind, int chains, const double* rho, double* rho2_ema, int nrho) {
     if (st->done) return;
-    adapt_nmcmc(st, chains, rho, rho2_ema, nrho);
+    adapt_nmcmc(st, kind, chains, rho, rho2_ema, nrho);
 }
 
-// Sums of the per-chain outcome arrays of a launch -> st->batch[] = {steps, accepted, evals, failed
-// chains}.  Integer sums: the result does not depend on the order, nor on how the chains were split
+// Sums of the per-chain outcome arrays of the chains [j0, j1) of a batch (those of sampler kind `kind`)
+// -> st->ctl[kind].batch[] = {steps, accepted, evals, failed chains}.  Integer sums: the result does not depend on the order, nor on how the chains were split
 // over GPUs.
 constexpr int kCorrThreads = 1024;    // block size of k_chain_corr / k_batch_counters (fixed: the reduction shape must not vary)
-__device__ __forceinline__ void block_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals,
-                                                     unsigned long long (*shc)[kCorrThreads]) {
+__device__ __forceinline__ void block_batch_counters(NSState* st, int kind, int j0, int j1, const int* steps, const int* acc,
+                                                     const int* evals, unsigned long long (*shc)[kCorrThreads]) {
     const int tid = threadIdx.x;
     unsigned long long a[4] = {0, 0, 0, 0};
-    for (int j = tid; j < K; j += kCorrThreads) {
+    for (int j = j0 + tid; j < j1; j += kCorrThreads) {
         a[0] += (unsigned long long)steps[j];
         a[1] += (unsigned long long)acc[j];
         a[2] += (unsigned long long)(evals != nullptr ? evals[j] : 0);
@@ -279,11 +281,12 @@ __device__ __forceinline__ void block_batch_counters(NSState* st, int K, const i
         __syncthreads();
     }
     if (tid == 0)
-        for (int k = 0; k < 4; ++k) st->batch[k] = shc[k][0];
+        for (int k = 0; k < 4; ++k) st->ctl[kind].batch[k] = shc[k][0];
 }
-__global__ void __launch_bounds__(kCorrThreads) k_batch_counters(NSState* st, int K, const int* steps, const int* acc, const int* evals) {
+__global__ void __launch_bounds__(kCorrThreads) k_batch_counters(NSState* st, int kind, int j0, int j1, const int* steps,
+                                                                 const int* acc, const int* evals) {
     __shared__ unsigned long long shc[4][kCorrThreads];
-    block_batch_counters(st, K, steps, acc, evals, shc);
+    block_batch_counters(st, kind, j0, j1, steps, acc, evals, shc);
 }
 
 // SliceSampler.adapt_length_scale (sampler.py:429-437): mu *= 2 Ne / (Ne + Nc).  The reference applies it per
@@ -291,12 +294,12 @@ __global__ void __launch_bounds__(kCorrThreads) k_batch_counters(NSState* st, in
 // ALL slices of the batch are pooled (integer sums: independent of order and of the split over GPUs), which
 // makes the estimate of the expansion/contraction balance precise enough to keep following the shrinking
 // constrained region for the whole run.
-__global__ void __launch_bounds__(256) k_adapt_slice_mu(NSState* st, int K, const int* ne, const int* nc) {
+__global__ void __launch_bounds__(256) k_adapt_slice_mu(NSState* st, int j0, int j1, const int* ne, const int* nc) {
     if (st->done) return;
     __shared__ unsigned long long sh[2][256];
     const int tid = threadIdx.x;
     unsigned long long a = 0, b = 0;
-    for (int j = tid; j < K; j += 256) { a += (unsigned long long)ne[j]; b += (unsigned long long)nc[j]; }
+    for (int j = j0 + tid; j < j1; j += 256) { a += (unsigned long long)ne[j]; b += (unsigned long long)nc[j]; }
     sh[0][tid] = a; sh[1][tid] = b;
     __syncthreads();
     for (int w = 128; w > 0; w >>= 1) {
@@ -315,31 +318,32 @@ __global__ void __launch_bounds__(256) k_adapt_slice_mu(NSState* st, int K, cons
 // gain of 0.05.  Must run after k_chain_corr (batch counters) and before k_merge_commit (which folds them).
 __global__ void k_adapt_hmc_dt(NSState* st) {
     if (st->done) return;
-    const unsigned long long traj = st->batch[0], accd = st->batch[1];
+    const unsigned long long traj = st->ctl[CPN_SAMPLER_HMC].batch[0], accd = st->ctl[CPN_SAMPLER_HMC].batch[1];
     if (traj == 0) return;
     const double acc = (double)accd / (double)traj;
     st->hmc_dt *= exp(0.05 * (acc - 0.5));
 }
 
-// corr_d(start, end) across the K chains of the batch, d in [0, D] (d == D is logL).
-// One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
-__global__ void __launch_bounds__(kCorrThreads) k_chain_corr(NSState* st, int K, int D, int Dp, const int* __restrict__ start_slot,
+// corr_d(start, end) across the chains [j0, j1) of the batch (those of sampler kind `kind`), d in [0, D] (d == D is
+// logL).  One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
+// rho points at this kind's D+1 values.
+__global__ void __launch_bounds__(kCorrThreads) k_chain_corr(NSState* st, int kind, int j0, int j1, int D, int Dp, const int* __restrict__ start_slot,
                                                     const double* __restrict__ live_x, const double* __restrict__ live_logL,
                                                     const double* __restrict__ new_x, const double* __restrict__ new_logL,
                                                     double* __restrict__ rho, const int* steps, const int* acc, const int* evals) {
     if (st->done) return;
     __shared__ double sh[5][kCorrThreads];
     if (blockIdx.x == D + 1) {
-        block_batch_counters(st, K, steps, acc, evals, reinterpret_cast<unsigned long long (*)[kCorrThreads]>(&sh[0][0]));
+        block_batch_counters(st, kind, j0, j1, steps, acc, evals, reinterpret_cast<unsigned long long (*)[kCorrThreads]>(&sh[0][0]));
         return;
     }
     const int d = blockIdx.x, tid = threadIdx.x;
     // shift by the first chain's values to keep the sums well conditioned
-    const int s0 = start_slot[0];
+    const int s0 = start_slot[j0];
     const double cs = (d < D) ? live_x[(size_t)s0 * Dp + d] : live_logL[s0];
-    const double ce = (d < D) ? new_x[d] : new_logL[0];
+    const double ce = (d < D) ? new_x[(size_t)j0 * Dp + d] : new_logL[j0];
     double a[5] = {0, 0, 0, 0, 0};
-    for (int j = tid; j < K; j += kCorrThreads) {
+    for (int j = j0 + tid; j < j1; j += kCorrThreads) {
         const int sl = start_slot[j];
         const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
         const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr(NSState* st, int K,
         __syncthreads();
     }
     if (tid == 0) {
-        const double n = (double)K;
+        const double n = (double)(j1 - j0);
         const double vs = sh[2][0] - sh[0][0] * sh[0][0] / n, ve = sh[3][0] - sh[1][0] * sh[1][0] / n;
         const double cv = sh[4][0] - sh[0][0] * sh[1][0] / n;
         rho[d] = cv / sqrt(vs * ve);
@@ -465,8 +469,9 @@ struct MergeParams {
     const double* new_x;       // [K][Dp]
     const double* new_logL;
     const double* new_logP;
-    const double* rho;         // [D+1] start/end correlations of this batch (k_chain_corr)
-    double* rho2_ema;          // [D+1] smoothed, de-biased squares
+    const double* rho;         // [kinds][D+1] start/end correlations of this batch (k_chain_corr), per sampler kind
+    double* rho2_ema;          // [kinds][D+1] smoothed, de-biased squares
+    int kind_n[kNumKinds];     // chains of each sampler kind in this batch
     double* dead_x;            // rows appended at dead0
     double* dead_logL;
     double* dead_logP;
@@ -533,7 +538,13 @@ __global__ void k_merge_commit(const MergeParams p) {
         p.dead_logP[dead0 + i] = p.live_logP[slot];
         p.live_logL[slot] = key;
         p.live_logP[slot] = p.new_logP[i];
-        if (i == 0) adapt_nmcmc(p.st_w, K, p.rho, p.rho2_ema, p.rho != nullptr ? p.Dreal + 1 : 0);
+        if (i == 0) {
+            const int nrho = p.Dreal + 1;
+            for (int kind = 0; kind < kNumKinds; ++kind)
+                if (p.kind_n[kind] > 0)
+                    adapt_nmcmc(p.st_w, kind, p.kind_n[kind], p.rho != nullptr ? p.rho + kind * nrho : nullptr,
+                                p.rho2_ema + kind * nrho, p.rho != nullptr ? nrho : 0);
+        }
     }
 }
 

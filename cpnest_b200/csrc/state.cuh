@@ -4,6 +4,20 @@
 #pragma once
 namespace cpn {
 
+constexpr int kNumKinds = 3;      // cpn_sampler: MH, slice, HMC
+
+// Chain control of one sampler kind.  The reference keeps these per sampler process (cpnest/sampler.py:79-105); a run
+// that mixes kinds (CPNest(nthreads, nslice, nhamiltonian), cpnest/cpnest.py:197-261) has one controller per kind:
+// an MH step, a slice and an HMC trajectory decorrelate at very different rates.
+struct KindCtl {
+    double nmcmc_exact;            // Sampler.Nmcmc_exact
+    double rho_target;             // chains run until the start/end correlation across the batch falls to this
+    double rho_max;                // smoothed max_d |corr(start_d, end_d)| of the last batches (d includes logL)
+    unsigned long long batch[4];   // steps, accepted, evals, failed chains of this kind in the last evolve
+    int nmcmc;                     // Sampler.Nmcmc
+    int pad_;
+};
+
 struct NSState {
     double logZ;          // _NSintegralState.logZ
     double B;             // info + logZ, the linear part of the information recurrence
@@ -13,11 +27,8 @@ struct NSState {
     double logLmax;       // manager.logLmax
     double condition;     // NestedSampler.condition
     double tolerance;     // NestedSampler.tolerance (stopping)
-    double nmcmc_exact;   // Sampler.Nmcmc_exact
     double nmcmc_safety;
     double nmcmc_tau;     // decay of the moving average, in chains
-    double rho_target;    // chains run until the start/end correlation across the batch falls to this
-    double rho_max;       // smoothed max_d |corr(start_d, end_d)| of the last batches (d includes logL)
     double slice_mu;      // SliceSampler.mu: length scale of the slice directions (sampler.py:422, 429-437)
     double hmc_dt;        // HamiltonianProposal.dt: leapfrog time step (proposal.py:393, 539-552)
     long long iteration;  // NestedSampler.iteration == number of dead points
@@ -25,13 +36,12 @@ struct NSState {
     long long n_ins;      // len(insertion_indices)
     long long batches;
     unsigned long long totals[4];   // steps, accepted, evals, failed chains (whole run)
-    unsigned long long batch[4];    // same, last evolve launch
-    int nmcmc;            // Sampler.Nmcmc
+    KindCtl ctl[kNumKinds];         // chain-length control + last-evolve counters, per sampler kind
     int maxmcmc;
     int adapt;
     int stop_next;        // condition <= tolerance seen: the following batch must not run
     int done;
-    int sampler;          // cpn_sampler of the context (the chain-length controller reads it)
+    int sampler;          // primary cpn_sampler of the context (the kind cpn_get_state reports)
 };
 
 }  // namespace cpn

@@ -44,7 +44,7 @@ def functor_blob(name, dim, params=None):
 class Engine:
     def __init__(self, functor, bounds, nlive, maxmcmc=100, seed=1234, params=None, device=0,
                  nmcmc_init=0, lanes=0, ns_mode="sequential", nmcmc_safety=5.0, adapt_nmcmc=True,
-                 rho_target=0.0, rank=0, world_size=1, sampler="mh"):
+                 rho_target=0.0, rank=0, world_size=1, sampler="mh", mix=None):
         self.lib = L.load()
         self.functor = functor
         self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
@@ -70,6 +70,20 @@ class Engine:
             raise ValueError("unknown sampler %r (known: %s)" % (sampler, ", ".join(L.SAMPLERS)))
         cfg.sampler = L.SAMPLERS[sampler]
         self.sampler = sampler
+        # mixed population: mix = dict(mh=a, slice=b, hmc=c) or a 3-sequence in the order of enum cpn_sampler
+        # (relative numbers of chains per batch, CPNest(nthreads, nslice, nhamiltonian), cpnest/cpnest.py:197-261)
+        if mix is not None:
+            if isinstance(mix, dict):
+                unknown = set(mix) - set(L.SAMPLERS)
+                if unknown:
+                    raise ValueError("unknown sampler(s) in mix: %s" % ", ".join(sorted(unknown)))
+                mix = [int(mix.get(k, 0)) for k in ("mh", "slice", "hmc")]
+            mix = [int(m) for m in mix]
+            if len(mix) != 3 or min(mix) < 0 or sum(mix) == 0:
+                raise ValueError("mix must hold three non-negative numbers (mh, slice, hmc), not all zero")
+            for i, m in enumerate(mix):
+                cfg.mix[i] = m
+        self.mix = mix
         blob = L.f64(functor_blob(functor, self.dim, params))
         lo = L.f64(self.bounds[:, 0])
         hi = L.f64(self.bounds[:, 1])

@@ -78,7 +78,12 @@ typedef struct cpn_config {
     int32_t world_size;    /* number of ranks sharing the live set (1 = single GPU) */
     int32_t rank;
     int32_t sampler;       /* enum cpn_sampler */
-    double rho_target;     /* chain-length control: start/end correlation to reach; <=0: 0.1 (MH), 0.05 (slice) */
+    double rho_target;     /* chain-length control: start/end correlation to reach; <=0: 0.1 (MH, HMC), 0.05 (slice) */
+    int32_t mix[3];        /* mixed sampler population, CPNest(nthreads, nslice, nhamiltonian) (cpnest/cpnest.py:197-261):
+                              relative numbers of MH / slice / HMC chains in every batch (indexed by enum cpn_sampler);
+                              the K chains of a batch are split in these proportions, MH chains first.  All zero: every
+                              chain is of kind `sampler` */
+    int32_t reserved_;
 } cpn_config;
 
 /* NestedSampler / _NSintegralState observable state (cpnest/NestedSampling.py:88-144, 254-262) */
@@ -102,6 +107,10 @@ typedef struct cpn_state {
     int32_t done;          /* condition <= tolerance reached */
     double slice_mu;       /* SliceSampler.mu */
     double hmc_dt;         /* HamiltonianProposal.dt */
+    /* per sampler kind (enum cpn_sampler); nmcmc / nmcmc_exact / rho_max above are those of the context's primary kind */
+    double rho_kind[3];
+    int32_t nmcmc_kind[3];
+    int32_t chains_kind[3];/* chains of each kind in the last batch */
 } cpn_state;
 
 const char* cpn_last_error(void);
@@ -144,8 +153,9 @@ int cpn_get_ensemble_stats(cpn_ctx* ctx, double* mean, double* cov, double* eigv
 /* NestedSampler.get_worst_n_live_points + _NSintegralState.increment + termination condition
  * (cpnest/NestedSampling.py:324-332, 368-375, 111-134).  Asynchronous. */
 int cpn_select_and_accumulate(cpn_ctx* ctx, int32_t K);
-/* MetropolisHastingsSampler.yield_sample for the K chains of the batch
- * (cpnest/sampler.py:322-358 driving cpnest/proposal.py:209-362).  Asynchronous. */
+/* MetropolisHastingsSampler / SliceSampler / HamiltonianMonteCarloSampler .yield_sample for the K chains of the batch
+ * (cpnest/sampler.py:322-358, 465-569, 365-402).  With a mixed population (cpn_config.mix) the chains [0, K) are cut
+ * into one contiguous range per kind and the kinds' kernels run concurrently on their own streams.  Asynchronous. */
 int cpn_evolve_batch(cpn_ctx* ctx, int32_t K);
 /* OrderedLivePoints.insert_live_point / remove_n_worst_points + insertion indices
  * (cpnest/NestedSampling.py:44-85, 343-366).  Asynchronous. */

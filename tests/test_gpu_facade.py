@@ -100,8 +100,22 @@ def test_functor_mismatch_and_unsupported_samplers_fail_loudly(tmp_path):
             return 2.0 * M.GaussianModel.log_likelihood(self, p)
     with pytest.raises(ValueError, match="disagrees"):
         cpnest.CPNest(Wrong(2), output=str(tmp_path), nlive=100)
-    with pytest.raises(NotImplementedError, match="single sampler kind"):
-        cpnest.CPNest(M.GaussianModel(2), output=str(tmp_path), nlive=100, nthreads=4, nslice=1)   # mixed population
+    with pytest.raises(ValueError, match="nslice"):
+        cpnest.CPNest(M.GaussianModel(2), output=str(tmp_path), nlive=100, nthreads=2, nslice=2, nhamiltonian=1)
+
+
+def test_mixed_sampler_population_like_the_reference_constructor(tmp_path):
+    # cpnest/cpnest.py:197-261: nthreads - nslice - nhamiltonian MH samplers, nhamiltonian HMC, nslice slice samplers
+    import cpnest_b200.models as M
+    model = M.GaussianModel(2)
+    work = _run(model, tmp_path, verbose=1, nthreads=4, nslice=1, nhamiltonian=1, nlive=1000, maxmcmc=1000, poolsize=1000)
+    assert work.sampler_kind == "mh+slice+hmc" and work.population == dict(mh=2, slice=1, hmc=1)
+    assert set(work.proposals) == {"mh", "slice", "hmc"}
+    s = work.engine.state()
+    assert work.batch == 250 and s["chains_kind"] == [125, 63, 62]      # largest remainder of 2 : 1 : 1
+    assert np.abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * np.sqrt(work.NS.state.info / work.NS.Nlive)
+    pos = work.posterior_samples
+    assert abs(pos["x"].mean()) < 0.2 and abs(pos["x"].std() - 1.0) < 0.2
 
 
 def test_2d_slice_like_reference_test(tmp_path):

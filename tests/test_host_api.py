@@ -25,9 +25,37 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_abi_struct_sizes_match_header():
     import ctypes
     from cpnest_b200 import _lib
-    # cpn_config: 8 int32 + uint64 + double + 4 int32 + double ; cpn_state: 8 doubles + 7 int64 + 2 int32 + 2 doubles
-    assert ctypes.sizeof(_lib.cpn_config) == 8 * 4 + 8 + 8 + 4 * 4 + 8
-    assert ctypes.sizeof(_lib.cpn_state) == 8 * 8 + 7 * 8 + 2 * 4 + 2 * 8
+    # cpn_config: 8 int32 + uint64 + double + 4 int32 + double + 4 int32; cpn_state: 8 doubles + 7 int64 + 2 int32 +
+    # 2 doubles + 3 doubles + 6 int32
+    assert ctypes.sizeof(_lib.cpn_config) == 8 * 4 + 8 + 8 + 4 * 4 + 8 + 4 * 4
+    assert ctypes.sizeof(_lib.cpn_state) == 8 * 8 + 7 * 8 + 2 * 4 + 2 * 8 + 3 * 8 + 6 * 4
+
+
+def test_abi_struct_layout_matches_a_c_compiler(tmp_path):
+    """The ctypes mirrors of cpn_config / cpn_state against what gcc makes of include/cpnest_b200.h: size and the offset
+    of every field (the header is plain C: it must compile as C, too)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from cpnest_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cpnest_b200.h"', 'int main(void) {']
+    for st in ("cpn_config", "cpn_state"):
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for name, _ in getattr(_lib, st)._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, name, st, name))
+    lines.append("return 0; }")
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st in ("cpn_config", "cpn_state"):
+        cls = getattr(_lib, st)
+        assert int(out[st]) == ctypes.sizeof(cls), st
+        for name, _ in cls._fields_:
+            assert int(out["%s.%s" % (st, name)]) == getattr(cls, name).offset, (st, name)
 
 
 def test_no_cpu_fallback_fails_loudly():
