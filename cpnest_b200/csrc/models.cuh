@@ -374,6 +374,35 @@ struct GaussMeanSigma : ModelBase {
     }
 };
 
+// exp(x) for x <= 0, straight-line code (no range branches, so that the unrolled copies of a data loop interleave on the
+// FP64 pipe): x is clamped at -50 (exp(-50) = 2e-22 vanishes against the 1 it is added to), n = rint(x log2 e) by the
+// 1.5 * 2^52 trick, r = x - n ln2 in two pieces, Taylor polynomial of degree 13 on |r| <= ln2 / 2 (truncation 4e-18),
+// 2^n applied to the exponent field.  Measured against numpy.exp on 3e6 points of [-50, 0]: <= 2 ulp.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -50.0);
+    const double magic = 6755399441055744.0;
+    const double t = fma(x, 1.4426950408889634074, magic);
+    const int n = __double2loint(t);
+    const double fn = t - magic;
+    double r = fma(fn, -6.93147180369123816490e-01, x);
+    r = fma(fn, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;              // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);            // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);           // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);           // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);          // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);            // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);           // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);          // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);           // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);          // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);          // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 // ---- two-component mixture over a data vector: examples/gaussianmixture.py:22-31 ;
 //      blob = {n_data, data[n_data]} ; parameters (mean1, sigma1, mean2, sigma2, weight) ----------
 struct GaussMixture : ModelBase {
@@ -402,7 +431,7 @@ struct GaussMixture : ModelBase {
                 const double l1 = c1 - 0.5 * t1 * t1, l2 = c2 - 0.5 * t2 * t2;
                 const double hi = fmax(l1, l2), lo = fmin(l1, l2);
                 acc += hi;
-                prod *= 1.0 + exp(lo - hi);
+                prod *= 1.0 + exp_nonpos(lo - hi);
             }
             acc += log(prod);
         }
