@@ -332,7 +332,7 @@ def main():
                          "algorithmic_flops_per_launch": alg_flops, "evals_per_launch": k_evals, "peak_source": f64_src},
                 "note": "gathers are served from L2 (live set %.1f MB, DRAM traffic per launch = `traffic`); the kernel is "
                         "bound by dependent-instruction latency at the occupancy K chains allow, see DESIGN.md" % (
-                    N * 52 * 8 / 1e6)}
+                    N * 64 * 8 / 1e6)}
 
     # ---- finish the run: log-evidence wall time and validity --------------------------------------
     full = None
@@ -428,7 +428,7 @@ def main():
                        "step": "one nested-sampling batch: select+accumulate, evolve K chains, insert",
                        "l2_policy": "working set per step (live set + staging, %.1f MB) is re-gathered at random; "
                                     "no explicit flush: every step reads points rewritten by the previous one" % (
-                                        (N + K) * 52 * 8 / 1e6)},
+                                        (N + K) * 64 * 8 / 1e6)},
             "runs_restarted_in_timed_region": restarts,
             "mcmc_steps_per_s": steps_mcmc / (dt_ms * 1e-3),
             "accepted_chain_steps_per_s": accepted / (dt_ms * 1e-3),

@@ -439,6 +439,18 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     c->cfg = *cfg;
     c->D = cfg->dim;
     c->Dp = (cfg->dim + 3) & ~3;
+    // Row padding.  When the rows are zero-padded up to G*E doubles, every slot a lane group gathers lies inside its own
+    // row and the MH kernel needs no masks for the slots beyond D (mh_kernel.cuh).  Taken when it costs at most a third
+    // more memory, for the functor that profits (iid Gaussian centred at 0: Model::pad_ok): D = 50 -> rows of 64 doubles.
+    if (cfg->functor == CPN_GAUSS_IID && blob && blob_bytes >= sizeof(double) && ((const double*)blob)[0] == 0.0 &&
+        !getenv("CPN_NO_ROW_PAD")) {
+        int pmin = 0;
+        for (int i = 0; i < kNumCfgs; ++i) {
+            const int prod = kCfgs[i][0] * kCfgs[i][1];
+            if (prod >= cfg->dim && (pmin == 0 || prod < pmin)) pmin = prod;
+        }
+        if (pmin >= 4 && 3 * pmin <= 4 * c->Dp) c->Dp = pmin;
+    }
     c->N = cfg->nlive;
     {
         int active = 0;
@@ -824,6 +836,7 @@ static int launch_chains_kind(cpn_ctx* c, int kind, int j0, int j1, int start_mo
         MHParams p;
         fill_mh(c, &p);
         p.kind = kind;
+        p.padded = c->Dp >= G * E;
         p.start_mode = start_mode; p.n_skip = n_skip; p.j0 = j0; p.j1 = j1;
         p.start_x = sx; p.start_logL = sl; p.start_logP = sp;
         if (use_override) { p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; }

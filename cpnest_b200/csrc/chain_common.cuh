@@ -44,6 +44,7 @@ struct ChainParams {
     int nmcmc_override;
     int maxmcmc;
     int j0, j1;               // chains [j0, j1) of the batch are evolved by this launch
+    int padded;               // rows of ens_x / eig_vec are zero-padded to at least G*E doubles (Dp >= G*E)
     unsigned long long chain_base;
     uint32_t seed_lo, seed_hi;
     const double* blob;

@@ -257,6 +257,12 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         }
     } else {
         // ================================ production ==================================================
+        // The loop exists twice: `mm` is the chain's functor context, or - when the gathered rows are zero-padded up to
+        // G*E doubles and the functor tolerates zeros in the slots beyond D (Model::pad_ok) - a copy whose slot masks
+        // are the constant all-ones, which lets the compiler drop the masking of every slot (17 of 155 instructions per
+        // step for the iid Gaussian at D=50): those slots then hold exact zeros in x, in every gathered row and hence in
+        // every proposal.
+        auto production = [&](const ModelCtx& mm) {
         const uint32_t ens_n = (uint32_t)p.ens_n;
         DrawFeed<G> feed;
         auto next_in = [&](int it) -> StepIn {
@@ -283,11 +289,11 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                 inb = inb & (blo[e] < xn[e]) & (xn[e] < bhi[e]);            // strict, model.py:33
             }
             inb = g.all(inb);
-            double logP_new = Model::template log_prior<G, E>(g, xn, m);
+            double logP_new = Model::template log_prior<G, E>(g, xn, mm);
             logP_new = inb ? logP_new : CPN_NEG_INF;
             const bool pass = (logP_new - logP > s.thr) && active;          // sampler.py:337
             if (Model::kCheap || __any_sync(FULL, pass)) {
-                const double logL_new = Model::template log_likelihood<G, E>(g, xn, m);   // sampler.py:338
+                const double logL_new = Model::template log_likelihood<G, E>(g, xn, mm);   // sampler.py:338
                 evals += pass ? 1 : 0;
                 const bool acc = pass && logL_new > logLmin;                // sampler.py:339
 #pragma unroll
@@ -311,6 +317,15 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             if (!__any_sync(FULL, active)) break;
             mcmc_step(it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
             if (!__any_sync(FULL, active)) break;
+        }
+        };
+        if (p.padded && Model::pad_ok(m)) {
+            ModelCtx mp = m;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mp.vmsk[e] = 0xffffffffu;
+            production(mp);
+        } else {
+            production(m);
         }
     }
 

@@ -35,6 +35,9 @@ __device__ __forceinline__ double masked(const ModelCtx& m, int e, double v) {
 
 struct ModelBase {
     static __device__ __forceinline__ void prepare(ModelCtx&) {}
+    // true if the functor's value does not change when the slots beyond D of a point hold +0.0 and are NOT masked: the
+    // MH kernel then skips the masks whenever the rows it gathers are zero-padded up to G*E doubles (mh_kernel.cuh)
+    static __device__ __forceinline__ bool pad_ok(const ModelCtx&) { return false; }
 };
 
 template <int G, int E>
@@ -74,6 +77,8 @@ struct GaussIid : FlatPrior {
         m.par[2] = (double)m.D * m.blob[2];
         m.par[3] = inv_sigma * inv_sigma;
     }
+    // a zero slot adds (0 - mu)^2 to the sum: nothing exactly when mu == 0
+    static __device__ __forceinline__ bool pad_ok(const ModelCtx& m) { return m.par[0] == 0.0; }
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         const double mu = m.par[0];

@@ -179,3 +179,26 @@ def test_checkpoint_resume_continues_bit_identically():
     with pytest.raises(Exception, match="different run"):
         c = Engine("gaussian_iid", [[-10, 10]] * 6, nlive=500, maxmcmc=100, seed=11)
         c.load_checkpoint(blob)
+
+
+@pytest.mark.parametrize("dim,lanes", [(50, 0), (50, 32), (10, 0), (10, 8), (6, 0)])
+def test_zero_padded_rows_give_the_same_run_bit_for_bit(dim, lanes, monkeypatch):
+    """For the iid Gaussian centred at 0 the live rows are zero-padded to G*E doubles and the MH kernel runs its loop without
+    the masks of the slots beyond D (mh_kernel.cuh, Model::pad_ok).  CPN_NO_ROW_PAD=1 keeps rows of roundup(D, 4) doubles and
+    the masked loop: both must produce the same chains, hence the same run, bit for bit."""
+    from cpnest_b200.engine import Engine
+
+    def run():
+        e = Engine("gaussian_iid", [[-10, 10]] * dim, nlive=1500, maxmcmc=300, seed=42, lanes=lanes)
+        e.set_cycle(O.make_cycle(np.random.RandomState(42)))
+        e.init_prior()
+        for _ in range(12):
+            e.ns_step(300)
+        s = e.state()
+        out = (s["logZ"], s["total_steps"], s["total_accepted"], s["total_evals"], s["nmcmc"], e.live().tobytes(), e.dead().tobytes())
+        e.close()
+        return out
+    padded = run()
+    monkeypatch.setenv("CPN_NO_ROW_PAD", "1")
+    plain = run()
+    assert padded == plain
