@@ -12,8 +12,9 @@ evolve K constrained MCMC chains (the hot kernel), insert the K replacements.
 
   value : evals/s with the live set resident in HBM, CUDA-event timed, max over ranks
   e2e   : the same batches driven through the sampler pipe protocol of the C-ABI with HOST
-          buffers (cpn_evolve_host): every step copies the K request points host->device from
-          pinned memory and the K replies device->host, and the host keeps the live set.
+          buffers (cpn_evolve_host_table): the host keeps the live set in one pinned table and
+          selects the worst points; every step the K request rows travel host->device and the K
+          replies device->host (read from / written into the table by the device itself).
   roofline / cpu_baseline : see DESIGN.md "Measurement".
 
 `--impl reference` times the reference's own MH sampler (oracle/_ref, unmodified) on the host
@@ -362,14 +363,12 @@ def main():
     eng.set_stream(stream.cuda_stream)
     eng.set_cycle(cycle)
     eng.init_prior()
-    live = eng.live()                                   # host copy of the live set, ascending logL
+    live_t = torch.from_numpy(eng.live()).pin_memory()  # the caller's live set: ONE pinned host table, ascending logL at start
+    live = live_t.numpy()
     rs = np.random.RandomState(SEED + rank)
-    req_t = torch.empty((K, DIM + 2), dtype=torch.float64).pin_memory()
-    rep_t = torch.empty((K, DIM + 2), dtype=torch.float64).pin_memory()
     st_t = torch.empty(K, dtype=torch.int32).pin_memory()
     ac_t = torch.empty(K, dtype=torch.int32).pin_memory()
-    sl_t = torch.empty(K, dtype=torch.int32).pin_memory()
-    req, rep, stp, acc_, slots = req_t.numpy(), rep_t.numpy(), st_t.numpy(), ac_t.numpy(), sl_t.numpy()
+    stp, acc_ = st_t.numpy(), ac_t.numpy()
     # the device pool mirrors the host live set slot by slot
     eng.set_live(live)
     nm = max(20, s1["nmcmc"])                           # the chain length the device-resident run settled on
@@ -384,11 +383,9 @@ def main():
         part = np.argpartition(logL, K - 1)
         worst, surv = part[:K], part[K:]
         logLmin = logL[worst].max()
-        starts = surv[rs.randint(0, N - K, size=K)]
-        np.take(live, starts, axis=0, out=req, mode="clip")   # requests: start points drawn among the survivors (unbuffered)
-        slots[:] = worst                                # the K worst slots are overwritten by the replies
-        eng.evolve_host(req, logLmin, nm, slots=slots, replies=rep, steps=stp, accepted=acc_)
-        live[worst] = rep
+        starts = surv[rs.randint(0, N - K, size=K)]     # requests: start points drawn among the survivors
+        # request j = row starts[j] of the host table, reply j -> row worst[j]: the device reads and writes the pinned table
+        eng.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_)
 
     for _ in range(args.warmup):
         host_step()
@@ -401,8 +398,8 @@ def main():
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_evals = eng.state()["total_evals"] - ev_before
     e2e_value = sum_over_ranks(e2e_evals) / t_e2e
-    h2d = K * (DIM + 2) * 8 + K * 4
-    d2h = K * (DIM + 2) * 8 + 2 * K * 4
+    h2d = K * (DIM + 2) * 8 + 2 * K * 4                 # K request rows read from the host table + start / slot indices
+    d2h = K * (DIM + 2) * 8 + 2 * K * 4                 # K reply rows written into the host table + steps / accepted
     eng.close()
 
     cpu = None
@@ -434,7 +431,7 @@ def main():
             "accepted_chain_steps_per_s": accepted / (dt_ms * 1e-3),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "cpn_evolve_host (sampler pipe protocol, pinned host buffers, host-side live set)",
+                    "api": "cpn_evolve_host_table (sampler pipe protocol over the caller's pinned host live table: the device reads the K request rows from it and writes the K replies into it; selection of the worst points on the host)",
                     "chain_length": nm},
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -39,12 +39,29 @@ def _digest():
     return h.hexdigest()
 
 
+def _unit_digest(src):
+    """Digest of one translation unit: its source, every header (all units include most of them) and the flags."""
+    h = hashlib.sha256()
+    heads = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    for f in [src] + heads + ["../../include/cpnest_b200.h"]:
+        h.update(f.encode())
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
 def _compile(src):
+    """Compile one unit unless its object is up to date (so a change to api.cu alone recompiles api.cu alone)."""
     out = os.path.join(OBJ, src[:-3] + ".o")
+    stamp = out + ".sha256"
+    dig = _unit_digest(src)
+    if os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return out
     cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    open(stamp, "w").write(dig + "\n")
     return out
 
 
@@ -52,6 +69,10 @@ def build(force=False, jobs=None, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(HERE, "lib", "build.sha256")
     dig = _digest()
+    if force:
+        for f in os.listdir(OBJ):
+            if f.endswith(".sha256"):
+                os.remove(os.path.join(OBJ, f))
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return LIB
     if not os.path.exists(NVCC):

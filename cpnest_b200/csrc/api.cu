@@ -1569,6 +1569,96 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
     return 0;
 }
 
+// ---- host protocol over a pinned host table: the device gathers the requests and scatters the replies itself ----
+__global__ void k_gather_table(const double* __restrict__ table, const int* __restrict__ idx, int K, int N, int D, int Dp,
+                               double* __restrict__ x, double* __restrict__ logL, double* __restrict__ logP) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Dp) return;
+    const int j = i / Dp, d = i % Dp;
+    const int r = min(max(idx[j], 0), N - 1);
+    const double* row = table + (size_t)r * (D + 2);
+    x[i] = (d < D) ? row[d] : 0.0;
+    if (d == 0) { logL[j] = row[D]; logP[j] = row[D + 1]; }
+}
+__global__ void k_scatter_table(double* __restrict__ table, const int* __restrict__ slots, int K, int N, int D, int Dp,
+                                const double* __restrict__ x, const double* __restrict__ logL, const double* __restrict__ logP) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * (D + 2)) return;
+    const int j = i / (D + 2), d = i % (D + 2);
+    const int r = slots[j];
+    if (r < 0 || r >= N) return;
+    table[(size_t)r * (D + 2) + d] = (d < D) ? x[(size_t)j * Dp + d] : (d == D ? logL[j] : logP[j]);
+}
+
+extern "C" int cpn_evolve_host_table(cpn_ctx* c, int32_t K, double logLmin, int32_t nmcmc, double* table,
+                                     const int32_t* start_idx, const int32_t* slots, int32_t* steps, int32_t* accepted) {
+    if (!c || !table || !start_idx || !slots) return fail("null argument");
+    if (!c->live_ready) return fail("live set not initialised");
+    if (K < 1 || K > c->N) return fail("K=%d must be in [1, nlive]", K);
+    CK(cudaSetDevice(c->cfg.device));
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, table) != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) {
+        cudaGetLastError();
+        return fail("cpn_evolve_host_table: the table must be pinned host memory (cudaHostAlloc / cudaHostRegister, e.g. "
+                    "torch.Tensor.pin_memory()); use cpn_evolve_host for pageable buffers");
+    }
+    double* d_table = (double*)at.devicePointer;
+    for (int j = 0; j < K; ++j) {
+        if (start_idx[j] < 0 || start_idx[j] >= c->N) return fail("cpn_evolve_host_table: start_idx[%d] = %d out of range", j, start_idx[j]);
+        if (slots[j] < 0 || slots[j] >= c->N) return fail("cpn_evolve_host_table: slots[%d] = %d out of range", j, slots[j]);
+    }
+    const int D = c->D, Dp = c->Dp, T = 256;
+    int* d_idx = c->d_sort_idx;                         // scratch of the initial sort, free during a run
+    CK(cudaMemcpyAsync(d_idx, start_idx, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_gather_table<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(d_table, d_idx, K, c->N, D, Dp, c->d_start_x, c->d_start_logL, c->d_start_logP);
+    if (launch_chains(c, K, 0, K, START_GIVEN, 0, true, logLmin, std::max(1, std::min(nmcmc, c->cfg.maxmcmc)), 1)) return 1;
+    for (int k = 0; k < kNumKinds; ++k) {
+        const int a = c->last_kb[k], b = c->last_kb[k + 1];
+        if (b <= a) continue;
+        k_batch_counters<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, k, a, b, c->d_new_steps, c->d_new_acc, c->d_new_evals);
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, k, b - a, nullptr, nullptr, 0);
+        if (k == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, a, b, c->d_new_ne, c->d_new_nc);
+        c->launches += 2 + (k == CPN_SAMPLER_SLICE);
+    }
+    k_pool_append<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rank, K, c->N, Dp, c->d_new_x, c->d_new_logL, c->d_new_logP,
+                                                          c->d_x, c->d_logL, c->d_logP);
+    k_scatter_table<<<(K * (D + 2) + T - 1) / T, T, 0, c->stream>>>(d_table, c->d_rank, K, c->N, D, Dp, c->d_new_x, c->d_new_logL,
+                                                                  c->d_new_logP);
+    CKL();
+    c->launches += 3;
+    if (steps) CK(cudaMemcpyAsync(steps, c->d_new_steps, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (accepted) CK(cudaMemcpyAsync(accepted, c->d_new_acc, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->chain_counter += (unsigned long long)K;
+    c->batches_enqueued += 1;
+    return 0;
+}
+
+// the caller's side of the protocol: rows of a host table by index (see the header)
+extern "C" int cpn_host_gather_rows(const double* table, int64_t nrows, int32_t row_doubles, const int64_t* idx, int32_t n,
+                                    double* out) {
+    if (!table || !idx || !out || row_doubles < 1 || n < 0) return fail("cpn_host_gather_rows: bad argument");
+    const size_t rb = (size_t)row_doubles * sizeof(double);
+    for (int32_t j = 0; j < n; ++j) {
+        const int64_t i = idx[j];
+        if (i < 0 || i >= nrows) return fail("cpn_host_gather_rows: index %lld at %d out of range [0, %lld)", (long long)i, j, (long long)nrows);
+        memcpy(out + (size_t)j * row_doubles, table + (size_t)i * row_doubles, rb);
+    }
+    return 0;
+}
+extern "C" int cpn_host_scatter_rows(double* table, int64_t nrows, int32_t row_doubles, const int64_t* idx, int32_t n,
+                                     const double* rows) {
+    if (!table || !idx || !rows || row_doubles < 1 || n < 0) return fail("cpn_host_scatter_rows: bad argument");
+    const size_t rb = (size_t)row_doubles * sizeof(double);
+    for (int32_t j = 0; j < n; ++j) {
+        const int64_t i = idx[j];
+        if (i < 0 || i >= nrows) return fail("cpn_host_scatter_rows: index %lld at %d out of range [0, %lld)", (long long)i, j, (long long)nrows);
+    }
+    for (int32_t j = 0; j < n; ++j) memcpy(table + (size_t)idx[j] * row_doubles, rows + (size_t)j * row_doubles, rb);
+    return 0;
+}
+
 // ---- parity entry points --------------------------------------------------------------------------------------
 extern "C" int cpn_eval_model(cpn_ctx* c, const double* x, int32_t n, double* logL, double* logP) {
     if (!c || !x || !logL || !logP || n < 1) return fail("bad argument");

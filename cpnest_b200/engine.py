@@ -222,6 +222,42 @@ class Engine:
                                          replies.ctypes.data, steps.ctypes.data, accepted.ctypes.data))
         return replies, steps, accepted
 
+    def evolve_host_table(self, table, start_idx, slots, logLmin, nmcmc, steps=None, accepted=None):
+        """The pipe protocol over the caller's pinned host live table (cpn_evolve_host_table): request j is row
+        table[start_idx[j]], reply j lands in row table[slots[j]].  `table` is the .numpy() view of a pinned torch tensor
+        (or any cudaHostRegister'ed C-contiguous float64 array) of shape [nlive][D+2]."""
+        K = len(start_idx)
+        assert table.flags.c_contiguous and table.dtype == np.float64 and table.shape == (self.nlive, self.dim + 2)
+        start_idx = np.ascontiguousarray(start_idx, dtype=np.int32)
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        assert len(slots) == K
+        if steps is None:
+            steps = np.empty(K, dtype=np.int32)
+        if accepted is None:
+            accepted = np.empty(K, dtype=np.int32)
+        L.check(self.lib.cpn_evolve_host_table(self.h, K, float(logLmin), int(nmcmc), table.ctypes.data, start_idx.ctypes.data,
+                                               slots.ctypes.data, steps.ctypes.data, accepted.ctypes.data))
+        return steps, accepted
+
+    @staticmethod
+    def host_gather_rows(table, idx, out):
+        """out[j] = table[idx[j]] for C-contiguous float64 tables (cpn_host_gather_rows)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        assert table.flags.c_contiguous and out.flags.c_contiguous and table.dtype == out.dtype == np.float64
+        assert out.shape == (len(idx), table.shape[1])
+        L.check(L.load().cpn_host_gather_rows(table.ctypes.data, table.shape[0], table.shape[1], idx.ctypes.data, len(idx),
+                                              out.ctypes.data))
+        return out
+
+    @staticmethod
+    def host_scatter_rows(table, idx, rows):
+        """table[idx[j]] = rows[j] (cpn_host_scatter_rows)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        assert table.flags.c_contiguous and rows.flags.c_contiguous and table.dtype == rows.dtype == np.float64
+        assert rows.shape == (len(idx), table.shape[1])
+        L.check(L.load().cpn_host_scatter_rows(table.ctypes.data, table.shape[0], table.shape[1], idx.ctypes.data, len(idx),
+                                               rows.ctypes.data))
+
     # ---- observation ------------------------------------------------------------------------
     def state(self):
         s = L.cpn_state()

@@ -221,6 +221,19 @@ int cpn_evolve_host(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc,
 /* `slots` (may be NULL): pool slot that reply j replaces afterwards, the device form of
  * `self.evolution_points.append(p)` (sampler.py:243, 351), so the proposal ensemble follows a
  * live set that the caller keeps in host memory. */
+/* The same protocol without host-side row moves: the caller's live set is ONE pinned host table[nlive][D+2]
+ * (cudaHostAlloc / cudaHostRegister memory, e.g. a torch tensor after .pin_memory()).  Request j is the row
+ * table[start_idx[j]]; the device reads those rows from host memory itself, evolves them, and writes reply j into
+ * row table[slots[j]] (and into pool slot slots[j] of the device ensemble).  start_idx / slots are host int32[K].
+ * When the call returns the table holds the replies.  Same bytes over the bus as cpn_evolve_host, no CPU gather/scatter. */
+int cpn_evolve_host_table(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc, double* table,
+                          const int32_t* start_idx, const int32_t* slots, int32_t* steps, int32_t* accepted);
+/* Host-side row moves of a caller that keeps the live set in host memory as one table[nrows][row_doubles] (the
+ * NestedSampler side of the protocol: `self.params[k]` handed to the pipes and replaced by the replies,
+ * cpnest/NestedSampling.py:324-366): out[j] = table[idx[j]] and table[idx[j]] = rows[j].  Plain memcpy loops (numpy's
+ * fancy indexing moves these rows at ~4 GB/s); pure host code, no context needed.  Indices out of range fail. */
+int cpn_host_gather_rows(const double* table, int64_t nrows, int32_t row_doubles, const int64_t* idx, int32_t n, double* out);
+int cpn_host_scatter_rows(double* table, int64_t nrows, int32_t row_doubles, const int64_t* idx, int32_t n, const double* rows);
 
 /* ---- parity / test entry points ------------------------------------------------------------ */
 /* Model.log_prior / log_likelihood on given points (functor parity vs the Python callables). */

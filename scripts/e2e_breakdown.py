@@ -10,14 +10,13 @@ e = Engine("gaussian_iid", [[-10, 10]] * DIM, nlive=N, maxmcmc=5000, seed=7)
 e.set_cycle(DefaultProposalCycle().device_cycle())
 e.init_prior()
 e.run(K, max_batches=60)
-live = e.live(); e.set_live(live)
+live_t = torch.from_numpy(e.live()).pin_memory(); live = live_t.numpy(); e.set_live(live)
 rs = np.random.RandomState(1)
 pin = lambda *s, dt=torch.float64: torch.empty(s, dtype=dt).pin_memory()
-req_t, rep_t = pin(K, DIM + 2), pin(K, DIM + 2)
-st_t, ac_t, sl_t = pin(K, dt=torch.int32), pin(K, dt=torch.int32), pin(K, dt=torch.int32)
-req, rep, stp, acc_, slots = req_t.numpy(), rep_t.numpy(), st_t.numpy(), ac_t.numpy(), sl_t.numpy()
+st_t, ac_t = pin(K, dt=torch.int32), pin(K, dt=torch.int32)
+stp, acc_ = st_t.numpy(), ac_t.numpy()
 nm = e.state()["nmcmc"]
-T = np.zeros(5)
+T = np.zeros(3)
 n = 40
 for i in range(n + 5):
     t0 = time.perf_counter()
@@ -27,13 +26,9 @@ for i in range(n + 5):
     logLmin = logL[worst].max()
     t1 = time.perf_counter()
     starts = surv[rs.randint(0, N - K, size=K)]
-    np.take(live, starts, axis=0, out=req)
-    slots[:] = worst
     t2 = time.perf_counter()
-    e.evolve_host(req, logLmin, nm, slots=slots, replies=rep, steps=stp, accepted=acc_)
+    e.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_)
     t3 = time.perf_counter()
-    live[worst] = rep
-    t4 = time.perf_counter()
     if i >= 5:
-        T[:4] += [t1 - t0, t2 - t1, t3 - t2, t4 - t3]
-print("per step [ms]: select %.3f  gather requests %.3f  cpn_evolve_host %.3f  scatter replies %.3f  (chain length %d)" % (*(1e3 * T[:4] / n), nm))
+        T += [t1 - t0, t2 - t1, t3 - t2]
+print("per step [ms]: select %.3f  draw starts %.3f  cpn_evolve_host_table %.3f  (chain length %d)" % (*(1e3 * T / n), nm))

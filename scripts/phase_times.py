@@ -30,3 +30,9 @@ t = np.array([[ev[i][k].elapsed_time(ev[i][k + 1]) for k in range(3)] for i in r
 tot = ev[0][0].elapsed_time(ev[n - 1][3]) / n
 print("lanes=%d " % lanes + "K=%d mean ms: select %.3f evolve %.3f insert %.3f | sum %.3f, wall/step %.3f" % (K, *t.mean(0), t.mean(0).sum(), tot))
 pass
+ev_t = t[:, 1]
+print("evolve ms: min %.3f median %.3f max %.3f; batches slower than 1.1 x median: %d of %d" % (
+    ev_t.min(), np.median(ev_t), ev_t.max(), int((ev_t > 1.1 * np.median(ev_t)).sum()), n))
+print("select ms: median %.3f max %.3f; insert ms: median %.3f max %.3f" % (
+    np.median(t[:, 0]), t[:, 0].max(), np.median(t[:, 2]), t[:, 2].max()))
+print("per batch [select evolve insert]:", " ".join("[%.3f %.3f %.3f]" % tuple(r) for r in t[:16]))

@@ -84,3 +84,46 @@ def test_large_batches_are_ranked_in_segments_with_ties():
         assert len(ins) == 4 * K and ins.min() >= 0 and ins.max() <= 1
     # the same run with K below the segment threshold must agree on the first batch's threshold
     assert before.shape == (N, D + 2)
+
+
+def test_host_table_protocol_equals_the_buffer_protocol():
+    """cpn_evolve_host_table (the device reads the requests from / writes the replies into the caller's pinned host table)
+    against cpn_evolve_host (request / reply buffers moved by the caller): same chains, same replies, same table."""
+    import torch
+    from cpnest_b200._lib import CpnError
+    from cpnest_b200.engine import Engine
+    D, N, K = 7, 600, 200
+    rs = np.random.RandomState(0)
+
+    def make():
+        e = Engine("gaussian_iid", [[-10, 10]] * D, nlive=N, maxmcmc=200, seed=21)
+        e.init_prior()
+        live = e.live()
+        e.set_live(live)
+        return e, live
+    a, live_a = make()
+    b, live_b = make()
+    assert np.array_equal(live_a, live_b)
+    table_t = torch.from_numpy(live_b.copy()).pin_memory()
+    table = table_t.numpy()
+    with a, b:
+        for it in range(3):
+            logL = live_a[:, D]
+            part = np.argpartition(logL, K - 1)
+            worst, surv = part[:K], part[K:]
+            logLmin = logL[worst].max()
+            starts = surv[rs.randint(0, N - K, size=K)]
+            req = np.ascontiguousarray(live_a[starts])
+            rep, st_a, ac_a = a.evolve_host(req, logLmin, 30, slots=worst.astype(np.int32))
+            live_a[worst] = rep
+            st_b, ac_b = b.evolve_host_table(table, starts, worst, logLmin, 30)
+            assert np.array_equal(table, live_a), it
+            assert np.array_equal(st_a, st_b) and np.array_equal(ac_a, ac_b)
+            assert np.all(table[worst, D] > logLmin)
+        assert a.state()["total_evals"] == b.state()["total_evals"]
+        with pytest.raises(CpnError, match="pinned"):
+            b.evolve_host_table(live_a, starts, worst, logLmin, 30)          # pageable numpy memory
+        bad = starts.copy()
+        bad[5] = N
+        with pytest.raises(CpnError, match="out of range"):
+            b.evolve_host_table(table, bad, worst, logLmin, 30)

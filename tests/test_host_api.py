@@ -58,6 +58,32 @@ def test_abi_struct_layout_matches_a_c_compiler(tmp_path):
             assert int(out["%s.%s" % (st, name)]) == getattr(cls, name).offset, (st, name)
 
 
+def test_host_row_helpers_match_numpy_indexing():
+    # cpn_host_gather_rows / cpn_host_scatter_rows: pure host code of the C-ABI (no device needed)
+    from cpnest_b200 import _lib
+    from cpnest_b200.engine import Engine
+    rs = np.random.RandomState(3)
+    table = rs.normal(size=(1000, 52))
+    idx = rs.randint(0, 1000, size=300)
+    out = np.empty((300, 52))
+    Engine.host_gather_rows(table, idx, out)
+    assert np.array_equal(out, table[idx])
+    rows = rs.normal(size=(300, 52))
+    uniq = rs.permutation(1000)[:300]
+    expect = table.copy()
+    expect[uniq] = rows
+    Engine.host_scatter_rows(table, uniq, rows)
+    assert np.array_equal(table, expect)
+    Engine.host_gather_rows(table, np.zeros(0, dtype=np.int64), np.empty((0, 52)))      # empty request
+    for bad in ([1000], [-1]):
+        with pytest.raises(_lib.CpnError, match="out of range"):
+            Engine.host_gather_rows(table, np.array(bad), np.empty((1, 52)))
+        before = table.copy()
+        with pytest.raises(_lib.CpnError, match="out of range"):
+            Engine.host_scatter_rows(table, np.array([0] + bad), np.ones((2, 52)))
+        assert np.array_equal(table, before)                                            # nothing written on failure
+
+
 def test_no_cpu_fallback_fails_loudly():
     import torch
     if torch.cuda.is_available():
