@@ -97,7 +97,7 @@ struct cpn_ctx {
     cudaStream_t side;
     cudaEvent_t ev_main, ev_cov, ev_eig;
     cudaStream_t acc_stream;    // evidence accumulation of a batch, beside its chain kernel
-    cudaEvent_t ev_thr, ev_acc;
+    cudaEvent_t ev_thr, ev_acc, ev_ins, ev_corr;
     bool acc_pending;           // an accumulation is in flight that the main stream has not waited for yet
     uint8_t* d_cycle;
     int cycle_len;
@@ -473,6 +473,8 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     CK(cudaStreamCreateWithFlags(&c->acc_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_thr, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_acc, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_ins, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_corr, cudaEventDisableTiming));
     if (c->mixed) {
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         for (int k = 0; k < kNumKinds; ++k) {
@@ -575,7 +577,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_cov); cudaEventDestroy(c->ev_eig);
     cudaStreamDestroy(c->side);
     cudaStreamDestroy(c->acc_stream);
-    cudaEventDestroy(c->ev_thr); cudaEventDestroy(c->ev_acc);
+    cudaEventDestroy(c->ev_thr); cudaEventDestroy(c->ev_acc); cudaEventDestroy(c->ev_ins); cudaEventDestroy(c->ev_corr);
     if (c->mixed) {
         cudaEventDestroy(c->ev_fork);
         for (int k = 0; k < kNumKinds; ++k) { cudaStreamSynchronize(c->kind_stream[k]); cudaStreamDestroy(c->kind_stream[k]); cudaEventDestroy(c->ev_kind[k]); }
@@ -1109,23 +1111,29 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     if (join_acc(c)) return 1;                 // the merge appends at the counters the accumulation has advanced
     int kb[kNumKinds + 1];
     if (kind_ranges(c, K, kb)) return 1;
-    if (!c->staged_external) {
+    const bool corr = !c->staged_external;
+    if (corr) {
         // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
-        // control, and the batch counters
+        // control, and the batch counters: on the accumulation stream (idle by now), beside the ranking of the
+        // replacements below; the merge waits for both
+        cudaStream_t cs = c->acc_stream;
+        CK(cudaEventRecord(c->ev_ins, c->stream));
+        CK(cudaStreamWaitEvent(cs, c->ev_ins, 0));
         for (int k = 0; k < kNumKinds; ++k) {
             if (kb[k + 1] <= kb[k]) continue;
-            k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, k, kb[k], kb[k + 1], c->D, c->Dp, c->d_new_start, c->d_x,
+            k_chain_corr<<<c->D + 2, kCorrThreads, 0, cs>>>(c->d_state, k, kb[k], kb[k + 1], c->D, c->Dp, c->d_new_start, c->d_x,
                                                           c->d_logL, c->d_new_x, c->d_new_logL, c->d_rho + k * (c->D + 1),
                                                           c->d_new_steps, c->d_new_acc, c->d_new_evals);
             c->launches += 1;
             if (k == CPN_SAMPLER_SLICE) {
-                k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, kb[k], kb[k + 1], c->d_new_ne, c->d_new_nc);
+                k_adapt_slice_mu<<<1, 256, 0, cs>>>(c->d_state, kb[k], kb[k + 1], c->d_new_ne, c->d_new_nc);
                 c->launches += 1;
             } else if (k == CPN_SAMPLER_HMC) {
-                k_adapt_hmc_dt<<<1, 1, 0, c->stream>>>(c->d_state);
+                k_adapt_hmc_dt<<<1, 1, 0, cs>>>(c->d_state);
                 c->launches += 1;
             }
         }
+        CK(cudaEventRecord(c->ev_corr, cs));
     }
     CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
     if (K <= 2 * kRankSeg) {
@@ -1156,6 +1164,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     m.new_x = c->d_new_x; m.new_logL = c->d_new_logL; m.new_logP = c->d_new_logP;
     m.dead_x = c->d_dead_x; m.dead_logL = c->d_dead_logL; m.dead_logP = c->d_dead_logP;
     m.insertion = c->d_ins;
+    if (corr) CK(cudaStreamWaitEvent(c->stream, c->ev_corr, 0));
     if (c->wait_cov) {     // an asynchronous refresh must have read the live rows before they are overwritten
         CK(cudaStreamWaitEvent(c->stream, c->ev_cov, 0));
         c->wait_cov = false;

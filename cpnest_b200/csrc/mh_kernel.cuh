@@ -48,16 +48,20 @@ struct StepIn {
 };
 
 // The inputs of G consecutive steps are computed once, one step per lane (Philox blocks (chain, step, 0/1),
-// Box-Muller, log(u), exp), packed into 8 words and handed out by shuffle step after step: a step costs
-// 8 shuffles instead of a redundant RNG evaluation on every lane, and the stream is a pure function of
-// (seed, chain, step) - independent of G and of the grid.
-template <int G>
+// Box-Muller, log(u), exp), packed into 8 words and handed out step after step through the lane's row of a
+// shared-memory table (two 128-bit broadcast loads per step; 8 shuffles before v8) instead of a redundant RNG
+// evaluation on every lane; the stream is a pure function of (seed, chain, step) - independent of G and of the grid.
+// FLAT: the prior is flat, so the prior MH test `dlogP > log(u) - log_J` (sampler.py:337) can only fail through the
+// box (dlogP = -inf) unless log_J != 0, i.e. only EnsembleStretch needs log(u); the other kinds get thr = -1 (any
+// negative number gives the same decisions as log(u) < 0).
+template <int G, bool FLAT>
 struct DrawFeed {
     uint32_t w[8];   // i0, i1, i2, c0, c1, c2 (fp32 bits), thr (fp64 bits)
+    uint4* row;      // this lane's 32-byte row of the block's table (G > 1)
     __device__ __forceinline__ void refill(int kind, uint32_t step, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1,
                                            uint32_t ens_n, uint32_t D, const double* eig_scale) {
         const Philox4 r = philox4x32_10(cid_lo, cid_hi, step, 0u, k0, k1);
-        double thr = log(u32_to_unit_open(r.v[3]));
+        double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : log(u32_to_unit_open(r.v[3]));
         uint32_t i0 = u32_to_index(r.v[0], ens_n), i1, i2;
         float c0, c1 = 0.0f, c2 = 0.0f;
         if (kind == CPN_WALK) {
@@ -98,11 +102,23 @@ struct DrawFeed {
         w[3] = __float_as_uint(c0); w[4] = __float_as_uint(c1); w[5] = __float_as_uint(c2);
         w[6] = (uint32_t)__double2loint(thr);
         w[7] = (uint32_t)__double2hiint(thr);
+        if (G > 1) {
+            __syncwarp();                       // every lane has read the previous G steps
+            row[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            row[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            __syncwarp();
+        }
     }
-    __device__ __forceinline__ StepIn get(int kind, int src_lane) const {
+    // src_row: row of the lane of this group that prepared the step
+    __device__ __forceinline__ StepIn get(int kind, const uint4* src_row) const {
         uint32_t v[8];
+        if (G == 1) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (G == 1) ? w[k] : __shfl_sync(FULL, w[k], src_lane, G);
+            for (int k = 0; k < 8; ++k) v[k] = w[k];
+        } else {
+            const uint4 a = src_row[0], b = src_row[1];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
         StepIn s;
         s.kind = kind;
         s.i0 = v[0]; s.i1 = v[1]; s.i2 = v[2];
@@ -168,6 +184,7 @@ template <int G, int E, class Model, bool REPLAY>
 // wave: time per launch is flat in the number of chains up to there)
 __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(const MHParams p) {
     extern __shared__ double smem[];
+    __shared__ uint4 feed_tab[REPLAY ? 1 : kMHThreads][2];     // DrawFeed: one 32-byte row per thread
     Chain<G, E, Model> ch;
     if (!ch.begin(p, smem, REPLAY)) return;
     const Group<G>& g = ch.g;
@@ -264,16 +281,19 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         // every proposal.
         auto production = [&](const ModelCtx& mm) {
         const uint32_t ens_n = (uint32_t)p.ens_n;
-        DrawFeed<G> feed;
+        DrawFeed<G, Model::kFlatPrior> feed;
+        feed.row = &feed_tab[threadIdx.x][0];
+        const uint4* grow = &feed_tab[threadIdx.x & ~(G - 1)][0];        // row of this group's lane 0
         auto next_in = [&](int it) -> StepIn {
             const int kind = p.cycle[npos];
             if ((it & (G - 1)) == 0) {                                   // this lane prepares step it + lane
-                const int lpos = (npos + g.lane) % clen;
+                int lpos = npos + g.lane;                                // (npos + lane) % clen without the division
+                while (lpos >= clen) lpos -= clen;
                 feed.refill(p.cycle[lpos], (uint32_t)(it + g.lane), cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D,
                             p.eig_scale);
             }
             npos = (npos + 1 == clen) ? 0 : npos + 1;
-            return feed.get(kind, it & (G - 1));
+            return feed.get(kind, grow + 2 * (it & (G - 1)));
         };
         // One MCMC step on (s, r0..r2); meanwhile the inputs of the following step are drawn and gathered into
         // (ns, n0..n2).  The caller alternates two such sets, so nothing is copied between steps.
