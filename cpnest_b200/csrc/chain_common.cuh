@@ -85,15 +85,25 @@ struct Chain {
     int start_slot;
     double blo[E], bhi[E];     // the box; coordinates beyond D get (-inf, +inf) so the test needs no branch
 
-    // false: the whole warp lies beyond the batch (or the run is over) and must return
-    __device__ __forceinline__ bool begin(const ChainParams& p, double* smem, bool replay) {
+    // false: the whole warp lies beyond the batch (or the run is over) and must return.
+    // team > 1 (G == 32 only): the block's `team` warps all own chain blockIdx.x; team_buf is block-shared scratch
+    __device__ __forceinline__ bool begin(const ChainParams& p, double* smem, bool replay, int team = 1, double* team_buf = nullptr) {
         if (!replay && p.state != nullptr && p.state->done) return false;
         const int cpb = kMHThreads / G;
         const int nchains = p.j1 - p.j0;
-        c = blockIdx.x * cpb + (int)threadIdx.x / G;
-        if ((c & ~(32 / G - 1)) >= nchains) return false;
-        valid = c < nchains;
-        if (!valid) c = nchains - 1;
+        if (team > 1) {
+            c = blockIdx.x;
+            if (c >= nchains) return false;
+            m.team = team;
+            m.team_rank = (int)threadIdx.x / G;
+            m.team_buf = team_buf;
+            valid = m.team_rank == 0;              // one warp hands the chain back
+        } else {
+            c = blockIdx.x * cpb + (int)threadIdx.x / G;
+            if ((c & ~(32 / G - 1)) >= nchains) return false;
+            valid = c < nchains;
+        }
+        if (!valid && team == 1) c = nchains - 1;
         j = p.j0 + c;
         m.blob = p.blob;
         m.D = p.D;

@@ -185,8 +185,11 @@ template <int G, int E, class Model, bool REPLAY>
 __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(const MHParams p) {
     extern __shared__ double smem[];
     __shared__ uint4 feed_tab[REPLAY ? 1 : kMHThreads][2];     // DrawFeed: one 32-byte row per thread
+    // team mode: the block's warps evolve one chain together and split the functor's data sum (models.cuh kTeam)
+    constexpr int TEAM = (!REPLAY && G == 32 && Model::kTeam > 1) ? kMHThreads / 32 : 1;
+    __shared__ double team_buf[TEAM];
     Chain<G, E, Model> ch;
-    if (!ch.begin(p, smem, REPLAY)) return;
+    if (!ch.begin(p, smem, REPLAY, TEAM, team_buf)) return;
     const Group<G>& g = ch.g;
     const ModelCtx& m = ch.m;
     const int c = ch.c, D = p.D, nmcmc = ch.nmcmc, maxmcmc = p.maxmcmc;

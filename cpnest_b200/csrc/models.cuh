@@ -21,6 +21,11 @@ struct ModelCtx {
     double* scratch;      // per-chain shared-memory scratch, kScratchRows * Dp doubles (functors with kScratch)
     double par[4];        // functor parameters kept in registers by Model::prepare (read once per chain, not per step)
     uint32_t vmsk[8];     // per slot e: all ones if coordinate lane + e*G exists (< D), else 0 (set by set_valid_mask)
+    // team mode (MH production kernel, functors with kTeam > 1): `team` warps of the block evolve the SAME chain in
+    // lock step (same draws, same decisions) and split the functor's data sum; team_buf[team] is block-shared
+    int team = 1;
+    int team_rank = 0;
+    double* team_buf = nullptr;
 };
 
 template <int G, int E>
@@ -34,6 +39,9 @@ __device__ __forceinline__ double masked(const ModelCtx& m, int e, double v) {
 }
 
 struct ModelBase {
+    // warps per chain in the MH production kernel when a chain owns a whole warp (G == 32): > 1 for functors whose
+    // cost is a long data sum, so that a batch of a few hundred chains still fills the SMs
+    static constexpr int kTeam = 1;
     static __device__ __forceinline__ void prepare(ModelCtx&) {}
     // true if the functor's value does not change when the slots beyond D of a point hold +0.0 and are NOT masked: the
     // MH kernel then skips the masks whenever the rows it gathers are zero-padded up to G*E doubles (mh_kernel.cuh)
@@ -414,6 +422,7 @@ struct GaussMixture : ModelBase {
     static constexpr bool kFlatPrior = false;
     static constexpr bool kScratch = false;
     static constexpr bool kCheap = false;
+    static constexpr int kTeam = 4;
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         const double m1 = coord<G, E>(g, x, 0), s1 = coord<G, E>(g, x, 1), m2 = coord<G, E>(g, x, 2),
@@ -425,12 +434,14 @@ struct GaussMixture : ModelBase {
         // np.logaddexp(l1, l2) = hi + log1p(exp(lo - hi)), summed over the data.  The log1p terms are collected as a
         // product: every factor 1 + exp(lo - hi) lies in [1, 2], so 512 of them cannot overflow, and one log per 512
         // terms replaces 512 log1p calls (rounding: <= 1 ulp per factor, i.e. < 1e-13 absolute on a sum of O(1e4)).
+        // the data are dealt to the lanes of the whole team (m.team warps of G lanes; team == 1 outside team mode)
+        const int W = G * m.team;
         double acc = 0.0;
-        for (int base = g.lane; base < n; base += 512 * G) {
-            const int end = min(n, base + 512 * G);
+        for (int base = m.team_rank * G + g.lane; base < n; base += 512 * W) {
+            const int end = min(n, base + 512 * W);
             double prod = 1.0;
 #pragma unroll 8
-            for (int i = base; i < end; i += G) {
+            for (int i = base; i < end; i += W) {
                 const double d = __ldg(data + i);
                 const double t1 = (d - m1) * i1, t2 = (d - m2) * i2;
                 const double l1 = c1 - 0.5 * t1 * t1, l2 = c2 - 0.5 * t2 * t2;
@@ -440,7 +451,17 @@ struct GaussMixture : ModelBase {
             }
             acc += log(prod);
         }
-        return g.sum(acc);
+        acc = g.sum(acc);
+        if (m.team > 1) {
+            // every warp of the team reaches this point together (identical chain state, hence identical control flow);
+            // all of them add the partial sums in the same order, so they keep agreeing bit for bit
+            if (g.lane == 0) m.team_buf[m.team_rank] = acc;
+            __syncthreads();
+            acc = 0.0;
+            for (int w = 0; w < m.team; ++w) acc += m.team_buf[w];
+            __syncthreads();
+        }
+        return acc;
     }
     template <int G, int E>
     static __device__ __forceinline__ double log_prior(const Group<G>& g, const double (&x)[E], const ModelCtx&) {

@@ -127,3 +127,36 @@ def test_host_table_protocol_equals_the_buffer_protocol():
         bad[5] = N
         with pytest.raises(CpnError, match="out of range"):
             b.evolve_host_table(table, bad, worst, logLmin, 30)
+
+
+def test_team_mode_chains_agree_with_the_plain_functor():
+    """The mixture functor (1e4 data terms per call) runs MH chains in team mode: the four warps of a block evolve one chain
+    in lock step and split the data sum.  The logL every chain hands back must be the functor's value at the point it hands
+    back (evaluated here by the eval kernel, which has no teams), the run must be reproducible, and chains must move."""
+    from cpnest_b200.engine import Engine
+    rs = np.random.RandomState(1234)
+    n = 2000
+    data = np.concatenate((rs.normal(0.5, 0.5, size=n // 10), rs.normal(-1.5, 0.03, size=n - n // 10)))
+    b = [[-3, 3], [0.01, 1], [-3, 3], [0.01, 1], [0.0, 1.0]]
+
+    def run(lanes):
+        e = Engine("gaussian_mixture", b, nlive=300, maxmcmc=60, seed=9, params=dict(data=data), lanes=lanes)
+        e.init_prior()
+        for _ in range(6):
+            e.ns_step(37)                      # ragged: not a multiple of anything
+        s = e.state()
+        live = e.live()
+        rows, steps, acc = e.last_batch(37)
+        logL, logP = e.eval_model(live[:, :5])
+        e.close()
+        return s, live, rows, steps, acc, logL, logP
+    s, live, rows, steps, acc, logL, logP = run(0)          # automatic: one warp per chain -> team mode
+    assert np.allclose(live[:, 5], logL, rtol=1e-12, atol=0)
+    assert np.allclose(live[:, 6], logP, rtol=1e-12, atol=0)
+    assert np.all(rows[:, 5] > s["logLmin"]) and np.all(acc > 0) and np.all(steps >= 1)
+    assert s["iteration"] == 6 * 37
+    s2, live2 = run(0)[:2]
+    assert s2["logZ"] == s["logZ"] and np.array_equal(live, live2)
+    # 8 lanes per chain: no teams; a different but equally valid run
+    s3, live3, rows3, steps3, acc3, logL3, _ = run(8)
+    assert np.allclose(live3[:, 5], logL3, rtol=1e-12, atol=0) and np.all(acc3 > 0)
