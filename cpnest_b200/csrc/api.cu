@@ -682,7 +682,9 @@ static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events
     k_mean_partial<<<kStatBlocks, kStatThreads, 0, st>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
     k_mean_final<<<(D + 127) / 128, 128, 0, st>>>(c->d_mean_partial, kStatBlocks, N, D, c->d_mean);
     CK(cudaMemcpyAsync(c->d_eigmean[buf], c->d_mean, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    k_cov_partial<<<kStatBlocks, kStatThreads, (size_t)kCovTile * D * sizeof(double), st>>>(
+    const size_t cov_sm = (size_t)kMmaStage * cov_mma_ld(D) * sizeof(double);
+    if (cov_sm > 48 * 1024) CK(cudaFuncSetAttribute(k_cov_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_sm));
+    k_cov_partial<<<kStatBlocks, kStatThreads, cov_sm, st>>>(
         c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
     k_cov_final<<<(D * D + 127) / 128, 128, 0, st>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
     CK(cudaMemcpyAsync(c->d_covbuf[buf], c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, st));

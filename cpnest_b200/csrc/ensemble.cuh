@@ -10,10 +10,8 @@
 
 namespace cpn {
 
-constexpr int kStatBlocks = 128;
+constexpr int kStatBlocks = 32;       // slices of the ensemble (fixed: the shape of the partial sums must not vary)
 constexpr int kStatThreads = 256;
-constexpr int kCovChunk = 16;      // covariance entries per thread per pass
-constexpr int kCovTile = 32;       // points staged in shared memory per step
 
 __global__ void __launch_bounds__(kStatThreads) k_mean_partial(const double* __restrict__ x, int n, int D, int Dp,
                                                                double* __restrict__ partial /*[blocks][D]*/) {
@@ -43,41 +41,65 @@ __global__ void k_mean_final(const double* __restrict__ partial, int nb, int n, 
     mean[d] = s / (double)n;
 }
 
+// Partial covariance sums of a slice of the ensemble on the FP64 tensor cores: C = sum_p xc_p xc_p^T with xc = x - mean,
+// as 8x8 output tiles of mma.sync.m8n8k4.f64 (DMMA: IEEE fp64 multiply-add, four points per instruction).  Per tile
+// (ti, tj) and group of four points p..p+3, lane l = 4 r + k supplies A[r][k] = xc[p+k][8 ti + r] and
+// B[k][r] = xc[p+k][8 tj + r] and accumulates C[r][2k], C[r][2k+1] (the PTX fragment layout of m8n8k4).  The centred
+// points of a stage live in shared memory with a leading dimension LD = 4 or 12 (mod 16), which makes the fragment loads
+// conflict-free, zero-padded to whole tiles and whole groups of four.  A warp owns up to kMmaTilesPerWarp tiles per pass
+// over the points; blocks, stages and the order of accumulation are fixed, so the sums are reproducible.
+constexpr int kMmaStage = 32;          // points staged in shared memory per step (multiple of 4)
+constexpr int kMmaTilesPerWarp = 8;
+__host__ __device__ inline int cov_mma_ld(int D) {
+    int ld = ((D + 7) / 8) * 8;
+    while ((ld & 15) != 4 && (ld & 15) != 12) ++ld;
+    return ld;
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 __global__ void __launch_bounds__(kStatThreads) k_cov_partial(const double* __restrict__ x, const double* __restrict__ mean,
                                                               int n, int D, int Dp, double* __restrict__ partial /*[blocks][D*D]*/) {
-    extern __shared__ double tile[];   // [kCovTile][D] centred points
+    extern __shared__ double tile[];   // [kMmaStage][LD] centred points
+    const int LD = cov_mma_ld(D);
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int p0 = blockIdx.x * per, p1 = min(n, p0 + per);
-    const int nent = D * D;
-    for (int ebase = 0; ebase < nent; ebase += kStatThreads * kCovChunk) {
-        double acc[kCovChunk];
-        int ra[kCovChunk], rb[kCovChunk];
+    const int T8 = (D + 7) >> 3, ntile = T8 * T8;
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, nwarp = kStatThreads >> 5;
+    const int r = lane >> 2, k = lane & 3;
+    for (int tbase = 0; tbase < ntile; tbase += nwarp * kMmaTilesPerWarp) {
+        double c0[kMmaTilesPerWarp], c1[kMmaTilesPerWarp];
+        int oa[kMmaTilesPerWarp], ob[kMmaTilesPerWarp];        // column offsets 8 ti, 8 tj of the warp's tiles
 #pragma unroll
-        for (int k = 0; k < kCovChunk; ++k) {
-            acc[k] = 0.0;
-            const int ent = ebase + k * kStatThreads + threadIdx.x;
-            ra[k] = (ent < nent) ? ent / D : -1;
-            rb[k] = (ent < nent) ? ent % D : 0;
+        for (int q = 0; q < kMmaTilesPerWarp; ++q) {
+            const int t = tbase + q * nwarp + warp;
+            c0[q] = c1[q] = 0.0;
+            oa[q] = (t < ntile) ? 8 * (t / T8) : 0;
+            ob[q] = (t < ntile) ? 8 * (t % T8) : 0;
         }
-        for (int t0 = p0; t0 < p1; t0 += kCovTile) {
-            const int nt = min(kCovTile, p1 - t0);
-            for (int i = threadIdx.x; i < nt * D; i += kStatThreads) {
-                const int pi = i / D, d = i % D;
-                tile[pi * D + d] = x[(size_t)(t0 + pi) * Dp + d] - mean[d];
+        for (int s0 = p0; s0 < p1; s0 += kMmaStage) {
+            const int ns = min(kMmaStage, p1 - s0), ns4 = (ns + 3) & ~3;
+            for (int i = threadIdx.x; i < ns4 * LD; i += kStatThreads) {
+                const int pi = i / LD, d = i % LD;
+                tile[i] = (pi < ns && d < D) ? x[(size_t)(s0 + pi) * Dp + d] - mean[d] : 0.0;
             }
             __syncthreads();
-            for (int pi = 0; pi < nt; ++pi) {
-                const double* row = tile + pi * D;
+            for (int pp = 0; pp < ns4; pp += 4) {
+                const double* row = tile + (pp + k) * LD + r;
 #pragma unroll
-                for (int k = 0; k < kCovChunk; ++k)
-                    if (ra[k] >= 0) acc[k] = fma(row[ra[k]], row[rb[k]], acc[k]);
+                for (int q = 0; q < kMmaTilesPerWarp; ++q) dmma_m8n8k4(c0[q], c1[q], row[oa[q]], row[ob[q]]);
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int k = 0; k < kCovChunk; ++k) {
-            const int ent = ebase + k * kStatThreads + threadIdx.x;
-            if (ent < nent) partial[(size_t)blockIdx.x * nent + ent] = acc[k];
+        for (int q = 0; q < kMmaTilesPerWarp; ++q) {
+            const int t = tbase + q * nwarp + warp;
+            if (t >= ntile) continue;
+            const int i = oa[q] + r, j = ob[q] + 2 * k;
+            double* out = partial + (size_t)blockIdx.x * D * D + (size_t)i * D;
+            if (i < D && j < D) out[j] = c0[q];
+            if (i < D && j + 1 < D) out[j + 1] = c1[q];
         }
     }
 }

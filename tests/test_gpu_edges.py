@@ -160,3 +160,22 @@ def test_team_mode_chains_agree_with_the_plain_functor():
     # 8 lanes per chain: no teams; a different but equally valid run
     s3, live3, rows3, steps3, acc3, logL3, _ = run(8)
     assert np.allclose(live3[:, 5], logL3, rtol=1e-12, atol=0) and np.all(acc3 > 0)
+
+
+@pytest.mark.parametrize("D,P", [(1, 5), (2, 4), (7, 33), (8, 64), (9, 1000), (17, 129), (50, 10000), (63, 257), (64, 4097), (100, 300)])
+def test_tensor_core_covariance_for_ragged_shapes(D, P):
+    """np.cov of the ensemble (EnsembleEigenVector.update_eigenvectors, cpnest/proposal.py:311-323) is accumulated with fp64
+    tensor-core MMAs in 8x8 tiles over groups of four points: dimensions that are not multiples of 8, ensembles that are
+    not multiples of 4 or of the 32 slices, and the D == 1 variance branch (np.var, ddof 0, proposal.py:314-318)."""
+    from cpnest_b200.engine import Engine
+    rs = np.random.RandomState(D * 1000 + P)
+    X = rs.normal(size=(P, D)) @ rs.normal(size=(D, D)) + 3.0 * rs.normal(size=(1, D))
+    with Engine("gaussian_iid", [[-1e3, 1e3]] * D, nlive=P) as e:
+        e.set_live(np.concatenate((X, np.arange(float(P))[:, None], np.zeros((P, 1))), axis=1))
+        mean, cov, w, v = e.ensemble_stats()
+    ref = np.atleast_2d(np.var(X[:, 0])) if D == 1 else np.cov(X.T)
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.max(np.abs(mean - X.mean(0))) < 1e-13 * (1 + np.max(np.abs(X)))
+    assert np.max(np.abs(cov - ref) / scale) < 1e-12
+    assert np.array_equal(cov, cov.T)
+    assert np.max(np.abs(ref @ v - v * w)) < 1e-10 * max(1.0, np.max(np.abs(w)))
