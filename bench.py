@@ -365,7 +365,7 @@ def main():
     eng.init_prior()
     live_t = torch.from_numpy(eng.live()).pin_memory()  # the caller's live set: ONE pinned host table, ascending logL at start
     live = live_t.numpy()
-    rs = np.random.RandomState(SEED + rank)
+    rs = np.random.Generator(np.random.PCG64(SEED + rank))        # host draws of the start points (3x faster than RandomState.randint)
     st_t = torch.empty(K, dtype=torch.int32).pin_memory()
     ac_t = torch.empty(K, dtype=torch.int32).pin_memory()
     stp, acc_ = st_t.numpy(), ac_t.numpy()
@@ -380,10 +380,10 @@ def main():
         # where it is (row i <-> device pool slot i); a partial selection replaces the reference's sorted list.
         nonlocal e2e_evals
         logL = live[:, DIM]
-        part = np.argpartition(logL, K - 1)
+        part = np.argpartition(logL, K - 1).astype(np.int32)   # int32: the index type of the C-ABI, no conversions later
         worst, surv = part[:K], part[K:]
-        logLmin = logL[worst].max()
-        starts = surv[rs.randint(0, N - K, size=K)]     # requests: start points drawn among the survivors
+        logLmin = logL[part[K - 1]]                     # the K-th smallest sits at position K-1 of a partition: max of the K worst
+        starts = surv[rs.integers(0, N - K, size=K, dtype=np.int32)]     # requests: start points drawn among the survivors
         # request j = row starts[j] of the host table, reply j -> row worst[j]: the device reads and writes the pinned table
         eng.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_)
 

@@ -11,7 +11,7 @@ e.set_cycle(DefaultProposalCycle().device_cycle())
 e.init_prior()
 e.run(K, max_batches=60)
 live_t = torch.from_numpy(e.live()).pin_memory(); live = live_t.numpy(); e.set_live(live)
-rs = np.random.RandomState(1)
+rs = np.random.Generator(np.random.PCG64(1))
 pin = lambda *s, dt=torch.float64: torch.empty(s, dtype=dt).pin_memory()
 st_t, ac_t = pin(K, dt=torch.int32), pin(K, dt=torch.int32)
 stp, acc_ = st_t.numpy(), ac_t.numpy()
@@ -21,11 +21,11 @@ n = 40
 for i in range(n + 5):
     t0 = time.perf_counter()
     logL = live[:, DIM]
-    part = np.argpartition(logL, K - 1)
+    part = np.argpartition(logL, K - 1).astype(np.int32)
     worst, surv = part[:K], part[K:]
-    logLmin = logL[worst].max()
+    logLmin = logL[part[K - 1]]
     t1 = time.perf_counter()
-    starts = surv[rs.randint(0, N - K, size=K)]
+    starts = surv[rs.integers(0, N - K, size=K, dtype=np.int32)]
     t2 = time.perf_counter()
     e.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_)
     t3 = time.perf_counter()
