@@ -116,6 +116,7 @@ struct cpn_ctx {
     double* d_rec;              // [N][D+2] record scratch of the host protocol
     int* d_sweeps;
     NSState* h_state;           // pinned
+    int* h_idx;                 // pinned [2 * nlive]: index arguments of cpn_evolve_host_table on their way to the device
     cudaEvent_t ev;
     RtcModule* rtc;             // kernels compiled at run time around a user-written functor (CPN_USER)
     bool user_flat_prior;
@@ -518,6 +519,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         dalloc(&c->d_rec, (size_t)N * (D + 2)) || dalloc(&c->d_sweeps, 1))
         return 1;
     CK(cudaMallocHost((void**)&c->h_state, sizeof(NSState)));
+    CK(cudaMallocHost((void**)&c->h_idx, 2 * (size_t)N * sizeof(int)));
     // DefaultProposalCycle weights 5:5:10:10 laid out deterministically until cpn_set_cycle is called
     {
         std::vector<uint8_t> cyc;
@@ -573,6 +575,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
         if (p) cudaFree(p);
     if (c->rtc) rtc_destroy(c->rtc);
     if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_idx) cudaFreeHost(c->h_idx);
     cudaEventDestroy(c->ev);
     cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_cov); cudaEventDestroy(c->ev_eig);
     cudaStreamDestroy(c->side);
@@ -1614,14 +1617,19 @@ extern "C" int cpn_evolve_host_table(cpn_ctx* c, int32_t K, double logLmin, int3
                     "torch.Tensor.pin_memory()); use cpn_evolve_host for pageable buffers");
     }
     double* d_table = (double*)at.devicePointer;
+    // checked and moved into pinned memory in one pass (the previous call has synchronised: the buffer is free)
+    int* h_start = c->h_idx;
+    int* h_slots = c->h_idx + c->N;
     for (int j = 0; j < K; ++j) {
         if (start_idx[j] < 0 || start_idx[j] >= c->N) return fail("cpn_evolve_host_table: start_idx[%d] = %d out of range", j, start_idx[j]);
         if (slots[j] < 0 || slots[j] >= c->N) return fail("cpn_evolve_host_table: slots[%d] = %d out of range", j, slots[j]);
+        h_start[j] = start_idx[j];
+        h_slots[j] = slots[j];
     }
     const int D = c->D, Dp = c->Dp, T = 256;
     int* d_idx = c->d_sort_idx;                         // scratch of the initial sort, free during a run
-    CK(cudaMemcpyAsync(d_idx, start_idx, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_idx, h_start, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_rank, h_slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     k_gather_table<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(d_table, d_idx, K, c->N, D, Dp, c->d_start_x, c->d_start_logL, c->d_start_logP);
     if (launch_chains(c, K, 0, K, START_GIVEN, 0, true, logLmin, std::max(1, std::min(nmcmc, c->cfg.maxmcmc)), 1)) return 1;
     for (int k = 0; k < kNumKinds; ++k) {
