@@ -239,7 +239,11 @@ class CPNest(object):
         """Posterior samples by rejection on the nested-sampling weights (cpnest/cpnest.py:343-406)."""
         from .nest2pos import draw_posterior_many
         nested_samples = self.get_nested_samples()      # writes nested_samples.dat, as the reference does
-        posterior_samples = np.array(draw_posterior_many([nested_samples], [self.nlive], verbose=self.verbose))
+        # weights from the integrator's own volume history: a batch of K removals shrinks the volume point by point with
+        # 1/(N-j), which the reference's reconstruction in compute_weights (one removal per iteration) does not describe
+        lv = getattr(self.NS.state, "log_vols", None)
+        lv = [np.asarray(lv)] if lv is not None and len(lv) == len(nested_samples) + 1 else None
+        posterior_samples = np.array(draw_posterior_many([nested_samples], [self.nlive], verbose=self.verbose, log_vols=lv))
         if self.prior_samples is None:
             self.prior_samples = {n: None for n in self.user.names}
         self.mcmc_samples = {n: None for n in self.user.names}

@@ -46,6 +46,23 @@ def compute_weights(data, Nlive):
     return log_ev, log_wts
 
 
+def compute_weights_from_volumes(log_likes, log_vols):
+    """(log_ev, log_wts) like compute_weights, for a run whose enclosed prior volumes are KNOWN: log_vols[0] = 0 belongs to
+    the dummy first sample, log_vols[i] to nested sample i (len(log_vols) == len(log_likes) + 1).
+
+    compute_weights (nest2pos.py:45-71) reconstructs the volumes assuming one replacement per iteration at constant
+    Nlive.  A device batch removes its K worst points before any replacement arrives, so the j-th of them shrinks the
+    volume by 1/(N-j) (the rule the reference itself applies in its final sweep, NestedSampling.py:474-476): over a run
+    the assumed and the true volumes drift apart by a factor ln(N/(N-K)) / (K/N) in the exponent, which would over-weight
+    the late, high-likelihood samples.  The integrator's own history (NS.state.log_vols) is the consistent choice."""
+    log_likes = np.asarray(log_likes, dtype=np.float64)
+    log_vols = np.asarray(log_vols, dtype=np.float64)
+    assert len(log_vols) == len(log_likes) + 1 and log_vols[0] == 0.0
+    log_ev = log_integrate_log_trap(np.concatenate(([-np.inf], log_likes)), log_vols)
+    log_dX = logsubexp(log_vols[:-1], log_vols[1:])
+    return log_ev, log_likes + log_dX - log_ev
+
+
 def draw_posterior(data, log_wts, verbose=False):
     """Rejection-sample rows of `data` with probability exp(log_wt - max) (nest2pos.py:73-81)."""
     log_wts = np.asarray(log_wts)
@@ -53,9 +70,13 @@ def draw_posterior(data, log_wts, verbose=False):
     return data[keep]
 
 
-def draw_posterior_many(datas, Nlives, verbose=False):
-    """Combine several runs, each weighted by its evidence (nest2pos.py:83-111)."""
-    pairs = [compute_weights(d["logL"], n) for d, n in zip(datas, Nlives)]
+def draw_posterior_many(datas, Nlives, verbose=False, log_vols=None):
+    """Combine several runs, each weighted by its evidence (nest2pos.py:83-111).  log_vols (not in the reference): per
+    run, the recorded log-volumes (compute_weights_from_volumes) or None for the reference's reconstruction."""
+    if log_vols is None:
+        log_vols = [None] * len(datas)
+    pairs = [compute_weights(d["logL"], n) if lv is None else compute_weights_from_volumes(d["logL"], lv)
+             for d, n, lv in zip(datas, Nlives, log_vols)]
     log_evs = [p[0] for p in pairs]
     LOGGER.critical("Computed log_evidences: {0!s}".format(str(tuple(log_evs))))
     top = max(log_evs)

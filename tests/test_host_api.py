@@ -84,6 +84,41 @@ def test_host_row_helpers_match_numpy_indexing():
         assert np.array_equal(table, before)                                            # nothing written on failure
 
 
+def test_weights_from_recorded_volumes():
+    """compute_weights_from_volumes: identical to compute_weights when fed the volumes compute_weights assumes; with the
+    volumes of batched removals (K of N per iteration, 1/(N-j) per point) the evidence of a known integrand comes out
+    right where the constant-N reconstruction is off."""
+    from cpnest_b200 import nest2pos as n2p
+    rs = np.random.RandomState(2)
+    N, ndead = 50, 400
+    logL = np.sort(rs.normal(size=ndead + N))
+    ev0, w0 = n2p.compute_weights(logL, N)
+    step = np.log1p(-1.0 / N)
+    # the volumes compute_weights assumes (nest2pos.py:52-60): dummy + ndead constant steps, then the final live points
+    v0 = step * (ndead + 2)
+    vols = np.concatenate((step * np.arange(ndead + 2), [v0], v0 + np.cumsum(np.log1p(-1.0 / (N - np.arange(N - 1))))))[:-1]
+    ev1, w1 = n2p.compute_weights_from_volumes(logL, vols)
+    assert np.allclose(w1 + ev1, w0 + ev0, rtol=0, atol=1e-12)          # same L_i dX_i
+    assert abs(ev1 - ev0) < 5e-3                                         # the reference adds one closing trapezoid
+    # batched removals: L(X) = exp(-X / 0.01) on the unit prior volume, Z = 0.01 (1 - e^-100)
+    N, K, nb = 1000, 500, 40
+    X, x = [], 1.0
+    rs = np.random.RandomState(3)
+    for b in range(nb):
+        for j in range(K):
+            x *= rs.beta(N - j, 1)                                      # largest of N - j uniforms on (0, x)
+            X.append(x)
+    X = np.array(X)
+    logL = -X / 0.01
+    true_vols = np.concatenate(([0.0], np.cumsum(np.tile(-1.0 / (N - np.arange(K)), nb))))
+    ev, w = n2p.compute_weights_from_volumes(logL, true_vols)
+    assert abs(ev - np.log(0.01)) < 0.15                                 # sigma = sqrt(H / N) ~ 0.06 (x the batch factor)
+    naive_vols = np.concatenate(([0.0], -np.arange(1, nb * K + 1) / N))
+    ev_naive, _ = n2p.compute_weights_from_volumes(logL, naive_vols)
+    assert ev_naive - np.log(0.01) > 0.5                                 # constant-N volumes shrink too slowly
+    assert abs(np.logaddexp.reduce(w)) < 0.05                            # normalised weights
+
+
 def test_no_cpu_fallback_fails_loudly():
     import torch
     if torch.cuda.is_available():
