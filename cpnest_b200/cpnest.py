@@ -160,6 +160,13 @@ class CPNest(object):
                 self._resume()                                  # cpnest/cpnest.py:181-183
             else:
                 eng.init_prior()
+                if self.verbose >= 3 and not self.prior_sampling:
+                    # cpnest/sampler.py:137-152: at verbose >= 3 every sampler saves samples of the prior,
+                    # prior_samples_<pid>.dat; here the initial live set IS nlive draws from the prior
+                    ps = LivePointList(self.user.names, eng.live()).asnparray()
+                    fn = "prior_samples_%d.dat" % os.getpid()
+                    np.savetxt(os.path.join(self.output, fn), ps.ravel(), header=" ".join(ps.dtype.names), newline="\n", delimiter=" ")
+                    self.logger.critical("Sampler process {0!s}: saved {1:d} prior samples in {2!s}".format(os.getpid(), len(ps), fn))
             NS.initialised = True
             if self.resume:                                     # cpnest/cpnest.py:271-277
                 for sig in (signal.SIGTERM, signal.SIGALRM, signal.SIGQUIT, signal.SIGINT, signal.SIGUSR1, signal.SIGUSR2):
@@ -220,6 +227,9 @@ class CPNest(object):
                 NS.check_insertion_indices(rolling=False, filename=None)
                 self.nested_samples = self.get_nested_samples(filename=None)
                 self.posterior_samples = self.get_posterior_samples(filename=None)
+            if self.verbose >= 3:                                # cpnest/cpnest.py:309-312
+                self.prior_samples = self.get_prior_samples(filename=None)
+                self.mcmc_samples = self.get_mcmc_samples(filename=None)
             if self.verbose >= 2:
                 try:
                     self.plot(corner=False)
@@ -253,11 +263,20 @@ class CPNest(object):
         return posterior_samples
 
     def get_prior_samples(self, filename="prior.dat"):
-        """cpnest/cpnest.py:408-443: with prior_sampling the nested samples are the prior samples."""
-        if not self.NS.prior_sampling:
+        """cpnest/cpnest.py:408-443: the prior_samples_*.dat files written at verbose >= 3 (read and removed, as the
+        reference does), and with prior_sampling the nested samples."""
+        from numpy.lib.recfunctions import stack_arrays
+        parts = []
+        for f in sorted(os.listdir(self.NS.output_folder)):
+            if "prior_samples" in f:
+                parts.append(np.atleast_1d(np.genfromtxt(os.path.join(self.NS.output_folder, f), names=True)))
+                os.remove(os.path.join(self.NS.output_folder, f))
+        if self.NS.prior_sampling:
+            parts.append(self.get_nested_samples(filename=None))
+        if not parts:
             self.logger.critical("ERROR, no prior samples found!")
             return None
-        prior_samples = self.get_nested_samples(filename=None)
+        prior_samples = parts[0] if len(parts) == 1 else stack_arrays(parts, usemask=False)
         if filename:
             np.savetxt(os.path.join(self.NS.output_folder, filename), prior_samples.ravel(),
                        header=" ".join(prior_samples.dtype.names), newline="\n", delimiter=" ")

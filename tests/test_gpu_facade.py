@@ -78,6 +78,14 @@ def test_verbosity_levels_and_mean_sigma_model(tmp_path):
         out = str(tmp_path / ("v%d" % v))
         assert os.path.exists(os.path.join(out, "posterior.dat")) == (v >= 2)
         assert os.path.exists(os.path.join(out, "insertion_indices.dat")) == (v >= 2)
+        if v >= 3:
+            # cpnest/sampler.py:137-152 + cpnest/cpnest.py:309-310: prior samples are saved by the samplers, then read
+            # back (and the per-process files removed) by get_prior_samples
+            ps = w.prior_samples
+            assert ps.dtype.names == ("mean", "sigma", "logL", "logPrior") and len(ps) == 100
+            assert not [f for f in os.listdir(out) if f.startswith("prior_samples")]
+            assert np.all((ps["sigma"] > 0.05) & (ps["sigma"] < 1.0)) and np.allclose(ps["logPrior"], -np.log(ps["sigma"]) - np.log(9.5))
+            assert w.mcmc_samples is None                  # no per-step chain history exists on the device
 
 
 def test_prior_sampling(tmp_path):
