@@ -1,6 +1,7 @@
 """Pin oracle/cpnest_oracle.py against the fixtures generated from the unmodified
 reference (tests/golden/gen_golden.py).  CPU only."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -281,3 +282,25 @@ def test_philox_known_answers():
     assert O.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert O.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_recorded_reference_runs_are_sane():
+    """tests/golden/ref_runs.json (complete runs of the unmodified reference, tests/golden/gen_ref_runs.py) against what is
+    known analytically about its models: the fixture the GPU runs are compared with is itself checked."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_runs.json")) as f:
+        runs = {r["name"]: r for r in json.load(f)}
+    assert set(runs) == {"gaussian2d_mh", "ring_mh", "gaussian_mean_sigma_mh", "gaussian2d_slice"}
+    anchors = {"gaussian2d_mh": -2 * math.log(20.0), "gaussian2d_slice": -2 * math.log(20.0), "ring_mh": -2.318358,
+               # normalised 1/sigma prior on [0.05, 1] x uniform mean on [-5, 5]: Z = 1/10 up to the tails beyond |mean| = 5
+               "gaussian_mean_sigma_mh": -math.log(10.0)}
+    for name, r in runs.items():
+        sigma = math.sqrt(r["info"] / r["kwargs"]["nlive"])
+        assert abs(r["logZ"] - anchors[name]) < 3.0 * sigma, (name, r["logZ"], anchors[name], sigma)
+        assert r["n_posterior"] > 1500 and all(len(v) == 1500 for v in r["posterior"].values())
+    g = runs["gaussian2d_mh"]
+    assert all(abs(g["posterior_mean"][n]) < 0.1 and abs(g["posterior_var"][n] - 1.0) < 0.1 for n in ("x", "y"))
+    ms = runs["gaussian_mean_sigma_mh"]
+    # p(sigma) ~ 1/sigma: E[sigma] = 0.95 / ln 20, Var(mean) = E[sigma^2] = (1 - 0.05^2) / (2 ln 20)
+    assert abs(ms["posterior_mean"]["sigma"] - 0.95 / math.log(20.0)) < 0.02
+    assert abs(ms["posterior_var"]["mean"] - (1 - 0.0025) / (2 * math.log(20.0))) < 0.02
