@@ -139,8 +139,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "gaussian50d_iid_bounds[-10,10]_mh_default_cycle", "dim": DIM,
-                   "step": "bounded sample: %d forked sampler processes x %.1f s of yield_sample" % (cores, per_step_s)},
+        # the workload of the GPU arm (same model, sampler and proposal cycle); the reference's sampler processes evolve
+        # one chain each from a pool of 1000 points, so nlive / K enter only through the sample described in `step`
+        "config": {"workload": "gaussian50d_iid_bounds[-10,10]_nlive%d_per_gpu_K%d_mh_default_cycle" % (args.nlive, args.k), "dim": DIM,
+                   "step": "bounded sample: %d forked sampler processes x %.1f s of yield_sample (poolsize 1000, Nmcmc 100)" % (cores, per_step_s)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": res[-1]["kind"], "sample": res[-1]["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "steps_per_s": float(np.mean([r["steps_per_s"] for r in res])),
