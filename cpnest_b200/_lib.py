@@ -81,6 +81,7 @@ SIGNATURES = {
     "cpn_set_staging": (C.c_int, [_vp, _P(_vp), C.c_int32]),
     "cpn_shard_record_doubles": (C.c_int64, [_vp]),
     "cpn_shard_range": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, _ip]),
+    "cpn_kind_ranges": (C.c_int, [_ip, C.c_int32, _ip]),
     "cpn_pack_shard": (C.c_int, [_vp, C.c_int32, _vp]),
     "cpn_unpack_shards": (C.c_int, [_vp, C.c_int32, _vp]),
     "cpn_ns_step": (C.c_int, [_vp, C.c_int32]),

@@ -137,25 +137,29 @@ static inline cudaStream_t chain_stream(cpn_ctx* c) { return c->chain_stream ? c
 // The K chains of a batch by sampler kind: kind s owns [kb[s], kb[s+1]).  Largest-remainder split of K in the
 // proportions c->mix, at least one chain for every kind present (the reference gives every sampler process one
 // of the nthreads worst points per iteration, cpnest/NestedSampling.py:324-342).
-static int kind_ranges(cpn_ctx* c, int K, int* kb) {
+static int split_by_kind(const int* mix, int K, int* kb) {
     long long W = 0;
     int active = 0;
-    for (int s = 0; s < kNumKinds; ++s) { W += c->mix[s]; active += c->mix[s] > 0; }
+    for (int s = 0; s < kNumKinds; ++s) {
+        if (mix[s] < 0) return fail("mix[%d] = %d must be >= 0", s, mix[s]);
+        W += mix[s]; active += mix[s] > 0;
+    }
+    if (active == 0) return fail("mix must not be all zero");
     if (K < active) return fail("K=%d chains cannot hold %d sampler kinds", K, active);
     int n[kNumKinds];
     long long rem[kNumKinds];
     int used = 0;
     for (int s = 0; s < kNumKinds; ++s) {
-        const long long q = (long long)K * c->mix[s];
+        const long long q = (long long)K * mix[s];
         n[s] = (int)(q / W);
         rem[s] = q % W;
-        if (c->mix[s] > 0 && n[s] == 0) { n[s] = 1; rem[s] = 0; }
+        if (mix[s] > 0 && n[s] == 0) { n[s] = 1; rem[s] = 0; }
         used += n[s];
     }
     while (used < K) {          // hand out what the floors left, largest remainder first (ties: lower kind)
         int best = -1;
         for (int s = 0; s < kNumKinds; ++s)
-            if (c->mix[s] > 0 && (best < 0 || rem[s] > rem[best])) best = s;
+            if (mix[s] > 0 && (best < 0 || rem[s] > rem[best])) best = s;
         n[best] += 1; rem[best] -= W; used += 1;
     }
     while (used > K) {          // the minimum of one chain per kind overshot: take from the largest
@@ -166,6 +170,12 @@ static int kind_ranges(cpn_ctx* c, int K, int* kb) {
     kb[0] = 0;
     for (int s = 0; s < kNumKinds; ++s) kb[s + 1] = kb[s] + n[s];
     return 0;
+}
+static int kind_ranges(cpn_ctx* c, int K, int* kb) { return split_by_kind(c->mix, K, kb); }
+extern "C" int cpn_kind_ranges(const int32_t* mix, int32_t K, int32_t* kb) {
+    if (!mix || !kb) return fail("null argument");
+    if (K < 1) return fail("K=%d must be >= 1", K);
+    return split_by_kind(mix, K, kb);
 }
 
 // Host -> device copy that has LANDED when it returns.  cudaMemcpy from pageable memory may return once the data is

@@ -240,6 +240,15 @@ class Engine:
         return steps, accepted
 
     @staticmethod
+    def kind_ranges(mix, K):
+        """Chain ranges [kb[s], kb[s+1]) of the sampler kinds (mh, slice, hmc) in a batch of K chains (cpn_kind_ranges)."""
+        m = np.ascontiguousarray(mix, dtype=np.int32)
+        assert m.shape == (3,)
+        kb = np.zeros(4, dtype=np.int32)
+        L.check(L.load().cpn_kind_ranges(L.iptr(m), int(K), L.iptr(kb)))
+        return kb.tolist()
+
+    @staticmethod
     def host_gather_rows(table, idx, out):
         """out[j] = table[idx[j]] for C-contiguous float64 tables (cpn_host_gather_rows)."""
         idx = np.ascontiguousarray(idx, dtype=np.int64)

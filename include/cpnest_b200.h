@@ -172,6 +172,11 @@ int64_t cpn_staging_bytes(cpn_ctx* ctx);   /* size of one peer block (two halves
 int cpn_set_staging(cpn_ctx* ctx, void* const* peer_blocks /*device addresses, [world]*/, int32_t npeers);
 int64_t cpn_shard_record_doubles(cpn_ctx* ctx);
 int cpn_shard_range(cpn_ctx* ctx, int32_t K, int32_t rank, int32_t* j0, int32_t* j1);
+/* Which chains of a batch run which sampler kind (cpn_config.mix; pure host function, no context): kind s owns the chains
+ * [kb[s], kb[s+1]) of [0, K), kb has 4 entries.  Largest-remainder split of K in the proportions mix[0] : mix[1] : mix[2],
+ * at least one chain for every kind present - the device form of "each of the nthreads sampler processes gets one of the
+ * worst points per iteration" (cpnest/NestedSampling.py:324-342, cpnest/cpnest.py:197-261).  Independent of the number of GPUs. */
+int cpn_kind_ranges(const int32_t* mix, int32_t K, int32_t* kb);
 int cpn_pack_shard(cpn_ctx* ctx, int32_t K, void* dev_send);
 int cpn_unpack_shards(cpn_ctx* ctx, int32_t K, const void* dev_recv);
 /* One consume_sample() = the three calls above (+ ensemble refresh on the sampler's cadence,

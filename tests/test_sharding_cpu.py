@@ -25,6 +25,38 @@ def test_shard_ranges_partition_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_kind_ranges_split_a_batch_and_compose_with_the_shards():
+    """cpn_kind_ranges (host-only ABI function): the chains of a batch by sampler kind - exact partition of [0, K), every kind
+    present gets a chain, shares within one chain of the requested proportions - and, composed with the rank slices, every
+    chain of the batch is evolved exactly once by exactly one (rank, kind) launch whatever the number of GPUs."""
+    from cpnest_b200._lib import CpnError
+    from cpnest_b200.engine import Engine
+    for mix in ((1, 0, 0), (0, 1, 0), (2, 1, 1), (1, 1, 1), (5, 0, 3), (1000, 1, 1), (1, 7, 0)):
+        active = sum(m > 0 for m in mix)
+        for K in (active, active + 1, 7, 64, 250, 4704, 37632):
+            kb = Engine.kind_ranges(mix, K)
+            assert kb[0] == 0 and kb[3] == K and all(a <= b for a, b in zip(kb[:-1], kb[1:]))
+            n = np.diff(kb)
+            for s in range(3):
+                assert (n[s] > 0) == (mix[s] > 0)
+                if K >= 20 * active and mix[s] > 0 and min(m for m in mix if m > 0) * K >= sum(mix):
+                    assert abs(n[s] - K * mix[s] / sum(mix)) <= 1.0 + 1e-9, (mix, K, n)
+            for world in (1, 2, 4, 8):
+                owner = np.zeros(K, dtype=int)
+                for r in range(world):
+                    j0, j1 = shard_range(K, r, world)
+                    for s in range(3):
+                        a, b = max(j0, kb[s]), min(j1, kb[s + 1])
+                        if b > a:
+                            owner[a:b] += 1
+                assert np.all(owner == 1), (mix, K, world)
+    assert Engine.kind_ranges((2, 1, 1), 100) == [0, 50, 75, 100]
+    assert Engine.kind_ranges((1, 1, 0), 7) == [0, 4, 7, 7]
+    for bad_mix, K in (((0, 0, 0), 10), ((1, -1, 0), 10), ((1, 1, 1), 2)):
+        with pytest.raises(CpnError):
+            Engine.kind_ranges(bad_mix, K)
+
+
 S_EXTRA = 5      # cpn_shard_record_doubles() - Dp
 
 
