@@ -387,7 +387,7 @@ def main():
         logLmin = logL[part[K - 1]]                     # the K-th smallest sits at position K-1 of a partition: max of the K worst
         starts = surv[rs.integers(0, N - K, size=K, dtype=np.int32)]     # requests: start points drawn among the survivors
         # request j = row starts[j] of the host table, reply j -> row worst[j]: the device reads and writes the pinned table
-        eng.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_)
+        eng.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_, rows_async=True)
 
     for _ in range(args.warmup):
         host_step()
@@ -396,6 +396,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         host_step()
+    eng.synchronize()                                   # the last step's rows have landed in the host table
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_evals = eng.state()["total_evals"] - ev_before
@@ -433,7 +434,7 @@ def main():
             "accepted_chain_steps_per_s": accepted / (dt_ms * 1e-3),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "cpn_evolve_host_table (sampler pipe protocol over the caller's pinned host live table: the device reads the K request rows from it and writes the K replies into it; selection of the worst points on the host)",
+                    "api": "cpn_evolve_host_table (sampler pipe protocol over the caller's pinned host live table: the device reads the K request rows from it and writes the K replies into it; selection of the worst points on the host while the coordinates of the previous replies are still landing)",
                     "chain_length": nm},
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -101,7 +101,7 @@ SIGNATURES = {
     "cpn_get_insertion_indices": (C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
     "cpn_get_last_batch": (C.c_int, [_vp, C.c_int32, _dp, _ip, _ip]),
     "cpn_evolve_host": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
-    "cpn_evolve_host_table": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "cpn_evolve_host_table": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32]),
     "cpn_host_gather_rows": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp]),
     "cpn_host_scatter_rows": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp]),
     "cpn_set_stream": (C.c_int, [_vp, _vp]),

@@ -1604,18 +1604,21 @@ __global__ void k_gather_table(const double* __restrict__ table, const int* __re
     x[i] = (d < D) ? row[d] : 0.0;
     if (d == 0) { logL[j] = row[D]; logP[j] = row[D + 1]; }
 }
-__global__ void k_scatter_table(double* __restrict__ table, const int* __restrict__ slots, int K, int N, int D, int Dp,
+// columns [d0, d1) of the K reply records into rows slots[j] of the host table
+__global__ void k_scatter_table(double* __restrict__ table, const int* __restrict__ slots, int K, int N, int D, int Dp, int d0, int d1,
                                 const double* __restrict__ x, const double* __restrict__ logL, const double* __restrict__ logP) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * (D + 2)) return;
-    const int j = i / (D + 2), d = i % (D + 2);
+    const int w = d1 - d0;
+    if (i >= K * w) return;
+    const int j = i / w, d = d0 + i % w;
     const int r = slots[j];
     if (r < 0 || r >= N) return;
     table[(size_t)r * (D + 2) + d] = (d < D) ? x[(size_t)j * Dp + d] : (d == D ? logL[j] : logP[j]);
 }
 
 extern "C" int cpn_evolve_host_table(cpn_ctx* c, int32_t K, double logLmin, int32_t nmcmc, double* table,
-                                     const int32_t* start_idx, const int32_t* slots, int32_t* steps, int32_t* accepted) {
+                                     const int32_t* start_idx, const int32_t* slots, int32_t* steps, int32_t* accepted,
+                                     int32_t flags) {
     if (!c || !table || !start_idx || !slots) return fail("null argument");
     if (!c->live_ready) return fail("live set not initialised");
     if (K < 1 || K > c->N) return fail("K=%d must be in [1, nlive]", K);
@@ -1652,13 +1655,18 @@ extern "C" int cpn_evolve_host_table(cpn_ctx* c, int32_t K, double logLmin, int3
     }
     k_pool_append<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rank, K, c->N, Dp, c->d_new_x, c->d_new_logL, c->d_new_logP,
                                                           c->d_x, c->d_logL, c->d_logP);
-    k_scatter_table<<<(K * (D + 2) + T - 1) / T, T, 0, c->stream>>>(d_table, c->d_rank, K, c->N, D, Dp, c->d_new_x, c->d_new_logL,
-                                                                  c->d_new_logP);
-    CKL();
-    c->launches += 3;
+    // the keys first (logL, logP: what the caller's next selection reads), then the coordinates
+    k_scatter_table<<<(K * 2 + T - 1) / T, T, 0, c->stream>>>(d_table, c->d_rank, K, c->N, D, Dp, D, D + 2, c->d_new_x, c->d_new_logL,
+                                                             c->d_new_logP);
     if (steps) CK(cudaMemcpyAsync(steps, c->d_new_steps, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (accepted) CK(cudaMemcpyAsync(accepted, c->d_new_acc, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->ev, c->stream));
+    k_scatter_table<<<(K * D + T - 1) / T, T, 0, c->stream>>>(d_table, c->d_rank, K, c->N, D, Dp, 0, D, c->d_new_x, c->d_new_logL,
+                                                             c->d_new_logP);
+    CKL();
+    c->launches += 4;
+    if (flags & CPN_TABLE_ROWS_ASYNC) CK(cudaEventSynchronize(c->ev));     // the rows land while the caller selects
+    else CK(cudaStreamSynchronize(c->stream));
     c->chain_counter += (unsigned long long)K;
     c->batches_enqueued += 1;
     return 0;

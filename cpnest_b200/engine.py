@@ -222,10 +222,12 @@ class Engine:
                                          replies.ctypes.data, steps.ctypes.data, accepted.ctypes.data))
         return replies, steps, accepted
 
-    def evolve_host_table(self, table, start_idx, slots, logLmin, nmcmc, steps=None, accepted=None):
+    def evolve_host_table(self, table, start_idx, slots, logLmin, nmcmc, steps=None, accepted=None, rows_async=False):
         """The pipe protocol over the caller's pinned host live table (cpn_evolve_host_table): request j is row
         table[start_idx[j]], reply j lands in row table[slots[j]].  `table` is the .numpy() view of a pinned torch tensor
-        (or any cudaHostRegister'ed C-contiguous float64 array) of shape [nlive][D+2]."""
+        (or any cudaHostRegister'ed C-contiguous float64 array) of shape [nlive][D+2].  rows_async: return once the
+        logL / logPrior columns and steps / accepted are final; the coordinates of the replaced rows are complete after
+        the next call on this engine or synchronize() (CPN_TABLE_ROWS_ASYNC)."""
         K = len(start_idx)
         assert table.flags.c_contiguous and table.dtype == np.float64 and table.shape == (self.nlive, self.dim + 2)
         start_idx = np.ascontiguousarray(start_idx, dtype=np.int32)
@@ -236,7 +238,7 @@ class Engine:
         if accepted is None:
             accepted = np.empty(K, dtype=np.int32)
         L.check(self.lib.cpn_evolve_host_table(self.h, K, float(logLmin), int(nmcmc), table.ctypes.data, start_idx.ctypes.data,
-                                               slots.ctypes.data, steps.ctypes.data, accepted.ctypes.data))
+                                               slots.ctypes.data, steps.ctypes.data, accepted.ctypes.data, 1 if rows_async else 0))
         return steps, accepted
 
     @staticmethod

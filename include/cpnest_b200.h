@@ -230,9 +230,13 @@ int cpn_evolve_host(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc,
  * (cudaHostAlloc / cudaHostRegister memory, e.g. a torch tensor after .pin_memory()).  Request j is the row
  * table[start_idx[j]]; the device reads those rows from host memory itself, evolves them, and writes reply j into
  * row table[slots[j]] (and into pool slot slots[j] of the device ensemble).  start_idx / slots are host int32[K].
- * When the call returns the table holds the replies.  Same bytes over the bus as cpn_evolve_host, no CPU gather/scatter. */
+ * When the call returns the table holds the replies.  Same bytes over the bus as cpn_evolve_host, no CPU gather/scatter.
+ * flags: CPN_TABLE_ROWS_ASYNC - return as soon as the logL / logP columns of the replaced rows (all the caller needs to pick the
+ * next worst points, NestedSampling.py:368-375) and steps / accepted are in host memory; the coordinate columns of those rows
+ * keep arriving while the caller works and are complete after the next call on this context or cpn_synchronize(). */
+enum cpn_table_flags { CPN_TABLE_ROWS_ASYNC = 1 };
 int cpn_evolve_host_table(cpn_ctx* ctx, int32_t K, double logLmin, int32_t nmcmc, double* table,
-                          const int32_t* start_idx, const int32_t* slots, int32_t* steps, int32_t* accepted);
+                          const int32_t* start_idx, const int32_t* slots, int32_t* steps, int32_t* accepted, int32_t flags);
 /* Host-side row moves of a caller that keeps the live set in host memory as one table[nrows][row_doubles] (the
  * NestedSampler side of the protocol: `self.params[k]` handed to the pipes and replaced by the replies,
  * cpnest/NestedSampling.py:324-366): out[j] = table[idx[j]] and table[idx[j]] = rows[j].  Plain memcpy loops (numpy's

@@ -27,7 +27,7 @@ for i in range(n + 5):
     t1 = time.perf_counter()
     starts = surv[rs.integers(0, N - K, size=K, dtype=np.int32)]
     t2 = time.perf_counter()
-    e.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_)
+    e.evolve_host_table(live, starts, worst, logLmin, nm, steps=stp, accepted=acc_, rows_async=True)
     t3 = time.perf_counter()
     if i >= 5:
         T += [t1 - t0, t2 - t1, t3 - t2]

@@ -54,7 +54,7 @@ table = table_t.numpy()
 e.set_live(table)
 for _ in range(3):
     part = np.argpartition(table[:, D], K - 1).astype(np.int32)
-    e.evolve_host_table(table, part[K:][:K], part[:K], table[part[K - 1], D], 20)
+    e.evolve_host_table(table, part[K:][:K], part[:K], table[part[K - 1], D], 20, rows_async=True)
 req = np.ascontiguousarray(table[:K])
 e.evolve_host(req, float(table[:, D].min()), 20, slots=np.arange(K, dtype=np.int32))
 print("host protocols ok", flush=True)

@@ -107,7 +107,7 @@ def test_host_table_protocol_equals_the_buffer_protocol():
     table_t = torch.from_numpy(live_b.copy()).pin_memory()
     table = table_t.numpy()
     with a, b:
-        for it in range(3):
+        for it in range(4):
             logL = live_a[:, D]
             part = np.argpartition(logL, K - 1)
             worst, surv = part[:K], part[K:]
@@ -116,7 +116,10 @@ def test_host_table_protocol_equals_the_buffer_protocol():
             req = np.ascontiguousarray(live_a[starts])
             rep, st_a, ac_a = a.evolve_host(req, logLmin, 30, slots=worst.astype(np.int32))
             live_a[worst] = rep
-            st_b, ac_b = b.evolve_host_table(table, starts, worst, logLmin, 30)
+            st_b, ac_b = b.evolve_host_table(table, starts, worst, logLmin, 30, rows_async=(it % 2 == 1))
+            # CPN_TABLE_ROWS_ASYNC: keys and counters are final at return, the coordinates after a synchronize
+            assert np.array_equal(table[:, D:], live_a[:, D:]), it
+            b.synchronize()
             assert np.array_equal(table, live_a), it
             assert np.array_equal(st_a, st_b) and np.array_equal(ac_a, ac_b)
             assert np.all(table[worst, D] > logLmin)
