@@ -92,6 +92,7 @@ class CPNest(object):
             self.nlive = nlive
             self.poolsize = poolsize
             self.posterior_samples = None
+            self.logZ_error = None
             self.nested_samples = None
             self.prior_samples = None
             self.mcmc_samples = None
@@ -216,6 +217,14 @@ class CPNest(object):
             NS.write_evidence_to_file()
             self.logger.critical("Final evidence: {0:0.2f}".format(NS.state.logZ))
             self.logger.critical("Information: {0:.2f}".format(NS.state.info))
+            # sqrt(H / nlive) is the error of a run that replaces one point per iteration; a batch removes its K worst points
+            # before any replacement arrives, which inflates the variance of the log-volume per unit of shrinkage by
+            # (1/(1-f) - 1) / (-ln(1-f)), f = K / nlive (profiles/r01_logz_validation.txt)
+            f = min(K / float(self.nlive), 0.999)
+            infl = (1.0 / (1.0 - f) - 1.0) / -np.log1p(-f)
+            self.logZ_error = float(np.sqrt(max(NS.state.info, 0.0) / self.nlive * infl))
+            self.logger.critical("Estimated error of the evidence: {0:.3f} (sqrt(H/nlive) = {1:.3f}, batches of {2:d})".format(
+                self.logZ_error, float(np.sqrt(max(NS.state.info, 0.0) / self.nlive)), K))
             self.logger.critical("Sampling time: {0:.2f} s, {1:d} likelihood evaluations".format(time.time() - t0, s["total_evals"]))
             if self.verbose >= 2:
                 NS.check_insertion_indices(rolling=False, filename="insertion_indices.dat")

@@ -24,6 +24,8 @@ def test_2d_gaussian_like_reference_test(tmp_path):
     # the reference asserts 2 sigma (tests/test_2d.py:37-38); BASELINE.json asks for 3 sigma
     tolerance = 3.0 * np.sqrt(work.NS.state.info / work.NS.Nlive)
     assert np.abs(work.NS.logZ - model.analytic_log_Z) < tolerance
+    # error estimate that knows about the batch size: nthreads=1, nlive=1000 -> batches of 250, inflation sqrt(1.159)
+    assert abs(work.logZ_error / np.sqrt(work.NS.state.info / 1000) - np.sqrt((1 / 0.75 - 1) / -np.log(0.75))) < 1e-9
     # attribute surface used by the reference's tests and users
     assert work.NS.Nlive == 1000 and work.NS.iteration == len(work.NS.nested_samples)
     assert len(work.NS.insertion_indices) == work.NS.iteration - 1000
