@@ -110,6 +110,8 @@ SIGNATURES = {
     "cpn_eval_gradients": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "cpn_replay_mh": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32,
                                 C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _dp]),
+    "cpn_trace_mh": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                               C.c_int32, C.c_uint64, _dp, _ip, _ip, _ip, _dp]),
     "cpn_replay_slice": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, C.c_int32, _dp, _P(C.c_int64), C.c_double,
                                    C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _ip, _dp]),
     "cpn_replay_hmc": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.c_double, _dp, _P(C.c_int64), C.c_double, C.c_int32, C.c_int32,

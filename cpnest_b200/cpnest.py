@@ -183,24 +183,31 @@ class CPNest(object):
                 self.nested_samples = self.get_nested_samples(filename=None)
                 self.prior_samples = self.get_prior_samples(filename=None)
                 return
-            while True:
-                try:
+            # a signal (CheckPoint, raised by sighandler) may arrive anywhere in the loop body, also inside the periodic
+            # checkpoint or while the state is read back: the whole loop and the final sweep sit inside the handler, which
+            # writes the resume file from the device state as it is and exits with 130 (cpnest/cpnest.py:286-288)
+            try:
+                while True:
                     eng.run(K, max_batches=max(1, self.nlive // K), tolerance=NS.tolerance)
                     s = eng.state()
-                except CheckPoint:                              # cpnest/cpnest.py:286-288
-                    self.checkpoint()
-                    sys.exit(130)
-                if time.time() - last_checkpoint > self.periodic_checkpoint_interval:      # NestedSampling.py:453-455
-                    self.checkpoint()
-                    last_checkpoint = time.time()
-                NS.update_from(s)
-                if self.verbose:
-                    acc = s["total_accepted"] / max(1, s["total_steps"])
-                    self.logger.info("{0:d}: n:{1:4d} acc:{2:.3f} H: {3:.2f} logLmin {4:.5f} dZ: {5:.3f} logZ: {6:.3f} logLmax: {7:.2f}".format(
-                        s["iteration"], s["nmcmc"], acc, s["info"], s["logLmin"], s["condition"], s["logZ"], s["logLmax"]))
-                if not (s["condition"] > NS.tolerance) or s["done"]:
-                    break
-            NS.insertion_indices = eng.insertion_indices()
+                    if time.time() - last_checkpoint > self.periodic_checkpoint_interval:      # NestedSampling.py:453-455
+                        self.checkpoint()
+                        last_checkpoint = time.time()
+                    NS.update_from(s)
+                    if self.verbose:
+                        acc = s["total_accepted"] / max(1, s["total_steps"])
+                        self.logger.info("{0:d}: n:{1:4d} acc:{2:.3f} H: {3:.2f} logLmin {4:.5f} dZ: {5:.3f} logZ: {6:.3f} logLmax: {7:.2f}".format(
+                            s["iteration"], s["nmcmc"], acc, s["info"], s["logLmin"], s["condition"], s["logZ"], s["logLmax"]))
+                    if not (s["condition"] > NS.tolerance) or s["done"]:
+                        break
+                NS.insertion_indices = eng.insertion_indices()
+            except CheckPoint:
+                self.checkpoint()
+                sys.exit(130)
+            # from here on the live set is consumed (final sweep): a signal can no longer be answered with a checkpoint
+            if self.resume:
+                for sig in (signal.SIGTERM, signal.SIGALRM, signal.SIGQUIT, signal.SIGINT, signal.SIGUSR1, signal.SIGUSR2):
+                    signal.signal(sig, signal.SIG_DFL)
             rect, trap = eng.finalise()
             s = eng.state()
             NS.update_from(s)
@@ -215,6 +222,8 @@ class CPNest(object):
             self.total_steps = s["total_steps"]
             NS.write_chain_to_file()
             NS.write_evidence_to_file()
+            if os.path.exists(self.resume_file):                 # a finished run leaves no resume file (NestedSampling.py:490-492)
+                os.remove(self.resume_file)
             self.logger.critical("Final evidence: {0:0.2f}".format(NS.state.logZ))
             self.logger.critical("Information: {0:.2f}".format(NS.state.info))
             # sqrt(H / nlive) is the error of a run that replaces one point per iteration; a batch removes its K worst points

@@ -100,6 +100,7 @@ struct cpn_ctx {
     cudaEvent_t ev_thr, ev_acc, ev_ins, ev_corr;
     bool acc_pending;           // an accumulation is in flight that the main stream has not waited for yet
     uint8_t* d_cycle;
+    uint8_t h_cycle[4096];      // host copy: cycles up to kCycInline slots travel in the launch parameters of the MH kernel
     int cycle_len;
     uint8_t* d_slice_cycle;     // EnsembleSliceProposalCycle
     int slice_cycle_len;
@@ -414,6 +415,9 @@ extern "C" int cpn_set_staging(cpn_ctx* c, void* const* peers, int32_t npeers) {
     return 0;
 }
 
+static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, const double* hi, const void* blob, size_t blob_bytes,
+                       size_t nb);
+
 extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double* hi, const void* blob,
                           size_t blob_bytes, cpn_ctx** out) {
     if (!cfg || !lo || !hi || !out) return fail("cpn_create: null argument");
@@ -448,6 +452,19 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     cpn_ctx* c = new cpn_ctx();
     memset(c, 0, sizeof *c);
     c->cfg = *cfg;
+    // every failure below leaves through one place that releases what has been allocated so far
+    if (create_impl(c, cfg, lo, hi, blob, blob_bytes, nb)) {
+        const std::string keep = g_err;
+        cpn_destroy(c);
+        g_err = keep;
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, const double* hi, const void* blob, size_t blob_bytes,
+                       size_t nb) {
     c->D = cfg->dim;
     c->Dp = (cfg->dim + 3) & ~3;
     // Row padding.  When the rows are zero-padded up to G*E doubles, every slot a lane group gathers lies inside its own
@@ -473,7 +490,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
             for (int k = kNumKinds - 1; k >= 0; --k) if (c->mix[k] > 0) c->primary = k;
         c->cfg.sampler = c->primary;
     }
-    if (pick_config(c->D, cfg->lanes, cfg->functor, c->N, &c->G, &c->E)) { delete c; return 1; }
+    if (pick_config(c->D, cfg->lanes, cfg->functor, c->N, &c->G, &c->E)) return 1;
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
@@ -536,6 +553,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         const uint8_t pat[6] = {CPN_WALK, CPN_STRETCH, CPN_DE, CPN_DE, CPN_EIGEN, CPN_EIGEN};
         for (int i = 0; i < 96; ++i) cyc.push_back(pat[i % 6]);
         c->cycle_len = (int)cyc.size();
+        memcpy(c->h_cycle, cyc.data(), cyc.size());
         if (dalloc(&c->d_cycle, 4096)) return 1;
         CK(h2d_sync(c->d_cycle, cyc.data(), cyc.size()));
     }
@@ -566,16 +584,16 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
         rows = std::max<long long>(std::min(rows, cap_rows), 4LL * N);
         if (grow_logs(c, rows)) return 1;
     }
-    *out = c;
     return 0;
 }
 
 extern "C" void cpn_destroy(cpn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
-    cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->side);
-    cudaStreamSynchronize(c->acc_stream);
+    // (a context whose creation failed half-way has null handles: nothing to wait for / destroy there)
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
+    if (c->acc_stream) cudaStreamSynchronize(c->acc_stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_seg_sorted, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
@@ -586,16 +604,14 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     if (c->rtc) rtc_destroy(c->rtc);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_idx) cudaFreeHost(c->h_idx);
-    cudaEventDestroy(c->ev);
-    cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_cov); cudaEventDestroy(c->ev_eig);
-    cudaStreamDestroy(c->side);
-    cudaStreamDestroy(c->acc_stream);
-    cudaEventDestroy(c->ev_thr); cudaEventDestroy(c->ev_acc); cudaEventDestroy(c->ev_ins); cudaEventDestroy(c->ev_corr);
-    if (c->mixed) {
-        cudaEventDestroy(c->ev_fork);
-        for (int k = 0; k < kNumKinds; ++k) { cudaStreamSynchronize(c->kind_stream[k]); cudaStreamDestroy(c->kind_stream[k]); cudaEventDestroy(c->ev_kind[k]); }
-    }
-    cudaStreamDestroy(c->own_stream);
+    cudaEvent_t evs[] = {c->ev, c->ev_main, c->ev_cov, c->ev_eig, c->ev_thr, c->ev_acc, c->ev_ins, c->ev_corr, c->ev_fork,
+                         c->ev_kind[0], c->ev_kind[1], c->ev_kind[2]};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    cudaStream_t sts[] = {c->side, c->acc_stream, c->kind_stream[0], c->kind_stream[1], c->kind_stream[2], c->own_stream};
+    for (cudaStream_t st : sts)
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    cudaGetLastError();
     delete c;
 }
 
@@ -606,6 +622,7 @@ extern "C" int cpn_set_cycle(cpn_ctx* c, const uint8_t* cycle, int32_t len) {
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaMemcpyAsync(c->d_cycle, cycle, len, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    memcpy(c->h_cycle, cycle, len);
     c->cycle_len = len;
     return 0;
 }
@@ -807,6 +824,7 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     memset(p, 0, sizeof *p);
     fill_common(c, p);
     p->cycle = c->d_cycle; p->cycle_len = c->cycle_len;
+    memcpy(p->cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
     p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
     p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
 }
@@ -1345,6 +1363,30 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
         h.maxmcmc != c->cfg.maxmcmc || h.mix[0] != c->mix[0] || h.mix[1] != c->mix[1] || h.mix[2] != c->mix[2])
         return fail("cpn_load_checkpoint: checkpoint of a different run (dim %d nlive %d functor %d sampler %d maxmcmc %d)", h.dim,
                     h.nlive, h.functor, h.sampler, h.maxmcmc);
+    // every field that sizes a copy or indexes a buffer is checked before the context is touched: a corrupt or truncated
+    // file leaves the context as it was
+    if (h.cycle_len < 1 || h.cycle_len > 4096 || h.slice_cycle_len < 1 || h.slice_cycle_len > 4096)
+        return fail("cpn_load_checkpoint: corrupt header (cycle lengths %d, %d)", h.cycle_len, h.slice_cycle_len);
+    if ((h.cur != 0 && h.cur != 1) || (h.eig_cur != 0 && h.eig_cur != 1))
+        return fail("cpn_load_checkpoint: corrupt header (buffer indices %d, %d)", h.cur, h.eig_cur);
+    if (h.n_dead < 0 || h.n_hist < 0 || h.n_ins < 0 || h.dead_upper < h.n_dead || h.batches_enqueued < 0 || h.chains_since_stats < 0 ||
+        h.eig_calls < 0 || h.eig_pending_age < 0)
+        return fail("cpn_load_checkpoint: corrupt header (negative or inconsistent counters)");
+    if (h.n_dead != h.state.iteration || h.n_hist != h.state.n_hist || h.n_ins != h.state.n_ins)
+        return fail("cpn_load_checkpoint: corrupt header (log lengths %lld/%lld/%lld do not match the saved state %lld/%lld/%lld)",
+                    h.n_dead, h.n_hist, h.n_ins, h.state.iteration, h.state.n_hist, h.state.n_ins);
+    {
+        // size of the sections with the header's counts, computed without touching the context
+        const size_t N = c->N, D = c->D, Dp = c->Dp;
+        const size_t sizes[] = {N * Dp * 8, N * 8, N * 8, N * 4, N * 8, (size_t)h.n_dead * Dp * 8, (size_t)h.n_dead * 8, (size_t)h.n_dead * 8,
+                                (size_t)h.n_hist * 8, (size_t)h.n_hist * 8, (size_t)h.n_ins * 8, kNumKinds * (D + 1) * 8,
+                                (size_t)h.cycle_len, (size_t)h.slice_cycle_len, D * 8, D * D * 8,
+                                2 * (D * 8), 2 * (D * Dp * 8), 2 * (D * 8), 2 * (D * 8), 2 * (D * D * 8)};
+        size_t tot = sizeof h;
+        for (int i = 0; i < 16; ++i) tot += (sizes[i] + 7) & ~(size_t)7;
+        for (int i = 16; i < 21; ++i) tot += 2 * (((sizes[i] / 2) + 7) & ~(size_t)7);
+        if ((size_t)bytes < tot) return fail("cpn_load_checkpoint: truncated blob (%lld of %zu bytes)", (long long)bytes, tot);
+    }
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->side));
@@ -1363,6 +1405,7 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
         if (sec.bytes) CK(h2d_sync(sec.dev, p, sec.bytes));
         p += (sec.bytes + 7) & ~(size_t)7;
     }
+    CK(cudaMemcpy(c->h_cycle, c->d_cycle, (size_t)c->cycle_len, cudaMemcpyDeviceToHost));
     *c->h_state = h.state;
     if (push_state(c)) return 1;
     if (c->eig_pending) {
@@ -1815,6 +1858,89 @@ extern "C" int cpn_replay_mh(cpn_ctx* c, int32_t P, const double* ensemble, int3
     for (void* q : fr)
         if (q) cudaFree(q);
     return 0;
+}
+
+// The PRODUCTION MH kernel (the instantiation every run and the benchmark launch) on given chains, with a record of
+// what every step consumed: see the header.
+extern "C" int cpn_trace_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start, const double* eigval,
+                            const double* eigvec, int32_t cycle_idx, int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t lanes,
+                            uint64_t chain_base, double* out, int32_t* steps, int32_t* accepted, int32_t* evals, double* draws) {
+    if (!c || !ensemble || !start || !out || !draws) return fail("null argument");
+    if (P < 4 || C < 1 || maxmcmc < 1 || nmcmc < 1) return fail("bad sizes");
+    if (c->cfg.functor == CPN_USER) return fail("cpn_trace_mh is not available for a user functor");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    int G, E;
+    if (pick_config(D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) return 1;
+    std::vector<double> ex((size_t)P * Dp, 0.0), sx((size_t)C * Dp, 0.0), sl(C), sp(C), ev((size_t)D * Dp, 0.0), es(D, 0.0);
+    for (int i = 0; i < P; ++i)
+        for (int d = 0; d < D; ++d) ex[(size_t)i * Dp + d] = ensemble[(size_t)i * D + d];
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) sx[(size_t)i * Dp + d] = start[(size_t)i * (D + 2) + d];
+        sl[i] = start[(size_t)i * (D + 2) + D];
+        sp[i] = start[(size_t)i * (D + 2) + D + 1];
+    }
+    if (eigval && eigvec)
+        for (int i = 0; i < D; ++i) {
+            es[i] = sqrt(fabs(eigval[i]));                                   // proposal.py:339
+            for (int k = 0; k < D; ++k) ev[(size_t)i * Dp + k] = eigvec[(size_t)k * D + i];
+        }
+    const size_t ndraw = (size_t)C * maxmcmc * 8;
+    double *dex = nullptr, *dsx = nullptr, *dsl = nullptr, *dsp = nullptr, *dev = nullptr, *des = nullptr, *dox = nullptr, *dol = nullptr,
+           *dop = nullptr, *ddraw = nullptr;
+    int *dst = nullptr, *dac = nullptr, *dnev = nullptr;
+    int rc = 1;
+    do {
+        if (dalloc(&dex, ex.size() + kRowSlack) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) ||
+            dalloc(&dev, ev.size() + kRowSlack) || dalloc(&des, D) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) ||
+            dalloc(&dop, C) || dalloc(&dst, C) || dalloc(&dac, C) || dalloc(&dnev, C) || dalloc(&ddraw, ndraw))
+            break;
+        if (h2d_sync(dex, ex.data(), ex.size() * sizeof(double)) != cudaSuccess || h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)) != cudaSuccess ||
+            h2d_sync(dsl, sl.data(), C * sizeof(double)) != cudaSuccess || h2d_sync(dsp, sp.data(), C * sizeof(double)) != cudaSuccess ||
+            h2d_sync(dev, ev.data(), ev.size() * sizeof(double)) != cudaSuccess || h2d_sync(des, es.data(), D * sizeof(double)) != cudaSuccess) {
+            fail("cpn_trace_mh: host to device copy failed");
+            break;
+        }
+        MHParams p;
+        memset(&p, 0, sizeof p);
+        p.ens_x = dex; p.ens_n = P; p.Dp = Dp; p.D = D;
+        p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
+        p.lo = c->d_lo; p.hi = c->d_hi;
+        p.cycle = c->d_cycle; p.cycle_len = c->cycle_len; p.cycle_pos0 = cycle_idx % c->cycle_len;
+        memcpy(p.cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
+        p.eig_scale = des; p.eig_vec = dev;
+        p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.maxmcmc = maxmcmc;
+        p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
+        p.padded = Dp >= G * E;
+        p.chain_base = chain_base;
+        p.seed_lo = (uint32_t)c->cfg.seed; p.seed_hi = (uint32_t)(c->cfg.seed >> 32);
+        p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
+        p.out_evals[0] = dnev;
+        p.draws = ddraw;
+        if (run_mh(c, G, E, 0, p)) break;
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { fail("cpn_trace_mh: launch failed"); break; }
+        std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
+        if (cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(draws, ddraw, ndraw * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            (steps && cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (accepted && cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (evals && cudaMemcpy(evals, dnev, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)) {
+            fail("cpn_trace_mh: device to host copy failed");
+            break;
+        }
+        for (int i = 0; i < C; ++i) {
+            for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
+            out[(size_t)i * (D + 2) + D] = ol[i];
+            out[(size_t)i * (D + 2) + D + 1] = op[i];
+        }
+        rc = 0;
+    } while (0);
+    void* fr[] = {dex, dsx, dsl, dsp, dev, des, dox, dol, dop, dst, dac, dnev, ddraw};
+    for (void* q : fr)
+        if (q) cudaFree(q);
+    return rc;
 }
 
 static int slice_scratch_launch(cpn_ctx* c, SliceParams& p, int replay, int lanes, int C) {

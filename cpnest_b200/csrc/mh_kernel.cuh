@@ -14,9 +14,11 @@
 
 namespace cpn {
 
+constexpr int kCycInline = 256;   // proposal cycles up to this length travel in the launch parameters (constant bank)
+
 struct MHParams : ChainParams {
     // proposal cycle + eigen directions
-    const uint8_t* cycle;
+    const uint8_t* cycle;     // [cycle_len] in device memory (replay kernel; production when cycle_len > kCycInline)
     int cycle_len;
     int cycle_pos0;
     const double* eig_scale;  // [D]     sqrt|lambda_i|
@@ -25,45 +27,59 @@ struct MHParams : ChainParams {
     const double* tape;       // [chains][maxmcmc][8]
     int compat;               // fp32 rounding of LivePoint scalars (cpnest/parameter.pyx:96-120)
     double* states;           // [chains][maxmcmc][D] or null
+    // production: the cycle inline (ProposalCycle's default length is 100, cpnest/proposal.py:52): the kind of a step is the
+    // same for every chain of the launch, read through the uniform datapath, and the proposal code branches on it uniformly
+    uint8_t cyc[kCycInline];
+    // production, test entry (cpn_trace_mh): what every step of every chain consumed besides the chain state,
+    // [chains][maxmcmc][8] doubles {kind, i0, i1, i2, c0, c1, c2, thr} (see DrawFeed), or null
+    double* draws;
 };
 
 // ---- what one MCMC step consumes besides the chain's current point ---------------------------------
 // Nothing of it depends on the chain state, so the inputs (and the gather they imply) of step t+1 are
 // produced while step t is still being evaluated.
 //
-// Production form.  All four proposals of the DefaultProposalCycle are instances of
-//     new = cx * old + c0 * r0 + c1 * r1 + c2 * r2          (r_j: gathered ensemble rows / eigen-direction)
-//   EnsembleWalk          old + sum_j g_j (s_j - com), com = (s0+s1+s2)/3  ->  cx = 1, c_j = g_j - mean(g)   proposal.py:230-234
-//   EnsembleStretch       a + Z (old - a)                                  ->  cx = Z, c0 = 1 - Z            proposal.py:253-260
-//   DifferentialEvolution old + g (b - a), g ~ N(1, 1e-4)                  ->  cx = 1, c0 = -g, c1 = g       proposal.py:284-286
-//   EnsembleEigenVector   old + sqrt|lambda_i| N(0,1) v_i                  ->  cx = 1, c0 = jump, r0 = v_i   proposal.py:336-342
-// so a step is straight-line code whatever the proposal kind: the compiler can interleave the draw and the
-// gather of the following step with the dependent chain proposal -> box test -> likelihood reduction ->
-// accept of this one.  `thr` = log(u) - log_J: the prior MH test (sampler.py:337) reads dlogP > thr.
+// Production form, per proposal kind of the DefaultProposalCycle (r_j: gathered ensemble rows / eigen-direction):
+//   EnsembleWalk          old + sum_j g_j (s_j - com), com = (s0+s1+s2)/3  =  old + sum_j c_j s_j, c_j = g_j - mean(g)   proposal.py:230-234
+//   EnsembleStretch       a + (old - a) Z,  log_J = D x, Z = exp(x), x = uniform(-1,1) log 2                            proposal.py:253-260
+//   DifferentialEvolution old + (b - a) g, g ~ N(1, 1e-4)                                                               proposal.py:284-286
+//   EnsembleEigenVector   old + jump v_i, jump = sqrt|lambda_i| N(0,1)                                                   proposal.py:336-342
+// The kind of step t is the same for all chains of a launch (same cycle, same position), so the step branches on it
+// uniformly and gathers only the rows that kind needs (1.67 rows per step on average instead of 3).
+// Scalars c_j, Z, g are fp32 values (the reference rounds the scalar of every LivePoint product to fp32,
+// parameter.pyx:96-120); the EigenVector jump is fp64 (proposal.py:339-341 does not go through LivePoint.__mul__).
+// `thr` = log(u) - log_J: the prior MH test (sampler.py:337) reads dlogP > thr.
+template <bool B>
+struct BoolC { static constexpr bool value = B; };
+
 struct StepIn {
-    int kind;
     uint32_t i0, i1, i2;
-    double cx, c0, c1, c2;
+    uint32_t w3, w4, w5;      // WALK: c0, c1, c2 (fp32 bits); STRETCH: w3 = Z; DE: w3 = g; EIGEN: (w4, w5) = jump (fp64 bits)
     double thr;
 };
 
 // The inputs of G consecutive steps are computed once, one step per lane (Philox blocks (chain, step, 0/1),
-// Box-Muller, log(u), exp), packed into 8 words and handed out step after step through the lane's row of a
-// shared-memory table (two 128-bit broadcast loads per step; 8 shuffles before v8) instead of a redundant RNG
-// evaluation on every lane; the stream is a pure function of (seed, chain, step) - independent of G and of the grid.
+// Box-Muller, log(u)), packed into 8 words and handed out step after step through the lane's row of a
+// shared-memory table (two 128-bit broadcast loads per step) instead of a redundant RNG evaluation on every lane;
+// the stream is a pure function of (seed, chain, step) - independent of G and of the grid.
 // FLAT: the prior is flat, so the prior MH test `dlogP > log(u) - log_J` (sampler.py:337) can only fail through the
 // box (dlogP = -inf) unless log_J != 0, i.e. only EnsembleStretch needs log(u); the other kinds get thr = -1 (any
 // negative number gives the same decisions as log(u) < 0).
 template <int G, bool FLAT>
 struct DrawFeed {
-    uint32_t w[8];   // i0, i1, i2, c0, c1, c2 (fp32 bits), thr (fp64 bits)
-    uint4* row;      // this lane's 32-byte row of the block's table (G > 1)
+    uint4* row;      // this lane's 32-byte row of the block's table
+    StepIn own;      // G == 1 only
+    // dump: where to record the 8 values of this step (test entry), or null
     __device__ __forceinline__ void refill(int kind, uint32_t step, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1,
-                                           uint32_t ens_n, uint32_t D, const double* eig_scale) {
+                                           uint32_t ens_n, uint32_t D, const double* eig_scale, double* dump) {
         const Philox4 r = philox4x32_10(cid_lo, cid_hi, step, 0u, k0, k1);
         double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : log(u32_to_unit_open(r.v[3]));
-        uint32_t i0 = u32_to_index(r.v[0], ens_n), i1, i2;
-        float c0, c1 = 0.0f, c2 = 0.0f;
+        uint32_t i0 = u32_to_index(r.v[0], kind == CPN_EIGEN ? D : ens_n);       // EIGEN: randrange(D), proposal.py:338
+        uint32_t i1 = i0, i2 = i0;
+        uint32_t w3 = 0u, w4 = 0u, w5 = 0u;
+        // inputs of the Box-Muller pair every kind but STRETCH needs (one shared evaluation: the lanes of a warp
+        // prepare steps of different kinds, the code after the kind-specific part runs converged)
+        uint32_t ba = r.v[1], bb = r.v[2], bc = 0u, bd = 0u;
         if (kind == CPN_WALK) {
             // three distinct members, `sample(list(ensemble), 3)` proposal.py:230
             i1 = u32_to_index(r.v[1], ens_n - 1);
@@ -73,79 +89,80 @@ struct DrawFeed {
             i2 += (i2 >= lo2);
             i2 += (i2 >= hi2);
             const Philox4 q = philox4x32_10(cid_lo, cid_hi, step, 1u, k0, k1);
-            float g0, g1, g2, g3;
-            box_muller_f(q.v[0], q.v[1], g0, g1);
-            box_muller_f(q.v[2], q.v[3], g2, g3);
-            const float gbar = (g0 + g1 + g2) * (1.0f / 3.0f);
-            c0 = g0 - gbar; c1 = g1 - gbar; c2 = g2 - gbar;
-        } else if (kind == CPN_STRETCH) {
-            i1 = i2 = i0;                                                          // random.choice, proposal.py:253
-            const double xs = (2.0 * u32_to_unit_open(r.v[1]) - 1.0) * 0.69314718055994530942;   // uniform(-1,1)*log(2)
-            c0 = (float)(1.0 - exp(xs));                                           // Z = exp(x), proposal.py:256-258
-            thr -= (double)D * log(1.0 - (double)c0);                              // log_J = D log Z of the Z applied, :260
+            ba = q.v[0]; bb = q.v[1]; bc = q.v[2]; bd = q.v[3];
         } else if (kind == CPN_DE) {
             i1 = u32_to_index(r.v[1], ens_n - 1);                                  // sample(...,2), proposal.py:284
             i1 += (i1 >= i0);
-            i2 = i1;
-            float gd, unused;
-            box_muller_f(r.v[2] << 16, r.v[2] & 0xffff0000u, gd, unused);
-            c1 = fmaf(1e-4f, gd, 1.0f);                                            // gauss(1.0, 1e-4), proposal.py:285-286
-            c0 = -c1;
+            ba = r.v[2] << 16; bb = r.v[2] & 0xffff0000u;
+        }
+        float ga, gb;
+        box_muller_f(ba, bb, ga, gb);
+        if (kind == CPN_WALK) {
+            float gc, unused;
+            box_muller_f(bc, bd, gc, unused);
+            const float gbar = (ga + gb + gc) * (1.0f / 3.0f);
+            w3 = __float_as_uint(ga - gbar); w4 = __float_as_uint(gb - gbar); w5 = __float_as_uint(gc - gbar);
+        } else if (kind == CPN_STRETCH) {
+            // x = uniform(-1,1) log 2, Z = exp(x) = 2^t rounded to fp32 (the LivePoint product rounds it, parameter.pyx:96),
+            // log_J = D x from the un-rounded x (proposal.py:255-260)
+            const float t = (float)(2.0 * u32_to_unit_open(r.v[1]) - 1.0);
+            w3 = __float_as_uint(exp2f(t));
+            thr -= (double)D * ((double)t * 0.69314718055994530942);
+        } else if (kind == CPN_DE) {
+            w3 = __float_as_uint(fmaf(1e-4f, ga, 1.0f));                            // gauss(1.0, 1e-4), proposal.py:285-286
         } else {
-            i0 = u32_to_index(r.v[0], D);                                          // randrange(D), proposal.py:338
-            i1 = i2 = i0;
-            float g, unused;
-            box_muller_f(r.v[1], r.v[2], g, unused);
-            c0 = (float)(__ldg(eig_scale + i0) * (double)g);                       // sqrt|lambda_i| * gauss(0,1), :339
+            const double jump = __ldg(eig_scale + i0) * (double)ga;               // sqrt|lambda_i| * gauss(0,1), :339
+            w4 = (uint32_t)__double2loint(jump); w5 = (uint32_t)__double2hiint(jump);
         }
-        w[0] = i0; w[1] = i1; w[2] = i2;
-        w[3] = __float_as_uint(c0); w[4] = __float_as_uint(c1); w[5] = __float_as_uint(c2);
-        w[6] = (uint32_t)__double2loint(thr);
-        w[7] = (uint32_t)__double2hiint(thr);
-        if (G > 1) {
-            __syncwarp();                       // every lane has read the previous G steps
-            row[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            row[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            __syncwarp();
+        if (dump != nullptr) {
+            dump[0] = (double)kind; dump[1] = (double)i0; dump[2] = (double)i1; dump[3] = (double)i2;
+            if (kind == CPN_EIGEN) {
+                dump[4] = __hiloint2double((int)w5, (int)w4); dump[5] = 0.0; dump[6] = 0.0;
+            } else {
+                dump[4] = (double)__uint_as_float(w3); dump[5] = (double)__uint_as_float(w4); dump[6] = (double)__uint_as_float(w5);
+            }
+            dump[7] = thr;
         }
+        if (G == 1) {                       // a chain per lane: the step is this lane's own
+            own.i0 = i0; own.i1 = i1; own.i2 = i2; own.w3 = w3; own.w4 = w4; own.w5 = w5; own.thr = thr;
+            return;
+        }
+        __syncwarp();                       // every lane has read the previous G steps
+        row[0] = make_uint4(i0, i1, i2, w3);
+        row[1] = make_uint4(w4, w5, (uint32_t)__double2loint(thr), (uint32_t)__double2hiint(thr));
+        __syncwarp();
     }
     // src_row: row of the lane of this group that prepared the step
-    __device__ __forceinline__ StepIn get(int kind, const uint4* src_row) const {
-        uint32_t v[8];
-        if (G == 1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = w[k];
-        } else {
-            const uint4 a = src_row[0], b = src_row[1];
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
+    __device__ __forceinline__ StepIn get(const uint4* src_row) const {
+        if (G == 1) return own;
+        const uint4 a = src_row[0], b = src_row[1];
         StepIn s;
-        s.kind = kind;
-        s.i0 = v[0]; s.i1 = v[1]; s.i2 = v[2];
-        s.c0 = (double)__uint_as_float(v[3]); s.c1 = (double)__uint_as_float(v[4]); s.c2 = (double)__uint_as_float(v[5]);
-        s.cx = (kind == CPN_STRETCH) ? 1.0 - s.c0 : 1.0;
-        s.thr = __hiloint2double((int)v[7], (int)v[6]);
+        s.i0 = a.x; s.i1 = a.y; s.i2 = a.z; s.w3 = a.w; s.w4 = b.x; s.w5 = b.y;
+        s.thr = __hiloint2double((int)b.w, (int)b.z);
         return s;
     }
 };
 
-// the three rows a production step gathers (kinds that need fewer re-read row i0: an L1 hit).  Straight-line:
-// every slot is loaded, also the slots beyond D of the last lanes, which then read the head of the following row
-// (the arrays carry kRowSlack doubles of slack at their end).  Those values are finite and never used: the box
-// test (+-inf bounds), the functors (valid_dim masks) and the final store ignore slots beyond D.
+// The rows the step of kind `kind` gathers: WALK three members, DE two, STRETCH one, EIGEN one eigen-direction.
+// `kind` is uniform over the launch.  Every slot of a lane is loaded, also the slots beyond D of the last lanes, which
+// then read the head of the following row (the arrays carry kRowSlack doubles of slack at their end).  Those values are
+// finite and never used: the box test (+-inf bounds), the functors (valid_dim masks) and the final store ignore slots beyond D.
 template <int G, int E>
-__device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, const StepIn& s, double (&r0)[E],
+__device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, int kind, const StepIn& s, double (&r0)[E],
                                             double (&r1)[E], double (&r2)[E]) {
-    const bool eig = s.kind == CPN_EIGEN;
     const unsigned Dp = (unsigned)p.Dp, lane = (unsigned)g.lane;
-    const double* b0 = (eig ? p.eig_vec : p.ens_x) + (s.i0 * Dp + lane);
-    const double* b1 = p.ens_x + (s.i1 * Dp + lane);
-    const double* b2 = p.ens_x + (s.i2 * Dp + lane);
+    const double* b0 = (kind == CPN_EIGEN ? p.eig_vec : p.ens_x) + (s.i0 * Dp + lane);
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        r0[e] = __ldg(b0 + e * G);
-        r1[e] = __ldg(b1 + e * G);
-        r2[e] = __ldg(b2 + e * G);
+    for (int e = 0; e < E; ++e) r0[e] = __ldg(b0 + e * G);
+    if (kind == CPN_WALK || kind == CPN_DE) {
+        const double* b1 = p.ens_x + (s.i1 * Dp + lane);
+#pragma unroll
+        for (int e = 0; e < E; ++e) r1[e] = __ldg(b1 + e * G);
+    }
+    if (kind == CPN_WALK) {
+        const double* b2 = p.ens_x + (s.i2 * Dp + lane);
+#pragma unroll
+        for (int e = 0; e < E; ++e) r2[e] = __ldg(b2 + e * G);
     }
 }
 
@@ -279,66 +296,106 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         // ================================ production ==================================================
         // The loop exists twice: `mm` is the chain's functor context, or - when the gathered rows are zero-padded up to
         // G*E doubles and the functor tolerates zeros in the slots beyond D (Model::pad_ok) - a copy whose slot masks
-        // are the constant all-ones, which lets the compiler drop the masking of every slot (17 of 155 instructions per
-        // step for the iid Gaussian at D=50): those slots then hold exact zeros in x, in every gathered row and hence in
-        // every proposal.
+        // are the constant all-ones, which lets the compiler drop the masking of every slot: those slots then hold exact
+        // zeros in x, in every gathered row and hence in every proposal.
         auto production = [&](const ModelCtx& mm) {
         const uint32_t ens_n = (uint32_t)p.ens_n;
         DrawFeed<G, Model::kFlatPrior> feed;
         feed.row = &feed_tab[threadIdx.x][0];
         const uint4* grow = &feed_tab[threadIdx.x & ~(G - 1)][0];        // row of this group's lane 0
-        auto next_in = [&](int it) -> StepIn {
-            const int kind = p.cycle[npos];
+        const bool cyc_inline = clen <= kCycInline;
+        auto kind_at = [&](int pos) -> int { return cyc_inline ? (int)p.cyc[pos] : (int)p.cycle[pos]; };
+        double* dump = (p.draws != nullptr && valid) ? p.draws + (size_t)c * maxmcmc * 8 : nullptr;
+        // kind and inputs of step `it`; the inputs are drawn G steps at a time, one step per lane
+        auto next_in = [&](int it, int& kind) -> StepIn {
+            kind = kind_at(npos);
             if ((it & (G - 1)) == 0) {                                   // this lane prepares step it + lane
                 int lpos = npos + g.lane;                                // (npos + lane) % clen without the division
                 while (lpos >= clen) lpos -= clen;
-                feed.refill(p.cycle[lpos], (uint32_t)(it + g.lane), cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D,
-                            p.eig_scale);
+                const int st = it + g.lane;
+                feed.refill(kind_at(lpos), (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D, p.eig_scale,
+                            (dump != nullptr && st < maxmcmc) ? dump + (size_t)st * 8 : nullptr);
             }
             npos = (npos + 1 == clen) ? 0 : npos + 1;
-            return feed.get(kind, grow + 2 * (it & (G - 1)));
+            return feed.get(grow + 2 * (it & (G - 1)));
         };
-        // One MCMC step on (s, r0..r2); meanwhile the inputs of the following step are drawn and gathered into
-        // (ns, n0..n2).  The caller alternates two such sets, so nothing is copied between steps.
-        auto mcmc_step = [&](int it, const StepIn& s, const double (&r0)[E], const double (&r1)[E], const double (&r2)[E],
-                             StepIn& ns, double (&n0)[E], double (&n1)[E], double (&n2)[E]) {
-            ns = next_in(it + 1);
-            gather_rows<G, E>(g, p, ns, n0, n1, n2);
+        // One MCMC step of kind `kind` on (s, r0..r2); meanwhile the inputs of the following step are drawn and its rows
+        // gathered into (ns, n0..n2).  The caller alternates two such sets, so nothing is copied between steps.
+        // TAIL = false: no chain of the launch can stop at this step (fewer than min(Nmcmc, maxmcmc) steps done), so the
+        // step carries no per-chain `active` state.
+        auto mcmc_step = [&](auto tail, int it, int kind, const StepIn& s, const double (&r0)[E], const double (&r1)[E],
+                             const double (&r2)[E], int& nkind, StepIn& ns, double (&n0)[E], double (&n1)[E], double (&n2)[E]) {
+            constexpr bool TAIL = decltype(tail)::value;
+            ns = next_in(it + 1, nkind);
+            gather_rows<G, E>(g, p, nkind, ns, n0, n1, n2);
             double xn[E];
-            bool inb = true;
+            if (kind == CPN_WALK) {                                         // old + sum_j c_j s_j, proposal.py:230-234
+                const double c0 = (double)__uint_as_float(s.w3), c1 = (double)__uint_as_float(s.w4), c2 = (double)__uint_as_float(s.w5);
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = fma(c2, r2[e], fma(c1, r1[e], fma(c0, r0[e], x[e])));
+            } else if (kind == CPN_STRETCH) {                               // a + (old - a) Z, proposal.py:258
+                const double Z = (double)__uint_as_float(s.w3);
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = fma(Z, x[e] - r0[e], r0[e]);
+            } else if (kind == CPN_DE) {                                    // old + (b - a) g, proposal.py:286
+                const double gd = (double)__uint_as_float(s.w3);
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = fma(gd, r1[e] - r0[e], x[e]);
+            } else {                                                        // old + jump v_i, proposal.py:340-341
+                const double jump = __hiloint2double((int)s.w5, (int)s.w4);
+#pragma unroll
+                for (int e = 0; e < E; ++e) xn[e] = fma(jump, r0[e], x[e]);
+            }
+            // strict box test, model.py:33 (independent comparison chains: the FP64 compare has a long latency)
+            bool in4[4] = {true, true, true, true};
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                xn[e] = fma(s.c2, r2[e], fma(s.c1, r1[e], fma(s.c0, r0[e], s.cx * x[e])));
-                inb = inb & (blo[e] < xn[e]) & (xn[e] < bhi[e]);            // strict, model.py:33
+                in4[(2 * e) & 3] = in4[(2 * e) & 3] & (blo[e] < xn[e]);
+                in4[(2 * e + 1) & 3] = in4[(2 * e + 1) & 3] & (xn[e] < bhi[e]);
             }
-            inb = g.all(inb);
+            const bool inb = g.all((in4[0] & in4[1]) & (in4[2] & in4[3]));
             double logP_new = Model::template log_prior<G, E>(g, xn, mm);
             logP_new = inb ? logP_new : CPN_NEG_INF;
-            const bool pass = (logP_new - logP > s.thr) && active;          // sampler.py:337
+            bool pass = logP_new - logP > s.thr;                            // sampler.py:337
+            if (TAIL) pass = pass && active;
             if (Model::kCheap || __any_sync(FULL, pass)) {
                 const double logL_new = Model::template log_likelihood<G, E>(g, xn, mm);   // sampler.py:338
                 evals += pass ? 1 : 0;
                 const bool acc = pass && logL_new > logLmin;                // sampler.py:339
+                if (__any_sync(FULL, acc)) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) x[e] = acc ? xn[e] : x[e];
-                logL = acc ? logL_new : logL;
-                logP = acc ? logP_new : logP;
-                accepted += acc ? 1 : 0;
+                    for (int e = 0; e < E; ++e) x[e] = acc ? xn[e] : x[e];
+                    logL = acc ? logL_new : logL;
+                    logP = acc ? logP_new : logP;
+                    accepted += acc ? 1 : 0;
+                }
             }
-            steps += active ? 1 : 0;
-            if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
+            if (TAIL) {
+                steps += active ? 1 : 0;
+                if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
+            }
         };
 
+        int ka, kb;
         StepIn sa, sb;
         double a0[E], a1[E], a2[E], b0[E], b1[E], b2[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) a0[e] = a1[e] = a2[e] = b0[e] = b1[e] = b2[e] = 0.0;
-        sa = next_in(0);
-        gather_rows<G, E>(g, p, sa, a0, a1, a2);
-        for (int it = 0; it < maxmcmc; it += 2) {
-            mcmc_step(it, sa, a0, a1, a2, sb, b0, b1, b2);
+        sa = next_in(0, ka);
+        gather_rows<G, E>(g, p, ka, sa, a0, a1, a2);
+        // a chain stops after step number n (counting from 1) if (n >= Nmcmc and it has moved) or n >= maxmcmc
+        // (sampler.py:347): none does during the first min(Nmcmc, maxmcmc) - 1 steps
+        const int n_main = max(0, min(nmcmc, maxmcmc) - 1) & ~1;
+        int it = 0;
+        for (; it < n_main; it += 2) {
+            mcmc_step(BoolC<false>{}, it, ka, sa, a0, a1, a2, kb, sb, b0, b1, b2);
+            mcmc_step(BoolC<false>{}, it + 1, kb, sb, b0, b1, b2, ka, sa, a0, a1, a2);
+        }
+        steps = n_main;
+        for (; it < maxmcmc; it += 2) {
+            mcmc_step(BoolC<true>{}, it, ka, sa, a0, a1, a2, kb, sb, b0, b1, b2);
             if (!__any_sync(FULL, active)) break;
-            mcmc_step(it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
+            mcmc_step(BoolC<true>{}, it + 1, kb, sb, b0, b1, b2, ka, sa, a0, a1, a2);
             if (!__any_sync(FULL, active)) break;
         }
         };
@@ -346,6 +403,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             ModelCtx mp = m;
 #pragma unroll
             for (int e = 0; e < 8; ++e) mp.vmsk[e] = 0xffffffffu;
+            Model::pad_specialise(mp);
             production(mp);
         } else {
             production(m);

@@ -46,6 +46,8 @@ struct ModelBase {
     // true if the functor's value does not change when the slots beyond D of a point hold +0.0 and are NOT masked: the
     // MH kernel then skips the masks whenever the rows it gathers are zero-padded up to G*E doubles (mh_kernel.cuh)
     static __device__ __forceinline__ bool pad_ok(const ModelCtx&) { return false; }
+    // called on the context of the mask-free loop: what pad_ok has established may be written down as constants
+    static __device__ __forceinline__ void pad_specialise(ModelCtx&) {}
 };
 
 template <int G, int E>
@@ -87,6 +89,7 @@ struct GaussIid : FlatPrior {
     }
     // a zero slot adds (0 - mu)^2 to the sum: nothing exactly when mu == 0
     static __device__ __forceinline__ bool pad_ok(const ModelCtx& m) { return m.par[0] == 0.0; }
+    static __device__ __forceinline__ void pad_specialise(ModelCtx& m) { m.par[0] = 0.0; }   // x - 0.0 folds away
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         const double mu = m.par[0];

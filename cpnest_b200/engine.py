@@ -344,6 +344,24 @@ class Engine:
                                        L.dptr(states) if record else None))
         return out, steps, acc, states
 
+    def trace_mh(self, ensemble, start, eigval, eigvec, cycle_idx, nmcmc, maxmcmc, logLmin, lanes=0, chain_base=0):
+        """The production MH kernel on given chains + the record of what every step consumed (cpn_trace_mh).
+        Returns (out[C][D+2], steps, accepted, evals, draws[C][maxmcmc][8])."""
+        ens = L.f64(ensemble)
+        start = L.f64(start).reshape(-1, self.dim + 2)
+        Cn = start.shape[0]
+        ev = L.f64(eigval)
+        evec = L.f64(eigvec)
+        out = np.empty((Cn, self.dim + 2))
+        steps = np.empty(Cn, dtype=np.int32)
+        acc = np.empty(Cn, dtype=np.int32)
+        evals = np.empty(Cn, dtype=np.int32)
+        draws = np.zeros((Cn, maxmcmc, 8))
+        L.check(self.lib.cpn_trace_mh(self.h, ens.shape[0], L.dptr(ens), Cn, L.dptr(start), L.dptr(ev), L.dptr(evec),
+                                      int(cycle_idx), int(nmcmc), int(maxmcmc), float(logLmin), int(lanes), int(chain_base),
+                                      L.dptr(out), L.iptr(steps), L.iptr(acc), L.iptr(evals), L.dptr(draws)))
+        return out, steps, acc, evals, draws
+
     def replay_slice(self, ensemble, start, cycle_idx, tapes, mu, nmcmc, maxmcmc, logLmin, compat=True, lanes=0):
         """Slice chains from explicit random tapes (one flat float sequence per chain, see
         include/cpnest_b200.h cpn_replay_slice).  Returns (out, steps, accepted, evals, last)."""

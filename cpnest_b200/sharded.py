@@ -38,6 +38,15 @@ class ShardedEngine(object):
         self.world = dist.get_world_size(self.group)
         self.comm = comm
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        # The exchange (symmetric-memory barrier / NCCL all-gather) is enqueued by torch, the chain kernel and the merge by the
+        # engine: both must use ONE stream, or the barrier could pass before the chain kernel has stored the staging block and
+        # the merge could read it before the exchange has finished (replicas would silently diverge).  The engine is moved
+        # onto torch's current stream; the legacy default stream (handle 0) cannot be handed over, so a run started on it
+        # gets a stream of its own that every exchange is issued on.
+        self.stream = torch.cuda.current_stream(self.dev)
+        if self.stream.cuda_stream == 0:
+            self.stream = torch.cuda.Stream(device=self.dev)
+        engine.set_stream(self.stream.cuda_stream)
         self.S = int(engine.lib.cpn_shard_record_doubles(engine.h))
         self._send = self._recv = self._symm = self._hdl = None
         if comm == "fused":
@@ -45,6 +54,7 @@ class ShardedEngine(object):
             nbytes = int(engine.lib.cpn_staging_bytes(engine.h))
             self._symm = symm_mem.empty((nbytes + 7) // 8, dtype=torch.float64, device=self.dev)
             self._symm.zero_()
+            torch.cuda.synchronize(self.dev)
             self._hdl = symm_mem.rendezvous(self._symm, self.group)
             ptrs = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in self._hdl.buffer_ptrs])
             L.check(engine.lib.cpn_set_staging(engine.h, ptrs, self.world))
@@ -59,6 +69,10 @@ class ShardedEngine(object):
 
     def exchange(self, K):
         """The one exchange step of a batch: after it every rank's staging block holds all K replacements."""
+        with self.torch.cuda.stream(self.stream):
+            self._exchange(K)
+
+    def _exchange(self, K):
         if self.comm == "fused":
             # the chain kernel has already written into every rank's block; wait for all ranks' kernels
             self._hdl.barrier(channel=0)

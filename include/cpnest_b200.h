@@ -261,6 +261,18 @@ int cpn_replay_mh(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C, co
                   double logLmin, int32_t compat, int32_t lanes,
                   double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted,
                   double* states /*[C][maxmcmc][D] or NULL*/);
+/* The PRODUCTION MH kernel - the instantiation cpn_evolve_batch launches, Philox draws and all - on C given chains, with a
+ * record of what each step consumed besides the chain state: draws[(c*maxmcmc+s)*8+..] = {proposal kind, i0, i1, i2, c0, c1,
+ * c2, thr}: the ensemble members (or the eigen-direction) the step gathered, its scalars (WALK: c_j = g_j - mean(g);
+ * STRETCH: c0 = Z; DE: c0 = g; EIGEN: c0 = sqrt|lambda_i| N(0,1)) and thr = log(u) - log_J of the prior MH test
+ * (cpnest/sampler.py:337; -1 where a flat prior makes the test depend on the box alone).  Feeding these to a restatement of
+ * MetropolisHastingsSampler.yield_sample (cpnest/sampler.py:322-358) must reproduce the chain: the step-level parity test
+ * of the timed code path.  Chain c uses the Philox stream of chain id chain_base + c; ensemble[P][D], start[C][D+2] as in
+ * cpn_replay_mh; the cycle is the context's (cpn_set_cycle), entered at cycle_idx. */
+int cpn_trace_mh(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C, const double* start,
+                 const double* eigval, const double* eigvec, int32_t cycle_idx, int32_t nmcmc, int32_t maxmcmc,
+                 double logLmin, int32_t lanes, uint64_t chain_base, double* out /*[C][D+2]*/, int32_t* steps,
+                 int32_t* accepted, int32_t* evals, double* draws /*[C][maxmcmc][8]*/);
 /* Slice chains driven by an explicit random tape (SliceSampler.yield_sample, cpnest/sampler.py:465-569).
  * Per chain c the doubles tape[tape_off[c] .. tape_off[c+1]) hold, slice after slice,
  *   { u of reset_boundaries, direction data, Exp(1) draw, u of J, X'_1, X'_2, ... }

@@ -765,3 +765,104 @@ def u32_to_unit_open(r):
 def u32_to_index(r, n):
     """mulhi(r, n): uniform index in [0, n)."""
     return (int(r) * int(n)) >> 32
+
+
+# ----------------------------------------------------------------------------------------
+# Step-level oracle of the PRODUCTION MH kernel (cpnest_b200/csrc/mh_kernel.cuh, the instantiation
+# every run launches): the kernel records what each step consumed besides the chain state
+# (cpn_trace_mh); the two functions below restate (a) how those inputs follow from the Philox
+# stream and (b) the reference's chain given those inputs.
+# ----------------------------------------------------------------------------------------
+def box_muller_f32(r0, r1):
+    """rng.cuh box_muller_f: two N(0,1) from two u32, fp32 arithmetic (the device uses the fast
+    fp32 log / sincos units, so agreement is to ~1e-5 absolute, not bit-exact)."""
+    f = np.float32
+    u1 = (f(int(r0) >> 8) + f(0.5)) * f(1.0 / 16777216.0)
+    th = (f(int(r1) >> 8) + f(0.5)) * f(2.0 / 16777216.0) - f(1.0)
+    rad = np.sqrt(f(-2.0) * np.log(u1, dtype=np.float32), dtype=np.float32)
+    ang = f(3.14159265358979) * th
+    return float(rad * np.cos(ang, dtype=np.float32)), float(rad * np.sin(ang, dtype=np.float32))
+
+
+def production_draw(seed, chain_id, step, kind, ens_n, D, eig_scale, flat_prior=True):
+    """mh_kernel.cuh DrawFeed::refill: the inputs of MCMC step `step` of chain `chain_id` as a function of the Philox
+    stream (counter = (chain id lo, hi, step, block), key = seed).  Returns [kind, i0, i1, i2, c0, c1, c2, thr]:
+      WALK    three distinct members (`random.sample(ensemble, 3)`, proposal.py:230), c_j = g_j - mean(g) in fp32
+      STRETCH one member (`choice`, :253), c0 = Z = 2^t (fp32), t = uniform(-1,1); thr = log u - D t log 2 (:255-260)
+      DE      two distinct members (:284), c0 = g = 1 + 1e-4 N(0,1) in fp32 (:285)
+      EIGEN   i0 = randrange(D) (:338), c0 = sqrt|lambda_i0| N(0,1) in fp64 (:339)
+    thr = log(u) - log_J of the prior MH test (sampler.py:337); -1 under a flat prior for the kinds with log_J = 0."""
+    f = np.float32
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    clo, chi = chain_id & 0xFFFFFFFF, (chain_id >> 32) & 0xFFFFFFFF
+    r = philox4x32_10((clo, chi, step, 0), key)
+    thr = -1.0 if (flat_prior and kind != STRETCH) else math.log(u32_to_unit_open(r[3]))
+    i0 = u32_to_index(r[0], D if kind == EIGEN else ens_n)
+    i1 = i2 = i0
+    c0 = c1 = c2 = 0.0
+    if kind == WALK:
+        i1 = u32_to_index(r[1], ens_n - 1)
+        i1 += i1 >= i0
+        i2 = u32_to_index(r[2], ens_n - 2)
+        lo2, hi2 = min(i0, i1), max(i0, i1)
+        i2 += i2 >= lo2
+        i2 += i2 >= hi2
+        q = philox4x32_10((clo, chi, step, 1), key)
+        ga, gb = box_muller_f32(q[0], q[1])
+        gc, _ = box_muller_f32(q[2], q[3])
+        gbar = (f(ga) + f(gb) + f(gc)) * f(1.0 / 3.0)
+        c0, c1, c2 = float(f(ga) - gbar), float(f(gb) - gbar), float(f(gc) - gbar)
+    elif kind == STRETCH:
+        t = f(2.0 * u32_to_unit_open(r[1]) - 1.0)
+        c0 = float(np.exp2(t, dtype=np.float32))
+        thr -= D * (float(t) * 0.69314718055994530942)
+    elif kind == DE:
+        i1 = u32_to_index(r[1], ens_n - 1)
+        i1 += i1 >= i0
+        ga, _ = box_muller_f32((r[2] << 16) & 0xFFFFFFFF, r[2] & 0xFFFF0000)
+        c0 = float(f(1e-4) * f(ga) + f(1.0))
+    else:
+        ga, _ = box_muller_f32(r[1], r[2])
+        c0 = float(eig_scale[i0]) * float(f(ga))
+    return [float(kind), float(i0), float(i1), float(i2), c0, c1, c2, thr]
+
+
+def mh_chain_from_draws(model, ens, eigen_vectors, start, start_logL, start_logP, draws, Nmcmc, maxmcmc, logLmin):
+    """MetropolisHastingsSampler.yield_sample (sampler.py:322-358) on the per-step inputs `draws[s] = [kind, i0, i1, i2,
+    c0, c1, c2, thr]` recorded by the production kernel.  The ensemble is the fixed live snapshot `ens` (the device does
+    not pop/append, DESIGN.md "pool = live set").  Proposals in the reference's own operation order with the scalars as
+    given (they already are fp32 values, the rounding LivePoint.__mul__ applies, parameter.pyx:96-120):
+      STRETCH a + (old - a) Z (proposal.py:258), DE old + (b - a) g (:286), EIGEN old + jump v_i (:340-341);
+      WALK old + sum_j c_j s_j, which is old + sum_j g_j (s_j - com) (:230-234) written with c_j = g_j - mean(g).
+    Prior MH test `new_logP - old_logP + log_J > log u` (sampler.py:337) as `dlogP > thr`."""
+    ens = np.asarray(ens, dtype=np.float64)
+    V = np.asarray(eigen_vectors, dtype=np.float64)
+    old = np.array(start, dtype=np.float64)
+    old_logL, logp_old = float(start_logL), float(start_logP)
+    steps = accepted = evals = 0
+    for s in range(maxmcmc):
+        kind, i0, i1, i2, c0, c1, c2, thr = draws[s]
+        kind, i0, i1, i2 = int(kind), int(i0), int(i1), int(i2)
+        steps += 1                                                       # :333
+        if kind == WALK:
+            assert len({i0, i1, i2}) == 3 and abs(c0 + c1 + c2) < 1e-6
+            new = ((old + c0 * ens[i0]) + c1 * ens[i1]) + c2 * ens[i2]
+        elif kind == STRETCH:
+            new = ens[i0] + lp_mul(old - ens[i0], c0, compat=False)
+        elif kind == DE:
+            assert i0 != i1
+            new = old + lp_mul(ens[i1] - ens[i0], c0, compat=False)
+        else:
+            new = old + c0 * V[:, i0]
+        new_logP = model.log_prior(new)                                  # :335
+        with np.errstate(all="ignore"):
+            test = (new_logP - logp_old) > thr                           # :337
+        if test:
+            new_logL = model.log_likelihood(new)                         # :338
+            evals += 1
+            if new_logL > logLmin:                                       # :339
+                old, old_logL, logp_old = new, new_logL, new_logP
+                accepted += 1
+        if (steps >= Nmcmc and accepted > 0) or steps >= maxmcmc:        # :347
+            break
+    return dict(out=old, logL=old_logL, logP=logp_old, steps=steps, accepted=accepted, evals=evals)

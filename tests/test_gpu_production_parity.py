@@ -1,0 +1,147 @@
+"""Step-level parity of the PRODUCTION chain kernels - the instantiations every run and bench.py launch, Philox draws
+included - against the CPU oracle (VERDICT r01 "what's weak" #1: the replay instantiations are separate code).
+
+cpn_trace_mh runs k_mh_chains<G, E, Model, REPLAY=false> on given chains and records what every step consumed besides the
+chain state: the ensemble members / eigen-direction it gathered, its scalars and the threshold of the prior MH test.
+  (a) those inputs are a known function of the Philox stream  -> oracle.production_draw   (indices exact, thr 1e-13,
+      fp32 scalars to the accuracy of the device's fast fp32 log / sincos / exp2 units);
+  (b) the chain they drive is the reference's MetropolisHastingsSampler.yield_sample (cpnest/sampler.py:322-358) with the
+      proposals of cpnest/proposal.py:209-342 -> oracle.mh_chain_from_draws: steps, accepted and likelihood-call counts
+      exact, end point / logL within 1e-12 relative (FMA contraction is the only difference).
+Run on the B200 box: -m gpu.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpnest_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(model, P, C, rs, spread):
+    D = model.D
+    lo, hi = model.lo, model.hi
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    ens = mid + spread * half * rs.uniform(-1, 1, size=(P, D))
+    ensL = np.array([model.log_likelihood(x) for x in ens])
+    logLmin = float(np.quantile(ensL, 0.35))
+    # chains start from points above the threshold, as survivors do
+    good = np.where(ensL > logLmin)[0]
+    st = ens[good[rs.randint(0, len(good), size=C)]] * (1 - 1e-3)
+    start = np.zeros((C, D + 2))
+    start[:, :D] = st
+    start[:, D] = [model.log_likelihood(x) for x in st]
+    start[:, D + 1] = [model.log_prior(x) for x in st]
+    _, _, w, v = O.ensemble_covariance(ens)
+    return ens, start, logLmin, w, v
+
+
+def _check(model, eng, lanes, rs, P=48, C=6, nmcmc=23, maxmcmc=120, spread=0.3, flat=True, chain_base=777, rtol=1e-12):
+    D = model.D
+    ens, start, logLmin, w, v = _setup(model, P, C, rs, spread)
+    cyc = O.make_cycle(np.random.RandomState(11))
+    eng.set_cycle(cyc)
+    cidx = 5
+    out, steps, acc, evals, draws = eng.trace_mh(ens, start, w, v, cidx, nmcmc, maxmcmc, logLmin, lanes=lanes, chain_base=chain_base)
+    scale = np.sqrt(np.abs(w))
+    seed = 1234
+    moved = 0
+    for c in range(C):
+        r = O.mh_chain_from_draws(model, ens, v, start[c, :D], start[c, D], start[c, D + 1], draws[c], nmcmc, maxmcmc, logLmin)
+        assert steps[c] == r["steps"] and acc[c] == r["accepted"] and evals[c] == r["evals"], (c, steps[c], acc[c], evals[c], r)
+        np.testing.assert_allclose(out[c, :D], r["out"], rtol=rtol, atol=1e-300)
+        np.testing.assert_allclose(out[c, D], r["logL"], rtol=rtol)
+        np.testing.assert_allclose(out[c, D + 1], r["logP"], rtol=rtol, atol=1e-300)
+        moved += r["accepted"]
+        # (a) the recorded inputs follow from the Philox stream as the oracle restates it
+        pos = cidx
+        for s in range(r["steps"]):
+            pos = (pos + 1) % len(cyc)                                  # pre-increment, proposal.py:93
+            kind = int(cyc[pos])
+            exp = O.production_draw(seed, chain_base + c, s, kind, P, D, scale, flat_prior=flat)
+            got = draws[c, s]
+            assert got[0] == kind and list(got[1:4]) == exp[1:4], (c, s, got, exp)
+            if kind == O.EIGEN:
+                np.testing.assert_allclose(got[4], exp[4], rtol=0, atol=2e-5 * scale[int(got[1])])
+            else:
+                np.testing.assert_allclose(got[4:7], exp[4:7], rtol=0, atol=2e-5)
+            if kind == O.STRETCH:
+                np.testing.assert_allclose(got[7], exp[7], rtol=1e-12, atol=2e-6 * D)      # D * t * log 2 with t from the fp32 unit
+            else:
+                np.testing.assert_allclose(got[7], exp[7], rtol=1e-13)
+    assert moved > 0, "no chain moved: the test would not see the proposals"
+    return moved
+
+
+@pytest.mark.parametrize("name,lanes", [("gaussian2d", 1), ("gaussian10d", 4), ("gaussian10d", 8), ("gaussian10d", 16),
+                                        ("gaussian50d", 8), ("gaussian50d", 16), ("gaussian50d", 32)])
+@pytest.mark.parametrize("padded", [True, False])
+def test_production_mh_chain_equals_the_oracle_step_by_step(name, lanes, padded):
+    """iid Gaussian (the bench functor), every lane configuration the dispatcher can pick, with rows zero-padded to the
+    lane group (mask-free loop) and not (masked loop)."""
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model(name)
+    old = os.environ.pop("CPN_NO_ROW_PAD", None)
+    if not padded:
+        os.environ["CPN_NO_ROW_PAD"] = "1"
+    try:
+        with Engine(m.functor, m.bounds, nlive=64, maxmcmc=200, seed=1234) as e:
+            _check(m, e, lanes, np.random.RandomState(3 + lanes))
+    finally:
+        os.environ.pop("CPN_NO_ROW_PAD", None)
+        if old is not None:
+            os.environ["CPN_NO_ROW_PAD"] = old
+
+
+@pytest.mark.parametrize("name,lanes,spread", [("rosenbrock10d", 8, 0.25), ("rosenbrock10d", 16, 0.25), ("eggbox", 1, 0.9),
+                                               ("ring", 1, 0.6), ("ackley10d", 4, 0.5)])
+def test_production_mh_chain_other_functors(name, lanes, spread):
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model(name)
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=200, seed=1234) as e:
+        _check(m, e, lanes, np.random.RandomState(17), spread=spread)
+
+
+def test_production_mh_chain_nonflat_prior():
+    """(mean, sigma) model with the 1/sigma prior (tests/test_gaussian.py:15-20): the prior MH test is live for every
+    proposal kind (thr = log u)."""
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model("gaussian_mean_sigma")
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=200, seed=1234) as e:
+        _check(m, e, 1, np.random.RandomState(5), spread=0.8, flat=False)
+
+
+def test_production_mh_chain_correlated_gaussian():
+    """The D^2 functor (correlated flavour): likelihood evaluated only when a chain of the warp passed
+    the prior test (Model::kCheap = false path)."""
+    from cpnest_b200.engine import Engine
+    m = O.make_correlated_gaussian(12)
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=200, seed=1234, params=m.params) as e:
+        for lanes in (4, 16):
+            _check(m, e, lanes, np.random.RandomState(23), spread=0.1, rtol=1e-11)
+
+
+def test_production_mh_chain_long_cycle_and_immobile_chain():
+    """A proposal cycle longer than the inline table (device-memory path), and a chain that cannot move (threshold above
+    every reachable logL): it runs to maxmcmc with zero accepted steps (sampler.py:347)."""
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model("gaussian10d")
+    rs = np.random.RandomState(29)
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=64, seed=1234) as e:
+        ens, start, logLmin, w, v = _setup(m, 32, 4, rs, 0.3)
+        cyc = O.make_cycle(np.random.RandomState(2), cyclelength=300)
+        e.set_cycle(cyc)
+        for thr in (logLmin, 1e9):
+            out, steps, acc, evals, draws = e.trace_mh(ens, start, w, v, 7, 9, 64, thr, lanes=8, chain_base=5)
+            for c in range(4):
+                r = O.mh_chain_from_draws(m, ens, v, start[c, :10], start[c, 10], start[c, 11], draws[c], 9, 64, thr)
+                assert (steps[c], acc[c], evals[c]) == (r["steps"], r["accepted"], r["evals"])
+                np.testing.assert_allclose(out[c, :10], r["out"], rtol=1e-12, atol=1e-300)
+            if thr > 1e8:
+                assert (steps == 64).all() and (acc == 0).all()
+                pos = 7
+                for s in range(64):
+                    pos = (pos + 1) % 300
+                    assert draws[0, s, 0] == cyc[pos]
