@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcpnest_b200.so")
+# CPNEST_B200_LIB: an alternative build of the same library (kernel experiments, scripts/build_variant.py)
+LIB_PATH = os.environ.get("CPNEST_B200_LIB") or os.path.join(_HERE, "lib", "libcpnest_b200.so")
 
 
 class CpnError(RuntimeError):

@@ -198,8 +198,11 @@ static int dalloc(T** p, size_t n) {
     return 0;
 }
 
-static const int kCfgs[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {4, 4}, {8, 2}, {8, 8}, {16, 4},
-                                {32, 1}, {32, 2}, {32, 4}, {32, 8}};
+static const int kCfgs[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {4, 4},
+#ifdef CPN_EXP_G4E16
+                                {4, 16},
+#endif
+                                {8, 2}, {8, 8}, {16, 4}, {32, 1}, {32, 2}, {32, 4}, {32, 8}};
 static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
 // smallest E instantiated for G lanes that covers D coordinates; 0 if none

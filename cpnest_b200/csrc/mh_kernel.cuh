@@ -52,8 +52,11 @@ struct MHParams : ChainParams {
 template <bool B>
 struct BoolC { static constexpr bool value = B; };
 
+constexpr int kKindShift = 30;                         // ensemble sizes stay below 2^30
+constexpr uint32_t kIndexMask = (1u << kKindShift) - 1u;
+
 struct StepIn {
-    uint32_t i0, i1, i2;
+    uint32_t i0, i1, i2;      // i0 carries the proposal kind in its two top bits (kKindShift)
     uint32_t w3, w4, w5;      // WALK: c0, c1, c2 (fp32 bits); STRETCH: w3 = Z; DE: w3 = g; EIGEN: (w4, w5) = jump (fp64 bits)
     double thr;
 };
@@ -72,6 +75,24 @@ struct DrawFeed {
     // dump: where to record the 8 values of this step (test entry), or null
     __device__ __forceinline__ void refill(int kind, uint32_t step, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1,
                                            uint32_t ens_n, uint32_t D, const double* eig_scale, double* dump) {
+#ifdef CPN_EXP_CHEAP_REFILL
+        // experiment only: an upper bound on what taking the draws off the chain warps could gain
+        if (kind >= 0) {
+            uint32_t h = (cid_lo * 2654435761u) ^ (step * 40503u + 12345u);
+            h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+            const uint32_t i0 = u32_to_index(h, kind == CPN_EIGEN ? D : ens_n - 2);
+            const float gg = (float)(int)(h >> 8) * (1.0f / 8388608.0f) - 1.0f;
+            uint32_t w3 = __float_as_uint(kind == CPN_WALK ? gg : (kind == CPN_STRETCH ? 1.0f + 0.3f * gg : 1.0f + 1e-4f * gg));
+            uint32_t w4 = __float_as_uint(-0.5f * gg), w5 = w4;
+            if (kind == CPN_EIGEN) { const double jump = 0.05 * (double)gg; w4 = (uint32_t)__double2loint(jump); w5 = (uint32_t)__double2hiint(jump); }
+            const double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : -0.5;
+            __syncwarp();
+            row[0] = make_uint4(i0, i0 + 1, i0 + 2, w3);
+            row[1] = make_uint4(w4, w5, (uint32_t)__double2loint(thr), (uint32_t)__double2hiint(thr));
+            __syncwarp();
+            return;
+        }
+#endif
         const Philox4 r = philox4x32_10(cid_lo, cid_hi, step, 0u, k0, k1);
         double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : log(u32_to_unit_open(r.v[3]));
         uint32_t i0 = u32_to_index(r.v[0], kind == CPN_EIGEN ? D : ens_n);       // EIGEN: randrange(D), proposal.py:338
@@ -123,6 +144,7 @@ struct DrawFeed {
             }
             dump[7] = thr;
         }
+        i0 |= (uint32_t)kind << kKindShift;
         if (G == 1) {                       // a chain per lane: the step is this lane's own
             own.i0 = i0; own.i1 = i1; own.i2 = i2; own.w3 = w3; own.w4 = w4; own.w5 = w5; own.thr = thr;
             return;
@@ -143,24 +165,25 @@ struct DrawFeed {
     }
 };
 
-// The rows the step of kind `kind` gathers: WALK three members, DE two, STRETCH one, EIGEN one eigen-direction.
-// `kind` is uniform over the launch.  Every slot of a lane is loaded, also the slots beyond D of the last lanes, which
-// then read the head of the following row (the arrays carry kRowSlack doubles of slack at their end).  Those values are
-// finite and never used: the box test (+-inf bounds), the functors (valid_dim masks) and the final store ignore slots beyond D.
+// The rows a step gathers: WALK three members, DE two, STRETCH one, EIGEN one eigen-direction.  The kind is the same for
+// all chains of a launch.  Every slot of a lane is loaded, also the slots beyond D of the last lanes, which then read the
+// head of the following row (the arrays carry kRowSlack doubles of slack at their end).  Those values are finite and never
+// used: the box test (+-inf bounds), the functors (valid_dim masks) and the final store ignore slots beyond D.
 template <int G, int E>
-__device__ __forceinline__ void gather_rows(const Group<G>& g, const MHParams& p, int kind, const StepIn& s, double (&r0)[E],
-                                            double (&r1)[E], double (&r2)[E]) {
-    const unsigned Dp = (unsigned)p.Dp, lane = (unsigned)g.lane;
-    const double* b0 = (kind == CPN_EIGEN ? p.eig_vec : p.ens_x) + (s.i0 * Dp + lane);
+__device__ __forceinline__ void gather_rows(const Group<G>& g, const double* ens_x, const double* eig_vec, unsigned Dp,
+                                            const StepIn& s, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
+    const int kind = (int)(s.i0 >> kKindShift);
+    const unsigned lane = (unsigned)g.lane;
+    const double* b0 = (kind == CPN_EIGEN ? eig_vec : ens_x) + ((s.i0 & kIndexMask) * Dp + lane);
 #pragma unroll
     for (int e = 0; e < E; ++e) r0[e] = __ldg(b0 + e * G);
     if (kind == CPN_WALK || kind == CPN_DE) {
-        const double* b1 = p.ens_x + (s.i1 * Dp + lane);
+        const double* b1 = ens_x + (s.i1 * Dp + lane);
 #pragma unroll
         for (int e = 0; e < E; ++e) r1[e] = __ldg(b1 + e * G);
     }
     if (kind == CPN_WALK) {
-        const double* b2 = p.ens_x + (s.i2 * Dp + lane);
+        const double* b2 = ens_x + (s.i2 * Dp + lane);
 #pragma unroll
         for (int e = 0; e < E; ++e) r2[e] = __ldg(b2 + e * G);
     }
@@ -304,30 +327,35 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         feed.row = &feed_tab[threadIdx.x][0];
         const uint4* grow = &feed_tab[threadIdx.x & ~(G - 1)][0];        // row of this group's lane 0
         const bool cyc_inline = clen <= kCycInline;
-        auto kind_at = [&](int pos) -> int { return cyc_inline ? (int)p.cyc[pos] : (int)p.cycle[pos]; };
         double* dump = (p.draws != nullptr && valid) ? p.draws + (size_t)c * maxmcmc * 8 : nullptr;
-        // kind and inputs of step `it`; the inputs are drawn G steps at a time, one step per lane
-        auto next_in = [&](int it, int& kind) -> StepIn {
-            kind = kind_at(npos);
+        // the two row bases live in registers (opaque to the compiler, which would otherwise re-read them from the constant
+        // bank in front of every gather: a long-latency load on the in-order path of the step)
+        const double* ens_x = p.ens_x;
+        const double* eig_vec = p.eig_vec;
+        asm volatile("" : "+l"(ens_x), "+l"(eig_vec));
+        const unsigned Dp = (unsigned)p.Dp;
+        // The inputs of step `it` (its kind rides in the top bits of i0).  They are drawn G steps at a time, one step per
+        // lane, when the first step of a window is asked for; by then every lane holds the previous window in registers.
+        auto load_in = [&](int it) -> StepIn {
             if ((it & (G - 1)) == 0) {                                   // this lane prepares step it + lane
-                int lpos = npos + g.lane;                                // (npos + lane) % clen without the division
-                while (lpos >= clen) lpos -= clen;
                 const int st = it + g.lane;
-                feed.refill(kind_at(lpos), (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D, p.eig_scale,
+                const int lpos = (p.cycle_pos0 + 1 + st) % clen;           // pre-increment, proposal.py:93
+                const int kind = cyc_inline ? (int)p.cyc[lpos] : (int)p.cycle[lpos];
+                feed.refill(kind, (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D, p.eig_scale,
                             (dump != nullptr && st < maxmcmc) ? dump + (size_t)st * 8 : nullptr);
             }
-            npos = (npos + 1 == clen) ? 0 : npos + 1;
             return feed.get(grow + 2 * (it & (G - 1)));
         };
-        // One MCMC step of kind `kind` on (s, r0..r2); meanwhile the inputs of the following step are drawn and its rows
-        // gathered into (ns, n0..n2).  The caller alternates two such sets, so nothing is copied between steps.
+        // One MCMC step on (s, r0..r2).  The rows of the following step are gathered at its start into (n0..n2) from the
+        // inputs `ns`, which were read one step earlier; the inputs of the step after that replace `s` as soon as this step
+        // has no use for it any more.  The caller alternates two such sets, so nothing is copied between steps.
         // TAIL = false: no chain of the launch can stop at this step (fewer than min(Nmcmc, maxmcmc) steps done), so the
         // step carries no per-chain `active` state.
-        auto mcmc_step = [&](auto tail, int it, int kind, const StepIn& s, const double (&r0)[E], const double (&r1)[E],
-                             const double (&r2)[E], int& nkind, StepIn& ns, double (&n0)[E], double (&n1)[E], double (&n2)[E]) {
+        auto mcmc_step = [&](auto tail, int it, StepIn& s, const double (&r0)[E], const double (&r1)[E], const double (&r2)[E],
+                             const StepIn& ns, double (&n0)[E], double (&n1)[E], double (&n2)[E]) {
             constexpr bool TAIL = decltype(tail)::value;
-            ns = next_in(it + 1, nkind);
-            gather_rows<G, E>(g, p, nkind, ns, n0, n1, n2);
+            gather_rows<G, E>(g, ens_x, eig_vec, Dp, ns, n0, n1, n2);
+            const int kind = (int)(s.i0 >> kKindShift);
             double xn[E];
             if (kind == CPN_WALK) {                                         // old + sum_j c_j s_j, proposal.py:230-234
                 const double c0 = (double)__uint_as_float(s.w3), c1 = (double)__uint_as_float(s.w4), c2 = (double)__uint_as_float(s.w5);
@@ -346,6 +374,8 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
 #pragma unroll
                 for (int e = 0; e < E; ++e) xn[e] = fma(jump, r0[e], x[e]);
             }
+            const double thr = s.thr;
+            s = load_in(it + 2);
             // strict box test, model.py:33 (independent comparison chains: the FP64 compare has a long latency)
             bool in4[4] = {true, true, true, true};
 #pragma unroll
@@ -356,7 +386,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             const bool inb = g.all((in4[0] & in4[1]) & (in4[2] & in4[3]));
             double logP_new = Model::template log_prior<G, E>(g, xn, mm);
             logP_new = inb ? logP_new : CPN_NEG_INF;
-            bool pass = logP_new - logP > s.thr;                            // sampler.py:337
+            bool pass = logP_new - logP > thr;                              // sampler.py:337
             if (TAIL) pass = pass && active;
             if (Model::kCheap || __any_sync(FULL, pass)) {
                 const double logL_new = Model::template log_likelihood<G, E>(g, xn, mm);   // sampler.py:338
@@ -376,26 +406,26 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             }
         };
 
-        int ka, kb;
         StepIn sa, sb;
         double a0[E], a1[E], a2[E], b0[E], b1[E], b2[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) a0[e] = a1[e] = a2[e] = b0[e] = b1[e] = b2[e] = 0.0;
-        sa = next_in(0, ka);
-        gather_rows<G, E>(g, p, ka, sa, a0, a1, a2);
+        sa = load_in(0);
+        sb = load_in(1);
+        gather_rows<G, E>(g, ens_x, eig_vec, Dp, sa, a0, a1, a2);
         // a chain stops after step number n (counting from 1) if (n >= Nmcmc and it has moved) or n >= maxmcmc
         // (sampler.py:347): none does during the first min(Nmcmc, maxmcmc) - 1 steps
         const int n_main = max(0, min(nmcmc, maxmcmc) - 1) & ~1;
         int it = 0;
         for (; it < n_main; it += 2) {
-            mcmc_step(BoolC<false>{}, it, ka, sa, a0, a1, a2, kb, sb, b0, b1, b2);
-            mcmc_step(BoolC<false>{}, it + 1, kb, sb, b0, b1, b2, ka, sa, a0, a1, a2);
+            mcmc_step(BoolC<false>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
+            mcmc_step(BoolC<false>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
         }
         steps = n_main;
         for (; it < maxmcmc; it += 2) {
-            mcmc_step(BoolC<true>{}, it, ka, sa, a0, a1, a2, kb, sb, b0, b1, b2);
+            mcmc_step(BoolC<true>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
             if (!__any_sync(FULL, active)) break;
-            mcmc_step(BoolC<true>{}, it + 1, kb, sb, b0, b1, b2, ka, sa, a0, a1, a2);
+            mcmc_step(BoolC<true>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
             if (!__any_sync(FULL, active)) break;
         }
         };

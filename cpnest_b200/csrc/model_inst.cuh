@@ -9,7 +9,11 @@
 #include "hmc_kernel.cuh"
 #include "launch.h"
 
+#ifdef CPN_EXP_G4E16
+#define CPN_CONFIGS(X) X(1, 1) X(1, 2) X(1, 4) X(1, 8) X(4, 4) X(4, 16) X(8, 2) X(8, 8) X(16, 4) X(32, 1) X(32, 2) X(32, 4) X(32, 8)
+#else
 #define CPN_CONFIGS(X) X(1, 1) X(1, 2) X(1, 4) X(1, 8) X(4, 4) X(8, 2) X(8, 8) X(16, 4) X(32, 1) X(32, 2) X(32, 4) X(32, 8)
+#endif
 
 namespace cpn {
 
