@@ -442,7 +442,7 @@ extern "C" int cpn_create(const cpn_config* cfg, const double* lo, const double*
     const size_t nb = blob_bytes / sizeof(double);
     switch (cfg->functor) {
         case CPN_GAUSS_IID: if (nb != 3) return fail("gauss_iid blob must be {mu, 1/sigma, -log(sigma)-log(2pi)/2}"); break;
-        case CPN_GAUSS_CORR: if (nb != 1 + (size_t)cfg->dim * cfg->dim) return fail("gauss_corr blob must be {logdet, Linv[D*D]}"); break;
+        case CPN_GAUSS_CORR: if (nb != 1 + 2 * (size_t)cfg->dim * cfg->dim) return fail("gauss_corr blob must be {logdet, Linv[D*D], LinvT[D*D]}"); break;
         case CPN_RING: if (nb != 2 || cfg->dim != 2) return fail("ring needs dim=2 and blob {radius, thickness}"); break;
         case CPN_GAUSS_MEAN_SIGMA: if (cfg->dim != 2) return fail("gauss_mean_sigma needs dim=2"); break;
         case CPN_GAUSS_MIXTURE:
@@ -1617,9 +1617,10 @@ extern "C" int cpn_evolve_host(cpn_ctx* c, int32_t K, double logLmin, int32_t nm
         const int a = c->last_kb[k], b = c->last_kb[k + 1];
         if (b <= a) continue;
         k_batch_counters<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, k, a, b, c->d_new_steps, c->d_new_acc, c->d_new_evals);
-        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, k, b - a, nullptr, nullptr, 0);
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, k, 0, nullptr, nullptr, 0);      // folds the batch counters into the totals
+        k_adapt_nmcmc_on_the_fly<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, k, a, b, c->d_new_steps, c->d_new_acc);
         if (k == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, a, b, c->d_new_ne, c->d_new_nc);
-        c->launches += 2 + (k == CPN_SAMPLER_SLICE);
+        c->launches += 3 + (k == CPN_SAMPLER_SLICE);
     }
     if (slots) {
         CK(cudaMemcpyAsync(c->d_rank, slots, K * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -1695,9 +1696,10 @@ extern "C" int cpn_evolve_host_table(cpn_ctx* c, int32_t K, double logLmin, int3
         const int a = c->last_kb[k], b = c->last_kb[k + 1];
         if (b <= a) continue;
         k_batch_counters<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, k, a, b, c->d_new_steps, c->d_new_acc, c->d_new_evals);
-        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, k, b - a, nullptr, nullptr, 0);
+        k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, k, 0, nullptr, nullptr, 0);      // folds the batch counters into the totals
+        k_adapt_nmcmc_on_the_fly<<<1, kCorrThreads, 0, c->stream>>>(c->d_state, k, a, b, c->d_new_steps, c->d_new_acc);
         if (k == CPN_SAMPLER_SLICE) k_adapt_slice_mu<<<1, 256, 0, c->stream>>>(c->d_state, a, b, c->d_new_ne, c->d_new_nc);
-        c->launches += 2 + (k == CPN_SAMPLER_SLICE);
+        c->launches += 3 + (k == CPN_SAMPLER_SLICE);
     }
     k_pool_append<<<(K * Dp + T - 1) / T, T, 0, c->stream>>>(c->d_rank, K, c->N, Dp, c->d_new_x, c->d_new_logL, c->d_new_logP,
                                                           c->d_x, c->d_logL, c->d_logP);

@@ -14,6 +14,7 @@ namespace cpn {
 
 constexpr int kMHThreads = 128;   // threads per block of every chain kernel
 constexpr int kMaxPeers = 8;
+constexpr int kMaxResend = 15;     // attempts of a chain that cannot move before it gives up (NestedSampling.py:354-357 loops for ever)
 constexpr int kRowSlack = 256;    // doubles of slack behind row arrays the chain kernels gather from (mh_kernel.cuh gather_rows)
 
 enum StartMode { START_SURVIVOR = 0, START_SELF = 1, START_GIVEN = 2 };
@@ -144,6 +145,23 @@ struct Chain {
             bhi[e] = (d < p.D) ? __ldg(p.hi + d) : -CPN_NEG_INF;
         }
         return true;
+    }
+
+    // `NestedSampler.consume_sample` sends a point down the pipe again when the sampler's reply does not beat the threshold
+    // (cpnest/NestedSampling.py:354-357: `while not accepted: ... send(self.params[k])`), i.e. it asks for another sample
+    // until one arrives that does.  A device chain that made no accepted step hands back its start point, a copy of a live
+    // survivor; instead of returning it the chain starts again from another survivor (attempt a draws it from Philox block
+    // (chain, 2^32 - 1 - a, 0); the chain's step counter - and with it its random stream - keeps running).
+    // Only chains that draw their own start (START_SURVIVOR): a caller that supplies the start points (host protocol) sees
+    // `accepted == 0` in the reply and resends itself, as the reference does.
+    __device__ __forceinline__ bool can_restart(const ChainParams& p) const { return p.start_mode == START_SURVIVOR; }
+    __device__ __forceinline__ void restart(const ChainParams& p, int attempt) {
+        const Philox4 r = philox4x32_10(cid_lo, cid_hi, 0xffffffffu - (uint32_t)attempt, 0u, p.seed_lo, p.seed_hi);
+        const int slot = p.order[p.n_skip + (int)u32_to_index(r.v[0], (uint32_t)(p.ens_n - p.n_skip))];
+        start_slot = slot;
+        logL = p.ens_logL[slot];
+        logP = p.ens_logP[slot];
+        load_row<G, E>(g, p.ens_x + (size_t)slot * p.Dp, p.D, x);
     }
 
     // strict box test, model.py:33

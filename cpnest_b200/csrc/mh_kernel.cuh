@@ -330,6 +330,8 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         double* dump = (p.draws != nullptr && valid) ? p.draws + (size_t)c * maxmcmc * 8 : nullptr;
         // the two row bases live in registers (opaque to the compiler, which would otherwise re-read them from the constant
         // bank in front of every gather: a long-latency load on the in-order path of the step)
+        const int max_resend = ch.can_restart(p) ? kMaxResend : 0;
+        int attempts = 0, attempt_end = maxmcmc;
         const double* ens_x = p.ens_x;
         const double* eig_vec = p.eig_vec;
         asm volatile("" : "+l"(ens_x), "+l"(eig_vec));
@@ -402,7 +404,16 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             }
             if (TAIL) {
                 steps += active ? 1 : 0;
-                if ((steps >= nmcmc && accepted > 0) || steps >= maxmcmc) active = false;   // sampler.py:347
+                if (steps >= nmcmc && accepted > 0) active = false;         // sampler.py:347
+                else if (active && steps >= attempt_end) {                  // maxmcmc steps and no move
+                    if (attempts < max_resend) {                            // NestedSampling.py:354-357: another sample, please
+                        ++attempts;
+                        attempt_end += maxmcmc;
+                        ch.restart(p, attempts);
+                    } else {
+                        active = false;
+                    }
+                }
             }
         };
 
@@ -422,7 +433,8 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             mcmc_step(BoolC<false>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
         }
         steps = n_main;
-        for (; it < maxmcmc; it += 2) {
+        const int it_end = maxmcmc * (1 + max_resend);
+        for (; it < it_end; it += 2) {
             mcmc_step(BoolC<true>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
             if (!__any_sync(FULL, active)) break;
             mcmc_step(BoolC<true>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);

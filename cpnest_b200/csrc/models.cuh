@@ -110,63 +110,71 @@ struct GaussIid : FlatPrior {
 };
 
 // ---- correlated Gaussian N(0, Sigma), Sigma = L L^T: logL = -|L^-1 x|^2/2 - sum log L_ii - D/2 log 2pi
-//      (not in the reference).  blob = {logdet, Linv[D][D] row-major lower} -------
+//      (not in the reference).  blob = {logdet, Linv[D][D] row-major lower, LinvT[D][D]}: the second
+//      copy is the transpose, LinvT[c][r] = Linv[r][c] (zero for r < c), so that for a fixed column the lanes of a group,
+//      which own consecutive rows, read consecutive doubles -------
 struct GaussCorr : FlatPrior {
     static constexpr bool kScratch = true;
     static constexpr bool kCheap = false;
+    // y = Linv x as a group mat-vec: lane l owns the rows l + G e; the point is broadcast column by column through the
+    // chain's shared-memory scratch.  Columns are walked in blocks of G: in block b the slots e > b take every column,
+    // slot e == b meets the diagonal block (the zeros above the diagonal are stored), slots e < b are done - D(D+G)/2
+    // multiply-adds on E independent accumulators per lane instead of a dependent chain of D per row.
     template <int G, int E>
-    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+    static __device__ __forceinline__ void whiten(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&y)[E]) {
         const int D = m.D;
-        const double* Linv = m.blob + 1;
+        const double* Lt = m.blob + 1 + (size_t)D * D + g.lane;      // + c*D + G*e
+        __syncwarp();
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            int d = g.lane + e * G;
+            const int d = g.lane + e * G;
             if (d < D) m.scratch[d] = x[e];
+            y[e] = 0.0;
         }
         __syncwarp();
-        double acc = 0.0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int r = g.lane + e * G;
-            if (r < D) {
-                const double* row = Linv + (size_t)r * D;
-                double y = 0.0;
-                for (int c = 0; c <= r; ++c) y = fma(__ldg(row + c), m.scratch[c], y);
-                acc = fma(y, y, acc);
+        for (int b = 0; b < E; ++b) {
+            const int c1 = min(D, G * (b + 1));
+            for (int c = G * b; c < c1; ++c) {
+                const double xc = m.scratch[c];
+                const double* col = Lt + (size_t)c * D;
+#pragma unroll
+                for (int e = b; e < E; ++e)
+                    if (G * e < D) y[e] = fma((g.lane + G * e < D) ? __ldg(col + G * e) : 0.0, xc, y[e]);
             }
         }
         __syncwarp();
-        return -0.5 * g.sum(acc) - m.blob[0] - D * CPN_HALF_LOG_2PI;
     }
-    // grad = -Linv^T (Linv x); scratch holds x in [0, D) and y = Linv x in [Dp, Dp + D)
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        double y[E];
+        whiten<G, E>(g, x, m, y);
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc = fma(y[e], y[e], acc);
+        return -0.5 * g.sum(acc) - m.blob[0] - m.D * CPN_HALF_LOG_2PI;
+    }
+    // grad = -Linv^T (Linv x): the second product walks the rows of Linv^T = columns of Linv, again consecutive in the
+    // lanes when read from the row-major copy transposed, i.e. from Linv itself: (Linv^T y)_c = sum_{r >= c} Linv[r][c] y_r
     template <int G, int E>
     static __device__ __forceinline__ void grad_log_likelihood(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&gr)[E]) {
         const int D = m.D, Dp = (D + 3) & ~3;
         const double* Linv = m.blob + 1;
-        double* y = m.scratch + Dp;
+        double y[E];
+        whiten<G, E>(g, x, m, y);
+        double* ys = m.scratch + Dp;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            int d = g.lane + e * G;
-            if (d < D) m.scratch[d] = x[e];
+            const int d = g.lane + e * G;
+            if (d < D) ys[d] = y[e];
         }
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            int r = g.lane + e * G;
-            if (r < D) {
-                const double* row = Linv + (size_t)r * D;
-                double v = 0.0;
-                for (int c = 0; c <= r; ++c) v = fma(__ldg(row + c), m.scratch[c], v);
-                y[r] = v;
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int c = g.lane + e * G;
+            const int c = g.lane + e * G;
             double v = 0.0;
             if (c < D)
-                for (int r = c; r < D; ++r) v = fma(__ldg(Linv + (size_t)r * D + c), y[r], v);
+                for (int r = c; r < D; ++r) v = fma(__ldg(Linv + (size_t)r * D + c), ys[r], v);
             gr[e] = -v;
         }
         __syncwarp();

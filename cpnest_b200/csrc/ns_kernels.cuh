@@ -289,6 +289,59 @@ __global__ void __launch_bounds__(kCorrThreads) k_batch_counters(NSState* st, in
     block_batch_counters(st, kind, j0, j1, steps, acc, evals, shc);
 }
 
+// Sampler.estimate_nmcmc_on_the_fly (cpnest/sampler.py:156-176), the rule the reference applies after every chain of
+// its burn-in, here for the chains [j0, j1) of a batch in chain order, each with its own sub-acceptance a_j = accepted_j /
+// steps_j:   Nmcmc_exact <- min(maxmcmc, (1 - 1/tau) Nmcmc_exact + (safety/tau) (2/a_j - 1))      (a_j > 0)
+//            Nmcmc_exact <- min(maxmcmc, (1 + 1/tau) Nmcmc_exact)                                 (a_j = 0)
+// Every update is a map x -> min(m x + b, c) with m > 0, and such maps compose into one of the same form,
+//   (m2, b2, c2) o (m1, b1, c1) = (m2 m1, m2 b1 + b2, min(m2 c1 + b2, c2)),
+// so the K sequential updates are one ordered parallel reduction: each thread composes a run of consecutive chains, a
+// fixed-shape tree composes the runs in order.  Used where no start/end correlation is available (host protocol); the
+// result equals the sequential rule up to the rounding of the re-associated products (tests: 1e-12).
+struct ClampAffine {
+    double m, b, c;
+    __device__ __forceinline__ void then(const ClampAffine& g) {      // this := g o this
+        const double nb = fma(g.m, b, g.b);
+        c = fmin(fma(g.m, c, g.b), g.c);
+        m = g.m * m;
+        b = nb;
+    }
+};
+__global__ void __launch_bounds__(kCorrThreads) k_adapt_nmcmc_on_the_fly(NSState* st, int kind, int j0, int j1, const int* steps,
+                                                                         const int* acc) {
+    if (st->done) return;
+    __shared__ ClampAffine sh[kCorrThreads];
+    const int tid = threadIdx.x, n = j1 - j0;
+    const double tau = st->nmcmc_tau, safety = st->nmcmc_safety, M = (double)st->maxmcmc;
+    const int per = (n + kCorrThreads - 1) / kCorrThreads;
+    ClampAffine f = {1.0, 0.0, INFINITY};
+    for (int j = j0 + tid * per; j < min(j1, j0 + (tid + 1) * per); ++j) {
+        ClampAffine u;
+        if (acc[j] == 0) u = {1.0 + 1.0 / tau, 0.0, M};
+        else u = {1.0 - 1.0 / tau, (safety / tau) * (2.0 / ((double)acc[j] / (double)steps[j]) - 1.0), M};
+        f.then(u);
+    }
+    sh[tid] = f;
+    __syncthreads();
+    for (int w = 1; w < kCorrThreads; w <<= 1) {          // ordered tree: sh[i] := sh[i + w] o sh[i]
+        if ((tid & (2 * w - 1)) == 0) {
+            ClampAffine a = sh[tid];
+            a.then(sh[tid + w]);
+            sh[tid] = a;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && n > 0 && st->adapt) {
+        KindCtl& k = st->ctl[kind];
+        const ClampAffine t = sh[0];
+        const double ne = fmin(fma(t.m, k.nmcmc_exact, t.b), t.c);
+        k.nmcmc_exact = ne;
+        int nn = (int)ne;
+        if (nn < (int)safety) nn = (int)safety;                      // max(safety, int(Nmcmc_exact))
+        k.nmcmc = nn;
+    }
+}
+
 // SliceSampler.adapt_length_scale (sampler.py:429-437): mu *= 2 Ne / (Ne + Nc).  The reference applies it per
 // chain with the counts of that chain's last slice, during its first 10*poolsize slices; here the counts of
 // ALL slices of the batch are pooled (integer sums: independent of order and of the split over GPUs), which

@@ -25,7 +25,8 @@ def functor_blob(name, dim, params=None):
     if name == "gaussian_corr":
         Linv = np.asarray(params["Linv"], dtype=np.float64)
         assert Linv.shape == (dim, dim)
-        return np.concatenate(([float(params["logdet"])], np.tril(Linv).ravel()))
+        Linv = np.tril(Linv)
+        return np.concatenate(([float(params["logdet"])], Linv.ravel(), np.ascontiguousarray(Linv.T).ravel()))
     if name == "ring":
         return np.array([float(params.get("radius", 1.0)), float(params.get("thickness", 0.1))])
     if name == "gaussian_mixture":

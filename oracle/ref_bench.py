@@ -234,3 +234,113 @@ if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(HERE))
     print(json.dumps(time_reference(budget_s=float(sys.argv[1]) if len(sys.argv) > 1 else 5.0,
                                     force_port="--port" in sys.argv), indent=1))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The stock path: the UNMODIFIED reference run through its own public API, `cpnest.CPNest(model, nlive, nthreads=cores,
+# ...).run()` (cpnest/cpnest.py:103-316), in a child process group, observed from outside for a bounded time
+# (SURVEY.md 8d "CPU reference timing": wall clock around run(), likelihood evaluations counted by a wrapper model that
+# bumps a multiprocessing.Value every 1000 calls).  MCMC steps are counted the same way through log_prior, which the MH
+# sampler calls once per step (cpnest/sampler.py:335).
+# ----------------------------------------------------------------------------------------------------------------
+def _stock_child(dim, nlive, nthreads, maxmcmc, poolsize, seed, n_evals, n_steps, outdir):
+    os.setsid()                                     # own process group: the parent stops exactly this group
+    devnull = open(os.devnull, "w")
+    os.dup2(devnull.fileno(), 1)
+    os.dup2(devnull.fileno(), 2)
+    sys.path.insert(0, REF)
+    import cpnest
+    import cpnest.model
+
+    class GaussianModel(cpnest.model.Model):
+        # the model of examples/test_50d.py:5-28, restated (the GPU box has no /root/reference)
+        _e = 0
+        _s = 0
+
+        def __init__(self, dim):
+            self.names = ['{0}'.format(i) for i in range(dim)]
+            self.bounds = [[-10, 10] for _ in range(dim)]
+
+        def log_likelihood(self, p):
+            GaussianModel._e += 1
+            if GaussianModel._e == 1000:
+                GaussianModel._e = 0
+                with n_evals.get_lock():
+                    n_evals.value += 1000
+            return np.sum([-0.5 * p[n] ** 2 - 0.5 * np.log(2.0 * np.pi) for n in p.names])
+
+        def log_prior(self, p):
+            GaussianModel._s += 1
+            if GaussianModel._s == 1000:
+                GaussianModel._s = 0
+                with n_steps.get_lock():
+                    n_steps.value += 1000
+            return super(GaussianModel, self).log_prior(p)
+
+    work = cpnest.CPNest(GaussianModel(dim), verbose=2, nthreads=nthreads, nlive=nlive, maxmcmc=maxmcmc, poolsize=poolsize,
+                         seed=seed, output=outdir)
+    work.run()
+
+
+class StockReferenceRun(object):
+    """cpnest.CPNest(...).run() of the unmodified reference in a child process group; progress() reads the counters and the
+    last iteration line of its cpnest.log (NestedSampling.py:360)."""
+
+    def __init__(self, dim=50, nlive=10000, cores=None, maxmcmc=5000, poolsize=1000, seed=1234):
+        import tempfile
+        if not reference_available():
+            raise RuntimeError("oracle/_ref is absent")
+        self.cores = cores or os.cpu_count() or 1
+        self.args = dict(dim=dim, nlive=nlive, nthreads=self.cores, maxmcmc=maxmcmc, poolsize=poolsize, seed=seed)
+        ctx = mp.get_context("fork")
+        self.n_evals = ctx.Value("q", 0)
+        self.n_steps = ctx.Value("q", 0)
+        self.outdir = tempfile.mkdtemp(prefix="cpnest_ref_")
+        self.proc = ctx.Process(target=_stock_child, args=(dim, nlive, self.cores, maxmcmc, poolsize, seed, self.n_evals,
+                                                           self.n_steps, self.outdir))
+        self.t0 = time.perf_counter()
+        self.proc.start()
+
+    def counts(self):
+        return self.n_evals.value, self.n_steps.value, time.perf_counter()
+
+    def progress(self):
+        """(NS iteration, Nmcmc, logZ) from the last progress line of cpnest.log, or None before the first one."""
+        import re
+        try:
+            with open(os.path.join(self.outdir, "cpnest.log"), "rb") as f:
+                f.seek(0, 2)
+                f.seek(max(0, f.tell() - 4096))
+                tail = f.read().decode(errors="replace")
+        except OSError:
+            return None
+        m = re.findall(r"(\d+): n:\s*(\d+) NS_acc:([\d.]+) .*? logZ: (\S+) logLmax", tail)
+        if not m:
+            return None
+        it, n, acc, z = m[-1]
+        return dict(iteration=int(it), nmcmc=int(n), ns_acceptance=float(acc), logZ=float(z))
+
+    def alive(self):
+        return self.proc.is_alive()
+
+    def wait_ready(self, timeout_s=240.0):
+        """until the nested-sampling loop is running (first progress line); False if the run ended or timed out first"""
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout_s:
+            if self.progress() is not None:
+                return True
+            if not self.alive():
+                return False
+            time.sleep(0.5)
+        return False
+
+    def stop(self):
+        import shutil
+        import signal
+        if self.proc.pid is not None and self.proc.is_alive():
+            try:
+                os.killpg(self.proc.pid, signal.SIGKILL)     # the group created by os.setsid() in the child
+            except (ProcessLookupError, PermissionError):
+                pass
+        self.proc.join(timeout=10)
+        shutil.rmtree(self.outdir, ignore_errors=True)

@@ -49,6 +49,15 @@ if 3 in which:
 if 4 in which:
     run("4: 50-D Gaussian (examples/test_50d.py), nlive=1e5, MH (EnsembleEigenVector in the default cycle)", "gaussian_iid", [[-10, 10]] * 50, 100000,
         WAVE, "mh", 5000, anchor=-50 * math.log(20))
+if 7 in which:
+    # config 4, correlated flavour: Sigma = A A^T, condition number 1e2; the D^2 likelihood
+    sys.path.insert(0, ".")
+    from oracle import cpnest_oracle as O          # (scripts/ is measurement tooling, not the product)
+    m = O.make_correlated_gaussian(50)
+    run("4c: 50-D correlated Gaussian (Sigma = A A^T, cond 1e2), nlive=1e5, MH", "gaussian_corr", m.bounds, 100000, WAVE, "mh", 5000,
+        anchor=-50 * math.log(20), params=m.params)
+    run("4c': 50-D correlated Gaussian, nlive=1e4, MH", "gaussian_corr", m.bounds, 10000, WAVE, "mh", 5000,
+        anchor=-50 * math.log(20), params=m.params)
 if 5 in which:
     # BASELINE's "20-D Gaussian mixture, HMC": the reference has no such model (examples/gaussianmixture.py is 5-D over
     # a data vector); the parameter-space mixture below is the stated stand-in, Z = 1/volume(box)

@@ -139,7 +139,33 @@ def test_full_size_invariants_50d_nlive_1e4():
         assert s["total_evals"] <= s["total_steps"] and s["total_accepted"] <= s["total_evals"]
         # the union of live and dead points holds every point exactly once (no slot lost in the merge)
         allp = np.concatenate((live, dead))
-        assert len(np.unique(allp[:, :3], axis=0)) == len(allp) - s["failed_chains"] or s["failed_chains"] > 0
+        assert s["failed_chains"] == 0
+        assert len(np.unique(allp[:, :3], axis=0)) == len(allp)
+
+
+def test_chain_that_cannot_move_is_sent_again_instead_of_returning_a_survivor():
+    """`consume_sample` asks again until the reply beats the threshold (cpnest/NestedSampling.py:354-357).  With maxmcmc = 3
+    a good part of the chains makes no accepted step in one attempt; each of them starts again from another survivor, so no
+    reply is the copy of a live point and no chain is reported as failed."""
+    from cpnest_b200.engine import Engine
+    N, K = 2000, 512
+    with Engine("gaussian_iid", [[-10, 10]] * 10, nlive=N, maxmcmc=3, nmcmc_init=3, adapt_nmcmc=False, seed=11) as e:
+        e.set_cycle(O.make_cycle(np.random.RandomState(5)))
+        e.init_prior()
+        longest = 0
+        for b in range(12):
+            e.ns_step(K)
+            rows, steps, acc = e.last_batch(K)
+            assert np.all(acc > 0)
+            assert np.all(rows[:, 10] > e.state()["logLmin"])
+            longest = max(longest, int(steps.max()))
+        s = e.state()
+        assert longest > 3, "no chain needed a second attempt: the test does not exercise the rule"
+        assert s["failed_chains"] == 0
+        allp = np.concatenate((e.live(), e.dead()))
+        assert len(np.unique(allp[:, :3], axis=0)) == len(allp)
+        # without the rule about a fifth of the chains of this set-up would have handed back a copy of their start point
+        assert s["total_steps"] > 12 * K * 3
 
 
 def test_checkpoint_resume_continues_bit_identically():
@@ -202,3 +228,19 @@ def test_zero_padded_rows_give_the_same_run_bit_for_bit(dim, lanes, monkeypatch)
     monkeypatch.setenv("CPN_NO_ROW_PAD", "1")
     plain = run()
     assert padded == plain
+
+
+def test_correlated_gaussian_50d_logz():
+    """BASELINE config 4, correlated flavour: N(0, Sigma), Sigma = A A^T with condition number 1e2 well inside the
+    box, so logZ stays -50 log 20 = -149.786614.  The one analytic config whose likelihood (D^2 + 3D = 2650 flops) can be
+    FP64 bound; the D x D group mat-vec of the functor is checked against numpy on the way."""
+    m = O.make_correlated_gaussian(50)
+    e, s, logz, ins, nb = run_ns(m.functor, m.bounds, nlive=2000, K=500, maxmcmc=5000, params=m.params, seed=21)
+    with e:
+        check_logz(s, logz, -50 * math.log(20.0), 2000)
+        assert 110 < s["info"] < 165, s["info"]        # H = 79 + sum_i -log(sigma_i) = 79 + 57.6 nats
+        assert stats.kstest(ins[-8000:], "uniform").pvalue > 1e-3
+        dead = e.dead()
+        ref = np.array([m.log_likelihood(x) for x in dead[-200:, :50]])
+        assert np.allclose(dead[-200:, 50], ref, rtol=1e-11, atol=0)
+        assert s["failed_chains"] == 0

@@ -36,11 +36,13 @@ def test_sizes_and_dimensions(sampler):
     _run("rosenbrock", 7, 100, 25, sampler, bound=5.0)     # neighbour shuffles across an odd dimension
 
 
-def test_chains_that_cannot_move_return_their_start():
-    """maxmcmc = 1 with a sharp constraint: most chains fail; the batch step must stay consistent (the reference
-    resends such points, NestedSampling.py:354-357; here they return a copy of their start point and are counted)."""
+def test_chains_that_cannot_move_are_sent_again():
+    """maxmcmc = 1 with a sharp constraint: most chains make no move in one attempt.  The reference resends such points
+    (NestedSampling.py:354-357); the device chain starts again from another survivor, up to 15 times, so a batch of 50
+    costs many more than 50 steps; the few chains that fail every attempt hand back a copy of a survivor and are counted."""
     s = _run("gaussian_iid", 20, 200, 50, "mh", maxmcmc=1, nbatches=10)
-    assert s["failed_chains"] > 0 and s["total_steps"] == 10 * 50
+    assert 10 * 50 < s["total_steps"] <= 16 * 10 * 50
+    assert s["failed_chains"] < 0.2 * 10 * 50
 
 
 def test_bad_arguments_fail_loudly():
@@ -63,27 +65,32 @@ def test_bad_arguments_fail_loudly():
 
 
 def test_large_batches_are_ranked_in_segments_with_ties():
-    """K > 8192 replacements are ranked by segment-wise counting + merge (csrc/ns_kernels.cuh k_rank_*_seg).  maxmcmc = 1
-    makes many chains return a copy of their start point, so equal keys occur inside and across segments: the merged
-    order must still be a sorted permutation of the live set, and no point may be lost."""
+    """K > 8192 replacements are ranked by segment-wise counting + merge (csrc/ns_kernels.cuh k_rank_*_seg).  The replies
+    are scripted (cpn_stage_replacements) as copies of survivors, each used several times, so equal keys occur inside and
+    across segments: the merged order must still be a sorted permutation of the live set, and no point may be lost."""
     from cpnest_b200.engine import Engine
     N, K, D = 20000, 10000, 3
+    rs = np.random.RandomState(4)
     with Engine("gaussian_iid", [[-10, 10]] * D, nlive=N, maxmcmc=1, seed=2) as e:
         e.init_prior()
-        before = e.live()
         for b in range(4):
-            e.ns_step(K)
-            live, dead = e.live(), e.dead()
-            assert np.all(np.diff(live[:, D]) >= 0) and np.all(np.diff(dead[:, D]) >= 0)
-            assert len(dead) == (b + 1) * K and dead[-1, D] <= live[0, D]
-            logL, _ = e.eval_model(live[:, :D])
-            assert np.allclose(logL, live[:, D], rtol=1e-12, atol=1e-12)
-        s = e.state()
-        assert s["failed_chains"] > 1000
+            live = e.live()
+            surv = live[K:]
+            reps = surv[rs.randint(0, 300, size=K) * 7 % len(surv)]          # 300 distinct rows for 10000 replies
+            e.select_and_accumulate(K)
+            e.stage_replacements(reps)
+            e.insert_batch(K)
+            new_live, dead = e.live(), e.dead()
+            assert np.all(np.diff(new_live[:, D]) >= 0) and np.all(np.diff(dead[:, D]) >= 0)
+            assert len(dead) == (b + 1) * K and dead[-1, D] <= new_live[0, D]
+            # the new live set is exactly survivors + replies, as a multiset
+            want = np.sort(np.concatenate((surv[:, D], reps[:, D])))
+            assert np.array_equal(new_live[:, D], want)
+            assert np.array_equal(dead[b * K:], live[:K])
+            logL, _ = e.eval_model(new_live[:, :D])
+            assert np.allclose(logL, new_live[:, D], rtol=1e-12, atol=1e-12)
         ins = e.insertion_indices()
         assert len(ins) == 4 * K and ins.min() >= 0 and ins.max() <= 1
-    # the same run with K below the segment threshold must agree on the first batch's threshold
-    assert before.shape == (N, D + 2)
 
 
 def test_host_table_protocol_equals_the_buffer_protocol():

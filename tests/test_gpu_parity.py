@@ -341,3 +341,32 @@ def test_ns_batch_loop_sequential_mode_vs_oracle():
         rows, lv = e.dead(log_vols=True)
         assert rows[:, 2].tolist() == ns.nested_logL
         assert rel_close(lv, ns.state.log_vols[1:], RTOL)
+
+
+def test_device_chain_length_rule_equals_estimate_nmcmc_on_the_fly():
+    """Sampler.estimate_nmcmc_on_the_fly (cpnest/sampler.py:156-176) - the moving average of safety * (2/acc - 1) the reference
+    applies chain after chain - against the device controller of the host protocol (k_adapt_nmcmc_on_the_fly: the K sequential
+    updates of a batch as one ordered reduction of clamped affine maps), including chains that made no move (acc = 0)."""
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model("gaussian10d")
+    N, K, maxmcmc = 256, 200, 60
+    rs = np.random.RandomState(8)
+    with Engine(m.functor, m.bounds, nlive=N, maxmcmc=maxmcmc, nmcmc_init=20, nmcmc_safety=5.0, adapt_nmcmc=True, seed=5) as e:
+        e.set_cycle(O.make_cycle(np.random.RandomState(5)))
+        e.init_prior()
+        live = e.live()
+        ne = e.state()["nmcmc_exact"]
+        saw_immobile = False
+        for q in (0.3, 0.6, 0.97, 0.5):
+            logLmin = float(np.quantile(live[:, 10], q))
+            good = np.where(live[:, 10] > logLmin)[0]
+            req = np.ascontiguousarray(live[good[rs.randint(0, len(good), size=K)]])
+            n_chain = e.state()["nmcmc"]
+            _, steps, acc = e.evolve_host(req, logLmin, n_chain)
+            for j in range(K):
+                ne, n = O.estimate_nmcmc_on_the_fly(ne, acc[j] / steps[j], maxmcmc, poolsize=N, safety=5.0)
+            saw_immobile |= bool((acc == 0).any())
+            s = e.state()
+            assert rel_close(s["nmcmc_exact"], ne, rtol=1e-12), (s["nmcmc_exact"], ne)
+            assert s["nmcmc"] == n
+        assert saw_immobile, "no chain without a move: the acc = 0 branch was not exercised"
