@@ -316,9 +316,9 @@ def main():
     else:
         N, K = args.nlive, args.k
 
-    def make_engine(seed, n=None, rk=rank, ws=world):
-        e = Engine(functor, bounds, nlive=n or N, maxmcmc=MAXMCMC, seed=seed, device=local_rank, lanes=args.lanes, rank=rk,
-                   world_size=ws, params=fparams, sampler=sampler)
+    def make_engine(seed, n=None, rk=rank, ws=world, lanes=None):
+        e = Engine(functor, bounds, nlive=n or N, maxmcmc=MAXMCMC, seed=seed, device=local_rank, lanes=args.lanes if lanes is None else lanes,
+                   rank=rk, world_size=ws, params=fparams, sampler=sampler)
         e.set_stream(stream.cuda_stream)
         e.set_cycle(cycle)
         return e
@@ -500,7 +500,12 @@ def main():
     replicas_identical = None
     if world > 1:
         NB = 6
-        e_sh = make_engine(SEED + 5)
+        # same lanes per chain in both (the likelihood sum is reduced over them: its rounding depends on their number; a
+        # single GPU with all K chains would by itself pick narrower groups than a rank with K / world chains)
+        probe = make_engine(SEED + 5)
+        lanes_eq = probe.pick_lanes(K // world)[0]
+        probe.close()
+        e_sh = make_engine(SEED + 5, lanes=lanes_eq)
         d_sh = make_driver(e_sh)
         e_sh.init_prior()
         for _ in range(NB):
@@ -513,7 +518,7 @@ def main():
         dist.all_gather_object(hs, h_sh)
         replicas_identical = len(set(hs)) == 1
         if rank == 0:
-            e_1 = make_engine(SEED + 5, rk=0, ws=1)      # all K chains of every batch on one GPU
+            e_1 = make_engine(SEED + 5, rk=0, ws=1, lanes=lanes_eq)      # all K chains of every batch on one GPU
             e_1.init_prior()
             for _ in range(NB):
                 e_1.ns_step(K)

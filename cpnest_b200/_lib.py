@@ -107,6 +107,7 @@ SIGNATURES = {
     "cpn_host_scatter_rows": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp]),
     "cpn_set_stream": (C.c_int, [_vp, _vp]),
     "cpn_launch_count": (C.c_int64, [_vp]),
+    "cpn_pick_lanes": (C.c_int, [_vp, C.c_int32, _ip, _ip]),
     "cpn_eval_model": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "cpn_eval_gradients": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "cpn_replay_mh": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.c_int32, _dp, C.c_int32,

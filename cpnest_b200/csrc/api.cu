@@ -1437,6 +1437,15 @@ extern "C" int cpn_set_stream(cpn_ctx* c, void* stream) {
 
 extern "C" int64_t cpn_launch_count(cpn_ctx* c) { return c ? c->launches : -1; }
 
+extern "C" int cpn_pick_lanes(cpn_ctx* c, int32_t chains, int32_t* lanes, int32_t* per_lane) {
+    if (!c || !lanes || chains < 1) return fail("bad argument");
+    int G, E;
+    if (pick_config(c->D, c->cfg.lanes, c->cfg.functor, chains, &G, &E)) return 1;
+    *lanes = G;
+    if (per_lane) *per_lane = E;
+    return 0;
+}
+
 extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
     if (!c || !o) return fail("null argument");
     CK(cudaSetDevice(c->cfg.device));

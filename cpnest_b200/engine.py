@@ -205,6 +205,12 @@ class Engine:
     def set_stream(self, cuda_stream):
         L.check(self.lib.cpn_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
+    def pick_lanes(self, chains):
+        """(lanes per chain, coordinates per lane) of a launch of `chains` chains (cpn_pick_lanes)."""
+        g, e = C.c_int32(), C.c_int32()
+        L.check(self.lib.cpn_pick_lanes(self.h, int(chains), C.byref(g), C.byref(e)))
+        return g.value, e.value
+
     def launch_count(self):
         return self.lib.cpn_launch_count(self.h)
 

@@ -205,6 +205,10 @@ int cpn_synchronize(cpn_ctx* ctx);
 int cpn_set_stream(cpn_ctx* ctx, void* cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t cpn_launch_count(cpn_ctx* ctx);
+/* Lanes per chain (and coordinates per lane) a launch of `chains` chains uses when cpn_config.lanes == 0.  The likelihood sum is
+ * reduced over the lanes of a chain, so its rounding - not the random stream - depends on this number: two runs agree bit
+ * for bit only if they use the same one (a sharded run launches K / world_size chains per GPU, a single GPU all K). */
+int cpn_pick_lanes(cpn_ctx* ctx, int32_t chains, int32_t* lanes, int32_t* per_lane);
 int cpn_get_state(cpn_ctx* ctx, cpn_state* out);
 int cpn_set_nmcmc(cpn_ctx* ctx, int32_t nmcmc);
 /* NestedSampler(stopping=) (cpnest/NestedSampling.py:229,250) */
