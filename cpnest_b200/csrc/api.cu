@@ -82,8 +82,11 @@ struct cpn_ctx {
     double *d_new_x, *d_new_logL, *d_new_logP;
     int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_new_ne, *d_new_nc, *d_rank;
     double *d_rho, *d_rho2;
+    double* d_corr_part;            // partial moments of k_chain_corr_partial, [D+2][segments][5]
+    size_t corr_part_cap;
     double* d_snew;
-    double* d_seg_sorted;           // large batches: the replacements sorted inside segments of kRankSeg keys
+    int* d_bucket;                  // ranking of the replacements: bucket histogram / starts [N+1], cursors [N+1], members [N]
+    int* d_nle;                     // [N] #(survivors <= key) of every replacement
     double *d_start_x, *d_start_logL, *d_start_logP;
     double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
     // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
@@ -535,7 +538,9 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
     if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
     if (dalloc(&c->d_rho, kNumKinds * (D + 1)) || dalloc(&c->d_rho2, kNumKinds * (D + 1)) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
-    if (dalloc(&c->d_seg_sorted, (size_t)((N + kRankSeg - 1) / kRankSeg) * kRankSeg)) return 1;
+    if (dalloc(&c->d_bucket, 3 * (size_t)(N + 1)) || dalloc(&c->d_nle, N)) return 1;
+    c->corr_part_cap = (size_t)(D + 2) * ((N + kCorrSeg - 1) / kCorrSeg + 1) * 5;
+    if (dalloc(&c->d_corr_part, c->corr_part_cap)) return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
@@ -598,7 +603,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->acc_stream) cudaStreamSynchronize(c->acc_stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
-                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_seg_sorted, c->d_start_x, c->d_start_logL,
+                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_bucket, c->d_nle, c->d_corr_part, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
@@ -923,6 +928,19 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
     return rc;
 }
 
+// start/end correlation + batch counters of the chains [j0, j1) of kind `kind` (ns_kernels.cuh), on stream `cs`
+static int launch_chain_corr(cpn_ctx* c, cudaStream_t cs, int kind, int j0, int j1, double* rho) {
+    const int nseg = std::max(1, (j1 - j0 + kCorrSeg - 1) / kCorrSeg);
+    const size_t need = (size_t)(c->D + 2) * nseg * 5;
+    if (need > c->corr_part_cap) return fail("chain statistics: %zu partial sums exceed the scratch of %zu", need, c->corr_part_cap);
+    k_chain_corr_partial<<<dim3(c->D + 2, nseg), kCorrThreads, 0, cs>>>(c->d_state, j0, j1, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
+                                                                      c->d_new_x, c->d_new_logL, c->d_new_steps, c->d_new_acc,
+                                                                      c->d_new_evals, c->d_corr_part);
+    k_chain_corr_final<<<(c->D + 2 + 127) / 128, 128, 0, cs>>>(c->d_state, kind, j1 - j0, c->D, nseg, c->d_corr_part, rho);
+    c->launches += 2;
+    return 0;
+}
+
 extern "C" int cpn_init_prior(cpn_ctx* c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));
@@ -961,14 +979,12 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         if (run_mh(c, G, E, 0, p)) return 1;
         CKL();
         // the burn-in chains (always MH) run under the primary kind's controller
-        k_chain_corr<<<c->D + 2, kCorrThreads, 0, c->stream>>>(c->d_state, c->primary, 0, c->N, c->D, c->Dp, c->d_new_start, c->d_x,
-                                                      c->d_logL, c->d_new_x, c->d_new_logL, c->d_rho, c->d_new_steps, c->d_new_acc,
-                                                      c->d_new_evals);
+        if (launch_chain_corr(c, c->stream, c->primary, 0, c->N, c->d_rho)) return 1;
         k_adapt_nmcmc<<<1, 1, 0, c->stream>>>(c->d_state, c->primary, c->N, c->d_rho, c->d_rho2, c->D);   // coordinates only: logL is unconstrained here
         CK(cudaMemcpyAsync(c->d_x, c->d_new_x, (size_t)c->N * c->Dp * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logL, c->d_new_logL, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_logP, c->d_new_logP, c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        c->launches += 3;
+        c->launches += 1;
         std::vector<double> rho(c->D);
         CK(cudaMemcpyAsync(rho.data(), c->d_rho, c->D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -1157,10 +1173,8 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         CK(cudaStreamWaitEvent(cs, c->ev_ins, 0));
         for (int k = 0; k < kNumKinds; ++k) {
             if (kb[k + 1] <= kb[k]) continue;
-            k_chain_corr<<<c->D + 2, kCorrThreads, 0, cs>>>(c->d_state, k, kb[k], kb[k + 1], c->D, c->Dp, c->d_new_start, c->d_x,
-                                                          c->d_logL, c->d_new_x, c->d_new_logL, c->d_rho + k * (c->D + 1),
-                                                          c->d_new_steps, c->d_new_acc, c->d_new_evals);
-            c->launches += 1;
+            // (the kinds' statistics share one scratch: they run one after the other on this stream)
+            if (launch_chain_corr(c, cs, k, kb[k], kb[k + 1], c->d_rho + k * (c->D + 1))) return 1;
             if (k == CPN_SAMPLER_SLICE) {
                 k_adapt_slice_mu<<<1, 256, 0, cs>>>(c->d_state, kb[k], kb[k + 1], c->d_new_ne, c->d_new_nc);
                 c->launches += 1;
@@ -1171,20 +1185,19 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         }
         CK(cudaEventRecord(c->ev_corr, cs));
     }
-    CK(cudaMemsetAsync(c->d_rank, 0, (size_t)K * sizeof(int), c->stream));
-    if (K <= 2 * kRankSeg) {
-        // K^2 comparisons over a 2-D grid
-        const int nt = (K + kRankTile - 1) / kRankTile;
-        k_rank_count<<<dim3(nt, nt), kRankTile, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank);
-        k_rank_scatter<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_snew);
-        c->launches += 2;
-    } else {
-        // segments of kRankSeg keys ranked by counting, then merged by binary search
-        const int nt = kRankSeg / kRankTile, nseg = (K + kRankSeg - 1) / kRankSeg;
-        k_rank_count_seg<<<dim3(nt, nt, nseg), kRankTile, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank);
-        k_rank_seg_sorted<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_rank, c->d_seg_sorted);
-        k_rank_merge_seg<<<(K + T - 1) / T, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_seg_sorted, c->d_rank, c->d_snew);
-        c->launches += 3;
+    // rank of every replacement among the replacements: buckets between the sorted survivors (ns_kernels.cuh)
+    {
+        const int ns = c->N - K, nb = ns + 1;
+        int* hist = c->d_bucket;                    // [nb] histogram -> bucket starts
+        int* cursor = c->d_bucket + c->N + 1;       // [nb]
+        int* members = c->d_bucket + 2 * (c->N + 1);   // [K]
+        CK(cudaMemsetAsync(c->d_bucket, 0, 2 * (size_t)(c->N + 1) * sizeof(int), c->stream));
+        const int gb = (K + T - 1) / T;
+        k_rank_bucket<<<gb, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_skeys[c->cur] + K, ns, c->d_nle, hist);
+        k_rank_scan<<<1, kScanThreads, 0, c->stream>>>(c->d_state, hist, nb);
+        k_rank_fill<<<gb, T, 0, c->stream>>>(c->d_state, K, c->d_nle, hist, cursor, members);
+        k_rank_final<<<gb, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_nle, hist, cursor, members, c->d_rank, c->d_snew);
+        c->launches += 4;
     }
     MergeParams m;
     memset(&m, 0, sizeof m);
@@ -1195,7 +1208,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     c->staged_external = false;
     m.order_in = c->d_order[c->cur]; m.skeys_in = c->d_skeys[c->cur];
     m.order_out = c->d_order[c->cur ^ 1]; m.skeys_out = c->d_skeys[c->cur ^ 1];
-    m.rank_new = c->d_rank; m.snew = c->d_snew;
+    m.rank_new = c->d_rank; m.snew = c->d_snew; m.nle = c->d_nle;
     m.live_x = c->d_x; m.live_logL = c->d_logL; m.live_logP = c->d_logP;
     m.new_x = c->d_new_x; m.new_logL = c->d_new_logL; m.new_logP = c->d_new_logP;
     m.dead_x = c->d_dead_x; m.dead_logL = c->d_dead_logL; m.dead_logP = c->d_dead_logP;

@@ -2,7 +2,7 @@
 // rounds of sampler requests (cpnest/NestedSampling.py):
 //   k_ns_accumulate   get_worst_n_live_points (:368-375) + _NSintegralState.increment (:111-134)
 //                     + termination condition (:332, :451) + Nmcmc moving average (sampler.py:156-176)
-//   k_rank_count/scatter  ordering of the K replacements (KeyOrderedList.search, :42-46)
+//   k_rank_bucket/scan/fill/final  ordering of the K replacements (KeyOrderedList.search, :42-46)
 //   k_merge_commit    insert_live_point / remove_n_worst_points (:74-85) + insertion indices (:347-350)
 //                     + nested_samples.extend (:327)
 //   k_bitonic_step    initial sort of the live set (OrderedLivePoints.__init__, :71-72)
@@ -378,29 +378,40 @@ __global__ void k_adapt_hmc_dt(NSState* st) {
 }
 
 // corr_d(start, end) across the chains [j0, j1) of the batch (those of sampler kind `kind`), d in [0, D] (d == D is
-// logL).  One block per d; fixed-shape tree reduction (deterministic).  Block D+1 sums the batch counters.
-// rho points at this kind's D+1 values.
-__global__ void __launch_bounds__(kCorrThreads) k_chain_corr(NSState* st, int kind, int j0, int j1, int D, int Dp, const int* __restrict__ start_slot,
-                                                    const double* __restrict__ live_x, const double* __restrict__ live_logL,
-                                                    const double* __restrict__ new_x, const double* __restrict__ new_logL,
-                                                    double* __restrict__ rho, const int* steps, const int* acc, const int* evals) {
+// logL).  Two kernels: k_chain_corr_partial - block (d, s) sums the five moments of coordinate d over its segment of
+// kCorrSeg chains (fixed-shape tree: deterministic), block row D+1 sums the batch counters; k_chain_corr_final adds the
+// segments in order and writes rho[d] and st->ctl[kind].batch[].  The grid grows with the batch, so the replicated
+// statistics of a multi-GPU batch (K = all ranks' chains) do not serialise on D+2 blocks.
+constexpr int kCorrSeg = 4 * kCorrThreads;
+__global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSState* st, int j0, int j1, int D, int Dp,
+                                                                     const int* __restrict__ start_slot, const double* __restrict__ live_x,
+                                                                     const double* __restrict__ live_logL, const double* __restrict__ new_x,
+                                                                     const double* __restrict__ new_logL, const int* steps, const int* acc,
+                                                                     const int* evals, double* __restrict__ part /*[D+2][nseg][5]*/) {
     if (st->done) return;
     __shared__ double sh[5][kCorrThreads];
-    if (blockIdx.x == D + 1) {
-        block_batch_counters(st, kind, j0, j1, steps, acc, evals, reinterpret_cast<unsigned long long (*)[kCorrThreads]>(&sh[0][0]));
-        return;
-    }
-    const int d = blockIdx.x, tid = threadIdx.x;
-    // shift by the first chain's values to keep the sums well conditioned
-    const int s0 = start_slot[j0];
-    const double cs = (d < D) ? live_x[(size_t)s0 * Dp + d] : live_logL[s0];
-    const double ce = (d < D) ? new_x[(size_t)j0 * Dp + d] : new_logL[j0];
+    const int d = blockIdx.x, sg = blockIdx.y, nseg = gridDim.y, tid = threadIdx.x;
+    const int a0 = j0 + sg * kCorrSeg, a1 = min(j1, a0 + kCorrSeg);
     double a[5] = {0, 0, 0, 0, 0};
-    for (int j = j0 + tid; j < j1; j += kCorrThreads) {
-        const int sl = start_slot[j];
-        const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
-        const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
-        a[0] += s; a[1] += e; a[2] += s * s; a[3] += e * e; a[4] += s * e;
+    if (d == D + 1) {
+        // counters as doubles: exact up to 2^53
+        for (int j = a0 + tid; j < a1; j += kCorrThreads) {
+            a[0] += (double)steps[j];
+            a[1] += (double)acc[j];
+            a[2] += (double)(evals != nullptr ? evals[j] : 0);
+            a[3] += (acc[j] == 0) ? 1.0 : 0.0;
+        }
+    } else {
+        // shift by the first chain's values to keep the sums well conditioned
+        const int s0 = start_slot[j0];
+        const double cs = (d < D) ? live_x[(size_t)s0 * Dp + d] : live_logL[s0];
+        const double ce = (d < D) ? new_x[(size_t)j0 * Dp + d] : new_logL[j0];
+        for (int j = a0 + tid; j < a1; j += kCorrThreads) {
+            const int sl = start_slot[j];
+            const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
+            const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
+            a[0] += s; a[1] += e; a[2] += s * s; a[3] += e * e; a[4] += s * e;
+        }
     }
     for (int k = 0; k < 5; ++k) sh[k][tid] = a[k];
     __syncthreads();
@@ -409,98 +420,97 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr(NSState* st, int ki
             for (int k = 0; k < 5; ++k) sh[k][tid] += sh[k][tid + w];
         __syncthreads();
     }
-    if (tid == 0) {
-        const double n = (double)(j1 - j0);
-        const double vs = sh[2][0] - sh[0][0] * sh[0][0] / n, ve = sh[3][0] - sh[1][0] * sh[1][0] / n;
-        const double cv = sh[4][0] - sh[0][0] * sh[1][0] / n;
-        rho[d] = cv / sqrt(vs * ve);
+    if (tid < 5) part[((size_t)d * nseg + sg) * 5 + tid] = sh[tid][0];
+}
+__global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg, const double* __restrict__ part, double* __restrict__ rho) {
+    if (st->done) return;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > D + 1) return;
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int sg = 0; sg < nseg; ++sg)
+        for (int k = 0; k < 5; ++k) a[k] += part[((size_t)d * nseg + sg) * 5 + k];
+    if (d == D + 1) {
+        for (int k = 0; k < 4; ++k) st->ctl[kind].batch[k] = (unsigned long long)a[k];
+        return;
     }
+    const double nn = (double)n;
+    const double vs = a[2] - a[0] * a[0] / nn, ve = a[3] - a[1] * a[1] / nn;
+    const double cv = a[4] - a[0] * a[1] / nn;
+    rho[d] = cv / sqrt(vs * ve);
 }
 
-// rank of each replacement among the K replacements (ties broken by chain index), and the sorted copy of
-// their keys.  Counting over a 2-D grid: block (bx, by) compares its 256 replacements with the by-th tile of
-// 256 keys and adds its partial counts (integer atomics: order-independent); k_rank_scatter then places the keys.
-constexpr int kRankTile = 256;
-__global__ void __launch_bounds__(kRankTile) k_rank_count(const NSState* st, const double* __restrict__ new_logL, int K,
-                                                          int* __restrict__ rank) {
-    if (st->done) return;
-    __shared__ double tile[kRankTile];
-    const int q = blockIdx.x * kRankTile + threadIdx.x;
-    const int base = blockIdx.y * kRankTile;
-    const int i = base + threadIdx.x;
-    tile[threadIdx.x] = (i < K) ? new_logL[i] : INFINITY;
-    __syncthreads();
-    if (q >= K) return;
-    const double key = new_logL[q];
-    const int lim = min(kRankTile, K - base);
-    int r = 0;
-#pragma unroll 8
-    for (int t = 0; t < lim; ++t) {
-        const double o = tile[t];
-        r += (o < key) || (o == key && base + t < q);
-    }
-    if (r) atomicAdd(rank + q, r);
-}
-__global__ void k_rank_scatter(const NSState* st, const double* __restrict__ new_logL, int K, const int* __restrict__ rank,
-                               double* __restrict__ snew) {
-    if (st->done) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < K) snew[rank[q]] = new_logL[q];
-}
-
-// Large batches: the K keys are cut into segments of kRankSeg; k_rank_count_seg ranks every key inside its segment
-// (same counting rule, grid z = segment) and k_rank_seg_sorted writes each segment in sorted order; k_rank_merge_seg
-// then adds, per key, the number of smaller keys in every OTHER segment by binary search (ties: keys of earlier
-// segments count as smaller - the chain-index rule) and scatters the key to its global rank.
-// Work K * kRankSeg comparisons + K * (#segments) searches instead of K^2.
-constexpr int kRankSeg = 4096;
-__global__ void __launch_bounds__(kRankTile) k_rank_count_seg(const NSState* st, const double* __restrict__ new_logL, int K,
-                                                              int* __restrict__ rank) {
-    if (st->done) return;
-    __shared__ double tile[kRankTile];
-    const int s0 = blockIdx.z * kRankSeg, s1 = min(s0 + kRankSeg, K);
-    const int q = s0 + blockIdx.x * kRankTile + threadIdx.x;
-    const int base = s0 + blockIdx.y * kRankTile;
-    if (s0 + (int)blockIdx.x * kRankTile >= s1 || base >= s1) return;
-    const int i = base + threadIdx.x;
-    tile[threadIdx.x] = (i < s1) ? new_logL[i] : INFINITY;
-    __syncthreads();
-    if (q >= s1) return;
-    const double key = new_logL[q];
-    const int lim = min(kRankTile, s1 - base);
-    int r = 0;
-#pragma unroll 8
-    for (int t = 0; t < lim; ++t) {
-        const double o = tile[t];
-        r += (o < key) || (o == key && base + t < q);
-    }
-    if (r) atomicAdd(rank + q, r);
-}
-__global__ void k_rank_seg_sorted(const NSState* st, const double* __restrict__ new_logL, int K, const int* __restrict__ rank,
-                                  double* __restrict__ seg_sorted) {
-    if (st->done) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < K) seg_sorted[(q / kRankSeg) * kRankSeg + rank[q]] = new_logL[q];
-}
-__global__ void k_rank_merge_seg(const NSState* st, const double* __restrict__ new_logL, int K, const double* __restrict__ seg_sorted,
-                                 int* __restrict__ rank, double* __restrict__ snew) {
+// Rank of each replacement among the K replacements (ties broken by chain index), and the sorted copy of their keys.
+// The sorted survivors are the pivots: replacement q falls into bucket nle_q = #(survivors <= key_q) (bisect-right, the
+// position `KeyOrderedList.search` returns, NestedSampling.py:42-46, which the merge needs anyway).  Replacements of
+// different buckets are ordered by bucket; a bucket holds K / (N - K) replacements on average, so the order inside it is
+// found by comparing its few members with each other:
+//   k_rank_bucket  nle_q by binary search, histogram of the buckets (integer atomics: order independent)
+//   k_rank_scan    exclusive prefix sum of the histogram (one block)
+//   k_rank_fill    the members of every bucket, listed in arbitrary order
+//   k_rank_final   rank_q = start of the bucket + #(members with (key, chain) < (key_q, q)): does not depend on the
+//                  order in which k_rank_fill listed them, so the result is deterministic
+// Work O(K log N) instead of the K^2 comparisons of a counting rank; every step of it is replicated on all ranks of a
+// multi-GPU run, where K is the whole batch.
+__global__ void k_rank_bucket(const NSState* st, const double* __restrict__ new_logL, int K, const double* __restrict__ surv, int ns,
+                              int* __restrict__ nle, int* __restrict__ hist) {
     if (st->done) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= K) return;
     const double key = new_logL[q];
-    const int mine = q / kRankSeg, nseg = (K + kRankSeg - 1) / kRankSeg;
-    int r = rank[q];
-    for (int s = 0; s < nseg; ++s) {
-        if (s == mine) continue;
-        const double* a = seg_sorted + (size_t)s * kRankSeg;
-        const int n = min(kRankSeg, K - s * kRankSeg);
-        int lo = 0, hi = n;                      // earlier segment: #(a <= key); later segment: #(a < key)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const bool less = (s < mine) ? (a[mid] <= key) : (a[mid] < key);
-            if (less) lo = mid + 1; else hi = mid;
-        }
-        r += lo;
+    int lo = 0, hi = ns;                      // #(surv <= key)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (surv[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    nle[q] = lo;
+    atomicAdd(hist + lo, 1);
+}
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) k_rank_scan(const NSState* st, int* __restrict__ hist, int nb) {
+    if (st->done) return;
+    __shared__ int sh[kScanThreads];
+    const int tid = threadIdx.x;
+    const int per = (nb + kScanThreads - 1) / kScanThreads;
+    const int b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
+    int mine = 0;
+    for (int b = b0; b < b1; ++b) mine += hist[b];
+    sh[tid] = mine;
+    __syncthreads();
+    for (int off = 1; off < kScanThreads; off <<= 1) {
+        const int add = (tid >= off) ? sh[tid - off] : 0;
+        __syncthreads();
+        sh[tid] += add;
+        __syncthreads();
+    }
+    int run = sh[tid] - mine;
+    for (int b = b0; b < b1; ++b) {
+        const int h = hist[b];
+        hist[b] = run;                        // start of bucket b in the sorted replacements
+        run += h;
+    }
+}
+__global__ void k_rank_fill(const NSState* st, int K, const int* __restrict__ nle, const int* __restrict__ start, int* __restrict__ cursor,
+                            int* __restrict__ members) {
+    if (st->done) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= K) return;
+    const int b = nle[q];
+    members[start[b] + atomicAdd(cursor + b, 1)] = q;
+}
+__global__ void k_rank_final(const NSState* st, const double* __restrict__ new_logL, int K, const int* __restrict__ nle,
+                             const int* __restrict__ start, const int* __restrict__ cursor, const int* __restrict__ members,
+                             int* __restrict__ rank, double* __restrict__ snew) {
+    if (st->done) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= K) return;
+    const int b = nle[q];
+    const int s0 = start[b], n = cursor[b];
+    const double key = new_logL[q];
+    int r = s0;
+    for (int t = 0; t < n; ++t) {
+        const int o = members[s0 + t];
+        const double ko = new_logL[o];
+        r += (ko < key) || (ko == key && o < q);
     }
     rank[q] = r;
     snew[r] = key;
@@ -515,6 +525,7 @@ struct MergeParams {
     int* order_out;
     double* skeys_out;
     const int* rank_new;       // [K]
+    const int* nle;            // [K] #(survivors <= key) of every replacement (k_rank_bucket)
     const double* snew;        // [K] sorted replacement keys
     double* live_x;            // [N][Dp]
     double* live_logL;
@@ -582,7 +593,7 @@ __global__ void k_merge_commit(const MergeParams p) {
     } else {
         const int slot = p.order_in[i];
         const double key = p.new_logL[i];
-        const int nle = upper_bound_d(p.skeys_in + K, N - K, key);
+        const int nle = p.nle[i];
         const int pos = p.rank_new[i] + nle;
         p.order_out[pos] = slot;
         p.skeys_out[pos] = key;
