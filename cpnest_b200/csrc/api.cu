@@ -538,7 +538,7 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
     if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
     if (dalloc(&c->d_rho, kNumKinds * (D + 1)) || dalloc(&c->d_rho2, kNumKinds * (D + 1)) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
         return 1;
-    if (dalloc(&c->d_bucket, 3 * (size_t)(N + 1)) || dalloc(&c->d_nle, N)) return 1;
+    if (dalloc(&c->d_bucket, 3 * (size_t)(N + 1) + (size_t)(N / kScanTile + 2)) || dalloc(&c->d_nle, N)) return 1;
     c->corr_part_cap = (size_t)(D + 2) * ((N + kCorrSeg - 1) / kCorrSeg + 1) * 5;
     if (dalloc(&c->d_corr_part, c->corr_part_cap)) return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
@@ -1194,10 +1194,13 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         CK(cudaMemsetAsync(c->d_bucket, 0, 2 * (size_t)(c->N + 1) * sizeof(int), c->stream));
         const int gb = (K + T - 1) / T;
         k_rank_bucket<<<gb, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_skeys[c->cur] + K, ns, c->d_nle, hist);
-        k_rank_scan<<<1, kScanThreads, 0, c->stream>>>(c->d_state, hist, nb);
+        const int ntile = (nb + kScanTile - 1) / kScanTile;
+        int* tile_sum = c->d_bucket + 3 * (c->N + 1);
+        k_rank_scan_tiles<<<ntile, kScanThreads, 0, c->stream>>>(c->d_state, hist, nb, tile_sum);
+        k_rank_scan_apply<<<ntile, kScanThreads, 0, c->stream>>>(c->d_state, hist, nb, tile_sum);
         k_rank_fill<<<gb, T, 0, c->stream>>>(c->d_state, K, c->d_nle, hist, cursor, members);
         k_rank_final<<<gb, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_nle, hist, cursor, members, c->d_rank, c->d_snew);
-        c->launches += 4;
+        c->launches += 5;
     }
     MergeParams m;
     memset(&m, 0, sizeof m);

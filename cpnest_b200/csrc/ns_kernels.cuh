@@ -445,7 +445,7 @@ __global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg
 // different buckets are ordered by bucket; a bucket holds K / (N - K) replacements on average, so the order inside it is
 // found by comparing its few members with each other:
 //   k_rank_bucket  nle_q by binary search, histogram of the buckets (integer atomics: order independent)
-//   k_rank_scan    exclusive prefix sum of the histogram (one block)
+//   k_rank_scan_*  exclusive prefix sum of the histogram (tiles, then tiles in front + scan of the tile)
 //   k_rank_fill    the members of every bucket, listed in arbitrary order
 //   k_rank_final   rank_q = start of the bucket + #(members with (key, chain) < (key_q, q)): does not depend on the
 //                  order in which k_rank_fill listed them, so the result is deterministic
@@ -465,28 +465,84 @@ __global__ void k_rank_bucket(const NSState* st, const double* __restrict__ new_
     nle[q] = lo;
     atomicAdd(hist + lo, 1);
 }
+// exclusive prefix sum of the bucket histogram in two launches with coalesced accesses: k_rank_scan_tiles sums tiles of
+// kScanTile buckets; k_rank_scan_apply adds up the tiles in front of its own and scans its tile (hist[b] becomes the start
+// of bucket b in the sorted replacements)
 constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) k_rank_scan(const NSState* st, int* __restrict__ hist, int nb) {
-    if (st->done) return;
-    __shared__ int sh[kScanThreads];
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+__device__ __forceinline__ int block_sum_int(int v, int* sh) {
     const int tid = threadIdx.x;
-    const int per = (nb + kScanThreads - 1) / kScanThreads;
-    const int b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
-    int mine = 0;
-    for (int b = b0; b < b1; ++b) mine += hist[b];
-    sh[tid] = mine;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((tid & 31) == 0) sh[tid >> 5] = v;
     __syncthreads();
-    for (int off = 1; off < kScanThreads; off <<= 1) {
-        const int add = (tid >= off) ? sh[tid - off] : 0;
-        __syncthreads();
-        sh[tid] += add;
-        __syncthreads();
+    int t = (tid < kScanThreads / 32) ? sh[tid] : 0;
+    if (tid < 32) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+        if (tid == 0) sh[0] = t;
     }
-    int run = sh[tid] - mine;
-    for (int b = b0; b < b1; ++b) {
-        const int h = hist[b];
-        hist[b] = run;                        // start of bucket b in the sorted replacements
-        run += h;
+    __syncthreads();
+    const int r = sh[0];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(kScanThreads) k_rank_scan_tiles(const NSState* st, const int* __restrict__ hist, int nb, int* __restrict__ tile_sum) {
+    if (st->done) return;
+    __shared__ int sh[32];
+    const int base = blockIdx.x * kScanTile;
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int b = base + i * kScanThreads + threadIdx.x;
+        v += (b < nb) ? hist[b] : 0;
+    }
+    v = block_sum_int(v, sh);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(kScanThreads) k_rank_scan_apply(const NSState* st, int* __restrict__ hist, int nb, const int* __restrict__ tile_sum) {
+    if (st->done) return;
+    __shared__ int sh[32];
+    __shared__ int wsum[kScanThreads / 32];
+    const int tid = threadIdx.x, base = blockIdx.x * kScanTile;
+    // buckets in front of this tile
+    int pre = 0;
+    for (int t = tid; t < (int)blockIdx.x; t += kScanThreads) pre += tile_sum[t];
+    pre = block_sum_int(pre, sh);
+    // this thread owns kScanItems consecutive buckets of the tile
+    int h[kScanItems], mine = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int b = base + tid * kScanItems + i;
+        h[i] = (b < nb) ? hist[b] : 0;
+        mine += h[i];
+    }
+    // exclusive scan of `mine` over the block: shuffles inside a warp, warp totals through shared memory
+    int incl = mine;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, m);
+        if ((tid & 31) >= m) incl += o;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int w = (tid < kScanThreads / 32) ? wsum[tid] : 0, wi = w;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, wi, m);
+            if (tid >= m) wi += o;
+        }
+        if (tid < kScanThreads / 32) wsum[tid] = wi - w;          // exclusive
+    }
+    __syncthreads();
+    int run = pre + wsum[tid >> 5] + incl - mine;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int b = base + tid * kScanItems + i;
+        if (b < nb) hist[b] = run;
+        run += h[i];
     }
 }
 __global__ void k_rank_fill(const NSState* st, int K, const int* __restrict__ nle, const int* __restrict__ start, int* __restrict__ cursor,

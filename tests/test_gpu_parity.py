@@ -357,9 +357,9 @@ def test_device_chain_length_rule_equals_estimate_nmcmc_on_the_fly():
         live = e.live()
         ne = e.state()["nmcmc_exact"]
         saw_immobile = False
-        for q in (0.3, 0.6, 0.999, 0.5):             # 0.999: every chain starts at the best point, just above the threshold
-            logLmin = float(np.quantile(live[:, 10], q))
-            good = np.where(live[:, 10] > logLmin)[0]
+        for q in (0.3, 0.6, None, 0.5):              # None: a threshold no proposal can beat - every chain returns unmoved
+            logLmin = float(np.quantile(live[:, 10], q)) if q is not None else 1e9
+            good = np.where(live[:, 10] > (logLmin if q is not None else -np.inf))[0]
             req = np.ascontiguousarray(live[good[rs.randint(0, len(good), size=K)]])
             n_chain = e.state()["nmcmc"]
             _, steps, acc = e.evolve_host(req, logLmin, n_chain)
