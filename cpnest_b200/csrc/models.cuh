@@ -110,9 +110,9 @@ struct GaussIid : FlatPrior {
 };
 
 // ---- correlated Gaussian N(0, Sigma), Sigma = L L^T: logL = -|L^-1 x|^2/2 - sum log L_ii - D/2 log 2pi
-//      (not in the reference).  blob = {logdet, Linv[D][D] row-major lower, LinvT[D][D]}: the second
-//      copy is the transpose, LinvT[c][r] = Linv[r][c] (zero for r < c), so that for a fixed column the lanes of a group,
-//      which own consecutive rows, read consecutive doubles -------
+//      (not in the reference).  blob = {logdet, Linv[D][D] row-major lower, LinvT[D][S]}: the second
+//      copy is the transpose, LinvT[c][r] = Linv[r][c] (zero for r < c and for the padding rows D..S-1, S = D rounded up
+//      to 32), so that for a fixed column the lanes of a group, which own consecutive rows, read consecutive doubles -------
 struct GaussCorr : FlatPrior {
     static constexpr bool kScratch = true;
     static constexpr bool kCheap = false;
@@ -120,10 +120,13 @@ struct GaussCorr : FlatPrior {
     // chain's shared-memory scratch.  Columns are walked in blocks of G: in block b the slots e > b take every column,
     // slot e == b meets the diagonal block (the zeros above the diagonal are stored), slots e < b are done - D(D+G)/2
     // multiply-adds on E independent accumulators per lane instead of a dependent chain of D per row.
+    // row stride of the transposed copy: D rounded up to 32, the rows D.. of every column are zero (a lane whose row
+    // does not exist multiplies zeros)
+    static __host__ __device__ __forceinline__ int ldt(int D) { return (D + 31) & ~31; }
     template <int G, int E>
     static __device__ __forceinline__ void whiten(const Group<G>& g, const double (&x)[E], const ModelCtx& m, double (&y)[E]) {
-        const int D = m.D;
-        const double* Lt = m.blob + 1 + (size_t)D * D + g.lane;      // + c*D + G*e
+        const int D = m.D, S = ldt(D);
+        const double* Lt = m.blob + 1 + (size_t)D * D + g.lane;      // + c*S + G*e
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -134,13 +137,16 @@ struct GaussCorr : FlatPrior {
         __syncwarp();
 #pragma unroll
         for (int b = 0; b < E; ++b) {
-            const int c1 = min(D, G * (b + 1));
-            for (int c = G * b; c < c1; ++c) {
-                const double xc = m.scratch[c];
-                const double* col = Lt + (size_t)c * D;
+            const int nc = min(G, D - G * b);                          // columns of this block (<= 0: none left)
+            const double* col = Lt + (size_t)(G * b) * S;
+            const double* xs = m.scratch + G * b;
+#pragma unroll 4
+            for (int c = 0; c < nc; ++c) {
+                const double xc = xs[c];
 #pragma unroll
                 for (int e = b; e < E; ++e)
-                    if (G * e < D) y[e] = fma((g.lane + G * e < D) ? __ldg(col + G * e) : 0.0, xc, y[e]);
+                    if (G * e < S) y[e] = fma(__ldg(col + G * e), xc, y[e]);
+                col += S;
             }
         }
         __syncwarp();

@@ -26,7 +26,9 @@ def functor_blob(name, dim, params=None):
         Linv = np.asarray(params["Linv"], dtype=np.float64)
         assert Linv.shape == (dim, dim)
         Linv = np.tril(Linv)
-        return np.concatenate(([float(params["logdet"])], Linv.ravel(), np.ascontiguousarray(Linv.T).ravel()))
+        LinvT = np.zeros((dim, (dim + 31) // 32 * 32))       # transposed copy, rows padded with zeros to a multiple of 32
+        LinvT[:, :dim] = Linv.T
+        return np.concatenate(([float(params["logdet"])], Linv.ravel(), LinvT.ravel()))
     if name == "ring":
         return np.array([float(params.get("radius", 1.0)), float(params.get("thickness", 0.1))])
     if name == "gaussian_mixture":

@@ -29,7 +29,8 @@ typedef struct cpn_ctx cpn_ctx;
 enum cpn_functor {
     CPN_GAUSS_IID = 0,        /* examples/test_50d.py:18-19, tests/test_2d.py:15-16, tests/test_1d.py:20-21;
                                  blob: {mu, sigma} (2 doubles) */
-    CPN_GAUSS_CORR = 1,       /* SURVEY 8d config 4, N(0,Sigma); blob: {logdet_L, Linv[D][D] row-major lower, LinvT[D][D] its transpose} */
+    CPN_GAUSS_CORR = 1,       /* SURVEY 8d config 4, N(0,Sigma); blob: {logdet_L, Linv[D][D] row-major lower, LinvT[D][S] its transpose, rows zero-padded to
+                                 S = D rounded up to 32} */
     CPN_EGGBOX = 2,           /* examples/eggbox.py:19-23 */
     CPN_ROSENBROCK = 3,       /* examples/rosenbrock.py:20-22 */
     CPN_ACKLEY = 4,           /* standard D-dim Ackley (examples/ackley.py:21-28 is non-finite everywhere) */
