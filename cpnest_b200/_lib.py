@@ -106,6 +106,8 @@ SIGNATURES = {
     "cpn_host_gather_rows": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp]),
     "cpn_host_scatter_rows": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp]),
     "cpn_set_stream": (C.c_int, [_vp, _vp]),
+    "cpn_enable_chain_log": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "cpn_get_chain_log": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _ip]),
     "cpn_launch_count": (C.c_int64, [_vp]),
     "cpn_pick_lanes": (C.c_int, [_vp, C.c_int32, _ip, _ip]),
     "cpn_eval_model": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),

@@ -116,6 +116,13 @@ class CPNest(object):
             self.engine = Engine(functor, self.user.bounds, nlive=nlive, maxmcmc=maxmcmc, seed=self.seed, params=params,
                                  device=device, lanes=lanes, rho_target=rho_target, sampler=primary,
                                  mix=self.population if len(kinds) > 1 else None)
+            # verbose >= 3: every sampler process of the reference keeps the last 5*maxmcmc states of its chains and saves
+            # them as mcmc_chain_<pid>.dat (cpnest/sampler.py:86, 261-267); here the MH kernel logs the first chains of every
+            # batch (slot i plays sampler process i)
+            self.chain_log_slots = 0
+            if verbose >= 3 and not self.prior_sampling and "mh" in kinds:
+                self.chain_log_slots = min(4, self.batch, max(1, self.nthreads))
+                self.engine.enable_chain_log(self.chain_log_slots, 3 * 5 * maxmcmc + 64)
             # one proposal object per sampler kind present, in the reference's order of construction
             # (cpnest/cpnest.py:197-261: MH samplers, then HMC, then slice); self.proposal is the first kind's
             self.proposals = {}
@@ -246,6 +253,7 @@ class CPNest(object):
                 self.nested_samples = self.get_nested_samples(filename=None)
                 self.posterior_samples = self.get_posterior_samples(filename=None)
             if self.verbose >= 3:                                # cpnest/cpnest.py:309-312
+                self._write_mcmc_chains()
                 self.prior_samples = self.get_prior_samples(filename=None)
                 self.mcmc_samples = self.get_mcmc_samples(filename=None)
             if self.verbose >= 2:
@@ -300,10 +308,38 @@ class CPNest(object):
                        header=" ".join(prior_samples.dtype.names), newline="\n", delimiter=" ")
         return prior_samples
 
+    def _write_mcmc_chains(self):
+        """cpnest/sampler.py:261-267: at verbose >= 3 every sampler saves its last 5*maxmcmc MCMC states as
+        mcmc_chain_<pid>.dat; one file per logged chain slot here."""
+        for slot in range(getattr(self, "chain_log_slots", 0)):
+            hist = self.engine.chain_history(slot, last=5 * self.maxmcmc)
+            if len(hist) == 0:
+                continue
+            arr = LivePointList(self.user.names, hist).asnparray()
+            fn = "mcmc_chain_{0}_{1}.dat".format(os.getpid(), slot)
+            np.savetxt(os.path.join(self.output, fn), arr.ravel(), header=" ".join(arr.dtype.names), newline="\n", delimiter=" ")
+            self.logger.critical("Sampler process {0!s}: saved {1:d} mcmc samples in {2!s}".format(os.getpid(), len(arr), fn))
+
     def get_mcmc_samples(self, filename="mcmc.dat"):
-        """cpnest/cpnest.py:445-478: per-sampler chain files do not exist on the device path."""
-        self.logger.critical("ERROR, no MCMC samples found!")
-        return None
+        """Resampled MCMC samples (cpnest/cpnest.py:445-478): every mcmc_chain_*.dat of the output folder is thinned by its
+        autocorrelation length and redrawn against the Metropolis-Hastings rule (nest2pos.resample_mcmc_chain), the files
+        are removed, the chains stacked."""
+        from numpy.lib.recfunctions import stack_arrays
+        from .nest2pos import resample_mcmc_chain
+        mcmc_samples = []
+        for f in sorted(os.listdir(self.NS.output_folder)):
+            if "mcmc_chain" in f:
+                path = os.path.join(self.NS.output_folder, f)
+                mcmc_samples.append(resample_mcmc_chain(np.atleast_1d(np.genfromtxt(path, names=True))))
+                os.remove(path)
+        if not mcmc_samples:
+            self.logger.critical("ERROR, no MCMC samples found!")
+            return None
+        mcmc_samples = mcmc_samples[0] if len(mcmc_samples) == 1 else stack_arrays(mcmc_samples, usemask=False)
+        if filename:
+            np.savetxt(os.path.join(self.NS.output_folder, filename), mcmc_samples.ravel(),
+                       header=" ".join(mcmc_samples.dtype.names), newline="\n", delimiter=" ")
+        return mcmc_samples
 
     def plot(self, corner=True):
         """Diagnostic plots (cpnest/cpnest.py:480-531); needs matplotlib (+ corner)."""

@@ -122,6 +122,9 @@ struct cpn_ctx {
     NSState* h_state;           // pinned
     int* h_idx;                 // pinned [2 * nlive]: index arguments of cpn_evolve_host_table on their way to the device
     cudaEvent_t ev;
+    double* d_chain_log;        // chain history of the first chain_log_n chains of every MH batch (mh_kernel.cuh), or null
+    unsigned long long* d_chain_log_count;
+    int chain_log_n, chain_log_cap;
     RtcModule* rtc;             // kernels compiled at run time around a user-written functor (CPN_USER)
     bool user_flat_prior;
     bool live_ready;
@@ -618,6 +621,8 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (c->d_chain_log) cudaFree(c->d_chain_log);
+    if (c->d_chain_log_count) cudaFree(c->d_chain_log_count);
     if (c->rtc) rtc_destroy(c->rtc);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_idx) cudaFreeHost(c->h_idx);
@@ -844,6 +849,8 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     memcpy(p->cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
     p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
     p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
+    p->chain_log = c->d_chain_log; p->chain_log_count = c->d_chain_log_count;
+    p->chain_log_n = c->chain_log_n; p->chain_log_cap = c->chain_log_cap;
 }
 
 static void fill_slice(cpn_ctx* c, SliceParams* p) {
@@ -978,6 +985,7 @@ extern "C" int cpn_init_prior(cpn_ctx* c) {
         MHParams p;
         fill_mh(c, &p);
         p.start_mode = START_SELF;
+        p.chain_log = nullptr;                      // the burn-in is not part of the run's chain history
         p.n_skip = 0;
         p.use_override = 0;
         p.j0 = 0; p.j1 = c->N;
@@ -1457,6 +1465,46 @@ extern "C" int cpn_set_stream(cpn_ctx* c, void* stream) {
     if (join_acc(c)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return 0;
+}
+
+// ---- chain history (Sampler.samples / mcmc_chain_*.dat, cpnest/sampler.py:86, 261-267, 345) ----
+extern "C" int cpn_enable_chain_log(cpn_ctx* c, int32_t n_chains, int32_t n_events) {
+    if (!c) return fail("null context");
+    if (n_chains < 0 || n_chains > c->N || (n_chains > 0 && n_events < 8)) return fail("cpn_enable_chain_log: bad sizes");
+    CK(cudaSetDevice(c->cfg.device));
+    if (join_acc(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->d_chain_log) { cudaFree(c->d_chain_log); cudaFree(c->d_chain_log_count); c->d_chain_log = nullptr; c->d_chain_log_count = nullptr; }
+    c->chain_log_n = 0; c->chain_log_cap = 0;
+    if (n_chains == 0) return 0;
+    if (dalloc(&c->d_chain_log, (size_t)n_chains * n_events * (c->Dp + 4)) || dalloc(&c->d_chain_log_count, n_chains)) return 1;
+    c->chain_log_n = n_chains; c->chain_log_cap = n_events;
+    return 0;
+}
+
+extern "C" int cpn_get_chain_log(cpn_ctx* c, int32_t slot, double* events, int32_t max_events, int32_t* n_out) {
+    if (!c || !events || !n_out) return fail("null argument");
+    if (!c->d_chain_log || slot < 0 || slot >= c->chain_log_n) return fail("cpn_get_chain_log: no such chain log (enable it with cpn_enable_chain_log)");
+    CK(cudaSetDevice(c->cfg.device));
+    if (join_acc(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long cnt = 0;
+    CK(cudaMemcpy(&cnt, c->d_chain_log_count + slot, sizeof cnt, cudaMemcpyDeviceToHost));
+    const int cap = c->chain_log_cap, W = c->Dp + 4, D = c->D;
+    const int n = (int)std::min<unsigned long long>(cnt, (unsigned long long)cap);
+    if (n > max_events) return fail("cpn_get_chain_log: %d events, room for %d", n, max_events);
+    std::vector<double> ring((size_t)cap * W);
+    CK(cudaMemcpy(ring.data(), c->d_chain_log + (size_t)slot * cap * W, ring.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // oldest event first; rows out: {tag, step, logL, logP, x[D]}
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long src = (cnt - n + i) % (unsigned long long)cap;
+        const double* r = ring.data() + (size_t)src * W;
+        double* o = events + (size_t)i * (D + 4);
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+        for (int d = 0; d < D; ++d) o[4 + d] = r[4 + d];
+    }
+    *n_out = n;
     return 0;
 }
 

@@ -33,6 +33,15 @@ struct MHParams : ChainParams {
     // production, test entry (cpn_trace_mh): what every step of every chain consumed besides the chain state,
     // [chains][maxmcmc][8] doubles {kind, i0, i1, i2, c0, c1, c2, thr} (see DrawFeed), or null
     double* draws;
+    // production, optional: the history of the first chain_log_n chains of the batch, the device form of the sampler's
+    // `samples` deque (cpnest/sampler.py:345: every step appends the current point; written to mcmc_chain_*.dat at
+    // verbose >= 3, :261-267).  A chain's state only changes when a step is accepted, so the log holds events, not steps:
+    // rows [chain_log_n][chain_log_cap][Dp + 4] = {tag, step, logL, logP, x[Dp]}, tag 0: this is the state from `step` on
+    // (step -1: the start point), tag 1: the chain ended after `step` steps; chain_log_count[slot] = events written so far
+    // (the ring index is count % cap).  Null: off.
+    double* chain_log;
+    unsigned long long* chain_log_count;
+    int chain_log_n, chain_log_cap;
 };
 
 // ---- what one MCMC step consumes besides the chain's current point ---------------------------------
@@ -330,6 +339,24 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         double* dump = (p.draws != nullptr && valid) ? p.draws + (size_t)c * maxmcmc * 8 : nullptr;
         // the two row bases live in registers (opaque to the compiler, which would otherwise re-read them from the constant
         // bank in front of every gather: a long-latency load on the in-order path of the step)
+        // chain history (off unless the caller asked for it): events of this chain go to its slot's ring
+        double* clog = nullptr;
+        unsigned long long clog_n = 0;
+        if (p.chain_log != nullptr && valid && ch.j < p.chain_log_n) {
+            clog = p.chain_log + (size_t)ch.j * p.chain_log_cap * (p.Dp + 4);
+            clog_n = p.chain_log_count[ch.j];
+        }
+        auto log_event = [&](double tag, double at) {          // executed by all lanes of a logging chain's group
+            double* row = clog + (size_t)(clog_n % (unsigned long long)p.chain_log_cap) * (p.Dp + 4);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < p.Dp) row[4 + d] = (d < D) ? x[e] : 0.0;
+            }
+            if (g.lane == 0) { row[0] = tag; row[1] = at; row[2] = logL; row[3] = logP; }
+            ++clog_n;
+        };
+        if (clog != nullptr) log_event(0.0, -1.0);
         const int max_resend = ch.can_restart(p) ? kMaxResend : 0;
         int attempts = 0, attempt_end = maxmcmc;
         const double* ens_x = p.ens_x;
@@ -400,6 +427,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                     logL = acc ? logL_new : logL;
                     logP = acc ? logP_new : logP;
                     accepted += acc ? 1 : 0;
+                    if (clog != nullptr && acc) log_event(0.0, (double)it);
                 }
             }
             if (TAIL) {
@@ -410,6 +438,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                         ++attempts;
                         attempt_end += maxmcmc;
                         ch.restart(p, attempts);
+                        if (clog != nullptr) log_event(0.0, (double)it);
                     } else {
                         active = false;
                     }
@@ -439,6 +468,10 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             if (!__any_sync(FULL, active)) break;
             mcmc_step(BoolC<true>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
             if (!__any_sync(FULL, active)) break;
+        }
+        if (clog != nullptr) {
+            log_event(1.0, (double)steps);
+            if (g.lane == 0) p.chain_log_count[ch.j] = clog_n;
         }
         };
         if (p.padded && Model::pad_ok(m)) {

@@ -207,6 +207,45 @@ class Engine:
     def set_stream(self, cuda_stream):
         L.check(self.lib.cpn_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
+    def enable_chain_log(self, n_chains, n_events):
+        """Record the history of the first n_chains chains of every MH batch (cpn_enable_chain_log)."""
+        L.check(self.lib.cpn_enable_chain_log(self.h, int(n_chains), int(n_events)))
+        self._chain_log_events = int(n_events)
+
+    def chain_history(self, slot, last=None):
+        """Per-step states of the chains that ran in `slot`, oldest first, as rows [x.., logL, logP] - the device form of
+        the sampler's `samples` deque (cpnest/sampler.py:345: one entry per MCMC step).  Rebuilt from the event log: a
+        state is repeated for every step up to the next accepted one.  `last`: keep only the most recent `last` states."""
+        cap = self._chain_log_events
+        ev = np.empty((cap, self.dim + 4))
+        n = C.c_int32(0)
+        L.check(self.lib.cpn_get_chain_log(self.h, int(slot), L.dptr(ev), cap, C.byref(n)))
+        ev = ev[:n.value]
+        # the ring may have cut the oldest chain: start at the first chain start
+        starts = np.where((ev[:, 0] == 0) & (ev[:, 1] == -1))[0]
+        if len(starts) == 0:
+            return np.empty((0, self.dim + 2))
+        ev = ev[starts[0]:]
+        out = []
+        i = 0
+        while i < len(ev):
+            j = i + 1
+            while j < len(ev) and not (ev[j, 0] == 1):
+                j += 1
+            if j >= len(ev):
+                break                                     # a chain without its end event: still running / cut
+            steps = int(ev[j, 1])
+            seg = ev[i:j]                                 # state events of this chain, first one at step -1
+            at = seg[:, 1].astype(np.int64)
+            idx = np.searchsorted(at, np.arange(steps), side="right") - 1     # state after step s: last event with step <= s
+            rows = np.concatenate((seg[idx, 4:], seg[idx, 2:4]), axis=1)
+            out.append(rows)
+            i = j + 1
+        if not out:
+            return np.empty((0, self.dim + 2))
+        hist = np.concatenate(out)
+        return hist[-last:] if last else hist
+
     def pick_lanes(self, chains):
         """(lanes per chain, coordinates per lane) of a launch of `chains` chains (cpn_pick_lanes)."""
         g, e = C.c_int32(), C.c_int32()

