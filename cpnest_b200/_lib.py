@@ -25,7 +25,7 @@ class cpn_config(C.Structure):
         ("nmcmc_init", C.c_int32), ("functor", C.c_int32), ("lanes", C.c_int32), ("ns_mode", C.c_int32),
         ("seed", C.c_uint64), ("nmcmc_safety", C.c_double), ("adapt_nmcmc", C.c_int32),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("sampler", C.c_int32), ("rho_target", C.c_double),
-        ("mix", C.c_int32 * 3), ("reserved_", C.c_int32),
+        ("mix", C.c_int32 * 3), ("flags", C.c_int32),
     ]
 
 

@@ -81,7 +81,8 @@ struct cpn_ctx {
     int rank, world;
     double *d_new_x, *d_new_logL, *d_new_logP;
     int *d_new_steps, *d_new_acc, *d_new_start, *d_new_evals, *d_new_ne, *d_new_nc, *d_rank;
-    double *d_rho, *d_rho2;
+    double *d_mid_x, *d_mid_logL;   // mid-chain snapshots of the batch (two-lag chain-length control), in the staging block
+    double *d_rho, *d_rho2, *d_rho_mid, *d_lag_ema;
     double* d_corr_part;            // partial moments of k_chain_corr_partial, [D+2][segments][5]
     size_t corr_part_cap;
     double* d_snew;
@@ -384,12 +385,12 @@ static void init_state(cpn_ctx* c, NSState* s) {
 static size_t stage_off(int N, int Dp, int which) {
     // byte offsets of the arrays inside a staging block for N chains
     size_t o = 0;
-    const size_t sizes[9] = {(size_t)N * Dp * 8, (size_t)N * 8, (size_t)N * 8, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4,
-                             (size_t)N * 4, (size_t)N * 4};
+    const size_t sizes[11] = {(size_t)N * Dp * 8, (size_t)N * 8, (size_t)N * 8, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4, (size_t)N * 4,
+                              (size_t)N * 4, (size_t)N * 4, (size_t)N * Dp * 8, (size_t)N * 8};
     for (int i = 0; i < which; ++i) o += (sizes[i] + 255) & ~(size_t)255;
     return o;
 }
-static size_t stage_bytes(int N, int Dp) { return stage_off(N, Dp, 9); }
+static size_t stage_bytes(int N, int Dp) { return stage_off(N, Dp, 11); }
 static void bind_staging(cpn_ctx* c, void* base) {
     char* b = (char*)base;
     c->d_new_x = (double*)(b + stage_off(c->N, c->Dp, 0));
@@ -401,6 +402,8 @@ static void bind_staging(cpn_ctx* c, void* base) {
     c->d_new_evals = (int*)(b + stage_off(c->N, c->Dp, 6));
     c->d_new_ne = (int*)(b + stage_off(c->N, c->Dp, 7));
     c->d_new_nc = (int*)(b + stage_off(c->N, c->Dp, 8));
+    c->d_mid_x = (double*)(b + stage_off(c->N, c->Dp, 9));
+    c->d_mid_logL = (double*)(b + stage_off(c->N, c->Dp, 10));
 }
 
 // two halves: batch b uses half b & 1, so that a fast rank's chains of batch b+1 never store into a
@@ -548,10 +551,11 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
     c->rank = std::max(0, cfg->rank);
     c->world = std::max(1, cfg->world_size);
     if (c->world > kMaxPeers || c->rank >= c->world) return fail("cpn_create: rank %d / world_size %d not supported (max %d)", c->rank, c->world, kMaxPeers);
-    if (dalloc(&c->d_rho, kNumKinds * (D + 1)) || dalloc(&c->d_rho2, kNumKinds * (D + 1)) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N))
+    if (dalloc(&c->d_rho, kNumKinds * (D + 1)) || dalloc(&c->d_rho2, kNumKinds * (D + 1)) || dalloc(&c->d_rank, N) || dalloc(&c->d_snew, N) ||
+        dalloc(&c->d_rho_mid, kNumKinds * (D + 1)) || dalloc(&c->d_lag_ema, 2 * kNumKinds * (D + 1)))
         return 1;
     if (dalloc(&c->d_bucket, 3 * (size_t)(N + 1) + (size_t)(N / kScanTile + 2)) || dalloc(&c->d_nle, N)) return 1;
-    c->corr_part_cap = (size_t)(D + 2) * ((N + kCorrSeg - 1) / kCorrSeg + 1) * 5;
+    c->corr_part_cap = (size_t)(D + 2) * ((N + kCorrSeg - 1) / kCorrSeg + 1) * kCorrMom;
     if (dalloc(&c->d_corr_part, c->corr_part_cap)) return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
@@ -615,7 +619,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->acc_stream) cudaStreamSynchronize(c->acc_stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
-                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rank, c->d_snew, c->d_bucket, c->d_nle, c->d_corr_part, c->d_start_x, c->d_start_logL,
+                    c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rho_mid, c->d_lag_ema, c->d_rank, c->d_snew, c->d_bucket, c->d_nle, c->d_corr_part, c->d_start_x, c->d_start_logL,
                     c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
@@ -839,6 +843,8 @@ static void fill_common(cpn_ctx* c, ChainParams* p) {
         p->out_evals[o] = (int*)(b + stage_off(c->N, c->Dp, 6));
         p->out_ne[o] = (int*)(b + stage_off(c->N, c->Dp, 7));
         p->out_nc[o] = (int*)(b + stage_off(c->N, c->Dp, 8));
+        p->out_mid_x[o] = (double*)(b + stage_off(c->N, c->Dp, 9));
+        p->out_mid_logL[o] = (double*)(b + stage_off(c->N, c->Dp, 10));
     }
 }
 
@@ -945,14 +951,16 @@ static int launch_chains(cpn_ctx* c, int K, int j0, int j1, int start_mode, int 
 }
 
 // start/end correlation + batch counters of the chains [j0, j1) of kind `kind` (ns_kernels.cuh), on stream `cs`
-static int launch_chain_corr(cpn_ctx* c, cudaStream_t cs, int kind, int j0, int j1, double* rho) {
+static int launch_chain_corr(cpn_ctx* c, cudaStream_t cs, int kind, int j0, int j1, double* rho, double* rho_mid = nullptr) {
     const int nseg = std::max(1, (j1 - j0 + kCorrSeg - 1) / kCorrSeg);
-    const size_t need = (size_t)(c->D + 2) * nseg * 5;
+    const size_t need = (size_t)(c->D + 2) * nseg * kCorrMom;
     if (need > c->corr_part_cap) return fail("chain statistics: %zu partial sums exceed the scratch of %zu", need, c->corr_part_cap);
-    k_chain_corr_partial<<<dim3(c->D + 2, nseg), kCorrThreads, 0, cs>>>(c->d_state, j0, j1, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
-                                                                      c->d_new_x, c->d_new_logL, c->d_new_steps, c->d_new_acc,
+    const bool mid = rho_mid != nullptr && kind == CPN_SAMPLER_MH;
+    k_chain_corr_partial<<<dim3(c->D + 2, nseg), kCorrThreads, 0, cs>>>(c->d_state, kind, j0, j1, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
+                                                                      c->d_new_x, c->d_new_logL, mid ? c->d_mid_x : nullptr,
+                                                                      mid ? c->d_mid_logL : nullptr, c->d_new_steps, c->d_new_acc,
                                                                       c->d_new_evals, c->d_corr_part);
-    k_chain_corr_final<<<(c->D + 2 + 127) / 128, 128, 0, cs>>>(c->d_state, kind, j1 - j0, c->D, nseg, c->d_corr_part, rho);
+    k_chain_corr_final<<<(c->D + 2 + 127) / 128, 128, 0, cs>>>(c->d_state, kind, j1 - j0, c->D, nseg, c->d_corr_part, rho, rho_mid);
     c->launches += 2;
     return 0;
 }
@@ -1181,6 +1189,8 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     int kb[kNumKinds + 1];
     if (kind_ranges(c, K, kb)) return 1;
     const bool corr = !c->staged_external;
+    // the mid-chain snapshots travel with the fused exchange (and trivially on one GPU), not with the NCCL record
+    const bool twolag_ok = (c->world == 1 || c->n_peers > 0) && !(c->cfg.flags & CPN_NO_TWO_LAG);
     if (corr) {
         // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
         // control, and the batch counters: on the accumulation stream (idle by now), beside the ranking of the
@@ -1191,7 +1201,8 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         for (int k = 0; k < kNumKinds; ++k) {
             if (kb[k + 1] <= kb[k]) continue;
             // (the kinds' statistics share one scratch: they run one after the other on this stream)
-            if (launch_chain_corr(c, cs, k, kb[k], kb[k + 1], c->d_rho + k * (c->D + 1))) return 1;
+            if (launch_chain_corr(c, cs, k, kb[k], kb[k + 1], c->d_rho + k * (c->D + 1), twolag_ok ? c->d_rho_mid + k * (c->D + 1) : nullptr))
+                return 1;
             if (k == CPN_SAMPLER_SLICE) {
                 k_adapt_slice_mu<<<1, 256, 0, cs>>>(c->d_state, kb[k], kb[k + 1], c->d_new_ne, c->d_new_nc);
                 c->launches += 1;
@@ -1224,6 +1235,9 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
     m.rho = c->staged_external ? nullptr : c->d_rho;
     m.rho2_ema = c->d_rho2;
+    m.rho_mid = (m.rho != nullptr && twolag_ok) ? c->d_rho_mid : nullptr;
+    m.lag_ema = c->d_lag_ema;
+    m.allow_twolag = twolag_ok ? 1 : 0;
     for (int k = 0; k < kNumKinds; ++k) m.kind_n[k] = kb[k + 1] - kb[k];
     c->staged_external = false;
     m.order_in = c->d_order[c->cur]; m.skeys_in = c->d_skeys[c->cur];
@@ -1329,7 +1343,7 @@ static std::vector<CkptSection> ckpt_sections(cpn_ctx* c, long long n_dead, long
         {c->d_order[c->cur], N * 4}, {c->d_skeys[c->cur], N * 8},
         {c->d_dead_x, (size_t)n_dead * Dp * 8}, {c->d_dead_logL, (size_t)n_dead * 8}, {c->d_dead_logP, (size_t)n_dead * 8},
         {c->d_hist_logL, (size_t)n_hist * 8}, {c->d_hist_logvol, (size_t)n_hist * 8}, {c->d_ins, (size_t)n_ins * 8},
-        {c->d_rho2, kNumKinds * (D + 1) * 8}, {c->d_cycle, (size_t)c->cycle_len}, {c->d_slice_cycle, (size_t)c->slice_cycle_len},
+        {c->d_rho2, kNumKinds * (D + 1) * 8}, {c->d_lag_ema, 2 * kNumKinds * (D + 1) * 8}, {c->d_cycle, (size_t)c->cycle_len}, {c->d_slice_cycle, (size_t)c->slice_cycle_len},
         {c->d_mean, D * 8}, {c->d_cov, D * D * 8}};
     for (int b = 0; b < 2; ++b) {
         v.push_back({c->d_eigval[b], D * 8});
@@ -1368,7 +1382,7 @@ extern "C" int cpn_save_checkpoint(cpn_ctx* c, void* blob, int64_t bytes) {
     CkptHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, "CPNB200", 8);
-    h.version = 2; h.dim = c->D; h.nlive = c->N; h.functor = c->cfg.functor; h.sampler = c->cfg.sampler; h.ns_mode = c->cfg.ns_mode;
+    h.version = 3; h.dim = c->D; h.nlive = c->N; h.functor = c->cfg.functor; h.sampler = c->cfg.sampler; h.ns_mode = c->cfg.ns_mode;
     h.maxmcmc = c->cfg.maxmcmc; h.cycle_len = c->cycle_len; h.slice_cycle_len = c->slice_cycle_len; h.cur = c->cur;
     h.eig_cur = c->eig_cur; h.eig_pending = c->eig_pending ? 1 : 0; h.eig_pending_age = c->eig_pending_age;
     for (int k = 0; k < kNumKinds; ++k) h.mix[k] = c->mix[k];
@@ -1394,7 +1408,7 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
     if ((size_t)bytes < sizeof(CkptHeader)) return fail("cpn_load_checkpoint: blob too small");
     CkptHeader h;
     memcpy(&h, blob, sizeof h);
-    if (memcmp(h.magic, "CPNB200", 8) != 0 || h.version != 2) return fail("cpn_load_checkpoint: not a cpnest_b200 checkpoint (version 2)");
+    if (memcmp(h.magic, "CPNB200", 8) != 0 || h.version != 3) return fail("cpn_load_checkpoint: not a cpnest_b200 checkpoint (version 3)");
     if (h.dim != c->D || h.nlive != c->N || h.functor != c->cfg.functor || h.sampler != c->cfg.sampler || h.ns_mode != c->cfg.ns_mode ||
         h.maxmcmc != c->cfg.maxmcmc || h.mix[0] != c->mix[0] || h.mix[1] != c->mix[1] || h.mix[2] != c->mix[2])
         return fail("cpn_load_checkpoint: checkpoint of a different run (dim %d nlive %d functor %d sampler %d maxmcmc %d)", h.dim,
@@ -1416,11 +1430,11 @@ extern "C" int cpn_load_checkpoint(cpn_ctx* c, const void* blob, int64_t bytes) 
         const size_t N = c->N, D = c->D, Dp = c->Dp;
         const size_t sizes[] = {N * Dp * 8, N * 8, N * 8, N * 4, N * 8, (size_t)h.n_dead * Dp * 8, (size_t)h.n_dead * 8, (size_t)h.n_dead * 8,
                                 (size_t)h.n_hist * 8, (size_t)h.n_hist * 8, (size_t)h.n_ins * 8, kNumKinds * (D + 1) * 8,
-                                (size_t)h.cycle_len, (size_t)h.slice_cycle_len, D * 8, D * D * 8,
+                                2 * kNumKinds * (D + 1) * 8, (size_t)h.cycle_len, (size_t)h.slice_cycle_len, D * 8, D * D * 8,
                                 2 * (D * 8), 2 * (D * Dp * 8), 2 * (D * 8), 2 * (D * 8), 2 * (D * D * 8)};
         size_t tot = sizeof h;
-        for (int i = 0; i < 16; ++i) tot += (sizes[i] + 7) & ~(size_t)7;
-        for (int i = 16; i < 21; ++i) tot += 2 * (((sizes[i] / 2) + 7) & ~(size_t)7);
+        for (int i = 0; i < 17; ++i) tot += (sizes[i] + 7) & ~(size_t)7;
+        for (int i = 17; i < 22; ++i) tot += 2 * (((sizes[i] / 2) + 7) & ~(size_t)7);
         if ((size_t)bytes < tot) return fail("cpn_load_checkpoint: truncated blob (%lld of %zu bytes)", (long long)bytes, tot);
     }
     CK(cudaSetDevice(c->cfg.device));

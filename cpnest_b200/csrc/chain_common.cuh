@@ -60,6 +60,8 @@ struct ChainParams {
     int* out_evals[kMaxPeers];    // likelihood evaluations of the chain
     int* out_ne[kMaxPeers];       // slice sampler: expansions summed over the chain's slices (else null)
     int* out_nc[kMaxPeers];       // slice sampler: contractions
+    double* out_mid_x[kMaxPeers]; // MH, two-lag control: the chain's point after half of its steps (KindCtl::twolag), [K][Dp]
+    double* out_mid_logL[kMaxPeers];
 };
 
 template <int G, int E>
@@ -162,6 +164,21 @@ struct Chain {
         logL = p.ens_logL[slot];
         logP = p.ens_logP[slot];
         load_row<G, E>(g, p.ens_x + (size_t)slot * p.Dp, p.D, x);
+    }
+
+    // the chain's point half-way, for the two-lag chain-length control (into every peer's staging block, like finish())
+    __device__ __forceinline__ void snapshot_mid(const ChainParams& p) const {
+        if (!valid) return;
+        for (int o = 0; o < p.n_out; ++o) {
+            if (p.out_mid_x[o] == nullptr) continue;
+            double* row = p.out_mid_x[o] + (size_t)j * p.Dp;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < p.Dp) row[d] = (d < p.D) ? x[e] : 0.0;
+            }
+            if (g.lane == 0) p.out_mid_logL[o][j] = logL;
+        }
     }
 
     // strict box test, model.py:33

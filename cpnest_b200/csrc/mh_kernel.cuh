@@ -228,7 +228,9 @@ __device__ __forceinline__ TapeIn tape_step(int kind, const double* t, int compa
     return s;
 }
 
-template <int G, int E, class Model, bool REPLAY>
+template <int G, int E, class Model, bool REPLAY, bool LOG = false>
+// LOG: the production kernel with the chain history switched on (a separate instantiation: the event log costs registers
+// and instruction-cache space in the hot loop, 8% of the step when merely compiled in)
 // E <= 4: 128 registers, 4 blocks = 16 warps per SM, one wave for up to 4736 chains of 16 lanes (one latency-bound
 // wave: time per launch is flat in the number of chains up to there)
 __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(const MHParams p) {
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         // chain history (off unless the caller asked for it): events of this chain go to its slot's ring
         double* clog = nullptr;
         unsigned long long clog_n = 0;
-        if (p.chain_log != nullptr && valid && ch.j < p.chain_log_n) {
+        if (LOG && p.chain_log != nullptr && valid && ch.j < p.chain_log_n) {
             clog = p.chain_log + (size_t)ch.j * p.chain_log_cap * (p.Dp + 4);
             clog_n = p.chain_log_count[ch.j];
         }
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             if (g.lane == 0) { row[0] = tag; row[1] = at; row[2] = logL; row[3] = logP; }
             ++clog_n;
         };
-        if (clog != nullptr) log_event(0.0, -1.0);
+        if (LOG && clog != nullptr) log_event(0.0, -1.0);
         const int max_resend = ch.can_restart(p) ? kMaxResend : 0;
         int attempts = 0, attempt_end = maxmcmc;
         const double* ens_x = p.ens_x;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                     logL = acc ? logL_new : logL;
                     logP = acc ? logP_new : logP;
                     accepted += acc ? 1 : 0;
-                    if (clog != nullptr && acc) log_event(0.0, (double)it);
+                    if (LOG && clog != nullptr && acc) log_event(0.0, (double)it);
                 }
             }
             if (TAIL) {
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                         ++attempts;
                         attempt_end += maxmcmc;
                         ch.restart(p, attempts);
-                        if (clog != nullptr) log_event(0.0, (double)it);
+                        if (LOG && clog != nullptr) log_event(0.0, (double)it);
                     } else {
                         active = false;
                     }
@@ -456,10 +458,17 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         // a chain stops after step number n (counting from 1) if (n >= Nmcmc and it has moved) or n >= maxmcmc
         // (sampler.py:347): none does during the first min(Nmcmc, maxmcmc) - 1 steps
         const int n_main = max(0, min(nmcmc, maxmcmc) - 1) & ~1;
+        // (the main phase in two halves: between them the chain may leave a snapshot for the two-lag control)
+        const bool twolag = p.state != nullptr && !p.use_override && p.state->ctl[p.kind].twolag != 0;
+        const int n_half = (n_main / 2) & ~1;
         int it = 0;
-        for (; it < n_main; it += 2) {
-            mcmc_step(BoolC<false>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
-            mcmc_step(BoolC<false>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
+        for (int half = 0; half < 2; ++half) {
+            const int it1 = half == 0 ? n_half : n_main;
+            for (; it < it1; it += 2) {
+                mcmc_step(BoolC<false>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
+                mcmc_step(BoolC<false>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
+            }
+            if (half == 0 && twolag) ch.snapshot_mid(p);
         }
         steps = n_main;
         const int it_end = maxmcmc * (1 + max_resend);
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             mcmc_step(BoolC<true>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
             if (!__any_sync(FULL, active)) break;
         }
-        if (clog != nullptr) {
+        if (LOG && clog != nullptr) {
             log_event(1.0, (double)steps);
             if (g.lane == 0) p.chain_log_count[ch.j] = clog_n;
         }

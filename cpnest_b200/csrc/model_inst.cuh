@@ -26,9 +26,10 @@ static int launch_mh_model(int G, int E, int replay, const MHParams& p, cudaStre
         const int cpb = kMHThreads / GG;                                                              \
         const int nb = (nchains + cpb - 1) / cpb;                                                     \
         const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;                  \
+        const int nbt = (GG == 32 && Model::kTeam > 1) ? nchains : nb;   /* team mode: one chain per block */ \
         if (replay) k_mh_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                   \
-        else if (GG == 32 && Model::kTeam > 1) k_mh_chains<GG, EE, Model, false><<<nchains, kMHThreads, sm, s>>>(p); /* one chain per block */ \
-        else k_mh_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                         \
+        else if (p.chain_log != nullptr) k_mh_chains<GG, EE, Model, false, true><<<nbt, kMHThreads, sm, s>>>(p); \
+        else k_mh_chains<GG, EE, Model, false><<<nbt, kMHThreads, sm, s>>>(p);                        \
         return 0;                                                                                     \
     }
     CPN_CONFIGS(CPN_CASE)

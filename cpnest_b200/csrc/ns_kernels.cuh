@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p
 //      rho = exp(-n/tau) the length that reaches rho_target is n * ln(rho_target) / ln(rho).
 // The chain length follows the larger of the two with a moving average.
 // One controller per sampler kind (KindCtl): `chains` chains of kind `kind` returned in this batch.
-__device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, const double* rho, double* rho2_ema, int nrho) {
+__device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, const double* rho, double* rho2_ema, int nrho,
+                                            const double* rho_mid = nullptr, double* lag_ema = nullptr, int allow_twolag = 0) {
     KindCtl& k = st->ctl[kind];
     const unsigned long long steps = k.batch[0], accd = k.batch[1];
     for (int i = 0; i < 4; ++i) { st->totals[i] += k.batch[i]; k.batch[i] = 0; }
@@ -231,6 +232,28 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, c
         }
         k.rho_max = sqrt(fmax(qmax, 0.0));
     }
+    // Two-lag estimate (MH chains that leave a mid-chain snapshot, KindCtl::twolag): with r1 = corr(start, mid) at lag n/2
+    // and r2 = corr(start, end) at lag n, rho(n) = c + (1 - c) a^n gives the part that does not decay,
+    // c = (r2 - r1^2) / (1 + r2 - 2 r1), and the part that does, (r2 - c) / (1 - c) = a^n: chains in separated modes keep
+    // c > 0 whatever their length, and only the decaying part tells how long a chain has to be.
+    double dmax = -1.0;
+    if (rho != nullptr && rho_mid != nullptr && lag_ema != nullptr && k.twolag >= 2) {
+        const bool first2 = k.twolag == 2;
+        dmax = 0.0;
+        for (int d = 0; d < nrho; ++d) {
+            double r1 = rho_mid[d], r2 = rho[d];
+            if (!(r1 == r1) || !(r2 == r2)) { r1 = 0.0; r2 = 0.0; }
+            const double e1 = first2 ? r1 : (1.0 - a) * lag_ema[2 * d] + a * r1;
+            const double e2 = first2 ? r2 : (1.0 - a) * lag_ema[2 * d + 1] + a * r2;
+            lag_ema[2 * d] = e1;
+            lag_ema[2 * d + 1] = e2;
+            const double den = 1.0 + e2 - 2.0 * e1;
+            const double c = den > 0.05 ? fmin(fmax((e2 - e1 * e1) / den, 0.0), 0.99) : 0.0;
+            const double dec = fmin(fmax((e2 - c) / (1.0 - c), 0.0), 1.0);
+            if (dec > dmax) dmax = dec;
+        }
+    }
+    if (k.twolag > 0 && k.twolag < 1000) k.twolag += 1;
     if (!st->adapt) return;
     const double safety = st->nmcmc_safety;
     const double sub_acc = (double)accd / (double)steps;
@@ -241,10 +264,16 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, c
         // resolution of q_max: z * sigma_q, sigma_q = sqrt(2)/K * sqrt(a/(2-a)), z = sqrt(2 ln nrho)
         const double floor2 = 2.0 * sqrt(2.0 * log((double)nrho + 1.0)) * 1.41421356 / (double)chains * sqrt(a / (2.0 - a));
         const double tgt2 = fmax(k.rho_target * k.rho_target, floor2);
-        const double r2 = fmin(fmax(qmax, 1e-6), 0.998);
+        const double r2 = fmin(fmax(dmax >= 0.0 ? dmax * dmax : qmax, 1e-6), 0.998);
         double t2 = mean_len * log(tgt2) / log(r2);
         t2 = fmin(fmax(t2, 0.5 * ne), 2.0 * ne);
         target = fmax(target, t2);
+        // switch to the two-lag estimate when the correlation stays far above the target at a chain length near maxmcmc
+        if (allow_twolag && k.twolag == 0) {
+            const bool far = k.rho_max > 2.5 * k.rho_target && ne >= 0.5 * (double)st->maxmcmc;
+            k.stuck = far ? (short)(k.stuck + 1) : (short)0;
+            if (k.stuck >= 3) k.twolag = 1;
+        }
     }
     ne = (1.0 - a) * ne + a * target;
     ne = fmin(ne, (double)st->maxmcmc);
@@ -383,16 +412,19 @@ __global__ void k_adapt_hmc_dt(NSState* st) {
 // segments in order and writes rho[d] and st->ctl[kind].batch[].  The grid grows with the batch, so the replicated
 // statistics of a multi-GPU batch (K = all ranks' chains) do not serialise on D+2 blocks.
 constexpr int kCorrSeg = 4 * kCorrThreads;
-__global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSState* st, int j0, int j1, int D, int Dp,
+constexpr int kCorrMom = 8;      // s, e, ss, ee, se and - two-lag control - m, mm, sm (m: the mid-chain snapshot)
+__global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSState* st, int kind, int j0, int j1, int D, int Dp,
                                                                      const int* __restrict__ start_slot, const double* __restrict__ live_x,
                                                                      const double* __restrict__ live_logL, const double* __restrict__ new_x,
-                                                                     const double* __restrict__ new_logL, const int* steps, const int* acc,
-                                                                     const int* evals, double* __restrict__ part /*[D+2][nseg][5]*/) {
+                                                                     const double* __restrict__ new_logL, const double* __restrict__ mid_x,
+                                                                     const double* __restrict__ mid_logL, const int* steps, const int* acc,
+                                                                     const int* evals, double* __restrict__ part /*[D+2][nseg][8]*/) {
     if (st->done) return;
-    __shared__ double sh[5][kCorrThreads];
+    __shared__ double sh[kCorrMom][kCorrThreads / 32];
     const int d = blockIdx.x, sg = blockIdx.y, nseg = gridDim.y, tid = threadIdx.x;
     const int a0 = j0 + sg * kCorrSeg, a1 = min(j1, a0 + kCorrSeg);
-    double a[5] = {0, 0, 0, 0, 0};
+    const bool mid = mid_x != nullptr && st->ctl[kind].twolag >= 2;       // this batch's chains left snapshots
+    double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (d == D + 1) {
         // counters as doubles: exact up to 2^53
         for (int j = a0 + tid; j < a1; j += kCorrThreads) {
@@ -411,24 +443,38 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSSta
             const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
             const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
             a[0] += s; a[1] += e; a[2] += s * s; a[3] += e * e; a[4] += s * e;
+            if (mid) {
+                const double m = ((d < D) ? mid_x[(size_t)j * Dp + d] : mid_logL[j]) - ce;
+                a[5] += m; a[6] += m * m; a[7] += s * m;
+            }
         }
     }
-    for (int k = 0; k < 5; ++k) sh[k][tid] = a[k];
-    __syncthreads();
-    for (int w = kCorrThreads / 2; w > 0; w >>= 1) {
-        if (tid < w)
-            for (int k = 0; k < 5; ++k) sh[k][tid] += sh[k][tid + w];
-        __syncthreads();
+    // fixed-shape reduction: butterflies inside a warp, then the 32 warp totals by the first warp
+#pragma unroll
+    for (int k = 0; k < kCorrMom; ++k) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], m);
+        if ((tid & 31) == 0) sh[k][tid >> 5] = a[k];
     }
-    if (tid < 5) part[((size_t)d * nseg + sg) * 5 + tid] = sh[tid][0];
+    __syncthreads();
+    if (tid < 32) {
+#pragma unroll
+        for (int k = 0; k < kCorrMom; ++k) {
+            double v = sh[k][tid];
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+            if (tid == 0) part[((size_t)d * nseg + sg) * kCorrMom + k] = v;
+        }
+    }
 }
-__global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg, const double* __restrict__ part, double* __restrict__ rho) {
+__global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg, const double* __restrict__ part, double* __restrict__ rho,
+                                   double* __restrict__ rho_mid) {
     if (st->done) return;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d > D + 1) return;
-    double a[5] = {0, 0, 0, 0, 0};
+    double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int sg = 0; sg < nseg; ++sg)
-        for (int k = 0; k < 5; ++k) a[k] += part[((size_t)d * nseg + sg) * 5 + k];
+        for (int k = 0; k < kCorrMom; ++k) a[k] += part[((size_t)d * nseg + sg) * kCorrMom + k];
     if (d == D + 1) {
         for (int k = 0; k < 4; ++k) st->ctl[kind].batch[k] = (unsigned long long)a[k];
         return;
@@ -437,6 +483,10 @@ __global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg
     const double vs = a[2] - a[0] * a[0] / nn, ve = a[3] - a[1] * a[1] / nn;
     const double cv = a[4] - a[0] * a[1] / nn;
     rho[d] = cv / sqrt(vs * ve);
+    if (rho_mid != nullptr) {
+        const double vm = a[6] - a[5] * a[5] / nn, cm = a[7] - a[0] * a[5] / nn;
+        rho_mid[d] = (st->ctl[kind].twolag >= 2) ? cm / sqrt(vs * vm) : __longlong_as_double(0x7ff8000000000000LL);
+    }
 }
 
 // Rank of each replacement among the K replacements (ties broken by chain index), and the sorted copy of their keys.
@@ -591,6 +641,9 @@ struct MergeParams {
     const double* new_logP;
     const double* rho;         // [kinds][D+1] start/end correlations of this batch (k_chain_corr), per sampler kind
     double* rho2_ema;          // [kinds][D+1] smoothed, de-biased squares
+    const double* rho_mid;     // [kinds][D+1] start/mid-chain correlations (two-lag control; NaN when not recorded)
+    double* lag_ema;           // [kinds][D+1][2] smoothed (r1, r2)
+    int allow_twolag;          // the exchange carries the mid-chain snapshots (always on one GPU; fused exchange on several)
     int kind_n[kNumKinds];     // chains of each sampler kind in this batch
     double* dead_x;            // rows appended at dead0
     double* dead_logL;
@@ -663,7 +716,9 @@ __global__ void k_merge_commit(const MergeParams p) {
             for (int kind = 0; kind < kNumKinds; ++kind)
                 if (p.kind_n[kind] > 0)
                     adapt_nmcmc(p.st_w, kind, p.kind_n[kind], p.rho != nullptr ? p.rho + kind * nrho : nullptr,
-                                p.rho2_ema + kind * nrho, p.rho != nullptr ? nrho : 0);
+                                p.rho2_ema + kind * nrho, p.rho != nullptr ? nrho : 0,
+                                (p.rho_mid != nullptr && kind == CPN_SAMPLER_MH) ? p.rho_mid + kind * nrho : nullptr,
+                                p.lag_ema + 2 * kind * nrho, kind == CPN_SAMPLER_MH ? p.allow_twolag : 0);
         }
     }
 }

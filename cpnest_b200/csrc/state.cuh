@@ -15,7 +15,12 @@ struct KindCtl {
     double rho_max;                // smoothed max_d |corr(start_d, end_d)| of the last batches (d includes logL)
     unsigned long long batch[4];   // steps, accepted, evals, failed chains of this kind in the last evolve
     int nmcmc;                     // Sampler.Nmcmc
-    int pad_;
+    // Two-lag control (MH): when the start/end correlation stays high although the chains are long, part of it does not decay
+    // with the chain length at all (chains stay in their mode of a multimodal live set).  `twolag` != 0 makes the chains
+    // record a mid-chain snapshot; from corr(start, mid) and corr(start, end) the persistent part c and the decaying part
+    // follow, rho(n) = c + (1 - c) a^n, and the target applies to the decaying part only.
+    short twolag;
+    short stuck;                   // consecutive batches with rho_max far above the target at a chain length near maxmcmc
 };
 
 struct NSState {

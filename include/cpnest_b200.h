@@ -84,8 +84,12 @@ typedef struct cpn_config {
                               relative numbers of MH / slice / HMC chains in every batch (indexed by enum cpn_sampler);
                               the K chains of a batch are split in these proportions, MH chains first.  All zero: every
                               chain is of kind `sampler` */
-    int32_t reserved_;
+    int32_t flags;         /* enum cpn_config_flags */
 } cpn_config;
+
+enum cpn_config_flags {
+    CPN_NO_TWO_LAG = 1     /* keep the single-lag chain-length control (start/end correlation only) even when it saturates */
+};
 
 /* NestedSampler / _NSintegralState observable state (cpnest/NestedSampling.py:88-144, 254-262) */
 typedef struct cpn_state {

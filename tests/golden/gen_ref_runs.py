@@ -58,6 +58,37 @@ class GaussianMeanSigma(cpnest.model.Model):
         return -np.log(p["sigma"]) - np.log(10) - np.log(0.95)
 
 
+class GaussianND(cpnest.model.Model):
+    """examples/test_50d.py:5-28 (iid unit Gaussian in a [-10, 10]^D box; no force: the HMC runs use the flat-prior force)"""
+
+    def __init__(self, dim):
+        self.names = ["{0}".format(i) for i in range(dim)]
+        self.bounds = [[-10, 10] for _ in range(dim)]
+
+    def log_likelihood(self, p):
+        return np.sum([-0.5 * p[n] ** 2 - 0.5 * np.log(2.0 * np.pi) for n in p.names])
+
+    def force(self, p):
+        return np.zeros(1, dtype={"names": p.names, "formats": ["f8" for _ in p.names]})
+
+
+class Gaussian10D(GaussianND):
+    def __init__(self):
+        GaussianND.__init__(self, 10)
+
+
+class Gaussian50D(GaussianND):
+    def __init__(self):
+        GaussianND.__init__(self, 50)
+
+
+class Gaussian2DForce(Gaussian2D):
+    """tests/test_2d_hmc.py:5-24"""
+
+    def force(self, p):
+        return np.zeros(1, dtype={"names": p.names, "formats": ["f8" for _ in p.names]})
+
+
 RUNS = [
     # name, model, CPNest keywords (the reference's own tests: tests/test_2d.py:30, tests/test_ring.py:31,
     # tests/test_gaussian.py:31, tests/test_2d_slice.py:30 with smaller maxmcmc to keep the recipe short)
@@ -65,22 +96,35 @@ RUNS = [
     ("ring_mh", Ring, dict(nlive=1000, nthreads=8, maxmcmc=1000, poolsize=1000, seed=1234)),
     ("gaussian_mean_sigma_mh", GaussianMeanSigma, dict(nlive=1000, nthreads=8, maxmcmc=500, poolsize=1000, seed=1234)),
     ("gaussian2d_slice", Gaussian2D, dict(nlive=1000, nthreads=8, nslice=8, maxmcmc=1000, poolsize=1000, seed=4321)),
+    # round 2: beyond two dimensions, and the third sampler (tests/test_2d_hmc.py:34; examples/test_50d.py:37 with MH)
+    ("gaussian10d_mh", Gaussian10D, dict(nlive=1000, nthreads=8, maxmcmc=1000, poolsize=1000, seed=1234)),
+    ("gaussian2d_hmc", Gaussian2DForce, dict(nlive=1000, nthreads=8, nhamiltonian=8, maxmcmc=200, poolsize=1000, seed=1234)),
+    ("gaussian50d_mh", Gaussian50D, dict(nlive=1000, nthreads=8, maxmcmc=100, poolsize=1000, seed=1234)),
 ]
 
 
 def main():
+    # python gen_ref_runs.py [name ...]: only these runs are (re)made, the others are kept from the existing file (the
+    # reference draws from the unseeded stdlib `random`: a rerun gives another realisation)
+    only = set(sys.argv[1:])
+    path = os.path.join(HERE, "ref_runs.json")
+    old = {r["name"]: r for r in json.load(open(path))} if (only and os.path.exists(path)) else {}
     out = []
     for name, cls, kw in RUNS:
+        if only and name not in only:
+            if name in old:
+                out.append(old[name])
+            continue
         tmp = tempfile.mkdtemp(prefix="cpnest_ref_run_")
         t0 = time.time()
         work = cpnest.CPNest(cls(), verbose=0, output=tmp, **kw)
         work.run()
         dt = time.time() - t0
         pos = work.posterior_samples
-        names = list(cls.names)
+        names = list(work.user.names)
         rs = np.random.RandomState(0)
         keep = np.sort(rs.permutation(len(pos))[:1500])
-        rec = dict(name=name, kwargs=kw, names=names, bounds=cls.bounds, logZ=float(work.NS.logZ), info=float(work.NS.state.info),
+        rec = dict(name=name, kwargs=kw, names=names, bounds=work.user.bounds, logZ=float(work.NS.logZ), info=float(work.NS.state.info),
                    n_posterior=int(len(pos)), n_nested=int(len(work.nested_samples)), wall_s=round(dt, 2),
                    posterior={n: [float(v) for v in np.asarray(pos[n]).ravel()[keep]] for n in names},
                    posterior_mean={n: float(np.mean(pos[n])) for n in names},
@@ -88,7 +132,6 @@ def main():
         print(name, "logZ %.4f H %.3f posterior %d samples, %.1f s" % (rec["logZ"], rec["info"], rec["n_posterior"], dt), flush=True)
         out.append(rec)
         shutil.rmtree(tmp, ignore_errors=True)
-    path = os.path.join(HERE, "ref_runs.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0, separators=(",", ":"))
         f.write("\n")

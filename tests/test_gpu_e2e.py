@@ -244,3 +244,21 @@ def test_correlated_gaussian_50d_logz():
         ref = np.array([m.log_likelihood(x) for x in dead[-200:, :50]])
         assert np.allclose(dead[-200:, 50], ref, rtol=1e-11, atol=0)
         assert s["failed_chains"] == 0
+
+
+def test_two_lag_control_on_a_bimodal_live_set():
+    """20-D mixture of two separated Gaussians (BASELINE config 5's stand-in): chains stay in their mode, so the start/end
+    correlation has a part that no chain length removes.  The single-lag control reads it as "not decorrelated" and pins the
+    chain length at maxmcmc; the two-lag control (mid-chain snapshot: rho(n) = c + (1 - c) a^n) applies the target to the
+    decaying part and settles on much shorter chains - with the same evidence."""
+    mix = dict(w=0.3, m1=-2.5, s1=1.0, m2=2.5, s2=1.0)
+    res = {}
+    for two in (False, True):
+        e, s, logz, ins, nb = run_ns("gaussian_mixture_nd", [[-10, 10]] * 20, nlive=4000, K=1000, maxmcmc=2000, params=mix, seed=31,
+                                     two_lag=two)
+        with e:
+            check_logz(s, logz, -20 * math.log(20.0), 4000)
+            res[two] = (s["total_steps"], s["nmcmc"], s["rho_max"])
+    assert res[False][1] > 1500, res                   # pinned (near) maxmcmc
+    assert res[True][1] < 0.6 * res[False][1], res     # the decaying part alone needs much less
+    assert res[True][0] < 0.75 * res[False][0], res
