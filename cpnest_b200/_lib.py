@@ -38,6 +38,7 @@ class cpn_state(C.Structure):
         ("failed_chains", C.c_int64), ("nmcmc", C.c_int32), ("done", C.c_int32),
         ("slice_mu", C.c_double), ("hmc_dt", C.c_double),
         ("rho_kind", C.c_double * 3), ("nmcmc_kind", C.c_int32 * 3), ("chains_kind", C.c_int32 * 3),
+        ("two_lag_kind", C.c_int32 * 3), ("rho_decay_kind", C.c_double * 3),
     ]
 
     def as_dict(self):

@@ -372,6 +372,9 @@ static void init_state(cpn_ctx* c, NSState* s) {
         // +1.0 sigma (+0.09 nats) mean deviation of logZ at 0.1 and none at 0.05
         s->ctl[k].rho_target = c->cfg.rho_target > 0 ? c->cfg.rho_target : (k == CPN_SAMPLER_SLICE ? 0.05 : 0.1);
         s->ctl[k].rho_max = -1.0;
+        s->ctl[k].rho_decay = -1.0;
+        s->ctl[k].ne_ref = 0.0;
+        s->ctl[k].rho_ref = 0.0;
     }
     s->nmcmc_safety = c->cfg.nmcmc_safety > 0 ? c->cfg.nmcmc_safety : 5.0;
     s->nmcmc_tau = (double)c->N / s->nmcmc_safety;        // tau = poolsize / safety (sampler.py:166)
@@ -1553,6 +1556,8 @@ extern "C" int cpn_get_state(cpn_ctx* c, cpn_state* o) {
         o->rho_kind[k] = s->ctl[k].rho_max;
         o->nmcmc_kind[k] = s->ctl[k].nmcmc;
         o->chains_kind[k] = c->last_kb[k + 1] - c->last_kb[k];
+        o->two_lag_kind[k] = s->ctl[k].twolag;
+        o->rho_decay_kind[k] = s->ctl[k].rho_decay;
     }
     o->slice_mu = s->slice_mu; o->hmc_dt = s->hmc_dt;
     return 0;

@@ -232,27 +232,26 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, c
         }
         k.rho_max = sqrt(fmax(qmax, 0.0));
     }
-    // Two-lag estimate (MH chains that leave a mid-chain snapshot, KindCtl::twolag): with r1 = corr(start, mid) at lag n/2
-    // and r2 = corr(start, end) at lag n, rho(n) = c + (1 - c) a^n gives the part that does not decay,
-    // c = (r2 - r1^2) / (1 + r2 - 2 r1), and the part that does, (r2 - c) / (1 - c) = a^n: chains in separated modes keep
-    // c > 0 whatever their length, and only the decaying part tells how long a chain has to be.
+    // Two-lag estimate (MH chains that leave a mid-chain snapshot, KindCtl::twolag).  A chain in a multimodal live set is
+    // x_t = (centre of its mode) + z_t: the centre never changes, so corr(start, end) keeps a part no chain length removes.
+    // The increments d1 = mid - start and d2 = end - mid do not contain the centre.  For a stationary z with autocovariance
+    // g(h) = g(0) q^(h / (n/2)):   corr(d1, d2) = (2 g(n/2) - g(0) - g(n)) / (2 (g(0) - g(n/2))) = -(1 - q) / 2,
+    // i.e. q = 1 + 2 corr(d1, d2) is the within-mode correlation over half a chain (0: forgotten, 1: frozen) and q^2 the part
+    // of the start/end correlation that decays with the chain length: the target applies to it.
     double dmax = -1.0;
     if (rho != nullptr && rho_mid != nullptr && lag_ema != nullptr && k.twolag >= 2) {
         const bool first2 = k.twolag == 2;
         dmax = 0.0;
         for (int d = 0; d < nrho; ++d) {
-            double r1 = rho_mid[d], r2 = rho[d];
-            if (!(r1 == r1) || !(r2 == r2)) { r1 = 0.0; r2 = 0.0; }
-            const double e1 = first2 ? r1 : (1.0 - a) * lag_ema[2 * d] + a * r1;
-            const double e2 = first2 ? r2 : (1.0 - a) * lag_ema[2 * d + 1] + a * r2;
-            lag_ema[2 * d] = e1;
-            lag_ema[2 * d + 1] = e2;
-            const double den = 1.0 + e2 - 2.0 * e1;
-            const double c = den > 0.05 ? fmin(fmax((e2 - e1 * e1) / den, 0.0), 0.99) : 0.0;
-            const double dec = fmin(fmax((e2 - c) / (1.0 - c), 0.0), 1.0);
-            if (dec > dmax) dmax = dec;
+            double ci = rho_mid[d];                          // corr(d1, d2) of this batch
+            if (!(ci == ci)) ci = -0.5;                      // a coordinate that does not move at all carries no information
+            const double e1 = first2 ? ci : (1.0 - a) * lag_ema[d] + a * ci;
+            lag_ema[d] = e1;
+            const double q = fmin(fmax(1.0 + 2.0 * e1, 0.0), 1.0);
+            if (q * q > dmax) dmax = q * q;
         }
     }
+    k.rho_decay = dmax;
     if (k.twolag > 0 && k.twolag < 1000) k.twolag += 1;
     if (!st->adapt) return;
     const double safety = st->nmcmc_safety;
@@ -268,11 +267,15 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, c
         double t2 = mean_len * log(tgt2) / log(r2);
         t2 = fmin(fmax(t2, 0.5 * ne), 2.0 * ne);
         target = fmax(target, t2);
-        // switch to the two-lag estimate when the correlation stays far above the target at a chain length near maxmcmc
+        // Switch to the two-lag estimate when lengthening the chains no longer lowers the correlation: every time the chain
+        // length has grown by 1.6x since the reference batch, rho_max is compared with its value there; still above the
+        // target and not even 20% lower means that what is left does not decay with the chain length.
         if (allow_twolag && k.twolag == 0) {
-            const bool far = k.rho_max > 2.5 * k.rho_target && ne >= 0.5 * (double)st->maxmcmc;
-            k.stuck = far ? (short)(k.stuck + 1) : (short)0;
-            if (k.stuck >= 3) k.twolag = 1;
+            if (!(k.ne_ref > 0.0) || ne < k.ne_ref) { k.ne_ref = ne; k.rho_ref = k.rho_max; }
+            else if (ne >= 1.6 * k.ne_ref || ne >= 0.999 * (double)st->maxmcmc) {
+                if (k.rho_max > 1.1 * k.rho_target && k.rho_max > 0.8 * k.rho_ref && ne > 1.2 * k.ne_ref) k.twolag = 1;
+                else { k.ne_ref = ne; k.rho_ref = k.rho_max; }
+            }
         }
     }
     ne = (1.0 - a) * ne + a * target;
@@ -412,7 +415,7 @@ __global__ void k_adapt_hmc_dt(NSState* st) {
 // segments in order and writes rho[d] and st->ctl[kind].batch[].  The grid grows with the batch, so the replicated
 // statistics of a multi-GPU batch (K = all ranks' chains) do not serialise on D+2 blocks.
 constexpr int kCorrSeg = 4 * kCorrThreads;
-constexpr int kCorrMom = 8;      // s, e, ss, ee, se and - two-lag control - m, mm, sm (m: the mid-chain snapshot)
+constexpr int kCorrMom = 9;      // s, e, ss, ee, se and - two-lag control - m, mm, sm, me (m: the mid-chain snapshot)
 __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSState* st, int kind, int j0, int j1, int D, int Dp,
                                                                      const int* __restrict__ start_slot, const double* __restrict__ live_x,
                                                                      const double* __restrict__ live_logL, const double* __restrict__ new_x,
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSSta
     const int d = blockIdx.x, sg = blockIdx.y, nseg = gridDim.y, tid = threadIdx.x;
     const int a0 = j0 + sg * kCorrSeg, a1 = min(j1, a0 + kCorrSeg);
     const bool mid = mid_x != nullptr && st->ctl[kind].twolag >= 2;       // this batch's chains left snapshots
-    double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (d == D + 1) {
         // counters as doubles: exact up to 2^53
         for (int j = a0 + tid; j < a1; j += kCorrThreads) {
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSSta
             a[0] += s; a[1] += e; a[2] += s * s; a[3] += e * e; a[4] += s * e;
             if (mid) {
                 const double m = ((d < D) ? mid_x[(size_t)j * Dp + d] : mid_logL[j]) - ce;
-                a[5] += m; a[6] += m * m; a[7] += s * m;
+                a[5] += m; a[6] += m * m; a[7] += s * m; a[8] += m * e;
             }
         }
     }
@@ -472,7 +475,7 @@ __global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg
     if (st->done) return;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d > D + 1) return;
-    double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int sg = 0; sg < nseg; ++sg)
         for (int k = 0; k < kCorrMom; ++k) a[k] += part[((size_t)d * nseg + sg) * kCorrMom + k];
     if (d == D + 1) {
@@ -484,8 +487,11 @@ __global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg
     const double cv = a[4] - a[0] * a[1] / nn;
     rho[d] = cv / sqrt(vs * ve);
     if (rho_mid != nullptr) {
-        const double vm = a[6] - a[5] * a[5] / nn, cm = a[7] - a[0] * a[5] / nn;
-        rho_mid[d] = (st->ctl[kind].twolag >= 2) ? cm / sqrt(vs * vm) : __longlong_as_double(0x7ff8000000000000LL);
+        // correlation of the increments d1 = mid - start, d2 = end - mid from the second moments of (s, m, e)
+        const double vm = a[6] - a[5] * a[5] / nn, csm = a[7] - a[0] * a[5] / nn, cme = a[8] - a[5] * a[1] / nn;
+        const double v1 = vm - 2.0 * csm + vs, v2 = ve - 2.0 * cme + vm;
+        const double c12 = cme - vm - cv + csm;
+        rho_mid[d] = (st->ctl[kind].twolag >= 2) ? c12 / sqrt(v1 * v2) : __longlong_as_double(0x7ff8000000000000LL);
     }
 }
 
@@ -641,8 +647,8 @@ struct MergeParams {
     const double* new_logP;
     const double* rho;         // [kinds][D+1] start/end correlations of this batch (k_chain_corr), per sampler kind
     double* rho2_ema;          // [kinds][D+1] smoothed, de-biased squares
-    const double* rho_mid;     // [kinds][D+1] start/mid-chain correlations (two-lag control; NaN when not recorded)
-    double* lag_ema;           // [kinds][D+1][2] smoothed (r1, r2)
+    const double* rho_mid;     // [kinds][D+1] correlation of the two half-chain increments (two-lag control; NaN when not recorded)
+    double* lag_ema;           // [kinds][D+1] (x2 reserved) its moving average
     int allow_twolag;          // the exchange carries the mid-chain snapshots (always on one GPU; fused exchange on several)
     int kind_n[kNumKinds];     // chains of each sampler kind in this batch
     double* dead_x;            // rows appended at dead0

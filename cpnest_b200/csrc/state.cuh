@@ -13,14 +13,16 @@ struct KindCtl {
     double nmcmc_exact;            // Sampler.Nmcmc_exact
     double rho_target;             // chains run until the start/end correlation across the batch falls to this
     double rho_max;                // smoothed max_d |corr(start_d, end_d)| of the last batches (d includes logL)
+    double rho_decay;              // two-lag control: max_d of the decaying part of that correlation (-1: not estimated)
+    double ne_ref, rho_ref;        // chain length and rho_max at the last reference batch (does rho fall when chains grow?)
     unsigned long long batch[4];   // steps, accepted, evals, failed chains of this kind in the last evolve
     int nmcmc;                     // Sampler.Nmcmc
     // Two-lag control (MH): when the start/end correlation stays high although the chains are long, part of it does not decay
     // with the chain length at all (chains stay in their mode of a multimodal live set).  `twolag` != 0 makes the chains
-    // record a mid-chain snapshot; from corr(start, mid) and corr(start, end) the persistent part c and the decaying part
-    // follow, rho(n) = c + (1 - c) a^n, and the target applies to the decaying part only.
+    // record a mid-chain snapshot; the two half-chain increments do not contain the mode centre, their correlation gives
+    // the within-mode correlation over half a chain (ns_kernels.cuh adapt_nmcmc), and the target applies to that part only.
     short twolag;
-    short stuck;                   // consecutive batches with rho_max far above the target at a chain length near maxmcmc
+    short stuck;                   // (unused)
 };
 
 struct NSState {

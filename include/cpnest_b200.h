@@ -116,6 +116,8 @@ typedef struct cpn_state {
     double rho_kind[3];
     int32_t nmcmc_kind[3];
     int32_t chains_kind[3];/* chains of each kind in the last batch */
+    int32_t two_lag_kind[3];/* two-lag chain-length control: 0 off, else batches since it was switched on */
+    double rho_decay_kind[3];/* its estimate of the decaying part of the start/end correlation (-1: none) */
 } cpn_state;
 
 const char* cpn_last_error(void);

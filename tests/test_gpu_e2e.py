@@ -248,9 +248,10 @@ def test_correlated_gaussian_50d_logz():
 
 def test_two_lag_control_on_a_bimodal_live_set():
     """20-D mixture of two separated Gaussians (BASELINE config 5's stand-in): chains stay in their mode, so the start/end
-    correlation has a part that no chain length removes.  The single-lag control reads it as "not decorrelated" and pins the
-    chain length at maxmcmc; the two-lag control (mid-chain snapshot: rho(n) = c + (1 - c) a^n) applies the target to the
-    decaying part and settles on much shorter chains - with the same evidence."""
+    correlation has a part that no chain length removes.  The single-lag control reads it as "not decorrelated" and ends with
+    the chain length pinned at maxmcmc; the two-lag control (mid-chain snapshot: the two half-chain increments do not contain
+    the mode centre, q = 1 + 2 corr(d1, d2)) applies the target to the part that decays and needs fewer steps for the same
+    evidence (measured: 2.8e8 -> 2.2e8 steps, final chain length 2000 -> ~900)."""
     mix = dict(w=0.3, m1=-2.5, s1=1.0, m2=2.5, s2=1.0)
     res = {}
     for two in (False, True):
@@ -258,7 +259,9 @@ def test_two_lag_control_on_a_bimodal_live_set():
                                      two_lag=two)
         with e:
             check_logz(s, logz, -20 * math.log(20.0), 4000)
-            res[two] = (s["total_steps"], s["nmcmc"], s["rho_max"])
-    assert res[False][1] > 1500, res                   # pinned (near) maxmcmc
-    assert res[True][1] < 0.6 * res[False][1], res     # the decaying part alone needs much less
-    assert res[True][0] < 0.75 * res[False][0], res
+            res[two] = (s["total_steps"], s["nmcmc"], s["rho_max"], s["two_lag_kind"][0], s["rho_decay_kind"][0])
+    assert res[False][1] > 1800 and res[False][3] == 0, res      # pinned at maxmcmc, two-lag never on
+    assert res[True][3] > 0 and 0 <= res[True][4] < 0.2, res       # switched on; the decaying part is small at the end
+    assert res[True][2] > 0.25, res                                # while the raw start/end correlation stays large
+    assert res[True][1] < 0.75 * res[False][1], res
+    assert res[True][0] < 0.9 * res[False][0], res

@@ -28,7 +28,7 @@ def test_abi_struct_sizes_match_header():
     # cpn_config: 8 int32 + uint64 + double + 4 int32 + double + 4 int32; cpn_state: 8 doubles + 7 int64 + 2 int32 +
     # 2 doubles + 3 doubles + 6 int32
     assert ctypes.sizeof(_lib.cpn_config) == 8 * 4 + 8 + 8 + 4 * 4 + 8 + 4 * 4
-    assert ctypes.sizeof(_lib.cpn_state) == 8 * 8 + 7 * 8 + 2 * 4 + 2 * 8 + 3 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.cpn_state) == 8 * 8 + 7 * 8 + 2 * 4 + 2 * 8 + 3 * 8 + 9 * 4 + 4 + 3 * 8
 
 
 def test_abi_struct_layout_matches_a_c_compiler(tmp_path):
