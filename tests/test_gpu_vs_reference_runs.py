@@ -23,6 +23,10 @@ def _model(name):
     import cpnest_b200.models as M
     if name.startswith("gaussian2d"):
         return M.GaussianModel(2)
+    if name.startswith("gaussian10d"):
+        return M.GaussianModel(10)
+    if name.startswith("gaussian50d"):
+        return M.GaussianModel(50)
     if name.startswith("ring"):
         return M.RingModel()
     if name.startswith("gaussian_mean_sigma"):
@@ -30,24 +34,37 @@ def _model(name):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["gaussian2d_mh", "ring_mh", "gaussian_mean_sigma_mh", "gaussian2d_slice"])
+@pytest.mark.parametrize("name", ["gaussian2d_mh", "ring_mh", "gaussian_mean_sigma_mh", "gaussian2d_slice", "gaussian10d_mh",
+                                  "gaussian50d_mh", "gaussian2d_hmc"])
 def test_run_agrees_with_the_reference_run(name, tmp_path):
     import cpnest_b200 as cpnest
     ref = _runs()[name]
     kw = dict(ref["kwargs"])
     model = _model(name)
     assert list(model.names) == ref["names"]
+    if name == "gaussian50d_mh":
+        # examples/test_50d.py:37 caps the chains at maxmcmc = 100 steps; the reference's run recorded with that value sits
+        # 2.6 sigma below the analytic evidence (-150.52 vs -149.79).  The device run gets room to decorrelate.
+        kw["maxmcmc"] = 5000
     work = cpnest.CPNest(model, output=str(tmp_path), verbose=0, **kw)
     work.run()
     # log-evidence: the two runs are independent estimates with errors sqrt(H/nlive) each
     s_dev = math.sqrt(work.NS.state.info / kw["nlive"])
     s_ref = math.sqrt(ref["info"] / kw["nlive"])
-    assert abs(work.NS.logZ - ref["logZ"]) < 3.0 * math.hypot(s_dev, s_ref), (work.NS.logZ, ref["logZ"], s_dev, s_ref)
-    assert abs(work.NS.state.info - ref["info"]) < 0.25 * max(1.0, ref["info"])
+    if name == "gaussian2d_hmc":
+        # the reference's own HMC run of tests/test_2d_hmc.py recorded here gave logZ = -6.324, 5.7 sigma below the analytic
+        # -5.991 (its spline-estimated reflection normals): agreement is asked of the analytic value
+        assert abs(ref["logZ"] - model.analytic_log_Z) > 3.0 * s_ref
+        assert abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * s_dev, (work.NS.logZ, model.analytic_log_Z, s_dev)
+    else:
+        assert abs(work.NS.logZ - ref["logZ"]) < 3.0 * math.hypot(s_dev, s_ref), (work.NS.logZ, ref["logZ"], s_dev, s_ref)
+        assert abs(work.NS.state.info - ref["info"]) < 0.25 * max(1.0, ref["info"])
+    if hasattr(model, "analytic_log_Z") and not name.startswith("gaussian_mean_sigma"):
+        assert abs(work.NS.logZ - model.analytic_log_Z) < 3.0 * s_dev
     # posterior: two-sample KS per parameter on thinned, (nearly) independent draws, plus first and second moments
     pos = work.posterior_samples
     rs = np.random.RandomState(1)
-    for n in ref["names"]:
+    for n in ref["names"][:8]:                          # (50-D: the first eight parameters)
         mine = np.asarray(pos[n]).ravel()
         mine = mine[rs.permutation(len(mine))[:1500]]
         theirs = np.asarray(ref["posterior"][n])
