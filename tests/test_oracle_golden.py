@@ -290,14 +290,26 @@ def test_recorded_reference_runs_are_sane():
     import json
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_runs.json")) as f:
         runs = {r["name"]: r for r in json.load(f)}
-    assert set(runs) == {"gaussian2d_mh", "ring_mh", "gaussian_mean_sigma_mh", "gaussian2d_slice"}
+    assert set(runs) == {"gaussian2d_mh", "ring_mh", "gaussian_mean_sigma_mh", "gaussian2d_slice",
+                         "gaussian10d_mh", "gaussian50d_mh", "gaussian2d_hmc"}
     anchors = {"gaussian2d_mh": -2 * math.log(20.0), "gaussian2d_slice": -2 * math.log(20.0), "ring_mh": -2.318358,
                # normalised 1/sigma prior on [0.05, 1] x uniform mean on [-5, 5]: Z = 1/10 up to the tails beyond |mean| = 5
-               "gaussian_mean_sigma_mh": -math.log(10.0)}
+               "gaussian_mean_sigma_mh": -math.log(10.0),
+               "gaussian10d_mh": -10 * math.log(20.0), "gaussian50d_mh": -50 * math.log(20.0),
+               "gaussian2d_hmc": -2 * math.log(20.0)}
+    # how far the reference's own run may sit from the analytic value, in its own sigma = sqrt(H/nlive): 3 everywhere except
+    # the HMC run (spline-estimated reflection normals; recorded at 5.7 sigma) — the GPU test of that
+    # fixture asserts the same fact and compares the device run with the analytic value instead
+    allowed = {"gaussian2d_hmc": 7.0}
     for name, r in runs.items():
         sigma = math.sqrt(r["info"] / r["kwargs"]["nlive"])
-        assert abs(r["logZ"] - anchors[name]) < 3.0 * sigma, (name, r["logZ"], anchors[name], sigma)
+        assert abs(r["logZ"] - anchors[name]) < allowed.get(name, 3.0) * sigma, (name, r["logZ"], anchors[name], sigma)
         assert r["n_posterior"] > 1500 and all(len(v) == 1500 for v in r["posterior"].values())
+    # information of an iid unit Gaussian in [-10, 10]^D: H = D (ln 20 - (1 + ln 2 pi) / 2)
+    for name, d in (("gaussian10d_mh", 10), ("gaussian50d_mh", 50)):
+        h = d * (math.log(20.0) - 0.5 * (1.0 + math.log(2.0 * math.pi)))
+        assert abs(runs[name]["info"] - h) < 0.1 * h, (name, runs[name]["info"], h)
+        assert all(abs(runs[name]["posterior_var"][n] - 1.0) < 0.25 for n in runs[name]["names"][:8])
     g = runs["gaussian2d_mh"]
     assert all(abs(g["posterior_mean"][n]) < 0.1 and abs(g["posterior_var"][n] - 1.0) < 0.1 for n in ("x", "y"))
     ms = runs["gaussian_mean_sigma_mh"]
