@@ -233,8 +233,10 @@ static int pick_config(int D, int lanes, int functor, long long chains, int* G, 
     }
     if (functor == CPN_GAUSS_MIXTURE && D <= 32) { *G = 32; *E = 1; return 0; }   // lanes split the data sum
     if (functor == CPN_GAUSS_CORR && D > 16) {
-        // the D x D mat-vec of the likelihood is the step's critical path: the widest group walks it in the fewest
-        // dependent multiply-adds per lane (measured at D = 50, K = 4704: 0.39 ns per chain-step with 32 lanes, 0.56 with 16)
+        // the D x D mat-vec of the likelihood is the step's cost.  Up to 64 dimensions: 16 lanes per chain, the eight chains of
+        // a block are the columns of FP64 tensor-core products (models.cuh log_likelihood_block).  Beyond: the widest group
+        // walks the mat-vec in the fewest dependent multiply-adds per lane.
+        if (D <= 64 && min_E(16, D)) { *G = 16; *E = min_E(16, D); return 0; }
         const int e = min_E(32, D);
         if (e) { *G = 32; *E = e; return 0; }
     }
@@ -272,6 +274,7 @@ static int run_eval(cpn_ctx* c, int G, int E, const EvalParams& p) {
 static int run_mh(cpn_ctx* c, int G, int E, int replay, const MHParams& p) {
     if (c->cfg.functor == CPN_USER) {
         if (replay) return fail("replay entry points are not available for a user functor");
+        if (p.cycle_len > kCycInline) return fail("a user functor takes proposal cycles of up to %d entries (got %d)", kCycInline, p.cycle_len);
         return user_launch(c, "mh", G, E, &p, p.j1 - p.j0, p.Dp, kMHThreads);
     }
     if (kMH[c->cfg.functor](G, E, replay, p, chain_stream(c))) return fail("no MH kernel for G=%d E=%d", G, E);
@@ -539,7 +542,11 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
     CK(h2d_sync(c->d_lo, lo, D * sizeof(double)));
     CK(h2d_sync(c->d_hi, hi, D * sizeof(double)));
     if (nb) CK(h2d_sync(c->d_blob, blob, nb * sizeof(double)));
-    if (dalloc(&c->d_x, (size_t)N * Dp + kRowSlack) || dalloc(&c->d_logL, N) || dalloc(&c->d_logP, N)) return 1;
+    // the live rows and, behind them, the two buffers of eigen-directions: one array, so the MH kernel gathers every row of a
+    // step from one base with a 32-bit row number (MHParams::eig_row0)
+    if (dalloc(&c->d_x, (size_t)(N + 2 * D) * Dp + kRowSlack) || dalloc(&c->d_logL, N) || dalloc(&c->d_logP, N)) return 1;
+    c->d_eigvec[0] = c->d_x + (size_t)N * Dp;
+    c->d_eigvec[1] = c->d_x + (size_t)(N + D) * Dp;
     for (int b = 0; b < 2; ++b)
         if (dalloc(&c->d_order[b], N) || dalloc(&c->d_skeys[b], N)) return 1;
     c->Npad = 1;
@@ -563,8 +570,8 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
         dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
-        dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigvec[0], (size_t)D * Dp + kRowSlack) || dalloc(&c->d_eigscale[0], D) ||
-        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigvec[1], (size_t)D * Dp + kRowSlack) || dalloc(&c->d_eigscale[1], D) ||
+        dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigscale[0], D) ||
+        dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigscale[1], D) ||
         dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) ||
         dalloc(&c->d_covbuf[0], (size_t)D * D) || dalloc(&c->d_covbuf[1], (size_t)D * D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
         dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))
@@ -623,7 +630,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     if (c->acc_stream) cudaStreamSynchronize(c->acc_stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rho_mid, c->d_lag_ema, c->d_rank, c->d_snew, c->d_bucket, c->d_nle, c->d_corr_part, c->d_start_x, c->d_start_logL,
-                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigvec[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigvec[1], c->d_eigscale[1],
+                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)
@@ -858,6 +865,7 @@ static void fill_mh(cpn_ctx* c, MHParams* p) {
     memcpy(p->cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
     p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
     p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
+    p->eig_row0 = c->N + c->eig_cur * c->D;
     p->chain_log = c->d_chain_log; p->chain_log_count = c->d_chain_log_count;
     p->chain_log_n = c->chain_log_n; p->chain_log_cap = c->chain_log_cap;
 }
@@ -1997,10 +2005,12 @@ extern "C" int cpn_trace_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32
     int *dst = nullptr, *dac = nullptr, *dnev = nullptr;
     int rc = 1;
     do {
-        if (dalloc(&dex, ex.size() + kRowSlack) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) ||
-            dalloc(&dev, ev.size() + kRowSlack) || dalloc(&des, D) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) ||
+        // (the eigen-directions behind the ensemble rows, as in the engine's own arrays)
+        if (dalloc(&dex, ex.size() + ev.size() + kRowSlack) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) ||
+            dalloc(&des, D) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) ||
             dalloc(&dop, C) || dalloc(&dst, C) || dalloc(&dac, C) || dalloc(&dnev, C) || dalloc(&ddraw, ndraw))
             break;
+        dev = dex + ex.size();
         if (h2d_sync(dex, ex.data(), ex.size() * sizeof(double)) != cudaSuccess || h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)) != cudaSuccess ||
             h2d_sync(dsl, sl.data(), C * sizeof(double)) != cudaSuccess || h2d_sync(dsp, sp.data(), C * sizeof(double)) != cudaSuccess ||
             h2d_sync(dev, ev.data(), ev.size() * sizeof(double)) != cudaSuccess || h2d_sync(des, es.data(), D * sizeof(double)) != cudaSuccess) {
@@ -2014,7 +2024,7 @@ extern "C" int cpn_trace_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32
         p.lo = c->d_lo; p.hi = c->d_hi;
         p.cycle = c->d_cycle; p.cycle_len = c->cycle_len; p.cycle_pos0 = cycle_idx % c->cycle_len;
         memcpy(p.cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
-        p.eig_scale = des; p.eig_vec = dev;
+        p.eig_scale = des; p.eig_vec = dev; p.eig_row0 = P;
         p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.maxmcmc = maxmcmc;
         p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
         p.padded = Dp >= G * E;
@@ -2043,7 +2053,7 @@ extern "C" int cpn_trace_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32
         }
         rc = 0;
     } while (0);
-    void* fr[] = {dex, dsx, dsl, dsp, dev, des, dox, dol, dop, dst, dac, dnev, ddraw};
+    void* fr[] = {dex, dsx, dsl, dsp, des, dox, dol, dop, dst, dac, dnev, ddraw};
     for (void* q : fr)
         if (q) cudaFree(q);
     return rc;

@@ -90,7 +90,9 @@ struct Chain {
 
     // false: the whole warp lies beyond the batch (or the run is over) and must return.
     // team > 1 (G == 32 only): the block's `team` warps all own chain blockIdx.x; team_buf is block-shared scratch
-    __device__ __forceinline__ bool begin(const ChainParams& p, double* smem, bool replay, int team = 1, double* team_buf = nullptr) {
+    // keep_all: warps beyond the batch stay (they shadow the last chain): the kernel runs block barriers
+    __device__ __forceinline__ bool begin(const ChainParams& p, double* smem, bool replay, int team = 1, double* team_buf = nullptr,
+                                          bool keep_all = false) {
         if (!replay && p.state != nullptr && p.state->done) return false;
         const int cpb = kMHThreads / G;
         const int nchains = p.j1 - p.j0;
@@ -103,7 +105,7 @@ struct Chain {
             valid = m.team_rank == 0;              // one warp hands the chain back
         } else {
             c = blockIdx.x * cpb + (int)threadIdx.x / G;
-            if ((c & ~(32 / G - 1)) >= nchains) return false;
+            if (!keep_all && (c & ~(32 / G - 1)) >= nchains) return false;
             valid = c < nchains;
         }
         if (!valid && team == 1) c = nchains - 1;

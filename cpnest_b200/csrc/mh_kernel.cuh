@@ -14,7 +14,7 @@
 
 namespace cpn {
 
-constexpr int kCycInline = 256;   // proposal cycles up to this length travel in the launch parameters (constant bank)
+constexpr int kCycInline = 1024;  // proposal cycles up to this length travel in the launch parameters (constant bank)
 
 struct MHParams : ChainParams {
     // proposal cycle + eigen directions
@@ -23,6 +23,8 @@ struct MHParams : ChainParams {
     int cycle_pos0;
     const double* eig_scale;  // [D]     sqrt|lambda_i|
     const double* eig_vec;    // [D][Dp] row i = eigenvector i
+    int eig_row0;             // production: eig_vec == ens_x + eig_row0 * Dp (the eigen-directions live behind the live rows in one
+                              // allocation, so a step gathers every row it needs from one base with a 32-bit row number)
     // replay (parity) mode
     const double* tape;       // [chains][maxmcmc][8]
     int compat;               // fp32 rounding of LivePoint scalars (cpnest/parameter.pyx:96-120)
@@ -82,26 +84,9 @@ struct DrawFeed {
     uint4* row;      // this lane's 32-byte row of the block's table
     StepIn own;      // G == 1 only
     // dump: where to record the 8 values of this step (test entry), or null
+    // tag: the kind rides in the top bits of i0 (kernels that cannot read it through the uniform datapath)
     __device__ __forceinline__ void refill(int kind, uint32_t step, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1,
-                                           uint32_t ens_n, uint32_t D, const double* eig_scale, double* dump) {
-#ifdef CPN_EXP_CHEAP_REFILL
-        // experiment only: an upper bound on what taking the draws off the chain warps could gain
-        if (kind >= 0) {
-            uint32_t h = (cid_lo * 2654435761u) ^ (step * 40503u + 12345u);
-            h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
-            const uint32_t i0 = u32_to_index(h, kind == CPN_EIGEN ? D : ens_n - 2);
-            const float gg = (float)(int)(h >> 8) * (1.0f / 8388608.0f) - 1.0f;
-            uint32_t w3 = __float_as_uint(kind == CPN_WALK ? gg : (kind == CPN_STRETCH ? 1.0f + 0.3f * gg : 1.0f + 1e-4f * gg));
-            uint32_t w4 = __float_as_uint(-0.5f * gg), w5 = w4;
-            if (kind == CPN_EIGEN) { const double jump = 0.05 * (double)gg; w4 = (uint32_t)__double2loint(jump); w5 = (uint32_t)__double2hiint(jump); }
-            const double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : -0.5;
-            __syncwarp();
-            row[0] = make_uint4(i0, i0 + 1, i0 + 2, w3);
-            row[1] = make_uint4(w4, w5, (uint32_t)__double2loint(thr), (uint32_t)__double2hiint(thr));
-            __syncwarp();
-            return;
-        }
-#endif
+                                           uint32_t ens_n, uint32_t D, const double* eig_scale, uint32_t eig_row0, bool tag, double* dump) {
         const Philox4 r = philox4x32_10(cid_lo, cid_hi, step, 0u, k0, k1);
         double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : log(u32_to_unit_open(r.v[3]));
         uint32_t i0 = u32_to_index(r.v[0], kind == CPN_EIGEN ? D : ens_n);       // EIGEN: randrange(D), proposal.py:338
@@ -153,7 +138,8 @@ struct DrawFeed {
             }
             dump[7] = thr;
         }
-        i0 |= (uint32_t)kind << kKindShift;
+        if (kind == CPN_EIGEN) i0 += eig_row0;                                    // row of the direction in the joint array
+        if (tag) i0 |= (uint32_t)kind << kKindShift;
         if (G == 1) {                       // a chain per lane: the step is this lane's own
             own.i0 = i0; own.i1 = i1; own.i2 = i2; own.w3 = w3; own.w4 = w4; own.w5 = w5; own.thr = thr;
             return;
@@ -174,28 +160,16 @@ struct DrawFeed {
     }
 };
 
-// The rows a step gathers: WALK three members, DE two, STRETCH one, EIGEN one eigen-direction.  The kind is the same for
-// all chains of a launch.  Every slot of a lane is loaded, also the slots beyond D of the last lanes, which then read the
-// head of the following row (the arrays carry kRowSlack doubles of slack at their end).  Those values are finite and never
-// used: the box test (+-inf bounds), the functors (valid_dim masks) and the final store ignore slots beyond D.
+// The rows a step gathers: WALK three members, DE two, STRETCH one, EIGEN one eigen-direction, all from one array (live rows,
+// then the eigen-directions) through one per-lane base pointer: address = base + row * (8 Dp), one IMAD.WIDE per row.  Every
+// slot of a lane is loaded, also the slots beyond D of the last lanes, which then read the head of the following row (the
+// array carries kRowSlack doubles of slack at its end).  Those values are finite and never used: the box test (+-inf bounds),
+// the functors (valid_dim masks) and the final store ignore slots beyond D.
 template <int G, int E>
-__device__ __forceinline__ void gather_rows(const Group<G>& g, const double* ens_x, const double* eig_vec, unsigned Dp,
-                                            const StepIn& s, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
-    const int kind = (int)(s.i0 >> kKindShift);
-    const unsigned lane = (unsigned)g.lane;
-    const double* b0 = (kind == CPN_EIGEN ? eig_vec : ens_x) + ((s.i0 & kIndexMask) * Dp + lane);
+__device__ __forceinline__ void gather_row(const double* lane_base, uint32_t row_bytes, uint32_t row, double (&r)[E]) {
+    const double* b = reinterpret_cast<const double*>(reinterpret_cast<const char*>(lane_base) + (unsigned long long)row * row_bytes);
 #pragma unroll
-    for (int e = 0; e < E; ++e) r0[e] = __ldg(b0 + e * G);
-    if (kind == CPN_WALK || kind == CPN_DE) {
-        const double* b1 = ens_x + (s.i1 * Dp + lane);
-#pragma unroll
-        for (int e = 0; e < E; ++e) r1[e] = __ldg(b1 + e * G);
-    }
-    if (kind == CPN_WALK) {
-        const double* b2 = ens_x + (s.i2 * Dp + lane);
-#pragma unroll
-        for (int e = 0; e < E; ++e) r2[e] = __ldg(b2 + e * G);
-    }
+    for (int e = 0; e < E; ++e) r[e] = __ldg(b + e * G);
 }
 
 // ---- replay (parity) form: the reference's own random numbers from the tape, one IEEE operation per
@@ -239,8 +213,15 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
     // team mode: the block's warps evolve one chain together and split the functor's data sum (models.cuh kTeam)
     constexpr int TEAM = (!REPLAY && G == 32 && Model::kTeam > 1) ? kMHThreads / 32 : 1;
     __shared__ double team_buf[TEAM];
+    // block mode: the chains of the block evaluate the likelihood together (models.cuh block_coop): no warp leaves early,
+    // the warps stay in lock step through the functor's block barriers
+    constexpr bool BLK = !REPLAY && TEAM == 1 && Model::template block_coop<G>;
     Chain<G, E, Model> ch;
-    if (!ch.begin(p, smem, REPLAY, TEAM, team_buf)) return;
+    if (!ch.begin(p, smem, REPLAY, TEAM, team_buf, BLK)) return;
+    if (BLK) {
+        ch.m.block_buf = smem + (Model::kScratch ? (kMHThreads / G) * kScratchRows * p.Dp : 0);
+        if (Model::block_doubles(p.D) > 0) Model::block_prepare(ch.m);
+    }
     const Group<G>& g = ch.g;
     const ModelCtx& m = ch.m;
     const int c = ch.c, D = p.D, nmcmc = ch.nmcmc, maxmcmc = p.maxmcmc;
@@ -336,11 +317,15 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         const uint32_t ens_n = (uint32_t)p.ens_n;
         DrawFeed<G, Model::kFlatPrior> feed;
         feed.row = &feed_tab[threadIdx.x][0];
-        const uint4* grow = &feed_tab[threadIdx.x & ~(G - 1)][0];        // row of this group's lane 0
-        const bool cyc_inline = clen <= kCycInline;
+        // row of this group's lane 0 in the feed table as a shared-window address held in a register (through a generic
+        // pointer the compiler rebuilds the window base from SR_CgaCtaId in front of every read)
+        uint32_t feed_base = (uint32_t)__cvta_generic_to_shared(&feed_tab[threadIdx.x & ~(G - 1)][0]);
+        asm volatile("" : "+r"(feed_base));
+        // KU: the kind of a step is read from the inline cycle through the uniform datapath (uniform branches, no
+        // reconvergence bookkeeping); else (chain-history instantiation, which also takes the cycles too long to travel
+        // inline) it rides in the top bits of the step's first index
+        constexpr bool KU = !LOG;
         double* dump = (p.draws != nullptr && valid) ? p.draws + (size_t)c * maxmcmc * 8 : nullptr;
-        // the two row bases live in registers (opaque to the compiler, which would otherwise re-read them from the constant
-        // bank in front of every gather: a long-latency load on the in-order path of the step)
         // chain history (off unless the caller asked for it): events of this chain go to its slot's ring
         double* clog = nullptr;
         unsigned long long clog_n = 0;
@@ -361,32 +346,52 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         if (LOG && clog != nullptr) log_event(0.0, -1.0);
         const int max_resend = ch.can_restart(p) ? kMaxResend : 0;
         int attempts = 0, attempt_end = maxmcmc;
-        const double* ens_x = p.ens_x;
-        const double* eig_vec = p.eig_vec;
-        asm volatile("" : "+l"(ens_x), "+l"(eig_vec));
-        const unsigned Dp = (unsigned)p.Dp;
-        // The inputs of step `it` (its kind rides in the top bits of i0).  They are drawn G steps at a time, one step per
-        // lane, when the first step of a window is asked for; by then every lane holds the previous window in registers.
+        // per-lane base of the row array (live rows, then the eigen-directions) in registers: opaque to the compiler, which
+        // would otherwise re-read the pointer from the constant bank in front of every gather
+        const double* lane_base = p.ens_x + g.lane;
+        asm volatile("" : "+l"(lane_base));
+        const uint32_t row_bytes = (uint32_t)p.Dp * 8u;
+        const uint32_t eig_row0 = (uint32_t)p.eig_row0;
+        // (the group's ballot mask too: rebuilt from the thread index in every step otherwise)
+        Group<G> gp = g;
+        asm volatile("" : "+r"(gp.gmask));
+        // The inputs of step `it`.  They are drawn G steps at a time, one step per lane, when the first step of a window is
+        // asked for; by then every lane holds the previous window in registers.
         auto load_in = [&](int it) -> StepIn {
             if ((it & (G - 1)) == 0) {                                   // this lane prepares step it + lane
                 const int st = it + g.lane;
                 const int lpos = (p.cycle_pos0 + 1 + st) % clen;           // pre-increment, proposal.py:93
-                const int kind = cyc_inline ? (int)p.cyc[lpos] : (int)p.cycle[lpos];
-                feed.refill(kind, (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D, p.eig_scale,
+                const int kind = KU ? (int)p.cyc[lpos] : (int)p.cycle[lpos];
+                feed.refill(kind, (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D, p.eig_scale, eig_row0, !KU,
                             (dump != nullptr && st < maxmcmc) ? dump + (size_t)st * 8 : nullptr);
             }
-            return feed.get(grow + 2 * (it & (G - 1)));
+            if (G == 1) return feed.own;
+            StepIn s;
+            uint32_t t0, t1;
+            const uint32_t addr = feed_base + 32u * (uint32_t)(it & (G - 1));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s.i0), "=r"(s.i1), "=r"(s.i2), "=r"(s.w3) : "r"(addr) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(s.w4), "=r"(s.w5), "=r"(t0), "=r"(t1) : "r"(addr) : "memory");
+            s.thr = __hiloint2double((int)t1, (int)t0);
+            return s;
         };
-        // One MCMC step on (s, r0..r2).  The rows of the following step are gathered at its start into (n0..n2) from the
-        // inputs `ns`, which were read one step earlier; the inputs of the step after that replace `s` as soon as this step
-        // has no use for it any more.  The caller alternates two such sets, so nothing is copied between steps.
+        auto gather = [&](int kind, const StepIn& s, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
+            gather_row<G, E>(lane_base, row_bytes, KU ? s.i0 : (s.i0 & kIndexMask), r0);
+            if (kind == CPN_WALK || kind == CPN_DE) gather_row<G, E>(lane_base, row_bytes, s.i1, r1);
+            if (kind == CPN_WALK) gather_row<G, E>(lane_base, row_bytes, s.i2, r2);
+        };
+        // position in the cycle -> kind (KU: a uniform load from the launch parameters)
+        auto advance2 = [&](int& pos) {
+            pos += 2;
+            if (pos >= clen) pos -= clen;
+            if (pos >= clen) pos -= clen;                               // cycles of length 1
+        };
+        // One MCMC step on its register set (s, kind, r0..r2).  As soon as the proposal has consumed the rows, the inputs
+        // of the step after the next one are read and ITS rows are gathered into the same registers: a gather has two steps
+        // to arrive (the L2 round trip is about as long as one step).  The caller alternates two sets.
         // TAIL = false: no chain of the launch can stop at this step (fewer than min(Nmcmc, maxmcmc) steps done), so the
         // step carries no per-chain `active` state.
-        auto mcmc_step = [&](auto tail, int it, StepIn& s, const double (&r0)[E], const double (&r1)[E], const double (&r2)[E],
-                             const StepIn& ns, double (&n0)[E], double (&n1)[E], double (&n2)[E]) {
+        auto mcmc_step = [&](auto tail, int it, StepIn& s, int& kind, int& pos, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
             constexpr bool TAIL = decltype(tail)::value;
-            gather_rows<G, E>(g, ens_x, eig_vec, Dp, ns, n0, n1, n2);
-            const int kind = (int)(s.i0 >> kKindShift);
             double xn[E];
             if (kind == CPN_WALK) {                                         // old + sum_j c_j s_j, proposal.py:230-234
                 const double c0 = (double)__uint_as_float(s.w3), c1 = (double)__uint_as_float(s.w4), c2 = (double)__uint_as_float(s.w5);
@@ -407,6 +412,13 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             }
             const double thr = s.thr;
             s = load_in(it + 2);
+            if (KU) {
+                advance2(pos);
+                kind = (int)p.cyc[pos];
+            } else {
+                kind = (int)(s.i0 >> kKindShift);
+            }
+            gather(kind, s, r0, r1, r2);
             // strict box test, model.py:33 (independent comparison chains: the FP64 compare has a long latency)
             bool in4[4] = {true, true, true, true};
 #pragma unroll
@@ -414,13 +426,21 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                 in4[(2 * e) & 3] = in4[(2 * e) & 3] & (blo[e] < xn[e]);
                 in4[(2 * e + 1) & 3] = in4[(2 * e + 1) & 3] & (xn[e] < bhi[e]);
             }
-            const bool inb = g.all((in4[0] & in4[1]) & (in4[2] & in4[3]));
+            const bool inb = gp.all((in4[0] & in4[1]) & (in4[2] & in4[3]));
             double logP_new = Model::template log_prior<G, E>(g, xn, mm);
-            logP_new = inb ? logP_new : CPN_NEG_INF;
-            bool pass = logP_new - logP > thr;                              // sampler.py:337
+            bool pass;
+            if (Model::kFlatPrior) {
+                // the prior is a constant inside the box: `logP_new - logP > thr` (sampler.py:337) does not wait for the box test
+                pass = (logP_new - logP > thr) && inb;
+            } else {
+                logP_new = inb ? logP_new : CPN_NEG_INF;
+                pass = logP_new - logP > thr;                               // sampler.py:337
+            }
             if (TAIL) pass = pass && active;
-            if (Model::kCheap || __any_sync(FULL, pass)) {
-                const double logL_new = Model::template log_likelihood<G, E>(g, xn, mm);   // sampler.py:338
+            if (BLK || Model::kCheap || __any_sync(FULL, pass)) {
+                double logL_new;                                            // sampler.py:338
+                if constexpr (BLK) logL_new = Model::template log_likelihood_block<G, E>(g, xn, mm);
+                else logL_new = Model::template log_likelihood<G, E>(g, xn, mm);
                 evals += pass ? 1 : 0;
                 const bool acc = pass && logL_new > logLmin;                // sampler.py:339
                 if (__any_sync(FULL, acc)) {
@@ -454,7 +474,11 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         for (int e = 0; e < E; ++e) a0[e] = a1[e] = a2[e] = b0[e] = b1[e] = b2[e] = 0.0;
         sa = load_in(0);
         sb = load_in(1);
-        gather_rows<G, E>(g, ens_x, eig_vec, Dp, sa, a0, a1, a2);
+        int posa = npos, posb = (npos + 1 == clen) ? 0 : npos + 1;          // cycle positions of steps 0 and 1
+        int ka = KU ? (int)p.cyc[posa] : (int)(sa.i0 >> kKindShift);
+        int kb = KU ? (int)p.cyc[posb] : (int)(sb.i0 >> kKindShift);
+        gather(ka, sa, a0, a1, a2);
+        gather(kb, sb, b0, b1, b2);
         // a chain stops after step number n (counting from 1) if (n >= Nmcmc and it has moved) or n >= maxmcmc
         // (sampler.py:347): none does during the first min(Nmcmc, maxmcmc) - 1 steps
         const int n_main = max(0, min(nmcmc, maxmcmc) - 1) & ~1;
@@ -465,18 +489,18 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         for (int half = 0; half < 2; ++half) {
             const int it1 = half == 0 ? n_half : n_main;
             for (; it < it1; it += 2) {
-                mcmc_step(BoolC<false>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
-                mcmc_step(BoolC<false>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
+                mcmc_step(BoolC<false>{}, it, sa, ka, posa, a0, a1, a2);
+                mcmc_step(BoolC<false>{}, it + 1, sb, kb, posb, b0, b1, b2);
             }
             if (half == 0 && twolag) ch.snapshot_mid(p);
         }
         steps = n_main;
         const int it_end = maxmcmc * (1 + max_resend);
         for (; it < it_end; it += 2) {
-            mcmc_step(BoolC<true>{}, it, sa, a0, a1, a2, sb, b0, b1, b2);
-            if (!__any_sync(FULL, active)) break;
-            mcmc_step(BoolC<true>{}, it + 1, sb, b0, b1, b2, sa, a0, a1, a2);
-            if (!__any_sync(FULL, active)) break;
+            mcmc_step(BoolC<true>{}, it, sa, ka, posa, a0, a1, a2);
+            if (!(BLK ? __syncthreads_or(active) != 0 : __any_sync(FULL, active) != 0)) break;
+            mcmc_step(BoolC<true>{}, it + 1, sb, kb, posb, b0, b1, b2);
+            if (!(BLK ? __syncthreads_or(active) != 0 : __any_sync(FULL, active) != 0)) break;
         }
         if (LOG && clog != nullptr) {
             log_event(1.0, (double)steps);

@@ -25,10 +25,11 @@ static int launch_mh_model(int G, int E, int replay, const MHParams& p, cudaStre
     if (G == GG && E == EE) {                                                                         \
         const int cpb = kMHThreads / GG;                                                              \
         const int nb = (nchains + cpb - 1) / cpb;                                                     \
-        const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;                  \
+        const size_t sm = (Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0) +               \
+                          (!replay && Model::template block_coop<GG> ? (size_t)Model::block_doubles(p.D) * sizeof(double) : 0); \
         const int nbt = (GG == 32 && Model::kTeam > 1) ? nchains : nb;   /* team mode: one chain per block */ \
         if (replay) k_mh_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                   \
-        else if (p.chain_log != nullptr) k_mh_chains<GG, EE, Model, false, true><<<nbt, kMHThreads, sm, s>>>(p); \
+        else if (p.chain_log != nullptr || p.cycle_len > kCycInline) k_mh_chains<GG, EE, Model, false, true><<<nbt, kMHThreads, sm, s>>>(p); \
         else k_mh_chains<GG, EE, Model, false><<<nbt, kMHThreads, sm, s>>>(p);                        \
         return 0;                                                                                     \
     }

@@ -13,6 +13,12 @@ namespace cpn {
 #define CPN_NEG_INF (__longlong_as_double(0xfff0000000000000LL))
 #define CPN_HALF_LOG_2PI 0.91893853320467274178
 
+// one FP64 tensor-core product C[8x8] += A[8x4] B[4x8]: lane 4 r + k supplies A[r][k] and B[k][r], holds C[r][2k], C[r][2k+1]
+__device__ __forceinline__ void dmma_f64(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 constexpr int kScratchRows = 2;   // shared-memory scratch per chain of functors with kScratch: kScratchRows * Dp doubles
 
 struct ModelCtx {
@@ -26,6 +32,9 @@ struct ModelCtx {
     int team = 1;
     int team_rank = 0;
     double* team_buf = nullptr;
+    // block mode (MH production kernel, functors with block_coop<G>): the chains of a block evaluate the functor together
+    // on data the block keeps in shared memory (block_buf: Model::block_doubles(D) doubles, filled by Model::block_prepare)
+    double* block_buf = nullptr;
 };
 
 template <int G, int E>
@@ -42,6 +51,11 @@ struct ModelBase {
     // warps per chain in the MH production kernel when a chain owns a whole warp (G == 32): > 1 for functors whose
     // cost is a long data sum, so that a batch of a few hundred chains still fills the SMs
     static constexpr int kTeam = 1;
+    // true for the lane-group widths at which the functor offers log_likelihood_block: a collective of the whole block
+    // (every thread calls it at every step, the block's warps stay in lock step; mh_kernel.cuh)
+    template <int G>
+    static constexpr bool block_coop = false;
+    static __host__ __device__ __forceinline__ int block_doubles(int) { return 0; }
     static __device__ __forceinline__ void prepare(ModelCtx&) {}
     // true if the functor's value does not change when the slots beyond D of a point hold +0.0 and are NOT masked: the
     // MH kernel then skips the masks whenever the rows it gathers are zero-padded up to G*E doubles (mh_kernel.cuh)
@@ -159,6 +173,105 @@ struct GaussCorr : FlatPrior {
 #pragma unroll
         for (int e = 0; e < E; ++e) acc = fma(y[e], y[e], acc);
         return -0.5 * g.sum(acc) - m.blob[0] - m.D * CPN_HALF_LOG_2PI;
+    }
+    // ---- block form: the eight 16-lane chains of a 128-thread block are the eight columns of FP64 tensor-core products.
+    // Y[56 x 8] = Linv[56 x 52] X[52 x 8] in 8 x 4 tiles of Linv (lower triangle only: row block i meets the column blocks
+    // j <= 2 i + 1), one mma.sync.m8n8k4.f64 (DMMA) per tile: the matrix is read once per EIGHT chains from shared memory,
+    // where the per-lane form above issues one load per multiply-add.  Tile (i, j) is stored in fragment order, lane
+    // 4 r + k holds Linv[8 i + r][4 j + k]; the points sit in a table X[chain][kXs] (kXs = 4 mod 16: the B fragments,
+    // lane 4 c + k <- X[c][4 j + k], load without bank conflicts).  Warp w owns the row blocks w and nrb - 1 - w (a short
+    // and a long one: 15-16 products per warp at D = 50), which share the B fragments; even and odd column blocks go to
+    // separate accumulators.  The squares of a warp's rows are summed over the rows by shuffles and over the warps in a
+    // fixed order through shared memory: every lane of a chain gets the bit-identical value.
+    template <int G>
+    static constexpr bool block_coop = (G == 16);
+    static constexpr int kXs = 68;
+    static __host__ __device__ __forceinline__ int block_tiles(int D) {
+        const int nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
+        int t = 0;
+        for (int i = 0; i < nrb; ++i) t += (2 * i + 2 < nkb) ? 2 * i + 2 : nkb;
+        return t;
+    }
+    static __host__ __device__ __forceinline__ int block_doubles(int D) { return D <= 64 ? block_tiles(D) * 32 + 8 * kXs + 32 : 0; }
+    static __device__ __forceinline__ int tile_base(int i, int nkb) {      // tiles of the row blocks before i
+        int t = 0;
+        for (int q = 0; q < i; ++q) t += (2 * q + 2 < nkb) ? 2 * q + 2 : nkb;
+        return t;
+    }
+    // called once by every thread of the block before the first step
+    static __device__ __forceinline__ void block_prepare(const ModelCtx& m) {
+        const int D = m.D, nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
+        const double* Linv = m.blob + 1;
+        double* tiles = m.block_buf;
+        const int ntile = block_tiles(D);
+        for (int i = 0, t0 = 0; i < nrb; ++i) {
+            const int nj = (2 * i + 2 < nkb) ? 2 * i + 2 : nkb;
+            for (int q = (int)threadIdx.x; q < nj * 32; q += (int)blockDim.x) {
+                const int j = q >> 5, l = q & 31, r = 8 * i + (l >> 2), c = 4 * j + (l & 3);
+                tiles[(size_t)(t0 + j) * 32 + l] = (r < D && c <= r) ? __ldg(Linv + (size_t)r * D + c) : 0.0;
+            }
+            t0 += nj;
+        }
+        double* X = tiles + (size_t)ntile * 32;
+        for (int q = (int)threadIdx.x; q < 8 * kXs + 32; q += (int)blockDim.x) X[q] = 0.0;
+        __syncthreads();
+    }
+    template <int G, int E>
+    static __device__ __forceinline__ double log_likelihood_block(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
+        static_assert(G == 16, "eight chains per 128-thread block");
+        const int D = m.D, nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
+        const int lane = (int)threadIdx.x & 31, w = (int)threadIdx.x >> 5, chain = (int)threadIdx.x >> 4;
+        double* tiles = m.block_buf;
+        double* X = tiles + (size_t)block_tiles(D) * 32;
+        double* part = X + 8 * kXs;                       // [4 warps][8 chains]
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int d = g.lane + e * G;
+            if (d < D) X[chain * kXs + d] = x[e];
+        }
+        __syncthreads();
+        double q0 = 0.0, q1 = 0.0;
+        const int iA = w, iB = nrb - 1 - w;               // short and long row block of this warp
+        if (iA <= iB) {
+            const int nA = (iA == iB) ? 0 : ((2 * iA + 2 < nkb) ? 2 * iA + 2 : nkb);
+            const int nB = (2 * iB + 2 < nkb) ? 2 * iB + 2 : nkb;
+            const double* At = tiles + (size_t)tile_base(iA, nkb) * 32 + lane;
+            const double* Bt = tiles + (size_t)tile_base(iB, nkb) * 32 + lane;
+            const double* xb = X + (lane >> 2) * kXs + (lane & 3);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            int j = 0;
+            for (; j + 1 < nA; j += 2) {                  // both row blocks (nA is even or nkb)
+                const double x0 = xb[4 * j], x1 = xb[4 * j + 4];
+                dmma_f64(b0, b1, Bt[32 * j], x0);
+                dmma_f64(a0, a1, At[32 * j], x0);
+                dmma_f64(b2, b3, Bt[32 * j + 32], x1);
+                dmma_f64(a2, a3, At[32 * j + 32], x1);
+            }
+            if (j < nA) {
+                const double x0 = xb[4 * j];
+                dmma_f64(b0, b1, Bt[32 * j], x0);
+                dmma_f64(a0, a1, At[32 * j], x0);
+                ++j;
+            }
+            for (; j + 1 < nB; j += 2) {                  // the long row block alone
+                dmma_f64(b0, b1, Bt[32 * j], xb[4 * j]);
+                dmma_f64(b2, b3, Bt[32 * j + 32], xb[4 * j + 4]);
+            }
+            if (j < nB) dmma_f64(b0, b1, Bt[32 * j], xb[4 * j]);
+            a0 += a2; a1 += a3; b0 += b2; b1 += b3;
+            q0 = fma(a0, a0, b0 * b0);
+            q1 = fma(a1, a1, b1 * b1);
+        }
+        // rows live in lane >> 2: sum over them; lanes 0..3 then hold the chains 2 k, 2 k + 1
+#pragma unroll
+        for (int msk = 4; msk <= 16; msk <<= 1) {
+            q0 += __shfl_xor_sync(FULL, q0, msk);
+            q1 += __shfl_xor_sync(FULL, q1, msk);
+        }
+        if (lane < 4) { part[w * 8 + 2 * lane] = q0; part[w * 8 + 2 * lane + 1] = q1; }
+        __syncthreads();
+        const double s = (part[chain] + part[8 + chain]) + (part[16 + chain] + part[24 + chain]);
+        return -0.5 * s - m.blob[0] - m.D * CPN_HALF_LOG_2PI;
     }
     // grad = -Linv^T (Linv x): the second product walks the rows of Linv^T = columns of Linv, again consecutive in the
     // lanes when read from the row-major copy transposed, i.e. from Linv itself: (Linv^T y)_c = sum_{r >= c} Linv[r][c] y_r
