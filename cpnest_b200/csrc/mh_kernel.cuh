@@ -218,9 +218,8 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
     constexpr bool BLK = !REPLAY && TEAM == 1 && Model::template block_coop<G>;
     Chain<G, E, Model> ch;
     if (!ch.begin(p, smem, REPLAY, TEAM, team_buf, BLK)) return;
-    if (BLK) {
-        ch.m.block_buf = smem + (Model::kScratch ? (kMHThreads / G) * kScratchRows * p.Dp : 0);
-        if (Model::block_doubles(p.D) > 0) Model::block_prepare(ch.m);
+    if constexpr (BLK) {
+        Model::block_prepare(ch.m, Model::kScratch ? (kMHThreads / G) * kScratchRows * p.Dp : 0);
     }
     const Group<G>& g = ch.g;
     const ModelCtx& m = ch.m;
@@ -380,14 +379,17 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
             if (kind == CPN_WALK) gather_row<G, E>(lane_base, row_bytes, s.i2, r2);
         };
         // position in the cycle -> kind (KU: a uniform load from the launch parameters)
-        auto advance2 = [&](int& pos) {
-            pos += 2;
+        // AHEAD: how many steps before its proposal the rows of a step are gathered.  2: two register sets alternate, a gather
+        // has two steps to arrive (the L2 round trip is about as long as one step of a cheap functor).  1 (block mode: the
+        // likelihood makes a step several L2 round trips long, and its own state needs the registers): one set.
+        constexpr int AHEAD = BLK ? 1 : 2;
+        auto advance = [&](int& pos) {
+            pos += AHEAD;
             if (pos >= clen) pos -= clen;
             if (pos >= clen) pos -= clen;                               // cycles of length 1
         };
         // One MCMC step on its register set (s, kind, r0..r2).  As soon as the proposal has consumed the rows, the inputs
-        // of the step after the next one are read and ITS rows are gathered into the same registers: a gather has two steps
-        // to arrive (the L2 round trip is about as long as one step).  The caller alternates two sets.
+        // of the step AHEAD steps later are read and ITS rows are gathered into the same registers.
         // TAIL = false: no chain of the launch can stop at this step (fewer than min(Nmcmc, maxmcmc) steps done), so the
         // step carries no per-chain `active` state.
         auto mcmc_step = [&](auto tail, int it, StepIn& s, int& kind, int& pos, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
@@ -411,9 +413,9 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                 for (int e = 0; e < E; ++e) xn[e] = fma(jump, r0[e], x[e]);
             }
             const double thr = s.thr;
-            s = load_in(it + 2);
+            s = load_in(it + AHEAD);
             if (KU) {
-                advance2(pos);
+                advance(pos);
                 kind = (int)p.cyc[pos];
             } else {
                 kind = (int)(s.i0 >> kKindShift);
@@ -473,12 +475,20 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
 #pragma unroll
         for (int e = 0; e < E; ++e) a0[e] = a1[e] = a2[e] = b0[e] = b1[e] = b2[e] = 0.0;
         sa = load_in(0);
-        sb = load_in(1);
         int posa = npos, posb = (npos + 1 == clen) ? 0 : npos + 1;          // cycle positions of steps 0 and 1
         int ka = KU ? (int)p.cyc[posa] : (int)(sa.i0 >> kKindShift);
-        int kb = KU ? (int)p.cyc[posb] : (int)(sb.i0 >> kKindShift);
+        int kb = 0;
         gather(ka, sa, a0, a1, a2);
-        gather(kb, sb, b0, b1, b2);
+        if (AHEAD == 2) {
+            sb = load_in(1);
+            kb = KU ? (int)p.cyc[posb] : (int)(sb.i0 >> kKindShift);
+            gather(kb, sb, b0, b1, b2);
+        }
+        auto step_a = [&](auto tail, int it_) { mcmc_step(tail, it_, sa, ka, posa, a0, a1, a2); };
+        auto step_b = [&](auto tail, int it_) {
+            if constexpr (AHEAD == 2) mcmc_step(tail, it_, sb, kb, posb, b0, b1, b2);
+            else mcmc_step(tail, it_, sa, ka, posa, a0, a1, a2);
+        };
         // a chain stops after step number n (counting from 1) if (n >= Nmcmc and it has moved) or n >= maxmcmc
         // (sampler.py:347): none does during the first min(Nmcmc, maxmcmc) - 1 steps
         const int n_main = max(0, min(nmcmc, maxmcmc) - 1) & ~1;
@@ -489,17 +499,17 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         for (int half = 0; half < 2; ++half) {
             const int it1 = half == 0 ? n_half : n_main;
             for (; it < it1; it += 2) {
-                mcmc_step(BoolC<false>{}, it, sa, ka, posa, a0, a1, a2);
-                mcmc_step(BoolC<false>{}, it + 1, sb, kb, posb, b0, b1, b2);
+                step_a(BoolC<false>{}, it);
+                step_b(BoolC<false>{}, it + 1);
             }
             if (half == 0 && twolag) ch.snapshot_mid(p);
         }
         steps = n_main;
         const int it_end = maxmcmc * (1 + max_resend);
         for (; it < it_end; it += 2) {
-            mcmc_step(BoolC<true>{}, it, sa, ka, posa, a0, a1, a2);
+            step_a(BoolC<true>{}, it);
             if (!(BLK ? __syncthreads_or(active) != 0 : __any_sync(FULL, active) != 0)) break;
-            mcmc_step(BoolC<true>{}, it + 1, sb, kb, posb, b0, b1, b2);
+            step_b(BoolC<true>{}, it + 1);
             if (!(BLK ? __syncthreads_or(active) != 0 : __any_sync(FULL, active) != 0)) break;
         }
         if (LOG && clog != nullptr) {

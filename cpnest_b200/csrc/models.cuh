@@ -33,8 +33,10 @@ struct ModelCtx {
     int team_rank = 0;
     double* team_buf = nullptr;
     // block mode (MH production kernel, functors with block_coop<G>): the chains of a block evaluate the functor together
-    // on data the block keeps in shared memory (block_buf: Model::block_doubles(D) doubles, filled by Model::block_prepare)
-    double* block_buf = nullptr;
+    // on data the block keeps in shared memory (Model::block_doubles(D) doubles of the dynamic array, filled by
+    // Model::block_prepare)
+    int bp[4] = {0, 0, 0, 0};   // per-thread constants of the block form (set by block_prepare)
+    int bo = 0;
 };
 
 template <int G, int E>
@@ -174,101 +176,108 @@ struct GaussCorr : FlatPrior {
         for (int e = 0; e < E; ++e) acc = fma(y[e], y[e], acc);
         return -0.5 * g.sum(acc) - m.blob[0] - m.D * CPN_HALF_LOG_2PI;
     }
-    // ---- block form: the eight 16-lane chains of a 128-thread block are the eight columns of FP64 tensor-core products.
-    // Y[56 x 8] = Linv[56 x 52] X[52 x 8] in 8 x 4 tiles of Linv (lower triangle only: row block i meets the column blocks
-    // j <= 2 i + 1), one mma.sync.m8n8k4.f64 (DMMA) per tile: the matrix is read once per EIGHT chains from shared memory,
-    // where the per-lane form above issues one load per multiply-add.  Tile (i, j) is stored in fragment order, lane
-    // 4 r + k holds Linv[8 i + r][4 j + k]; the points sit in a table X[chain][kXs] (kXs = 4 mod 16: the B fragments,
-    // lane 4 c + k <- X[c][4 j + k], load without bank conflicts).  Warp w owns the row blocks w and nrb - 1 - w (a short
-    // and a long one: 15-16 products per warp at D = 50), which share the B fragments; even and odd column blocks go to
-    // separate accumulators.  The squares of a warp's rows are summed over the rows by shuffles and over the warps in a
-    // fixed order through shared memory: every lane of a chain gets the bit-identical value.
+    // ---- block form: the eight 16-lane chains of a 128-thread block are the eight rows of FP64 tensor-core products.
+    // Y^T[8 x 56] = X^T[8 x 52] Linv^T[52 x 56] in 4 x 8 tiles of Linv^T (lower triangle of Linv only: the block of output
+    // coordinates i meets the blocks of input coordinates j <= 2 i + 1), one mma.sync.m8n8k4.f64 (DMMA) per tile: the
+    // matrix is read once per EIGHT chains, from shared memory, where the per-lane form above issues one load per
+    // multiply-add.  Tile (i, j) is stored in fragment order, lane 4 n + k holds Linv[8 i + n][4 j + k]; the points sit in a
+    // table X[chain][kXs] (kXs = 4 mod 16: the A fragments, lane 4 c + k <- X[c][4 j + k], load without bank conflicts).
+    // Warp w owns the output blocks w and nrb - 1 - w (a short and a long one: 16 products per warp at D = 50), which share
+    // the A fragments; even and odd input blocks go to separate accumulators; every output block has an even number of tiles
+    // (a zero tile is appended).  A lane ends up with two output coordinates per block of ONE chain (lane >> 2): their squares
+    // are summed in the lane, over the four lanes of the chain by two shuffles, over the warps in a fixed order through shared
+    // memory: every lane of a chain gets the bit-identical value.  All shared-memory traffic goes through the kernel's
+    // dynamic array by offset (a generic pointer costs a window conversion per access).
     template <int G>
     static constexpr bool block_coop = (G == 16);
     static constexpr int kXs = 68;
-    static __host__ __device__ __forceinline__ int block_tiles(int D) {
-        const int nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
+    static __host__ __device__ __forceinline__ int ntile_row(int i, int nkb) {       // tiles of output block i (even)
+        const int n = (2 * i + 2 < nkb) ? 2 * i + 2 : nkb;
+        return (n + 1) & ~1;
+    }
+    static __host__ __device__ __forceinline__ int tile_base(int i, int nkb) {       // tiles of the output blocks before i
         int t = 0;
-        for (int i = 0; i < nrb; ++i) t += (2 * i + 2 < nkb) ? 2 * i + 2 : nkb;
+        for (int q = 0; q < i; ++q) t += ntile_row(q, nkb);
         return t;
     }
-    static __host__ __device__ __forceinline__ int block_doubles(int D) { return D <= 64 ? block_tiles(D) * 32 + 8 * kXs + 32 : 0; }
-    static __device__ __forceinline__ int tile_base(int i, int nkb) {      // tiles of the row blocks before i
-        int t = 0;
-        for (int q = 0; q < i; ++q) t += (2 * q + 2 < nkb) ? 2 * q + 2 : nkb;
-        return t;
+    static __host__ __device__ __forceinline__ int block_doubles(int D) {
+        return D <= 64 ? tile_base((D + 7) >> 3, (D + 3) >> 2) * 32 + 8 * kXs + 32 : 0;
     }
-    // called once by every thread of the block before the first step
-    static __device__ __forceinline__ void block_prepare(const ModelCtx& m) {
+    // called once by every thread of the block before the first step: fills the tile table and the thread's constants
+    // bp = {offset of its B fragments of the short output block, of the long one, of its A fragments (doubles from the start
+    // of the dynamic shared array), input blocks of the short | long output block << 8 | role << 16}; bo = offset of the
+    // point table
+    static __device__ __forceinline__ void block_prepare(ModelCtx& m, int buf_off) {
+        extern __shared__ double cpn_dyn_smem[];
         const int D = m.D, nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
         const double* Linv = m.blob + 1;
-        double* tiles = m.block_buf;
-        const int ntile = block_tiles(D);
+        double* tiles = cpn_dyn_smem + buf_off;
+        const int ntile = tile_base(nrb, nkb);
         for (int i = 0, t0 = 0; i < nrb; ++i) {
-            const int nj = (2 * i + 2 < nkb) ? 2 * i + 2 : nkb;
+            const int nj = ntile_row(i, nkb);
             for (int q = (int)threadIdx.x; q < nj * 32; q += (int)blockDim.x) {
                 const int j = q >> 5, l = q & 31, r = 8 * i + (l >> 2), c = 4 * j + (l & 3);
-                tiles[(size_t)(t0 + j) * 32 + l] = (r < D && c <= r) ? __ldg(Linv + (size_t)r * D + c) : 0.0;
+                tiles[(t0 + j) * 32 + l] = (r < D && c <= r) ? __ldg(Linv + (size_t)r * D + c) : 0.0;
             }
             t0 += nj;
         }
-        double* X = tiles + (size_t)ntile * 32;
-        for (int q = (int)threadIdx.x; q < 8 * kXs + 32; q += (int)blockDim.x) X[q] = 0.0;
+        for (int q = (int)threadIdx.x; q < 8 * kXs + 32; q += (int)blockDim.x) tiles[ntile * 32 + q] = 0.0;
+        // (the role of a warp rotates with the block index: a warp stays on one SM sub-partition, and so do its tensor-core
+        // products; the four roles carry 16, 16, 16 and 8 of them at D = 50, the four blocks resident on an SM then load
+        // every sub-partition alike)
+        const int lane = (int)threadIdx.x & 31, w = (((int)threadIdx.x >> 5) + (int)blockIdx.x) & 3;
+        const int iA = w, iB = nrb - 1 - w;               // short and long output block of this warp (iA > iB: none)
+        int nA = 0, nB = 0;
+        if (iA <= iB) {
+            nA = (iA == iB) ? 0 : ntile_row(iA, nkb);
+            nB = ntile_row(iB, nkb);
+        }
+        m.bp[0] = buf_off + tile_base(iA < nrb ? iA : 0, nkb) * 32 + lane;
+        m.bp[1] = buf_off + tile_base(iB >= 0 ? iB : 0, nkb) * 32 + lane;
+        m.bp[2] = buf_off + ntile * 32 + (lane >> 2) * kXs + (lane & 3);
+        m.bp[3] = nA | (nB << 8) | (w << 16);
+        m.bo = buf_off + ntile * 32;
         __syncthreads();
     }
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood_block(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         static_assert(G == 16, "eight chains per 128-thread block");
-        const int D = m.D, nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
-        const int lane = (int)threadIdx.x & 31, w = (int)threadIdx.x >> 5, chain = (int)threadIdx.x >> 4;
-        double* tiles = m.block_buf;
-        double* X = tiles + (size_t)block_tiles(D) * 32;
+        extern __shared__ double cpn_dyn_smem[];
+        const int D = m.D;
+        const int lane = (int)threadIdx.x & 31, w = m.bp[3] >> 16, chain = (int)threadIdx.x >> 4;
+        double* X = cpn_dyn_smem + m.bo;
         double* part = X + 8 * kXs;                       // [4 warps][8 chains]
+        const double* At = cpn_dyn_smem + m.bp[0];
+        const double* Bt = cpn_dyn_smem + m.bp[1];
+        const double* xb = cpn_dyn_smem + m.bp[2];
+        const int nA = m.bp[3] & 0xff, nB = (m.bp[3] >> 8) & 0xff;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int d = g.lane + e * G;
             if (d < D) X[chain * kXs + d] = x[e];
         }
         __syncthreads();
-        double q0 = 0.0, q1 = 0.0;
-        const int iA = w, iB = nrb - 1 - w;               // short and long row block of this warp
-        if (iA <= iB) {
-            const int nA = (iA == iB) ? 0 : ((2 * iA + 2 < nkb) ? 2 * iA + 2 : nkb);
-            const int nB = (2 * iB + 2 < nkb) ? 2 * iB + 2 : nkb;
-            const double* At = tiles + (size_t)tile_base(iA, nkb) * 32 + lane;
-            const double* Bt = tiles + (size_t)tile_base(iB, nkb) * 32 + lane;
-            const double* xb = X + (lane >> 2) * kXs + (lane & 3);
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-            int j = 0;
-            for (; j + 1 < nA; j += 2) {                  // both row blocks (nA is even or nkb)
-                const double x0 = xb[4 * j], x1 = xb[4 * j + 4];
-                dmma_f64(b0, b1, Bt[32 * j], x0);
-                dmma_f64(a0, a1, At[32 * j], x0);
-                dmma_f64(b2, b3, Bt[32 * j + 32], x1);
-                dmma_f64(a2, a3, At[32 * j + 32], x1);
-            }
-            if (j < nA) {
-                const double x0 = xb[4 * j];
-                dmma_f64(b0, b1, Bt[32 * j], x0);
-                dmma_f64(a0, a1, At[32 * j], x0);
-                ++j;
-            }
-            for (; j + 1 < nB; j += 2) {                  // the long row block alone
-                dmma_f64(b0, b1, Bt[32 * j], xb[4 * j]);
-                dmma_f64(b2, b3, Bt[32 * j + 32], xb[4 * j + 4]);
-            }
-            if (j < nB) dmma_f64(b0, b1, Bt[32 * j], xb[4 * j]);
-            a0 += a2; a1 += a3; b0 += b2; b1 += b3;
-            q0 = fma(a0, a0, b0 * b0);
-            q1 = fma(a1, a1, b1 * b1);
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        int j = 0;
+#pragma unroll 2
+        for (; j < nA; j += 2) {                          // both output blocks, which share the A fragments
+            const double x0 = xb[4 * j], x1 = xb[4 * j + 4];
+            dmma_f64(b0, b1, x0, Bt[32 * j]);
+            dmma_f64(a0, a1, x0, At[32 * j]);
+            dmma_f64(b2, b3, x1, Bt[32 * j + 32]);
+            dmma_f64(a0, a1, x1, At[32 * j + 32]);
         }
-        // rows live in lane >> 2: sum over them; lanes 0..3 then hold the chains 2 k, 2 k + 1
-#pragma unroll
-        for (int msk = 4; msk <= 16; msk <<= 1) {
-            q0 += __shfl_xor_sync(FULL, q0, msk);
-            q1 += __shfl_xor_sync(FULL, q1, msk);
+#pragma unroll 2
+        for (; j < nB; j += 2) {                          // the long output block alone (even and odd input blocks apart)
+            dmma_f64(b0, b1, xb[4 * j], Bt[32 * j]);
+            dmma_f64(b2, b3, xb[4 * j + 4], Bt[32 * j + 32]);
         }
-        if (lane < 4) { part[w * 8 + 2 * lane] = q0; part[w * 8 + 2 * lane + 1] = q1; }
+        b0 += b2; b1 += b3;
+        double q = fma(a0, a0, a1 * a1) + fma(b0, b0, b1 * b1);
+        // the chain lives in lane >> 2: sum over its four lanes
+        q += __shfl_xor_sync(FULL, q, 1);
+        q += __shfl_xor_sync(FULL, q, 2);
+        if ((lane & 3) == 0) part[w * 8 + (lane >> 2)] = q;
         __syncthreads();
         const double s = (part[chain] + part[8 + chain]) + (part[16 + chain] + part[24 + chain]);
         return -0.5 * s - m.blob[0] - m.D * CPN_HALF_LOG_2PI;

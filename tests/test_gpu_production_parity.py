@@ -123,6 +123,17 @@ def test_production_mh_chain_correlated_gaussian():
             _check(m, e, lanes, np.random.RandomState(23), spread=0.1, rtol=1e-11)
 
 
+@pytest.mark.parametrize("dim,chains", [(50, 6), (50, 19), (33, 8), (64, 11), (20, 3)])
+def test_production_mh_chain_correlated_gaussian_block_form(dim, chains):
+    """16 lanes per chain: the eight chains of a block evaluate the likelihood together, Linv X as FP64 tensor-core products
+    (models.cuh GaussCorr::log_likelihood_block).  Blocks that are partly filled (shadow chains), several blocks, dimensions
+    that are not multiples of the 8 x 4 tiles, the largest dimension of the configuration."""
+    from cpnest_b200.engine import Engine
+    m = O.make_correlated_gaussian(dim)
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=200, seed=1234, params=m.params) as e:
+        _check(m, e, 16, np.random.RandomState(dim + chains), C=chains, spread=0.1, rtol=1e-11)
+
+
 def test_production_mh_chain_long_cycle_and_immobile_chain():
     """A proposal cycle longer than the inline table (device-memory path), and a chain that cannot move (threshold above
     every reachable logL): it runs to maxmcmc with zero accepted steps (sampler.py:347)."""
