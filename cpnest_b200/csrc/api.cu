@@ -240,6 +240,9 @@ static int pick_config(int D, int lanes, int functor, long long chains, int* G, 
         const int e = min_E(32, D);
         if (e) { *G = 32; *E = e; return 0; }
     }
+    // 33..64 dimensions: 16 lanes x 4 coordinates is the fastest MH configuration from half a wave of chains upwards
+    // (D = 50: 0.092 ns per chain-step at K = 4704, 0.083 at K = 37632; 8 lanes: 0.099 / 0.092)
+    if (D > 32 && D <= 64 && min_E(16, D) && chains * 16 / 32 >= 148LL * 4) { *G = 16; *E = min_E(16, D); return 0; }
     int gmax = 1;
     while (gmax < D && gmax < 32) gmax <<= 1;          // no more lanes than coordinates
     static const int Gs[] = {1, 4, 8, 16, 32};
@@ -858,11 +861,23 @@ static void fill_common(cpn_ctx* c, ChainParams* p) {
     }
 }
 
+// the proposal cycle as it travels in the launch parameters of the production MH kernel (cycles of up to kCycInline slots):
+// the kinds themselves and, for every cycle position, the kinds of the kKindWin steps that start there packed into a word
+static void fill_inline_cycle(MHParams* p, const uint8_t* cyc, int len) {
+    if (len > kCycInline) return;                       // longer cycles are read from device memory (chain-history instantiation)
+    memcpy(p->cyc, cyc, len);
+    for (int q = 0; q < len; ++q) {
+        uint32_t w = 0;
+        for (int j = 0; j < kKindWin; ++j) w |= (uint32_t)(cyc[(q + j) % len] & 3) << (2 * j);
+        p->cycw[q] = make_uint2(w, (uint32_t)((q + kKindWin) % len));
+    }
+}
+
 static void fill_mh(cpn_ctx* c, MHParams* p) {
     memset(p, 0, sizeof *p);
     fill_common(c, p);
     p->cycle = c->d_cycle; p->cycle_len = c->cycle_len;
-    memcpy(p->cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
+    fill_inline_cycle(p, c->h_cycle, c->cycle_len);
     p->cycle_pos0 = (int)((c->batches_enqueued * 37) % c->cycle_len);
     p->eig_scale = c->d_eigscale[c->eig_cur]; p->eig_vec = c->d_eigvec[c->eig_cur];
     p->eig_row0 = c->N + c->eig_cur * c->D;
@@ -2023,7 +2038,7 @@ extern "C" int cpn_trace_mh(cpn_ctx* c, int32_t P, const double* ensemble, int32
         p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
         p.lo = c->d_lo; p.hi = c->d_hi;
         p.cycle = c->d_cycle; p.cycle_len = c->cycle_len; p.cycle_pos0 = cycle_idx % c->cycle_len;
-        memcpy(p.cyc, c->h_cycle, std::min(c->cycle_len, kCycInline));
+        fill_inline_cycle(&p, c->h_cycle, c->cycle_len);
         p.eig_scale = des; p.eig_vec = dev; p.eig_row0 = P;
         p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.maxmcmc = maxmcmc;
         p.j0 = 0; p.j1 = C; p.blob = c->d_blob;

@@ -14,7 +14,8 @@
 
 namespace cpn {
 
-constexpr int kCycInline = 1024;  // proposal cycles up to this length travel in the launch parameters (constant bank)
+constexpr int kCycInline = 256;   // proposal cycles up to this length travel in the launch parameters (constant bank)
+constexpr int kKindWin = 16;     // steps whose kinds fit one word of MHParams::cycw
 
 struct MHParams : ChainParams {
     // proposal cycle + eigen directions
@@ -32,6 +33,10 @@ struct MHParams : ChainParams {
     // production: the cycle inline (ProposalCycle's default length is 100, cpnest/proposal.py:52): the kind of a step is the
     // same for every chain of the launch, read through the uniform datapath, and the proposal code branches on it uniformly
     uint8_t cyc[kCycInline];
+    // cycw[q] = {the kinds of the kKindWin steps that start at cycle position q, two bits each (step j of the window in bits
+    // 2j, 2j+1); the cycle position of the window after it, (q + kKindWin) % cycle_len}: one uniform load per window, a shift
+    // and a mask per step, no arithmetic on the position
+    uint2 cycw[kCycInline];
     // production, test entry (cpn_trace_mh): what every step of every chain consumed besides the chain state,
     // [chains][maxmcmc][8] doubles {kind, i0, i1, i2, c0, c1, c2, thr} (see DrawFeed), or null
     double* draws;
@@ -375,51 +380,55 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         };
         auto gather = [&](int kind, const StepIn& s, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
             gather_row<G, E>(lane_base, row_bytes, KU ? s.i0 : (s.i0 & kIndexMask), r0);
-            if (kind == CPN_WALK || kind == CPN_DE) gather_row<G, E>(lane_base, row_bytes, s.i1, r1);
-            if (kind == CPN_WALK) gather_row<G, E>(lane_base, row_bytes, s.i2, r2);
+            if ((kind & 1) == 0) {                                          // WALK, DE
+                gather_row<G, E>(lane_base, row_bytes, s.i1, r1);
+                if (kind == CPN_WALK) gather_row<G, E>(lane_base, row_bytes, s.i2, r2);
+            }
         };
         // position in the cycle -> kind (KU: a uniform load from the launch parameters)
         // AHEAD: how many steps before its proposal the rows of a step are gathered.  2: two register sets alternate, a gather
         // has two steps to arrive (the L2 round trip is about as long as one step of a cheap functor).  1 (block mode: the
         // likelihood makes a step several L2 round trips long, and its own state needs the registers): one set.
         constexpr int AHEAD = BLK ? 1 : 2;
-        auto advance = [&](int& pos) {
-            pos += AHEAD;
-            if (pos >= clen) pos -= clen;
-            if (pos >= clen) pos -= clen;                               // cycles of length 1
+        // kinds of the window of kKindWin steps that holds the step whose inputs are read next (KU)
+        uint2 kw = p.cycw[KU ? npos : 0];
+        auto kind_of = [&](int st) -> int {                                 // st in the current window, or the first of the next
+            if ((st & (kKindWin - 1)) == 0 && st > 0) kw = p.cycw[kw.y];
+            return (int)((kw.x >> (2 * (st & (kKindWin - 1)))) & 3u);
         };
         // One MCMC step on its register set (s, kind, r0..r2).  As soon as the proposal has consumed the rows, the inputs
         // of the step AHEAD steps later are read and ITS rows are gathered into the same registers.
         // TAIL = false: no chain of the launch can stop at this step (fewer than min(Nmcmc, maxmcmc) steps done), so the
         // step carries no per-chain `active` state.
-        auto mcmc_step = [&](auto tail, int it, StepIn& s, int& kind, int& pos, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
+        auto mcmc_step = [&](auto tail, int it, StepIn& s, int& kind, double (&r0)[E], double (&r1)[E], double (&r2)[E]) {
             constexpr bool TAIL = decltype(tail)::value;
             double xn[E];
-            if (kind == CPN_WALK) {                                         // old + sum_j c_j s_j, proposal.py:230-234
-                const double c0 = (double)__uint_as_float(s.w3), c1 = (double)__uint_as_float(s.w4), c2 = (double)__uint_as_float(s.w5);
+            // (two uniform bit tests: a four-way comparison chain becomes a jump table, an indirect branch per step)
+            static_assert(CPN_WALK == 0 && CPN_STRETCH == 1 && CPN_DE == 2 && CPN_EIGEN == 3, "kind bits");
+            if (kind & 2) {
+                if (kind & 1) {                                             // EIGEN: old + jump v_i, proposal.py:340-341
+                    const double jump = __hiloint2double((int)s.w5, (int)s.w4);
 #pragma unroll
-                for (int e = 0; e < E; ++e) xn[e] = fma(c2, r2[e], fma(c1, r1[e], fma(c0, r0[e], x[e])));
-            } else if (kind == CPN_STRETCH) {                               // a + (old - a) Z, proposal.py:258
-                const double Z = (double)__uint_as_float(s.w3);
+                    for (int e = 0; e < E; ++e) xn[e] = fma(jump, r0[e], x[e]);
+                } else {                                                    // DE: old + (b - a) g, proposal.py:286
+                    const double gd = (double)__uint_as_float(s.w3);
 #pragma unroll
-                for (int e = 0; e < E; ++e) xn[e] = fma(Z, x[e] - r0[e], r0[e]);
-            } else if (kind == CPN_DE) {                                    // old + (b - a) g, proposal.py:286
-                const double gd = (double)__uint_as_float(s.w3);
+                    for (int e = 0; e < E; ++e) xn[e] = fma(gd, r1[e] - r0[e], x[e]);
+                }
+            } else {
+                if (kind & 1) {                                             // STRETCH: a + (old - a) Z, proposal.py:258
+                    const double Z = (double)__uint_as_float(s.w3);
 #pragma unroll
-                for (int e = 0; e < E; ++e) xn[e] = fma(gd, r1[e] - r0[e], x[e]);
-            } else {                                                        // old + jump v_i, proposal.py:340-341
-                const double jump = __hiloint2double((int)s.w5, (int)s.w4);
+                    for (int e = 0; e < E; ++e) xn[e] = fma(Z, x[e] - r0[e], r0[e]);
+                } else {                                                    // WALK: old + sum_j c_j s_j, proposal.py:230-234
+                    const double c0 = (double)__uint_as_float(s.w3), c1 = (double)__uint_as_float(s.w4), c2 = (double)__uint_as_float(s.w5);
 #pragma unroll
-                for (int e = 0; e < E; ++e) xn[e] = fma(jump, r0[e], x[e]);
+                    for (int e = 0; e < E; ++e) xn[e] = fma(c2, r2[e], fma(c1, r1[e], fma(c0, r0[e], x[e])));
+                }
             }
             const double thr = s.thr;
             s = load_in(it + AHEAD);
-            if (KU) {
-                advance(pos);
-                kind = (int)p.cyc[pos];
-            } else {
-                kind = (int)(s.i0 >> kKindShift);
-            }
+            kind = KU ? kind_of(it + AHEAD) : (int)(s.i0 >> kKindShift);
             gather(kind, s, r0, r1, r2);
             // strict box test, model.py:33 (independent comparison chains: the FP64 compare has a long latency)
             bool in4[4] = {true, true, true, true};
@@ -475,19 +484,18 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
 #pragma unroll
         for (int e = 0; e < E; ++e) a0[e] = a1[e] = a2[e] = b0[e] = b1[e] = b2[e] = 0.0;
         sa = load_in(0);
-        int posa = npos, posb = (npos + 1 == clen) ? 0 : npos + 1;          // cycle positions of steps 0 and 1
-        int ka = KU ? (int)p.cyc[posa] : (int)(sa.i0 >> kKindShift);
+        int ka = KU ? kind_of(0) : (int)(sa.i0 >> kKindShift);
         int kb = 0;
         gather(ka, sa, a0, a1, a2);
         if (AHEAD == 2) {
             sb = load_in(1);
-            kb = KU ? (int)p.cyc[posb] : (int)(sb.i0 >> kKindShift);
+            kb = KU ? kind_of(1) : (int)(sb.i0 >> kKindShift);
             gather(kb, sb, b0, b1, b2);
         }
-        auto step_a = [&](auto tail, int it_) { mcmc_step(tail, it_, sa, ka, posa, a0, a1, a2); };
+        auto step_a = [&](auto tail, int it_) { mcmc_step(tail, it_, sa, ka, a0, a1, a2); };
         auto step_b = [&](auto tail, int it_) {
-            if constexpr (AHEAD == 2) mcmc_step(tail, it_, sb, kb, posb, b0, b1, b2);
-            else mcmc_step(tail, it_, sa, ka, posa, a0, a1, a2);
+            if constexpr (AHEAD == 2) mcmc_step(tail, it_, sb, kb, b0, b1, b2);
+            else mcmc_step(tail, it_, sa, ka, a0, a1, a2);
         };
         // a chain stops after step number n (counting from 1) if (n >= Nmcmc and it has moved) or n >= maxmcmc
         // (sampler.py:347): none does during the first min(Nmcmc, maxmcmc) - 1 steps

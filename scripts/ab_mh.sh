@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 {
 echo "== determinism / equality of chains: old"; CPNEST_B200_LIB=$OLD python scripts/determinism.py
 echo "== determinism / equality of chains: new"; python scripts/determinism.py
-for cfg in "4704 16" "4704 8" "4704 32" "2352 16" "37632 8 10 10 100000" "37632 16 10 10 100000"; do
+for cfg in ${CFGS:-"4704 16" "4704 8" "4704 32" "2352 16" "37632 8 10 10 100000" "37632 16 10 10 100000"}; do
   echo "== time_mh $cfg: old"; CPNEST_B200_LIB=$OLD python scripts/time_mh.py $cfg
   echo "== time_mh $cfg: new"; python scripts/time_mh.py $cfg
 done
