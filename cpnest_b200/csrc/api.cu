@@ -2083,15 +2083,17 @@ static int slice_scratch_launch(cpn_ctx* c, SliceParams& p, int replay, int lane
     return 0;
 }
 
-extern "C" int cpn_replay_slice(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start,
-                                int32_t cycle_idx, const double* tape, const int64_t* tape_off, double mu, int32_t nmcmc,
-                                int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes, double* out, int32_t* steps,
-                                int32_t* accepted, int32_t* evals, double* last) {
-    if (!c || !ensemble || !start || !tape || !tape_off || !out) return fail("null argument");
+// slice chains on a given ensemble from given starts: the replay instantiation on explicit tapes, or the production
+// instantiation (Philox draws) recording what it consumed (trace)
+static int slice_on_given(cpn_ctx* c, bool replay, int32_t P, const double* ensemble, int32_t C, const double* start,
+                          int32_t cycle_idx, const double* tape, const int64_t* tape_off, double mu, int32_t nmcmc,
+                          int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes, uint64_t chain_base, const double* mean,
+                          const double* eigval, const double* eigvec, double* out, int32_t* steps, int32_t* accepted,
+                          int32_t* evals, double* last, double* trace, int32_t trace_cap) {
     if (P < 2 || C < 1 || maxmcmc < 1) return fail("bad sizes");
     CK(cudaSetDevice(c->cfg.device));
     const int D = c->D, Dp = c->Dp;
-    std::vector<double> ex((size_t)P * Dp, 0.0), sx((size_t)C * Dp, 0.0), sl(C), sp(C);
+    std::vector<double> ex((size_t)P * Dp, 0.0), sx((size_t)C * Dp, 0.0), sl(C), sp(C), ev((size_t)D * Dp, 0.0), es(D, 0.0), mn(D, 0.0);
     for (int i = 0; i < P; ++i)
         for (int d = 0; d < D; ++d) ex[(size_t)i * Dp + d] = ensemble[(size_t)i * D + d];
     for (int i = 0; i < C; ++i) {
@@ -2099,49 +2101,93 @@ extern "C" int cpn_replay_slice(cpn_ctx* c, int32_t P, const double* ensemble, i
         sl[i] = start[(size_t)i * (D + 2) + D];
         sp[i] = start[(size_t)i * (D + 2) + D + 1];
     }
-    const size_t ntape = (size_t)tape_off[C];
-    double *dex, *dsx, *dsl, *dsp, *dtape, *dox, *dol, *dop, *dlast, *dEL, *dEP;
-    long long* doff;
-    int *dst, *dac, *dev;
-    if (dalloc(&dex, ex.size()) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) || dalloc(&dtape, ntape + 8) ||
-        dalloc(&doff, C + 1) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) || dalloc(&dst, C) ||
-        dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dlast, (size_t)C * 4) || dalloc(&dEL, P) || dalloc(&dEP, P))
-        return 1;
-    CK(h2d_sync(dex, ex.data(), ex.size() * sizeof(double)));
-    CK(h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)));
-    CK(h2d_sync(dsl, sl.data(), C * sizeof(double)));
-    CK(h2d_sync(dsp, sp.data(), C * sizeof(double)));
-    CK(h2d_sync(dtape, tape, ntape * sizeof(double)));
-    CK(h2d_sync(doff, tape_off, (C + 1) * sizeof(long long)));
-    SliceParams p;
-    memset(&p, 0, sizeof p);
-    p.ens_x = dex; p.ens_logL = dEL; p.ens_logP = dEP; p.ens_n = P; p.Dp = Dp; p.D = D;
-    p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
-    p.lo = c->d_lo; p.hi = c->d_hi;
-    p.cycle = c->d_slice_cycle; p.cycle_len = c->slice_cycle_len; p.cycle_pos0 = cycle_idx;
-    p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.mu_override = mu;
-    p.maxmcmc = maxmcmc; p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
-    p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
-    p.out_evals[0] = dev;
-    p.tape = dtape; p.tape_off = doff; p.compat = compat; p.last = dlast;
-    if (slice_scratch_launch(c, p, 1, lanes, C)) return 1;
-    std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
-    CK(cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < C; ++i) {
-        for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
-        out[(size_t)i * (D + 2) + D] = ol[i];
-        out[(size_t)i * (D + 2) + D + 1] = op[i];
-    }
-    if (steps) CK(cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost));
-    if (accepted) CK(cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost));
-    if (evals) CK(cudaMemcpy(evals, dev, C * sizeof(int), cudaMemcpyDeviceToHost));
-    if (last) CK(cudaMemcpy(last, dlast, (size_t)C * 4 * sizeof(double), cudaMemcpyDeviceToHost));
-    void* fr[] = {dex, dsx, dsl, dsp, dtape, doff, dox, dol, dop, dst, dac, dev, dlast, dEL, dEP};
+    if (mean && eigval && eigvec)
+        for (int i = 0; i < D; ++i) {
+            mn[i] = mean[i];
+            es[i] = sqrt(fabs(eigval[i]));
+            for (int k = 0; k < D; ++k) ev[(size_t)i * Dp + k] = eigvec[(size_t)k * D + i];   // numpy layout: column i = eigenvector i
+        }
+    const size_t ntape = replay ? (size_t)tape_off[C] : 0;
+    const size_t ntrace = trace ? (size_t)C * trace_cap : 0;
+    double *dex = nullptr, *dsx = nullptr, *dsl = nullptr, *dsp = nullptr, *dtape = nullptr, *dox = nullptr, *dol = nullptr, *dop = nullptr,
+           *dlast = nullptr, *dEL = nullptr, *dEP = nullptr, *dmn = nullptr, *des = nullptr, *dvec = nullptr, *dtr = nullptr;
+    long long* doff = nullptr;
+    int *dst = nullptr, *dac = nullptr, *dev = nullptr;
+    int rc = 1;
+    do {
+        if (dalloc(&dex, ex.size()) || dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) || dalloc(&dtape, ntape + 8) ||
+            dalloc(&doff, C + 1) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) || dalloc(&dst, C) ||
+            dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dlast, (size_t)C * 4) || dalloc(&dEL, P) || dalloc(&dEP, P) ||
+            dalloc(&dmn, D) || dalloc(&des, D) || dalloc(&dvec, ev.size()) || dalloc(&dtr, ntrace + 1))
+            break;
+        if (h2d_sync(dex, ex.data(), ex.size() * sizeof(double)) != cudaSuccess || h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)) != cudaSuccess ||
+            h2d_sync(dsl, sl.data(), C * sizeof(double)) != cudaSuccess || h2d_sync(dsp, sp.data(), C * sizeof(double)) != cudaSuccess ||
+            h2d_sync(dmn, mn.data(), D * sizeof(double)) != cudaSuccess || h2d_sync(des, es.data(), D * sizeof(double)) != cudaSuccess ||
+            h2d_sync(dvec, ev.data(), ev.size() * sizeof(double)) != cudaSuccess ||
+            (replay && (h2d_sync(dtape, tape, ntape * sizeof(double)) != cudaSuccess ||
+                        h2d_sync(doff, tape_off, (C + 1) * sizeof(long long)) != cudaSuccess))) {
+            fail("slice chains on a given ensemble: host to device copy failed");
+            break;
+        }
+        SliceParams p;
+        memset(&p, 0, sizeof p);
+        p.ens_x = dex; p.ens_logL = dEL; p.ens_logP = dEP; p.ens_n = P; p.Dp = Dp; p.D = D;
+        p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
+        p.lo = c->d_lo; p.hi = c->d_hi;
+        p.cycle = c->d_slice_cycle; p.cycle_len = c->slice_cycle_len; p.cycle_pos0 = cycle_idx % c->slice_cycle_len;
+        p.mean = dmn; p.eig_scale = des; p.eig_vec = dvec;
+        p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.nmcmc_override = nmcmc; p.mu_override = mu;
+        p.maxmcmc = maxmcmc; p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
+        p.chain_base = chain_base;
+        p.seed_lo = (uint32_t)c->cfg.seed; p.seed_hi = (uint32_t)(c->cfg.seed >> 32);
+        p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
+        p.out_evals[0] = dev;
+        p.tape = dtape; p.tape_off = doff; p.compat = compat; p.last = dlast;
+        if (trace) { p.trace = dtr; p.trace_cap = trace_cap; }
+        if (slice_scratch_launch(c, p, replay ? 1 : 0, lanes, C)) break;
+        std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
+        if (cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            (steps && cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (accepted && cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (evals && cudaMemcpy(evals, dev, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (last && cudaMemcpy(last, dlast, (size_t)C * 4 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (trace && cudaMemcpy(trace, dtr, ntrace * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)) {
+            fail("slice chains on a given ensemble: device to host copy failed");
+            break;
+        }
+        for (int i = 0; i < C; ++i) {
+            for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
+            out[(size_t)i * (D + 2) + D] = ol[i];
+            out[(size_t)i * (D + 2) + D + 1] = op[i];
+        }
+        rc = 0;
+    } while (0);
+    void* fr[] = {dex, dsx, dsl, dsp, dtape, doff, dox, dol, dop, dst, dac, dev, dlast, dEL, dEP, dmn, des, dvec, dtr};
     for (void* q : fr)
         if (q) cudaFree(q);
-    return 0;
+    return rc;
+}
+
+extern "C" int cpn_replay_slice(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start,
+                                int32_t cycle_idx, const double* tape, const int64_t* tape_off, double mu, int32_t nmcmc,
+                                int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes, double* out, int32_t* steps,
+                                int32_t* accepted, int32_t* evals, double* last) {
+    if (!c || !ensemble || !start || !tape || !tape_off || !out) return fail("null argument");
+    return slice_on_given(c, true, P, ensemble, C, start, cycle_idx, tape, tape_off, mu, nmcmc, maxmcmc, logLmin, compat, lanes, 0,
+                          nullptr, nullptr, nullptr, out, steps, accepted, evals, last, nullptr, 0);
+}
+
+extern "C" int cpn_trace_slice(cpn_ctx* c, int32_t P, const double* ensemble, int32_t C, const double* start,
+                               const double* mean, const double* eigval, const double* eigvec, int32_t cycle_idx, double mu,
+                               int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t lanes, uint64_t chain_base, double* out,
+                               int32_t* steps, int32_t* accepted, int32_t* evals, double* last, double* trace, int32_t trace_cap) {
+    if (!c || !ensemble || !start || !out || !trace) return fail("null argument");
+    if (trace_cap < c->D + 16) return fail("cpn_trace_slice: trace_cap too small");
+    if (c->cfg.functor == CPN_USER) return fail("cpn_trace_slice is not available for a user functor");
+    return slice_on_given(c, false, P, ensemble, C, start, cycle_idx, nullptr, nullptr, mu, nmcmc, maxmcmc, logLmin, 0, lanes,
+                          chain_base, mean, eigval, eigvec, out, steps, accepted, evals, last, trace, trace_cap);
 }
 
 extern "C" int cpn_replay_hmc(cpn_ctx* c, int32_t C, const double* start, const double* cov, double logdet,

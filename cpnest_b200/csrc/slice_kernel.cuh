@@ -29,6 +29,11 @@ struct SliceParams : ChainParams {      // maxmcmc is also max_steps_out and max
     int compat;
     double* last;                 // [chains][4] = {Ne, Nc, L, R} of the chain's last slice, or null
     double* dir_out;              // [chains][D] direction of the chain's first slice, or null (tests)
+    // production, test entry (cpn_trace_slice): what every slice of every chain consumed besides the chain state, in the order
+    // of the replay tape: trace[c][trace_cap] = { n, then per slice: kind, nX, uL, direction data ({i0, i1} / the D-vector),
+    // Exp(1), uJ, X'_1 .. X'_nX }, n = doubles written after the first (-1: the area was too small), or null
+    double* trace;
+    int trace_cap;
 };
 
 template <int G, int E, class Model, bool REPLAY>
@@ -58,6 +63,9 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
     const uint32_t ens_n = (uint32_t)p.ens_n;
     const double mu_diff = (REPLAY && p.compat) ? (double)(float)mu : mu;   // LivePoint * float, parameter.pyx:96
 
+    double* tr = (!REPLAY && p.trace != nullptr && valid) ? p.trace + (size_t)c * p.trace_cap : nullptr;
+    int ti = 1, ti_nx = 0;        // next free double of the chain's trace area; where the current slice's nX goes
+
     // point on the slice: direction * t + old (LivePoint.__mul__ then __add__; t rounded to fp32 in the reference)
     auto along = [&](const double (&dir)[E], double t, double (&out)[E]) {
         const double ts = (REPLAY && p.compat) ? (double)(float)t : t;
@@ -74,6 +82,9 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
         // ---- draws of this slice + direction ----------------------------------------------------------
         double uL, eexp, uJ;
         double dir[E];
+        double trace_a = 0.0, trace_b = 0.0, trace_v[E];     // direction data as the replay tape holds it (trace entry only)
+#pragma unroll
+        for (int e = 0; e < E; ++e) trace_v[e] = 0.0;
         if (REPLAY) {
             uL = active ? tp[0] : 0.5;
             const double* q = tp + 1;
@@ -121,6 +132,7 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
                 load_row<G, E>(g, p.ens_x + (size_t)i1 * p.Dp, D, rb);
 #pragma unroll
                 for (int e = 0; e < E; ++e) dir[e] = (ra[e] - rb[e]) * mu;
+                trace_a = (double)i0; trace_b = (double)i1;
             } else {
                 // one N(0,1) per coordinate: block (chain, slice, 0x80000000 | d)
                 double z[E], n2 = 0.0;
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
                 if (kind == CPN_SLICE_GAUSS) {
                     const double sc = mu / sqrt(g.sum(n2));           // unit vector * mu, proposal.py:184-187
 #pragma unroll
-                    for (int e = 0; e < E; ++e) dir[e] = z[e] * sc;
+                    for (int e = 0; e < E; ++e) { dir[e] = z[e] * sc; trace_v[e] = z[e]; }
                 } else {
                     // mu * N(mean, cov) (the mean is not subtracted, proposal.py:172)
                     double acc[E];
@@ -155,10 +167,36 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
                         }
                     }
 #pragma unroll
-                    for (int e = 0; e < E; ++e) dir[e] = mu * acc[e];
+                    for (int e = 0; e < E; ++e) { dir[e] = mu * acc[e]; trace_v[e] = acc[e]; }
                 }
             }
         }
+        bool rec = false;             // this slice of this chain is recorded
+        if (!REPLAY && tr != nullptr && active) {
+            if (ti + D + 8 > p.trace_cap) {
+                if (g.lane == 0) tr[0] = -1.0;
+                tr = nullptr;
+            } else {
+                rec = true;
+                if (g.lane == 0) { tr[ti] = (double)kind; tr[ti + 2] = uL; }
+                ti_nx = ti + 1;
+                ti += 3;
+                if (kind == CPN_SLICE_DIFF) {
+                    if (g.lane == 0) { tr[ti] = trace_a; tr[ti + 1] = trace_b; }
+                    ti += 2;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int d = g.lane + e * G;
+                        if (d < D) tr[ti + d] = trace_v[e];
+                    }
+                    ti += D;
+                }
+                if (g.lane == 0) { tr[ti] = eexp; tr[ti + 1] = uJ; tr[ti_nx] = 0.0; }
+                ti += 2;
+            }
+        }
+        int nX = 0;
         if (p.dir_out != nullptr && s == 0 && valid) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -233,6 +271,15 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
                 const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 0x40000000u | (uint32_t)(sl >> 2), p.seed_lo, p.seed_hi);
                 const uint32_t w = (sl & 2) ? ((sl & 1) ? ru.v[3] : ru.v[2]) : ((sl & 1) ? ru.v[1] : ru.v[0]);
                 Xp = fma(R - L, u32_to_unit_open(w), L);
+                if (rec && searching) {
+                    if (ti >= p.trace_cap) {
+                        if (g.lane == 0) tr[0] = -1.0;
+                        tr = nullptr; rec = false;
+                    } else {
+                        if (g.lane == 0) tr[ti] = Xp;
+                        ++ti; ++nX;
+                    }
+                }
             }
             double xn[E];
             along(dir, Xp, xn);
@@ -256,6 +303,7 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
             else if (shrink && Xp > 0.0) { R = Xp; Nc += 1.0; }
             searching = shrink;
         }
+        if (rec && g.lane == 0) tr[ti_nx] = (double)nX;
         if (active) {
             ++steps;
             ne_sum += (int)Ne;
@@ -265,6 +313,7 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
     }
 
     ch.finish(p, steps, accepted, evals, ne_sum, nc_sum);
+    if (tr != nullptr && g.lane == 0) tr[0] = (double)(ti - 1);
     if (valid) {
         if (p.last != nullptr && g.lane == 0) {
             double* q = p.last + (size_t)c * 4;

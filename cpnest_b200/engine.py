@@ -432,6 +432,55 @@ class Engine:
                                           L.iptr(acc), L.iptr(evals), L.dptr(last)))
         return out, steps, acc, evals, last
 
+    def trace_slice(self, ensemble, start, cycle_idx, mu, nmcmc, maxmcmc, logLmin, mean=None, eigval=None, eigvec=None, lanes=0,
+                    chain_base=0, trace_cap=None):
+        """The production slice kernel on given chains (include/cpnest_b200.h cpn_trace_slice).  Returns (out, steps, accepted,
+        evals, last, tapes): tapes[c] is the list of events (kind, value) the chain consumed, in the vocabulary of the oracle's
+        tape reader ("np_uniform", "sample", "np_normal", "np_mvn", "np_exponential"), kinds[c] the direction kind per slice."""
+        ens = L.f64(ensemble)
+        start = L.f64(start).reshape(-1, self.dim + 2)
+        Cn, D = start.shape[0], self.dim
+        cap = int(trace_cap or (maxmcmc + 2) * (D + 6 + 64))
+        out = np.empty((Cn, D + 2))
+        steps = np.empty(Cn, dtype=np.int32)
+        acc = np.empty(Cn, dtype=np.int32)
+        evals = np.empty(Cn, dtype=np.int32)
+        last = np.empty((Cn, 4))
+        trace = np.zeros((Cn, cap))
+        stats = [None, None, None]
+        if mean is not None:
+            stats = [L.f64(mean), L.f64(eigval), L.f64(np.asarray(eigvec).reshape(D, D))]
+        L.check(self.lib.cpn_trace_slice(self.h, ens.shape[0], L.dptr(ens), Cn, L.dptr(start),
+                                         *[L.dptr(a) if a is not None else None for a in stats], int(cycle_idx), float(mu),
+                                         int(nmcmc), int(maxmcmc), float(logLmin), int(lanes), int(chain_base), L.dptr(out),
+                                         L.iptr(steps), L.iptr(acc), L.iptr(evals), L.dptr(last), L.dptr(trace), cap))
+        tapes, kinds = [], []
+        for c in range(Cn):
+            t = trace[c]
+            n = int(t[0])
+            if n < 0:
+                raise RuntimeError("trace_slice: trace_cap %d too small" % cap)
+            ev, kd, i = [], [], 1
+            while i < 1 + n:
+                kind, nx = int(t[i]), int(t[i + 1])
+                ev.append(("np_uniform", float(t[i + 2])))
+                i += 3
+                if kind == 0:
+                    ev.append(("sample", (int(t[i]), int(t[i + 1]))))
+                    i += 2
+                else:
+                    ev.append(("np_normal" if kind == 1 else "np_mvn", t[i:i + D].copy()))
+                    i += D
+                ev.append(("np_exponential", float(t[i])))
+                ev.append(("np_uniform", float(t[i + 1])))
+                i += 2
+                ev.extend(("np_uniform", float(v)) for v in t[i:i + nx])
+                i += nx
+                kd.append(kind)
+            tapes.append(ev)
+            kinds.append(kd)
+        return out, steps, acc, evals, last, tapes, kinds
+
     def replay_hmc(self, start, cov, logdet, tapes, dt, L, logLmin, max_traj=1000, lanes=0):
         """HMC chains from explicit tapes (include/cpnest_b200.h cpn_replay_hmc).
         Returns (out, steps, accepted, evals, log_J)."""

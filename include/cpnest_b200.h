@@ -305,6 +305,19 @@ int cpn_replay_slice(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C,
                      int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t compat, int32_t lanes,
                      double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted, int32_t* evals,
                      double* last /*[C][4]*/);
+/* The PRODUCTION slice kernel (the instantiation every run launches: Philox draws, closed-form stepping out under a flat
+ * prior, fused multiply-adds) on given chains, recording what every slice consumed besides the chain state, in the order of
+ * the replay tape above: trace[c][trace_cap] = { n, then per slice: direction kind, nX, u of reset_boundaries, direction data
+ * ({i0, i1} or the D-vector), Exp(1) draw, u of J, X'_1 .. X'_nX }, n = doubles written after the first (-1: trace_cap was
+ * too small).  Feeding these to a restatement of SliceSampler.yield_sample (cpnest/sampler.py:465-569, with its stepping-out
+ * loops :495-524) must reproduce the chain: the step-level parity test of the production path.  mean[D], eigval[D],
+ * eigvec[D][D] (numpy layout) feed the correlated-Gaussian direction (cpnest/proposal.py:167-173), NULL: zeros.  Chain c uses
+ * the Philox stream of chain id chain_base + c; the cycle is the context's (cpn_set_slice_cycle), entered at cycle_idx. */
+int cpn_trace_slice(cpn_ctx* ctx, int32_t P, const double* ensemble, int32_t C, const double* start,
+                    const double* mean, const double* eigval, const double* eigvec, int32_t cycle_idx, double mu,
+                    int32_t nmcmc, int32_t maxmcmc, double logLmin, int32_t lanes, uint64_t chain_base,
+                    double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted, int32_t* evals, double* last /*[C][4]*/,
+                    double* trace /*[C][trace_cap]*/, int32_t trace_cap);
 /* HMC chains driven by an explicit tape (HamiltonianMonteCarloSampler.yield_sample, cpnest/sampler.py:365-402, with
  * ConstrainedLeapFrog, cpnest/proposal.py:793-844).  Per chain c the doubles tape[tape_off[c] .. tape_off[c+1]) hold,
  * trajectory after trajectory, { p0[D] (momenta_distribution.rvs()), normal[D] for every reflection off the likelihood

@@ -827,6 +827,44 @@ def production_draw(seed, chain_id, step, kind, ens_n, D, eig_scale, flat_prior=
     return [float(kind), float(i0), float(i1), float(i2), c0, c1, c2, thr]
 
 
+def production_slice_draw(seed, chain_id, s, kind, ens_n, D, mean=None, eig_scale=None, eigen_vectors=None):
+    """slice_kernel.cuh, production branch: what slice number `s` of chain `chain_id` draws from the Philox stream before the
+    shrinkage (counter = (chain id lo, hi, slice, block), key = seed).  Returns (uL, direction data, Exp(1), uJ):
+      block 0: uL = u(v0) (reset_boundaries, sampler.py:444), uJ = u(v1) (:491), Exp(1) = -log u(v2) (:490),
+               differential direction: first member = index(v3, n); block 1: second member = index(v0, n - 1), skipping the first
+               (`sample(list(ensemble), 2)`, proposal.py:131)
+      block 0x80000000 | d: one N(0,1) per coordinate d (fp32 Box-Muller of v0, v1) -> the vector np.random.normal returns
+               (proposal.py:183), or z of mean + sum_i z_i sqrt|lambda_i| v_i = the multivariate_normal sample (:169-171)."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    clo, chi = chain_id & 0xFFFFFFFF, (chain_id >> 32) & 0xFFFFFFFF
+    r = philox4x32_10((clo, chi, s, 0), key)
+    uL, uJ = u32_to_unit_open(r[0]), u32_to_unit_open(r[1])
+    eexp = -math.log(u32_to_unit_open(r[2]))
+    if kind == SLICE_DIFF:
+        i0 = u32_to_index(r[3], ens_n)
+        i1 = u32_to_index(philox4x32_10((clo, chi, s, 1), key)[0], ens_n - 1)
+        i1 += i1 >= i0
+        return uL, (i0, i1), eexp, uJ
+    z = np.empty(D)
+    for d in range(D):
+        q = philox4x32_10((clo, chi, s, 0x80000000 | d), key)
+        z[d] = box_muller_f32(q[0], q[1])[0]
+    if kind == SLICE_GAUSS:
+        return uL, z, eexp, uJ
+    v = np.array(mean, dtype=np.float64)
+    for i in range(D):
+        v = v + (z[i] * eig_scale[i]) * np.asarray(eigen_vectors)[:, i]
+    return uL, v, eexp, uJ
+
+
+def production_slice_uniform(seed, chain_id, s, k):
+    """The uniform behind the k-th shrinkage candidate of slice `s` (slice_kernel.cuh: word k & 3 of block
+    0x40000000 | (k >> 2)); the candidate is X' = fma(R - L, u, L), np.random.uniform(L, R) of sampler.py:530."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    r = philox4x32_10((chain_id & 0xFFFFFFFF, (chain_id >> 32) & 0xFFFFFFFF, s, 0x40000000 | (k >> 2)), key)
+    return u32_to_unit_open(r[k & 3])
+
+
 def mh_chain_from_draws(model, ens, eigen_vectors, start, start_logL, start_logP, draws, Nmcmc, maxmcmc, logLmin):
     """MetropolisHastingsSampler.yield_sample (sampler.py:322-358) on the per-step inputs `draws[s] = [kind, i0, i1, i2,
     c0, c1, c2, thr]` recorded by the production kernel.  The ensemble is the fixed live snapshot `ens` (the device does

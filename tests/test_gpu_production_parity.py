@@ -156,3 +156,73 @@ def test_production_mh_chain_long_cycle_and_immobile_chain():
                 for s in range(64):
                     pos = (pos + 1) % 300
                     assert draws[0, s, 0] == cyc[pos]
+
+
+# ---- the production SLICE kernel --------------------------------------------------------------------------------------------
+# cpn_trace_slice runs k_slice_chains<G, E, Model, REPLAY=false> (Philox draws, closed-form stepping out under a flat prior,
+# FMAs) and records what every slice consumed, in the vocabulary of the oracle's tape reader.  (a) those inputs are a known
+# function of the Philox stream -> oracle.production_slice_draw / production_slice_uniform; (b) the chain they drive is the
+# reference's SliceSampler.yield_sample (cpnest/sampler.py:465-569) WITH its stepping-out loops (:495-524) -> oracle.slice_chain:
+# slices, accepted, likelihood calls, expansions and contractions exact, interval and end point to 1e-12.
+@pytest.mark.parametrize("name,lanes,spread,mu", [("gaussian2d", 1, 0.3, 1.5), ("gaussian10d", 4, 0.3, 1.0), ("gaussian10d", 8, 0.3, 4.0),
+                                                  ("gaussian10d", 16, 0.3, 0.3), ("gaussian50d", 16, 0.3, 1.0), ("gaussian50d", 8, 0.3, 2.0),
+                                                  ("rosenbrock10d", 8, 0.25, 0.5), ("gaussian_mean_sigma", 1, 0.8, 0.3)])
+def test_production_slice_chain_equals_the_oracle_slice_by_slice(name, lanes, spread, mu):
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model(name)
+    D = m.D
+    rs = np.random.RandomState(41 + lanes)
+    P, C, nmcmc, maxmcmc, cidx, chain_base, seed = 40, 5, 6, 30, 3, 4242, 1234
+    ens, start, logLmin, w, v = _setup(m, P, C, rs, spread)
+    mean = ens.mean(0)
+    cycle = [0, 1, 2, 2, 0, 1, 0]                          # differential, Gaussian, correlated-Gaussian directions
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=maxmcmc, seed=seed, sampler="slice") as e:
+        e.set_slice_cycle(cycle)
+        out, steps, acc, evals, last, tapes, kinds = e.trace_slice(ens, start, cidx, mu, nmcmc, maxmcmc, logLmin, mean=mean,
+                                                                    eigval=w, eigvec=v, lanes=lanes, chain_base=chain_base)
+    scale = np.sqrt(np.abs(w))
+    moved = 0
+    for c in range(C):
+        pool = [start[c, :D].copy()] + [x.copy() for x in ens]
+        pool_logL = [start[c, D]] + [0.0] * P                # (only the start point's values are read)
+        pool_logP = [start[c, D + 1]] + [0.0] * P
+        tp = O.TapeReader(tapes[c])
+        r = O.slice_chain(m, pool, pool_logL, pool_logP, cycle, cidx, mu, tp, nmcmc, maxmcmc, logLmin, compat=False,
+                          mcmc_counter=10 ** 9)
+        assert tp.exhausted(), (name, lanes, c)
+        assert (steps[c], acc[c], evals[c]) == (r["steps"], r["accepted"], r["evals"]), (name, lanes, c, steps[c], acc[c], evals[c], r)
+        assert (last[c, 0], last[c, 1]) == (r["Ne"], r["Nc"]), (name, lanes, c, last[c], r["Ne"], r["Nc"])
+        np.testing.assert_allclose(last[c, 2:], [r["L"], r["R"]], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(out[c, :D], r["out"], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(out[c, D], r["logL"], rtol=1e-12)
+        np.testing.assert_allclose(out[c, D + 1], r["logP"], rtol=1e-12, atol=1e-300)
+        moved += r["accepted"]
+        # (a) the recorded inputs follow from the Philox stream as the oracle restates it
+        assert len(kinds[c]) == r["steps"]
+        i = 0
+        for s, kind in enumerate(kinds[c]):
+            assert kind == cycle[(cidx + 1 + s) % len(cycle)]
+            uL, data, eexp, uJ = O.production_slice_draw(seed, chain_base + c, s, kind, P, D, mean, scale, v)
+            ev = tapes[c]
+            assert ev[i] == ("np_uniform", uL)
+            if kind == 0:
+                assert ev[i + 1] == ("sample", data)
+            else:
+                # fp32 Box-Muller on the device's fast log / sincos units: a few fp32 ulps
+                np.testing.assert_allclose(ev[i + 1][1], data, rtol=2e-5, atol=2e-5 * (1.0 if kind == 1 else float(np.max(scale))))
+            np.testing.assert_allclose(ev[i + 2][1], eexp, rtol=1e-13)
+            assert ev[i + 3] == ("np_uniform", uJ)
+            i += 4
+            k = 0
+            while i < len(ev) and ev[i][0] == "np_uniform" and not _starts_slice(ev, i, kinds[c], s):
+                assert 0.0 < O.production_slice_uniform(seed, chain_base + c, s, k) < 1.0
+                i += 1
+                k += 1
+    assert moved > 0
+
+
+def _starts_slice(ev, i, kinds, s):
+    """True if event i is the first event of slice s + 1 (a slice starts with np_uniform followed by its direction data)."""
+    if s + 1 >= len(kinds) or i + 1 >= len(ev):
+        return False
+    return ev[i + 1][0] in ("sample", "np_normal", "np_mvn")
