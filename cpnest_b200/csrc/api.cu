@@ -1217,14 +1217,23 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     const bool corr = !c->staged_external;
     // the mid-chain snapshots travel with the fused exchange (and trivially on one GPU), not with the NCCL record
     const bool twolag_ok = (c->world == 1 || c->n_peers > 0) && !(c->cfg.flags & CPN_NO_TWO_LAG);
-    if (corr) {
+    MergeParams m;
+    memset(&m, 0, sizeof m);
+    m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
+    m.rho = c->staged_external ? nullptr : c->d_rho;
+    m.rho2_ema = c->d_rho2;
+    m.rho_mid = (m.rho != nullptr && twolag_ok) ? c->d_rho_mid : nullptr;
+    m.lag_ema = c->d_lag_ema;
+    m.allow_twolag = twolag_ok ? 1 : 0;
+    for (int k = 0; k < kNumKinds; ++k) m.kind_n[k] = kb[k + 1] - kb[k];
+    {
         // dependence between chain start and chain end across the (whole, gathered) batch for the chain-length
-        // control, and the batch counters: on the accumulation stream (idle by now), beside the ranking of the
-        // replacements below; the merge waits for both
+        // control, the batch counters and the controllers themselves: on the accumulation stream (idle by now), beside
+        // the ranking of the replacements below; the merge waits for both
         cudaStream_t cs = c->acc_stream;
         CK(cudaEventRecord(c->ev_ins, c->stream));
         CK(cudaStreamWaitEvent(cs, c->ev_ins, 0));
-        for (int k = 0; k < kNumKinds; ++k) {
+        for (int k = 0; corr && k < kNumKinds; ++k) {
             if (kb[k + 1] <= kb[k]) continue;
             // (the kinds' statistics share one scratch: they run one after the other on this stream)
             if (launch_chain_corr(c, cs, k, kb[k], kb[k + 1], c->d_rho + k * (c->D + 1), twolag_ok ? c->d_rho_mid + k * (c->D + 1) : nullptr))
@@ -1237,6 +1246,8 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
                 c->launches += 1;
             }
         }
+        k_adapt_batch<<<1, 1, 0, cs>>>(m);
+        c->launches += 1;
         CK(cudaEventRecord(c->ev_corr, cs));
     }
     // rank of every replacement among the replacements: buckets between the sorted survivors (ns_kernels.cuh)
@@ -1256,15 +1267,6 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         k_rank_final<<<gb, T, 0, c->stream>>>(c->d_state, c->d_new_logL, K, c->d_nle, hist, cursor, members, c->d_rank, c->d_snew);
         c->launches += 5;
     }
-    MergeParams m;
-    memset(&m, 0, sizeof m);
-    m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
-    m.rho = c->staged_external ? nullptr : c->d_rho;
-    m.rho2_ema = c->d_rho2;
-    m.rho_mid = (m.rho != nullptr && twolag_ok) ? c->d_rho_mid : nullptr;
-    m.lag_ema = c->d_lag_ema;
-    m.allow_twolag = twolag_ok ? 1 : 0;
-    for (int k = 0; k < kNumKinds; ++k) m.kind_n[k] = kb[k + 1] - kb[k];
     c->staged_external = false;
     m.order_in = c->d_order[c->cur]; m.skeys_in = c->d_skeys[c->cur];
     m.order_out = c->d_order[c->cur ^ 1]; m.skeys_out = c->d_skeys[c->cur ^ 1];
@@ -1273,7 +1275,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     m.new_x = c->d_new_x; m.new_logL = c->d_new_logL; m.new_logP = c->d_new_logP;
     m.dead_x = c->d_dead_x; m.dead_logL = c->d_dead_logL; m.dead_logP = c->d_dead_logP;
     m.insertion = c->d_ins;
-    if (corr) CK(cudaStreamWaitEvent(c->stream, c->ev_corr, 0));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_corr, 0));
     if (c->wait_cov) {     // an asynchronous refresh must have read the live rows before they are overwritten
         CK(cudaStreamWaitEvent(c->stream, c->ev_cov, 0));
         c->wait_cov = false;

@@ -717,16 +717,21 @@ __global__ void k_merge_commit(const MergeParams p) {
         p.dead_logP[dead0 + i] = p.live_logP[slot];
         p.live_logL[slot] = key;
         p.live_logP[slot] = p.new_logP[i];
-        if (i == 0) {
-            const int nrho = p.Dreal + 1;
-            for (int kind = 0; kind < kNumKinds; ++kind)
-                if (p.kind_n[kind] > 0)
-                    adapt_nmcmc(p.st_w, kind, p.kind_n[kind], p.rho != nullptr ? p.rho + kind * nrho : nullptr,
-                                p.rho2_ema + kind * nrho, p.rho != nullptr ? nrho : 0,
-                                (p.rho_mid != nullptr && kind == CPN_SAMPLER_MH) ? p.rho_mid + kind * nrho : nullptr,
-                                p.lag_ema + 2 * kind * nrho, kind == CPN_SAMPLER_MH ? p.allow_twolag : 0);
-        }
     }
+}
+
+// The chain-length controllers of the batch's sampler kinds (adapt_nmcmc: a serial pass over the D + 1 correlations of a
+// kind).  Its own launch on the stream of the chain statistics, beside the ranking kernels: in the merge kernel it was one
+// thread's serial work on the main stream's critical path.
+__global__ void k_adapt_batch(const MergeParams p) {
+    if (p.st->done) return;
+    const int nrho = p.Dreal + 1;
+    for (int kind = 0; kind < kNumKinds; ++kind)
+        if (p.kind_n[kind] > 0)
+            adapt_nmcmc(p.st_w, kind, p.kind_n[kind], p.rho != nullptr ? p.rho + kind * nrho : nullptr,
+                        p.rho2_ema + kind * nrho, p.rho != nullptr ? nrho : 0,
+                        (p.rho_mid != nullptr && kind == CPN_SAMPLER_MH) ? p.rho_mid + kind * nrho : nullptr,
+                        p.lag_ema + 2 * kind * nrho, kind == CPN_SAMPLER_MH ? p.allow_twolag : 0);
 }
 
 // copy the (sorted) remaining live points into the dead log: the final sweep
