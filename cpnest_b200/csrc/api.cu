@@ -744,8 +744,8 @@ static int sort_live(cpn_ctx* c) {
     return 0;
 }
 
-// mean, covariance, eigen-decomposition of the live ensemble into eigen buffer `buf`, on stream `st`
-static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events) {
+// mean and covariance of the live ensemble (for eigen buffer `buf`) on stream `st`
+static int launch_moments(cpn_ctx* c, cudaStream_t st, int buf) {
     const int D = c->D, N = c->N;
     if (D > kStatThreads) return fail("ensemble statistics support dim <= %d", kStatThreads);
     k_mean_partial<<<kStatBlocks, kStatThreads, 0, st>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
@@ -757,20 +757,29 @@ static int launch_stats(cpn_ctx* c, cudaStream_t st, int buf, bool record_events
         c->d_x, c->d_mean, N, D, c->Dp, c->d_cov_partial);
     k_cov_final<<<(D * D + 127) / 128, 128, 0, st>>>(c->d_cov_partial, kStatBlocks, N, D, c->d_cov);
     CK(cudaMemcpyAsync(c->d_covbuf[buf], c->d_cov, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if (record_events) CK(cudaEventRecord(c->ev_cov, st));     // the live rows have been read
+    CKL();
+    c->launches += 4;
+    return 0;
+}
+
+// eigen-decomposition of the covariance launch_moments left in d_cov, into eigen buffer `buf`, on stream `st`
+static int launch_eigen(cpn_ctx* c, cudaStream_t st, int buf, bool beside_chains) {
+    const int D = c->D;
     const size_t sm = 4 * (size_t)D * (D | 1) * sizeof(double);
     const int use_smem = sm <= 200 * 1024;
     if (use_smem && sm > 40 * 1024)
         CK(cudaFuncSetAttribute(k_jacobi_eigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     c->eig_calls += 1;
     // beside a running chain kernel only a small block finds room on an SM (registers); alone, use them all
-    const int jt = record_events ? 256 : kJacobiThreads;
-    k_jacobi_eigh<<<1, jt, use_smem ? sm : 0, st>>>(c->d_cov, c->d_covwork, use_smem, D, c->Dp, c->d_eigval[buf],
-                                                               c->d_eigvec[buf], c->d_eigscale[buf], c->d_sweeps);
+    const int jt = beside_chains ? 256 : kJacobiThreads;
+    // (warm start from the eigenvectors in use, the other buffer)
+    k_jacobi_eigh<<<1, jt, use_smem ? sm : 0, st>>>(c->d_cov, c->d_covwork, use_smem, D, c->Dp,
+                                                               (c->cfg.flags & CPN_COLD_EIGEN) ? nullptr : c->d_eigvec[buf ^ 1],
+                                                               c->d_eigval[buf], c->d_eigvec[buf], c->d_eigscale[buf], c->d_sweeps);
     CKL();
-    if (record_events) CK(cudaEventRecord(c->ev_eig, st));
+    if (beside_chains) CK(cudaEventRecord(c->ev_eig, st));
     c->chains_since_stats = 0;
-    c->launches += 5;
+    c->launches += 1;
     return 0;
 }
 
@@ -787,17 +796,22 @@ extern "C" int cpn_update_ensemble_stats(cpn_ctx* c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->cfg.device));
     if (adopt_pending_stats(c)) return 1;
-    if (launch_stats(c, c->stream, c->eig_cur ^ 1, false)) return 1;
+    if (launch_moments(c, c->stream, c->eig_cur ^ 1) || launch_eigen(c, c->stream, c->eig_cur ^ 1, false)) return 1;
     c->eig_cur ^= 1;
     return 0;
 }
 
 // refresh on the side stream: reads the live set as it is now (after everything already enqueued on
-// the main stream), overlaps with the chain kernel of the coming batch, is adopted by the batch after
+// the main stream), overlaps with the chain kernels of the coming batches, is adopted by a later batch.
+// (Measured: a refresh slows the two chain kernels it runs beside by 0.09 ms each - the eigen-decomposition's block
+// shares an SM with three chain blocks for 1 ms.  Running the moments alone on the main stream with one block per SM did
+// not change that and cost 55 us per refresh.)
 static int start_async_stats(cpn_ctx* c) {
     CK(cudaEventRecord(c->ev_main, c->stream));
     CK(cudaStreamWaitEvent(c->side, c->ev_main, 0));
-    if (launch_stats(c, c->side, c->eig_cur ^ 1, true)) return 1;
+    if (launch_moments(c, c->side, c->eig_cur ^ 1)) return 1;
+    CK(cudaEventRecord(c->ev_cov, c->side));     // the live rows have been read
+    if (launch_eigen(c, c->side, c->eig_cur ^ 1, true)) return 1;
     c->eig_pending = true;
     c->eig_pending_age = 0;
     c->wait_cov = true;

@@ -90,8 +90,15 @@ struct DrawFeed {
     StepIn own;      // G == 1 only
     // dump: where to record the 8 values of this step (test entry), or null
     // tag: the kind rides in the top bits of i0 (kernels that cannot read it through the uniform datapath)
+    // self_slot: the live slot the chain started from (-1: the start point was given).  The reference pops a chain's point
+    // from the pool before it evolves it (sampler.py:325: `old = self.evolution_points.popleft()`), so a proposal never
+    // meets the chain's own start among the ensemble members; here the members are drawn from the other ens_n - 1 slots
+    // (a stretch move towards oneself would be a null move that counts as accepted).
     __device__ __forceinline__ void refill(int kind, uint32_t step, uint32_t cid_lo, uint32_t cid_hi, uint32_t k0, uint32_t k1,
-                                           uint32_t ens_n, uint32_t D, const double* eig_scale, uint32_t eig_row0, bool tag, double* dump) {
+                                           uint32_t ens_n, int self_slot, uint32_t D, const double* eig_scale, uint32_t eig_row0,
+                                           bool tag, double* dump) {
+        const uint32_t self = (uint32_t)self_slot;            // compact index c of the other slots -> slot c + (c >= self)
+        if (self_slot >= 0) ens_n -= 1u;
         const Philox4 r = philox4x32_10(cid_lo, cid_hi, step, 0u, k0, k1);
         double thr = (FLAT && kind != CPN_STRETCH) ? -1.0 : log(u32_to_unit_open(r.v[3]));
         uint32_t i0 = u32_to_index(r.v[0], kind == CPN_EIGEN ? D : ens_n);       // EIGEN: randrange(D), proposal.py:338
@@ -108,12 +115,16 @@ struct DrawFeed {
             const uint32_t lo2 = min(i0, i1), hi2 = max(i0, i1);
             i2 += (i2 >= lo2);
             i2 += (i2 >= hi2);
+            if (self_slot >= 0) { i0 += (i0 >= self); i1 += (i1 >= self); i2 += (i2 >= self); }
             const Philox4 q = philox4x32_10(cid_lo, cid_hi, step, 1u, k0, k1);
             ba = q.v[0]; bb = q.v[1]; bc = q.v[2]; bd = q.v[3];
         } else if (kind == CPN_DE) {
             i1 = u32_to_index(r.v[1], ens_n - 1);                                  // sample(...,2), proposal.py:284
             i1 += (i1 >= i0);
+            if (self_slot >= 0) { i0 += (i0 >= self); i1 += (i1 >= self); }
             ba = r.v[2] << 16; bb = r.v[2] & 0xffff0000u;
+        } else if (kind == CPN_STRETCH) {
+            if (self_slot >= 0) i0 += (i0 >= self);
         }
         float ga, gb;
         box_muller_f(ba, bb, ga, gb);
@@ -366,7 +377,7 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
                 const int st = it + g.lane;
                 const int lpos = (p.cycle_pos0 + 1 + st) % clen;           // pre-increment, proposal.py:93
                 const int kind = KU ? (int)p.cyc[lpos] : (int)p.cycle[lpos];
-                feed.refill(kind, (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, (uint32_t)D, p.eig_scale, eig_row0, !KU,
+                feed.refill(kind, (uint32_t)st, cid_lo, cid_hi, p.seed_lo, p.seed_hi, ens_n, ch.start_slot, (uint32_t)D, p.eig_scale, eig_row0, !KU,
                             (dump != nullptr && st < maxmcmc) ? dump + (size_t)st * 8 : nullptr);
             }
             if (G == 1) return feed.own;

@@ -47,7 +47,7 @@ def functor_blob(name, dim, params=None):
 class Engine:
     def __init__(self, functor, bounds, nlive, maxmcmc=100, seed=1234, params=None, device=0,
                  nmcmc_init=0, lanes=0, ns_mode="sequential", nmcmc_safety=5.0, adapt_nmcmc=True,
-                 rho_target=0.0, rank=0, world_size=1, sampler="mh", mix=None, two_lag=True):
+                 rho_target=0.0, rank=0, world_size=1, sampler="mh", mix=None, two_lag=True, cold_eigen=False):
         self.lib = L.load()
         self.functor = functor
         self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
@@ -67,7 +67,7 @@ class Engine:
         cfg.nmcmc_safety = float(nmcmc_safety)
         cfg.adapt_nmcmc = 1 if adapt_nmcmc else 0
         cfg.rho_target = float(rho_target)
-        cfg.flags = 0 if two_lag else 1              # CPN_NO_TWO_LAG
+        cfg.flags = (0 if two_lag else 1) | (2 if cold_eigen else 0)      # CPN_NO_TWO_LAG, CPN_COLD_EIGEN
         cfg.world_size = int(world_size)
         cfg.rank = int(rank)
         if sampler not in L.SAMPLERS:

@@ -88,7 +88,9 @@ typedef struct cpn_config {
 } cpn_config;
 
 enum cpn_config_flags {
-    CPN_NO_TWO_LAG = 1     /* keep the single-lag chain-length control (start/end correlation only) even when it saturates */
+    CPN_NO_TWO_LAG = 1,    /* keep the single-lag chain-length control (start/end correlation only) even when it saturates */
+    CPN_COLD_EIGEN = 2     /* eigen-decomposition of the ensemble covariance from the identity at every refresh (default: warm
+                              start from the eigenvectors in use, a few Jacobi sweeps instead of ~9) */
 };
 
 /* NestedSampler / _NSintegralState observable state (cpnest/NestedSampling.py:88-144, 254-262) */

@@ -784,15 +784,20 @@ def box_muller_f32(r0, r1):
     return float(rad * np.cos(ang, dtype=np.float32)), float(rad * np.sin(ang, dtype=np.float32))
 
 
-def production_draw(seed, chain_id, step, kind, ens_n, D, eig_scale, flat_prior=True):
+def production_draw(seed, chain_id, step, kind, ens_n, D, eig_scale, flat_prior=True, self_slot=None):
     """mh_kernel.cuh DrawFeed::refill: the inputs of MCMC step `step` of chain `chain_id` as a function of the Philox
     stream (counter = (chain id lo, hi, step, block), key = seed).  Returns [kind, i0, i1, i2, c0, c1, c2, thr]:
       WALK    three distinct members (`random.sample(ensemble, 3)`, proposal.py:230), c_j = g_j - mean(g) in fp32
       STRETCH one member (`choice`, :253), c0 = Z = 2^t (fp32), t = uniform(-1,1); thr = log u - D t log 2 (:255-260)
       DE      two distinct members (:284), c0 = g = 1 + 1e-4 N(0,1) in fp32 (:285)
       EIGEN   i0 = randrange(D) (:338), c0 = sqrt|lambda_i0| N(0,1) in fp64 (:339)
-    thr = log(u) - log_J of the prior MH test (sampler.py:337); -1 under a flat prior for the kinds with log_J = 0."""
+    thr = log(u) - log_J of the prior MH test (sampler.py:337); -1 under a flat prior for the kinds with log_J = 0.
+    self_slot: the live slot the chain started from; the members are then drawn from the other ens_n - 1 slots (the reference
+    pops a chain's point from the pool before evolving it, sampler.py:325), compact index c -> slot c + (c >= self_slot)."""
     f = np.float32
+    if self_slot is not None:
+        ens_n -= 1
+    unc = (lambda c: c + (c >= self_slot)) if self_slot is not None else (lambda c: c)
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     clo, chi = chain_id & 0xFFFFFFFF, (chain_id >> 32) & 0xFFFFFFFF
     r = philox4x32_10((clo, chi, step, 0), key)
@@ -807,18 +812,21 @@ def production_draw(seed, chain_id, step, kind, ens_n, D, eig_scale, flat_prior=
         lo2, hi2 = min(i0, i1), max(i0, i1)
         i2 += i2 >= lo2
         i2 += i2 >= hi2
+        i0, i1, i2 = unc(i0), unc(i1), unc(i2)
         q = philox4x32_10((clo, chi, step, 1), key)
         ga, gb = box_muller_f32(q[0], q[1])
         gc, _ = box_muller_f32(q[2], q[3])
         gbar = (f(ga) + f(gb) + f(gc)) * f(1.0 / 3.0)
         c0, c1, c2 = float(f(ga) - gbar), float(f(gb) - gbar), float(f(gc) - gbar)
     elif kind == STRETCH:
+        i0 = unc(i0)                                        # (i1, i2 are not used by this kind)
         t = f(2.0 * u32_to_unit_open(r[1]) - 1.0)
         c0 = float(np.exp2(t, dtype=np.float32))
         thr -= D * (float(t) * 0.69314718055994530942)
     elif kind == DE:
         i1 = u32_to_index(r[1], ens_n - 1)
         i1 += i1 >= i0
+        i0, i1 = unc(i0), unc(i1)
         ga, _ = box_muller_f32((r[2] << 16) & 0xFFFFFFFF, r[2] & 0xFFFF0000)
         c0 = float(f(1e-4) * f(ga) + f(1.0))
     else:
