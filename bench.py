@@ -65,6 +65,9 @@ WORKLOADS = {
     # (HMC as the reference specifies it - mass matrix from the global ensemble covariance - has no inter-mode move and
     # loses a mode of the separated mixture, scripts/baseline_configs.py: the mixture runs with MH)
     "mix20": ("gaussian_mixture_nd", 20, (-10.0, 10.0), None, "mh", -20 * math.log(20.0)),
+    # BASELINE config 4, correlated flavour: N(0, Sigma), condition number 1e2; the D^2 likelihood runs on the
+    # FP64 tensor cores (models.cuh GaussCorr::log_likelihood_block); parameters filled in below
+    "corr50": ("gaussian_corr", 50, (-10.0, 10.0), "corr", "mh", -50 * math.log(20.0)),
 }
 
 
@@ -306,6 +309,9 @@ def main():
         return float(t.item())
 
     functor, dim, (blo, bhi), fparams, sampler, analytic = WORKLOADS[args.workload]
+    if fparams == "corr":
+        from cpnest_b200.models import CorrelatedGaussianModel
+        fparams = CorrelatedGaussianModel(dim=dim, bound=bhi).device_functor[1]
     bounds = [[blo, bhi]] * dim
     np.random.seed(SEED)
     cycle = DefaultProposalCycle().device_cycle()        # drawn like the reference's (proposal.py:71-75)
@@ -378,7 +384,9 @@ def main():
             print(json.dumps({"metric": "whole-run likelihood evals/s (%s, %s sampler)" % (args.workload, sampler), "unit": UNIT,
                               "value": full["evals_per_s"] if full else None, "n_gpus": world, "scaling": args.scaling,
                               "config": {"workload": args.workload, "functor": functor, "dim": dim, "nlive": N, "K": K, "sampler": sampler},
-                              "logz_wall_s": logz_wall_s, "sampler_run": full}), flush=True)
+                              "logz_wall_s": logz_wall_s, "sampler_run": full,
+                              "algorithmic_fp64_tflops": ((full["total_evals"] * 2650.0 + full["total_mcmc_steps"] * 308.0) / logz_wall_s / 1e12
+                                                          if full and args.workload == "corr50" else None)}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return

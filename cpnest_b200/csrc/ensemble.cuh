@@ -196,9 +196,14 @@ __global__ void __launch_bounds__(kJacobiThreads) k_jacobi_eigh(const double* __
     for (; sweep < 30; ++sweep) {
         // convergence: off-diagonal Frobenius norm against the diagonal
         double off = 0.0, dia = 0.0;
-        for (int i = tid; i < D * D; i += nt) {
-            const double a = A[(i / D) * LD + (i % D)];
-            if ((i / D) == (i % D)) dia += a * a; else off += a * a;
+        {
+            const int di = nt / D, dj = nt % D;
+            for (int w = tid, i = tid / D, j = tid % D; w < D * D; w += nt) {
+                const double a = A[i * LD + j];
+                if (i == j) dia += a * a; else off += a * a;
+                i += di; j += dj;
+                if (j >= D) { j -= D; ++i; }
+            }
         }
         red[tid] = off;
         __syncthreads();
@@ -234,14 +239,17 @@ __global__ void __launch_bounds__(kJacobiThreads) k_jacobi_eigh(const double* __
                 }
             }
             __syncthreads();
-            for (int w = tid; w < D * D; w += nt) {
-                const int i = w / D, j = w % D;
+            // (element w = i D + j, w = tid, tid + nt, ...: the pair (i, j) is advanced without divisions)
+            const int di = nt / D, dj = nt % D;
+            for (int w = tid, i = tid / D, j = tid % D; w < D * D; w += nt) {
                 const int pi = partner[i], pj = partner[j];
                 const double ai = alpha[i], bi = beta[i], aj = alpha[j], bj = beta[j];
                 const double t0 = ai * A[i * LD + j] + bi * A[pi * LD + j];
                 const double t1 = ai * A[i * LD + pj] + bi * A[pi * LD + pj];
                 A2[i * LD + j] = aj * t0 + bj * t1;
                 V2[i * LD + j] = aj * V[i * LD + j] + bj * V[i * LD + pj];
+                i += di; j += dj;
+                if (j >= D) { j -= D; ++i; }
             }
             __syncthreads();
             double* t = A; A = A2; A2 = t;
