@@ -1260,7 +1260,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
                 c->launches += 1;
             }
         }
-        k_adapt_batch<<<1, 1, 0, cs>>>(m);
+        k_adapt_batch<<<1, 32, 0, cs>>>(m);
         c->launches += 1;
         CK(cudaEventRecord(c->ev_corr, cs));
     }

@@ -402,9 +402,11 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_mh_chains(cons
         // likelihood makes a step several L2 round trips long, and its own state needs the registers): one set.
         constexpr int AHEAD = BLK ? 1 : 2;
         // kinds of the window of kKindWin steps that holds the step whose inputs are read next (KU)
+        // (the word of the following window is loaded one window ahead: its latency never meets a step)
         uint2 kw = p.cycw[KU ? npos : 0];
+        uint2 kwn = p.cycw[KU ? kw.y : 0];
         auto kind_of = [&](int st) -> int {                                 // st in the current window, or the first of the next
-            if ((st & (kKindWin - 1)) == 0 && st > 0) kw = p.cycw[kw.y];
+            if ((st & (kKindWin - 1)) == 0 && st > 0) { kw = kwn; kwn = p.cycw[kw.y]; }
             return (int)((kw.x >> (2 * (st & (kKindWin - 1)))) & 3u);
         };
         // One MCMC step on its register set (s, kind, r0..r2).  As soon as the proposal has consumed the rows, the inputs

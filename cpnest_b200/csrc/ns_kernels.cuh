@@ -211,26 +211,36 @@ __global__ void __launch_bounds__(kAccThreads) k_ns_accumulate(const AccParams p
 //      rho = exp(-n/tau) the length that reaches rho_target is n * ln(rho_target) / ln(rho).
 // The chain length follows the larger of the two with a moving average.
 // One controller per sampler kind (KindCtl): `chains` chains of kind `kind` returned in this batch.
+// WARP: called by the 32 lanes of one warp - the passes over the nrho correlations (two global loads per entry, otherwise a
+// serial chain of L2 round trips: 17 us for 51 entries) are split over the lanes, the maxima meet by shuffles, lane 0 does the
+// scalar rest.  The per-entry averages and the maxima do not depend on the order: same numbers as the one-thread form.
+template <bool WARP = false>
 __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, const double* rho, double* rho2_ema, int nrho,
                                             const double* rho_mid = nullptr, double* lag_ema = nullptr, int allow_twolag = 0) {
     KindCtl& k = st->ctl[kind];
+    const int lane = WARP ? ((int)threadIdx.x & 31) : 0, nl = WARP ? 32 : 1;
     const unsigned long long steps = k.batch[0], accd = k.batch[1];
-    for (int i = 0; i < 4; ++i) { st->totals[i] += k.batch[i]; k.batch[i] = 0; }
+    const bool first = k.rho_max < 0.0;
+    const int twolag_in = k.twolag;
+    if (WARP) __syncwarp();
+    if (lane == 0)
+        for (int i = 0; i < 4; ++i) { st->totals[i] += k.batch[i]; k.batch[i] = 0; }
     if (steps == 0 || chains <= 0) return;
     const double a = 0.2;
     double qmax = -1.0;
     if (rho != nullptr) {
         // q_d = EMA(rho_d^2 - 1/K): the sampling noise of a correlation over K chains is removed in
         // expectation and averaged down BEFORE the maximum over d is taken
-        const bool first = k.rho_max < 0.0;
-        for (int d = 0; d < nrho; ++d) {
+        for (int d = lane; d < nrho; d += nl) {
             double r2 = rho[d] * rho[d] - 1.0 / (double)chains;
             if (!(r2 == r2)) r2 = 0.0;                       // zero variance in this coordinate
             const double q = first ? r2 : (1.0 - a) * rho2_ema[d] + a * r2;
             rho2_ema[d] = q;
             if (q > qmax) qmax = q;
         }
-        k.rho_max = sqrt(fmax(qmax, 0.0));
+        if (WARP)
+            for (int m = 16; m > 0; m >>= 1) qmax = fmax(qmax, __shfl_xor_sync(0xffffffffu, qmax, m));
+        if (lane == 0) k.rho_max = sqrt(fmax(qmax, 0.0));
     }
     // Two-lag estimate (MH chains that leave a mid-chain snapshot, KindCtl::twolag).  A chain in a multimodal live set is
     // x_t = (centre of its mode) + z_t: the centre never changes, so corr(start, end) keeps a part no chain length removes.
@@ -239,10 +249,10 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, c
     // i.e. q = 1 + 2 corr(d1, d2) is the within-mode correlation over half a chain (0: forgotten, 1: frozen) and q^2 the part
     // of the start/end correlation that decays with the chain length: the target applies to it.
     double dmax = -1.0;
-    if (rho != nullptr && rho_mid != nullptr && lag_ema != nullptr && k.twolag >= 2) {
-        const bool first2 = k.twolag == 2;
+    if (rho != nullptr && rho_mid != nullptr && lag_ema != nullptr && twolag_in >= 2) {
+        const bool first2 = twolag_in == 2;
         dmax = 0.0;
-        for (int d = 0; d < nrho; ++d) {
+        for (int d = lane; d < nrho; d += nl) {
             double ci = rho_mid[d];                          // corr(d1, d2) of this batch
             if (!(ci == ci)) ci = -0.5;                      // a coordinate that does not move at all carries no information
             const double e1 = first2 ? ci : (1.0 - a) * lag_ema[d] + a * ci;
@@ -250,7 +260,10 @@ __device__ __forceinline__ void adapt_nmcmc(NSState* st, int kind, int chains, c
             const double q = fmin(fmax(1.0 + 2.0 * e1, 0.0), 1.0);
             if (q * q > dmax) dmax = q * q;
         }
+        if (WARP)
+            for (int m = 16; m > 0; m >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, m));
     }
+    if (lane != 0) return;
     k.rho_decay = dmax;
     if (k.twolag > 0 && k.twolag < 1000) k.twolag += 1;
     if (!st->adapt) return;
@@ -720,15 +733,14 @@ __global__ void k_merge_commit(const MergeParams p) {
     }
 }
 
-// The chain-length controllers of the batch's sampler kinds (adapt_nmcmc: a serial pass over the D + 1 correlations of a
-// kind).  Its own launch on the stream of the chain statistics, beside the ranking kernels: in the merge kernel it was one
+// The chain-length controllers of the batch's sampler kinds (adapt_nmcmc: a pass over the D + 1 correlations of a kind).  Its own launch on the stream of the chain statistics, beside the ranking kernels: in the merge kernel it was one
 // thread's serial work on the main stream's critical path.
-__global__ void k_adapt_batch(const MergeParams p) {
+__global__ void k_adapt_batch(const MergeParams p) {      // one warp
     if (p.st->done) return;
     const int nrho = p.Dreal + 1;
     for (int kind = 0; kind < kNumKinds; ++kind)
         if (p.kind_n[kind] > 0)
-            adapt_nmcmc(p.st_w, kind, p.kind_n[kind], p.rho != nullptr ? p.rho + kind * nrho : nullptr,
+            adapt_nmcmc<true>(p.st_w, kind, p.kind_n[kind], p.rho != nullptr ? p.rho + kind * nrho : nullptr,
                         p.rho2_ema + kind * nrho, p.rho != nullptr ? nrho : 0,
                         (p.rho_mid != nullptr && kind == CPN_SAMPLER_MH) ? p.rho_mid + kind * nrho : nullptr,
                         p.lag_ema + 2 * kind * nrho, kind == CPN_SAMPLER_MH ? p.allow_twolag : 0);
