@@ -18,12 +18,12 @@ def _run(engine, drv, K, nb):
     return dict(logZ=s["logZ"], steps=s["total_steps"], evals=s["total_evals"], nmcmc=s["nmcmc"], it=s["iteration"], hash=h)
 
 
-def _make(rank, world, lanes=16, mix=None):
+def _make(rank, world, lanes=16, mix=None, two_lag=True):
     from cpnest_b200.engine import Engine
     from cpnest_b200.proposal import DefaultProposalCycle
     np.random.seed(5)
     e = Engine("gaussian_iid", [[-10, 10]] * 10, nlive=2000, maxmcmc=400, seed=5, device=rank, lanes=lanes,
-               rank=rank, world_size=world, mix=mix)
+               rank=rank, world_size=world, mix=mix, two_lag=two_lag)
     e.set_cycle(DefaultProposalCycle().device_cycle())
     e.init_prior()
     return e
@@ -39,7 +39,9 @@ def _worker(rank, world, port, comm, out, mix=None):
     from cpnest_b200.sharded import ShardedEngine
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    e = _make(rank, world, mix=mix)
+    # (the mid-chain snapshots of the two-lag chain-length control travel with the fused exchange only: a run over the NCCL
+    # record has the single-lag control, and is compared with a single-GPU run that has it too)
+    e = _make(rank, world, mix=mix, two_lag=(comm == "fused"))
     e.set_stream(stream.cuda_stream)
     drv = ShardedEngine(e, comm=comm)
     out[rank] = _run(e, drv, 256, 12)
@@ -54,7 +56,7 @@ def test_sharded_run_equals_single_gpu(comm):
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    e = _make(0, 1)
+    e = _make(0, 1, two_lag=(comm == "fused"))
     ref = _run(e, e, 256, 12)
     e.close()
     s = socket.socket()
