@@ -205,6 +205,12 @@ static int dalloc(T** p, size_t n) {
     return 0;
 }
 
+// Slices of the ensemble the moments are summed over: a function of nlive alone (the shape of the partial sums, and with it
+// every bit of the result, is the same on every rank and in every run); 32 up to nlive = 1e4, ~320 points per slice beyond
+// (at nlive = 8e4 the 32-slice covariance took longer than the chain kernel it runs beside, and the merge had to wait for it:
+// 0.25 ms on one batch in six)
+static int stat_blocks(int N) { return std::min(256, std::max(32, (N + 319) / 320)); }
+
 static const int kCfgs[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {4, 4},
 #ifdef CPN_EXP_G4E16
                                 {4, 16},
@@ -576,8 +582,8 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
         dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigscale[0], D) ||
         dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigscale[1], D) ||
         dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) ||
-        dalloc(&c->d_covbuf[0], (size_t)D * D) || dalloc(&c->d_covbuf[1], (size_t)D * D) || dalloc(&c->d_mean_partial, (size_t)kStatBlocks * D) ||
-        dalloc(&c->d_cov_partial, (size_t)kStatBlocks * D * D))
+        dalloc(&c->d_covbuf[0], (size_t)D * D) || dalloc(&c->d_covbuf[1], (size_t)D * D) || dalloc(&c->d_mean_partial, (size_t)stat_blocks(N) * D) ||
+        dalloc(&c->d_cov_partial, (size_t)stat_blocks(N) * D * D))
         return 1;
     if (dalloc(&c->d_state, 1) || dalloc(&c->d_trap_partial, 256) || dalloc(&c->d_scalar, 4) ||
         dalloc(&c->d_rec, (size_t)N * (D + 2)) || dalloc(&c->d_sweeps, 1))
@@ -747,6 +753,7 @@ static int sort_live(cpn_ctx* c) {
 // mean and covariance of the live ensemble (for eigen buffer `buf`) on stream `st`
 static int launch_moments(cpn_ctx* c, cudaStream_t st, int buf) {
     const int D = c->D, N = c->N;
+    const int kStatBlocks = stat_blocks(N);
     if (D > kStatThreads) return fail("ensemble statistics support dim <= %d", kStatThreads);
     k_mean_partial<<<kStatBlocks, kStatThreads, 0, st>>>(c->d_x, N, D, c->Dp, c->d_mean_partial);
     k_mean_final<<<(D + 127) / 128, 128, 0, st>>>(c->d_mean_partial, kStatBlocks, N, D, c->d_mean);
@@ -775,6 +782,9 @@ static int launch_eigen(cpn_ctx* c, cudaStream_t st, int buf, bool beside_chains
     // (warm start from the eigenvectors in use, the other buffer)
     k_jacobi_eigh<<<1, jt, use_smem ? sm : 0, st>>>(c->d_cov, c->d_covwork, use_smem, D, c->Dp,
                                                                (c->cfg.flags & CPN_COLD_EIGEN) ? nullptr : c->d_eigvec[buf ^ 1],
+                                                               // beside the chain kernels the block slows its SM's chain blocks for as long
+                                                               // as it runs (0.09 ms per batch it overlaps): five sweeps, one batch
+                                                               beside_chains ? 5 : 30,
                                                                c->d_eigval[buf], c->d_eigvec[buf], c->d_eigscale[buf], c->d_sweeps);
     CKL();
     if (beside_chains) CK(cudaEventRecord(c->ev_eig, st));
@@ -996,11 +1006,11 @@ static int launch_chain_corr(cpn_ctx* c, cudaStream_t cs, int kind, int j0, int 
     const size_t need = (size_t)(c->D + 2) * nseg * kCorrMom;
     if (need > c->corr_part_cap) return fail("chain statistics: %zu partial sums exceed the scratch of %zu", need, c->corr_part_cap);
     const bool mid = rho_mid != nullptr && kind == CPN_SAMPLER_MH;
-    k_chain_corr_partial<<<dim3(c->D + 2, nseg), kCorrThreads, 0, cs>>>(c->d_state, kind, j0, j1, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
+    k_chain_corr_partial<<<dim3((c->D + 1 + 31) / 32 + 1, nseg), kCorrThreads, 0, cs>>>(c->d_state, kind, j0, j1, c->D, c->Dp, c->d_new_start, c->d_x, c->d_logL,
                                                                       c->d_new_x, c->d_new_logL, mid ? c->d_mid_x : nullptr,
                                                                       mid ? c->d_mid_logL : nullptr, c->d_new_steps, c->d_new_acc,
                                                                       c->d_new_evals, c->d_corr_part);
-    k_chain_corr_final<<<(c->D + 2 + 127) / 128, 128, 0, cs>>>(c->d_state, kind, j1 - j0, c->D, nseg, c->d_corr_part, rho, rho_mid);
+    k_chain_corr_final<<<c->D + 2, 32, 0, cs>>>(c->d_state, kind, j1 - j0, c->D, nseg, c->d_corr_part, rho, rho_mid);
     c->launches += 2;
     return 0;
 }
@@ -1234,6 +1244,8 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
     MergeParams m;
     memset(&m, 0, sizeof m);
     m.st = c->d_state; m.st_w = c->d_state; m.N = c->N; m.K = K; m.Dp = c->Dp; m.Dreal = c->D;
+    m.dshift = 0;
+    while ((1 << m.dshift) < c->Dp) ++m.dshift;
     m.rho = c->staged_external ? nullptr : c->d_rho;
     m.rho2_ema = c->d_rho2;
     m.rho_mid = (m.rho != nullptr && twolag_ok) ? c->d_rho_mid : nullptr;
@@ -1294,7 +1306,7 @@ extern "C" int cpn_insert_batch(cpn_ctx* c, int32_t K) {
         CK(cudaStreamWaitEvent(c->stream, c->ev_cov, 0));
         c->wait_cov = false;
     }
-    k_merge_commit<<<(c->N + K * c->Dp + T - 1) / T, T, 0, c->stream>>>(m);
+    k_merge_commit<<<(int)(((long long)c->N + ((long long)K << m.dshift) + T - 1) / T), T, 0, c->stream>>>(m);
     CKL();
     c->cur ^= 1;
     c->launches += 1;

@@ -10,7 +10,7 @@
 
 namespace cpn {
 
-constexpr int kStatBlocks = 32;       // slices of the ensemble (fixed: the shape of the partial sums must not vary)
+// (the number of slices of the ensemble, i.e. of blocks of the partial kernels, is api.cu stat_blocks(nlive))
 constexpr int kStatThreads = 256;
 
 __global__ void __launch_bounds__(kStatThreads) k_mean_partial(const double* __restrict__ x, int n, int D, int Dp,
@@ -119,12 +119,15 @@ __global__ void k_cov_final(const double* __restrict__ partial, int nb, int n, i
 // rotations, A' = J^T A J is computed element-wise from the OLD matrix (every entry needs the four
 // entries at the crossing of its row pair and its column pair) into a second buffer, so a round costs
 // two block barriers.  A, A', V, V' live in shared memory with an odd leading dimension when they fit
-// (D <= 80), otherwise in global scratch.  On exit eigval is ascending (np.linalg.eigh order),
+// (D <= 80), otherwise in global scratch.  max_sweeps bounds the sweeps: V is a product of plane rotations and stays orthonormal
+// whatever their number, and the EnsembleEigenVector proposal is symmetric for ANY orthonormal basis and scales - an unconverged
+// decomposition costs proposal efficiency in proportion to what is left off the diagonal (relative 1e-5 after 5 sweeps from the
+// identity at D = 50), not correctness.  On exit eigval is ascending (np.linalg.eigh order),
 // eig_vec[i][0..D) = i-th eigenvector (a ROW here), eig_scale[i] = sqrt|eigval[i]| (proposal.py:339).
 constexpr int kJacobiThreads = 1024;
 
 __global__ void __launch_bounds__(kJacobiThreads) k_jacobi_eigh(const double* __restrict__ C, double* scratch, int use_smem,
-                                                                int D, int Dp, const double* __restrict__ prev_vec,
+                                                                int D, int Dp, const double* __restrict__ prev_vec, int max_sweeps,
                                                                 double* __restrict__ eigval,
                                                                 double* __restrict__ eig_vec, double* __restrict__ eig_scale,
                                                                 int* __restrict__ sweeps_out) {
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kJacobiThreads) k_jacobi_eigh(const double* __
     }
     __syncthreads();
     int sweep = 0;
-    for (; sweep < 30; ++sweep) {
+    for (; sweep < max_sweeps; ++sweep) {
         // convergence: off-diagonal Frobenius norm against the diagonal
         double off = 0.0, dia = 0.0;
         {

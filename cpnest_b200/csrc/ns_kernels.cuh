@@ -427,21 +427,27 @@ __global__ void k_adapt_hmc_dt(NSState* st) {
 // kCorrSeg chains (fixed-shape tree: deterministic), block row D+1 sums the batch counters; k_chain_corr_final adds the
 // segments in order and writes rho[d] and st->ctl[kind].batch[].  The grid grows with the batch, so the replicated
 // statistics of a multi-GPU batch (K = all ranks' chains) do not serialise on D+2 blocks.
-constexpr int kCorrSeg = 4 * kCorrThreads;
+constexpr int kCorrSeg = 512;          // chains per block of k_chain_corr_partial: 16 per warp (K = 37632: 74 segments x 3 block rows)
 constexpr int kCorrMom = 9;      // s, e, ss, ee, se and - two-lag control - m, mm, sm, me (m: the mid-chain snapshot)
 __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSState* st, int kind, int j0, int j1, int D, int Dp,
                                                                      const int* __restrict__ start_slot, const double* __restrict__ live_x,
                                                                      const double* __restrict__ live_logL, const double* __restrict__ new_x,
                                                                      const double* __restrict__ new_logL, const double* __restrict__ mid_x,
                                                                      const double* __restrict__ mid_logL, const int* steps, const int* acc,
-                                                                     const int* evals, double* __restrict__ part /*[D+2][nseg][8]*/) {
+                                                                     const int* evals, double* __restrict__ part /*[D+2][nseg][kCorrMom]*/) {
+    // grid (ceil((D + 1) / 32) + 1, nseg).  Block (ds, sg), ds below the last: the lanes of a warp are the 32 coordinates
+    // d = 32 ds + lane (d == D: logL), the 32 warps stride over the segment's chains - a chain's rows are read with
+    // consecutive lanes on consecutive doubles (one thread per chain and block per coordinate, as before, fetched a 32-byte
+    // sector per 8 useful bytes, and every row D + 1 times: 32 us at K = 37632).  The last block row sums the batch counters.
     if (st->done) return;
-    __shared__ double sh[kCorrMom][kCorrThreads / 32];
-    const int d = blockIdx.x, sg = blockIdx.y, nseg = gridDim.y, tid = threadIdx.x;
+    __shared__ double sh[32][33];
+    const int sg = blockIdx.y, nseg = gridDim.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a0 = j0 + sg * kCorrSeg, a1 = min(j1, a0 + kCorrSeg);
     const bool mid = mid_x != nullptr && st->ctl[kind].twolag >= 2;       // this batch's chains left snapshots
     double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (d == D + 1) {
+    const bool counters = (int)blockIdx.x == (int)gridDim.x - 1;
+    const int d = counters ? D + 1 : (int)blockIdx.x * 32 + lane;
+    if (counters) {
         // counters as doubles: exact up to 2^53
         for (int j = a0 + tid; j < a1; j += kCorrThreads) {
             a[0] += (double)steps[j];
@@ -449,12 +455,18 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSSta
             a[2] += (double)(evals != nullptr ? evals[j] : 0);
             a[3] += (acc[j] == 0) ? 1.0 : 0.0;
         }
-    } else {
+        // lanes hold different chains here: butterflies inside the warp first
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], m);
+    } else if (d <= D) {
         // shift by the first chain's values to keep the sums well conditioned
         const int s0 = start_slot[j0];
         const double cs = (d < D) ? live_x[(size_t)s0 * Dp + d] : live_logL[s0];
         const double ce = (d < D) ? new_x[(size_t)j0 * Dp + d] : new_logL[j0];
-        for (int j = a0 + tid; j < a1; j += kCorrThreads) {
+#pragma unroll 4
+        for (int j = a0 + warp; j < a1; j += 32) {
             const int sl = start_slot[j];
             const double s = ((d < D) ? live_x[(size_t)sl * Dp + d] : live_logL[sl]) - cs;
             const double e = ((d < D) ? new_x[(size_t)j * Dp + d] : new_logL[j]) - ce;
@@ -465,32 +477,37 @@ __global__ void __launch_bounds__(kCorrThreads) k_chain_corr_partial(const NSSta
             }
         }
     }
-    // fixed-shape reduction: butterflies inside a warp, then the 32 warp totals by the first warp
+    // fixed-shape reduction over the 32 warps, one moment at a time: lane l of warp 0 adds the 32 warp values of coordinate
+    // 32 ds + l in order (counters: every lane holds its warp's total, lane 0's column is used)
 #pragma unroll
     for (int k = 0; k < kCorrMom; ++k) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], m);
-        if ((tid & 31) == 0) sh[k][tid >> 5] = a[k];
-    }
-    __syncthreads();
-    if (tid < 32) {
-#pragma unroll
-        for (int k = 0; k < kCorrMom; ++k) {
-            double v = sh[k][tid];
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-            if (tid == 0) part[((size_t)d * nseg + sg) * kCorrMom + k] = v;
+        sh[warp][lane] = a[k];
+        __syncthreads();
+        if (warp == 0) {
+            double v = 0.0;
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) v += sh[w][lane];
+            if (counters ? (lane == 0 && k < 4) : (d <= D)) part[((size_t)d * nseg + sg) * kCorrMom + k] = v;
         }
+        __syncthreads();
     }
 }
-__global__ void k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg, const double* __restrict__ part, double* __restrict__ rho,
-                                   double* __restrict__ rho_mid) {
+// one warp per coordinate (block d): lane l adds the segments l, l + 32, ... in order, the 32 lane sums meet in a butterfly -
+// a fixed shape for a given number of segments, so the result is reproducible
+__global__ void __launch_bounds__(32) k_chain_corr_final(NSState* st, int kind, int n, int D, int nseg, const double* __restrict__ part,
+                                                         double* __restrict__ rho, double* __restrict__ rho_mid) {
     if (st->done) return;
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.x, lane = threadIdx.x;
     if (d > D + 1) return;
     double a[kCorrMom] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int sg = 0; sg < nseg; ++sg)
+    for (int sg = lane; sg < nseg; sg += 32)
+#pragma unroll
         for (int k = 0; k < kCorrMom; ++k) a[k] += part[((size_t)d * nseg + sg) * kCorrMom + k];
+#pragma unroll
+    for (int k = 0; k < kCorrMom; ++k)
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], m);
+    if (lane != 0) return;
     if (d == D + 1) {
         for (int k = 0; k < 4; ++k) st->ctl[kind].batch[k] = (unsigned long long)a[k];
         return;
@@ -645,6 +662,7 @@ struct MergeParams {
     const NSState* st;
     NSState* st_w;
     int N, K, Dp, Dreal;
+    int dshift;                // smallest shift with (1 << dshift) >= Dp
     const int* order_in;       // [N]
     const double* skeys_in;    // [N]
     int* order_out;
@@ -704,13 +722,14 @@ __global__ void k_merge_commit(const MergeParams p) {
     // k_ns_accumulate of this batch already advanced the counters
     const long long dead0 = p.st->iteration - K, ins0 = p.st->n_ins - K;
     if (i >= N) {
+        // row r, coordinate d of the replacements: 2^dshift >= Dp threads per row (no division per element)
         const int w = i - N;
-        if (w >= K * p.Dp) return;
-        const int r = w / p.Dp, d = w % p.Dp;
+        const int r = w >> p.dshift, d = w & ((1 << p.dshift) - 1);
+        if (r >= K || d >= p.Dp) return;
         const int slot = p.order_in[r];
         double* l = p.live_x + (size_t)slot * p.Dp + d;
         p.dead_x[(size_t)(dead0 + r) * p.Dp + d] = *l;
-        *l = p.new_x[w];
+        *l = p.new_x[(size_t)r * p.Dp + d];
         return;
     }
     if (i >= K) {

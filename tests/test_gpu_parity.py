@@ -252,6 +252,14 @@ def test_ensemble_covariance_and_eigen(golden):
                 assert rel_close(s * v[:, i], V[:, i], 1e-7, 1e-8), (D, i)
             # decomposition residual independent of LAPACK's conventions
             assert np.max(np.abs(cov @ v - v * w)) < 1e-12 * max(1.0, np.max(np.abs(w)))
+    # more than 32 slices of the ensemble (api.cu stat_blocks: ~320 points per slice beyond nlive = 1e4)
+    rs = np.random.RandomState(6)
+    X = rs.normal(size=(40123, 20)) @ rs.normal(size=(20, 20))
+    with Engine("gaussian_iid", [[-1e3, 1e3]] * 20, nlive=40123) as e:
+        e.set_live(np.concatenate((X, np.arange(40123.0)[:, None], np.zeros((40123, 1))), axis=1))
+        mean, cov, w, v = e.ensemble_stats()
+        assert rel_close(mean, X.mean(0), 1e-12, 1e-13)
+        assert rel_close(cov, np.cov(X.T), 1e-11, 1e-12)
     rs = np.random.RandomState(5)
     X = rs.normal(size=(4000, 50)) @ rs.normal(size=(50, 50))
     with Engine("gaussian_iid", [[-1e3, 1e3]] * 50, nlive=4000) as e:
