@@ -89,7 +89,7 @@ struct cpn_ctx {
     int* d_bucket;                  // ranking of the replacements: bucket histogram / starts [N+1], cursors [N+1], members [N]
     int* d_nle;                     // [N] #(survivors <= key) of every replacement
     double *d_start_x, *d_start_logL, *d_start_logP;
-    double *d_mean, *d_cov, *d_covwork, *d_V, *d_Vprev, *d_mean_partial, *d_cov_partial;
+    double *d_mean, *d_cov, *d_covwork, *d_mean_partial, *d_cov_partial;
     // eigen-directions are double buffered: chains read buffer eig_cur while a refresh, running on the
     // side stream concurrently with the chain kernel, writes the other one
     double *d_eigval[2], *d_eigvec[2], *d_eigscale[2], *d_eigmean[2], *d_covbuf[2];
@@ -578,7 +578,6 @@ static int create_impl(cpn_ctx* c, const cpn_config* cfg, const double* lo, cons
     if (dalloc(&c->d_corr_part, c->corr_part_cap)) return 1;
     if (dalloc(&c->d_start_x, (size_t)N * Dp) || dalloc(&c->d_start_logL, N) || dalloc(&c->d_start_logP, N)) return 1;
     if (dalloc(&c->d_mean, D) || dalloc(&c->d_cov, (size_t)D * D) || dalloc(&c->d_covwork, 4 * (size_t)D * (D | 1)) ||
-        dalloc(&c->d_V, (size_t)D * (D | 1)) || dalloc(&c->d_Vprev, (size_t)D * D) ||
         dalloc(&c->d_eigval[0], D) || dalloc(&c->d_eigscale[0], D) ||
         dalloc(&c->d_eigval[1], D) || dalloc(&c->d_eigscale[1], D) ||
         dalloc(&c->d_eigmean[0], D) || dalloc(&c->d_eigmean[1], D) ||
@@ -639,7 +638,7 @@ extern "C" void cpn_destroy(cpn_ctx* c) {
     if (c->acc_stream) cudaStreamSynchronize(c->acc_stream);
     void* ptrs[] = {c->d_lo, c->d_hi, c->d_blob, c->d_x, c->d_logL, c->d_logP, c->d_order[0], c->d_order[1],
                     c->d_skeys[0], c->d_skeys[1], c->d_sort_keys, c->d_sort_idx, c->d_stage_own, c->d_rho, c->d_rho2, c->d_rho_mid, c->d_lag_ema, c->d_rank, c->d_snew, c->d_bucket, c->d_nle, c->d_corr_part, c->d_start_x, c->d_start_logL,
-                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_V, c->d_Vprev, c->d_eigval[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigscale[1],
+                    c->d_start_logP, c->d_mean, c->d_cov, c->d_covwork, c->d_eigval[0], c->d_eigscale[0], c->d_eigval[1], c->d_eigscale[1],
                     c->d_mean_partial, c->d_cov_partial, c->d_cycle, c->d_slice_cycle, c->d_eigmean[0], c->d_eigmean[1], c->d_covbuf[0], c->d_covbuf[1], c->d_state, c->d_dead_x, c->d_dead_logL,
                     c->d_dead_logP, c->d_hist_logL, c->d_hist_logvol, c->d_ins, c->d_trap_partial, c->d_scalar, c->d_rec};
     for (void* p : ptrs)

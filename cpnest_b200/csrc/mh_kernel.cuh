@@ -60,8 +60,9 @@ struct MHParams : ChainParams {
 //   EnsembleStretch       a + (old - a) Z,  log_J = D x, Z = exp(x), x = uniform(-1,1) log 2                            proposal.py:253-260
 //   DifferentialEvolution old + (b - a) g, g ~ N(1, 1e-4)                                                               proposal.py:284-286
 //   EnsembleEigenVector   old + jump v_i, jump = sqrt|lambda_i| N(0,1)                                                   proposal.py:336-342
-// The kind of step t is the same for all chains of a launch (same cycle, same position), so the step branches on it
-// uniformly and gathers only the rows that kind needs (1.67 rows per step on average instead of 3).
+// The kind of step t is the same for all chains of a launch (same cycle, same position): it is read through the uniform
+// datapath (MHParams::cycw), the step branches on it uniformly and gathers only the rows that kind needs (1.67 rows per
+// step on average instead of 3).
 // Scalars c_j, Z, g are fp32 values (the reference rounds the scalar of every LivePoint product to fp32,
 // parameter.pyx:96-120); the EigenVector jump is fp64 (proposal.py:339-341 does not go through LivePoint.__mul__).
 // `thr` = log(u) - log_J: the prior MH test (sampler.py:337) reads dlogP > thr.
@@ -72,7 +73,8 @@ constexpr int kKindShift = 30;                         // ensemble sizes stay be
 constexpr uint32_t kIndexMask = (1u << kKindShift) - 1u;
 
 struct StepIn {
-    uint32_t i0, i1, i2;      // i0 carries the proposal kind in its two top bits (kKindShift)
+    uint32_t i0, i1, i2;      // rows to gather (EIGEN: i0 = eig_row0 + direction); chain-history instantiation: i0 carries the
+                              // proposal kind in its two top bits (kKindShift)
     uint32_t w3, w4, w5;      // WALK: c0, c1, c2 (fp32 bits); STRETCH: w3 = Z; DE: w3 = g; EIGEN: (w4, w5) = jump (fp64 bits)
     double thr;
 };
