@@ -378,3 +378,39 @@ def test_device_chain_length_rule_equals_estimate_nmcmc_on_the_fly():
             assert rel_close(s["nmcmc_exact"], ne, rtol=1e-12), (s["nmcmc_exact"], ne)
             assert s["nmcmc"] == n
         assert saw_immobile, "no chain without a move: the acc = 0 branch was not exercised"
+
+
+def test_chain_statistics_equal_the_correlations_of_the_recorded_chains():
+    """k_chain_corr_partial / _final + the controller's de-biased maximum (ns_kernels.cuh) against numpy: the chain history
+    records where every chain of a batch started, cpn_get_last_batch where it ended; corr(start, end) per coordinate and for
+    logL across the K chains, rho_max = sqrt(max_d(rho_d^2 - 1/K)) on the first batch (no moving average yet).  K = 1300 is
+    two full 512-chain segments and a ragged one; D + 1 = 41 coordinates are a full and a ragged group of 32 lanes."""
+    import ctypes as C
+    from cpnest_b200.engine import Engine
+    from cpnest_b200 import _lib as L
+    D, N, K = 40, 3000, 1300
+    m = O.builtin_model("gaussian40d")
+    # (maxmcmc far above the chain length: no chain is sent again from another start, which the log could not tell from a move)
+    with Engine(m.functor, m.bounds, nlive=N, maxmcmc=400, nmcmc_init=20, adapt_nmcmc=True, seed=21) as e:
+        e.set_cycle(O.make_cycle(np.random.RandomState(5)))
+        e.init_prior()
+        cap = 160
+        e.enable_chain_log(K, cap)
+        e.ns_step(K)
+        rows, steps, acc = e.last_batch(K)
+        start = np.empty((K, D + 1))
+        ev = np.empty((cap, D + 4))
+        n = C.c_int32(0)
+        for j in range(K):
+            L.check(e.lib.cpn_get_chain_log(e.h, j, L.dptr(ev), cap, C.byref(n)))
+            first = ev[0]
+            assert first[0] == 0 and first[1] == -1 and n.value >= 2          # (tag 0, step -1): the chain's start point
+            start[j, :D] = first[4:4 + D]
+            start[j, D] = first[2]
+        end = rows[:, :D + 1]
+        rho = np.array([np.corrcoef(start[:, d], end[:, d])[0, 1] for d in range(D + 1)])
+        expect = math.sqrt(max(np.max(rho ** 2 - 1.0 / K), 0.0))
+        s = e.state()
+        assert s["failed_chains"] == 0 and steps.max() < 400 and acc.min() > 0
+        assert rel_close(s["rho_max"], expect, 1e-9), (s["rho_max"], expect)
+        assert 0.0 < expect < 1.0
