@@ -121,6 +121,8 @@ SIGNATURES = {
                                    C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, _dp, _ip, _ip, _ip, _dp]),
     "cpn_trace_slice": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                   C.c_double, C.c_int32, C.c_uint64, _dp, _ip, _ip, _ip, _dp, _dp, C.c_int32]),
+    "cpn_trace_hmc": (C.c_int, [_vp, C.c_int32, _dp, _dp, _dp, _dp, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_uint64,
+                                _dp, _ip, _ip, _ip, _dp, C.c_int32]),
     "cpn_replay_hmc": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.c_double, _dp, _P(C.c_int64), C.c_double, C.c_int32, C.c_int32,
                                  C.c_double, C.c_int32, _dp, _ip, _ip, _ip, _dp]),
     "cpn_slice_directions": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_double, _dp]),

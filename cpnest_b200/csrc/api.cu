@@ -2282,6 +2282,83 @@ extern "C" int cpn_replay_hmc(cpn_ctx* c, int32_t C, const double* start, const 
     return 0;
 }
 
+extern "C" int cpn_trace_hmc(cpn_ctx* c, int32_t C, const double* start, const double* cov, const double* eigval,
+                             const double* eigvec, double dt, int32_t nmcmc, int32_t max_traj, double logLmin, int32_t lanes,
+                             uint64_t chain_base, double* out, int32_t* steps, int32_t* accepted, int32_t* evals, double* trace,
+                             int32_t trace_cap) {
+    if (!c || !start || !cov || !eigval || !eigvec || !out || !trace) return fail("null argument");
+    if (C < 1 || nmcmc < 1 || max_traj < 1 || trace_cap < c->D + 8) return fail("bad sizes");
+    if (c->cfg.functor == CPN_USER) return fail("cpn_trace_hmc is not available for a user functor");
+    CK(cudaSetDevice(c->cfg.device));
+    const int D = c->D, Dp = c->Dp;
+    std::vector<double> sx((size_t)C * Dp, 0.0), sl(C), sp(C), ev((size_t)D * Dp, 0.0), es(D, 0.0);
+    for (int i = 0; i < C; ++i) {
+        for (int d = 0; d < D; ++d) sx[(size_t)i * Dp + d] = start[(size_t)i * (D + 2) + d];
+        sl[i] = start[(size_t)i * (D + 2) + D];
+        sp[i] = start[(size_t)i * (D + 2) + D + 1];
+    }
+    for (int i = 0; i < D; ++i) {
+        es[i] = sqrt(fabs(eigval[i]));
+        for (int k = 0; k < D; ++k) ev[(size_t)i * Dp + k] = eigvec[(size_t)k * D + i];       // numpy layout: column i = eigenvector i
+    }
+    const size_t ntrace = (size_t)C * trace_cap;
+    double *dsx = nullptr, *dsl = nullptr, *dsp = nullptr, *dcov = nullptr, *des = nullptr, *dvec = nullptr, *dox = nullptr, *dol = nullptr,
+           *dop = nullptr, *dtr = nullptr;
+    int *dst = nullptr, *dac = nullptr, *dev = nullptr;
+    int rc = 1;
+    do {
+        if (dalloc(&dsx, sx.size()) || dalloc(&dsl, C) || dalloc(&dsp, C) || dalloc(&dcov, (size_t)D * D) || dalloc(&des, D) ||
+            dalloc(&dvec, ev.size()) || dalloc(&dox, (size_t)C * Dp) || dalloc(&dol, C) || dalloc(&dop, C) || dalloc(&dst, C) ||
+            dalloc(&dac, C) || dalloc(&dev, C) || dalloc(&dtr, ntrace))
+            break;
+        if (h2d_sync(dsx, sx.data(), sx.size() * sizeof(double)) != cudaSuccess || h2d_sync(dsl, sl.data(), C * sizeof(double)) != cudaSuccess ||
+            h2d_sync(dsp, sp.data(), C * sizeof(double)) != cudaSuccess || h2d_sync(dcov, cov, (size_t)D * D * sizeof(double)) != cudaSuccess ||
+            h2d_sync(des, es.data(), D * sizeof(double)) != cudaSuccess || h2d_sync(dvec, ev.data(), ev.size() * sizeof(double)) != cudaSuccess) {
+            fail("cpn_trace_hmc: host to device copy failed");
+            break;
+        }
+        HMCParams p;
+        memset(&p, 0, sizeof p);
+        p.ens_n = 0; p.Dp = Dp; p.D = D;
+        p.start_mode = START_GIVEN; p.start_x = dsx; p.start_logL = dsl; p.start_logP = dsp;
+        p.lo = c->d_lo; p.hi = c->d_hi;
+        p.cov = dcov; p.eig_scale = des; p.eig_vec = dvec;
+        p.state = nullptr; p.use_override = 1; p.logLmin_override = logLmin; p.dt_override = dt; p.L_override = 0;
+        p.nmcmc_override = nmcmc; p.base_L = c->hmc_base_L;
+        p.max_traj = max_traj; p.j0 = 0; p.j1 = C; p.blob = c->d_blob;
+        p.chain_base = chain_base;
+        p.seed_lo = (uint32_t)c->cfg.seed; p.seed_hi = (uint32_t)(c->cfg.seed >> 32);
+        p.n_out = 1; p.out_x[0] = dox; p.out_logL[0] = dol; p.out_logP[0] = dop; p.out_steps[0] = dst; p.out_acc[0] = dac;
+        p.out_evals[0] = dev;
+        p.trace = dtr; p.trace_cap = trace_cap;
+        int G, E;
+        if (pick_config(D, lanes > 0 ? lanes : c->cfg.lanes, c->cfg.functor, C, &G, &E)) break;
+        if (run_hmc(c, G, E, 0, p)) break;
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { fail("cpn_trace_hmc: launch failed"); break; }
+        std::vector<double> ox((size_t)C * Dp), ol(C), op(C);
+        if (cudaMemcpy(ox.data(), dox, ox.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(ol.data(), dol, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(op.data(), dop, C * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(trace, dtr, ntrace * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            (steps && cudaMemcpy(steps, dst, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (accepted && cudaMemcpy(accepted, dac, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            (evals && cudaMemcpy(evals, dev, C * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)) {
+            fail("cpn_trace_hmc: device to host copy failed");
+            break;
+        }
+        for (int i = 0; i < C; ++i) {
+            for (int d = 0; d < D; ++d) out[(size_t)i * (D + 2) + d] = ox[(size_t)i * Dp + d];
+            out[(size_t)i * (D + 2) + D] = ol[i];
+            out[(size_t)i * (D + 2) + D + 1] = op[i];
+        }
+        rc = 0;
+    } while (0);
+    void* fr[] = {dsx, dsl, dsp, dcov, des, dvec, dox, dol, dop, dst, dac, dev, dtr};
+    for (void* q : fr)
+        if (q) cudaFree(q);
+    return rc;
+}
+
 extern "C" int cpn_slice_directions(cpn_ctx* c, int32_t direction, int32_t C, double mu, double* out) {
     if (!c || !out) return fail("null argument");
     if (!c->live_ready) return fail("live set not initialised");

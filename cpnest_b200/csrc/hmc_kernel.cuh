@@ -53,6 +53,11 @@ struct HMCParams : ChainParams {        // nmcmc = trajectories per chain (1 in 
     const long long* tape_off;
     double* traj;             // replay scratch [chains][2L+1][Dp + 3] = {q.., logL, logP, H}
     double* logJ_out;         // [chains] log_J of the last trajectory, or null
+    // production, test entry (cpn_trace_hmc): what every trajectory of every chain consumed besides the chain state:
+    // trace[c][trace_cap] = { n, then per trajectory: L, p0[D], the uniforms of the weighted draw for the points 1 .. 2L-1
+    // in the order they are visited, the uniform of the acceptance test }, n = doubles written after the first (-1: too small)
+    double* trace;
+    int trace_cap;
 };
 
 template <int G, int E, class Model, bool REPLAY>
@@ -114,6 +119,8 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
     const double* tp = REPLAY ? p.tape + p.tape_off[c] : nullptr;
     const int npts = 2 * Lmax + 1;
     double* traj = REPLAY ? p.traj + (size_t)c * npts * (p.Dp + 3) : nullptr;
+    double* tr = (!REPLAY && p.trace != nullptr && valid) ? p.trace + (size_t)c * p.trace_cap : nullptr;
+    int ti = 1;                   // next free double of the chain's trace area
 
     for (int attempt = 0; attempt < p.max_traj; ++attempt) {
         if (!__any_sync(FULL, active)) break;
@@ -154,6 +161,24 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
                     const int d = g.lane + e * G;
                     p0[e] = fma(zi, (d < D) ? __ldg(vrow + d) : 0.0, p0[e]);
                 }
+            }
+        }
+        bool rec = false;             // this trajectory of this chain is recorded
+        int ti_u = 0;                 // where its uniforms start
+        if (!REPLAY && tr != nullptr && active) {
+            if (ti + D + 2 * L + 2 > p.trace_cap) {
+                if (g.lane == 0) tr[0] = -1.0;
+                tr = nullptr;
+            } else {
+                rec = true;
+                if (g.lane == 0) tr[ti] = (double)L;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int d = g.lane + e * G;
+                    if (d < D) tr[ti + 1 + d] = p0[e];
+                }
+                ti_u = ti + 1 + D;
+                ti = ti_u + (2 * L - 1) + 1;
             }
         }
         const double E0 = kinetic(p0) - logP;                           // hamiltonian(p0, q0), :621
@@ -268,6 +293,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
                     const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 0x40000000u | (uint32_t)(point >> 2), p.seed_lo, p.seed_hi);
                     const int k = point & 3;
                     const uint32_t wv = (k & 2) ? ((k & 1) ? ru.v[3] : ru.v[2]) : ((k & 1) ? ru.v[1] : ru.v[0]);
+                    if (rec && g.lane == 0) tr[ti_u + point - 1] = u32_to_unit_open(wv);
                     const double lw = -H;
                     const double hi2 = fmax(logW, lw), lo2 = fmin(logW, lw);
                     const double logWn = (hi2 > CPN_NEG_INF) ? hi2 + log1p(exp(lo2 - hi2)) : CPN_NEG_INF;
@@ -314,6 +340,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
         } else {
             const Philox4 ra = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 1u, p.seed_lo, p.seed_hi);
             u_acc = u32_to_unit_open(ra.v[0]);
+            if (rec && g.lane == 0) tr[ti_u + 2 * L - 1] = u_acc;
         }
         const double log_J = fmin(0.0, E0 - Hc);                         // :626
         const bool acc = active && (log_J > log(u_acc)) && (logLc > logLmin);   // sampler.py:380-382
@@ -331,6 +358,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
     }
 
     ch.finish(p, steps, accepted, evals, 0, 0);
+    if (tr != nullptr && g.lane == 0) tr[0] = (double)(ti - 1);
     if (valid) {
         if (p.logJ_out != nullptr && g.lane == 0) p.logJ_out[c] = last_logJ;
     }

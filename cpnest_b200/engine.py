@@ -481,6 +481,35 @@ class Engine:
             kinds.append(kd)
         return out, steps, acc, evals, last, tapes, kinds
 
+    def trace_hmc(self, start, cov, eigval, eigvec, dt, nmcmc, max_traj, logLmin, lanes=0, chain_base=0, trace_cap=8192):
+        """The production HMC kernel on given chains (include/cpnest_b200.h cpn_trace_hmc).  Returns (out, steps, accepted, evals,
+        trajectories): trajectories[c] = list of dict(L, p0, u (the 2L-1 uniforms of the weighted draw), u_acc)."""
+        start = L_.f64(start).reshape(-1, self.dim + 2)
+        Cn, D = start.shape[0], self.dim
+        cov = L_.f64(cov).reshape(D, D)
+        eigval, eigvec = L_.f64(eigval), L_.f64(np.asarray(eigvec).reshape(D, D))
+        out = np.empty((Cn, D + 2))
+        steps = np.empty(Cn, dtype=np.int32)
+        acc = np.empty(Cn, dtype=np.int32)
+        evals = np.empty(Cn, dtype=np.int32)
+        trace = np.zeros((Cn, int(trace_cap)))
+        L_.check(self.lib.cpn_trace_hmc(self.h, Cn, L_.dptr(start), L_.dptr(cov), L_.dptr(eigval), L_.dptr(eigvec), float(dt), int(nmcmc),
+                                        int(max_traj), float(logLmin), int(lanes), int(chain_base), L_.dptr(out), L_.iptr(steps),
+                                        L_.iptr(acc), L_.iptr(evals), L_.dptr(trace), int(trace_cap)))
+        trajs = []
+        for c in range(Cn):
+            t = trace[c]
+            n = int(t[0])
+            if n < 0:
+                raise RuntimeError("trace_hmc: trace_cap %d too small" % trace_cap)
+            lst, i = [], 1
+            while i < 1 + n:
+                Lt = int(t[i])
+                lst.append(dict(L=Lt, p0=t[i + 1:i + 1 + D].copy(), u=t[i + 1 + D:i + D + 2 * Lt].copy(), u_acc=float(t[i + D + 2 * Lt])))
+                i += D + 2 * Lt + 1
+            trajs.append(lst)
+        return out, steps, acc, evals, trajs
+
     def replay_hmc(self, start, cov, logdet, tapes, dt, L, logLmin, max_traj=1000, lanes=0):
         """HMC chains from explicit tapes (include/cpnest_b200.h cpn_replay_hmc).
         Returns (out, steps, accepted, evals, log_J)."""

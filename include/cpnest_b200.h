@@ -329,6 +329,19 @@ int cpn_replay_hmc(cpn_ctx* ctx, int32_t C, const double* start /*[C][D+2]*/, co
                    const double* tape, const int64_t* tape_off, double dt, int32_t L, int32_t max_traj,
                    double logLmin, int32_t lanes, double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted,
                    int32_t* evals, double* log_J /*[C]*/);
+/* The PRODUCTION HMC kernel (the instantiation every run launches: Philox draws, momenta through the eigen-decomposition of
+ * the covariance, analytic reflection normals, reflection in the metric of the kinetic energy, one-pass weighted draw of the
+ * trajectory point, nmcmc trajectories per chain - hmc_kernel.cuh header) on given chains, recording what every trajectory
+ * consumed besides the chain state: trace[c][trace_cap] = { n, then per trajectory: L, p0[D], the uniforms of the weighted
+ * draw for the points 1 .. 2L-1 in the order they are visited, the uniform of the acceptance test }, n = doubles written
+ * after the first (-1: trace_cap was too small).  A restatement of the kernel's trajectory on those inputs must reproduce the
+ * chain: the step-level test of the production path (it differs from the reference's HamiltonianMonteCarloSampler by design,
+ * so the restatement is of THIS algorithm, built on the reference's leapfrog, cpnest/proposal.py:714-835).
+ * cov[D][D], eigval[D], eigvec[D][D] (numpy layout): the ensemble covariance and its eigen-decomposition. */
+int cpn_trace_hmc(cpn_ctx* ctx, int32_t C, const double* start /*[C][D+2]*/, const double* cov, const double* eigval,
+                  const double* eigvec, double dt, int32_t nmcmc, int32_t max_traj, double logLmin, int32_t lanes,
+                  uint64_t chain_base, double* out /*[C][D+2]*/, int32_t* steps, int32_t* accepted, int32_t* evals,
+                  double* trace /*[C][trace_cap]*/, int32_t trace_cap);
 /* Directions of the production slice kernel for chains [0, C) of the next batch's first slice, all of kind
  * `direction` (test entry: distribution of the three direction proposals, cpnest/proposal.py:121-187). */
 int cpn_slice_directions(cpn_ctx* ctx, int32_t direction, int32_t C, double mu, double* out /*[C][D]*/);

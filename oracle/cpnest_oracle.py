@@ -560,6 +560,109 @@ def hmc_chain(model, grad_V, start, start_logL, start_logP, C, inverse_mass, log
             return dict(out=q0, logL=start_logL, logP=start_logP, steps=steps, log_J=log_J, evals=2 * L * steps)
 
 
+def hmc_production_chain(model, grad_logL, grad_V, flat_prior, start, start_logL, start_logP, C, dt, logLmin, trajectories,
+                         nmcmc, max_traj):
+    """The PRODUCTION HMC kernel's chain (cpnest_b200/csrc/hmc_kernel.cuh) on recorded inputs.  It is the reference's
+    constrained leapfrog (position step with reflection off the bounds, proposal.py:729-741; momentum step :760-773; the two
+    half trajectories of evolve_trajectory, :793-835; energies and log_J of get_sample, :605-627) with the stated differences:
+    the reflection normal is the analytic gradient of log_likelihood (the reference fits splines, :417-486); the reflection is
+    p -= 2 (n.C.p / n.C.n) n, in the metric of the kinetic energy (:769-771 uses the Euclidean one); the trajectory point is
+    drawn in one pass by weighted reservoir sampling with weights exp(-H) over the points 1 .. 2L-1 (same distribution as the
+    multinomial draw of sample_trajectory, :837-844); the kinetic energy is re-evaluated only after the momentum can have
+    changed it (first point, a bound reflection, a non-flat prior); a chain runs trajectories until steps >= nmcmc and one was
+    accepted (the MH rule, sampler.py:347; the reference stops at the first accepted one, :375).
+    trajectories: list of dict(L, p0, u, u_acc) as cpn_trace_hmc records them.  Returns dict(out, logL, logP, steps, accepted, evals)."""
+    lo, hi = model.lo, model.hi
+    D = len(start)
+    C = np.asarray(C, dtype=np.float64)
+    imass = np.diag(C).copy()                                             # inverse_mass = diag(covariance), :519
+    x = np.array(start, dtype=np.float64)
+    logL, logP = float(start_logL), float(start_logP)
+    steps = accepted = evals = reflections = 0
+    neg_inf = -np.inf
+    for tr in trajectories:
+        L, p0, us, u_acc = int(tr["L"]), np.array(tr["p0"], dtype=np.float64), list(tr["u"]), float(tr["u_acc"])
+        E0 = 0.5 * float(p0 @ (C @ p0)) - logP                            # hamiltonian(p0, q0), :621
+        logW = neg_inf
+        qc, logLc, logPc, Hc = x.copy(), neg_inf, neg_inf, 0.0
+        point = 0
+        for sign in (1.0, -1.0):
+            pm = sign * p0
+            q = x.copy()
+            pm = pm + (-0.5 * dt) * grad_V(q)                             # half step, :757-759
+            T, dirty = 0.0, True
+            for i in range(L):
+                point += 1
+                flipped = False
+                for j in range(D):                                        # :729-741
+                    q[j] += dt * pm[j] * imass[j]
+                    while q[j] < lo[j] or q[j] > hi[j]:
+                        if q[j] > hi[j]:
+                            q[j] = hi[j] - (q[j] - hi[j]); pm[j] *= -1; flipped = True
+                        if q[j] < lo[j]:
+                            q[j] = lo[j] + (lo[j] - q[j]); pm[j] *= -1; flipped = True
+                lp = model.log_prior(q) if model.in_bounds(q) else neg_inf
+                ll = model.log_likelihood(q)
+                evals += 1
+                gv = grad_V(q)
+                if ll - logLmin > 0:                                      # :764-766
+                    pm = pm + (-dt) * gv
+                else:
+                    n = np.array(grad_logL(q), dtype=np.float64)
+                    n2 = float(n @ n)
+                    n = n * (1.0 / math.sqrt(n2)) if n2 > 0 else n * 0.0
+                    cn = C @ n
+                    ncn = float(cn @ n)
+                    pn = float(cn @ pm) / ncn if ncn > 0 else 0.0
+                    pm = pm + (-2.0 * pn) * n
+                    reflections += 1
+                dirty = dirty or (not flat_prior) or flipped
+                if dirty:
+                    T = 0.5 * float(pm @ (C @ pm))
+                    dirty = False
+                H = T - lp
+                if not (sign < 0 and i == L - 1):                         # trajectory[1:-1], :841
+                    u = us[point - 1]
+                    lw = -H
+                    hi2, lo2 = max(logW, lw), min(logW, lw)
+                    logWn = hi2 + math.log1p(math.exp(lo2 - hi2)) if hi2 > neg_inf else neg_inf
+                    if lw > neg_inf and math.log(u) < lw - logWn:
+                        qc, logLc, logPc, Hc = q.copy(), ll, lp, H
+                    logW = logWn
+        log_J = min(0.0, E0 - Hc)                                         # :626
+        acc = (log_J > math.log(u_acc)) and (logLc > logLmin)             # sampler.py:380-382
+        if acc:
+            x, logL, logP = qc, logLc, logPc
+        steps += 1
+        accepted += 1 if acc else 0
+        if (steps >= nmcmc and accepted > 0) or steps >= max_traj:
+            break
+    return dict(out=x, logL=logL, logP=logP, steps=steps, accepted=accepted, evals=evals, reflections=reflections)
+
+
+def production_hmc_draw(seed, chain_id, attempt, D, base_L, eig_scale, eigen_vectors):
+    """hmc_kernel.cuh, production branch: what trajectory number `attempt` of chain `chain_id` draws from the Philox stream:
+    L = base_L + 10 + index(v0 of block 2, 40) (cf. proposal.py:553-559; chains sharing a warp use the first chain's),
+    p0 = sum_i z_i |lambda_i|^-1/2 v_i with z_d = the first fp32 Box-Muller Gaussian of block 0x80000000 | d (momenta ~ N(0, M),
+    M = C^-1, proposal.py:516-522, 620), u_acc = u(v0 of block 1); the uniform of point k of the weighted draw is word k & 3 of
+    block 0x40000000 | (k >> 2).  Returns (L, p0, u_acc, uniform_of_point)."""
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    clo, chi = chain_id & 0xFFFFFFFF, (chain_id >> 32) & 0xFFFFFFFF
+    L = base_L + 10 + u32_to_index(philox4x32_10((clo, chi, attempt, 2), key)[0], 40)
+    z = np.zeros(D)
+    for d in range(D):
+        q = philox4x32_10((clo, chi, attempt, 0x80000000 | d), key)
+        z[d] = box_muller_f32(q[0], q[1])[0] / eig_scale[d] if eig_scale[d] > 0 else 0.0
+    p0 = np.zeros(D)
+    for i in range(D):
+        p0 = p0 + z[i] * np.asarray(eigen_vectors)[:, i]
+    u_acc = u32_to_unit_open(philox4x32_10((clo, chi, attempt, 1), key)[0])
+
+    def uniform_of_point(k):
+        return u32_to_unit_open(philox4x32_10((clo, chi, attempt, 0x40000000 | (k >> 2)), key)[k & 3])
+    return L, p0, u_acc, uniform_of_point
+
+
 def hmc_update_time_step(scale, acceptance, base_dt, target=0.5, adaptation=0.001):
     """proposal.py:539-550 -> (scale, dt)"""
     scale = float(np.exp(np.log(scale) + adaptation * (acceptance - target)))

@@ -226,3 +226,49 @@ def _starts_slice(ev, i, kinds, s):
     if s + 1 >= len(kinds) or i + 1 >= len(ev):
         return False
     return ev[i + 1][0] in ("sample", "np_normal", "np_mvn")
+
+
+# ---- the production HMC kernel -----------------------------------------------------------------------------------------------
+# cpn_trace_hmc runs k_hmc_chains<G, E, Model, REPLAY=false> and records what every trajectory consumed (length, momentum, the
+# uniforms of the weighted draw and of the acceptance test).  The production algorithm differs from the reference's sampler by
+# design (hmc_kernel.cuh header), so (b) is a restatement of THIS algorithm on the reference's leapfrog
+# (oracle.hmc_production_chain); (a) the recorded inputs follow from the Philox stream (oracle.production_hmc_draw).
+@pytest.mark.parametrize("name,lanes,spread", [("gaussian2d", 1, 0.3), ("gaussian10d", 4, 0.2), ("gaussian10d", 8, 0.2),
+                                               ("gaussian10d", 32, 0.2), ("gaussian50d", 16, 0.15)])
+def test_production_hmc_chain_equals_its_restatement_trajectory_by_trajectory(name, lanes, spread):
+    from cpnest_b200.engine import Engine
+    m = O.builtin_model(name)
+    D = m.D
+    rs = np.random.RandomState(70 + lanes)
+    P, C, nmcmc, max_traj, chain_base, seed = 4 * D + 24, 6, 3, 12, 555, 1234
+    ens, start, logLmin, _, _ = _setup(m, P, C, rs, spread)
+    cov = np.cov(ens.T).reshape(D, D)
+    w, v = np.linalg.eigh(cov)
+    base_L, base_dt = O.hmc_set_integration_parameters(m.bounds)
+    dt = 3.0 * base_dt
+    with Engine(m.functor, m.bounds, nlive=64, maxmcmc=max_traj, seed=seed, sampler="hmc") as e:
+        out, steps, acc, evals, trajs = e.trace_hmc(start, cov, w, v, dt, nmcmc, max_traj, logLmin, lanes=lanes, chain_base=chain_base)
+    grad_logL = lambda q: -np.asarray(q)                     # unit Gaussian centred at 0 (examples/test_50d.py)
+    grad_V = lambda q: np.zeros(D)                           # flat prior
+    scale = np.sqrt(np.abs(w))
+    cpw = max(1, 32 // lanes)                                # chains per warp: they share the first chain's trajectory length
+    moved = reflected = 0
+    for c in range(C):
+        r = O.hmc_production_chain(m, grad_logL, grad_V, True, start[c, :D], start[c, D], start[c, D + 1], cov, dt, logLmin, trajs[c],
+                                   nmcmc, max_traj)
+        assert (steps[c], acc[c], evals[c]) == (r["steps"], r["accepted"], r["evals"]), (name, lanes, c, steps[c], acc[c], evals[c], r)
+        np.testing.assert_allclose(out[c, :D], r["out"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(out[c, D], r["logL"], rtol=1e-9)
+        np.testing.assert_allclose(out[c, D + 1], r["logP"], rtol=1e-9, atol=1e-300)
+        moved += r["accepted"]
+        reflected += r["reflections"]
+        assert len(trajs[c]) == r["steps"]
+        for a, tr in enumerate(trajs[c]):
+            L, p0, u_acc, u_of = O.production_hmc_draw(seed, chain_base + c, a, D, base_L, scale, v)
+            L_warp = O.production_hmc_draw(seed, chain_base + (c // cpw) * cpw, a, D, base_L, scale, v)[0]
+            assert tr["L"] == L_warp and len(tr["u"]) == 2 * tr["L"] - 1
+            np.testing.assert_allclose(tr["p0"], p0, rtol=3e-5, atol=3e-5 * float(np.max(1.0 / scale)))
+            assert tr["u_acc"] == u_acc
+            assert all(tr["u"][k - 1] == u_of(k) for k in (1, 2, 5, 2 * tr["L"] - 1))
+    assert moved > 0
+    assert reflected > 0 or D < 10, "no trajectory met the likelihood boundary: the reflection was not exercised"
