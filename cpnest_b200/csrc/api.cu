@@ -270,7 +270,7 @@ static int user_launch(cpn_ctx* c, const char* kind, int G, int E, const void* p
     if (n <= 0) return 0;
     const int cpb = threads / G;
     const int nb = (n + cpb - 1) / cpb;
-    const size_t sm = (size_t)cpb * kScratchRows * Dp * sizeof(double);
+    const size_t sm = (size_t)cpb * (kScratchRows + 1) * Dp * sizeof(double);     // functor scratch + the HMC kernel's mat-vec row
     char err[4096];
     if (rtc_launch(c->rtc, kind, G, E, params, nb, threads, sm, chain_stream(c), err, sizeof err)) return fail("%s", err);
     return 0;

@@ -61,7 +61,7 @@ struct HMCParams : ChainParams {        // nmcmc = trajectories per chain (1 in 
 };
 
 template <int G, int E, class Model, bool REPLAY>
-__global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
+__global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_hmc_chains(const HMCParams p) {
     extern __shared__ double smem[];
     Chain<G, E, Model> ch;
     if (!ch.begin(p, smem, REPLAY)) return;
@@ -87,11 +87,24 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
 
     // 0.5 p.C.p (+ the constants of proposal.py:575 in replay, where they enter exp(logw - norm) rounding)
     const double tconst = REPLAY ? (-p.logdet - 0.5 * (double)D * 1.8378770664093454836) : 0.0;
-    auto matvec = [&](const double (&pp)[E], double (&w)[E]) {          // w = C pp (this lane's coordinates)
+    // w = C pp (this lane's coordinates).  Production: the vector is exchanged through the chain's row of shared memory (one
+    // broadcast load per column; the shuffle form - a select over the lane's slots and a 64-bit shuffle per column - was the
+    // bulk of a reflecting step).  Same multiply-adds in the same order in both forms.
+    double* hsm = smem + (Model::kScratch ? (kMHThreads / G) * kScratchRows * p.Dp : 0) + ((int)threadIdx.x / G) * p.Dp;
+    auto matvec = [&](const double (&pp)[E], double (&w)[E]) {
 #pragma unroll
         for (int e = 0; e < E; ++e) w[e] = 0.0;
+        if (!REPLAY && G > 1) {
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = g.lane + e * G;
+                if (d < D) hsm[d] = pp[e];
+            }
+            __syncwarp();
+        }
         for (int k = 0; k < D; ++k) {
-            const double pk = coord<G, E>(g, pp, k);
+            const double pk = (!REPLAY && G > 1) ? hsm[k] : coord<G, E>(g, pp, k);
             const double* crow = p.cov + (size_t)k * D;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
         const double E0 = kinetic(p0) - logP;                           // hamiltonian(p0, q0), :621
 
         // ---- the two half trajectories + the weighted draw ----------------------------------------------
-        double logW = CPN_NEG_INF;                                      // production: running log sum of weights
+        double Wsum = 0.0, Href = 0.0, Hprev = 0.0, wprev = 0.0;        // production: running sum of the weights exp(Href - H)
         double qc[E], logLc = CPN_NEG_INF, logPc = CPN_NEG_INF, Hc = 0.0;
 #pragma unroll
         for (int e = 0; e < E; ++e) qc[e] = x[e];
@@ -201,13 +214,22 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
             for (int i = 0; i < L; ++i) {
                 ++point;
                 // position step with reflection off the prior bounds, :729-741
-                bool flipped = false;
+                bool flipped = false, outside = false;
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     q[e] = add(q[e], mul(mul(dt, pm[e]), imass[e]));
-                    for (int guard = 0; guard < 64 && (q[e] < blo[e] || q[e] > bhi[e]); ++guard) {
-                        if (q[e] > bhi[e]) { q[e] = bhi[e] - (q[e] - bhi[e]); pm[e] *= -1.0; flipped = true; }
-                        if (q[e] < blo[e]) { q[e] = blo[e] + (blo[e] - q[e]); pm[e] *= -1.0; flipped = true; }
+                    outside = outside | (q[e] < blo[e]) | (q[e] > bhi[e]);
+                }
+                // the reflection loop of :733-741 runs only when some coordinate of some chain of the warp left the box, and
+                // as a loop: unrolled and predicated (64 rounds x E coordinates) it was 5 of every 6 instructions of a step
+                if (__any_sync(FULL, outside)) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+#pragma unroll 1
+                        for (int guard = 0; guard < 64 && (q[e] < blo[e] || q[e] > bhi[e]); ++guard) {
+                            if (q[e] > bhi[e]) { q[e] = bhi[e] - (q[e] - bhi[e]); pm[e] *= -1.0; flipped = true; }
+                            if (q[e] < blo[e]) { q[e] = blo[e] + (blo[e] - q[e]); pm[e] *= -1.0; flipped = true; }
+                        }
                     }
                 }
                 // momentum step, :760-773
@@ -293,12 +315,24 @@ __global__ void __launch_bounds__(kMHThreads) k_hmc_chains(const HMCParams p) {
                     const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 0x40000000u | (uint32_t)(point >> 2), p.seed_lo, p.seed_hi);
                     const int k = point & 3;
                     const uint32_t wv = (k & 2) ? ((k & 1) ? ru.v[3] : ru.v[2]) : ((k & 1) ? ru.v[1] : ru.v[0]);
-                    if (rec && g.lane == 0) tr[ti_u + point - 1] = u32_to_unit_open(wv);
-                    const double lw = -H;
-                    const double hi2 = fmax(logW, lw), lo2 = fmin(logW, lw);
-                    const double logWn = (hi2 > CPN_NEG_INF) ? hi2 + log1p(exp(lo2 - hi2)) : CPN_NEG_INF;
-                    const bool take = (lw > CPN_NEG_INF) && (log(u32_to_unit_open(wv)) < lw - logWn);
-                    logW = logWn;
+                    const double uu = u32_to_unit_open(wv);
+                    if (rec && g.lane == 0) tr[ti_u + point - 1] = uu;
+                    // weights exp(-H) relative to a reference energy, summed in the linear domain: under a flat prior H is
+                    // constant along the trajectory and a point costs an add, a multiply and a compare (the log-domain form
+                    // took a log1p, an exp and a log in fp64 per point).  The reference energy follows H downwards.
+                    bool take = false;
+                    if (H < -CPN_NEG_INF) {                              // a point outside the box has weight 0
+                        double wgt;
+                        if (!(Wsum > 0.0)) { Href = H; wgt = 1.0; }
+                        else if (H == Hprev) wgt = wprev;
+                        else {
+                            if (H < Href - 50.0) { Wsum *= exp(H - Href); Href = H; }
+                            wgt = exp(Href - H);
+                        }
+                        Hprev = H; wprev = wgt;
+                        Wsum += wgt;
+                        take = uu * Wsum < wgt;
+                    }
 #pragma unroll
                     for (int e = 0; e < E; ++e) qc[e] = take ? q[e] : qc[e];
                     logLc = take ? ll : logLc;

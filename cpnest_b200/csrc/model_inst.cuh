@@ -64,7 +64,8 @@ static int launch_hmc_model(int G, int E, int replay, const HMCParams& p, cudaSt
     if (G == GG && E == EE) {                                                                         \
         const int cpb = kMHThreads / GG;                                                              \
         const int nb = (nchains + cpb - 1) / cpb;                                                     \
-        const size_t sm = Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0;  \
+        const size_t sm = (Model::kScratch ? (size_t)cpb * kScratchRows * p.Dp * sizeof(double) : 0) +  \
+                          (size_t)cpb * p.Dp * sizeof(double);   /* + a row per chain: the vector of a mat-vec */ \
         if (replay) k_hmc_chains<GG, EE, Model, true><<<nb, kMHThreads, sm, s>>>(p);                  \
         else k_hmc_chains<GG, EE, Model, false><<<nb, kMHThreads, sm, s>>>(p);                        \
         return 0;                                                                                     \

@@ -567,8 +567,8 @@ def hmc_production_chain(model, grad_logL, grad_V, flat_prior, start, start_logL
     half trajectories of evolve_trajectory, :793-835; energies and log_J of get_sample, :605-627) with the stated differences:
     the reflection normal is the analytic gradient of log_likelihood (the reference fits splines, :417-486); the reflection is
     p -= 2 (n.C.p / n.C.n) n, in the metric of the kinetic energy (:769-771 uses the Euclidean one); the trajectory point is
-    drawn in one pass by weighted reservoir sampling with weights exp(-H) over the points 1 .. 2L-1 (same distribution as the
-    multinomial draw of sample_trajectory, :837-844); the kinetic energy is re-evaluated only after the momentum can have
+    drawn in one pass by weighted reservoir sampling with weights exp(-H) over the points 1 .. 2L-1, summed in the linear domain
+    relative to a reference energy (same distribution as the multinomial draw of sample_trajectory, :837-844); the kinetic energy is re-evaluated only after the momentum can have
     changed it (first point, a bound reflection, a non-flat prior); a chain runs trajectories until steps >= nmcmc and one was
     accepted (the MH rule, sampler.py:347; the reference stops at the first accepted one, :375).
     trajectories: list of dict(L, p0, u, u_acc) as cpn_trace_hmc records them.  Returns dict(out, logL, logP, steps, accepted, evals)."""
@@ -583,7 +583,7 @@ def hmc_production_chain(model, grad_logL, grad_V, flat_prior, start, start_logL
     for tr in trajectories:
         L, p0, us, u_acc = int(tr["L"]), np.array(tr["p0"], dtype=np.float64), list(tr["u"]), float(tr["u_acc"])
         E0 = 0.5 * float(p0 @ (C @ p0)) - logP                            # hamiltonian(p0, q0), :621
-        logW = neg_inf
+        Wsum = Href = Hprev = wprev = 0.0                                 # running sum of the weights exp(Href - H)
         qc, logLc, logPc, Hc = x.copy(), neg_inf, neg_inf, 0.0
         point = 0
         for sign in (1.0, -1.0):
@@ -623,12 +623,20 @@ def hmc_production_chain(model, grad_logL, grad_V, flat_prior, start, start_logL
                 H = T - lp
                 if not (sign < 0 and i == L - 1):                         # trajectory[1:-1], :841
                     u = us[point - 1]
-                    lw = -H
-                    hi2, lo2 = max(logW, lw), min(logW, lw)
-                    logWn = hi2 + math.log1p(math.exp(lo2 - hi2)) if hi2 > neg_inf else neg_inf
-                    if lw > neg_inf and math.log(u) < lw - logWn:
-                        qc, logLc, logPc, Hc = q.copy(), ll, lp, H
-                    logW = logWn
+                    if H < np.inf:                                        # a point outside the box has weight 0
+                        if not Wsum > 0.0:
+                            Href, wgt = H, 1.0
+                        elif H == Hprev:
+                            wgt = wprev
+                        else:
+                            if H < Href - 50.0:                           # the reference energy follows H downwards
+                                Wsum *= math.exp(H - Href)
+                                Href = H
+                            wgt = math.exp(Href - H)
+                        Hprev, wprev = H, wgt
+                        Wsum += wgt
+                        if u * Wsum < wgt:                                # keep this point with probability w / (sum so far)
+                            qc, logLc, logPc, Hc = q.copy(), ll, lp, H
         log_J = min(0.0, E0 - Hc)                                         # :626
         acc = (log_J > math.log(u_acc)) and (logLc > logLmin)             # sampler.py:380-382
         if acc:
