@@ -91,26 +91,29 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_hmc_chains(con
     // broadcast load per column; the shuffle form - a select over the lane's slots and a 64-bit shuffle per column - was the
     // bulk of a reflecting step).  Same multiply-adds in the same order in both forms.
     double* hsm = smem + (Model::kScratch ? (kMHThreads / G) * kScratchRows * p.Dp : 0) + ((int)threadIdx.x / G) * p.Dp;
+    // (this lane's column of the covariance as a pointer held in a register and advanced row by row: with the address rebuilt
+    // from the launch parameters for every element the mat-vec was half of all instructions the kernel executed)
+    const double* cov_lane = p.cov + g.lane;
+    asm volatile("" : "+l"(cov_lane));
+    bool has[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) has[e] = g.lane + e * G < D;
     auto matvec = [&](const double (&pp)[E], double (&w)[E]) {
 #pragma unroll
         for (int e = 0; e < E; ++e) w[e] = 0.0;
         if (!REPLAY && G > 1) {
             __syncwarp();
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int d = g.lane + e * G;
-                if (d < D) hsm[d] = pp[e];
-            }
+            for (int e = 0; e < E; ++e)
+                if (has[e]) hsm[g.lane + e * G] = pp[e];
             __syncwarp();
         }
+        const double* crow = cov_lane;
         for (int k = 0; k < D; ++k) {
             const double pk = (!REPLAY && G > 1) ? hsm[k] : coord<G, E>(g, pp, k);
-            const double* crow = p.cov + (size_t)k * D;
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int d = g.lane + e * G;
-                w[e] = fma((d < D) ? __ldg(crow + d) : 0.0, pk, w[e]);
-            }
+            for (int e = 0; e < E; ++e) w[e] = fma(has[e] ? __ldg(crow + e * G) : 0.0, pk, w[e]);
+            crow += D;
         }
     };
     auto kinetic = [&](const double (&pp)[E]) -> double {
