@@ -169,14 +169,12 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_hmc_chains(con
                 z[e] = (d < D && sc > 0.0) ? g0 / sc : 0.0;                            // z_i |lambda_i|^-1/2
                 p0[e] = 0.0;
             }
+            const double* vrow = p.eig_vec + g.lane;
             for (int i = 0; i < D; ++i) {
                 const double zi = coord<G, E>(g, z, i);
-                const double* vrow = p.eig_vec + (size_t)i * p.Dp;
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int d = g.lane + e * G;
-                    p0[e] = fma(zi, (d < D) ? __ldg(vrow + d) : 0.0, p0[e]);
-                }
+                for (int e = 0; e < E; ++e) p0[e] = fma(zi, has[e] ? __ldg(vrow + e * G) : 0.0, p0[e]);
+                vrow += p.Dp;
             }
         }
         bool rec = false;             // this trajectory of this chain is recorded

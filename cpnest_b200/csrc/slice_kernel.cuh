@@ -157,14 +157,15 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
                         const int d = g.lane + e * G;
                         acc[e] = (d < D) ? __ldg(p.mean + d) : 0.0;
                     }
+                    // (this lane's column of the eigenvector table as a running pointer: rebuilt from the launch parameters
+                    // per element the address arithmetic outweighed the multiply-adds, as in the HMC kernel's mat-vec)
+                    const double* vrow = p.eig_vec + g.lane;
+                    const double* esc = p.eig_scale;
                     for (int i = 0; i < D; ++i) {
-                        const double zi = coord<G, E>(g, z, i) * __ldg(p.eig_scale + i);
-                        const double* vrow = p.eig_vec + (size_t)i * p.Dp;
+                        const double zi = coord<G, E>(g, z, i) * __ldg(esc + i);
 #pragma unroll
-                        for (int e = 0; e < E; ++e) {
-                            const int d = g.lane + e * G;
-                            acc[e] = fma(zi, (d < D) ? __ldg(vrow + d) : 0.0, acc[e]);
-                        }
+                        for (int e = 0; e < E; ++e) acc[e] = fma(zi, (g.lane + e * G < D) ? __ldg(vrow + e * G) : 0.0, acc[e]);
+                        vrow += p.Dp;
                     }
 #pragma unroll
                     for (int e = 0; e < E; ++e) { dir[e] = mu * acc[e]; trace_v[e] = acc[e]; }
