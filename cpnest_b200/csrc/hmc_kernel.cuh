@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_hmc_chains(con
 #pragma unroll
         for (int e = 0; e < E; ++e) qc[e] = x[e];
         int point = 0;                                                  // index in the reference's trajectory list
+        Philox4 ru;
+        ru.v[0] = ru.v[1] = ru.v[2] = ru.v[3] = 0u;
         for (int dirn = 0; dirn < 2; ++dirn) {
             double pm[E], q[E], gv[E];
 #pragma unroll
@@ -313,7 +315,9 @@ __global__ void __launch_bounds__(kMHThreads, (E <= 4) ? 4 : 1) k_hmc_chains(con
                     }
                 } else if (!last) {
                     // weighted reservoir: keep this point with probability w / (sum of weights so far)
-                    const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 0x40000000u | (uint32_t)(point >> 2), p.seed_lo, p.seed_hi);
+                    // (a Philox block serves four points: it is drawn when the first of them is visited)
+                    if (point == 1 || (point & 3) == 0)
+                        ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)attempt, 0x40000000u | (uint32_t)(point >> 2), p.seed_lo, p.seed_hi);
                     const int k = point & 3;
                     const uint32_t wv = (k & 2) ? ((k & 1) ? ru.v[3] : ru.v[2]) : ((k & 1) ? ru.v[1] : ru.v[0]);
                     const double uu = u32_to_unit_open(wv);

@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
 
         // ---- shrinkage (sampler.py:529-551) ---------------------------------------------------------------
         bool searching = active;
+        Philox4 ru;
+        ru.v[0] = ru.v[1] = ru.v[2] = ru.v[3] = 0u;
         for (int sl = 0; sl < maxmcmc; ++sl) {
             if (!__any_sync(FULL, searching)) break;
             double Xp;
@@ -269,7 +271,8 @@ __global__ void __launch_bounds__(kMHThreads) k_slice_chains(const SliceParams p
                 Xp = searching ? tp[0] : 0.0;                        // the value np.random.uniform(L, R) returned
                 if (searching) ++tp;
             } else {
-                const Philox4 ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 0x40000000u | (uint32_t)(sl >> 2), p.seed_lo, p.seed_hi);
+                // (a Philox block serves four candidates: it is drawn when the first of them is asked for)
+                if ((sl & 3) == 0) ru = philox4x32_10(cid_lo, cid_hi, (uint32_t)s, 0x40000000u | (uint32_t)(sl >> 2), p.seed_lo, p.seed_hi);
                 const uint32_t w = (sl & 2) ? ((sl & 1) ? ru.v[3] : ru.v[2]) : ((sl & 1) ? ru.v[1] : ru.v[0]);
                 Xp = fma(R - L, u32_to_unit_open(w), L);
                 if (rec && searching) {
