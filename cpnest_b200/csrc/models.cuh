@@ -204,9 +204,8 @@ struct GaussCorr : FlatPrior {
         return D <= 64 ? tile_base((D + 7) >> 3, (D + 3) >> 2) * 32 + 8 * kXs + 32 : 0;
     }
     // called once by every thread of the block before the first step: fills the tile table and the thread's constants
-    // bp = {offset of its B fragments of the short output block, of the long one, of its A fragments (doubles from the start
-    // of the dynamic shared array), input blocks of the short | long output block << 8 | role << 16}; bo = offset of the
-    // point table
+    // bp = {shared-window byte address of its B fragments of the short output block, of the long one, of its A fragments, input
+    // blocks of the short | long output block << 8}; bo = address of the point table
     static __device__ __forceinline__ void block_prepare(ModelCtx& m, int buf_off) {
         extern __shared__ double cpn_dyn_smem[];
         const int D = m.D, nrb = (D + 7) >> 3, nkb = (D + 3) >> 2;
@@ -222,64 +221,78 @@ struct GaussCorr : FlatPrior {
             t0 += nj;
         }
         for (int q = (int)threadIdx.x; q < 8 * kXs + 32; q += (int)blockDim.x) tiles[ntile * 32 + q] = 0.0;
-        // (the role of a warp rotates with the block index: a warp stays on one SM sub-partition, and so do its tensor-core
-        // products; the four roles carry 16, 16, 16 and 8 of them at D = 50, the four blocks resident on an SM then load
-        // every sub-partition alike)
-        const int lane = (int)threadIdx.x & 31, w = (((int)threadIdx.x >> 5) + (int)blockIdx.x) & 3;
+        const int lane = (int)threadIdx.x & 31, w = (int)threadIdx.x >> 5;
         const int iA = w, iB = nrb - 1 - w;               // short and long output block of this warp (iA > iB: none)
         int nA = 0, nB = 0;
         if (iA <= iB) {
             nA = (iA == iB) ? 0 : ntile_row(iA, nkb);
             nB = ntile_row(iB, nkb);
         }
-        m.bp[0] = buf_off + tile_base(iA < nrb ? iA : 0, nkb) * 32 + lane;
-        m.bp[1] = buf_off + tile_base(iB >= 0 ? iB : 0, nkb) * 32 + lane;
-        m.bp[2] = buf_off + ntile * 32 + (lane >> 2) * kXs + (lane & 3);
-        m.bp[3] = nA | (nB << 8) | (w << 16);
-        m.bo = buf_off + ntile * 32;
+        // (as shared-window byte addresses: log_likelihood_block reads and writes through them)
+        const int sb = (int)(uint32_t)__cvta_generic_to_shared(cpn_dyn_smem);
+        m.bp[0] = sb + 8 * (buf_off + tile_base(iA < nrb ? iA : 0, nkb) * 32 + lane);
+        m.bp[1] = sb + 8 * (buf_off + tile_base(iB >= 0 ? iB : 0, nkb) * 32 + lane);
+        m.bp[2] = sb + 8 * (buf_off + ntile * 32 + (lane >> 2) * kXs + (lane & 3));
+        m.bp[3] = nA | (nB << 8);
+        m.bo = sb + 8 * (buf_off + ntile * 32);
         __syncthreads();
     }
+    // shared-memory accesses of the block form by 32-bit shared-window address (a pointer derived from the dynamic array is
+    // generic: every loop rebuilt the window base from SR_CgaCtaId, a quarter of the functor's instructions)
+    static __device__ __forceinline__ double lds64(uint32_t a) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ double lds64_256(uint32_t a) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1+256];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ double lds64_32(uint32_t a) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1+32];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
     template <int G, int E>
     static __device__ __forceinline__ double log_likelihood_block(const Group<G>& g, const double (&x)[E], const ModelCtx& m) {
         static_assert(G == 16, "eight chains per 128-thread block");
-        extern __shared__ double cpn_dyn_smem[];
         const int D = m.D;
-        const int lane = (int)threadIdx.x & 31, w = m.bp[3] >> 16, chain = (int)threadIdx.x >> 4;
-        double* X = cpn_dyn_smem + m.bo;
-        double* part = X + 8 * kXs;                       // [4 warps][8 chains]
-        const double* At = cpn_dyn_smem + m.bp[0];
-        const double* Bt = cpn_dyn_smem + m.bp[1];
-        const double* xb = cpn_dyn_smem + m.bp[2];
-        const int nA = m.bp[3] & 0xff, nB = (m.bp[3] >> 8) & 0xff;
+        const int lane = (int)threadIdx.x & 31, w = (int)threadIdx.x >> 5, chain = (int)threadIdx.x >> 4;
+        const uint32_t aX = (uint32_t)m.bo, aP = aX + 8u * 8u * kXs;               // point table, partial sums [4 warps][8 chains]
+        uint32_t aA = (uint32_t)m.bp[0], aB = (uint32_t)m.bp[1], ax = (uint32_t)m.bp[2];
+        const int nA = m.bp[3] & 0xff, nB = m.bp[3] >> 8;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int d = g.lane + e * G;
-            if (d < D) X[chain * kXs + d] = x[e];
+            if (d < D) sts64(aX + 8u * (uint32_t)(chain * kXs + d), x[e]);
         }
         __syncthreads();
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
         int j = 0;
-#pragma unroll 2
         for (; j < nA; j += 2) {                          // both output blocks, which share the A fragments
-            const double x0 = xb[4 * j], x1 = xb[4 * j + 4];
-            dmma_f64(b0, b1, x0, Bt[32 * j]);
-            dmma_f64(a0, a1, x0, At[32 * j]);
-            dmma_f64(b2, b3, x1, Bt[32 * j + 32]);
-            dmma_f64(a0, a1, x1, At[32 * j + 32]);
+            const double x0 = lds64(ax), x1 = lds64_32(ax);
+            dmma_f64(b0, b1, x0, lds64(aB));
+            dmma_f64(a0, a1, x0, lds64(aA));
+            dmma_f64(b2, b3, x1, lds64_256(aB));
+            dmma_f64(a0, a1, x1, lds64_256(aA));
+            ax += 64u; aA += 512u; aB += 512u;
         }
-#pragma unroll 2
         for (; j < nB; j += 2) {                          // the long output block alone (even and odd input blocks apart)
-            dmma_f64(b0, b1, xb[4 * j], Bt[32 * j]);
-            dmma_f64(b2, b3, xb[4 * j + 4], Bt[32 * j + 32]);
+            dmma_f64(b0, b1, lds64(ax), lds64(aB));
+            dmma_f64(b2, b3, lds64_32(ax), lds64_256(aB));
+            ax += 64u; aB += 512u;
         }
         b0 += b2; b1 += b3;
         double q = fma(a0, a0, a1 * a1) + fma(b0, b0, b1 * b1);
         // the chain lives in lane >> 2: sum over its four lanes
         q += __shfl_xor_sync(FULL, q, 1);
         q += __shfl_xor_sync(FULL, q, 2);
-        if ((lane & 3) == 0) part[w * 8 + (lane >> 2)] = q;
+        if ((lane & 3) == 0) sts64(aP + 8u * (uint32_t)(w * 8 + (lane >> 2)), q);
         __syncthreads();
-        const double s = (part[chain] + part[8 + chain]) + (part[16 + chain] + part[24 + chain]);
+        const uint32_t ac = aP + 8u * (uint32_t)chain;
+        const double s = (lds64(ac) + lds64(ac + 64u)) + (lds64(ac + 128u) + lds64(ac + 192u));
         return -0.5 * s - m.blob[0] - m.D * CPN_HALF_LOG_2PI;
     }
     // grad = -Linv^T (Linv x): the second product walks the rows of Linv^T = columns of Linv, again consecutive in the
