@@ -316,3 +316,74 @@ def test_recorded_reference_runs_are_sane():
     # p(sigma) ~ 1/sigma: E[sigma] = 0.95 / ln 20, Var(mean) = E[sigma^2] = (1 - 0.05^2) / (2 ln 20)
     assert abs(ms["posterior_mean"]["sigma"] - 0.95 / math.log(20.0)) < 0.02
     assert abs(ms["posterior_var"]["mean"] - (1 - 0.0025) / (2 * math.log(20.0))) < 0.02
+
+
+def test_production_draw_excludes_the_chains_own_slot():
+    """oracle.production_draw with self_slot (mh_kernel.cuh DrawFeed::refill): the ensemble members of a step are drawn from the
+    slots other than the one the chain started from (the reference pops a chain's point from the pool, sampler.py:325); distinct
+    where the reference samples without replacement; the mapping from the compact index is monotone, so without a self slot the
+    same Philox words give the un-shifted indices."""
+    n, D, seed = 37, 5, 99
+    scale = np.ones(D)
+    for kind in (O.WALK, O.STRETCH, O.DE, O.EIGEN):
+        seen = set()
+        for step in range(400):
+            self_slot = step % n
+            a = O.production_draw(seed, 12, step, kind, n, D, scale, self_slot=self_slot)
+            b = O.production_draw(seed, 12, step, kind, n - 1, D, scale)           # the same words over n - 1 slots, no exclusion
+            used = {O.WALK: 3, O.STRETCH: 1, O.DE: 2, O.EIGEN: 1}[kind]
+            idx = [int(v) for v in a[1:1 + used]]
+            if kind == O.EIGEN:
+                assert idx == [int(b[1])] and 0 <= idx[0] < D
+                continue
+            assert all(0 <= i < n and i != self_slot for i in idx), (kind, step, idx, self_slot)
+            assert len(set(idx)) == used
+            assert idx == [int(v) + (int(v) >= self_slot) for v in b[1:1 + used]]
+            assert a[4:] == b[4:]                                                    # scalars and threshold do not depend on it
+            seen.update(idx)
+        if kind != O.EIGEN:
+            assert len(seen) == n                                                    # every slot is reachable
+
+
+def test_hmc_production_chain_restatement_is_self_consistent():
+    """oracle.hmc_production_chain (the restatement the production HMC kernel is stepped against on the GPU): under a flat prior
+    the metric reflection conserves the kinetic energy, so log_J = 0 and a trajectory is accepted exactly when the drawn point lies
+    above the threshold; the counts follow the rule of sampler.py:347; every likelihood call is counted."""
+    m = O.builtin_model("gaussian2d")
+    rs = np.random.RandomState(3)
+    C = np.array([[1.3, 0.4], [0.4, 0.7]])
+    start = np.array([0.3, -0.2])
+    logLmin = m.log_likelihood(np.array([1.2, 0.0]))                                  # the disc |x| < 1.2
+    grad_logL = lambda q: -np.asarray(q)
+    grad_V = lambda q: np.zeros(2)
+    trajs = []
+    for a in range(9):
+        L = 20 + a
+        trajs.append(dict(L=L, p0=np.linalg.solve(np.linalg.cholesky(C).T, rs.normal(size=2)), u=rs.uniform(size=2 * L - 1), u_acc=0.999999))
+    r = O.hmc_production_chain(m, grad_logL, grad_V, True, start, m.log_likelihood(start), 0.0, C, 0.15, logLmin, trajs, nmcmc=4, max_traj=9)
+    assert r["steps"] >= 4 and r["accepted"] >= 1 and r["steps"] <= 9
+    assert r["evals"] == sum(2 * t["L"] for t in trajs[:r["steps"]])
+    assert r["reflections"] > 0                                                       # dt * L spans the disc several times
+    assert r["logL"] > logLmin and abs(r["logL"] - m.log_likelihood(r["out"])) < 1e-12
+    # energy conservation, seen from outside: with u_acc ~ 1 a trajectory is rejected only through the likelihood constraint,
+    # i.e. accepted + (draws that fell outside the disc) = steps; rerun with the threshold removed: every trajectory is accepted
+    r2 = O.hmc_production_chain(m, grad_logL, grad_V, True, start, m.log_likelihood(start), 0.0, C, 0.15, -np.inf, trajs, nmcmc=9, max_traj=9)
+    assert r2["accepted"] == r2["steps"] == 9 and r2["reflections"] == 0
+
+
+def test_production_slice_draw_follows_the_philox_blocks():
+    """oracle.production_slice_draw / production_slice_uniform (slice_kernel.cuh): which Philox block and word feeds which draw."""
+    seed, cid, s, n, D = 7, 3, 11, 50, 4
+    key = (seed, 0)
+    r0 = O.philox4x32_10((cid, 0, s, 0), key)
+    uL, (i0, i1), eexp, uJ = O.production_slice_draw(seed, cid, s, O.SLICE_DIFF, n, D)
+    assert uL == O.u32_to_unit_open(r0[0]) and uJ == O.u32_to_unit_open(r0[1])
+    assert eexp == -math.log(O.u32_to_unit_open(r0[2])) and i0 == O.u32_to_index(r0[3], n)
+    assert i1 != i0 and 0 <= i1 < n
+    _, z, _, _ = O.production_slice_draw(seed, cid, s, O.SLICE_GAUSS, n, D)
+    assert z.shape == (D,) and z[2] == O.box_muller_f32(*O.philox4x32_10((cid, 0, s, 0x80000000 | 2), key)[:2])[0]
+    mean, scale, V = np.arange(D) * 0.1, np.array([0.5, 1.0, 2.0, 0.0]), np.eye(D)
+    _, v, _, _ = O.production_slice_draw(seed, cid, s, O.SLICE_CORR, n, D, mean, scale, V)
+    np.testing.assert_allclose(v, mean + z * scale, rtol=1e-15)
+    for k in (0, 3, 4, 9):
+        assert O.production_slice_uniform(seed, cid, s, k) == O.u32_to_unit_open(O.philox4x32_10((cid, 0, s, 0x40000000 | (k >> 2)), key)[k & 3])
